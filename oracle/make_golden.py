@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* by running the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python oracle/make_golden.py [case ...]
+
+Each fixture is an .npz holding the inputs (scenario parameters, the injected sample
+stream) and what the reference produced for them (node positions, costs, parent indices,
+path, every `check_collision` verdict in call order).  The reference classes are loaded by
+`oracle/ref_loader.py` (definition block only, stub matplotlib) and driven through their own
+`planning()`; only the sampler methods are replaced by a function that pops the recorded
+stream, and `check_collision` is wrapped to log its verdicts.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+C1 = dict(start=[0, 0], goal=[6.0, 10.0],
+          obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2),
+                         (8, 10, 1)],
+          rand_area=[-2, 15], expand_dis=1.0, path_resolution=0.1, goal_sample_rate=5,
+          max_iter=500, play_area=[0, 10, 0, 14], robot_radius=0.6,
+          connect_circle_dist=50.0)  # rrt_04:1498-1546
+
+
+def random_circles(seed, n, lo=-2.0, hi=15.0, rmin=0.1, rmax=0.4, keep_clear=((0.0, 0.0), (13.0, 13.0))):
+    """C2-style obstacle set: seeded, rejected if within r+0.5 of start/goal."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        x, y = rng.uniform(lo, hi, 2)
+        r = rng.uniform(rmin, rmax)
+        if all(np.hypot(x - cx, y - cy) > r + 0.5 for cx, cy in keep_clear):
+            out.append((float(x), float(y), float(r)))
+    return out
+
+
+def tree_arrays(node_list):
+    idx = {id(n): i for i, n in enumerate(node_list)}
+    par = []
+    orphans = 0
+    for n in node_list:
+        if n.parent is None:
+            par.append(-1)
+        elif isinstance(n.parent, int):
+            par.append(n.parent)
+        else:
+            j = idx.get(id(n.parent), -2)
+            orphans += (j == -2)
+            par.append(j)
+    assert orphans == 0, "reference tree holds a parent object that left node_list"
+    x = np.array([float(n.x) for n in node_list])
+    y = np.array([float(n.y) for n in node_list])
+    c = np.array([float(n.cost) for n in node_list]) if hasattr(node_list[0], "cost") else None
+    return x, y, c, np.array(par, dtype=np.int64)
+
+
+def run_rrt04(name, params, sobol_sampler, search_until_max_iter, seed, stream=None):
+    """Drive rrt_04's RRT (RRT*).  If `stream` is None the reference samples by itself
+    (random.seed(seed) + its Sobol code) and the stream it produced is recorded."""
+    ns = ref_loader.load("rrt_04")
+    R = ns["RRT"]
+    ref_loader.reset_sobol(ns)
+    random.seed(seed)
+    rrt = R(sobol_sampler=sobol_sampler, search_until_max_iter=search_until_max_iter, **params)
+    recorded = []
+    verdicts = []
+
+    if stream is None:
+        inner = rrt.get_random_node_sobol if sobol_sampler else rrt.get_random_node
+
+        def sampler():
+            n = inner()
+            recorded.append((float(n.x), float(n.y)))
+            return n
+    else:
+        it = iter(stream)
+
+        def sampler():
+            x, y = next(it)
+            recorded.append((float(x), float(y)))
+            return rrt.Node(float(x), float(y))
+    rrt.get_random_node_sobol = sampler
+    rrt.get_random_node = sampler
+
+    orig_cc = R.check_collision
+
+    def logged_cc(node, obstacle_list, robot_radius):
+        ok = orig_cc(node, obstacle_list, robot_radius)
+        verdicts.append(bool(ok))
+        return ok
+    rrt.check_collision = logged_cc  # instance attribute shadows the staticmethod
+
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        path = rrt.planning(animation=False)
+    wall = time.perf_counter() - t0
+    x, y, c, par = tree_arrays(rrt.node_list)
+    meta = dict(params)
+    meta.update(sobol_sampler=bool(sobol_sampler), search_until_max_iter=bool(search_until_max_iter),
+                seed=seed, reference_wall_s=wall, iters=len(recorded), kind="rrt_04",
+                sobol_inter=int(rrt.sobol_inter_))
+    out = dict(meta=json.dumps(meta), stream=np.array(recorded, dtype=np.float64),
+               x=x, y=y, cost=c, parent=par,
+               verdicts=np.array(verdicts, dtype=np.uint8),
+               path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 2)))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: {len(x)} nodes, {len(recorded)} iterations, path "
+          f"{0 if path is None else len(path)} waypoints, {len(verdicts)} verdicts, "
+          f"{wall:.2f} s ({len(recorded) / wall:.1f} tree-iter/s)")
+
+
+def c2_params(seed, n_obs, max_iter):
+    return dict(start=[0.0, 0.0], goal=[13.0, 13.0], obstacle_list=random_circles(seed, n_obs),
+                rand_area=[-2, 15], expand_dis=1.0, path_resolution=0.1, goal_sample_rate=5,
+                max_iter=max_iter, play_area=None, robot_radius=0.0, connect_circle_dist=50.0)
+
+
+CASES = {
+    # C1: the built-in scenario, the reference samples by itself (Sobol + random.seed(0))
+    "rrt04_c1_sobol_500": lambda: run_rrt04("rrt04_c1_sobol_500", C1, True, True, 0),
+    "rrt04_c1_sobol_2000": lambda: run_rrt04("rrt04_c1_sobol_2000", dict(C1, max_iter=2000), True, True, 0),
+    "rrt04_c1_uniform_500": lambda: run_rrt04("rrt04_c1_uniform_500", C1, False, True, 3),
+    # script default: stop at the first goal connection
+    "rrt04_c1_sobol_early": lambda: run_rrt04("rrt04_c1_sobol_early", C1, True, False, 1),
+    "rrt04_c1_uniform_early": lambda: run_rrt04("rrt04_c1_uniform_early", C1, False, False, 2),
+    # C2 shape (random circles, no play area, robot_radius 0)
+    "rrt04_c2_o64_600": lambda: run_rrt04("rrt04_c2_o64_600", c2_params(1234, 64, 600), True, True, 5),
+    "rrt04_c2_o256_800": lambda: run_rrt04("rrt04_c2_o256_800", c2_params(1235, 256, 800), True, True, 6),
+    "rrt04_c2_o256_2000": lambda: run_rrt04("rrt04_c2_o256_2000", c2_params(1236, 256, 2000), True, True, 7),
+}
+
+
+if __name__ == "__main__":
+    if not ref_loader.available():
+        sys.exit("reference not present at " + ref_loader.REF_DIR)
+    os.makedirs(GOLDEN, exist_ok=True)
+    want = sys.argv[1:] or list(CASES)
+    for name in want:
+        if name.endswith("*"):
+            for k in CASES:
+                if k.startswith(name[:-1]):
+                    CASES[k]()
+        else:
+            CASES[name]()

@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the plain-C oracle (oracle/rrtk_oracle.c).
+
+`build()` compiles oracle/_build/liborc.so with gcc (see oracle/Makefile); building the checker
+is not using it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "liborc.so")
+_lib = None
+
+
+class Params(C.Structure):
+    _fields_ = [("sx", C.c_double), ("sy", C.c_double), ("gx", C.c_double), ("gy", C.c_double),
+                ("expand_dis", C.c_double), ("res", C.c_double), ("robot_radius", C.c_double),
+                ("connect_circle_dist", C.c_double), ("play", C.c_double * 4),
+                ("has_play", C.c_int32), ("max_iter", C.c_int32),
+                ("search_until_max_iter", C.c_int32), ("n_obs", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "rrtk_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_hypot.restype = C.c_double
+        _lib.orc_hypot.argtypes = [C.c_double, C.c_double]
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def make_params(start, goal, obstacle_list, expand_dis, path_resolution, max_iter, play_area,
+                robot_radius, connect_circle_dist=50.0, search_until_max_iter=True):
+    p = Params()
+    p.sx, p.sy, p.gx, p.gy = float(start[0]), float(start[1]), float(goal[0]), float(goal[1])
+    p.expand_dis, p.res = float(expand_dis), float(path_resolution)
+    p.robot_radius, p.connect_circle_dist = float(robot_radius), float(connect_circle_dist)
+    p.has_play = 0 if play_area is None else 1
+    if play_area is not None:
+        for i in range(4):
+            p.play[i] = float(play_area[i])
+    p.max_iter = int(max_iter)
+    p.search_until_max_iter = int(bool(search_until_max_iter))
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    p.n_obs = obs.shape[0]
+    return p, obs
+
+
+def hypot(a: float, b: float) -> float:
+    return lib().orc_hypot(a, b)
+
+
+def sobol_fill(dim: int, first: int, count: int) -> np.ndarray:
+    out = np.empty((count, dim), dtype=np.float64)
+    rc = lib().orc_sobol_fill(C.c_int(dim), C.c_int64(first), C.c_int64(count), _p(out, C.c_double))
+    if rc:
+        raise ValueError("orc_sobol_fill: bad dimension")
+    return out
+
+
+def sobol_table(dim: int) -> np.ndarray:
+    v = np.empty((dim, 30), dtype=np.uint32)
+    if lib().orc_sobol_table(C.c_int(dim), _p(v, C.c_uint32)):
+        raise ValueError("orc_sobol_table: bad dimension")
+    return v
+
+
+def rrtstar_run(params: Params, obs: np.ndarray, stream: np.ndarray, want_trace=True,
+                verdict_cap=0):
+    """Returns dict(x, y, cost, parent, n, iters_done, goal_index, trace, verdicts)."""
+    cap = params.max_iter + 1
+    stream = np.ascontiguousarray(stream, dtype=np.float64).reshape(-1, 2)
+    if stream.shape[0] < params.max_iter:
+        pad = np.zeros((params.max_iter - stream.shape[0], 2))
+        stream = np.ascontiguousarray(np.vstack([stream, pad]))
+    x = np.zeros(cap); y = np.zeros(cap); cost = np.zeros(cap)
+    parent = np.full(cap, -1, dtype=np.int32)
+    n = C.c_int32(); it = C.c_int32(); gi = C.c_int32()
+    trace = np.zeros((params.max_iter, 8), dtype=np.int32) if want_trace else None
+    verd = np.zeros(max(verdict_cap, 1), dtype=np.uint8)
+    nv = C.c_int64()
+    lib().orc_rrtstar_run(C.byref(params), _p(obs, C.c_double), _p(stream, C.c_double),
+                          _p(x, C.c_double), _p(y, C.c_double), _p(cost, C.c_double),
+                          _p(parent, C.c_int32), C.byref(n), C.byref(it), C.byref(gi),
+                          _p(trace, C.c_int32) if want_trace else None,
+                          _p(verd, C.c_uint8) if verdict_cap else None, C.c_int64(verdict_cap),
+                          C.byref(nv))
+    k = n.value
+    return dict(x=x[:k], y=y[:k], cost=cost[:k], parent=parent[:k], n=k, iters_done=it.value,
+                goal_index=gi.value, trace=None if trace is None else trace[:it.value],
+                verdicts=verd[:min(nv.value, verdict_cap)], n_verdicts=nv.value)
+
+
+def rrt_run(params: Params, obs: np.ndarray, stream: np.ndarray):
+    cap = params.max_iter + 1
+    stream = np.ascontiguousarray(stream, dtype=np.float64).reshape(-1, 2)
+    if stream.shape[0] < params.max_iter:
+        stream = np.ascontiguousarray(np.vstack([stream, np.zeros((params.max_iter - stream.shape[0], 2))]))
+    x = np.zeros(cap); y = np.zeros(cap)
+    parent = np.full(cap, -1, dtype=np.int32)
+    n = C.c_int32(); it = C.c_int32(); gi = C.c_int32()
+    lib().orc_rrt_run(C.byref(params), _p(obs, C.c_double), _p(stream, C.c_double),
+                      _p(x, C.c_double), _p(y, C.c_double), _p(parent, C.c_int32),
+                      C.byref(n), C.byref(it), C.byref(gi))
+    k = n.value
+    return dict(x=x[:k], y=y[:k], parent=parent[:k], n=k, iters_done=it.value, goal_index=gi.value)
+
+
+def final_course(res: dict, goal) -> list | None:
+    """generate_final_course (rrt_04:1117-1125) from an oracle result."""
+    gi = res["goal_index"]
+    if gi < 0:
+        return None
+    path = [[float(goal[0]), float(goal[1])]]
+    i = gi
+    while res["parent"][i] >= 0:
+        path.append([float(res["x"][i]), float(res["y"][i])])
+        i = int(res["parent"][i])
+    path.append([float(res["x"][i]), float(res["y"][i])])
+    return path

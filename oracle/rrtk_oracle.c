@@ -1,0 +1,410 @@
+/* TEST INFRASTRUCTURE ONLY -- plain-C (FP64) restatement of the reference hot path.
+ *
+ * CPU oracle for the RRT-family inner loop of gouldberg/robotics-path-planning.  It performs
+ * the same IEEE-754 double operations, in the same order, as the reference's Python code:
+ *   - `math.hypot`  -> orc_hypot(): CPython's correctly-rounded vector_norm algorithm
+ *                      (glibc hypot() differs from CPython's in ~0.6 % of inputs),
+ *   - `x ** 2`      -> pow(x, 2.0)  (CPython float_pow calls libm pow; it is NOT always x*x),
+ *   - `math.cos/sin/atan2/log/sqrt/floor` -> the same glibc functions CPython calls.
+ * It is pinned bit-for-bit against tests/golden/ (outputs of the unmodified reference, made
+ * by oracle/make_golden.py); see tests/test_oracle_golden.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product never does.
+ *
+ * Citations are alias:line into /root/reference/src_path_planning.
+ * Build: oracle/Makefile (gcc -O2 -ffp-contract=off, no -ffast-math, no -march flags).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------ */
+/* math.hypot of CPython >= 3.10 (Modules/mathmodule.c vector_norm, n = 2)               */
+/* ------------------------------------------------------------------------------------ */
+typedef struct { double hi, lo; } dl_t;
+
+static inline dl_t dl_fast_sum(double a, double b) {
+    double x = a + b;
+    double y = (a - x) + b;
+    dl_t r = {x, y};
+    return r;
+}
+
+static inline dl_t dl_mul(double x, double y) {
+    double z = x * y;
+    double zz = fma(x, y, -z); /* exact low word; software fma when the ISA has none */
+    dl_t r = {z, zz};
+    return r;
+}
+
+ORC_EXPORT double orc_hypot(double a, double b) {
+    double v[2];
+    v[0] = fabs(a);
+    v[1] = fabs(b);
+    double max = v[0] > v[1] ? v[0] : v[1];
+    if (isinf(v[0]) || isinf(v[1])) return INFINITY;
+    if (isnan(a) || isnan(b)) return NAN;
+    if (max == 0.0) return max;
+    int max_e;
+    frexp(max, &max_e);
+    if (max_e < -1023) return DBL_MIN * orc_hypot(v[0] / DBL_MIN, v[1] / DBL_MIN);
+    double scale = ldexp(1.0, -max_e);
+    double csum = 1.0, frac1 = 0.0, frac2 = 0.0, x, h;
+    dl_t pr, sm;
+    for (int i = 0; i < 2; i++) {
+        x = v[i] * scale;
+        pr = dl_mul(x, x);
+        sm = dl_fast_sum(csum, pr.hi);
+        csum = sm.hi;
+        frac1 += pr.lo;
+        frac2 += sm.lo;
+    }
+    h = sqrt(csum - 1.0 + (frac1 + frac2));
+    pr = dl_mul(-h, h);
+    sm = dl_fast_sum(csum, pr.hi);
+    csum = sm.hi;
+    frac1 += pr.lo;
+    frac2 += sm.lo;
+    x = csum - 1.0 + (frac1 + frac2);
+    h += x / (2.0 * h);
+    return h / scale;
+}
+
+static inline double sq(double x) { return pow(x, 2.0); } /* Python `x ** 2` */
+
+/* ------------------------------------------------------------------------------------ */
+/* Sobol (rrt_04:230-503): closed form, Gray-code order                                  */
+/* ------------------------------------------------------------------------------------ */
+#define SOBOL_BITS 30
+#define SOBOL_DIM_MAX 40
+static const int k_poly[SOBOL_DIM_MAX] = {
+    1, 3, 7, 11, 13, 19, 25, 37, 59, 47, 61, 55, 41, 67, 97, 91, 109, 103, 115, 131,
+    193, 137, 145, 143, 241, 157, 185, 167, 229, 171, 213, 191, 253, 203, 211, 239,
+    247, 285, 369, 299};
+/* initial m_j per column: (first dimension index, count, values) -- the data at rrt_04:320-356 */
+static const int k_c1[] = {1, 3, 1, 3, 1, 3, 3, 1, 3, 1, 3, 1, 3, 1, 1, 3, 1, 3, 1, 3, 1, 3, 3, 1, 3, 1, 3, 1, 3, 1, 1, 3, 1, 3, 1, 3, 1, 3};
+static const int k_c2[] = {7, 5, 1, 3, 3, 7, 5, 5, 7, 7, 1, 3, 3, 7, 5, 1, 1, 5, 3, 3, 1, 7, 5, 1, 3, 3, 7, 5, 1, 1, 5, 7, 7, 5, 1, 3, 3};
+static const int k_c3[] = {1, 7, 9, 13, 11, 1, 3, 7, 9, 5, 13, 13, 11, 3, 15, 5, 3, 15, 7, 9, 13, 9, 1, 11, 7, 5, 15, 1, 15, 11, 5, 3, 1, 7, 9};
+static const int k_c4[] = {9, 3, 27, 15, 29, 21, 23, 19, 11, 25, 7, 13, 17, 1, 25, 29, 3, 31, 11, 5, 23, 27, 19, 21, 5, 1, 17, 13, 7, 15, 9, 31, 9};
+static const int k_c5[] = {37, 33, 7, 5, 11, 39, 63, 27, 17, 15, 23, 29, 3, 21, 13, 31, 25, 9, 49, 33, 19, 29, 11, 19, 27, 15, 25};
+static const int k_c6[] = {13, 33, 115, 41, 79, 17, 29, 119, 75, 73, 105, 7, 59, 65, 21, 3, 113, 61, 89, 45, 107};
+static const int k_c7[] = {7, 23, 39};
+
+ORC_EXPORT int orc_sobol_table(int dim_num, uint32_t *v /* [dim_num][30] */) {
+    if (dim_num < 1 || dim_num > SOBOL_DIM_MAX) return -1;
+    static const int *cols[8] = {0, k_c1, k_c2, k_c3, k_c4, k_c5, k_c6, k_c7};
+    static const int first[8] = {0, 2, 3, 5, 7, 13, 19, 37};
+    uint32_t m[SOBOL_DIM_MAX][SOBOL_BITS];
+    memset(m, 0, sizeof m);
+    for (int d = 0; d < dim_num; d++) m[d][0] = 1;
+    for (int c = 1; c < 8; c++)
+        for (int d = first[c]; d < dim_num; d++) m[d][c] = (uint32_t)cols[c][d - first[c]];
+    for (int j = 0; j < SOBOL_BITS; j++) m[0][j] = 1;
+    for (int d = 1; d < dim_num; d++) {
+        int poly = k_poly[d], deg = 0;
+        for (int p = poly >> 1; p; p >>= 1) deg++;
+        for (int j = deg; j < SOBOL_BITS; j++) {
+            uint32_t newv = m[d][j - deg];
+            for (int k = 0; k < deg; k++)
+                if ((poly >> (deg - 1 - k)) & 1) newv ^= (2u << k) * m[d][j - k - 1];
+            m[d][j] = newv;
+        }
+    }
+    for (int d = 0; d < dim_num; d++)
+        for (int j = 0; j < SOBOL_BITS; j++) v[d * SOBOL_BITS + j] = m[d][j] << (SOBOL_BITS - 1 - j);
+    return 0;
+}
+
+/* out[i*dim + d] = d-th coordinate of point (first_index + i)  (i4_sobol, rrt_04:494-503) */
+ORC_EXPORT int orc_sobol_fill(int dim_num, int64_t first_index, int64_t count, double *out) {
+    uint32_t v[SOBOL_DIM_MAX * SOBOL_BITS];
+    if (orc_sobol_table(dim_num, v)) return -1;
+    const double recipd = 1.0 / 1073741824.0;
+    for (int64_t i = 0; i < count; i++) {
+        int64_t n = first_index + i;
+        if (n < 0) n = 0;
+        uint64_t g = (uint64_t)n ^ ((uint64_t)n >> 1);
+        for (int d = 0; d < dim_num; d++) {
+            uint32_t q = 0;
+            uint64_t gg = g;
+            for (int j = 0; gg && j < SOBOL_BITS; j++, gg >>= 1)
+                if (gg & 1) q ^= v[d * SOBOL_BITS + j];
+            out[i * dim_num + d] = (double)q * recipd;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Scenario + tree                                                                       */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    double sx, sy, gx, gy;
+    double expand_dis, res, robot_radius, connect_circle_dist;
+    double play[4]; /* xmin xmax ymin ymax */
+    int32_t has_play;
+    int32_t max_iter;
+    int32_t search_until_max_iter;
+    int32_t n_obs;
+} orc_params_t;
+
+#define MAXPTS 4096
+
+typedef struct {
+    const orc_params_t *p;
+    const double *obs; /* n_obs * 3 */
+    double *x, *y, *cost;
+    int32_t *parent;
+    int n;
+    uint8_t *verdicts;
+    int64_t n_verdicts, verdict_cap;
+    /* scratch for one edge */
+    double px[MAXPTS], py[MAXPTS];
+    int npts;
+} orc_tree_t;
+
+/* steer (rrt_04:1086-1115): fills t->px/py, returns the end point */
+static void steer(orc_tree_t *t, double fx, double fy, double tx, double ty, double extend,
+                  double *ex, double *ey) {
+    const double res = t->p->res;
+    double x = fx, y = fy;
+    double dx = tx - x, dy = ty - y;
+    double d = orc_hypot(dx, dy);
+    double theta = atan2(dy, dx);
+    int np = 0;
+    t->px[np] = x; t->py[np] = y; np++;
+    if (extend > d) extend = d;
+    double q = floor(extend / res);
+    long n_expand = (long)q;
+    for (long k = 0; k < n_expand; k++) {
+        x += res * cos(theta);
+        y += res * sin(theta);
+        if (np < MAXPTS) { t->px[np] = x; t->py[np] = y; np++; }
+    }
+    double d2 = orc_hypot(tx - x, ty - y);
+    if (d2 <= res) {
+        if (np < MAXPTS) { t->px[np] = tx; t->py[np] = ty; np++; }
+        x = tx; y = ty;
+    }
+    t->npts = np;
+    *ex = x; *ey = y;
+}
+
+/* check_collision (rrt_04:1216-1230) on the edge in scratch; logs the verdict. 1 = safe */
+static int collision_free(orc_tree_t *t) {
+    const orc_params_t *p = t->p;
+    int ok = 1;
+    for (int o = 0; o < p->n_obs && ok; o++) {
+        double ox = t->obs[3 * o], oy = t->obs[3 * o + 1], size = t->obs[3 * o + 2];
+        double mn = INFINITY;
+        for (int k = 0; k < t->npts; k++) {
+            double dx = ox - t->px[k], dy = oy - t->py[k];
+            double dd = dx * dx + dy * dy;
+            if (dd < mn) mn = dd;
+        }
+        if (mn <= sq(size + p->robot_radius)) ok = 0;
+    }
+    if (t->verdicts && t->n_verdicts < t->verdict_cap) t->verdicts[t->n_verdicts] = (uint8_t)ok;
+    t->n_verdicts++;
+    return ok;
+}
+
+static int inside_play(const orc_params_t *p, double x, double y) { /* rrt_04:1204-1214 */
+    if (!p->has_play) return 1;
+    if (x < p->play[0] || x > p->play[1] || y < p->play[2] || y > p->play[3]) return 0;
+    return 1;
+}
+
+static int edge_ok(orc_tree_t *t, double ex, double ey) { /* rrt_04:1267-1269 order */
+    return collision_free(t) && inside_play(t->p, ex, ey);
+}
+
+static void propagate(orc_tree_t *t, int p) { /* rrt_04:1379-1384 */
+    for (int c = 0; c < t->n; c++)
+        if (t->parent[c] == p) {
+            t->cost[c] = t->cost[p] + orc_hypot(t->x[c] - t->x[p], t->y[c] - t->y[p]);
+            propagate(t, c);
+        }
+}
+
+/* search_best_goal_node (rrt_04:1284-1312); -1 = None.  `dist`, `first` are scratch [n]. */
+static int best_goal(orc_tree_t *t, double *dist, int *cand) {
+    const orc_params_t *p = t->p;
+    int n = t->n, nc = 0;
+    for (int i = 0; i < n; i++) dist[i] = orc_hypot(t->x[i] - p->gx, t->y[i] - p->gy);
+    for (int i = 0; i < n; i++)
+        if (dist[i] <= p->expand_dis) {
+            int f = 0;
+            while (dist[f] != dist[i]) f++; /* list.index(): first equal value */
+            cand[nc++] = f;
+        }
+    int best = -1;
+    double best_cost = INFINITY;
+    for (int k = 0; k < nc; k++) {
+        int gi = cand[k];
+        double ex, ey;
+        steer(t, t->x[gi], t->y[gi], p->gx, p->gy, INFINITY, &ex, &ey);
+        if (edge_ok(t, ex, ey)) {
+            double c = t->cost[gi] + orc_hypot(t->x[gi] - p->gx, t->y[gi] - p->gy);
+            if (best < 0 || c < best_cost) { best = gi; best_cost = c; } /* first minimum */
+        }
+    }
+    return best;
+}
+
+/* RRT* planning loop (rrt_04:1036-1084).  Arrays x,y,cost,parent have capacity max_iter+1.
+ * trace (optional): int32[max_iter][8] = nearest,status,n_near,parent,cp_ok,rw_ok,rw_applied,n_after
+ * Returns 0.  *goal_index = best goal node (-1 = no path). */
+ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const double *stream,
+                               double *x, double *y, double *cost, int32_t *parent,
+                               int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+                               int32_t *trace, uint8_t *verdicts, int64_t verdict_cap,
+                               int64_t *n_verdicts) {
+    orc_tree_t *t = (orc_tree_t *)calloc(1, sizeof(orc_tree_t));
+    int cap = p->max_iter + 1;
+    double *dist = (double *)malloc(sizeof(double) * cap);
+    int *near = (int *)malloc(sizeof(int) * cap);
+    double *costs = (double *)malloc(sizeof(double) * cap);
+    t->p = p; t->obs = obs; t->x = x; t->y = y; t->cost = cost; t->parent = parent;
+    t->verdicts = verdicts; t->verdict_cap = verdict_cap;
+    x[0] = p->sx; y[0] = p->sy; cost[0] = 0.0; parent[0] = -1; t->n = 1;
+    int gi = -1, it = 0, done = 0;
+    for (it = 0; it < p->max_iter; it++) {
+        double rx = stream[2 * it], ry = stream[2 * it + 1];
+        int n = t->n;
+        /* nearest (rrt_04:1196-1202): first minimum */
+        int ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(x[i] - rx) + sq(y[i] - ry);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double nx, ny;
+        steer(t, x[ni], y[ni], rx, ry, p->expand_dis, &nx, &ny);
+        double ncost = cost[ni] + orc_hypot(nx - x[ni], ny - y[ni]);
+        int status = 0, n_near = 0, par = -1, cp_ok = 0, rw_ok = 0, rw_applied = 0;
+        if (inside_play(p, nx, ny)) {
+            status = 1;
+            if (collision_free(t)) {
+                /* find_near_nodes (rrt_04:1314-1338) */
+                double nnode = (double)(n + 1);
+                double r = p->connect_circle_dist * sqrt(log(nnode) / nnode);
+                if (p->expand_dis < r) r = p->expand_dis;
+                double r2 = sq(r);
+                for (int i = 0; i < n; i++) dist[i] = sq(x[i] - nx) + sq(y[i] - ny);
+                for (int i = 0; i < n; i++)
+                    if (dist[i] <= r2) {
+                        int f = 0;
+                        while (dist[f] != dist[i]) f++;
+                        near[n_near++] = f;
+                    }
+                /* choose_parent (rrt_04:1242-1282) */
+                int best = -1;
+                double min_cost = INFINITY;
+                for (int k = 0; k < n_near; k++) {
+                    int i = near[k];
+                    double ex, ey;
+                    steer(t, x[i], y[i], nx, ny, INFINITY, &ex, &ey);
+                    if (edge_ok(t, ex, ey)) {
+                        costs[k] = cost[i] + orc_hypot(nx - x[i], ny - y[i]);
+                        cp_ok++;
+                    } else {
+                        costs[k] = INFINITY;
+                    }
+                    if (costs[k] < min_cost) { min_cost = costs[k]; best = i; }
+                }
+                if (best >= 0) {
+                    double cx, cy;
+                    steer(t, x[best], y[best], nx, ny, INFINITY, &cx, &cy);
+                    double ccost = min_cost;
+                    /* rewire (rrt_04:1340-1373), before the append (rrt_04:1064-1065) */
+                    for (int k = 0; k < n_near; k++) {
+                        int i = near[k];
+                        double ex, ey;
+                        steer(t, cx, cy, x[i], y[i], INFINITY, &ex, &ey);
+                        double ecost = ccost + orc_hypot(x[i] - cx, y[i] - cy);
+                        int ok = edge_ok(t, ex, ey);
+                        rw_ok += ok;
+                        if (ok && cost[i] > ecost) {
+                            x[i] = ex; y[i] = ey; cost[i] = ecost; parent[i] = n;
+                            rw_applied++;
+                            propagate(t, i);
+                        }
+                    }
+                    x[n] = cx; y[n] = cy; cost[n] = ccost; parent[n] = best;
+                    status = 3; par = best;
+                } else {
+                    x[n] = nx; y[n] = ny; cost[n] = ncost; parent[n] = ni;
+                    status = 2; par = ni;
+                }
+                t->n = n + 1;
+            }
+        }
+        if (trace) {
+            int32_t *tr = trace + 8 * it;
+            tr[0] = ni; tr[1] = status; tr[2] = n_near; tr[3] = par; tr[4] = cp_ok;
+            tr[5] = rw_ok; tr[6] = rw_applied; tr[7] = t->n;
+        }
+        if (!p->search_until_max_iter) {
+            gi = best_goal(t, dist, near);
+            if (gi >= 0) { it++; done = 1; break; }
+        }
+    }
+    if (!done) gi = best_goal(t, dist, near);
+    *n_nodes = t->n; *iters_done = it; *goal_index = gi;
+    if (n_verdicts) *n_verdicts = t->n_verdicts;
+    free(dist); free(near); free(costs); free(t);
+    return 0;
+}
+
+/* basic RRT loop (rrt_01:71-101); *goal_index = index of the node that reached the goal */
+ORC_EXPORT int orc_rrt_run(const orc_params_t *p, const double *obs, const double *stream,
+                           double *x, double *y, int32_t *parent, int32_t *n_nodes,
+                           int32_t *iters_done, int32_t *goal_index) {
+    orc_tree_t *t = (orc_tree_t *)calloc(1, sizeof(orc_tree_t));
+    t->p = p; t->obs = obs; t->x = x; t->y = y; t->parent = parent;
+    x[0] = p->sx; y[0] = p->sy; parent[0] = -1; t->n = 1;
+    int gi = -1, it;
+    for (it = 0; it < p->max_iter; it++) {
+        double rx = stream[2 * it], ry = stream[2 * it + 1];
+        int n = t->n, ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(x[i] - rx) + sq(y[i] - ry);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double nx, ny;
+        steer(t, x[ni], y[ni], rx, ry, p->expand_dis, &nx, &ny);
+        if (inside_play(p, nx, ny) && collision_free(t)) {
+            x[n] = nx; y[n] = ny; parent[n] = ni; t->n = n + 1;
+        }
+        double lx = x[t->n - 1], ly = y[t->n - 1];
+        if (orc_hypot(lx - p->gx, ly - p->gy) <= p->expand_dis) {
+            double ex, ey;
+            steer(t, lx, ly, p->gx, p->gy, p->expand_dis, &ex, &ey);
+            if (collision_free(t)) { gi = t->n - 1; it++; break; }
+        }
+    }
+    *n_nodes = t->n; *iters_done = it; *goal_index = gi;
+    free(t);
+    return 0;
+}
+
+/* single-edge helper for unit tests: steer + collision + play area */
+ORC_EXPORT int orc_steer_collide(const orc_params_t *p, const double *obs, double fx, double fy,
+                                 double tx, double ty, double extend, double *ex, double *ey,
+                                 int32_t *npts, int32_t *free_flag, int32_t *inside_flag) {
+    orc_tree_t *t = (orc_tree_t *)calloc(1, sizeof(orc_tree_t));
+    t->p = p; t->obs = obs;
+    steer(t, fx, fy, tx, ty, extend, ex, ey);
+    *npts = t->npts;
+    *free_flag = collision_free(t);
+    *inside_flag = inside_play(p, *ex, *ey);
+    free(t);
+    return 0;
+}
