@@ -1,0 +1,147 @@
+/* rrtk.h -- C-ABI of librrtk.so: B200-native (sm_100a) kernels for the RRT-family hot path of
+ * gouldberg/robotics-path-planning.
+ *
+ * The reference is pure Python and has no FFI; the boundary it exposes is its class API
+ * (`RRT(...).planning()`).  This header is what a binding for that path binds:
+ * each entry point names the reference function(s) it replaces (alias:line into
+ * /root/reference/src_path_planning, aliases in SURVEY.md section 0).  The Python classes in
+ * robotics-path-planning_b200/rrtk/ (same names, kwargs and return values as the reference's)
+ * call these through ctypes; INTEGRATION.md shows the stub a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, negative = error (rrtk_last_error() gives the
+ *     message for the calling thread); nothing throws;
+ *   - `*_dev` entry points take CALLER-OWNED DEVICE pointers (e.g. torch `tensor.data_ptr()`),
+ *     explicit element counts, and a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *     they enqueue work and return without synchronising;
+ *   - `*_host` entry points take HOST pointers, allocate temporaries, copy in, run, copy out and
+ *     synchronise before returning (the end-to-end path);
+ *   - no global mutable state; the current CUDA device is the caller's;
+ *   - all floating-point tree state is FP64 (see DESIGN.md "Arithmetic"): the reference computes in
+ *     Python floats and its trees are only reproducible bit-for-bit in FP64 with correctly rounded
+ *     hypot/atan2/cos/sin (csrc/crmath.h).
+ */
+#ifndef RRTK_H
+#define RRTK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTK_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define RRTK_API __attribute__((visibility("default")))
+#else
+#define RRTK_API
+#endif
+
+/* status codes */
+#define RRTK_OK 0
+#define RRTK_ERR_INVALID (-1) /* bad argument */
+#define RRTK_ERR_CUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define RRTK_ERR_NO_DEVICE (-3)
+
+/* per-query status bits written by the planners */
+#define RRTK_Q_OK 0
+#define RRTK_Q_NEAR_OVERFLOW 1 /* |near| exceeded near_cap; the query stopped at that iteration */
+#define RRTK_Q_NODE_OVERFLOW 2 /* tree reached node_cap */
+
+/* sampler kinds (get_random_node / get_random_node_sobol, rrt_04:1132-1153) */
+#define RRTK_SAMPLER_STREAM 0  /* read (x, y) per iteration from `sample_stream` */
+#define RRTK_SAMPLER_SOBOL 1   /* in-kernel: goal coin + Sobol point `sobol_offset[q] + #non-goal` */
+#define RRTK_SAMPLER_UNIFORM 2 /* in-kernel: goal coin + two counter-based uniforms */
+
+RRTK_API int rrtk_version(void);
+RRTK_API const char *rrtk_last_error(void);
+/* number of CUDA devices visible, or a negative status */
+RRTK_API int rrtk_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sobol generator: i4_sobol (rrt_04:230-503) in closed form (Gray-code order, 30 bits, <= 40 dims,
+ * Bratley-Fox direction numbers rrt_04:320-364 + recurrence :393-436).
+ *   out[i * dim + d] = coordinate d of point (first_index + i), as FP64 in [0, 1).
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_sobol_fill_dev(int dim, int64_t first_index, int64_t count, double *out_dev, void *stream);
+RRTK_API int rrtk_sobol_fill_host(int dim, int64_t first_index, int64_t count, double *out_host);
+/* the scaled direction integers V[dim][30] (host memory), for tests */
+RRTK_API int rrtk_sobol_table(int dim, uint32_t *v_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched RRT* -- the whole `planning()` loop of rrt_04:1036-1084 for Q independent queries in one
+ * persistent kernel (one warp per query): get_random_node[_sobol] (:1132-1153),
+ * get_nearest_node_index (:1196-1202), steer (:1086-1115), check_if_outside_play_area (:1204-1214),
+ * check_collision (:1216-1230), find_near_nodes (:1314-1338, including the `.index()` quirk),
+ * choose_parent (:1242-1282), rewire (:1340-1373) + propagate_cost_to_leaves (:1379-1384),
+ * search_best_goal_node (:1284-1312).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rrtk_rrtstar_params {
+    int32_t n_queries;
+    int32_t max_iter;
+    int32_t node_cap;               /* capacity of each tree, >= max_iter + 1 */
+    int32_t obs_stride;             /* obstacles per query in the `obstacles` array (max count) */
+    int32_t near_cap;               /* capacity of the near list per query (multiple of 32) */
+    int32_t search_until_max_iter;  /* 0: stop at the first goal connection (script default) */
+    int32_t sampler;                /* RRTK_SAMPLER_* */
+    int32_t goal_sample_rate;       /* percent, `random.randint(0, 100) > rate` -> non-goal */
+    int32_t has_play_area;
+    int32_t rrt_only;               /* 1: basic RRT loop of rrt_01:71-101 (no near/choose/rewire) */
+    double expand_dis;
+    double path_resolution;
+    double min_rand, max_rand;
+    double play_area[4];            /* xmin, xmax, ymin, ymax */
+    uint64_t seed;                  /* counter-based RNG key for the in-kernel samplers */
+} rrtk_rrtstar_params;
+
+/* Device-pointer entry point.
+ *   start_goal   [Q][4]                 sx, sy, gx, gy
+ *   obstacles    [Q][obs_stride][4]     x, y, R = size + robot_radius, R2 = (size + robot_radius)**2
+ *                                        (R2 is computed by the host exactly as rrt_04:1227 does)
+ *   n_obs        [Q]
+ *   near_r2      [node_cap + 2]         near_r2[k] = min(ccd*sqrt(log(k)/k), expand_dis)**2, k = #nodes+1
+ *                                        (rrt_04:1329-1335; host-evaluated, same libm as the reference)
+ *   sample_stream[Q][max_iter][2] or NULL   (RRTK_SAMPLER_STREAM)
+ *   sobol_offset [Q] or NULL                first Sobol index of each query (RRTK_SAMPLER_SOBOL)
+ * outputs (caller allocated):
+ *   xy [Q][node_cap][2], cost [Q][node_cap], parent [Q][node_cap] (-1 = root),
+ *   n_nodes [Q], iters_done [Q], goal_index [Q] (-1 = no path), status [Q],
+ *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
+ */
+RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
+                         const double *obstacles, const int32_t *n_obs, const double *near_r2,
+                         const double *sample_stream, const int64_t *sobol_offset, double *xy,
+                         double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
+                         int32_t *goal_index, int32_t *status, int32_t *trace, void *stream);
+
+/* Same with HOST pointers (allocates, copies in, runs, copies out, synchronises). */
+RRTK_API int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal,
+                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
+                          const double *sample_stream, const int64_t *sobol_offset, double *xy,
+                          double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
+                          int32_t *goal_index, int32_t *status, int32_t *trace);
+
+/* generate_final_course (rrt_04:1117-1125) for every query on the device:
+ *   path [Q][path_cap][2] = goal, node(goal_index), ..., root;  path_len [Q] (0 = no path) */
+RRTK_API int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
+                           const double *start_goal, const double *xy, const int32_t *parent,
+                           const int32_t *goal_index, double *path, int32_t *path_len, void *stream);
+
+/* The in-kernel samplers, exposed so a sample stream can be materialised (tests, CPU baseline):
+ *   out [Q][max_iter][2]; uses p->sampler, seed, goal_sample_rate, min/max_rand, start_goal */
+RRTK_API int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,
+                           const int64_t *sobol_offset, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
+ *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
+ *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTK_H */

@@ -22,12 +22,19 @@ class Params(C.Structure):
                 ("expand_dis", C.c_double), ("res", C.c_double), ("robot_radius", C.c_double),
                 ("connect_circle_dist", C.c_double), ("play", C.c_double * 4),
                 ("has_play", C.c_int32), ("max_iter", C.c_int32),
-                ("search_until_max_iter", C.c_int32), ("n_obs", C.c_int32)]
+                ("search_until_max_iter", C.c_int32), ("n_obs", C.c_int32),
+                ("math_mode", C.c_int32), ("pad_", C.c_int32)]
+
+MATH_LIBM = 0   # the reference's arithmetic on this platform (CPython -> glibc)
+MATH_CR = 1     # correctly-rounded leaf functions (what the GPU path computes)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(HERE, "rrtk_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "rrtk_oracle.c"),
+            os.path.join(HERE, "..", "robotics-path-planning_b200", "csrc", "crmath.h"),
+            os.path.join(HERE, "..", "robotics-path-planning_b200", "csrc", "crmath_consts.h")]
+    if force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE])
     return LIB_PATH
 
@@ -37,8 +44,14 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(LIB_PATH)
-        _lib.orc_hypot.restype = C.c_double
-        _lib.orc_hypot.argtypes = [C.c_double, C.c_double]
+        for name, nargs in (("orc_hypot", 2), ("orc_cr_hypot", 2), ("orc_cr_sin", 1),
+                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2)):
+            f = getattr(_lib, name)
+            f.restype = C.c_double
+            f.argtypes = [C.c_double] * nargs
+        _lib.orc_cr_atan2_sincos.restype = C.c_double
+        _lib.orc_cr_atan2_sincos.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double)]
     return _lib
 
 
@@ -47,8 +60,10 @@ def _p(a, t):
 
 
 def make_params(start, goal, obstacle_list, expand_dis, path_resolution, max_iter, play_area,
-                robot_radius, connect_circle_dist=50.0, search_until_max_iter=True):
+                robot_radius, connect_circle_dist=50.0, search_until_max_iter=True,
+                math_mode=MATH_LIBM):
     p = Params()
+    p.math_mode = int(math_mode)
     p.sx, p.sy, p.gx, p.gy = float(start[0]), float(start[1]), float(goal[0]), float(goal[1])
     p.expand_dis, p.res = float(expand_dis), float(path_resolution)
     p.robot_radius, p.connect_circle_dist = float(robot_radius), float(connect_circle_dist)
@@ -83,7 +98,7 @@ def sobol_table(dim: int) -> np.ndarray:
 
 
 def rrtstar_run(params: Params, obs: np.ndarray, stream: np.ndarray, want_trace=True,
-                verdict_cap=0):
+                verdict_cap=0, tie_cap=0):
     """Returns dict(x, y, cost, parent, n, iters_done, goal_index, trace, verdicts)."""
     cap = params.max_iter + 1
     stream = np.ascontiguousarray(stream, dtype=np.float64).reshape(-1, 2)
@@ -96,16 +111,20 @@ def rrtstar_run(params: Params, obs: np.ndarray, stream: np.ndarray, want_trace=
     trace = np.zeros((params.max_iter, 8), dtype=np.int32) if want_trace else None
     verd = np.zeros(max(verdict_cap, 1), dtype=np.uint8)
     nv = C.c_int64()
+    ties = np.zeros((max(tie_cap, 1), 3), dtype=np.float64)
+    nt = C.c_int64()
     lib().orc_rrtstar_run(C.byref(params), _p(obs, C.c_double), _p(stream, C.c_double),
                           _p(x, C.c_double), _p(y, C.c_double), _p(cost, C.c_double),
                           _p(parent, C.c_int32), C.byref(n), C.byref(it), C.byref(gi),
                           _p(trace, C.c_int32) if want_trace else None,
                           _p(verd, C.c_uint8) if verdict_cap else None, C.c_int64(verdict_cap),
-                          C.byref(nv))
+                          C.byref(nv), _p(ties, C.c_double) if tie_cap else None, C.c_int64(tie_cap),
+                          C.byref(nt))
     k = n.value
     return dict(x=x[:k], y=y[:k], cost=cost[:k], parent=parent[:k], n=k, iters_done=it.value,
                 goal_index=gi.value, trace=None if trace is None else trace[:it.value],
-                verdicts=verd[:min(nv.value, verdict_cap)], n_verdicts=nv.value)
+                verdicts=verd[:min(nv.value, verdict_cap)], n_verdicts=nv.value,
+                ties=ties[:min(nt.value, tie_cap)], n_ties=nt.value)
 
 
 def rrt_run(params: Params, obs: np.ndarray, stream: np.ndarray):
@@ -135,3 +154,9 @@ def final_course(res: dict, goal) -> list | None:
         i = int(res["parent"][i])
     path.append([float(res["x"][i]), float(res["y"][i])])
     return path
+
+
+def cr_atan2_sincos(y: float, x: float):
+    s = C.c_double(); c = C.c_double()
+    th = lib().orc_cr_atan2_sincos(y, x, C.byref(s), C.byref(c))
+    return th, s.value, c.value

@@ -23,6 +23,13 @@
 
 #define ORC_EXPORT __attribute__((visibility("default")))
 
+/* "cr" math mode: the correctly-rounded leaf functions the GPU path uses (same header, so the
+ * GPU and the oracle's cr mode are bit-identical by construction; the header itself is checked
+ * against mpmath in tests/test_crmath.py).  The "libm" mode uses none of it. */
+#include "../robotics-path-planning_b200/csrc/crmath.h"
+#define ORC_MATH_LIBM 0
+#define ORC_MATH_CR 1
+
 /* ------------------------------------------------------------------------------------ */
 /* math.hypot of CPython >= 3.10 (Modules/mathmodule.c vector_norm, n = 2)               */
 /* ------------------------------------------------------------------------------------ */
@@ -75,7 +82,17 @@ ORC_EXPORT double orc_hypot(double a, double b) {
     return h / scale;
 }
 
-static inline double sq(double x) { return pow(x, 2.0); } /* Python `x ** 2` */
+static inline double sq_libm(double x) { return pow(x, 2.0); } /* Python `x ** 2` */
+/* per-node squared distances: libm mode = Python `**` (libm pow); cr mode = exact IEEE square */
+static inline double sq(int mode, double x) { return mode == ORC_MATH_LIBM ? pow(x, 2.0) : x * x; }
+
+ORC_EXPORT double orc_cr_sin(double x) { return crm_sin(x); }
+ORC_EXPORT double orc_cr_cos(double x) { return crm_cos(x); }
+ORC_EXPORT double orc_cr_atan2(double y, double x) { return crm_atan2(y, x); }
+ORC_EXPORT double orc_cr_hypot(double a, double b) { return crm_hypot(a, b); }
+ORC_EXPORT double orc_cr_atan2_sincos(double y, double x, double *s, double *c) {
+    return crm_atan2_sincos(y, x, s, c);
+}
 
 /* ------------------------------------------------------------------------------------ */
 /* Sobol (rrt_04:230-503): closed form, Gray-code order                                  */
@@ -151,6 +168,8 @@ typedef struct {
     int32_t max_iter;
     int32_t search_until_max_iter;
     int32_t n_obs;
+    int32_t math_mode; /* ORC_MATH_LIBM (the reference on this platform) or ORC_MATH_CR */
+    int32_t pad_;
 } orc_params_t;
 
 #define MAXPTS 4096
@@ -166,7 +185,24 @@ typedef struct {
     /* scratch for one edge */
     double px[MAXPTS], py[MAXPTS];
     int npts;
+    /* tie log: decisions whose relative margin is below ORC_TIE_EPS (north_star: "ties within 1e-6
+     * are logged").  rows of (iteration, kind, margin); kinds: 0 snap `d <= res`, 1 floor(extend/res),
+     * 2 near `d2 <= r2`, 3 collision `min d2 <= R2`, 4 rewire `cost > edge cost`, 5 nearest argmin */
+    double *ties;
+    int64_t n_ties, tie_cap;
+    int cur_it;
 } orc_tree_t;
+
+#define ORC_TIE_EPS 1e-6
+static void log_tie(orc_tree_t *t, int kind, double margin) {
+    if (fabs(margin) >= ORC_TIE_EPS) return;
+    if (t->ties && t->n_ties < t->tie_cap) {
+        t->ties[3 * t->n_ties] = (double)t->cur_it;
+        t->ties[3 * t->n_ties + 1] = (double)kind;
+        t->ties[3 * t->n_ties + 2] = margin;
+    }
+    t->n_ties++;
+}
 
 /* steer (rrt_04:1086-1115): fills t->px/py, returns the end point */
 static void steer(orc_tree_t *t, double fx, double fy, double tx, double ty, double extend,
@@ -175,18 +211,27 @@ static void steer(orc_tree_t *t, double fx, double fy, double tx, double ty, dou
     double x = fx, y = fy;
     double dx = tx - x, dy = ty - y;
     double d = orc_hypot(dx, dy);
-    double theta = atan2(dy, dx);
+    double ct, st;
+    if (t->p->math_mode == ORC_MATH_LIBM) {
+        double theta = atan2(dy, dx);
+        ct = cos(theta);
+        st = sin(theta);
+    } else {
+        (void)crm_atan2_sincos(dy, dx, &st, &ct);
+    }
     int np = 0;
     t->px[np] = x; t->py[np] = y; np++;
     if (extend > d) extend = d;
     double q = floor(extend / res);
     long n_expand = (long)q;
+    if (t->ties) { double fr = extend / res - q; log_tie(t, 1, fr < 0.5 ? fr : fr - 1.0); }
     for (long k = 0; k < n_expand; k++) {
-        x += res * cos(theta);
-        y += res * sin(theta);
+        x += res * ct;
+        y += res * st;
         if (np < MAXPTS) { t->px[np] = x; t->py[np] = y; np++; }
     }
     double d2 = orc_hypot(tx - x, ty - y);
+    if (t->ties) log_tie(t, 0, (d2 - res) / res);
     if (d2 <= res) {
         if (np < MAXPTS) { t->px[np] = tx; t->py[np] = ty; np++; }
         x = tx; y = ty;
@@ -207,7 +252,8 @@ static int collision_free(orc_tree_t *t) {
             double dd = dx * dx + dy * dy;
             if (dd < mn) mn = dd;
         }
-        if (mn <= sq(size + p->robot_radius)) ok = 0;
+        if (t->ties) log_tie(t, 3, (mn - sq_libm(size + p->robot_radius)) / sq_libm(size + p->robot_radius));
+        if (mn <= sq_libm(size + p->robot_radius)) ok = 0; /* per-obstacle constant: host libm */
     }
     if (t->verdicts && t->n_verdicts < t->verdict_cap) t->verdicts[t->n_verdicts] = (uint8_t)ok;
     t->n_verdicts++;
@@ -264,7 +310,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
                                double *x, double *y, double *cost, int32_t *parent,
                                int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
                                int32_t *trace, uint8_t *verdicts, int64_t verdict_cap,
-                               int64_t *n_verdicts) {
+                               int64_t *n_verdicts, double *ties, int64_t tie_cap, int64_t *n_ties) {
     orc_tree_t *t = (orc_tree_t *)calloc(1, sizeof(orc_tree_t));
     int cap = p->max_iter + 1;
     double *dist = (double *)malloc(sizeof(double) * cap);
@@ -272,18 +318,22 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
     double *costs = (double *)malloc(sizeof(double) * cap);
     t->p = p; t->obs = obs; t->x = x; t->y = y; t->cost = cost; t->parent = parent;
     t->verdicts = verdicts; t->verdict_cap = verdict_cap;
+    t->ties = ties; t->tie_cap = tie_cap;
     x[0] = p->sx; y[0] = p->sy; cost[0] = 0.0; parent[0] = -1; t->n = 1;
     int gi = -1, it = 0, done = 0;
     for (it = 0; it < p->max_iter; it++) {
         double rx = stream[2 * it], ry = stream[2 * it + 1];
         int n = t->n;
+        t->cur_it = it;
         /* nearest (rrt_04:1196-1202): first minimum */
         int ni = 0;
-        double dmin = INFINITY;
+        double dmin = INFINITY, dsecond = INFINITY;
         for (int i = 0; i < n; i++) {
-            double d = sq(x[i] - rx) + sq(y[i] - ry);
-            if (d < dmin) { dmin = d; ni = i; }
+            double d = sq(p->math_mode, x[i] - rx) + sq(p->math_mode, y[i] - ry);
+            if (d < dmin) { dsecond = dmin; dmin = d; ni = i; }
+            else if (d < dsecond) dsecond = d;
         }
+        if (t->ties && dsecond < INFINITY && dsecond != dmin && dmin > 0.0) log_tie(t, 5, (dsecond - dmin) / dmin);
         double nx, ny;
         steer(t, x[ni], y[ni], rx, ry, p->expand_dis, &nx, &ny);
         double ncost = cost[ni] + orc_hypot(nx - x[ni], ny - y[ni]);
@@ -295,14 +345,16 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
                 double nnode = (double)(n + 1);
                 double r = p->connect_circle_dist * sqrt(log(nnode) / nnode);
                 if (p->expand_dis < r) r = p->expand_dis;
-                double r2 = sq(r);
-                for (int i = 0; i < n; i++) dist[i] = sq(x[i] - nx) + sq(y[i] - ny);
-                for (int i = 0; i < n; i++)
+                double r2 = sq_libm(r); /* per-iteration constant: host libm in the product too */
+                for (int i = 0; i < n; i++) dist[i] = sq(p->math_mode, x[i] - nx) + sq(p->math_mode, y[i] - ny);
+                for (int i = 0; i < n; i++) {
+                    if (t->ties && r2 > 0.0) log_tie(t, 2, (dist[i] - r2) / r2);
                     if (dist[i] <= r2) {
                         int f = 0;
                         while (dist[f] != dist[i]) f++;
                         near[n_near++] = f;
                     }
+                }
                 /* choose_parent (rrt_04:1242-1282) */
                 int best = -1;
                 double min_cost = INFINITY;
@@ -330,6 +382,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
                         double ecost = ccost + orc_hypot(x[i] - cx, y[i] - cy);
                         int ok = edge_ok(t, ex, ey);
                         rw_ok += ok;
+                        if (t->ties && ok && cost[i] != ecost) log_tie(t, 4, (cost[i] - ecost) / ecost);
                         if (ok && cost[i] > ecost) {
                             x[i] = ex; y[i] = ey; cost[i] = ecost; parent[i] = n;
                             rw_applied++;
@@ -358,6 +411,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
     if (!done) gi = best_goal(t, dist, near);
     *n_nodes = t->n; *iters_done = it; *goal_index = gi;
     if (n_verdicts) *n_verdicts = t->n_verdicts;
+    if (n_ties) *n_ties = t->n_ties;
     free(dist); free(near); free(costs); free(t);
     return 0;
 }
@@ -375,7 +429,7 @@ ORC_EXPORT int orc_rrt_run(const orc_params_t *p, const double *obs, const doubl
         int n = t->n, ni = 0;
         double dmin = INFINITY;
         for (int i = 0; i < n; i++) {
-            double d = sq(x[i] - rx) + sq(y[i] - ry);
+            double d = sq(p->math_mode, x[i] - rx) + sq(p->math_mode, y[i] - ry);
             if (d < dmin) { dmin = d; ni = i; }
         }
         double nx, ny;

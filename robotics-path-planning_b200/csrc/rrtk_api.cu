@@ -1,0 +1,208 @@
+// rrtk_api.cu -- the extern "C" boundary (include/rrtk.h): argument checks, error strings, host-buffer
+// wrappers.  No torch types; plain pointers and sizes.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/rrtk.h"
+#include "rrtk_device.cuh"
+
+namespace rrtk {
+
+static thread_local std::string g_err;
+
+int set_error(int code, const char *msg) {
+    g_err = msg ? msg : "";
+    return code;
+}
+int set_cuda_error(cudaError_t e, const char *where) {
+    g_err = std::string(where ? where : "cuda") + ": " + cudaGetErrorString(e);
+    return RRTK_ERR_CUDA;
+}
+
+// launchers (defined next to their kernels)
+int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
+                   const int32_t *n_obs, const double *near_r2, const double *sample_stream,
+                   const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
+                   int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                   int32_t *trace, unsigned int *counter, cudaStream_t s);
+int launch_extract_paths(int32_t nq, int32_t node_cap, int32_t path_cap, const double *start_goal,
+                         const double *xy, const int32_t *parent, const int32_t *goal_index,
+                         double *path, int32_t *path_len, cudaStream_t s);
+int launch_sample_stream(const rrtk_rrtstar_params &p, const double *start_goal,
+                         const int64_t *sobol_offset, double *out, cudaStream_t s);
+int launch_crmath_probe(int kind, int64_t n, const double *a, const double *b, double *out, cudaStream_t s);
+int launch_sobol_fill(int dim, int64_t first, int64_t count, double *out, cudaStream_t s);
+
+static int check_params(const rrtk_rrtstar_params *p) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->n_queries < 0 || p->max_iter < 0) return set_error(RRTK_ERR_INVALID, "n_queries/max_iter negative");
+    if (p->node_cap < 1) return set_error(RRTK_ERR_INVALID, "node_cap < 1");
+    if (p->near_cap < 32 || (p->near_cap & 31)) return set_error(RRTK_ERR_INVALID, "near_cap must be a positive multiple of 32");
+    if (!(p->path_resolution > 0.0)) return set_error(RRTK_ERR_INVALID, "path_resolution must be > 0");
+    if (!(p->expand_dis >= 0.0)) return set_error(RRTK_ERR_INVALID, "expand_dis must be >= 0");
+    if (p->sampler < 0 || p->sampler > 2) return set_error(RRTK_ERR_INVALID, "unknown sampler");
+    if (p->obs_stride < 0) return set_error(RRTK_ERR_INVALID, "obs_stride negative");
+    return RRTK_OK;
+}
+
+// a per-call device counter for the persistent kernel's work queue
+struct DevCounter {
+    unsigned int *ptr = nullptr;
+    cudaStream_t s;
+    explicit DevCounter(cudaStream_t st) : s(st) { cudaMallocAsync(&ptr, sizeof(unsigned int), st); }
+    ~DevCounter() { if (ptr) cudaFreeAsync(ptr, s); }
+};
+
+}  // namespace rrtk
+
+using namespace rrtk;
+
+extern "C" {
+
+int rrtk_version(void) { return RRTK_VERSION; }
+const char *rrtk_last_error(void) { return g_err.c_str(); }
+
+int rrtk_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_cuda_error(e, "cudaGetDeviceCount"); }
+    return n;
+}
+
+int rrtk_sobol_table(int dim, uint32_t *v_host) {
+    if (dim < 1 || dim > SOBOL_DIM_MAX || !v_host) return set_error(RRTK_ERR_INVALID, "1 <= dim <= 40");
+    static const SobolTable t = make_sobol_table();
+    std::memcpy(v_host, t.v, sizeof(uint32_t) * SOBOL_BITS * dim);
+    return RRTK_OK;
+}
+
+int rrtk_sobol_fill_dev(int dim, int64_t first_index, int64_t count, double *out_dev, void *stream) {
+    if (dim < 1 || dim > SOBOL_DIM_MAX) return set_error(RRTK_ERR_INVALID, "1 <= dim <= 40 (rrt_04:382-387)");
+    if (count < 0 || (count > 0 && !out_dev)) return set_error(RRTK_ERR_INVALID, "bad count/out");
+    if (count == 0) return RRTK_OK;
+    return launch_sobol_fill(dim, first_index, count, out_dev, (cudaStream_t)stream);
+}
+
+int rrtk_sobol_fill_host(int dim, int64_t first_index, int64_t count, double *out_host) {
+    if (dim < 1 || dim > SOBOL_DIM_MAX) return set_error(RRTK_ERR_INVALID, "1 <= dim <= 40 (rrt_04:382-387)");
+    if (count < 0 || (count > 0 && !out_host)) return set_error(RRTK_ERR_INVALID, "bad count/out");
+    if (count == 0) return RRTK_OK;
+    double *d = nullptr;
+    size_t bytes = sizeof(double) * (size_t)count * dim;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc");
+    int rc = launch_sobol_fill(dim, first_index, count, d, 0);
+    if (rc == RRTK_OK) {
+        e = cudaMemcpy(out_host, d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_cuda_error(e, "cudaMemcpy D2H");
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
+                         const double *obstacles, const int32_t *n_obs, const double *near_r2,
+                         const double *sample_stream, const int64_t *sobol_offset, double *xy,
+                         double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
+                         int32_t *goal_index, int32_t *status, int32_t *trace, void *stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->n_queries == 0) return RRTK_OK;
+    if (!start_goal || !n_obs || !xy || !cost || !parent || !n_nodes || !iters_done || !goal_index || !status)
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (!p->rrt_only && !near_r2) return set_error(RRTK_ERR_INVALID, "near_r2 is NULL");
+    if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
+    if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
+        return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
+    cudaStream_t s = (cudaStream_t)stream;
+    DevCounter ctr(s);
+    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    return launch_rrtstar(*p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost,
+                          parent, n_nodes, iters_done, goal_index, status, trace, ctr.ptr, s);
+}
+
+int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
+                           const double *start_goal, const double *xy, const int32_t *parent,
+                           const int32_t *goal_index, double *path, int32_t *path_len, void *stream) {
+    if (n_queries < 0 || node_cap < 1 || path_cap < 2) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (n_queries == 0) return RRTK_OK;
+    if (!start_goal || !xy || !parent || !goal_index || !path || !path_len)
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_extract_paths(n_queries, node_cap, path_cap, start_goal, xy, parent, goal_index, path,
+                                path_len, (cudaStream_t)stream);
+}
+
+int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,
+                           const int64_t *sobol_offset, double *out, void *stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->sampler == RRTK_SAMPLER_STREAM) return set_error(RRTK_ERR_INVALID, "sampler = STREAM has nothing to generate");
+    if (p->n_queries == 0 || p->max_iter == 0) return RRTK_OK;
+    if (!start_goal || !out) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_sample_stream(*p, start_goal, sobol_offset, out, (cudaStream_t)stream);
+}
+
+int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out, void *stream) {
+    if (kind < 0 || kind > 5 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
+    if (n == 0) return RRTK_OK;
+    if (!a || !out || (!b && (kind == 0 || kind == 1 || kind >= 4))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_crmath_probe(kind, n, a, b, out, (cudaStream_t)stream);
+}
+
+// ---- host-buffer wrapper: the end-to-end path (H2D, kernel, D2H inside the call) ----
+#define RRTK_TRY_CUDA(expr, what)                                      \
+    do {                                                               \
+        cudaError_t e__ = (expr);                                      \
+        if (e__ != cudaSuccess) { rc = set_cuda_error(e__, what); goto cleanup; } \
+    } while (0)
+
+int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal,
+                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
+                          const double *sample_stream, const int64_t *sobol_offset, double *xy,
+                          double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
+                          int32_t *goal_index, int32_t *status, int32_t *trace) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->n_queries == 0) return RRTK_OK;
+    const size_t Q = (size_t)p->n_queries, cap = (size_t)p->node_cap, it = (size_t)p->max_iter;
+    const size_t b_sg = Q * 4 * 8, b_obs = Q * (size_t)p->obs_stride * 4 * 8, b_no = Q * 4,
+                 b_r2 = (cap + 2) * 8, b_st = sample_stream ? Q * it * 16 : 0,
+                 b_so = sobol_offset ? Q * 8 : 0, b_xy = Q * cap * 16, b_c = Q * cap * 8,
+                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0;
+    char *d = nullptr;
+    size_t off[16], total = 0;
+    const size_t sizes[14] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr};
+    for (int i = 0; i < 14; i++) { off[i] = total; total += (sizes[i] + 255) & ~(size_t)255; }
+    cudaStream_t s = 0;
+    RRTK_TRY_CUDA(cudaMalloc(&d, total ? total : 256), "cudaMalloc");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[0], start_goal, b_sg, cudaMemcpyHostToDevice, s), "H2D start_goal");
+    if (b_obs) RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[1], obstacles, b_obs, cudaMemcpyHostToDevice, s), "H2D obstacles");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[2], n_obs, b_no, cudaMemcpyHostToDevice, s), "H2D n_obs");
+    if (near_r2) RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[3], near_r2, b_r2, cudaMemcpyHostToDevice, s), "H2D near_r2");
+    if (b_st) RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[4], sample_stream, b_st, cudaMemcpyHostToDevice, s), "H2D stream");
+    if (b_so) RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[5], sobol_offset, b_so, cudaMemcpyHostToDevice, s), "H2D sobol_offset");
+    rc = rrtk_rrtstar_run_dev(p, (double *)(d + off[0]), (double *)(d + off[1]), (int32_t *)(d + off[2]),
+                              near_r2 ? (double *)(d + off[3]) : nullptr,
+                              b_st ? (double *)(d + off[4]) : nullptr, b_so ? (int64_t *)(d + off[5]) : nullptr,
+                              (double *)(d + off[6]), (double *)(d + off[7]), (int32_t *)(d + off[8]),
+                              (int32_t *)(d + off[9]), (int32_t *)(d + off[10]), (int32_t *)(d + off[11]),
+                              (int32_t *)(d + off[12]), b_tr ? (int32_t *)(d + off[13]) : nullptr, s);
+    if (rc) goto cleanup;
+    RRTK_TRY_CUDA(cudaMemcpyAsync(xy, d + off[6], b_xy, cudaMemcpyDeviceToHost, s), "D2H xy");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(cost, d + off[7], b_c, cudaMemcpyDeviceToHost, s), "D2H cost");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(parent, d + off[8], b_p, cudaMemcpyDeviceToHost, s), "D2H parent");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(n_nodes, d + off[9], b_q, cudaMemcpyDeviceToHost, s), "D2H n_nodes");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(iters_done, d + off[10], b_q, cudaMemcpyDeviceToHost, s), "D2H iters_done");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(goal_index, d + off[11], b_q, cudaMemcpyDeviceToHost, s), "D2H goal_index");
+    RRTK_TRY_CUDA(cudaMemcpyAsync(status, d + off[12], b_q, cudaMemcpyDeviceToHost, s), "D2H status");
+    if (b_tr) RRTK_TRY_CUDA(cudaMemcpyAsync(trace, d + off[13], b_tr, cudaMemcpyDeviceToHost, s), "D2H trace");
+    RRTK_TRY_CUDA(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+cleanup:
+    if (d) cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

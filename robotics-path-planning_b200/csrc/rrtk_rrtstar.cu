@@ -1,0 +1,669 @@
+// rrtk_rrtstar.cu -- batched RRT / RRT* planning loop, one warp per query, persistent grid.
+//
+// Replaces the whole `planning()` loop of the reference's RRT* (rrt_04:1036-1084) and basic RRT
+// (rrt_01:71-101) for Q independent queries.  Design:
+//   * one warp owns one query for all its iterations; warps pull query ids from an atomic counter
+//     (persistent grid sized to the SM count), so ragged per-query work balances itself;
+//   * the tree lives in the caller's output arrays (xy as double2, cost, parent) -- L2-resident for
+//     the active set -- and is scanned with coalesced 16-byte loads (nearest, near, propagate);
+//   * all decisions are taken in FP64 with the reference's operation order and correctly rounded
+//     hypot/atan2/cos/sin (crmath.h); compiled with -fmad=false so no multiply-add is contracted;
+//   * per iteration the obstacles are culled once (exact, conservative disc test around the new
+//     node) into shared memory; every edge of that iteration (1 + 2|near| steers) is tested only
+//     against the survivors -- collision verdicts are unchanged because a culled obstacle cannot
+//     touch any path point of that iteration;
+//   * choose_parent / rewire: one lane per near candidate (steer + collision + cost in parallel),
+//     warp-shuffle first-min, then the order-dependent apply phase of rewire runs in list order with
+//     level-synchronous cost propagation over the parent array.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrtk.h"
+#include "crmath.h"
+#include "rrtk_device.cuh"
+
+namespace rrtk {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CULL_CAP = 64;      // culled obstacle list per warp (overflow -> full list)
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Steer {
+    double ex, ey;    // end point
+    double stx, sty;  // step vector = res * (cos, sin)
+    int n;            // number of accumulated steps
+    bool snap;        // final point snapped to the target
+};
+
+// steer (rrt_04:1086-1115)
+__device__ __noinline__ Steer steer(double fx, double fy, double tx, double ty, double extend,
+                                    double res) {
+    Steer st;
+    double dx = tx - fx, dy = ty - fy;
+    double d = crm_hypot(dx, dy);
+    double s, c;
+    (void)crm_atan2_sincos(dy, dx, &s, &c);
+    if (extend > d) extend = d;
+    double q = floor(extend / res);
+    int n = q < 2.0e9 ? (int)q : 2000000000;
+    st.stx = res * c;
+    st.sty = res * s;
+    double x = fx, y = fy;
+    for (int k = 0; k < n; k++) {
+        x += st.stx;
+        y += st.sty;
+    }
+    double d2 = crm_hypot(tx - x, ty - y);
+    st.snap = d2 <= res;
+    if (st.snap) {
+        x = tx;
+        y = ty;
+    }
+    st.ex = x;
+    st.ey = y;
+    st.n = n;
+    return st;
+}
+
+struct ObsList {  // SoA view of the obstacles an edge must be tested against
+    const double *ox, *oy, *r2;
+    int stride;  // element stride (1 for the shared-memory list, 4 for the global AoS rows)
+    int m;
+};
+
+// check_collision (rrt_04:1216-1230) of one edge by ONE lane: any path point within any circle.
+__device__ __forceinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
+                                               double ty, const ObsList &L) {
+    double x = fx, y = fy;
+    for (int k = 0;; k++) {
+        for (int j = 0; j < L.m; j++) {
+            double dx = L.ox[j * L.stride] - x, dy = L.oy[j * L.stride] - y;
+            if (dx * dx + dy * dy <= L.r2[j * L.stride]) return false;
+        }
+        if (k == st.n) break;
+        x += st.stx;
+        y += st.sty;
+    }
+    if (st.snap) {
+        for (int j = 0; j < L.m; j++) {
+            double dx = L.ox[j * L.stride] - tx, dy = L.oy[j * L.stride] - ty;
+            if (dx * dx + dy * dy <= L.r2[j * L.stride]) return false;
+        }
+    }
+    return true;
+}
+
+// the same verdict computed by the whole warp (lanes split the obstacles); uniform result
+__device__ __forceinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
+                                               double ty, const ObsList &L, int lane) {
+    bool hit = false;
+    for (int j = lane; j < L.m && !hit; j += 32) {
+        double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
+        double x = fx, y = fy;
+        for (int k = 0;; k++) {
+            double dx = ox - x, dy = oy - y;
+            if (dx * dx + dy * dy <= r2) { hit = true; break; }
+            if (k == st.n) break;
+            x += st.stx;
+            y += st.sty;
+        }
+        if (!hit && st.snap) {
+            double dx = ox - tx, dy = oy - ty;
+            if (dx * dx + dy * dy <= r2) hit = true;
+        }
+    }
+    return __ballot_sync(FULL, hit) == 0u;
+}
+
+__device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double x, double y) {
+    if (!p.has_play_area) return true;  // rrt_04:1207-1208
+    return !(x < p.play_area[0] || x > p.play_area[1] || y < p.play_area[2] || y > p.play_area[3]);
+}
+
+// warp argmin of (value, index): smaller value wins, ties -> smaller index (list.index(min(..)))
+__device__ __forceinline__ void warp_argmin(double &v, int &i) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        double ov = __shfl_xor_sync(FULL, v, off);
+        int oi = __shfl_xor_sync(FULL, i, off);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// per-warp shared memory
+struct WarpSmem {
+    double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];     // obstacles near the new node
+    double gcull_x[CULL_CAP], gcull_y[CULL_CAP], gcull_r2[CULL_CAP];  // obstacles near the goal
+};
+
+// layout of the dynamic shared memory of one warp:
+//   WarpSmem | near_idx[near_cap] int | near_ok[near_cap] int | nd[near_cap] double (d2, then edge cost)
+//   | ex[near_cap] | ey[near_cap] | nc[near_cap] (node cost) | bits_cur[words] | bits_next[words]
+__host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
+    size_t words = (size_t)(node_cap + 31) / 32;
+    size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 4) + words * 4 * 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+// Conservative exact cull: keep obstacle o iff |o - c| <= (reach + R_o) * (1 + 1e-9) + 1e-9.
+// Returns the list to test edges against (shared-memory survivors, or all obstacles on overflow).
+__device__ __forceinline__ ObsList cull_obstacles(const double4 *obs, int n_obs, double cx, double cy,
+                                                  double reach, double *sx, double *sy, double *sr2,
+                                                  int lane) {
+    int count = 0;
+    bool overflow = false;
+    for (int base = 0; base < n_obs; base += 32) {
+        int j = base + lane;
+        bool keep = false;
+        double4 o = make_double4(0, 0, 0, 0);
+        if (j < n_obs) {
+            o = obs[j];
+            double dx = o.x - cx, dy = o.y - cy;
+            double lim = (reach + o.z) * (1.0 + 1e-9) + 1e-9;
+            keep = dx * dx + dy * dy <= lim * lim;
+        }
+        unsigned mask = __ballot_sync(FULL, keep);
+        int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (keep) {
+            if (pos < CULL_CAP) { sx[pos] = o.x; sy[pos] = o.y; sr2[pos] = o.w; }
+            else overflow = true;
+        }
+        count += __popc(mask);
+    }
+    overflow = __any_sync(FULL, overflow);
+    __syncwarp();
+    ObsList L;
+    if (!overflow) {
+        L.ox = sx; L.oy = sy; L.r2 = sr2; L.stride = 1; L.m = count;
+    } else {
+        const double *g = reinterpret_cast<const double *>(obs);
+        L.ox = g; L.oy = g + 1; L.r2 = g + 3; L.stride = 4; L.m = n_obs;
+    }
+    return L;
+}
+
+// propagate_cost_to_leaves (rrt_04:1379-1384): level-synchronous sweeps over the parent array.
+__device__ __noinline__ void propagate(int root, int n, double2 *xy, double *cost, const int32_t *parent,
+                                       uint32_t *cur, uint32_t *nxt, int words, int lane) {
+    for (int w = lane; w < words; w += 32) { cur[w] = 0u; nxt[w] = 0u; }
+    __syncwarp();
+    if (lane == 0) cur[root >> 5] = 1u << (root & 31);
+    __syncwarp();
+    for (;;) {
+        bool any = false;
+        for (int c = lane; c < n; c += 32) {
+            int p = parent[c];
+            if (p >= 0 && ((cur[p >> 5] >> (p & 31)) & 1u)) {
+                double2 a = xy[p], b = xy[c];
+                cost[c] = cost[p] + crm_hypot(b.x - a.x, b.y - a.y);
+                atomicOr(&nxt[c >> 5], 1u << (c & 31));
+                any = true;
+            }
+        }
+        any = __any_sync(FULL, any);
+        __syncwarp();
+        if (!any) break;
+        for (int w = lane; w < words; w += 32) { cur[w] = nxt[w]; nxt[w] = 0u; }
+        __syncwarp();
+    }
+}
+
+struct Sample { double x, y; };
+
+// get_random_node / get_random_node_sobol (rrt_04:1132-1153) with a counter-based coin
+__device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, double gx,
+                                              double gy, const double2 *stream, int64_t sobol_base,
+                                              int &nongoal) {
+    Sample s;
+    if (p.sampler == RRTK_SAMPLER_STREAM) {
+        double2 v = stream[it];
+        s.x = v.x; s.y = v.y;
+        return s;
+    }
+    uint64_t k0 = rng_key(p.seed, (uint64_t)q, (uint64_t)it);
+    int coin = (int)(splitmix64(k0) % 101ull);  // random.randint(0, 100)
+    if (coin > p.goal_sample_rate) {
+        double w = p.max_rand - p.min_rand;
+        if (p.sampler == RRTK_SAMPLER_SOBOL) {
+            uint32_t q0, q1;
+            sobol2(sobol_base + nongoal, q0, q1);
+            const double recipd = 1.0 / 1073741824.0;
+            s.x = p.min_rand + ((double)q0 * recipd) * w;
+            s.y = p.min_rand + ((double)q1 * recipd) * w;
+        } else {
+            s.x = p.min_rand + w * u01(splitmix64(k0 + 1));
+            s.y = p.min_rand + w * u01(splitmix64(k0 + 2));
+        }
+        nongoal++;
+    } else {
+        s.x = gx; s.y = gy;
+    }
+    return s;
+}
+
+// search_best_goal_node (rrt_04:1284-1312).  Returns the goal node index or -1.  Uniform result.
+__device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n, const double2 *xy,
+                                      const double *cost, double gx, double gy, const ObsList &G,
+                                      int *near_idx, double *nd, int near_cap, int lane, bool &overflow) {
+    // candidates: dist <= expand_dis, each mapped to the first index with the same dist
+    int count = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        bool hit = false;
+        double d = 0.0;
+        if (i < n) {
+            double2 a = xy[i];
+            d = crm_hypot(a.x - gx, a.y - gy);
+            hit = d <= p.expand_dis;
+        }
+        unsigned mask = __ballot_sync(FULL, hit);
+        int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+        count += __popc(mask);
+    }
+    __syncwarp();
+    if (count > near_cap) { overflow = true; count = near_cap; }
+    double best_c = CUDART_INF;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < count; k += 32) {
+        double dk = nd[k];
+        int f = k;
+        for (int j = 0; j < k; j++)
+            if (nd[j] == dk) { f = j; break; }
+        int i = near_idx[f];
+        double2 a = xy[i];
+        Steer st = steer(a.x, a.y, gx, gy, CUDART_INF, p.path_resolution);
+        bool ok = edge_free_lane(a.x, a.y, st, gx, gy, G) && inside_play(p, st.ex, st.ey);
+        if (ok) {
+            double c = cost[i] + crm_hypot(a.x - gx, a.y - gy);
+            // first minimum over the candidate list; equal costs keep the earlier list entry
+            if (c < best_c) { best_c = c; best_k = k; }
+        }
+    }
+    // reduce over lanes: min cost, ties -> smaller list position
+    warp_argmin(best_c, best_k);
+    if (best_k == 0x7fffffff) return -1;
+    // map the list position back to the node index (first index with the same distance)
+    double dk = nd[best_k];
+    int f = best_k;
+    for (int j = 0; j < best_k; j++)
+        if (nd[j] == dk) { f = j; break; }
+    return near_idx[f];
+}
+
+__device__ unsigned int g_query_counter;
+
+extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
+               const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
+               const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
+               const int64_t *__restrict__ sobol_offset, double2 *xy_all, double *cost_all,
+               int32_t *parent_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+               int32_t *status_out, int32_t *trace_all, unsigned int *counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int near_cap = p.near_cap;
+    const int words = (p.node_cap + 31) / 32;
+    unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(near_cap, p.node_cap);
+    WarpSmem *ws = reinterpret_cast<WarpSmem *>(base);
+    double *nd = reinterpret_cast<double *>(base + sizeof(WarpSmem));
+    double *s_ex = nd + near_cap;
+    double *s_ey = s_ex + near_cap;
+    double *s_nc = s_ey + near_cap;
+    int *near_idx = reinterpret_cast<int *>(s_nc + near_cap);
+    int *near_ok = near_idx + near_cap;
+    uint32_t *bits_cur = reinterpret_cast<uint32_t *>(near_ok + near_cap);
+    uint32_t *bits_nxt = bits_cur + words;
+    const double res = p.path_resolution;
+    const double INF = CUDART_INF;
+
+    for (;;) {
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= (unsigned)p.n_queries) break;
+
+        const double4 sg = start_goal[q];
+        const double gx = sg.z, gy = sg.w;
+        const double4 *obs = obstacles + (size_t)q * p.obs_stride;
+        const int n_obs = n_obs_arr[q];
+        double2 *xy = xy_all + (size_t)q * p.node_cap;
+        double *cost = cost_all + (size_t)q * p.node_cap;
+        int32_t *parent = parent_all + (size_t)q * p.node_cap;
+        const double2 *stream = sample_stream ? sample_stream + (size_t)q * p.max_iter : nullptr;
+        int32_t *trace = trace_all ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
+        const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
+
+        if (lane == 0) {
+            xy[0] = make_double2(sg.x, sg.y);
+            cost[0] = 0.0;
+            parent[0] = -1;
+        }
+        __syncwarp();
+        // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
+        ObsList G = cull_obstacles(obs, n_obs, gx, gy, p.expand_dis > res ? p.expand_dis : res,
+                                   ws->gcull_x, ws->gcull_y, ws->gcull_r2, lane);
+        int n = 1, nongoal = 0, status = RRTK_Q_OK, gi = -1, it = 0;
+        bool done = false;
+
+        for (it = 0; it < p.max_iter; it++) {
+            Sample smp = draw_sample(p, (int)q, it, gx, gy, stream, sobol_base, nongoal);
+            const double rx = smp.x, ry = smp.y;
+            // ---- get_nearest_node_index (rrt_04:1196-1202) ----
+            double bd = INF;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                double2 a = xy[i];
+                double ddx = a.x - rx, ddy = a.y - ry;
+                double d = ddx * ddx + ddy * ddy;
+                if (d < bd) { bd = d; bi = i; }
+            }
+            warp_argmin(bd, bi);
+            const int ni = bi;
+            const double2 from = xy[ni];
+            // ---- steer towards the sample (rrt_04:1051-1052) ----
+            Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
+            const double nx = e0.ex, ny = e0.ey;
+            int t_status = 0, t_near = 0, t_par = -1, t_cpok = 0, t_rwok = 0, t_rwap = 0;
+            bool accept = false;
+            if (inside_play(p, nx, ny)) {
+                t_status = 1;
+                double reach = p.expand_dis > res ? p.expand_dis : res;
+                ObsList L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y,
+                                           ws->cull_r2, lane);
+                accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
+                if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
+                if (accept && p.rrt_only) {
+                    if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni; }
+                    t_status = 2; t_par = ni;
+                    n++;
+                    __syncwarp();
+                } else if (accept) {
+                    const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
+                    // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
+                    const double r2 = near_r2[n + 1];
+                    int count = 0;
+                    for (int b0 = 0; b0 < n; b0 += 32) {
+                        int i = b0 + lane;
+                        bool hit = false;
+                        double d = 0.0;
+                        if (i < n) {
+                            double2 a = xy[i];
+                            double ddx = a.x - nx, ddy = a.y - ny;
+                            d = ddx * ddx + ddy * ddy;
+                            hit = d <= r2;
+                        }
+                        unsigned mask = __ballot_sync(FULL, hit);
+                        int pos = count + __popc(mask & ((1u << lane) - 1u));
+                        if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+                        count += __popc(mask);
+                    }
+                    __syncwarp();
+                    if (count > near_cap) {
+                        status |= RRTK_Q_NEAR_OVERFLOW;
+                        done = true;
+                    } else {
+                        t_near = count;
+                        // `.index()` quirk: every hit is replaced by the first hit with the same d2
+                        for (int k = lane; k < count; k += 32) {
+                            double dk = nd[k];
+                            int f = k;
+                            for (int j = 0; j < k; j++)
+                                if (nd[j] == dk) { f = j; break; }
+                            near_ok[k] = near_idx[f];  // staged: resolved node index
+                        }
+                        __syncwarp();
+                        for (int k = lane; k < count; k += 32) near_idx[k] = near_ok[k];
+                        __syncwarp();
+                        // ---- choose_parent (rrt_04:1242-1282): one lane per candidate ----
+                        double bc = INF, bex = 0.0, bey = 0.0;
+                        int bk = 0x7fffffff;
+                        for (int k = lane; k < count; k += 32) {
+                            int i = near_idx[k];
+                            double2 a = xy[i];
+                            Steer st = steer(a.x, a.y, nx, ny, INF, res);
+                            bool ok = edge_free_lane(a.x, a.y, st, nx, ny, L) && inside_play(p, st.ex, st.ey);
+                            if (ok) {
+                                t_cpok++;
+                                double c = cost[i] + crm_hypot(nx - a.x, ny - a.y);
+                                if (c < bc) { bc = c; bk = k; bex = st.ex; bey = st.ey; }
+                            }
+                        }
+                        warp_argmin(bc, bk);  // first minimum of the cost list
+                        if (bk != 0x7fffffff) {
+                            bex = __shfl_sync(FULL, bex, bk & 31);  // k = lane (mod 32): the winner's lane
+                            bey = __shfl_sync(FULL, bey, bk & 31);
+                        }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) t_cpok += __shfl_xor_sync(FULL, t_cpok, off);
+                        if (bk != 0x7fffffff) {
+                            const int best = near_idx[bk];
+                            // the node is re-steered from the winner (rrt_04:1279): same edge as above
+                            const double cx = bex, cy = bey, ccost = bc;
+                            // ---- rewire (rrt_04:1340-1373), phase A: per-candidate edge, in parallel ----
+                            for (int k = lane; k < count; k += 32) {
+                                int i = near_idx[k];
+                                double2 a = xy[i];
+                                Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                                bool ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
+                                near_ok[k] = ok ? 1 : 0;
+                                nd[k] = ccost + crm_hypot(a.x - cx, a.y - cy);
+                                s_ex[k] = st.ex;
+                                s_ey[k] = st.ey;
+                                s_nc[k] = cost[i];
+                            }
+                            __syncwarp();
+                            // ---- phase B: apply in list order (later entries see propagated costs) ----
+                            bool dirty = false;
+                            for (int k = 0; k < count; k++) {
+                                const int i = near_idx[k];
+                                int ok = near_ok[k];
+                                double ecost = nd[k], ex = s_ex[k], ey = s_ey[k];
+                                if (ok == 2) {
+                                    // node i moved earlier in this call: redo its edge from the new position
+                                    double2 a = xy[i];
+                                    Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                                    ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) &&
+                                         inside_play(p, st.ex, st.ey);
+                                    ecost = ccost + crm_hypot(a.x - cx, a.y - cy);
+                                    ex = st.ex; ey = st.ey;
+                                }
+                                t_rwok += ok ? 1 : 0;
+                                if (!ok) continue;
+                                const double ci = dirty ? cost[i] : s_nc[k];
+                                if (ci > ecost) {
+                                    const double2 old = xy[i];
+                                    const bool moved = (old.x != ex) || (old.y != ey);
+                                    __syncwarp();
+                                    if (lane == 0) {
+                                        xy[i] = make_double2(ex, ey);
+                                        cost[i] = ecost;
+                                        parent[i] = n;
+                                    }
+                                    __syncwarp();
+                                    if (moved) {  // later repeats of i must be re-evaluated
+                                        for (int k2 = k + 1 + lane; k2 < count; k2 += 32)
+                                            if (near_idx[k2] == i) near_ok[k2] = 2;
+                                        __syncwarp();
+                                    }
+                                    t_rwap++;
+                                    propagate(i, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
+                                    dirty = true;
+                                }
+                            }
+                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; }
+                            t_status = 3; t_par = best;
+                        } else {
+                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; }
+                            t_status = 2; t_par = ni;
+                        }
+                        n++;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (trace && lane == 0) {
+                int32_t *tr = trace + (size_t)it * 8;
+                tr[0] = ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = t_cpok;
+                tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
+            }
+            if (done) { it++; break; }
+            if (p.rrt_only) {
+                // goal test on the last node (rrt_01:90-96)
+                double2 last = xy[n - 1];
+                if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
+                    Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
+                    if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane)) { gi = n - 1; it++; done = true; break; }
+                }
+            } else if (!p.search_until_max_iter) {
+                bool ovf = false;
+                gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
+                if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
+                if (gi >= 0) { it++; done = true; break; }
+            }
+        }
+        if (!done && !p.rrt_only) {
+            bool ovf = false;
+            gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
+            if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
+        }
+        if (lane == 0) {
+            n_nodes[q] = n;
+            iters_done[q] = it;
+            goal_index[q] = gi;
+            status_out[q] = status;
+        }
+        __syncwarp();
+    }
+}
+
+// generate_final_course (rrt_04:1117-1125): one thread per query walks the parent chain
+extern "C" __global__ void extract_paths_kernel(int n_queries, int node_cap, int path_cap,
+                                                const double4 *__restrict__ start_goal,
+                                                const double2 *__restrict__ xy,
+                                                const int32_t *__restrict__ parent,
+                                                const int32_t *__restrict__ goal_index,
+                                                double2 *path, int32_t *path_len) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    int gi = goal_index[q];
+    if (gi < 0) { path_len[q] = 0; return; }
+    const double2 *t = xy + (size_t)q * node_cap;
+    const int32_t *par = parent + (size_t)q * node_cap;
+    double2 *out = path + (size_t)q * path_cap;
+    int len = 0;
+    double4 sg = start_goal[q];
+    if (len < path_cap) out[len] = make_double2(sg.z, sg.w);
+    len++;
+    int i = gi;
+    for (int guard = 0; guard <= node_cap; guard++) {
+        if (len < path_cap) out[len] = t[i];
+        len++;
+        if (par[i] < 0) break;
+        i = par[i];
+    }
+    path_len[q] = len;
+}
+
+// materialise the in-kernel sampler as a stream [Q][max_iter][2]
+extern "C" __global__ void sample_stream_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
+                                                const int64_t *__restrict__ sobol_offset, double2 *out) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.n_queries) return;
+    double4 sg = start_goal[q];
+    int nongoal = 0;
+    int64_t base = sobol_offset ? sobol_offset[q] : 0;
+    for (int it = 0; it < p.max_iter; it++) {
+        Sample s = draw_sample(p, q, it, sg.z, sg.w, nullptr, base, nongoal);
+        out[(size_t)q * p.max_iter + it] = make_double2(s.x, s.y);
+    }
+}
+
+extern "C" __global__ void crmath_probe_kernel(int kind, int64_t n, const double *a, const double *b,
+                                               double *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c, r = 0.0;
+    switch (kind) {
+        case 0: r = crm_hypot(a[i], b[i]); break;
+        case 1: r = crm_atan2(a[i], b[i]); break;
+        case 2: r = crm_sin(a[i]); break;
+        case 3: r = crm_cos(a[i]); break;
+        case 4: (void)crm_atan2_sincos(a[i], b[i], &s, &c); r = s; break;
+        case 5: (void)crm_atan2_sincos(a[i], b[i], &s, &c); r = c; break;
+    }
+    out[i] = r;
+}
+
+}  // namespace rrtk
+
+// ------------------------------------------------------------------------------------------------
+// host side: launch wrappers (called by rrtk_api.cu)
+// ------------------------------------------------------------------------------------------------
+namespace rrtk {
+
+int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
+                   const int32_t *n_obs, const double *near_r2, const double *sample_stream,
+                   const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
+                   int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                   int32_t *trace, unsigned int *counter, cudaStream_t s) {
+    size_t per_warp = warp_smem_bytes(p.near_cap, p.node_cap);
+    size_t smem = per_warp * WARPS_PER_CTA;
+    if (smem > 227 * 1024) return set_error(RRTK_ERR_INVALID, "near_cap/node_cap need more than 227 KB of shared memory");
+    cudaError_t e = cudaFuncSetAttribute(rrtstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_kernel)");
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrtstar_kernel, WARPS_PER_CTA * 32, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)p.n_queries + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    long long grid = (long long)sms * per_sm;  // persistent: a multiple of the SM count
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
+    rrtstar_kernel<<<(unsigned)grid, WARPS_PER_CTA * 32, smem, s>>>(
+        p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(obstacles),
+        n_obs, near_r2, reinterpret_cast<const double2 *>(sample_stream), sobol_offset,
+        reinterpret_cast<double2 *>(xy), cost, parent, n_nodes, iters_done, goal_index, status, trace,
+        counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rrtstar_kernel launch");
+    return RRTK_OK;
+}
+
+int launch_extract_paths(int32_t nq, int32_t node_cap, int32_t path_cap, const double *start_goal,
+                         const double *xy, const int32_t *parent, const int32_t *goal_index,
+                         double *path, int32_t *path_len, cudaStream_t s) {
+    int threads = 128;
+    extract_paths_kernel<<<(nq + threads - 1) / threads, threads, 0, s>>>(
+        nq, node_cap, path_cap, reinterpret_cast<const double4 *>(start_goal),
+        reinterpret_cast<const double2 *>(xy), parent, goal_index, reinterpret_cast<double2 *>(path),
+        path_len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "extract_paths_kernel launch");
+    return RRTK_OK;
+}
+
+int launch_sample_stream(const rrtk_rrtstar_params &p, const double *start_goal,
+                         const int64_t *sobol_offset, double *out, cudaStream_t s) {
+    int threads = 64;
+    sample_stream_kernel<<<(p.n_queries + threads - 1) / threads, threads, 0, s>>>(
+        p, reinterpret_cast<const double4 *>(start_goal), sobol_offset, reinterpret_cast<double2 *>(out));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "sample_stream_kernel launch");
+    return RRTK_OK;
+}
+
+int launch_crmath_probe(int kind, int64_t n, const double *a, const double *b, double *out, cudaStream_t s) {
+    int threads = 128;
+    crmath_probe_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(kind, n, a, b, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "crmath_probe_kernel launch");
+    return RRTK_OK;
+}
+
+}  // namespace rrtk

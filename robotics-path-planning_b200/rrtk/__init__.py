@@ -1,0 +1,7 @@
+"""rrtk -- B200-native RRT-family planning kernels behind the reference's Python class API."""
+from ._lib import RrtkError, lib, LIB_PATH  # noqa: F401
+from .planners import RRT, RRTStar, Node, AreaBounds  # noqa: F401
+from .batch import RRTStarBatch, shard_range  # noqa: F401
+
+__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "RRTStarBatch", "shard_range", "RrtkError",
+           "lib", "LIB_PATH"]

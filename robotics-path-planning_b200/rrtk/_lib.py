@@ -1,0 +1,78 @@
+"""ctypes binding of librrtk.so (include/rrtk.h).  There is no CPU fallback: if the CUDA extension
+is missing or no GPU is present, every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librrtk.so")
+
+SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
+Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW = 0, 1, 2
+
+
+class RrtkError(RuntimeError):
+    pass
+
+
+class RRTStarParams(C.Structure):
+    """struct rrtk_rrtstar_params (include/rrtk.h)."""
+    _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
+                ("obs_stride", C.c_int32), ("near_cap", C.c_int32),
+                ("search_until_max_iter", C.c_int32), ("sampler", C.c_int32),
+                ("goal_sample_rate", C.c_int32), ("has_play_area", C.c_int32),
+                ("rrt_only", C.c_int32), ("expand_dis", C.c_double),
+                ("path_resolution", C.c_double), ("min_rand", C.c_double),
+                ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64)]
+
+
+_lib = None
+
+_VP = C.c_void_p
+_SIGS = {
+    "rrtk_version": (C.c_int, []),
+    "rrtk_last_error": (C.c_char_p, []),
+    "rrtk_device_count": (C.c_int, []),
+    "rrtk_sobol_fill_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP, _VP]),
+    "rrtk_sobol_fill_host": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP]),
+    "rrtk_sobol_table": (C.c_int, [C.c_int, _VP]),
+    "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 15),
+    "rrtk_rrtstar_run_host": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 14),
+    "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
+    "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
+    "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
+}
+
+EXPORTED = tuple(_SIGS)
+
+
+def lib():
+    """Load librrtk.so (built by `__graft_entry__.build()` / csrc/Makefile).  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RrtkError(f"CUDA extension not built: {LIB_PATH} is missing "
+                            "(run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "rrtk has no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "rrtk") -> None:
+    if rc != 0:
+        msg = lib().rrtk_last_error().decode("utf-8", "replace")
+        raise RrtkError(f"{what} failed (status {rc}): {msg}")
+
+
+def require_cuda():
+    """torch + a visible GPU, or raise (no CPU fallback)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RrtkError("rrtk needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    return torch

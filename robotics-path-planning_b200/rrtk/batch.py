@@ -1,0 +1,94 @@
+"""Batched planning: Q independent RRT* queries in one launch (BASELINE config 2), and the static
+partition of queries across the GPUs of one box (no per-iteration collectives)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, engine
+
+
+class RRTStarBatch:
+    """Q independent RRT* problems with the reference's per-query semantics (rrt_04:1036-1084).
+
+    starts, goals      [Q, 2]
+    obstacle_lists     length-Q sequence of [(x, y, size), ...]  (or a prepared [Q, O, 4] array of
+                       x, y, size + rr, (size + rr) ** 2 rows together with `n_obs`)
+    sampler            "sobol" | "uniform": in-kernel generator (goal coin from a counter-based RNG
+                       keyed by (seed, query, iteration); Sobol index offset `q * max_iter`)
+                       or an explicit `sample_stream` [Q, max_iter, 2].
+    """
+
+    def __init__(self, starts, goals, obstacle_lists, rand_area, expand_dis=3.0,
+                 path_resolution=0.5, goal_sample_rate=5, max_iter=500, play_area=None,
+                 robot_radius=0.0, sampler="sobol", connect_circle_dist=50.0,
+                 search_until_max_iter=True, seed=0, near_cap=256, n_obs=None,
+                 sample_stream=None, sobol_offset=None, device=None):
+        torch = _lib.require_cuda()
+        self.device = torch.device("cuda" if device is None else device)
+        starts = np.asarray(starts, dtype=np.float64).reshape(-1, 2)
+        goals = np.asarray(goals, dtype=np.float64).reshape(-1, 2)
+        self.n_queries = q = starts.shape[0]
+        self.max_iter = int(max_iter)
+        self.node_cap = self.max_iter + 1
+        if isinstance(obstacle_lists, np.ndarray) and obstacle_lists.ndim == 3 and obstacle_lists.shape[2] == 4:
+            rows = np.ascontiguousarray(obstacle_lists, dtype=np.float64)
+            counts = np.full(q, rows.shape[1], np.int32) if n_obs is None else np.asarray(n_obs, np.int32)
+        else:
+            rows, counts = engine.pack_obstacles(obstacle_lists, robot_radius)
+        self.sampler = {"stream": _lib.SAMPLER_STREAM, "sobol": _lib.SAMPLER_SOBOL,
+                        "uniform": _lib.SAMPLER_UNIFORM}["stream" if sample_stream is not None else sampler]
+        self.params = engine.make_params(q, self.max_iter, self.node_cap, rows.shape[1], expand_dis,
+                                         path_resolution, play_area, search_until_max_iter,
+                                         self.sampler, goal_sample_rate, rand_area[0], rand_area[1],
+                                         seed, near_cap)
+        # pinned host staging (inputs of the end-to-end path) + device copies
+        self.h_start_goal = torch.from_numpy(np.ascontiguousarray(np.hstack([starts, goals]))).pin_memory()
+        self.h_obstacles = torch.from_numpy(rows).pin_memory()
+        self.h_n_obs = torch.from_numpy(counts).pin_memory()
+        self.near_r2 = torch.from_numpy(
+            engine.near_r2_table(self.node_cap, connect_circle_dist, expand_dis)).to(self.device)
+        if sobol_offset is None:
+            sobol_offset = np.arange(q, dtype=np.int64) * self.max_iter
+        self.sobol_offset = torch.from_numpy(np.asarray(sobol_offset, dtype=np.int64)).to(self.device)
+        self.sample_stream = None
+        if sample_stream is not None:
+            ss = np.ascontiguousarray(np.asarray(sample_stream, dtype=np.float64).reshape(q, self.max_iter, 2))
+            self.sample_stream = torch.from_numpy(ss).to(self.device)
+        self.upload()
+        self.result = None
+
+    # ---- data movement ----
+    def upload(self):
+        """Host -> device copy of the scenario (start/goal, obstacle rows, counts)."""
+        self.start_goal = self.h_start_goal.to(self.device, non_blocking=True)
+        self.obstacles = self.h_obstacles.to(self.device, non_blocking=True)
+        self.n_obs = self.h_n_obs.to(self.device, non_blocking=True)
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_start_goal, self.h_obstacles, self.h_n_obs))
+
+    # ---- compute ----
+    def run(self, want_trace=False):
+        """Enqueue the planning kernel on the current stream; results stay on the GPU."""
+        self.result = engine.run_dev(self.params, self.start_goal, self.obstacles, self.n_obs,
+                                     self.near_r2, self.sample_stream, self.sobol_offset,
+                                     want_trace=want_trace,
+                                     out=self.result if (self.result is not None and not want_trace) else None)
+        return self.result
+
+    def planning(self, animation=False):
+        """Paths for every query: list of `[[x, y], ...]` (goal -> start) or None."""
+        return self.run().paths()
+
+    def materialised_stream(self):
+        """The samples the in-kernel sampler produces, [Q, max_iter, 2] (for the CPU oracle)."""
+        if self.sample_stream is not None:
+            return self.sample_stream
+        return engine.sample_stream_dev(self.params, self.start_goal, self.sobol_offset)
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous block partition of `n_items` independent queries over `world_size` ranks."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,146 @@
+"""Host-side driver of the batched RRT / RRT* kernel (rrtk_rrtstar_run_dev).
+
+Everything that depends only on the scenario -- not on the tree -- is evaluated here on the host with
+the same Python float operations the reference uses, then handed to the kernel as tables:
+  * per obstacle  R2 = (size + robot_radius) ** 2            (rrt_04:1227)
+  * per tree size r2[k] = min(ccd * sqrt(log(k) / k), expand_dis) ** 2, k = len(node_list) + 1
+                                                             (rrt_04:1329-1336)
+The tree itself (nearest, steer, collision, near, choose_parent, rewire, goal search) is computed on
+the GPU only."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+_NEAR_R2_CACHE: dict = {}
+
+
+def near_r2_table(node_cap: int, connect_circle_dist: float, expand_dis) -> np.ndarray:
+    """near_r2[k] for k = 0 .. node_cap + 1 (index = number of nodes + 1); [0] is unused."""
+    key = (int(node_cap), float(connect_circle_dist), None if expand_dis is None else float(expand_dis))
+    tab = _NEAR_R2_CACHE.get(key)
+    if tab is None:
+        tab = np.zeros(node_cap + 2, dtype=np.float64)
+        for k in range(1, node_cap + 2):
+            r = connect_circle_dist * math.sqrt(math.log(k) / k)
+            if expand_dis is not None:
+                r = min(r, expand_dis)
+            tab[k] = r ** 2
+        _NEAR_R2_CACHE[key] = tab
+    return tab
+
+
+def pack_obstacles(obstacle_lists, robot_radius: float, stride: int | None = None):
+    """obstacle_lists: sequence (per query) of iterables of (x, y, size).
+    Returns (rows [Q, stride, 4] float64 = x, y, size + rr, (size + rr) ** 2 ; n_obs [Q] int32)."""
+    q = len(obstacle_lists)
+    counts = [len(o) for o in obstacle_lists]
+    stride = max(max(counts, default=0), 1) if stride is None else stride
+    rows = np.zeros((q, stride, 4), dtype=np.float64)
+    for i, obs in enumerate(obstacle_lists):
+        for j, (ox, oy, size) in enumerate(obs):
+            rows[i, j, 0] = ox
+            rows[i, j, 1] = oy
+            rows[i, j, 2] = size + robot_radius
+            rows[i, j, 3] = (size + robot_radius) ** 2  # Python pow, as the reference evaluates it
+    return rows, np.asarray(counts, dtype=np.int32)
+
+
+@dataclass
+class BatchResult:
+    """Device-resident result of a batched run (torch tensors on the GPU)."""
+    xy: "object"          # [Q, node_cap, 2] float64
+    cost: "object"        # [Q, node_cap]    float64
+    parent: "object"      # [Q, node_cap]    int32, -1 = root
+    n_nodes: "object"     # [Q] int32
+    iters_done: "object"  # [Q] int32
+    goal_index: "object"  # [Q] int32, -1 = no path
+    status: "object"      # [Q] int32 (RRTK_Q_* bits)
+    trace: "object"       # [Q, max_iter, 8] int32 or None
+    start_goal: "object"  # [Q, 4] float64
+
+    def paths_device(self, path_cap: int | None = None):
+        """generate_final_course for every query on the GPU -> (path [Q, path_cap, 2], length [Q])."""
+        torch = _lib.require_cuda()
+        q, cap = self.parent.shape
+        path_cap = cap + 1 if path_cap is None else path_cap
+        path = torch.empty((q, path_cap, 2), dtype=torch.float64, device=self.xy.device)
+        plen = torch.empty((q,), dtype=torch.int32, device=self.xy.device)
+        _lib.check(_lib.lib().rrtk_extract_paths_dev(
+            q, cap, path_cap, self.start_goal.data_ptr(), self.xy.data_ptr(), self.parent.data_ptr(),
+            self.goal_index.data_ptr(), path.data_ptr(), plen.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "rrtk_extract_paths_dev")
+        return path, plen
+
+    def paths(self):
+        """list (per query) of `[[x, y], ...]` goal -> start, or None (what `planning()` returns)."""
+        path, plen = self.paths_device()
+        path = path.cpu().numpy()
+        plen = plen.cpu().numpy()
+        return [None if n == 0 else path[i, :n].tolist() for i, n in enumerate(plen)]
+
+
+def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_resolution,
+                play_area=None, search_until_max_iter=True, sampler=_lib.SAMPLER_STREAM,
+                goal_sample_rate=5, min_rand=0.0, max_rand=0.0, seed=0, near_cap=256,
+                rrt_only=False) -> _lib.RRTStarParams:
+    p = _lib.RRTStarParams()
+    p.n_queries, p.max_iter, p.node_cap = int(n_queries), int(max_iter), int(node_cap)
+    p.obs_stride, p.near_cap = int(obs_stride), int(near_cap)
+    p.search_until_max_iter = int(bool(search_until_max_iter))
+    p.sampler, p.goal_sample_rate = int(sampler), int(goal_sample_rate)
+    p.has_play_area = 0 if play_area is None else 1
+    if play_area is not None:
+        for i in range(4):
+            p.play_area[i] = float(play_area[i])
+    p.rrt_only = int(bool(rrt_only))
+    p.expand_dis, p.path_resolution = float(expand_dis), float(path_resolution)
+    p.min_rand, p.max_rand = float(min_rand), float(max_rand)
+    p.seed = int(seed) & ((1 << 64) - 1)
+    return p
+
+
+def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample_stream=None,
+            sobol_offset=None, want_trace=False, out: BatchResult | None = None) -> BatchResult:
+    """Launch the planning kernel on device tensors (float64 / int32 / int64, contiguous, CUDA)."""
+    torch = _lib.require_cuda()
+    dev = start_goal.device
+    q, cap = p.n_queries, p.node_cap
+    for t, dt in ((start_goal, torch.float64), (obstacles, torch.float64), (n_obs, torch.int32)):
+        if t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
+            raise _lib.RrtkError("run_dev: tensors must be contiguous CUDA tensors of the documented dtype")
+    if out is None:
+        out = BatchResult(
+            xy=torch.empty((q, cap, 2), dtype=torch.float64, device=dev),
+            cost=torch.empty((q, cap), dtype=torch.float64, device=dev),
+            parent=torch.empty((q, cap), dtype=torch.int32, device=dev),
+            n_nodes=torch.empty((q,), dtype=torch.int32, device=dev),
+            iters_done=torch.empty((q,), dtype=torch.int32, device=dev),
+            goal_index=torch.empty((q,), dtype=torch.int32, device=dev),
+            status=torch.empty((q,), dtype=torch.int32, device=dev),
+            trace=torch.zeros((q, p.max_iter, 8), dtype=torch.int32, device=dev) if want_trace else None,
+            start_goal=start_goal)
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    rc = _lib.lib().rrtk_rrtstar_run_dev(
+        C.byref(p), ptr(start_goal), ptr(obstacles), ptr(n_obs), ptr(near_r2), ptr(sample_stream),
+        ptr(sobol_offset), ptr(out.xy), ptr(out.cost), ptr(out.parent), ptr(out.n_nodes),
+        ptr(out.iters_done), ptr(out.goal_index), ptr(out.status), ptr(out.trace),
+        torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "rrtk_rrtstar_run_dev")
+    return out
+
+
+def sample_stream_dev(p: _lib.RRTStarParams, start_goal, sobol_offset=None):
+    """Materialise the in-kernel sampler: [Q, max_iter, 2] float64 on the GPU."""
+    torch = _lib.require_cuda()
+    out = torch.empty((p.n_queries, p.max_iter, 2), dtype=torch.float64, device=start_goal.device)
+    rc = _lib.lib().rrtk_sample_stream_dev(C.byref(p), start_goal.data_ptr(),
+                                           None if sobol_offset is None else sobol_offset.data_ptr(),
+                                           out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "rrtk_sample_stream_dev")
+    return out

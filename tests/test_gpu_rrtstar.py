@@ -1,0 +1,257 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / the reference-shaped Python
+classes, against the oracle on identical inputs.
+
+Chain of evidence
+  reference  == oracle[libm]   bit for bit on every fixture          (tests/test_oracle_golden.py)
+  oracle[cr] == oracle[libm]   bit for bit except logged sub-ulp ties (tests/test_oracle_golden.py)
+  GPU        == oracle[cr]     bit for bit, every array, every iteration trace  (this file)
+so wherever the cr arithmetic reproduces the fixture, the GPU is also compared with the reference's
+own output directly.  Bar: positions, costs, parents, traces and paths are compared with
+array_equal -- no tolerance."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names, load_golden, scenario_args
+
+pytestmark = pytest.mark.gpu
+
+RRT04 = golden_names("rrt04_")
+CR_EXACT = [n for n in RRT04 if n != "rrt04_c2_o256_800"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+def _planner(m):
+    import rrtk
+    return rrtk.RRTStar(m["start"], m["goal"], m["obstacle_list"], m["rand_area"], m["expand_dis"],
+                        m["path_resolution"], m["goal_sample_rate"], m["max_iter"], m["play_area"],
+                        m["robot_radius"], m["sobol_sampler"], m["connect_circle_dist"],
+                        m["search_until_max_iter"])
+
+
+def _pad(stream, n):
+    stream = np.asarray(stream, dtype=np.float64).reshape(-1, 2)
+    if len(stream) < n:
+        stream = np.vstack([stream, np.zeros((n - len(stream), 2))])
+    return stream
+
+
+@pytest.mark.parametrize("name", RRT04)
+def test_rrtstar_bitwise_vs_oracle_cr(name, torch_cuda, oracle_lib):
+    O = oracle_lib
+    g, m = load_golden(name)
+    p, obs = O.make_params(*scenario_args(m), math_mode=O.MATH_CR)
+    ref = O.rrtstar_run(p, obs, g["stream"])
+    rrt = _planner(m)
+    path = rrt.planning(animation=False, sample_stream=_pad(g["stream"], m["max_iter"]), want_trace=True)
+    a = rrt.tree_arrays()
+    assert rrt.iters_done == ref["iters_done"]
+    assert np.array_equal(rrt.trace, ref["trace"]), "iteration traces differ"
+    assert len(a["x"]) == ref["n"]
+    assert np.array_equal(a["parent"], ref["parent"])
+    assert np.array_equal(a["x"], ref["x"]) and np.array_equal(a["y"], ref["y"])
+    assert np.array_equal(a["cost"], ref["cost"])
+    assert (rrt.goal_index if rrt.goal_index is not None else -1) == ref["goal_index"]
+    assert path == O.final_course(ref, m["goal"])
+
+
+@pytest.mark.parametrize("name", CR_EXACT)
+def test_rrtstar_bitwise_vs_reference_fixture(name, torch_cuda):
+    """Directly against what the unmodified reference produced (no oracle in between)."""
+    g, m = load_golden(name)
+    rrt = _planner(m)
+    path = rrt.planning(animation=False, sample_stream=_pad(g["stream"], m["max_iter"]))
+    a = rrt.tree_arrays()
+    assert rrt.iters_done == m["iters"]
+    assert np.array_equal(a["parent"], g["parent"])
+    assert np.array_equal(a["x"], g["x"]) and np.array_equal(a["y"], g["y"])
+    assert np.array_equal(a["cost"], g["cost"])
+    assert np.array_equal(np.array(path, float), g["path"])
+    # Node objects as the reference exposes them
+    nl = rrt.node_list
+    assert nl[0].parent is None and all(n.parent is nl[p] for n, p in zip(nl[1:], a["parent"][1:]))
+
+
+def test_planning_with_own_sampler_matches_reference(torch_cuda):
+    """No injected stream: the planner draws the goal coins from `random` and the Sobol points from the
+    GPU generator exactly like the reference did after random.seed(0) (rrt04_c1_sobol_500)."""
+    import random
+    g, m = load_golden("rrt04_c1_sobol_500")
+    random.seed(m["seed"])
+    rrt = _planner(m)
+    path = rrt.planning(animation=False)
+    assert np.array_equal(rrt.sample_stream, g["stream"])
+    assert rrt.sobol_inter_ == m["sobol_inter"]
+    assert np.array_equal(rrt.tree_arrays()["parent"], g["parent"])
+    assert np.array_equal(np.array(path, float), g["path"])
+    assert len(path) == 24 and len(rrt.node_list) == 152          # SURVEY.md 8c anchor
+    assert rrt.node_list[-1].cost == 10.096284324107767
+
+
+def _random_scenario(rng, n_obs, max_iter, play=False, rr=0.0, expand=1.0, res=0.1):
+    obs = []
+    while len(obs) < n_obs:
+        x, y = rng.uniform(-2, 15, 2)
+        r = rng.uniform(0.1, 0.5)
+        if min(np.hypot(x, y), np.hypot(x - 13, y - 13)) > r + rr + 0.5:
+            obs.append((float(x), float(y), float(r)))
+    goal_rate = 5
+    stream = rng.uniform(-2, 15, (max_iter, 2))
+    coin = rng.integers(0, 101, max_iter) <= goal_rate
+    stream[coin] = (13.0, 13.0)
+    return dict(start=[0.0, 0.0], goal=[13.0, 13.0], obstacle_list=obs, rand_area=[-2, 15],
+                expand_dis=expand, path_resolution=res, goal_sample_rate=goal_rate, max_iter=max_iter,
+                play_area=[-1.0, 14.0, -1.0, 14.0] if play else None, robot_radius=rr,
+                connect_circle_dist=50.0, search_until_max_iter=True, sobol_sampler=False), stream
+
+
+@pytest.mark.parametrize("seed,n_obs,max_iter,play,rr,expand,res", [
+    (1, 0, 300, False, 0.0, 1.0, 0.1),      # no obstacles at all
+    (2, 40, 500, True, 0.3, 1.0, 0.1),
+    (3, 256, 700, False, 0.0, 1.0, 0.1),
+    (4, 100, 400, False, 0.2, 3.0, 0.5),    # reference defaults: expand 3.0 / resolution 0.5
+    (5, 300, 300, True, 0.1, 2.0, 0.25),    # > CULL_CAP survivors possible -> full-list fallback
+    (6, 64, 1500, False, 0.0, 0.5, 0.1),
+])
+def test_rrtstar_random_scenarios_bitwise(seed, n_obs, max_iter, play, rr, expand, res, torch_cuda, oracle_lib):
+    O = oracle_lib
+    rng = np.random.default_rng(seed)
+    m, stream = _random_scenario(rng, n_obs, max_iter, play, rr, expand, res)
+    p, obs = O.make_params(*scenario_args(m), math_mode=O.MATH_CR)
+    if n_obs == 0:
+        obs = np.zeros((0, 3))
+    ref = O.rrtstar_run(p, obs, stream)
+    rrt = _planner(m)
+    path = rrt.planning(animation=False, sample_stream=stream, want_trace=True)
+    a = rrt.tree_arrays()
+    assert np.array_equal(rrt.trace, ref["trace"])
+    assert np.array_equal(a["parent"], ref["parent"])
+    assert np.array_equal(a["x"], ref["x"]) and np.array_equal(a["y"], ref["y"])
+    assert np.array_equal(a["cost"], ref["cost"])
+    assert path == O.final_course(ref, m["goal"])
+
+
+def test_batch_matches_single_queries_and_oracle(torch_cuda, oracle_lib):
+    """Q queries in one launch (in-kernel Sobol sampler + counter-based coins) == each query alone ==
+    oracle[cr] fed the materialised stream; also checks the host restatement of the coins."""
+    import rrtk
+    from rrtk import sampling
+    O = oracle_lib
+    Q, iters, n_obs = 24, 400, 96
+    rng = np.random.default_rng(7)
+    obstacle_lists, starts, goals = [], [], []
+    for q in range(Q):
+        m, _ = _random_scenario(np.random.default_rng(100 + q), n_obs, iters)
+        obstacle_lists.append(m["obstacle_list"])
+        starts.append(m["start"]); goals.append(m["goal"])
+    b = rrtk.RRTStarBatch(starts, goals, obstacle_lists, [-2, 15], expand_dis=1.0, path_resolution=0.1,
+                          goal_sample_rate=5, max_iter=iters, sampler="sobol", seed=99)
+    res = b.run(want_trace=True)
+    stream = b.materialised_stream().cpu().numpy()
+    n_nodes = res.n_nodes.cpu().numpy()
+    xy = res.xy.cpu().numpy(); cost = res.cost.cpu().numpy(); parent = res.parent.cpu().numpy()
+    trace = res.trace.cpu().numpy(); gi = res.goal_index.cpu().numpy()
+    assert (res.status.cpu().numpy() == 0).all()
+    paths = res.paths()
+    for q in range(Q):
+        coins = sampling.kernel_coins(99, q, iters, 5)
+        assert np.array_equal(np.all(stream[q] == np.array(goals[q]), axis=1), coins)
+        nong = ~coins
+        pts = O.sobol_fill(2, q * iters, int(nong.sum()))
+        assert np.array_equal(stream[q][nong], -2 + pts * 17)
+        p, obs = O.make_params(starts[q], goals[q], obstacle_lists[q], 1.0, 0.1, iters, None, 0.0, 50.0, True,
+                               math_mode=O.MATH_CR)
+        ref = O.rrtstar_run(p, obs, stream[q])
+        n = ref["n"]
+        assert n_nodes[q] == n
+        assert np.array_equal(trace[q], ref["trace"])
+        assert np.array_equal(parent[q, :n], ref["parent"])
+        assert np.array_equal(xy[q, :n, 0], ref["x"]) and np.array_equal(xy[q, :n, 1], ref["y"])
+        assert np.array_equal(cost[q, :n], ref["cost"])
+        assert gi[q] == ref["goal_index"]
+        assert paths[q] == O.final_course(ref, goals[q])
+
+
+def test_rrt_basic_bitwise(torch_cuda, oracle_lib):
+    """Basic RRT loop (rrt_01:71-101) against the oracle, with and without a play area."""
+    import rrtk
+    O = oracle_lib
+    for seed, play in ((11, False), (12, True)):
+        m, stream = _random_scenario(np.random.default_rng(seed), 60, 600, play, 0.2, 1.0, 0.1)
+        p, obs = O.make_params(*scenario_args(m), math_mode=O.MATH_CR)
+        ref = O.rrt_run(p, obs, stream)
+        rrt = rrtk.RRT(m["start"], m["goal"], m["obstacle_list"], m["rand_area"], m["expand_dis"],
+                       m["path_resolution"], m["goal_sample_rate"], m["max_iter"], m["play_area"],
+                       m["robot_radius"])
+        path = rrt.planning(animation=False, sample_stream=stream)
+        a = rrt.tree_arrays()
+        assert rrt.iters_done == ref["iters_done"]
+        assert np.array_equal(a["parent"], ref["parent"])
+        assert np.array_equal(a["x"], ref["x"]) and np.array_equal(a["y"], ref["y"])
+        assert (path is None) == (ref["goal_index"] < 0)
+        if path is not None:
+            assert path == O.final_course(ref, m["goal"])
+
+
+def test_crmath_on_device(torch_cuda):
+    """The device build of csrc/crmath.h against the mpmath fixture (tests/golden/crmath.npz)."""
+    torch = torch_cuda
+    from rrtk import _lib
+    g = np.load(os.path.join(GOLDEN, "crmath.npz"))
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+
+    def probe(kind, a, b=None):
+        ta = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        tb = None if b is None else torch.from_numpy(np.ascontiguousarray(b)).cuda()
+        out = torch.empty_like(ta)
+        _lib.check(L.rrtk_crmath_probe_dev(kind, ta.numel(), ta.data_ptr(), None if tb is None else tb.data_ptr(),
+                                           out.data_ptr(), s))
+        return out.cpu().numpy()
+    assert np.array_equal(probe(0, g["y"], g["x"]), g["hypot"])
+    assert np.array_equal(probe(1, g["y"], g["x"]), g["atan2"])
+    assert np.array_equal(probe(4, g["y"], g["x"]), g["sin_t"])
+    assert np.array_equal(probe(5, g["y"], g["x"]), g["cos_t"])
+    assert np.array_equal(probe(2, g["arg"]), g["sin"])
+    assert np.array_equal(probe(3, g["arg"]), g["cos"])
+
+
+def test_sobol_device(torch_cuda, oracle_lib):
+    from rrtk import sampling
+    O = oracle_lib
+    for dim, first, count in ((2, 0, 20000), (3, 12345, 5000), (40, 7, 300), (1, 2 ** 29, 64)):
+        assert np.array_equal(sampling.sobol_points(dim, first, count), O.sobol_fill(dim, first, count))
+    assert sampling.sobol_points(2, 1000, 1)[0].tolist() == [0.2197265625, 0.0966796875]
+    assert sampling.sobol_points(2, 0, 0).shape == (0, 2)
+
+
+def test_host_buffer_entry_point(torch_cuda, oracle_lib):
+    """rrtk_rrtstar_run_host: plain host pointers in, host arrays out (the end-to-end C-ABI call)."""
+    from rrtk import _lib, engine
+    O = oracle_lib
+    m, stream = _random_scenario(np.random.default_rng(21), 50, 300)
+    rows, n_obs = engine.pack_obstacles([m["obstacle_list"]], 0.0)
+    cap = m["max_iter"] + 1
+    p = engine.make_params(1, m["max_iter"], cap, rows.shape[1], 1.0, 0.1)
+    near = engine.near_r2_table(cap, 50.0, 1.0)
+    sg = np.array([[0.0, 0.0, 13.0, 13.0]])
+    xy = np.zeros((1, cap, 2)); cost = np.zeros((1, cap)); parent = np.zeros((1, cap), np.int32)
+    nn = np.zeros(1, np.int32); itd = np.zeros(1, np.int32); gi = np.zeros(1, np.int32); st = np.zeros(1, np.int32)
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    rc = _lib.lib().rrtk_rrtstar_run_host(C.byref(p), ptr(sg), ptr(rows), ptr(n_obs), ptr(near),
+                                          ptr(np.ascontiguousarray(stream)), None, ptr(xy), ptr(cost),
+                                          ptr(parent), ptr(nn), ptr(itd), ptr(gi), ptr(st), None)
+    _lib.check(rc)
+    po, obs = O.make_params(*scenario_args(m), math_mode=O.MATH_CR)
+    ref = O.rrtstar_run(po, obs, stream)
+    n = ref["n"]
+    assert nn[0] == n and np.array_equal(parent[0, :n], ref["parent"])
+    assert np.array_equal(xy[0, :n, 0], ref["x"]) and np.array_equal(cost[0, :n], ref["cost"])
