@@ -134,6 +134,24 @@ RRTK_API int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *
                            const int64_t *sobol_offset, double *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.
+ *   rrtk_nearest_f32_dev: get_nearest_node_index (rrt_04:1196-1202, rrt_07:1210-1214) for B samples in
+ *     one pass over the n nodes; idx[b] = argmin_i |xy[i] - samples[b]|^2 with the LOWEST index on exact
+ *     ties, d2[b] = that squared distance (FP32).  8*n bytes of HBM traffic per pass of <= 8 samples.
+ *   rrtk_near_f32_dev: find_near_nodes (rrt_04:1314-1338, rrt_07:1137-1143): all i with d2 <= r2, written
+ *     unordered to out_idx[0 .. min(*out_n, cap)); *out_n is the total hit count.
+ *   xy must be 16-byte aligned; scratch is B uint64 of device memory.
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_nearest_f32_dev(const float *xy, int64_t n, const float *samples, int32_t n_samples,
+                                  uint64_t *scratch, int32_t *idx, float *d2, void *stream);
+RRTK_API int rrtk_near_f32_dev(const float *xy, int64_t n, float cx, float cy, float r2, int32_t *out_idx,
+                               int32_t cap, int32_t *out_n, void *stream);
+
+/* FMA-loop pipe probes (roofline denominators): blocks x 256 threads x 8 chains x iters FMAs.
+ * fp64 != 0 -> DFMA, else FFMA.  flops = blocks * 256 * 8 * 2 * iters. */
+RRTK_API int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)

@@ -113,18 +113,20 @@ def rrtstar_run(params: Params, obs: np.ndarray, stream: np.ndarray, want_trace=
     nv = C.c_int64()
     ties = np.zeros((max(tie_cap, 1), 3), dtype=np.float64)
     nt = C.c_int64()
+    work = np.zeros(2, dtype=np.int64)
     lib().orc_rrtstar_run(C.byref(params), _p(obs, C.c_double), _p(stream, C.c_double),
                           _p(x, C.c_double), _p(y, C.c_double), _p(cost, C.c_double),
                           _p(parent, C.c_int32), C.byref(n), C.byref(it), C.byref(gi),
                           _p(trace, C.c_int32) if want_trace else None,
                           _p(verd, C.c_uint8) if verdict_cap else None, C.c_int64(verdict_cap),
                           C.byref(nv), _p(ties, C.c_double) if tie_cap else None, C.c_int64(tie_cap),
-                          C.byref(nt))
+                          C.byref(nt), _p(work, C.c_int64))
     k = n.value
     return dict(x=x[:k], y=y[:k], cost=cost[:k], parent=parent[:k], n=k, iters_done=it.value,
                 goal_index=gi.value, trace=None if trace is None else trace[:it.value],
                 verdicts=verd[:min(nv.value, verdict_cap)], n_verdicts=nv.value,
-                ties=ties[:min(nt.value, tie_cap)], n_ties=nt.value)
+                ties=ties[:min(nt.value, tie_cap)], n_ties=nt.value,
+                work_pairs=int(work[0]), work_scan=int(work[1]))
 
 
 def rrt_run(params: Params, obs: np.ndarray, stream: np.ndarray):

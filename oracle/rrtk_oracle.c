@@ -191,6 +191,8 @@ typedef struct {
     double *ties;
     int64_t n_ties, tie_cap;
     int cur_it;
+    /* work counters: point-circle tests and node-distance evaluations the reference performs */
+    int64_t work_pairs, work_scan;
 } orc_tree_t;
 
 #define ORC_TIE_EPS 1e-6
@@ -247,6 +249,7 @@ static int collision_free(orc_tree_t *t) {
     for (int o = 0; o < p->n_obs && ok; o++) {
         double ox = t->obs[3 * o], oy = t->obs[3 * o + 1], size = t->obs[3 * o + 2];
         double mn = INFINITY;
+        t->work_pairs += t->npts;
         for (int k = 0; k < t->npts; k++) {
             double dx = ox - t->px[k], dy = oy - t->py[k];
             double dd = dx * dx + dy * dy;
@@ -310,7 +313,8 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
                                double *x, double *y, double *cost, int32_t *parent,
                                int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
                                int32_t *trace, uint8_t *verdicts, int64_t verdict_cap,
-                               int64_t *n_verdicts, double *ties, int64_t tie_cap, int64_t *n_ties) {
+                               int64_t *n_verdicts, double *ties, int64_t tie_cap, int64_t *n_ties,
+                               int64_t *work /* [2] or NULL */) {
     orc_tree_t *t = (orc_tree_t *)calloc(1, sizeof(orc_tree_t));
     int cap = p->max_iter + 1;
     double *dist = (double *)malloc(sizeof(double) * cap);
@@ -334,6 +338,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
             else if (d < dsecond) dsecond = d;
         }
         if (t->ties && dsecond < INFINITY && dsecond != dmin && dmin > 0.0) log_tie(t, 5, (dsecond - dmin) / dmin);
+        t->work_scan += n;
         double nx, ny;
         steer(t, x[ni], y[ni], rx, ry, p->expand_dis, &nx, &ny);
         double ncost = cost[ni] + orc_hypot(nx - x[ni], ny - y[ni]);
@@ -346,6 +351,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
                 double r = p->connect_circle_dist * sqrt(log(nnode) / nnode);
                 if (p->expand_dis < r) r = p->expand_dis;
                 double r2 = sq_libm(r); /* per-iteration constant: host libm in the product too */
+                t->work_scan += n;
                 for (int i = 0; i < n; i++) dist[i] = sq(p->math_mode, x[i] - nx) + sq(p->math_mode, y[i] - ny);
                 for (int i = 0; i < n; i++) {
                     if (t->ties && r2 > 0.0) log_tie(t, 2, (dist[i] - r2) / r2);
@@ -412,6 +418,7 @@ ORC_EXPORT int orc_rrtstar_run(const orc_params_t *p, const double *obs, const d
     *n_nodes = t->n; *iters_done = it; *goal_index = gi;
     if (n_verdicts) *n_verdicts = t->n_verdicts;
     if (n_ties) *n_ties = t->n_ties;
+    if (work) { work[0] = t->work_pairs; work[1] = t->work_scan; }
     free(dist); free(near); free(costs); free(t);
     return 0;
 }

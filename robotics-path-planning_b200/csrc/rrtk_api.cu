@@ -35,6 +35,11 @@ int launch_sample_stream(const rrtk_rrtstar_params &p, const double *start_goal,
                          const int64_t *sobol_offset, double *out, cudaStream_t s);
 int launch_crmath_probe(int kind, int64_t n, const double *a, const double *b, double *out, cudaStream_t s);
 int launch_sobol_fill(int dim, int64_t first, int64_t count, double *out, cudaStream_t s);
+int launch_nearest(const float *xy, long long n, const float *samples, int B, unsigned long long *scratch,
+                   int *idx, float *d2, cudaStream_t s);
+int launch_near(const float *xy, long long n, float cx, float cy, float r2, int *out_idx, int cap, int *out_n,
+                cudaStream_t s);
+int launch_fma_peak(int fp64, int iters, int blocks, void *out, cudaStream_t s);
 
 static int check_params(const rrtk_rrtstar_params *p) {
     if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
@@ -150,6 +155,27 @@ int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b,
     if (n == 0) return RRTK_OK;
     if (!a || !out || (!b && (kind == 0 || kind == 1 || kind >= 4))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_crmath_probe(kind, n, a, b, out, (cudaStream_t)stream);
+}
+
+int rrtk_nearest_f32_dev(const float *xy, int64_t n, const float *samples, int32_t n_samples,
+                         uint64_t *scratch, int32_t *idx, float *d2, void *stream) {
+    if (n < 1 || n > 0xfffffffell || n_samples < 1) return set_error(RRTK_ERR_INVALID, "need 1 <= n < 2^32 and n_samples >= 1");
+    if (!xy || !samples || !scratch || !idx || !d2) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)xy & 15) return set_error(RRTK_ERR_INVALID, "xy must be 16-byte aligned");
+    return launch_nearest(xy, n, samples, n_samples, (unsigned long long *)scratch, idx, d2, (cudaStream_t)stream);
+}
+
+int rrtk_near_f32_dev(const float *xy, int64_t n, float cx, float cy, float r2, int32_t *out_idx, int32_t cap,
+                      int32_t *out_n, void *stream) {
+    if (n < 1 || n > 0x7fffffffll || cap < 0) return set_error(RRTK_ERR_INVALID, "need 1 <= n < 2^31 and cap >= 0");
+    if (!xy || !out_n || (cap > 0 && !out_idx)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)xy & 15) return set_error(RRTK_ERR_INVALID, "xy must be 16-byte aligned");
+    return launch_near(xy, n, cx, cy, r2, out_idx, cap, out_n, (cudaStream_t)stream);
+}
+
+int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *out, void *stream) {
+    if (iters < 1 || blocks < 1 || !out) return set_error(RRTK_ERR_INVALID, "bad iters/blocks/out");
+    return launch_fma_peak(fp64, iters, blocks, out, (cudaStream_t)stream);
 }
 
 // ---- host-buffer wrapper: the end-to-end path (H2D, kernel, D2H inside the call) ----

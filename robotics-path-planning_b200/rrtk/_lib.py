@@ -42,6 +42,9 @@ _SIGS = {
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
+    "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "rrtk_near_f32_dev": (C.c_int, [_VP, C.c_int64, C.c_float, C.c_float, C.c_float, _VP, C.c_int32, _VP, _VP]),
+    "rrtk_fma_peak_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _VP, _VP]),
 }
 
 EXPORTED = tuple(_SIGS)
