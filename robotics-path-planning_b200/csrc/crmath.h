@@ -26,13 +26,22 @@
 #ifdef __CUDACC__
 #define CRM_FN static __device__ __forceinline__
 #define CRM_NOINLINE static __device__ __noinline__
-#define CRM_CONST static __device__ __constant__ const
+#define CRM_CONST static __device__ __constant__ const  /* uniform index: constant cache */
+#define CRM_TABLE static __device__ const               /* per-lane index: global memory / L1 */
+#define CRM_ROLLED _Pragma("unroll 1")
+CRM_FN long long crm_d2ll(double x) { return __double_as_longlong(x); }
+CRM_FN double crm_ll2d(long long v) { return __longlong_as_double(v); }
 #else
 #include <float.h>
 #include <math.h>
+#include <string.h>
 #define CRM_FN static inline
 #define CRM_NOINLINE static
 #define CRM_CONST static const
+#define CRM_TABLE static const
+#define CRM_ROLLED
+CRM_FN long long crm_d2ll(double x) { long long v; memcpy(&v, &x, 8); return v; }
+CRM_FN double crm_ll2d(long long v) { double x; memcpy(&x, &v, 8); return x; }
 #endif
 
 #include "crmath_consts.h"
@@ -86,29 +95,41 @@ CRM_FN crm_dd crm_mul_d(crm_dd a, double b) {
     return crm_fast_two_sum(p.hi, p.lo);
 }
 CRM_FN crm_dd crm_div(crm_dd a, crm_dd b) {
-    double q1 = a.hi / b.hi;
+    /* quotient digits from one reciprocal; each digit is corrected by the exact residual */
+    double inv = 1.0 / b.hi;
+    double q1 = a.hi * inv;
     crm_dd r = crm_sub(a, crm_mul_d(b, q1));
-    double q2 = r.hi / b.hi;
+    double q2 = r.hi * inv;
     r = crm_sub(r, crm_mul_d(b, q2));
-    double q3 = r.hi / b.hi;
+    double q3 = r.hi * inv;
     crm_dd q = crm_fast_two_sum(q1, q2);
     return crm_add_d(q, q3);
 }
 
 /* ---- math.hypot of CPython (correctly rounded in practice; bit-identical to the reference) ---- */
-CRM_FN double crm_hypot(double a, double b) {
+CRM_NOINLINE double crm_hypot(double a, double b) {
     double v0 = fabs(a), v1 = fabs(b);
     double mx = v0 > v1 ? v0 : v1;
     if (mx == 0.0) return mx;
-    int max_e;
-    (void)frexp(mx, &max_e);
-    double post = 1.0;
-    if (max_e < -1023) { /* subnormal range: rescale first, as CPython does */
-        const double dmin = 2.2250738585072014e-308;
-        v0 /= dmin; v1 /= dmin; mx /= dmin; post = dmin;
+    /* frexp(mx) -> max_e, scale = 2^-max_e, and the final h / scale = h * 2^max_e, by exponent-field
+     * arithmetic when mx is a normal number away from the range ends (bit-identical to frexp/ldexp) */
+    int be = (int)((crm_d2ll(mx) >> 52) & 0x7ff);
+    double scale, unscale, post = 1.0;
+    int fast = be >= 2 && be <= 2040;
+    if (fast) {
+        scale = crm_ll2d((long long)(2045 - be) << 52);
+        unscale = crm_ll2d((long long)(be + 1) << 52);
+    } else {
+        int max_e;
         (void)frexp(mx, &max_e);
+        if (max_e < -1023) { /* subnormal range: rescale first, as CPython does */
+            const double dmin = 2.2250738585072014e-308;
+            v0 /= dmin; v1 /= dmin; mx /= dmin; post = dmin;
+            (void)frexp(mx, &max_e);
+        }
+        scale = ldexp(1.0, -max_e);
+        unscale = 0.0;
     }
-    double scale = ldexp(1.0, -max_e);
     double csum = 1.0, frac1 = 0.0, frac2 = 0.0;
     double x = v0 * scale;
     crm_dd pr = crm_two_prod(x, x);
@@ -124,7 +145,7 @@ CRM_FN double crm_hypot(double a, double b) {
     csum = sm.hi; frac1 += pr.lo; frac2 += sm.lo;
     x = csum - 1.0 + (frac1 + frac2);
     h += x / (2.0 * h);
-    return post * (h / scale);
+    return fast ? h * unscale : post * (h / scale);
 }
 
 /* ---- double-double sin and cos of a double ---- */
@@ -141,16 +162,35 @@ CRM_NOINLINE void crm_sincos_dd(double x, crm_dd *s_out, crm_dd *c_out) {
         p3.lo += kf * CRM_PIO2_3L;
         r = crm_sub(r, p3);
     }
-    crm_dd r2 = crm_mul(r, r);
-    /* sin(r) = r * (1 + r2 * S(r2)),  cos(r) = 1 + r2 * C(r2), Taylor / Horner in double-double */
-    crm_dd ps = crm_mk(crm_sin_c[CRM_NSIN - 1][0], crm_sin_c[CRM_NSIN - 1][1]);
-    for (int k = CRM_NSIN - 2; k >= 0; k--)
-        ps = crm_add(crm_mul(ps, r2), crm_mk(crm_sin_c[k][0], crm_sin_c[k][1]));
+    /* second reduction: |r| = i/128 + h, |h| <= 2^-8; sin/cos(i/128) from the table */
+    int neg = r.hi < 0.0;
+    if (neg) r = crm_neg(r);
+    int ti = (int)rint(r.hi * 128.0);
+    double xi = (double)ti * 0.0078125;
+    crm_dd h = crm_fast_two_sum(r.hi - xi, r.lo); /* r.hi - xi is exact (Sterbenz) */
+    crm_dd h2 = crm_mul(h, h);
+    /* sin(h) = h * (1 + h2 * S(h2)),  cos(h) = 1 + h2 * C(h2): Taylor / Horner in double-double */
+    /* the two Horner chains are independent: one loop, interleaved, for instruction-level parallelism */
     crm_dd pc = crm_mk(crm_cos_c[CRM_NCOS - 1][0], crm_cos_c[CRM_NCOS - 1][1]);
-    for (int k = CRM_NCOS - 2; k >= 0; k--)
-        pc = crm_add(crm_mul(pc, r2), crm_mk(crm_cos_c[k][0], crm_cos_c[k][1]));
-    crm_dd sr = crm_add(r, crm_mul(r, crm_mul(ps, r2)));
-    crm_dd cr = crm_add_d(crm_mul(pc, r2), 1.0);
+    crm_dd ps = crm_mk(crm_sin_c[CRM_NSIN - 1][0], crm_sin_c[CRM_NSIN - 1][1]);
+    pc = crm_add(crm_mul(pc, h2), crm_mk(crm_cos_c[CRM_NCOS - 2][0], crm_cos_c[CRM_NCOS - 2][1]));
+    CRM_ROLLED
+    for (int k = CRM_NSIN - 2; k >= 0; k--) { /* CRM_NCOS == CRM_NSIN + 1 */
+        ps = crm_add(crm_mul(ps, h2), crm_mk(crm_sin_c[k][0], crm_sin_c[k][1]));
+        pc = crm_add(crm_mul(pc, h2), crm_mk(crm_cos_c[k][0], crm_cos_c[k][1]));
+    }
+    crm_dd sh = crm_add(h, crm_mul(h, crm_mul(ps, h2)));
+    crm_dd ch = crm_add_d(crm_mul(pc, h2), 1.0);
+    crm_dd sr, cr;
+    if (ti == 0) {
+        sr = sh; cr = ch;
+    } else { /* angle addition with the table entry */
+        crm_dd si = crm_mk(crm_sincos_tab[ti][0], crm_sincos_tab[ti][1]);
+        crm_dd ci = crm_mk(crm_sincos_tab[ti][2], crm_sincos_tab[ti][3]);
+        sr = crm_add(crm_mul(si, ch), crm_mul(ci, sh));
+        cr = crm_sub(crm_mul(ci, ch), crm_mul(si, sh));
+    }
+    if (neg) sr = crm_neg(sr);
     int q = ((int)kf) & 3;
     if (q == 0) { *s_out = sr; *c_out = cr; }
     else if (q == 1) { *s_out = cr; *c_out = crm_neg(sr); }
@@ -179,6 +219,7 @@ CRM_FN double crm_atan2_guess(double y, double x) {
     if (t > 0.41421356237309503) { t = (t - 1.0) / (t + 1.0); off = CRM_PIO4_H; }
     double z = t * t;
     double p = crm_atan_c[CRM_NATAN - 1];
+    CRM_ROLLED
     for (int k = CRM_NATAN - 2; k >= 0; k--) p = p * z + crm_atan_c[k];
     double a = off + (t + t * (z * p));
     if (ay > ax) a = CRM_PIO2_H - a;

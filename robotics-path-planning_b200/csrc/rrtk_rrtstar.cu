@@ -72,7 +72,7 @@ struct ObsList {  // SoA view of the obstacles an edge must be tested against
 };
 
 // check_collision (rrt_04:1216-1230) of one edge by ONE lane: any path point within any circle.
-__device__ __forceinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
+__device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
                                                double ty, const ObsList &L) {
     double x = fx, y = fy;
     for (int k = 0;; k++) {
@@ -132,8 +132,8 @@ __device__ __forceinline__ void warp_argmin(double &v, int &i) {
 
 // per-warp shared memory
 struct WarpSmem {
-    double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];     // obstacles near the new node
-    double gcull_x[CULL_CAP], gcull_y[CULL_CAP], gcull_r2[CULL_CAP];  // obstacles near the goal
+    // obstacles near the new node of the current iteration (re-used for the goal by best_goal)
+    double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];
 };
 
 // layout of the dynamic shared memory of one warp:
@@ -147,11 +147,12 @@ __host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
 
 // Conservative exact cull: keep obstacle o iff |o - c| <= (reach + R_o) * (1 + 1e-9) + 1e-9.
 // Returns the list to test edges against (shared-memory survivors, or all obstacles on overflow).
-__device__ __forceinline__ ObsList cull_obstacles(const double4 *obs, int n_obs, double cx, double cy,
+__device__ __noinline__ ObsList cull_obstacles(const double4 *obs, int n_obs, double cx, double cy,
                                                   double reach, double *sx, double *sy, double *sr2,
                                                   int lane) {
     int count = 0;
     bool overflow = false;
+#pragma unroll 2
     for (int base = 0; base < n_obs; base += 32) {
         int j = base + lane;
         bool keep = false;
@@ -191,6 +192,7 @@ __device__ __noinline__ void propagate(int root, int n, double2 *xy, double *cos
     __syncwarp();
     for (;;) {
         bool any = false;
+#pragma unroll 4
         for (int c = lane; c < n; c += 32) {
             int p = parent[c];
             if (p >= 0 && ((cur[p >> 5] >> (p & 31)) & 1u)) {
@@ -293,7 +295,7 @@ __device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n, const
 
 __device__ unsigned int g_query_counter;
 
-extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
                const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
@@ -341,9 +343,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             parent[0] = -1;
         }
         __syncwarp();
-        // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
-        ObsList G = cull_obstacles(obs, n_obs, gx, gy, p.expand_dis > res ? p.expand_dis : res,
-                                   ws->gcull_x, ws->gcull_y, ws->gcull_r2, lane);
+        const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
         int n = 1, nongoal = 0, status = RRTK_Q_OK, gi = -1, it = 0;
         bool done = false;
 
@@ -353,6 +353,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             // ---- get_nearest_node_index (rrt_04:1196-1202) ----
             double bd = INF;
             int bi = 0x7fffffff;
+#pragma unroll 4
             for (int i = lane; i < n; i += 32) {
                 double2 a = xy[i];
                 double ddx = a.x - rx, ddy = a.y - ry;
@@ -384,6 +385,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
                     const double r2 = near_r2[n + 1];
                     int count = 0;
+#pragma unroll 2
                     for (int b0 = 0; b0 < n; b0 += 32) {
                         int i = b0 + lane;
                         bool hit = false;
@@ -513,11 +515,16 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                 // goal test on the last node (rrt_01:90-96)
                 double2 last = xy[n - 1];
                 if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
+                    ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
+                                               ws->cull_r2, lane);
                     Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
                     if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane)) { gi = n - 1; it++; done = true; break; }
                 }
             } else if (!p.search_until_max_iter) {
                 bool ovf = false;
+                // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
+                ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
+                                           ws->cull_r2, lane);
                 gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
                 if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
                 if (gi >= 0) { it++; done = true; break; }
@@ -525,6 +532,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         }
         if (!done && !p.rrt_only) {
             bool ovf = false;
+            ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
             gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
             if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
         }
