@@ -31,6 +31,7 @@ constexpr unsigned FULL = 0xffffffffu;
 struct Steer {
     double ex, ey;    // end point
     double stx, sty;  // step vector = res * (cos, sin)
+    double d;         // hypot(to - from): what calc_distance_and_angle returns (rrt_04:1232-1238)
     int n;            // number of accumulated steps
     bool snap;        // final point snapped to the target
 };
@@ -41,6 +42,7 @@ __device__ __noinline__ Steer steer(double fx, double fy, double tx, double ty, 
     Steer st;
     double dx = tx - fx, dy = ty - fy;
     double d = crm_hypot(dx, dy);
+    st.d = d;
     double s, c;
     (void)crm_atan2_sincos(dy, dx, &s, &c);
     if (extend > d) extend = d;
@@ -137,11 +139,11 @@ struct WarpSmem {
 };
 
 // layout of the dynamic shared memory of one warp:
-//   WarpSmem | near_idx[near_cap] int | near_ok[near_cap] int | nd[near_cap] double (d2, then edge cost)
-//   | ex[near_cap] | ey[near_cap] | nc[near_cap] (node cost) | bits_cur[words] | bits_next[words]
+//   WarpSmem | nd[near_cap] double (d2, then edge length) | nc[near_cap] double (node cost)
+//   | near_idx[near_cap] int | near_ok[near_cap] int | bits_cur[words] | bits_next[words]
 __host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
     size_t words = (size_t)(node_cap + 31) / 32;
-    size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 4) + words * 4 * 2;
+    size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 2) + words * 4 * 2;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -295,7 +297,10 @@ __device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n, const
 
 __device__ unsigned int g_query_counter;
 
-extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+#ifndef RRTK_MIN_BLOCKS
+#define RRTK_MIN_BLOCKS 4
+#endif
+extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32, RRTK_MIN_BLOCKS)
 rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
                const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
@@ -310,9 +315,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
     unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(near_cap, p.node_cap);
     WarpSmem *ws = reinterpret_cast<WarpSmem *>(base);
     double *nd = reinterpret_cast<double *>(base + sizeof(WarpSmem));
-    double *s_ex = nd + near_cap;
-    double *s_ey = s_ex + near_cap;
-    double *s_nc = s_ey + near_cap;
+    double *s_nc = nd + near_cap;
     int *near_idx = reinterpret_cast<int *>(s_nc + near_cap);
     int *near_ok = near_idx + near_cap;
     uint32_t *bits_cur = reinterpret_cast<uint32_t *>(near_ok + near_cap);
@@ -424,11 +427,14 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                         for (int k = lane; k < count; k += 32) {
                             int i = near_idx[k];
                             double2 a = xy[i];
+                            double ci = cost[i];
                             Steer st = steer(a.x, a.y, nx, ny, INF, res);
                             bool ok = edge_free_lane(a.x, a.y, st, nx, ny, L) && inside_play(p, st.ex, st.ey);
+                            nd[k] = st.d;   // = hypot(new - node), calc_new_cost's distance (rrt_04:1375-1377)
+                            s_nc[k] = ci;
                             if (ok) {
                                 t_cpok++;
-                                double c = cost[i] + crm_hypot(nx - a.x, ny - a.y);
+                                double c = ci + st.d;
                                 if (c < bc) { bc = c; bk = k; bex = st.ex; bey = st.ey; }
                             }
                         }
@@ -437,61 +443,99 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                             bex = __shfl_sync(FULL, bex, bk & 31);  // k = lane (mod 32): the winner's lane
                             bey = __shfl_sync(FULL, bey, bk & 31);
                         }
+                        if (trace) {
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) t_cpok += __shfl_xor_sync(FULL, t_cpok, off);
+                            for (int off = 16; off >= 1; off >>= 1) t_cpok += __shfl_xor_sync(FULL, t_cpok, off);
+                        }
                         if (bk != 0x7fffffff) {
                             const int best = near_idx[bk];
                             // the node is re-steered from the winner (rrt_04:1279): same edge as above
                             const double cx = bex, cy = bey, ccost = bc;
-                            // ---- rewire (rrt_04:1340-1373), phase A: per-candidate edge, in parallel ----
-                            for (int k = lane; k < count; k += 32) {
-                                int i = near_idx[k];
-                                double2 a = xy[i];
-                                Steer st = steer(cx, cy, a.x, a.y, INF, res);
-                                bool ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
-                                near_ok[k] = ok ? 1 : 0;
-                                nd[k] = ccost + crm_hypot(a.x - cx, a.y - cy);
-                                s_ex[k] = st.ex;
-                                s_ey[k] = st.ey;
-                                s_nc[k] = cost[i];
-                            }
-                            __syncwarp();
-                            // ---- phase B: apply in list order (later entries see propagated costs) ----
-                            bool dirty = false;
-                            for (int k = 0; k < count; k++) {
-                                const int i = near_idx[k];
-                                int ok = near_ok[k];
-                                double ecost = nd[k], ex = s_ex[k], ey = s_ey[k];
-                                if (ok == 2) {
-                                    // node i moved earlier in this call: redo its edge from the new position
-                                    double2 a = xy[i];
-                                    Steer st = steer(cx, cy, a.x, a.y, INF, res);
-                                    ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) &&
-                                         inside_play(p, st.ex, st.ey);
-                                    ecost = ccost + crm_hypot(a.x - cx, a.y - cy);
-                                    ex = st.ex; ey = st.ey;
+                            const bool c_is_new = (cx == nx) && (cy == ny);  // the winner's edge snapped
+                            // ---- rewire (rrt_04:1340-1373) ----
+                            // An entry can only be re-parented if node.cost > new.cost + d (:1362); costs
+                            // never increase while this loop runs (unless a node MOVES, handled below), so
+                            // the steer + collision of an entry that fails the test now is dead work: only
+                            // lanes whose entry passes evaluate their edge.  With a trace every edge is
+                            // evaluated (the trace counts collision-free rewire edges).
+                            bool dirty = false;      // a propagate ran: node costs must be re-read
+                            int fallback_from = -1;  // >= 0: a node moved; redo entries from here serially
+                            for (int b0 = 0; b0 < count && fallback_from < 0; b0 += 32) {
+                                const int k = b0 + lane;
+                                int i = -1;
+                                double2 a = make_double2(0.0, 0.0);
+                                double ecost = 0.0, snc = 0.0;
+                                bool want = false, ok = false;
+                                Steer st;
+                                st.ex = st.ey = 0.0;
+                                if (k < count) {
+                                    i = near_idx[k];
+                                    a = xy[i];
+                                    snc = s_nc[k];
+                                    // hypot(node - c) == the forward edge's d when c is the sample point itself
+                                    double dk = c_is_new ? nd[k] : crm_hypot(a.x - cx, a.y - cy);
+                                    ecost = ccost + dk;
+                                    want = (trace != nullptr) || (snc > ecost);
                                 }
-                                t_rwok += ok ? 1 : 0;
-                                if (!ok) continue;
-                                const double ci = dirty ? cost[i] : s_nc[k];
-                                if (ci > ecost) {
-                                    const double2 old = xy[i];
-                                    const bool moved = (old.x != ex) || (old.y != ey);
-                                    __syncwarp();
-                                    if (lane == 0) {
-                                        xy[i] = make_double2(ex, ey);
-                                        cost[i] = ecost;
-                                        parent[i] = n;
-                                    }
-                                    __syncwarp();
-                                    if (moved) {  // later repeats of i must be re-evaluated
-                                        for (int k2 = k + 1 + lane; k2 < count; k2 += 32)
-                                            if (near_idx[k2] == i) near_ok[k2] = 2;
+                                if (want) {
+                                    st = steer(cx, cy, a.x, a.y, INF, res);
+                                    ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
+                                }
+                                const unsigned okmask = __ballot_sync(FULL, ok);
+                                t_rwok += __popc(okmask);
+                                unsigned m = __ballot_sync(FULL, ok && (snc > ecost));
+                                while (m) {  // apply in list order
+                                    const int b = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const int ii = __shfl_sync(FULL, i, b);
+                                    const double ec = __shfl_sync(FULL, ecost, b);
+                                    const double ex = __shfl_sync(FULL, st.ex, b), ey = __shfl_sync(FULL, st.ey, b);
+                                    const double ax = __shfl_sync(FULL, a.x, b), ay = __shfl_sync(FULL, a.y, b);
+                                    const double c0 = __shfl_sync(FULL, snc, b);
+                                    const double ci = dirty ? cost[ii] : c0;
+                                    if (ci > ec) {
+                                        const bool moved = (ax != ex) || (ay != ey);
                                         __syncwarp();
+                                        if (lane == 0) {
+                                            xy[ii] = make_double2(ex, ey);
+                                            cost[ii] = ec;
+                                            parent[ii] = n;
+                                        }
+                                        __syncwarp();
+                                        t_rwap++;
+                                        propagate(ii, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
+                                        dirty = true;
+                                        if (moved) {
+                                            // the node no longer sits where the parallel pass saw it, and the
+                                            // costs of its descendants may have gone UP: every later entry is
+                                            // re-evaluated from the current tree, one at a time
+                                            fallback_from = b0 + b + 1;
+                                            t_rwok -= __popc(okmask >> b >> 1);  // recounted below
+                                            break;
+                                        }
                                     }
-                                    t_rwap++;
-                                    propagate(i, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
-                                    dirty = true;
+                                }
+                            }
+                            if (fallback_from >= 0) {
+                                for (int k = fallback_from; k < count; k++) {
+                                    const int i = near_idx[k];
+                                    const double2 a = xy[i];
+                                    Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                                    const bool ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) &&
+                                                    inside_play(p, st.ex, st.ey);
+                                    const double ec = ccost + st.d;
+                                    t_rwok += ok ? 1 : 0;
+                                    if (ok && cost[i] > ec) {
+                                        __syncwarp();
+                                        if (lane == 0) {
+                                            xy[i] = make_double2(st.ex, st.ey);
+                                            cost[i] = ec;
+                                            parent[i] = n;
+                                        }
+                                        __syncwarp();
+                                        t_rwap++;
+                                        propagate(i, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
+                                    }
                                 }
                             }
                             if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; }

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librrtk.so")
+LIB_PATH = os.environ.get("RRTK_LIB", os.path.join(HERE, "librrtk.so"))  # override: tuning builds only
 
 SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
 Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW = 0, 1, 2

@@ -137,6 +137,11 @@ def test_rrtstar_random_scenarios_bitwise(seed, n_obs, max_iter, play, rr, expan
     assert np.array_equal(a["x"], ref["x"]) and np.array_equal(a["y"], ref["y"])
     assert np.array_equal(a["cost"], ref["cost"])
     assert path == O.final_course(ref, m["goal"])
+    # production path (no trace: rewire edges are evaluated lazily) must give the same tree
+    rrt2 = _planner(m)
+    path2 = rrt2.planning(animation=False, sample_stream=stream)
+    b = rrt2.tree_arrays()
+    assert all(np.array_equal(a[k], b[k]) for k in ("x", "y", "cost", "parent")) and path2 == path
 
 
 def test_batch_matches_single_queries_and_oracle(torch_cuda, oracle_lib):
