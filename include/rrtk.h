@@ -108,12 +108,15 @@ typedef struct rrtk_rrtstar_params {
  *   xy [Q][node_cap][2], cost [Q][node_cap], parent [Q][node_cap] (-1 = root),
  *   n_nodes [Q], iters_done [Q], goal_index [Q] (-1 = no path), status [Q],
  *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
+ * scratch (caller allocated, contents undefined afterwards):
+ *   workspace [Q][node_cap] int32   (children-per-node counts used by propagate_cost_to_leaves)
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
                          const double *sample_stream, const int64_t *sobol_offset, double *xy,
                          double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
-                         int32_t *goal_index, int32_t *status, int32_t *trace, void *stream);
+                         int32_t *goal_index, int32_t *status, int32_t *trace, int32_t *workspace,
+                         void *stream);
 
 /* Same with HOST pointers (allocates, copies in, runs, copies out, synchronises). */
 RRTK_API int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal,

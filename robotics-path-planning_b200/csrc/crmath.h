@@ -29,6 +29,8 @@
 #define CRM_CONST static __device__ __constant__ const  /* uniform index: constant cache */
 #define CRM_TABLE static __device__ const               /* per-lane index: global memory / L1 */
 #define CRM_ROLLED _Pragma("unroll 1")
+/* double-double primitives: inlined (out-of-line calls measured 2 % slower on B200) */
+#define CRM_DDOP static __device__ __forceinline__
 CRM_FN long long crm_d2ll(double x) { return __double_as_longlong(x); }
 CRM_FN double crm_ll2d(long long v) { return __longlong_as_double(v); }
 #else
@@ -40,6 +42,7 @@ CRM_FN double crm_ll2d(long long v) { return __longlong_as_double(v); }
 #define CRM_CONST static const
 #define CRM_TABLE static const
 #define CRM_ROLLED
+#define CRM_DDOP static inline
 CRM_FN long long crm_d2ll(double x) { long long v; memcpy(&v, &x, 8); return v; }
 CRM_FN double crm_ll2d(long long v) { double x; memcpy(&x, &v, 8); return x; }
 #endif
@@ -69,7 +72,7 @@ CRM_FN crm_dd crm_two_prod(double a, double b) {
 }
 
 /* double-double arithmetic (Dekker / Hida-Li-Bailey "accurate" variants) */
-CRM_FN crm_dd crm_add(crm_dd a, crm_dd b) {
+CRM_DDOP crm_dd crm_add(crm_dd a, crm_dd b) {
     crm_dd s = crm_two_sum(a.hi, b.hi);
     crm_dd t = crm_two_sum(a.lo, b.lo);
     s.lo += t.hi;
@@ -77,24 +80,24 @@ CRM_FN crm_dd crm_add(crm_dd a, crm_dd b) {
     s.lo += t.lo;
     return crm_fast_two_sum(s.hi, s.lo);
 }
-CRM_FN crm_dd crm_add_d(crm_dd a, double b) {
+CRM_DDOP crm_dd crm_add_d(crm_dd a, double b) {
     crm_dd s = crm_two_sum(a.hi, b);
     s.lo += a.lo;
     return crm_fast_two_sum(s.hi, s.lo);
 }
 CRM_FN crm_dd crm_neg(crm_dd a) { return crm_mk(-a.hi, -a.lo); }
 CRM_FN crm_dd crm_sub(crm_dd a, crm_dd b) { return crm_add(a, crm_neg(b)); }
-CRM_FN crm_dd crm_mul(crm_dd a, crm_dd b) {
+CRM_DDOP crm_dd crm_mul(crm_dd a, crm_dd b) {
     crm_dd p = crm_two_prod(a.hi, b.hi);
     p.lo += a.hi * b.lo + a.lo * b.hi;
     return crm_fast_two_sum(p.hi, p.lo);
 }
-CRM_FN crm_dd crm_mul_d(crm_dd a, double b) {
+CRM_DDOP crm_dd crm_mul_d(crm_dd a, double b) {
     crm_dd p = crm_two_prod(a.hi, b);
     p.lo += a.lo * b;
     return crm_fast_two_sum(p.hi, p.lo);
 }
-CRM_FN crm_dd crm_div(crm_dd a, crm_dd b) {
+CRM_DDOP crm_dd crm_div(crm_dd a, crm_dd b) {
     /* quotient digits from one reciprocal; each digit is corrected by the exact residual */
     double inv = 1.0 / b.hi;
     double q1 = a.hi * inv;
@@ -170,15 +173,21 @@ CRM_NOINLINE void crm_sincos_dd(double x, crm_dd *s_out, crm_dd *c_out) {
     crm_dd h = crm_fast_two_sum(r.hi - xi, r.lo); /* r.hi - xi is exact (Sterbenz) */
     crm_dd h2 = crm_mul(h, h);
     /* sin(h) = h * (1 + h2 * S(h2)),  cos(h) = 1 + h2 * C(h2): Taylor / Horner in double-double */
-    /* the two Horner chains are independent: one loop, interleaved, for instruction-level parallelism */
-    crm_dd pc = crm_mk(crm_cos_c[CRM_NCOS - 1][0], crm_cos_c[CRM_NCOS - 1][1]);
-    crm_dd ps = crm_mk(crm_sin_c[CRM_NSIN - 1][0], crm_sin_c[CRM_NSIN - 1][1]);
-    pc = crm_add(crm_mul(pc, h2), crm_mk(crm_cos_c[CRM_NCOS - 2][0], crm_cos_c[CRM_NCOS - 2][1]));
+    /* |h| <= 2^-8: the terms from h^7/7! (sin) and h^6/6! (cos) on are below 2^-57 of the result, so
+     * their polynomial runs in plain double (error < 2^-109); the two leading coefficients of each
+     * series are applied in double-double */
+    double z = h2.hi;
+    double ts = crm_sin_c[CRM_NSIN - 1][0], tc = crm_cos_c[CRM_NCOS - 1][0];
+    tc = fma(tc, z, crm_cos_c[CRM_NCOS - 2][0]);
     CRM_ROLLED
-    for (int k = CRM_NSIN - 2; k >= 0; k--) { /* CRM_NCOS == CRM_NSIN + 1 */
-        ps = crm_add(crm_mul(ps, h2), crm_mk(crm_sin_c[k][0], crm_sin_c[k][1]));
-        pc = crm_add(crm_mul(pc, h2), crm_mk(crm_cos_c[k][0], crm_cos_c[k][1]));
+    for (int k = CRM_NSIN - 2; k >= 2; k--) { /* CRM_NCOS == CRM_NSIN + 1 */
+        ts = fma(ts, z, crm_sin_c[k][0]);
+        tc = fma(tc, z, crm_cos_c[k][0]);
     }
+    crm_dd ps = crm_add(crm_mul_d(h2, ts), crm_mk(crm_sin_c[1][0], crm_sin_c[1][1]));
+    crm_dd pc = crm_add(crm_mul_d(h2, tc), crm_mk(crm_cos_c[1][0], crm_cos_c[1][1]));
+    ps = crm_add(crm_mul(ps, h2), crm_mk(crm_sin_c[0][0], crm_sin_c[0][1]));
+    pc = crm_add(crm_mul(pc, h2), crm_mk(crm_cos_c[0][0], crm_cos_c[0][1]));
     crm_dd sh = crm_add(h, crm_mul(h, crm_mul(ps, h2)));
     crm_dd ch = crm_add_d(crm_mul(pc, h2), 1.0);
     crm_dd sr, cr;

@@ -27,7 +27,7 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
                    const int32_t *n_obs, const double *near_r2, const double *sample_stream,
                    const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
                    int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
-                   int32_t *trace, unsigned int *counter, cudaStream_t s);
+                   int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s);
 int launch_extract_paths(int32_t nq, int32_t node_cap, int32_t path_cap, const double *start_goal,
                          const double *xy, const int32_t *parent, const int32_t *goal_index,
                          double *path, int32_t *path_len, cudaStream_t s);
@@ -112,13 +112,15 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
                          const double *sample_stream, const int64_t *sobol_offset, double *xy,
                          double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
-                         int32_t *goal_index, int32_t *status, int32_t *trace, void *stream) {
+                         int32_t *goal_index, int32_t *status, int32_t *trace, int32_t *workspace,
+                         void *stream) {
     int rc = check_params(p);
     if (rc) return rc;
     if (p->n_queries == 0) return RRTK_OK;
     if (!start_goal || !n_obs || !xy || !cost || !parent || !n_nodes || !iters_done || !goal_index || !status)
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if (!p->rrt_only && !near_r2) return set_error(RRTK_ERR_INVALID, "near_r2 is NULL");
+    if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * node_cap int32)");
     if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
     if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
@@ -126,7 +128,7 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
     DevCounter ctr(s);
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
     return launch_rrtstar(*p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost,
-                          parent, n_nodes, iters_done, goal_index, status, trace, ctr.ptr, s);
+                          parent, n_nodes, iters_done, goal_index, status, trace, workspace, ctr.ptr, s);
 }
 
 int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
@@ -197,11 +199,11 @@ int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal
     const size_t b_sg = Q * 4 * 8, b_obs = Q * (size_t)p->obs_stride * 4 * 8, b_no = Q * 4,
                  b_r2 = (cap + 2) * 8, b_st = sample_stream ? Q * it * 16 : 0,
                  b_so = sobol_offset ? Q * 8 : 0, b_xy = Q * cap * 16, b_c = Q * cap * 8,
-                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0;
+                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * cap * 4;
     char *d = nullptr;
     size_t off[16], total = 0;
-    const size_t sizes[14] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr};
-    for (int i = 0; i < 14; i++) { off[i] = total; total += (sizes[i] + 255) & ~(size_t)255; }
+    const size_t sizes[15] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr, b_ws};
+    for (int i = 0; i < 15; i++) { off[i] = total; total += (sizes[i] + 255) & ~(size_t)255; }
     cudaStream_t s = 0;
     RRTK_TRY_CUDA(cudaMalloc(&d, total ? total : 256), "cudaMalloc");
     RRTK_TRY_CUDA(cudaMemcpyAsync(d + off[0], start_goal, b_sg, cudaMemcpyHostToDevice, s), "H2D start_goal");
@@ -215,7 +217,8 @@ int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal
                               b_st ? (double *)(d + off[4]) : nullptr, b_so ? (int64_t *)(d + off[5]) : nullptr,
                               (double *)(d + off[6]), (double *)(d + off[7]), (int32_t *)(d + off[8]),
                               (int32_t *)(d + off[9]), (int32_t *)(d + off[10]), (int32_t *)(d + off[11]),
-                              (int32_t *)(d + off[12]), b_tr ? (int32_t *)(d + off[13]) : nullptr, s);
+                              (int32_t *)(d + off[12]), b_tr ? (int32_t *)(d + off[13]) : nullptr,
+                              (int32_t *)(d + off[14]), s);
     if (rc) goto cleanup;
     RRTK_TRY_CUDA(cudaMemcpyAsync(xy, d + off[6], b_xy, cudaMemcpyDeviceToHost, s), "D2H xy");
     RRTK_TRY_CUDA(cudaMemcpyAsync(cost, d + off[7], b_c, cudaMemcpyDeviceToHost, s), "D2H cost");

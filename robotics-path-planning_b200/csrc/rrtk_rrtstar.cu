@@ -25,6 +25,17 @@
 namespace rrtk {
 
 constexpr int WARPS_PER_CTA = 4;
+#define RRTK_PRAGMA(x) _Pragma(#x)
+#define RRTK_UNROLL(n) RRTK_PRAGMA(unroll n)
+#ifndef RRTK_UNROLL_NEAREST
+#define RRTK_UNROLL_NEAREST 1
+#endif
+#ifndef RRTK_UNROLL_NEAR
+#define RRTK_UNROLL_NEAR 1
+#endif
+#ifndef RRTK_UNROLL_PROP
+#define RRTK_UNROLL_PROP 1
+#endif
 constexpr int CULL_CAP = 64;      // culled obstacle list per warp (overflow -> full list)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -186,27 +197,32 @@ __device__ __noinline__ ObsList cull_obstacles(const double4 *obs, int n_obs, do
 }
 
 // propagate_cost_to_leaves (rrt_04:1379-1384): level-synchronous sweeps over the parent array.
+// nchild[] (children per node, maintained on append / re-parent) prunes the work: a childless root
+// costs nothing, and the sweeps stop as soon as no node updated in the last level has children.
 __device__ __noinline__ void propagate(int root, int n, double2 *xy, double *cost, const int32_t *parent,
-                                       uint32_t *cur, uint32_t *nxt, int words, int lane) {
+                                       const int32_t *nchild, uint32_t *cur, uint32_t *nxt, int words, int lane) {
+    if (nchild[root] == 0) return;
     for (int w = lane; w < words; w += 32) { cur[w] = 0u; nxt[w] = 0u; }
     __syncwarp();
     if (lane == 0) cur[root >> 5] = 1u << (root & 31);
     __syncwarp();
     for (;;) {
-        bool any = false;
-#pragma unroll 4
+        bool more = false;
+RRTK_UNROLL(RRTK_UNROLL_PROP)
         for (int c = lane; c < n; c += 32) {
             int p = parent[c];
             if (p >= 0 && ((cur[p >> 5] >> (p & 31)) & 1u)) {
                 double2 a = xy[p], b = xy[c];
                 cost[c] = cost[p] + crm_hypot(b.x - a.x, b.y - a.y);
-                atomicOr(&nxt[c >> 5], 1u << (c & 31));
-                any = true;
+                if (nchild[c] > 0) {
+                    atomicOr(&nxt[c >> 5], 1u << (c & 31));
+                    more = true;
+                }
             }
         }
-        any = __any_sync(FULL, any);
+        more = __any_sync(FULL, more);
         __syncwarp();
-        if (!any) break;
+        if (!more) break;
         for (int w = lane; w < words; w += 32) { cur[w] = nxt[w]; nxt[w] = 0u; }
         __syncwarp();
     }
@@ -214,10 +230,16 @@ __device__ __noinline__ void propagate(int root, int n, double2 *xy, double *cos
 
 struct Sample { double x, y; };
 
+// Sobol state of one query: the current point (30-bit integers) and its index; advanced with the
+// Antonov-Saleev update point(n+1) = point(n) ^ V[lowest zero bit of n] (what i4_sobol does, rrt_04:448-452)
+struct SobolState {
+    int64_t n;
+    uint32_t q0, q1;
+};
+
 // get_random_node / get_random_node_sobol (rrt_04:1132-1153) with a counter-based coin
 __device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, double gx,
-                                              double gy, const double2 *stream, int64_t sobol_base,
-                                              int &nongoal) {
+                                              double gy, const double2 *stream, SobolState &sob) {
     Sample s;
     if (p.sampler == RRTK_SAMPLER_STREAM) {
         double2 v = stream[it];
@@ -229,16 +251,16 @@ __device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int 
     if (coin > p.goal_sample_rate) {
         double w = p.max_rand - p.min_rand;
         if (p.sampler == RRTK_SAMPLER_SOBOL) {
-            uint32_t q0, q1;
-            sobol2(sobol_base + nongoal, q0, q1);
             const double recipd = 1.0 / 1073741824.0;
-            s.x = p.min_rand + ((double)q0 * recipd) * w;
-            s.y = p.min_rand + ((double)q1 * recipd) * w;
+            s.x = p.min_rand + ((double)sob.q0 * recipd) * w;
+            s.y = p.min_rand + ((double)sob.q1 * recipd) * w;
+            int c = __ffsll(~sob.n) - 1;  // lowest zero bit of the index just used
+            if (c < SOBOL_BITS) { sob.q0 ^= c_sobol.v[0][c]; sob.q1 ^= c_sobol.v[1][c]; }
+            sob.n++;
         } else {
             s.x = p.min_rand + w * u01(splitmix64(k0 + 1));
             s.y = p.min_rand + w * u01(splitmix64(k0 + 2));
         }
-        nongoal++;
     } else {
         s.x = gx; s.y = gy;
     }
@@ -306,7 +328,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
                const int64_t *__restrict__ sobol_offset, double2 *xy_all, double *cost_all,
                int32_t *parent_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
-               int32_t *status_out, int32_t *trace_all, unsigned int *counter) {
+               int32_t *status_out, int32_t *trace_all, int32_t *workspace, unsigned int *counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -340,23 +362,28 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         int32_t *trace = trace_all ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
+        int32_t *nchild = workspace + (size_t)q * p.node_cap;
         if (lane == 0) {
             xy[0] = make_double2(sg.x, sg.y);
             cost[0] = 0.0;
             parent[0] = -1;
+            nchild[0] = 0;
         }
         __syncwarp();
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
-        int n = 1, nongoal = 0, status = RRTK_Q_OK, gi = -1, it = 0;
+        SobolState sob;
+        sob.n = sobol_base < 0 ? 0 : sobol_base;
+        sobol2(sob.n, sob.q0, sob.q1);
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
         bool done = false;
 
         for (it = 0; it < p.max_iter; it++) {
-            Sample smp = draw_sample(p, (int)q, it, gx, gy, stream, sobol_base, nongoal);
+            Sample smp = draw_sample(p, (int)q, it, gx, gy, stream, sob);
             const double rx = smp.x, ry = smp.y;
             // ---- get_nearest_node_index (rrt_04:1196-1202) ----
             double bd = INF;
             int bi = 0x7fffffff;
-#pragma unroll 4
+RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             for (int i = lane; i < n; i += 32) {
                 double2 a = xy[i];
                 double ddx = a.x - rx, ddy = a.y - ry;
@@ -384,11 +411,12 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                     n++;
                     __syncwarp();
                 } else if (accept) {
+                    if (lane == 0) nchild[n] = 0;  // children arrive through rewire, before the append
                     const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
                     const double r2 = near_r2[n + 1];
                     int count = 0;
-#pragma unroll 2
+RRTK_UNROLL(RRTK_UNROLL_NEAR)
                     for (int b0 = 0; b0 < n; b0 += 32) {
                         int i = b0 + lane;
                         bool hit = false;
@@ -497,13 +525,15 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                                         const bool moved = (ax != ex) || (ay != ey);
                                         __syncwarp();
                                         if (lane == 0) {
+                                            nchild[parent[ii]]--;
+                                            nchild[n]++;
                                             xy[ii] = make_double2(ex, ey);
                                             cost[ii] = ec;
                                             parent[ii] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate(ii, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
+                                        propagate(ii, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
                                         dirty = true;
                                         if (moved) {
                                             // the node no longer sits where the parallel pass saw it, and the
@@ -528,20 +558,22 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                                     if (ok && cost[i] > ec) {
                                         __syncwarp();
                                         if (lane == 0) {
+                                            nchild[parent[i]]--;
+                                            nchild[n]++;
                                             xy[i] = make_double2(st.ex, st.ey);
                                             cost[i] = ec;
                                             parent[i] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate(i, n, xy, cost, parent, bits_cur, bits_nxt, words, lane);
+                                        propagate(i, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
                                     }
                                 }
                             }
-                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; }
+                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; nchild[best]++; }
                             t_status = 3; t_par = best;
                         } else {
-                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; }
+                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; nchild[ni]++; }
                             t_status = 2; t_par = ni;
                         }
                         n++;
@@ -624,10 +656,11 @@ extern "C" __global__ void sample_stream_kernel(rrtk_rrtstar_params p, const dou
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= p.n_queries) return;
     double4 sg = start_goal[q];
-    int nongoal = 0;
-    int64_t base = sobol_offset ? sobol_offset[q] : 0;
+    SobolState sob;
+    sob.n = sobol_offset ? (sobol_offset[q] < 0 ? 0 : sobol_offset[q]) : 0;
+    sobol2(sob.n, sob.q0, sob.q1);
     for (int it = 0; it < p.max_iter; it++) {
-        Sample s = draw_sample(p, q, it, sg.z, sg.w, nullptr, base, nongoal);
+        Sample s = draw_sample(p, q, it, sg.z, sg.w, nullptr, sob);
         out[(size_t)q * p.max_iter + it] = make_double2(s.x, s.y);
     }
 }
@@ -659,7 +692,7 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
                    const int32_t *n_obs, const double *near_r2, const double *sample_stream,
                    const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
                    int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
-                   int32_t *trace, unsigned int *counter, cudaStream_t s) {
+                   int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s) {
     size_t per_warp = warp_smem_bytes(p.near_cap, p.node_cap);
     size_t smem = per_warp * WARPS_PER_CTA;
     if (smem > 227 * 1024) return set_error(RRTK_ERR_INVALID, "near_cap/node_cap need more than 227 KB of shared memory");
@@ -681,7 +714,7 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
         p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(obstacles),
         n_obs, near_r2, reinterpret_cast<const double2 *>(sample_stream), sobol_offset,
         reinterpret_cast<double2 *>(xy), cost, parent, n_nodes, iters_done, goal_index, status, trace,
-        counter);
+        workspace, counter);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "rrtstar_kernel launch");
     return RRTK_OK;

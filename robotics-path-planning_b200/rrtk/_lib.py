@@ -37,7 +37,7 @@ _SIGS = {
     "rrtk_sobol_fill_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP, _VP]),
     "rrtk_sobol_fill_host": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP]),
     "rrtk_sobol_table": (C.c_int, [C.c_int, _VP]),
-    "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 15),
+    "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 16),
     "rrtk_rrtstar_run_host": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 14),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),

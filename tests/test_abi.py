@@ -47,15 +47,15 @@ def test_bad_params_rejected_without_gpu():
     from rrtk import _lib, engine
     L = _lib.lib()
     p = engine.make_params(4, 10, 11, 1, 1.0, 0.1, near_cap=33)
-    rc = L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 15))
+    rc = L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 16))
     assert rc == -1 and b"near_cap" in L.rrtk_last_error()
     p = engine.make_params(4, 10, 11, 1, 1.0, 0.0)
-    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 15)) == -1
+    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 16)) == -1
     p = engine.make_params(4, 10, 11, 1, 1.0, 0.1)
-    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 15)) == -1
+    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 16)) == -1
     assert b"NULL" in L.rrtk_last_error()
     p = engine.make_params(0, 10, 11, 1, 1.0, 0.1)
-    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 15)) == 0   # empty batch is a no-op
+    assert L.rrtk_rrtstar_run_dev(C.byref(p), *([None] * 16)) == 0   # empty batch is a no-op
 
 
 def test_sobol_table_matches_oracle(oracle_lib):
