@@ -155,6 +155,19 @@ RRTK_API int rrtk_near_f32_dev(const float *xy, int64_t n, float cx, float cy, f
 RRTK_API int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Arm C-space occupancy grid: get_occupancy_grid (arm02:79-110) with NLinkArm.update_points
+ * (:257-262, joint k uses theta1 for k = 1 and theta1 + theta2 for k >= 2) and detect_collision (:46-76),
+ * for S obstacle sets at once and rows [row0, row0 + n_rows) of the M x M joint grid.
+ *   theta        [M]  (device)  the reference's theta_list, evaluated by the host (arm02:95)
+ *   link_lengths [n_links] (HOST, n_links <= 16)
+ *   obstacles    [S][O][3] (device)  x, y, radius
+ *   grid         [S][n_rows][M] uint8 (device)  1 = the arm touches an obstacle of that set
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
+                               const double *link_lengths, const double *obstacles, int32_t n_sets,
+                               int32_t n_obs, uint8_t *grid, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)

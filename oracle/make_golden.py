@@ -128,7 +128,36 @@ def c2_params(seed, n_obs, max_iter):
                 max_iter=max_iter, play_area=None, robot_radius=0.0, connect_circle_dist=50.0)
 
 
+def run_arm02(name, M, link_length, obstacles):
+    """get_occupancy_grid of the unmodified arm02 (NLinkArm + detect_collision)."""
+    ns = ref_loader.load("arm02")
+    arm = ns["NLinkArm"](link_length, [0.0] * len(link_length))
+    t0 = time.perf_counter()
+    grid = ns["get_occupancy_grid"](arm, obstacles, M)
+    wall = time.perf_counter() - t0
+    grid = np.asarray(grid)
+    meta = dict(kind="arm02", M=M, link_length=list(link_length), obstacles=[list(map(float, o)) for o in obstacles],
+                reference_wall_s=wall, occupied=int(grid.sum()), dtype=str(grid.dtype))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta),
+                        grid_bits=np.packbits(grid.astype(np.uint8), axis=None), shape=np.array(grid.shape))
+    print(f"{name}: M={M}, {int(grid.sum())} occupied cells, {wall:.2f} s ({M * M / wall:.0f} cells/s)")
+
+
+ARM_OBS = [[1.75, 0.75, 0.6], [0.55, 1.5, 0.5], [0, -1, 0.7], [0, -0.6, 0.4], [-1, 1., 0.3]]  # arm02:298
+ARM_LINKS = [0.5, 0.5, 0.3, 0.5, 0.1]                                                            # arm02:302
+
+
+def _rand_arm_obs(seed, n=5):
+    rng = np.random.default_rng(seed)
+    return [[float(x), float(y), float(r)] for (x, y), r in
+            zip(rng.uniform(-2, 2, (n, 2)), rng.uniform(0.2, 0.7, n))]
+
+
 CASES = {
+    "arm02_script_m100": lambda: run_arm02("arm02_script_m100", 100, ARM_LINKS, ARM_OBS),
+    "arm02_2link_m100": lambda: run_arm02("arm02_2link_m100", 100, [1.0, 1.0], ARM_OBS),
+    "arm02_script_m51_rand": lambda: run_arm02("arm02_script_m51_rand", 51, ARM_LINKS, _rand_arm_obs(5)),
+    "arm02_3link_m64_rand": lambda: run_arm02("arm02_3link_m64_rand", 64, [0.8, 0.6, 0.4], _rand_arm_obs(6, 7)),
     # C1: the built-in scenario, the reference samples by itself (Sobol + random.seed(0))
     "rrt04_c1_sobol_500": lambda: run_rrt04("rrt04_c1_sobol_500", C1, True, True, 0),
     "rrt04_c1_sobol_2000": lambda: run_rrt04("rrt04_c1_sobol_2000", dict(C1, max_iter=2000), True, True, 0),

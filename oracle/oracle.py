@@ -162,3 +162,24 @@ def cr_atan2_sincos(y: float, x: float):
     s = C.c_double(); c = C.c_double()
     th = lib().orc_cr_atan2_sincos(y, x, C.byref(s), C.byref(c))
     return th, s.value, c.value
+
+
+def arm_theta_list(M: int) -> np.ndarray:
+    """theta_list[:M] of arm02:95: [2 * i * pi / M for i in range(-M // 2, M // 2 + 1)]."""
+    from math import pi
+    return np.array([2 * i * pi / M for i in range(-M // 2, M // 2 + 1)][:M], dtype=np.float64)
+
+
+def arm_grid(M, link_lengths, obstacles, math_mode=MATH_LIBM, row0=0, n_rows=None):
+    """get_occupancy_grid (arm02:79-110) -> uint8 [n_rows, M]."""
+    n_rows = M - row0 if n_rows is None else n_rows
+    theta = arm_theta_list(M)
+    link = np.ascontiguousarray(link_lengths, dtype=np.float64)
+    obs = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
+    grid = np.zeros((n_rows, M), dtype=np.uint8)
+    rc = lib().orc_arm_grid(C.c_int32(M), _p(theta, C.c_double), C.c_int32(row0), C.c_int32(n_rows),
+                            C.c_int32(len(link)), _p(link, C.c_double), _p(obs, C.c_double),
+                            C.c_int32(obs.shape[0]), C.c_int32(math_mode), _p(grid, C.c_uint8))
+    if rc:
+        raise ValueError("orc_arm_grid: bad arguments")
+    return grid

@@ -469,3 +469,56 @@ ORC_EXPORT int orc_steer_collide(const orc_params_t *p, const double *obs, doubl
     free(t);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Arm C-space occupancy grid (arm02:46-110, :257-262)                                   */
+/* ------------------------------------------------------------------------------------ */
+/* numpy's dot of two 2-vectors on this platform (OpenBLAS ddot, FMA kernel) evaluates
+ * fma(a1, b1, a0 * b0) -- verified against numpy for 20 000 random pairs */
+static inline double dot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
+
+/* detect_collision (arm02:46-76): 1 = the link [a, b] touches the circle */
+static int arm_detect_collision(double ax, double ay, double bx, double by, double cx, double cy, double r) {
+    double l0 = bx - ax, l1 = by - ay;
+    double mag = sqrt(dot2(l0, l1, l0, l1)); /* np.linalg.norm */
+    double v0 = cx - ax, v1 = cy - ay;
+    double proj = dot2(v0, v1, l0 / mag, l1 / mag);
+    double p0, p1;
+    if (proj <= 0) { p0 = ax; p1 = ay; }
+    else if (proj >= mag) { p0 = bx; p1 = by; }
+    else { p0 = ax + l0 * proj / mag; p1 = ay + l1 * proj / mag; }
+    double w0 = p0 - cx, w1 = p1 - cy;
+    double dist = sqrt(dot2(w0, w1, w0, w1));
+    if (dist > r) return 0;
+    return 1;
+}
+
+/* get_occupancy_grid (arm02:79-110) for rows [row0, row0 + n_rows): grid[(i - row0) * M + j].
+ * theta[M] is the reference's theta_list (host-evaluated); joint k uses theta1 (k = 1) or
+ * theta1 + theta2 (k >= 2), the 2-angle prefix-sum rule of arm02:259-260. */
+ORC_EXPORT int orc_arm_grid(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
+                            const double *link, const double *obs /* [O][3] */, int32_t O,
+                            int32_t math_mode, uint8_t *grid) {
+    if (n_links < 1 || n_links > 16) return -1;
+    for (int i = row0; i < row0 + n_rows; i++)
+        for (int j = 0; j < M; j++) {
+            double px[17], py[17];
+            px[0] = 0.0; py[0] = 0.0;
+            double a1 = theta[i], a2 = theta[i] + theta[j];
+            for (int k = 1; k <= n_links; k++) {
+                double ang = k == 1 ? a1 : a2;
+                double c, s;
+                if (math_mode == ORC_MATH_LIBM) { c = cos(ang); s = sin(ang); }
+                else { c = crm_cos(ang); s = crm_sin(ang); }
+                px[k] = px[k - 1] + link[k - 1] * c;
+                py[k] = py[k - 1] + link[k - 1] * s;
+            }
+            int hit = 0;
+            for (int k = 0; k < n_links && !hit; k++)
+                for (int o = 0; o < O && !hit; o++)
+                    hit = arm_detect_collision(px[k], py[k], px[k + 1], py[k + 1], obs[3 * o], obs[3 * o + 1],
+                                               obs[3 * o + 2]);
+            grid[(size_t)(i - row0) * M + j] = (uint8_t)hit;
+        }
+    return 0;
+}

@@ -40,6 +40,8 @@ int launch_nearest(const float *xy, long long n, const float *samples, int B, un
 int launch_near(const float *xy, long long n, float cx, float cy, float r2, int *out_idx, int cap, int *out_n,
                 cudaStream_t s);
 int launch_fma_peak(int fp64, int iters, int blocks, void *out, cudaStream_t s);
+int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
+                    const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
 static int check_params(const rrtk_rrtstar_params *p) {
     if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
@@ -173,6 +175,18 @@ int rrtk_near_f32_dev(const float *xy, int64_t n, float cx, float cy, float r2, 
     if (!xy || !out_n || (cap > 0 && !out_idx)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if ((uintptr_t)xy & 15) return set_error(RRTK_ERR_INVALID, "xy must be 16-byte aligned");
     return launch_near(xy, n, cx, cy, r2, out_idx, cap, out_n, (cudaStream_t)stream);
+}
+
+int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
+                      const double *link_lengths, const double *obstacles, int32_t n_sets, int32_t n_obs,
+                      uint8_t *grid, void *stream) {
+    if (M < 1 || row0 < 0 || n_rows < 0 || row0 + n_rows > M) return set_error(RRTK_ERR_INVALID, "bad M / row range");
+    if (n_links < 1 || n_links > 16) return set_error(RRTK_ERR_INVALID, "1 <= n_links <= 16");
+    if (n_sets < 0 || n_obs < 0) return set_error(RRTK_ERR_INVALID, "negative set / obstacle count");
+    if (n_rows == 0 || n_sets == 0) return RRTK_OK;
+    if (!theta || !link_lengths || !grid || (n_obs > 0 && !obstacles)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_arm_grid(M, theta, row0, n_rows, n_links, link_lengths, obstacles, n_sets, n_obs, grid,
+                           (cudaStream_t)stream);
 }
 
 int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *out, void *stream) {

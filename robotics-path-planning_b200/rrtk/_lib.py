@@ -45,6 +45,8 @@ _SIGS = {
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_near_f32_dev": (C.c_int, [_VP, C.c_int64, C.c_float, C.c_float, C.c_float, _VP, C.c_int32, _VP, _VP]),
     "rrtk_fma_peak_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _VP, _VP]),
+    "rrtk_arm_grid_dev": (C.c_int, [C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.c_int32,
+                                    C.c_int32, _VP, _VP]),
 }
 
 EXPORTED = tuple(_SIGS)

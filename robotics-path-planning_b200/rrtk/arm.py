@@ -1,0 +1,75 @@
+"""Arm C-space occupancy grid (02_arm_obstacle_navigation.py) behind the reference's API.
+
+`NLinkArm` and `get_occupancy_grid(arm, obstacles, M)` keep the reference's signatures
+(arm02:79-110, :236-281); the grid itself is computed on the GPU (rrtk_arm_grid_dev), for one obstacle
+set or for many at once (`get_occupancy_grids`).  No CPU fallback."""
+from __future__ import annotations
+
+from math import pi
+
+import numpy as np
+
+from . import _lib
+
+
+class NLinkArm(object):
+    """Planar arm with an arbitrary number of links (arm02:236-262)."""
+
+    def __init__(self, link_lengths, joint_angles):
+        self.n_links = len(link_lengths)
+        if self.n_links != len(joint_angles):
+            raise ValueError()
+        self.link_lengths = np.array(link_lengths)
+        self.joint_angles = np.array(joint_angles)
+        self.points = [[0, 0] for _ in range(self.n_links + 1)]
+        self.lim = sum(link_lengths)
+        self.update_points()
+
+    def update_joints(self, joint_angles):
+        self.joint_angles = joint_angles
+        self.update_points()
+
+    def update_points(self):
+        for i in range(1, self.n_links + 1):
+            self.points[i][0] = self.points[i - 1][0] + \
+                self.link_lengths[i - 1] * np.cos(np.sum(self.joint_angles[:i]))
+            self.points[i][1] = self.points[i - 1][1] + \
+                self.link_lengths[i - 1] * np.sin(np.sum(self.joint_angles[:i]))
+        self.end_effector = np.array(self.points[self.n_links]).T
+
+
+def theta_list(M: int) -> np.ndarray:
+    """The first M entries of arm02:95's theta_list, with the reference's Python float arithmetic."""
+    return np.array([2 * i * pi / M for i in range(-M // 2, M // 2 + 1)][:M], dtype=np.float64)
+
+
+def occupancy_grids_device(link_lengths, obstacle_sets, M, row0=0, n_rows=None, device=None):
+    """uint8 tensor [S, n_rows, M] on the GPU: cell (i, j) of set s is 1 iff the arm at joint angles
+    (theta_list[row0 + i], theta_list[j]) touches a circle of `obstacle_sets[s]` ([S, O, 3])."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    n_rows = M - row0 if n_rows is None else n_rows
+    obs = np.ascontiguousarray(np.asarray(obstacle_sets, dtype=np.float64))
+    if obs.ndim != 3 or obs.shape[2] != 3:
+        raise ValueError("obstacle_sets must have shape [S, O, 3]")
+    S, O = obs.shape[0], obs.shape[1]
+    link = np.ascontiguousarray(link_lengths, dtype=np.float64)
+    with torch.cuda.device(dev):
+        theta = torch.from_numpy(theta_list(M)).to(dev)
+        d_obs = torch.from_numpy(obs).to(dev)
+        grid = torch.empty((S, n_rows, M), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().rrtk_arm_grid_dev(M, theta.data_ptr(), row0, n_rows, len(link), link.ctypes.data,
+                                                d_obs.data_ptr(), S, O, grid.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "rrtk_arm_grid_dev")
+    return grid
+
+
+def get_occupancy_grids(arm, obstacle_sets, M):
+    """Batched form: numpy int64 array [S, M, M] (the reference's dtype)."""
+    return occupancy_grids_device(arm.link_lengths, obstacle_sets, M).cpu().numpy().astype(np.int64)
+
+
+def get_occupancy_grid(arm, obstacles, M):
+    """Drop-in for arm02:79-110: M x M numpy int array, 1 = collision."""
+    obs = np.asarray(obstacles, dtype=np.float64).reshape(1, -1, 3)
+    return get_occupancy_grids(arm, obs, M)[0]

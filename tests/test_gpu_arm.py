@@ -1,0 +1,71 @@
+"""GPU tests of the arm C-space grid against the reference fixtures and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names("arm02_"))
+def test_grid_equals_reference_fixture(name):
+    import rrtk
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m = json.loads(str(g["meta"]))
+    M = m["M"]
+    want = np.unpackbits(g["grid_bits"])[:M * M].reshape(M, M)
+    arm = rrtk.NLinkArm(m["link_length"], [0.0] * len(m["link_length"]))
+    got = rrtk.get_occupancy_grid(arm, m["obstacles"], M)
+    assert got.dtype == np.int64 and got.shape == (M, M)
+    assert np.array_equal(got, want)
+    assert int(got.sum()) == m["occupied"]
+
+
+def test_survey_anchor_counts():
+    """script arm + script obstacles: M=100 -> 5793, M=200 -> 23206; [1,1] arm M=100 -> 5010."""
+    import rrtk
+    obs = [[1.75, 0.75, 0.6], [0.55, 1.5, 0.5], [0, -1, 0.7], [0, -0.6, 0.4], [-1, 1., 0.3]]
+    arm = rrtk.NLinkArm([0.5, 0.5, 0.3, 0.5, 0.1], [0.0] * 5)
+    assert int(rrtk.get_occupancy_grid(arm, obs, 100).sum()) == 5793
+    assert int(rrtk.get_occupancy_grid(arm, obs, 200).sum()) == 23206
+    assert int(rrtk.get_occupancy_grid(rrtk.NLinkArm([1.0, 1.0], [0.0, 0.0]), obs, 100).sum()) == 5010
+
+
+@pytest.mark.parametrize("M,n_links,S,O", [(33, 1, 3, 4), (128, 5, 8, 5), (257, 2, 5, 9), (96, 7, 2, 1), (64, 3, 4, 0)])
+def test_batched_grids_vs_oracle(M, n_links, S, O, oracle_lib):
+    from rrtk import arm as A
+    Or = oracle_lib
+    rng = np.random.default_rng(M * 7 + S)
+    links = rng.uniform(0.1, 0.9, n_links)
+    sets = np.concatenate([rng.uniform(-2, 2, (S, O, 2)), rng.uniform(0.1, 0.7, (S, O, 1))], axis=2)
+    got = A.occupancy_grids_device(links, sets, M).cpu().numpy()
+    for s in range(S):
+        want = Or.arm_grid(M, links, sets[s], Or.MATH_CR) if O > 0 else np.zeros((M, M), np.uint8)
+        assert np.array_equal(got[s], want), (s, int((got[s] != want).sum()))
+
+
+def test_row_sharding_is_invariant(oracle_lib):
+    """Rows computed as two shards (the multi-GPU partition) equal the whole grid."""
+    from rrtk import arm as A
+    rng = np.random.default_rng(3)
+    links = [0.5, 0.5, 0.3, 0.5, 0.1]
+    sets = np.concatenate([rng.uniform(-2, 2, (6, 5, 2)), rng.uniform(0.2, 0.7, (6, 5, 1))], axis=2)
+    M = 200
+    whole = A.occupancy_grids_device(links, sets, M).cpu().numpy()
+    a = A.occupancy_grids_device(links, sets, M, 0, 77).cpu().numpy()
+    b = A.occupancy_grids_device(links, sets, M, 77, M - 77).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b], axis=1), whole)
+
+
+def test_degenerate_zero_length_link(oracle_lib):
+    """A zero-length link makes the reference's projection NaN, which it reports as a collision."""
+    from rrtk import arm as A
+    Or = oracle_lib
+    links = [0.7, 0.0, 0.4]
+    sets = np.array([[[1.0, 0.5, 0.3]]])
+    got = A.occupancy_grids_device(links, sets, 40).cpu().numpy()[0]
+    assert np.array_equal(got, Or.arm_grid(40, links, sets[0], Or.MATH_CR))
+    assert got.all()
