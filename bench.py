@@ -302,19 +302,26 @@ def main():
 
     # ---- end to end: pinned host inputs -> H2D -> kernel -> path extraction -> D2H, every step ----
     path_cap = 256
+    h_path = torch.empty((len(qids), path_cap, 2), dtype=torch.float64).pin_memory()
+    h_plen = torch.empty((len(qids),), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        batch.upload()                                   # pinned host -> device (start/goal, obstacles, counts)
+        r = batch.run()
+        path, plen = r.paths_device(path_cap)            # generate_final_course on the device
+        h_path.copy_(path, non_blocking=True)            # device -> pinned host: what planning() returns
+        h_plen.copy_(plen, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step()                                           # untimed: allocator / pinned-buffer warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        batch.upload()
-        r = batch.run()
-        path, plen = r.paths_device(path_cap)
-        h_path = path.cpu()
-        h_plen = plen.cpu()
+        e2e_step()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = dict(value=total_iters / t_e2e, unit=UNIT, h2d_bytes_per_step=batch.h2d_bytes() * world,
                d2h_bytes_per_step=(h_path.numel() * 8 + h_plen.numel() * 4) * world,
-               result="paths [Q, 256, 2] + lengths")
+               result="paths [Q, 256, 2] + lengths, pinned host buffers")
     found = int((h_plen.numpy() > 0).sum())
 
     # optional final gather of per-query results over NCCL (tiny; not in the timed regions)
