@@ -48,6 +48,7 @@ extern "C" {
 #define RRTK_Q_OK 0
 #define RRTK_Q_NEAR_OVERFLOW 1 /* |near| exceeded near_cap; the query stopped at that iteration */
 #define RRTK_Q_NODE_OVERFLOW 2 /* tree reached node_cap */
+#define RRTK_Q_PATH_OVERFLOW 4 /* best path longer than path_cap (length is still reported) */
 
 /* sampler kinds (get_random_node / get_random_node_sobol, rrt_04:1132-1153) */
 #define RRTK_SAMPLER_STREAM 0  /* read (x, y) per iteration from `sample_stream` */
@@ -135,6 +136,38 @@ RRTK_API int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t
  *   out [Q][max_iter][2]; uses p->sampler, seed, goal_sample_rate, min/max_rand, start_goal */
 RRTK_API int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                            const int64_t *sobol_offset, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched Informed RRT* -- `informed_rrt_star_search` of rrt_07:1044-1108 for Q independent queries:
+ * informed_sample (:1145-1159), get_nearest_list_index (:1210-1214), get_new_node (:1216-1224),
+ * check_collision / check_segment_collision / distance_squared_point_to_segment (:1249-1276),
+ * find_near_nodes (:1137-1143), choose_parent (:1110-1135), rewire (:1232-1246), is_near_goal,
+ * get_final_course, get_path_len and the c_best bookkeeping (:1094-1103).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rrtk_informed_params {
+    int32_t n_queries;
+    int32_t max_iter;
+    int32_t node_cap;    /* >= max_iter + 1 */
+    int32_t obs_stride;
+    int32_t path_cap;    /* capacity of each best-path snapshot */
+    int32_t pad_;
+    double expand_dis;
+} rrtk_informed_params;
+
+/*   start_goal [Q][4]; rot [Q][4] = c00, c01, c10, c11 of the rotation matrix C (rrt_07:1063-1068, host SVD);
+ *   obstacles [Q][obs_stride][4] = x, y, size, size**2 (host-evaluated square, rrt_07:1267); n_obs [Q];
+ *   near_rr2 [node_cap + 1][2] = (r, r**2), r = 50*sqrt(log(n)/n), indexed by n = len(node_list) (:1139);
+ *   free_samples [Q][max_iter][2] = what sample_free_space[_sobol] returns in iteration i (:1173-1191);
+ *   ball_draws [Q][max_iter][2]   = the two random.random() draws of sample_unit_ball (:1162-1171);
+ * outputs: xy [Q][node_cap][2], cost, parent [Q][node_cap], n_nodes [Q],
+ *   path [Q][path_cap][2] + path_len [Q] (0 = None): snapshot of the best path, goal -> start; c_best [Q];
+ *   status [Q];  scratch: ws_idx [Q][node_cap] int32, ws_d [Q][node_cap] double */
+RRTK_API int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goal, const double *rot,
+                                   const double *obstacles, const int32_t *n_obs, const double *near_rr2,
+                                   const double *free_samples, const double *ball_draws, double *xy,
+                                   double *cost, int32_t *parent, int32_t *n_nodes, double *path,
+                                   int32_t *path_len, double *c_best, int32_t *status, int32_t *ws_idx,
+                                   double *ws_d, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.

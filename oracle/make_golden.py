@@ -128,6 +128,71 @@ def c2_params(seed, n_obs, max_iter):
                 max_iter=max_iter, play_area=None, robot_radius=0.0, connect_circle_dist=50.0)
 
 
+def informed_rotation(start, goal):
+    """The rotation matrix C of rrt_07:1054-1068 (numpy SVD), 2 x 2 block, row major."""
+    import math
+    c_min = math.hypot(start[0] - goal[0], start[1] - goal[1])
+    a1 = np.array([[(goal[0] - start[0]) / c_min], [(goal[1] - start[1]) / c_min], [0]])
+    id1_t = np.array([1.0, 0.0, 0.0]).reshape(1, 3)
+    m = a1 @ id1_t
+    u, s, vh = np.linalg.svd(m, True, True)
+    c = u @ np.diag([1.0, 1.0, np.linalg.det(u) * np.linalg.det(np.transpose(vh))]) @ vh
+    return [float(c[0, 0]), float(c[0, 1]), float(c[1, 0]), float(c[1, 1])]
+
+
+def run_rrt07(name, params, seed):
+    """Drive rrt_07's RRT.informed_rrt_star_search with injected per-iteration draws: iteration i gets
+    free[i] from sample_free_space[_sobol] and ball[i] = (a, b) inside sample_unit_ball."""
+    import math
+    ns = ref_loader.load("rrt_07")
+    R = ns["RRT"]
+    rng = np.random.default_rng(seed)
+    n = params["max_iter"]
+    lo, hi = params["rand_area"]
+    free = rng.uniform(lo, hi, (n, 2))
+    coin = rng.integers(0, 101, n) <= params["goal_sample_rate"]
+    free[coin] = params["goal"]
+    ball = rng.random((n, 2))
+    rrt = R(sobol_sampler=False, **params)
+    state = dict(i=-1)
+    orig_informed = rrt.informed_sample
+
+    def informed_sample(c_max, c_min, x_center, c):
+        state["i"] += 1
+        return orig_informed(c_max, c_min, x_center, c)
+
+    def free_space():
+        return [float(free[state["i"], 0]), float(free[state["i"], 1])]
+
+    def unit_ball():
+        a, b = float(ball[state["i"], 0]), float(ball[state["i"], 1])
+        if b < a:
+            a, b = b, a
+        sample = (b * math.cos(2 * math.pi * a / b), b * math.sin(2 * math.pi * a / b))
+        return np.array([[sample[0]], [sample[1]], [0]])
+    rrt.informed_sample = informed_sample
+    rrt.sample_free_space = free_space
+    rrt.sample_free_space_sobol = free_space
+    rrt.sample_unit_ball = unit_ball
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        path = rrt.informed_rrt_star_search(animation=False)
+    wall = time.perf_counter() - t0
+    x, y, c, par = tree_arrays(rrt.node_list)
+    meta = dict(params)
+    meta.update(kind="rrt_07", seed=seed, reference_wall_s=wall, rot=informed_rotation(params["start"], params["goal"]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), free=free, ball=ball,
+                        x=x, y=y, cost=c, parent=par,
+                        path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 2)))
+    print(f"{name}: {len(x)} nodes, {n} iterations, path {0 if path is None else len(path)} waypoints, "
+          f"{wall:.2f} s ({n / wall:.1f} it/s)")
+
+
+C7 = dict(start=[0.0, 0.0], goal=[6.0, 10.0],
+          obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
+          rand_area=[-2, 15], expand_dis=0.5, goal_sample_rate=10, max_iter=200)   # rrt_07:1339-1378
+
+
 def run_arm02(name, M, link_length, obstacles):
     """get_occupancy_grid of the unmodified arm02 (NLinkArm + detect_collision)."""
     ns = ref_loader.load("arm02")
@@ -154,6 +219,12 @@ def _rand_arm_obs(seed, n=5):
 
 
 CASES = {
+    "rrt07_builtin_200": lambda: run_rrt07("rrt07_builtin_200", C7, 1),
+    "rrt07_builtin_1000": lambda: run_rrt07("rrt07_builtin_1000", dict(C7, max_iter=1000), 2),
+    "rrt07_builtin_2500": lambda: run_rrt07("rrt07_builtin_2500", dict(C7, max_iter=2500), 3),
+    "rrt07_alt_800": lambda: run_rrt07("rrt07_alt_800", dict(
+        C7, max_iter=800, start=[1.0, 12.0], goal=[11.5, 1.0], expand_dis=0.8,
+        obstacle_list=[(5, 5, 0.5), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]), 4),
     "arm02_script_m100": lambda: run_arm02("arm02_script_m100", 100, ARM_LINKS, ARM_OBS),
     "arm02_2link_m100": lambda: run_arm02("arm02_2link_m100", 100, [1.0, 1.0], ARM_OBS),
     "arm02_script_m51_rand": lambda: run_arm02("arm02_script_m51_rand", 51, ARM_LINKS, _rand_arm_obs(5)),

@@ -183,3 +183,33 @@ def arm_grid(M, link_lengths, obstacles, math_mode=MATH_LIBM, row0=0, n_rows=Non
     if rc:
         raise ValueError("orc_arm_grid: bad arguments")
     return grid
+
+
+class InformedParams(C.Structure):
+    _fields_ = [("sx", C.c_double), ("sy", C.c_double), ("gx", C.c_double), ("gy", C.c_double),
+                ("expand_dis", C.c_double), ("rot", C.c_double * 4), ("max_iter", C.c_int32),
+                ("n_obs", C.c_int32), ("math_mode", C.c_int32), ("path_cap", C.c_int32)]
+
+
+def informed_run(start, goal, obstacle_list, expand_dis, max_iter, rot, free, ball, math_mode=MATH_LIBM,
+                 path_cap=4096):
+    """rrt_07 informed_rrt_star_search with injected draws -> dict(x, y, cost, parent, n, path, c_best)."""
+    p = InformedParams()
+    p.sx, p.sy, p.gx, p.gy = float(start[0]), float(start[1]), float(goal[0]), float(goal[1])
+    p.expand_dis = float(expand_dis)
+    for i in range(4):
+        p.rot[i] = float(rot[i])
+    p.max_iter, p.math_mode, p.path_cap = int(max_iter), int(math_mode), int(path_cap)
+    obs4 = np.array([[ox, oy, s, s ** 2] for ox, oy, s in obstacle_list], dtype=np.float64).reshape(-1, 4)
+    p.n_obs = obs4.shape[0]
+    free = np.ascontiguousarray(free, dtype=np.float64).reshape(-1, 2)
+    ball = np.ascontiguousarray(ball, dtype=np.float64).reshape(-1, 2)
+    cap = max_iter + 1
+    x = np.zeros(cap); y = np.zeros(cap); cost = np.zeros(cap); parent = np.full(cap, -1, np.int32)
+    path = np.zeros((path_cap, 2)); n = C.c_int32(); plen = C.c_int32(); cb = C.c_double()
+    lib().orc_informed_run(C.byref(p), _p(obs4, C.c_double), _p(free, C.c_double), _p(ball, C.c_double),
+                           _p(x, C.c_double), _p(y, C.c_double), _p(cost, C.c_double), _p(parent, C.c_int32),
+                           C.byref(n), _p(path, C.c_double), C.byref(plen), C.byref(cb))
+    k = n.value
+    return dict(x=x[:k], y=y[:k], cost=cost[:k], parent=parent[:k], n=k, c_best=cb.value,
+                path=None if plen.value == 0 else path[:plen.value].tolist())

@@ -522,3 +522,154 @@ ORC_EXPORT int orc_arm_grid(int32_t M, const double *theta, int32_t row0, int32_
         }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Informed RRT* (rrt_07:1027-1285)                                                      */
+/* ------------------------------------------------------------------------------------ */
+/* check_segment_collision + distance_squared_point_to_segment (rrt_07:1249-1269); obs rows are
+ * (x, y, size, size**2) with the square taken by the host as Python does.  1 = free */
+static int segment_free(double x1, double y1, double x2, double y2, const double *obs4, int n_obs) {
+    for (int o = 0; o < n_obs; o++) {
+        double ox = obs4[4 * o], oy = obs4[4 * o + 1], r2 = obs4[4 * o + 3];
+        double dd;
+        if (x1 == x2 && y1 == y2) {
+            dd = dot2(ox - x1, oy - y1, ox - x1, oy - y1);
+        } else {
+            double wx = x2 - x1, wy = y2 - y1;
+            double l2 = dot2(wx, wy, wx, wy);
+            double t = dot2(ox - x1, oy - y1, wx, wy) / l2;
+            t = t < 1.0 ? t : 1.0;   /* min(1, t); a NaN t stays NaN like Python's min/max chain... */
+            t = t > 0.0 ? t : 0.0;   /* ...then max(0, nan) = 0 in Python because `nan > 0` is False */
+            double px = x1 + t * wx, py = y1 + t * wy;
+            dd = dot2(ox - px, oy - py, ox - px, oy - py);
+        }
+        if (dd <= r2) return 0;
+    }
+    return 1;
+}
+
+typedef struct {
+    double sx, sy, gx, gy;
+    double expand_dis;
+    double rot[4];      /* 2 x 2 block of C (rrt_07:1063-1068), host-evaluated */
+    int32_t max_iter, n_obs, math_mode, path_cap;
+} orc_informed_params_t;
+
+static void dir_trig(int mode, double dy, double dx, double *theta, double *s, double *c) {
+    if (mode == ORC_MATH_LIBM) { *theta = atan2(dy, dx); *c = cos(*theta); *s = sin(*theta); }
+    else *theta = crm_atan2_sincos(dy, dx, s, c);
+}
+
+/* check_collision (rrt_07:1271-1276) given cos/sin of theta */
+static int inf_check(double x, double y, double c, double s, double d, const double *obs4, int n_obs) {
+    return segment_free(x, y, x + c * d, y + s * d, obs4, n_obs);
+}
+
+ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *obs4, const double *free_s,
+                                const double *ball, double *x, double *y, double *cost, int32_t *parent,
+                                int32_t *n_nodes, double *path /* [path_cap][2] */, int32_t *path_len,
+                                double *c_best_out) {
+    const int mode = p->math_mode;
+    int cap = p->max_iter + 1, n = 1;
+    double *dl = (double *)malloc(sizeof(double) * cap);
+    int *near = (int *)malloc(sizeof(int) * cap);
+    x[0] = p->sx; y[0] = p->sy; cost[0] = 0.0; parent[0] = -1;
+    double c_best = INFINITY;
+    const double c_min = orc_hypot(p->sx - p->gx, p->sy - p->gy);
+    const double xc = (p->sx + p->gx) / 2.0, yc = (p->sy + p->gy) / 2.0, ed = p->expand_dis;
+    *path_len = 0;
+    for (int it = 0; it < p->max_iter; it++) {
+        double rx, ry;
+        if (c_best < INFINITY) { /* informed_sample rrt_07:1145-1159 */
+            double r0 = c_best / 2.0;
+            double r1 = sqrt(sq(mode, c_best) - sq(mode, c_min)) / 2.0;
+            double a = ball[2 * it], b = ball[2 * it + 1];
+            if (b < a) { double t = a; a = b; b = t; }
+            double ang = 2 * 3.141592653589793 * a / b, bx, by; /* Python: 2 * math.pi * a / b */
+            if (mode == ORC_MATH_LIBM) { bx = b * cos(ang); by = b * sin(ang); }
+            else { bx = b * crm_cos(ang); by = b * crm_sin(ang); }
+            double m00 = p->rot[0] * r0, m01 = p->rot[1] * r1, m10 = p->rot[2] * r0, m11 = p->rot[3] * r1;
+            rx = fma(m00, bx, m01 * by) + xc; /* numpy (3x3)@(3x1) on this platform, see DESIGN.md */
+            ry = fma(m10, bx, m11 * by) + yc;
+        } else {
+            rx = free_s[2 * it]; ry = free_s[2 * it + 1];
+        }
+        int ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(mode, x[i] - rx) + sq(mode, y[i] - ry);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double theta, st, ct;
+        dir_trig(mode, ry - y[ni], rx - x[ni], &theta, &st, &ct);
+        double nx = x[ni] + ed * ct, ny = y[ni] + ed * st; /* get_new_node rrt_07:1216-1224 */
+        double ncost = cost[ni] + ed;
+        int npar = ni;
+        double d = orc_hypot(x[ni] - nx, y[ni] - ny);
+        if (!inf_check(x[ni], y[ni], ct, st, d, obs4, p->n_obs)) continue;
+        /* find_near_nodes rrt_07:1137-1143 */
+        double r = 50.0 * sqrt(log((double)n) / (double)n);
+        double r2 = sq_libm(r); /* per-size constant: host libm in the product too */
+        int n_near = 0;
+        for (int i = 0; i < n; i++) dl[i] = sq(mode, x[i] - nx) + sq(mode, y[i] - ny);
+        for (int i = 0; i < n; i++)
+            if (dl[i] <= r2) {
+                int f = 0;
+                while (dl[f] != dl[i]) f++;
+                near[n_near++] = f;
+            }
+        /* choose_parent rrt_07:1110-1135 */
+        double mc = INFINITY;
+        int best = -1;
+        for (int k = 0; k < n_near; k++) {
+            int i = near[k];
+            double dx = nx - x[i], dy = ny - y[i], th, s2, c2;
+            double dd = orc_hypot(dx, dy);
+            dir_trig(mode, dy, dx, &th, &s2, &c2);
+            double c = inf_check(x[i], y[i], c2, s2, dd, obs4, p->n_obs) ? cost[i] + dd : INFINITY;
+            if (c < mc) { mc = c; best = i; }
+        }
+        if (best >= 0) { ncost = mc; npar = best; }
+        x[n] = nx; y[n] = ny; cost[n] = ncost; parent[n] = npar;
+        int newi = n;
+        n++;
+        /* rewire rrt_07:1232-1246 */
+        for (int k = 0; k < n_near; k++) {
+            int i = near[k];
+            double dd = orc_hypot(x[i] - nx, y[i] - ny);
+            double sc = ncost + dd;
+            if (cost[i] > sc) {
+                double th, s2, c2;
+                dir_trig(mode, ny - y[i], nx - x[i], &th, &s2, &c2);
+                if (inf_check(x[i], y[i], c2, s2, dd, obs4, p->n_obs)) { parent[i] = newi; cost[i] = sc; }
+            }
+        }
+        /* goal bookkeeping rrt_07:1094-1103 */
+        if (orc_hypot(nx - p->gx, ny - p->gy) < ed && segment_free(nx, ny, p->gx, p->gy, obs4, p->n_obs)) {
+            double plen = 0.0, qx = p->gx, qy = p->gy;
+            int k = newi, len = 1;
+            while (parent[k] >= 0) {
+                plen += orc_hypot(x[k] - qx, y[k] - qy);
+                qx = x[k]; qy = y[k];
+                k = parent[k]; len++;
+            }
+            plen += orc_hypot(p->sx - qx, p->sy - qy);
+            len++;
+            if (plen < c_best) {
+                c_best = plen;
+                int w = 0;
+                if (w < p->path_cap) { path[0] = p->gx; path[1] = p->gy; }
+                w++;
+                for (k = newi; parent[k] >= 0; k = parent[k], w++)
+                    if (w < p->path_cap) { path[2 * w] = x[k]; path[2 * w + 1] = y[k]; }
+                if (w < p->path_cap) { path[2 * w] = p->sx; path[2 * w + 1] = p->sy; }
+                w++;
+                *path_len = w;
+            }
+        }
+    }
+    *n_nodes = n;
+    *c_best_out = c_best;
+    free(dl); free(near);
+    return 0;
+}

@@ -40,6 +40,11 @@ int launch_nearest(const float *xy, long long n, const float *samples, int B, un
 int launch_near(const float *xy, long long n, float cx, float cy, float r2, int *out_idx, int cap, int *out_n,
                 cudaStream_t s);
 int launch_fma_peak(int fp64, int iters, int blocks, void *out, cudaStream_t s);
+int launch_informed(const rrtk_informed_params &p, const double *start_goal, const double *rot,
+                    const double *obstacles, const int32_t *n_obs, const double *near_rr2, const double *free_s,
+                    const double *ball, double *xy, double *cost, int32_t *parent, int32_t *n_nodes, double *path,
+                    int32_t *path_len, double *c_best, int32_t *status, int32_t *ws_idx, double *ws_d,
+                    unsigned int *counter, cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -131,6 +136,27 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
     return launch_rrtstar(*p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost,
                           parent, n_nodes, iters_done, goal_index, status, trace, workspace, ctr.ptr, s);
+}
+
+int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goal, const double *rot,
+                          const double *obstacles, const int32_t *n_obs, const double *near_rr2,
+                          const double *free_samples, const double *ball_draws, double *xy, double *cost,
+                          int32_t *parent, int32_t *n_nodes, double *path, int32_t *path_len, double *c_best,
+                          int32_t *status, int32_t *ws_idx, double *ws_d, void *stream) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->n_queries < 0 || p->max_iter < 0 || p->node_cap < 1 || p->path_cap < 2 || p->obs_stride < 0)
+        return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (!(p->expand_dis > 0.0)) return set_error(RRTK_ERR_INVALID, "expand_dis must be > 0");
+    if (p->n_queries == 0) return RRTK_OK;
+    if (!start_goal || !rot || !n_obs || !near_rr2 || !xy || !cost || !parent || !n_nodes || !path || !path_len ||
+        !c_best || !status || !ws_idx || !ws_d || (p->max_iter > 0 && (!free_samples || !ball_draws)) ||
+        (p->obs_stride > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    DevCounter ctr(s);
+    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    return launch_informed(*p, start_goal, rot, obstacles, n_obs, near_rr2, free_samples, ball_draws, xy, cost, parent,
+                           n_nodes, path, path_len, c_best, status, ws_idx, ws_d, ctr.ptr, s);
 }
 
 int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,

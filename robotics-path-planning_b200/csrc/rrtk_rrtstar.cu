@@ -21,6 +21,7 @@
 #include "../../include/rrtk.h"
 #include "crmath.h"
 #include "rrtk_device.cuh"
+#include "rrtk_planner.cuh"
 
 namespace rrtk {
 
@@ -36,8 +37,6 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef RRTK_UNROLL_PROP
 #define RRTK_UNROLL_PROP 1
 #endif
-constexpr int CULL_CAP = 64;      // culled obstacle list per warp (overflow -> full list)
-constexpr unsigned FULL = 0xffffffffu;
 
 struct Steer {
     double ex, ey;    // end point
@@ -77,12 +76,6 @@ __device__ __noinline__ Steer steer(double fx, double fy, double tx, double ty, 
     st.n = n;
     return st;
 }
-
-struct ObsList {  // SoA view of the obstacles an edge must be tested against
-    const double *ox, *oy, *r2;
-    int stride;  // element stride (1 for the shared-memory list, 4 for the global AoS rows)
-    int m;
-};
 
 // check_collision (rrt_04:1216-1230) of one edge by ONE lane: any path point within any circle.
 __device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
@@ -133,16 +126,6 @@ __device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double
     return !(x < p.play_area[0] || x > p.play_area[1] || y < p.play_area[2] || y > p.play_area[3]);
 }
 
-// warp argmin of (value, index): smaller value wins, ties -> smaller index (list.index(min(..)))
-__device__ __forceinline__ void warp_argmin(double &v, int &i) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        double ov = __shfl_xor_sync(FULL, v, off);
-        int oi = __shfl_xor_sync(FULL, i, off);
-        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-}
-
 // per-warp shared memory
 struct WarpSmem {
     // obstacles near the new node of the current iteration (re-used for the goal by best_goal)
@@ -156,44 +139,6 @@ __host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
     size_t words = (size_t)(node_cap + 31) / 32;
     size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 2) + words * 4 * 2;
     return (b + 15) & ~(size_t)15;
-}
-
-// Conservative exact cull: keep obstacle o iff |o - c| <= (reach + R_o) * (1 + 1e-9) + 1e-9.
-// Returns the list to test edges against (shared-memory survivors, or all obstacles on overflow).
-__device__ __noinline__ ObsList cull_obstacles(const double4 *obs, int n_obs, double cx, double cy,
-                                                  double reach, double *sx, double *sy, double *sr2,
-                                                  int lane) {
-    int count = 0;
-    bool overflow = false;
-#pragma unroll 2
-    for (int base = 0; base < n_obs; base += 32) {
-        int j = base + lane;
-        bool keep = false;
-        double4 o = make_double4(0, 0, 0, 0);
-        if (j < n_obs) {
-            o = obs[j];
-            double dx = o.x - cx, dy = o.y - cy;
-            double lim = (reach + o.z) * (1.0 + 1e-9) + 1e-9;
-            keep = dx * dx + dy * dy <= lim * lim;
-        }
-        unsigned mask = __ballot_sync(FULL, keep);
-        int pos = count + __popc(mask & ((1u << lane) - 1u));
-        if (keep) {
-            if (pos < CULL_CAP) { sx[pos] = o.x; sy[pos] = o.y; sr2[pos] = o.w; }
-            else overflow = true;
-        }
-        count += __popc(mask);
-    }
-    overflow = __any_sync(FULL, overflow);
-    __syncwarp();
-    ObsList L;
-    if (!overflow) {
-        L.ox = sx; L.oy = sy; L.r2 = sr2; L.stride = 1; L.m = count;
-    } else {
-        const double *g = reinterpret_cast<const double *>(obs);
-        L.ox = g; L.oy = g + 1; L.r2 = g + 3; L.stride = 4; L.m = n_obs;
-    }
-    return L;
 }
 
 // propagate_cost_to_leaves (rrt_04:1379-1384): level-synchronous sweeps over the parent array.

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRTK_LIB", os.path.join(HERE, "librrtk.so"))  # override: tuning builds only
 
 SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
-Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW = 0, 1, 2
+Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW = 0, 1, 2, 4
 
 
 class RrtkError(RuntimeError):
@@ -27,6 +27,13 @@ class RRTStarParams(C.Structure):
                 ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64)]
 
 
+class InformedParams(C.Structure):
+    """struct rrtk_informed_params (include/rrtk.h)."""
+    _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
+                ("obs_stride", C.c_int32), ("path_cap", C.c_int32), ("pad_", C.c_int32),
+                ("expand_dis", C.c_double)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -39,6 +46,7 @@ _SIGS = {
     "rrtk_sobol_table": (C.c_int, [C.c_int, _VP]),
     "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 16),
     "rrtk_rrtstar_run_host": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 14),
+    "rrtk_informed_run_dev": (C.c_int, [C.POINTER(InformedParams)] + [_VP] * 18),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),

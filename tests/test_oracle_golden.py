@@ -126,3 +126,57 @@ def test_sobol_closed_form_matches_reference_points(oracle_lib):
     lo, hi = m["rand_area"]
     assert np.array_equal(lo + q * (hi - lo), s[nongoal])
     assert int(nongoal.sum()) == m["sobol_inter"]
+
+
+# ---- Informed RRT* (rrt_07) ----
+RRT07 = golden_names("rrt07_")
+
+
+@pytest.mark.parametrize("name", [n for n in RRT07 if "2500" not in n])
+def test_informed_python_port_bit_identical_to_reference(name):
+    import pyport
+    g, m = load_golden(name)
+    p = pyport.InformedRRTStarPort(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"])
+    path = p.search([tuple(r) for r in g["free"]], [tuple(r) for r in g["ball"]])
+    assert np.array_equal(np.array(p.x), g["x"]) and np.array_equal(np.array(p.y), g["y"])
+    assert np.array_equal(np.array(p.cost), g["cost"]) and np.array_equal(np.array(p.parent), g["parent"])
+    assert np.array_equal(np.array(path, float), g["path"])
+
+
+@pytest.mark.parametrize("name", RRT07)
+def test_informed_c_oracle_libm_bit_identical_to_reference(name, oracle_lib):
+    O = oracle_lib
+    g, m = load_golden(name)
+    r = O.informed_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"],
+                       g["free"], g["ball"], O.MATH_LIBM)
+    assert r["n"] == len(g["x"])
+    assert np.array_equal(r["x"], g["x"]) and np.array_equal(r["y"], g["y"])
+    assert np.array_equal(r["cost"], g["cost"]) and np.array_equal(r["parent"], g["parent"])
+    assert np.array_equal(np.array(r["path"], float), g["path"])
+
+
+@pytest.mark.parametrize("name", [n for n in RRT07 if "2500" not in n])
+def test_informed_c_oracle_cr_bit_identical_to_reference(name, oracle_lib):
+    O = oracle_lib
+    g, m = load_golden(name)
+    r = O.informed_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"],
+                       g["free"], g["ball"], O.MATH_CR)
+    assert np.array_equal(r["x"], g["x"]) and np.array_equal(r["cost"], g["cost"])
+    assert np.array_equal(r["parent"], g["parent"])
+    assert np.array_equal(np.array(r["path"], float), g["path"])
+
+
+def test_informed_cr_divergence_is_small(oracle_lib):
+    """rrt07_builtin_2500: cr and libm arithmetic differ through one ulp-level tie; the trees keep the same
+    size and the best path cost agrees to 1e-5 relative (north_star's tolerance)."""
+    O = oracle_lib
+    g, m = load_golden("rrt07_builtin_2500")
+    a = O.informed_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"],
+                       g["free"], g["ball"], O.MATH_LIBM)
+    b = O.informed_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"],
+                       g["free"], g["ball"], O.MATH_CR)
+    assert a["n"] == b["n"]
+    same = (a["x"] == b["x"]) & (a["y"] == b["y"])
+    first = int(np.argmin(same)) if not same.all() else a["n"]
+    assert first > 100                      # identical for a long prefix
+    assert abs(a["c_best"] - b["c_best"]) <= 1e-5 * a["c_best"]
