@@ -170,6 +170,23 @@ RRTK_API int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *
                                    double *ws_d, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched Dubins steering: plan_dubins_path (rrt_05:1021-1109 == dub00) + the sampled collision test of
+ * the course (check_collision rrt_05:1625-1638) -- one edge of RRT*-Dubins' `steer` (rrt_05:1458-1479).
+ *   from3, to3 [N][3] = x, y, yaw;  curvature, step_size (0.1 in the reference)
+ *   obs_set [N] or NULL (all requests use set 0): obstacle set of each request
+ *   obstacles [S][obs_stride][4] = x, y, size + robot_radius, (size + robot_radius)**2 ; n_obs [S] (or NULL: none)
+ * outputs: mode [N] (0..5 = LSL,RSR,LSR,RSL,RLR,LRL in _PATH_TYPE_MAP order, -1 = none),
+ *   lengths [N][3] (segment lengths / curvature), end [N][3] (last course point x, y, yaw),
+ *   n_pts [N] (len(px); steer returns None when <= 1), free [N] uint8 (1 = no course point inside a circle),
+ *   pts [N][max_pts][3] or NULL (course points x, y, yaw in order)
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_size, const double *from3,
+                                   const double *to3, const int32_t *obs_set, const double *obstacles,
+                                   int32_t obs_stride, const int32_t *n_obs, int32_t *mode, double *lengths,
+                                   double *end, int32_t *n_pts, uint8_t *free_flag, double *pts,
+                                   int32_t max_pts, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.
  *   rrtk_nearest_f32_dev: get_nearest_node_index (rrt_04:1196-1202, rrt_07:1210-1214) for B samples in
  *     one pass over the n nodes; idx[b] = argmin_i |xy[i] - samples[b]|^2 with the LOWEST index on exact
@@ -204,6 +221,7 @@ RRTK_API int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)
+ *   kind 6: acos(a[i])
  * ------------------------------------------------------------------------------------------- */
 RRTK_API int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out,
                           void *stream);

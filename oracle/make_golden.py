@@ -188,6 +188,35 @@ def run_rrt07(name, params, seed):
           f"{wall:.2f} s ({n / wall:.1f} it/s)")
 
 
+def run_dubins(name, n, seed):
+    """plan_dubins_path of the unmodified rrt_05 on seeded random pose pairs (+ the docstring example)."""
+    import math
+    ns = ref_loader.load("rrt_05")
+    f = ns["plan_dubins_path"]
+    rng = np.random.default_rng(seed)
+    rows = []
+    pts_all, off = [], [0]
+    for i in range(n):
+        if i == 0:
+            s, g, kappa = [1.0, 1.0, math.radians(45.0)], [-3.0, -3.0, math.radians(-45.0)], 1.0   # rrt_05:1067-1075
+        else:
+            s = [float(rng.uniform(-2, 15)), float(rng.uniform(-2, 15)), float(rng.uniform(-math.pi, math.pi))]
+            if i % 3 == 0:   # close goals: the CCC words win
+                g = [s[0] + float(rng.uniform(-3, 3)), s[1] + float(rng.uniform(-3, 3)), float(rng.uniform(-math.pi, math.pi))]
+            else:
+                g = [float(rng.uniform(-2, 15)), float(rng.uniform(-2, 15)), float(rng.uniform(-math.pi, math.pi))]
+            kappa = float(rng.choice([1.0, 1.0, 0.5, 2.0]))
+        x, y, yaw, mode, lengths = f(s[0], s[1], s[2], g[0], g[1], g[2], kappa)
+        mi = ["LSL", "RSR", "LSR", "RSL", "RLR", "LRL"].index("".join(mode))
+        rows.append(s + g + [kappa, mi] + [float(v) for v in lengths] + [len(x)])
+        pts_all.append(np.column_stack([x, y, yaw]))
+        off.append(off[-1] + len(x))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(dict(kind="dubins", n=n, seed=seed)),
+                        cases=np.array(rows, dtype=np.float64), pts=np.vstack(pts_all), offsets=np.array(off))
+    print(f"{name}: {n} pose pairs, {off[-1]} course points, modes "
+          f"{np.bincount(np.array(rows)[:, 7].astype(int), minlength=6).tolist()}")
+
+
 C7 = dict(start=[0.0, 0.0], goal=[6.0, 10.0],
           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
           rand_area=[-2, 15], expand_dis=0.5, goal_sample_rate=10, max_iter=200)   # rrt_07:1339-1378
@@ -219,6 +248,7 @@ def _rand_arm_obs(seed, n=5):
 
 
 CASES = {
+    "dubins_pairs_150": lambda: run_dubins("dubins_pairs_150", 150, 21),
     "rrt07_builtin_200": lambda: run_rrt07("rrt07_builtin_200", C7, 1),
     "rrt07_builtin_1000": lambda: run_rrt07("rrt07_builtin_1000", dict(C7, max_iter=1000), 2),
     "rrt07_builtin_2500": lambda: run_rrt07("rrt07_builtin_2500", dict(C7, max_iter=2500), 3),

@@ -45,7 +45,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB_PATH)
         for name, nargs in (("orc_hypot", 2), ("orc_cr_hypot", 2), ("orc_cr_sin", 1),
-                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2)):
+                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2), ("orc_cr_acos", 1)):
             f = getattr(_lib, name)
             f.restype = C.c_double
             f.argtypes = [C.c_double] * nargs
@@ -213,3 +213,23 @@ def informed_run(start, goal, obstacle_list, expand_dis, max_iter, rot, free, ba
     k = n.value
     return dict(x=x[:k], y=y[:k], cost=cost[:k], parent=parent[:k], n=k, c_best=cb.value,
                 path=None if plen.value == 0 else path[:plen.value].tolist())
+
+
+DUBINS_MODES = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
+
+
+def dubins_plan(s, g, curvature=1.0, step=0.1, math_mode=MATH_LIBM, max_pts=2048):
+    """plan_dubins_path (rrt_05:1021-1109) -> dict(mode, lengths [3], pts [n, 3] = x, y, yaw)."""
+    L = lib()
+    L.orc_dubins_plan.restype = C.c_int
+    L.orc_dubins_plan.argtypes = [C.c_double] * 8 + [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                                    C.POINTER(C.c_double), C.c_int32]
+    mode = C.c_int32()
+    lengths = np.zeros(3)
+    pts = np.zeros((max_pts, 3))
+    n = L.orc_dubins_plan(float(s[0]), float(s[1]), float(s[2]), float(g[0]), float(g[1]), float(g[2]),
+                          float(curvature), float(step), int(math_mode), C.byref(mode), _p(lengths, C.c_double),
+                          _p(pts, C.c_double), max_pts)
+    if n < 0:
+        return None
+    return dict(mode=mode.value, lengths=lengths, pts=pts[:min(n, max_pts)], n=n)

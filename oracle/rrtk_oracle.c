@@ -90,6 +90,7 @@ ORC_EXPORT double orc_cr_sin(double x) { return crm_sin(x); }
 ORC_EXPORT double orc_cr_cos(double x) { return crm_cos(x); }
 ORC_EXPORT double orc_cr_atan2(double y, double x) { return crm_atan2(y, x); }
 ORC_EXPORT double orc_cr_hypot(double a, double b) { return crm_hypot(a, b); }
+ORC_EXPORT double orc_cr_acos(double x) { return crm_acos(x); }
 ORC_EXPORT double orc_cr_atan2_sincos(double y, double x, double *s, double *c) {
     return crm_atan2_sincos(y, x, s, c);
 }
@@ -672,4 +673,159 @@ ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *ob
     *c_best_out = c_best;
     free(dl); free(near);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Dubins local planner (rrt_05:935-1278 == dub00)                                       */
+/* ------------------------------------------------------------------------------------ */
+#define ORC_TWO_PI 6.283185307179586 /* 2 * math.pi */
+#define ORC_PI 3.141592653589793
+
+typedef struct { int mode; } orc_math_t;
+static inline double m_sin(int m, double x) { return m == ORC_MATH_LIBM ? sin(x) : crm_sin(x); }
+static inline double m_cos(int m, double x) { return m == ORC_MATH_LIBM ? cos(x) : crm_cos(x); }
+static inline double m_atan2(int m, double y, double x) { return m == ORC_MATH_LIBM ? atan2(y, x) : crm_atan2(y, x); }
+static inline double m_acos(int m, double x) { return m == ORC_MATH_LIBM ? acos(x) : crm_acos(x); }
+
+/* Python float `%` (== numpy mod): fmod, then move into the sign of the divisor */
+static inline double py_mod(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0) { if ((b < 0) != (r < 0)) r += b; }
+    else r = copysign(0.0, b);
+    return r;
+}
+static inline double mod2pi(double t) { return py_mod(t, ORC_TWO_PI); }              /* rrt_05:1112 */
+static inline double angle_mod_pi(double x) { return py_mod(x + ORC_PI, ORC_TWO_PI) - ORC_PI; } /* :1005 */
+
+/* rot_mat_2d(angle) = [[c, -s], [s, c]] through SciPy's quaternion (see oracle/pyport.py) */
+static void rot2d(int m, double angle, double *c, double *s) {
+    double z = m_sin(m, angle / 2), w = m_cos(m, angle / 2);
+    *c = w * w - z * z;
+    *s = 2 * (z * w);
+}
+
+/* word k of _PATH_TYPE_MAP order LSL,RSR,LSR,RSL,RLR,LRL (rrt_05:1125-1198); returns 0 if infeasible */
+static int dubins_word(int m, int k, double alpha, double beta, double d, double *w) {
+    double sa = m_sin(m, alpha), sb = m_sin(m, beta), ca = m_cos(m, alpha), cb = m_cos(m, beta);
+    double cab = m_cos(m, alpha - beta);
+    double d2 = sq(m, d), p2, tmp, d1;
+    switch (k) {
+        case 0:
+            p2 = 2 + d2 - (2 * cab) + (2 * d * (sa - sb));
+            if (p2 < 0) return 0;
+            tmp = m_atan2(m, (cb - ca), d + sa - sb);
+            w[0] = mod2pi(-alpha + tmp); w[1] = sqrt(p2); w[2] = mod2pi(beta - tmp);
+            return 1;
+        case 1:
+            p2 = 2 + d2 - (2 * cab) + (2 * d * (sb - sa));
+            if (p2 < 0) return 0;
+            tmp = m_atan2(m, (ca - cb), d - sa + sb);
+            w[0] = mod2pi(alpha - tmp); w[1] = sqrt(p2); w[2] = mod2pi(-beta + tmp);
+            return 1;
+        case 2:
+            p2 = -2 + d2 + (2 * cab) + (2 * d * (sa + sb));
+            if (p2 < 0) return 0;
+            d1 = sqrt(p2);
+            tmp = m_atan2(m, (-ca - cb), (d + sa + sb)) - m_atan2(m, -2.0, d1);
+            w[0] = mod2pi(-alpha + tmp); w[1] = d1; w[2] = mod2pi(-mod2pi(beta) + tmp);
+            return 1;
+        case 3:
+            p2 = d2 - 2 + (2 * cab) - (2 * d * (sa + sb));
+            if (p2 < 0) return 0;
+            d1 = sqrt(p2);
+            tmp = m_atan2(m, (ca + cb), (d - sa - sb)) - m_atan2(m, 2.0, d1);
+            w[0] = mod2pi(alpha - tmp); w[1] = d1; w[2] = mod2pi(beta - tmp);
+            return 1;
+        case 4:
+            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
+            if (fabs(tmp) > 1.0) return 0;
+            w[1] = mod2pi(2 * ORC_PI - m_acos(m, tmp));
+            w[0] = mod2pi(alpha - m_atan2(m, ca - cb, d - sa + sb) + w[1] / 2.0);
+            w[2] = mod2pi(alpha - beta - w[0] + w[1]);
+            return 1;
+        default:
+            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (-sa + sb)) / 8.0;
+            if (fabs(tmp) > 1.0) return 0;
+            w[1] = mod2pi(2 * ORC_PI - m_acos(m, tmp));
+            w[0] = mod2pi(-alpha - m_atan2(m, ca - cb, d + sa - sb) + w[1] / 2.0);
+            w[2] = mod2pi(mod2pi(beta) - alpha - w[0] + mod2pi(w[1]));
+            return 1;
+    }
+}
+
+static const char k_dubins_modes[6][4] = {"LSL", "RSR", "LSR", "RSL", "RLR", "LRL"};
+
+/* _interpolate (rrt_05:1232-1255) */
+static void dubins_interp(int m, double length, char mode, double kappa, double ox, double oy, double oyaw,
+                          double *x, double *y, double *yaw) {
+    if (mode == 'S') {
+        *x = ox + length / kappa * m_cos(m, oyaw);
+        *y = oy + length / kappa * m_sin(m, oyaw);
+        *yaw = oyaw;
+    } else {
+        double ldx = m_sin(m, length) / kappa, ldy;
+        if (mode == 'L') ldy = (1.0 - m_cos(m, length)) / kappa;
+        else ldy = (1.0 - m_cos(m, length)) / -kappa;
+        double gdx = m_cos(m, -oyaw) * ldx + m_sin(m, -oyaw) * ldy;
+        double gdy = -m_sin(m, -oyaw) * ldx + m_cos(m, -oyaw) * ldy;
+        *x = ox + gdx;
+        *y = oy + gdy;
+        *yaw = mode == 'L' ? oyaw + length : oyaw - length;
+    }
+}
+
+/* plan_dubins_path (rrt_05:1021-1109).  out_xyyaw [max_pts][3] may be NULL.  Returns the number of points. */
+ORC_EXPORT int orc_dubins_plan(double s_x, double s_y, double s_yaw, double g_x, double g_y, double g_yaw,
+                               double kappa, double step, int math_mode, int32_t *mode_out, double *lengths,
+                               double *out_xyyaw, int32_t max_pts) {
+    const int m = math_mode;
+    double c, s;
+    rot2d(m, s_yaw, &c, &s);
+    double vx = g_x - s_x, vy = g_y - s_y;
+    double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s); /* numpy (2,)@(2,2) on this platform */
+    double lgyaw = g_yaw - s_yaw;
+    double d = orc_hypot(lgx, lgy) * kappa;
+    double theta = mod2pi(m_atan2(m, lgy, lgx));
+    double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
+    double best_cost = INFINITY, bw[3] = {0, 0, 0};
+    int bi = -1;
+    for (int k = 0; k < 6; k++) {
+        double w[3];
+        if (!dubins_word(m, k, alpha, beta, d, w)) continue;
+        double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+        if (best_cost > cost) { best_cost = cost; bi = k; bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2]; }
+    }
+    if (bi < 0) return -1;
+    *mode_out = bi;
+    for (int k = 0; k < 3; k++) lengths[k] = bw[k] / kappa;
+    double c2, s2;
+    rot2d(m, -s_yaw, &c2, &s2);
+    /* _generate_local_course (rrt_05:1258-1278), each local point converted to the world frame */
+    int np = 0;
+    double lx = 0.0, ly = 0.0, lyaw = 0.0;
+#define EMIT(px, py, pyaw)                                                                   \
+    do {                                                                                     \
+        if (out_xyyaw && np < max_pts) {                                                     \
+            out_xyyaw[3 * np] = fma((py), s2, (px) * c2) + s_x;                              \
+            out_xyyaw[3 * np + 1] = fma((py), c2, (px) * -s2) + s_y;                          \
+            out_xyyaw[3 * np + 2] = angle_mod_pi((pyaw) + s_yaw);                            \
+        }                                                                                    \
+        np++;                                                                                \
+    } while (0)
+    EMIT(lx, ly, lyaw);
+    for (int k = 0; k < 3; k++) {
+        double length = bw[k];
+        char md = k_dubins_modes[bi][k];
+        if (length == 0.0) continue;
+        double ox = lx, oy = ly, oyaw = lyaw, cur = step;
+        while (fabs(cur + step) <= fabs(length)) {
+            dubins_interp(m, cur, md, kappa, ox, oy, oyaw, &lx, &ly, &lyaw);
+            EMIT(lx, ly, lyaw);
+            cur += step;
+        }
+        dubins_interp(m, length, md, kappa, ox, oy, oyaw, &lx, &ly, &lyaw);
+        EMIT(lx, ly, lyaw);
+    }
+#undef EMIT
+    return np;
 }

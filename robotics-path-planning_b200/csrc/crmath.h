@@ -275,4 +275,27 @@ CRM_FN double crm_atan2(double y, double x) {
     return crm_atan2_sincos(y, x, &s, &c);
 }
 
+/* RN(acos(x)) for |x| <= 1 (NaN outside): acos(x) = atan2(sqrt((1 - x)(1 + x)), x) with the square root
+ * carried in double-double and the same Newton step as crm_atan2_sincos. */
+CRM_FN double crm_acos(double x) {
+    if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
+    if (x == 1.0) return 0.0;
+    if (x == -1.0) return CRM_PI_H;
+    crm_dd a = crm_two_sum(1.0, -x), b = crm_two_sum(1.0, x); /* exact */
+    crm_dd p = crm_mul(a, b);
+    double s0 = sqrt(p.hi);
+    crm_dd e = crm_sub(p, crm_two_prod(s0, s0));
+    crm_dd y = crm_fast_two_sum(s0, e.hi / (2.0 * s0)); /* sqrt(p) to ~2^-104 */
+    double t0 = crm_atan2_guess(y.hi, x);
+    crm_dd s0d, c0d;
+    crm_sincos_dd(t0, &s0d, &c0d);
+    crm_dd num = crm_sub(crm_mul(c0d, y), crm_mul_d(s0d, x));
+    crm_dd den = crm_add(crm_mul_d(c0d, x), crm_mul(s0d, y));
+    crm_dd u = crm_div(num, den);
+    crm_dd u3 = crm_mul(crm_mul(u, u), u);
+    crm_dd del = crm_sub(u, crm_mul(u3, crm_mk(CRM_THIRD_H, CRM_THIRD_L)));
+    crm_dd th = crm_add_d(del, t0);
+    return th.hi;
+}
+
 #endif /* RRTK_CRMATH_H */

@@ -40,6 +40,10 @@ int launch_nearest(const float *xy, long long n, const float *samples, int B, un
 int launch_near(const float *xy, long long n, float cx, float cy, float r2, int *out_idx, int cap, int *out_n,
                 cudaStream_t s);
 int launch_fma_peak(int fp64, int iters, int blocks, void *out, cudaStream_t s);
+int launch_dubins_steer(int n_req, double kappa, double step, const double *from3, const double *to3,
+                        const int32_t *obs_set, const double *obstacles, int obs_stride, const int32_t *n_obs,
+                        int32_t *mode, double *lengths, double *end, int32_t *n_pts, uint8_t *free_flag,
+                        double *pts, int max_pts, cudaStream_t s);
 int launch_informed(const rrtk_informed_params &p, const double *start_goal, const double *rot,
                     const double *obstacles, const int32_t *n_obs, const double *near_rr2, const double *free_s,
                     const double *ball, double *xy, double *cost, int32_t *parent, int32_t *n_nodes, double *path,
@@ -159,6 +163,19 @@ int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goa
                            n_nodes, path, path_len, c_best, status, ws_idx, ws_d, ctr.ptr, s);
 }
 
+int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_size, const double *from3,
+                          const double *to3, const int32_t *obs_set, const double *obstacles, int32_t obs_stride,
+                          const int32_t *n_obs, int32_t *mode, double *lengths, double *end, int32_t *n_pts,
+                          uint8_t *free_flag, double *pts, int32_t max_pts, void *stream) {
+    if (n_req < 0 || obs_stride < 0 || max_pts < 0) return set_error(RRTK_ERR_INVALID, "negative size");
+    if (!(curvature > 0.0) || !(step_size > 0.0)) return set_error(RRTK_ERR_INVALID, "curvature and step_size must be > 0");
+    if (n_req == 0) return RRTK_OK;
+    if (!from3 || !to3 || !mode || !lengths || !end || !n_pts || !free_flag) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (n_obs && !obstacles) return set_error(RRTK_ERR_INVALID, "n_obs given without obstacles");
+    return launch_dubins_steer(n_req, curvature, step_size, from3, to3, obs_set, obstacles, obs_stride, n_obs, mode,
+                               lengths, end, n_pts, free_flag, pts, max_pts, (cudaStream_t)stream);
+}
+
 int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
                            const double *start_goal, const double *xy, const int32_t *parent,
                            const int32_t *goal_index, double *path, int32_t *path_len, void *stream) {
@@ -181,9 +198,9 @@ int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goa
 }
 
 int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out, void *stream) {
-    if (kind < 0 || kind > 5 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
+    if (kind < 0 || kind > 6 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
     if (n == 0) return RRTK_OK;
-    if (!a || !out || (!b && (kind == 0 || kind == 1 || kind >= 4))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (!a || !out || (!b && (kind == 0 || kind == 1 || kind == 4 || kind == 5))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_crmath_probe(kind, n, a, b, out, (cudaStream_t)stream);
 }
 

@@ -180,3 +180,33 @@ def test_informed_cr_divergence_is_small(oracle_lib):
     first = int(np.argmin(same)) if not same.all() else a["n"]
     assert first > 100                      # identical for a long prefix
     assert abs(a["c_best"] - b["c_best"]) <= 1e-5 * a["c_best"]
+
+
+# ---- Dubins local planner (rrt_05:1021-1278 == dub00) ----
+def test_dubins_port_and_c_oracle_bit_identical_to_reference(oracle_lib):
+    import pyport
+    O = oracle_lib
+    g, _ = load_golden("dubins_pairs_150")
+    cases, pts, off = g["cases"], g["pts"], g["offsets"]
+    for ci, row in enumerate(cases):
+        ref_pts = pts[off[ci]:off[ci + 1]]
+        px, py, pyaw, bi, ln = pyport.plan_dubins_path(*row[0:6], row[6])
+        assert bi == int(row[7]) and ln == list(row[8:11]) and len(px) == int(row[11])
+        assert np.array_equal(np.column_stack([px, py, pyaw]), ref_pts)
+        r = O.dubins_plan(row[0:3], row[3:6], row[6], 0.1, O.MATH_LIBM)
+        assert r["mode"] == bi and np.array_equal(r["lengths"], row[8:11]) and np.array_equal(r["pts"], ref_pts)
+        c = O.dubins_plan(row[0:3], row[3:6], row[6], 0.1, O.MATH_CR)
+        assert c["mode"] == bi and c["n"] == len(ref_pts) and np.allclose(c["pts"], ref_pts, rtol=0, atol=1e-12)
+
+
+def test_acos_correctly_rounded(oracle_lib):
+    """crm_acos against mpmath-derived values stored with the leaf-math fixture is covered on the GPU; here
+    the exact identities and a libm cross-check (glibc acos is correctly rounded in > 99.9 % of inputs)."""
+    import math
+    L = oracle_lib.lib()
+    assert L.orc_cr_acos(1.0) == 0.0 and L.orc_cr_acos(-1.0) == math.pi and L.orc_cr_acos(0.0) == math.pi / 2
+    rng = np.random.default_rng(3)
+    xs = rng.uniform(-1, 1, 20000)
+    diff = sum(L.orc_cr_acos(float(x)) != math.acos(float(x)) for x in xs)
+    assert diff <= 40
+    assert all(abs(L.orc_cr_acos(float(x)) - math.acos(float(x))) <= 4.5e-16 for x in xs[:2000])
