@@ -187,6 +187,38 @@ RRTK_API int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_
                                    int32_t max_pts, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched RRT*-Dubins -- `planning()` of rrt_05:1416-1456 for Q independent queries: nearest on xy
+ * (:1605-1610), steer = full Dubins course (:1458-1479), check_collision over the course (:1625-1638),
+ * find_near_nodes (:1715-1739), choose_parent (:1648-1689), rewire + propagate with the EUCLIDEAN
+ * calc_new_cost (:1741-1779), search_best_goal_node (:1691-1712).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rrtk_dubins_params {
+    int32_t n_queries;
+    int32_t max_iter;
+    int32_t node_cap;               /* >= max_iter + 1 */
+    int32_t obs_stride;
+    int32_t near_cap;               /* multiple of 32 */
+    int32_t search_until_max_iter;  /* the `planning(search_until_max_iter=True)` argument (rrt_05:1416) */
+    double curvature;
+    double step_size;               /* 0.1 in the reference (rrt_05:1022) */
+    double goal_xy_th, goal_yaw_th;
+} rrtk_dubins_params;
+
+/*   start_goal6 [Q][6] = sx, sy, syaw, gx, gy, gyaw;  obstacles [Q][obs_stride][4] = x, y, size + rr, (size + rr)**2;
+ *   n_obs [Q];  near_r2 [node_cap + 2] as for rrtk_rrtstar_run_dev;  stream3 [Q][max_iter][3] = (x, y, yaw) samples
+ *   (get_random_node rrt_05:1528-1538)
+ * outputs: xy [Q][node_cap][2], yaw, cost, parent [Q][node_cap]; edge_from / edge_to [Q][node_cap][3]: the pose pair
+ *   whose Dubins course is the node's path_x / path_y / path_yaw (rrtk_dubins_steer_dev regenerates it);
+ *   n_nodes, iters_done, goal_index (-1 = none; index 0 counts as none like the reference), status [Q];
+ *   scratch workspace [Q][node_cap] int32 */
+RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6,
+                                         const double *obstacles, const int32_t *n_obs, const double *near_r2,
+                                         const double *stream3, double *xy, double *yaw, double *cost,
+                                         int32_t *parent, double *edge_from, double *edge_to, int32_t *n_nodes,
+                                         int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                                         int32_t *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.
  *   rrtk_nearest_f32_dev: get_nearest_node_index (rrt_04:1196-1202, rrt_07:1210-1214) for B samples in
  *     one pass over the n nodes; idx[b] = argmin_i |xy[i] - samples[b]|^2 with the LOWEST index on exact

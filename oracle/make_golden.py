@@ -217,6 +217,43 @@ def run_dubins(name, n, seed):
           f"{np.bincount(np.array(rows)[:, 7].astype(int), minlength=6).tolist()}")
 
 
+def run_rrt05(name, params, seed, search_until_max_iter=True):
+    """Drive rrt_05's RRT.planning (RRT*-Dubins) with an injected (x, y, yaw) sample stream."""
+    import math
+    ns = ref_loader.load("rrt_05")
+    R = ns["RRT"]
+    rng = np.random.default_rng(seed)
+    n = params["max_iter"]
+    lo, hi = params["rand_area"]
+    stream = np.column_stack([rng.uniform(lo, hi, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+    coin = rng.integers(0, 101, n) <= params["goal_sample_rate"]
+    stream[coin] = params["goal"]
+    rrt = R(**params)
+    it = iter(stream)
+    rrt.get_random_node = lambda: rrt.Node(*[float(v) for v in next(it)])
+    sys.setrecursionlimit(100000)          # steer deep-copies the whole ancestor chain (rrt_05:1468)
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        path = rrt.planning(animation=False, search_until_max_iter=search_until_max_iter)
+    wall = time.perf_counter() - t0
+    x, y, c, par = tree_arrays(rrt.node_list)
+    yaw = np.array([float(nd.yaw) for nd in rrt.node_list])
+    meta = dict(params)
+    meta.update(kind="rrt_05", seed=seed, reference_wall_s=wall, search_until_max_iter=search_until_max_iter,
+                goal_yaw_th=float(params.get("goal_yaw_th", np.deg2rad(1.0))))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), stream=stream,
+                        x=x, y=y, yaw=yaw, cost=c, parent=par,
+                        path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 2)))
+    print(f"{name}: {len(x)} nodes, {n} iterations, path {0 if path is None else len(path)} points, "
+          f"{wall:.2f} s ({n / wall:.1f} it/s)")
+
+
+C5D = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 10.0, 0.0],
+           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)],
+           rand_area=[-2, 15], expand_dis=3.0, goal_sample_rate=10, max_iter=500, robot_radius=0.0,
+           connect_circle_dist=50.0, curvature=1.0, goal_xy_th=0.5)          # rrt_05:1804-1859
+
+
 C7 = dict(start=[0.0, 0.0], goal=[6.0, 10.0],
           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
           rand_area=[-2, 15], expand_dis=0.5, goal_sample_rate=10, max_iter=200)   # rrt_07:1339-1378
@@ -248,6 +285,13 @@ def _rand_arm_obs(seed, n=5):
 
 
 CASES = {
+    "rrt05_builtin_500": lambda: run_rrt05("rrt05_builtin_500", C5D, 1),
+    "rrt05_builtin_1500": lambda: run_rrt05("rrt05_builtin_1500", dict(C5D, max_iter=1500), 2),
+    "rrt05_loose_goal_800": lambda: run_rrt05("rrt05_loose_goal_800", dict(
+        C5D, max_iter=800, goal_yaw_th=float(np.deg2rad(20.0)), goal_xy_th=1.0, robot_radius=0.3, curvature=1.5,
+        obstacle_list=[(5, 5, 1), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]), 3),
+    "rrt05_early_exit_600": lambda: run_rrt05("rrt05_early_exit_600", dict(
+        C5D, max_iter=600, goal_yaw_th=float(np.deg2rad(30.0)), goal_xy_th=1.5), 4, False),
     "dubins_pairs_150": lambda: run_dubins("dubins_pairs_150", 150, 21),
     "rrt07_builtin_200": lambda: run_rrt07("rrt07_builtin_200", C7, 1),
     "rrt07_builtin_1000": lambda: run_rrt07("rrt07_builtin_1000", dict(C7, max_iter=1000), 2),

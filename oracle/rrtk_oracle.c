@@ -829,3 +829,144 @@ ORC_EXPORT int orc_dubins_plan(double s_x, double s_y, double s_yaw, double g_x,
 #undef EMIT
     return np;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* RRT*-Dubins planning loop (rrt_05:1416-1779)                                          */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    double sx, sy, syaw, gx, gy, gyaw;
+    double expand_dis, robot_radius, connect_circle_dist, kappa, goal_yaw_th, goal_xy_th;
+    int32_t max_iter, n_obs, search_until_max_iter, math_mode;
+} orc_dubins_params_t;
+
+#define DUB_MAXPTS 8192
+typedef struct { double end[3]; int npts; int free_; } dub_edge_t;
+
+/* steer (rrt_05:1458-1479) + check_collision (:1625-1638): npts <= 1 means steer returned None */
+static dub_edge_t dubins_edge(const orc_dubins_params_t *p, const double *obs3, const double *f, const double *t,
+                              double *buf) {
+    dub_edge_t e;
+    int32_t mode;
+    double lengths[3];
+    int n = orc_dubins_plan(f[0], f[1], f[2], t[0], t[1], t[2], p->kappa, 0.1, p->math_mode, &mode, lengths, buf,
+                            DUB_MAXPTS);
+    e.npts = n;
+    e.free_ = 0;
+    e.end[0] = e.end[1] = e.end[2] = 0.0;
+    if (n <= 1) return e;
+    if (n > DUB_MAXPTS) n = DUB_MAXPTS;
+    e.end[0] = buf[3 * (n - 1)]; e.end[1] = buf[3 * (n - 1) + 1]; e.end[2] = buf[3 * (n - 1) + 2];
+    int ok = 1;
+    for (int o = 0; o < p->n_obs && ok; o++) {
+        double ox = obs3[3 * o], oy = obs3[3 * o + 1], size = obs3[3 * o + 2], mn = INFINITY;
+        for (int k = 0; k < n; k++) {
+            double dx = ox - buf[3 * k], dy = oy - buf[3 * k + 1], dd = dx * dx + dy * dy;
+            if (dd < mn) mn = dd;
+        }
+        if (mn <= sq_libm(size + p->robot_radius)) ok = 0;
+    }
+    e.free_ = ok;
+    return e;
+}
+
+static void dub_propagate(int n, double *x, double *y, double *cost, const int32_t *parent, int p) {
+    for (int c = 0; c < n; c++)
+        if (parent[c] == p) {
+            cost[c] = cost[p] + orc_hypot(x[c] - x[p], y[c] - y[p]);
+            dub_propagate(n, x, y, cost, parent, c);
+        }
+}
+
+static int dub_best_goal(const orc_dubins_params_t *p, int n, const double *x, const double *y, const double *yaw,
+                         const double *cost) {
+    int best = -1;
+    double bc = INFINITY;
+    for (int i = 0; i < n; i++)
+        if (orc_hypot(x[i] - p->gx, y[i] - p->gy) <= p->goal_xy_th && fabs(yaw[i] - p->gyaw) <= p->goal_yaw_th)
+            if (best < 0 || cost[i] < bc) { best = i; bc = cost[i]; }
+    return best;
+}
+
+/* edge_from / edge_to [cap][3]: the pose pair whose Dubins course is the node's path_x/path_y/path_yaw
+ * (plan_dubins_path(edge_from, edge_to) regenerates it).  *goal_index: -1 none (index 0 also counts as none) */
+ORC_EXPORT int orc_rrtstar_dubins_run(const orc_dubins_params_t *p, const double *obs3, const double *stream3,
+                                      double *x, double *y, double *yaw, double *cost, int32_t *parent,
+                                      double *edge_from, double *edge_to, int32_t *n_nodes, int32_t *iters_done,
+                                      int32_t *goal_index) {
+    const int mode = p->math_mode;
+    int cap = p->max_iter + 1, n = 1, it, gi = -1, done = 0;
+    double *buf = (double *)malloc(sizeof(double) * 3 * DUB_MAXPTS);
+    double *dl = (double *)malloc(sizeof(double) * cap);
+    int *near = (int *)malloc(sizeof(int) * cap);
+    x[0] = p->sx; y[0] = p->sy; yaw[0] = p->syaw; cost[0] = 0.0; parent[0] = -1;
+    for (it = 0; it < p->max_iter; it++) {
+        const double *rnd = stream3 + 3 * it;
+        int ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(mode, x[i] - rnd[0]) + sq(mode, y[i] - rnd[1]);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double from[3] = {x[ni], y[ni], yaw[ni]};
+        dub_edge_t e0 = dubins_edge(p, obs3, from, rnd, buf);
+        int truthy = e0.npts > 1;
+        if (e0.npts > 1 && e0.free_) {
+            double nw[3] = {e0.end[0], e0.end[1], e0.end[2]};
+            double nnode = (double)(n + 1);
+            double r = p->connect_circle_dist * sqrt(log(nnode) / nnode);
+            if (p->expand_dis < r) r = p->expand_dis;
+            double r2 = sq_libm(r);
+            int n_near = 0;
+            for (int i = 0; i < n; i++) dl[i] = sq(mode, x[i] - nw[0]) + sq(mode, y[i] - nw[1]);
+            for (int i = 0; i < n; i++)
+                if (dl[i] <= r2) {
+                    int f = 0;
+                    while (dl[f] != dl[i]) f++;
+                    near[n_near++] = f;
+                }
+            truthy = 0;
+            int best = -1;
+            double mc = INFINITY;
+            for (int k = 0; k < n_near; k++) {
+                int i = near[k];
+                double fi[3] = {x[i], y[i], yaw[i]};
+                dub_edge_t e = dubins_edge(p, obs3, fi, nw, buf);
+                double c = (e.npts > 1 && e.free_) ? cost[i] + orc_hypot(nw[0] - x[i], nw[1] - y[i]) : INFINITY;
+                if (c < mc) { mc = c; best = i; }
+            }
+            if (best >= 0) {
+                double fb[3] = {x[best], y[best], yaw[best]};
+                dub_edge_t e = dubins_edge(p, obs3, fb, nw, buf);
+                int newi = n;
+                x[newi] = e.end[0]; y[newi] = e.end[1]; yaw[newi] = e.end[2]; cost[newi] = mc; parent[newi] = best;
+                memcpy(edge_from + 3 * newi, fb, sizeof fb);
+                memcpy(edge_to + 3 * newi, nw, sizeof nw);
+                n++;
+                truthy = 1;
+                double cp[3] = {e.end[0], e.end[1], e.end[2]};
+                for (int k = 0; k < n_near; k++) { /* rewire (:1741-1775), after the append */
+                    int i = near[k];
+                    double ti[3] = {x[i], y[i], yaw[i]};
+                    dub_edge_t ed = dubins_edge(p, obs3, cp, ti, buf);
+                    if (ed.npts <= 1) continue;
+                    double ecost = mc + orc_hypot(x[i] - cp[0], y[i] - cp[1]);
+                    if (ed.free_ && cost[i] > ecost) {
+                        x[i] = ed.end[0]; y[i] = ed.end[1]; yaw[i] = ed.end[2]; cost[i] = ecost; parent[i] = newi;
+                        memcpy(edge_from + 3 * i, cp, sizeof cp);
+                        memcpy(edge_to + 3 * i, ti, sizeof ti);
+                        dub_propagate(n, x, y, cost, parent, i);
+                    }
+                }
+            }
+        }
+        if (!p->search_until_max_iter && truthy) {
+            gi = dub_best_goal(p, n, x, y, yaw, cost);
+            if (gi > 0) { it++; done = 1; break; }
+        }
+    }
+    if (!done) gi = dub_best_goal(p, n, x, y, yaw, cost);
+    if (gi <= 0) gi = -1; /* `if last_index:` -- index 0 is falsy (rrt_05:1445, :1451) */
+    *n_nodes = n; *iters_done = it; *goal_index = gi;
+    free(buf); free(dl); free(near);
+    return 0;
+}

@@ -15,116 +15,9 @@
 #include "crmath.h"
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
+#include "rrtk_dubins.cuh"
 
 namespace rrtk {
-
-constexpr double D_TWO_PI = 6.283185307179586;  // 2 * math.pi
-constexpr double D_PI = 3.141592653589793;
-
-// Python float `%` / numpy mod
-__device__ __forceinline__ double py_mod(double a, double b) {
-    double r = fmod(a, b);
-    if (r != 0.0) { if ((b < 0) != (r < 0)) r += b; }
-    else r = copysign(0.0, b);
-    return r;
-}
-__device__ __forceinline__ double mod2pi(double t) { return py_mod(t, D_TWO_PI); }
-__device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
-
-__device__ __forceinline__ void sincos_cr(double x, double *s, double *c) {
-    crm_dd sd, cd;
-    crm_sincos_dd(x, &sd, &cd);
-    *s = x == 0.0 ? x : sd.hi;
-    *c = cd.hi;
-}
-
-// rot_mat_2d(angle) = [[c, -s], [s, c]] via SciPy's quaternion: c = w*w - z*z, s = 2*(z*w)
-__device__ __forceinline__ void rot2d(double angle, double *c, double *s) {
-    double z, w;
-    sincos_cr(angle / 2, &z, &w);
-    *c = w * w - z * z;
-    *s = 2 * (z * w);
-}
-
-// word k in _PATH_TYPE_MAP order; false = infeasible
-__device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, double *w) {
-    double sa, ca, sb, cb;
-    sincos_cr(alpha, &sa, &ca);
-    sincos_cr(beta, &sb, &cb);
-    const double cab = crm_cos(alpha - beta);
-    const double d2 = d * d;
-    double p2, tmp, d1;
-    switch (k) {
-        case 0:
-            p2 = 2 + d2 - (2 * cab) + (2 * d * (sa - sb));
-            if (p2 < 0) return false;
-            tmp = crm_atan2((cb - ca), d + sa - sb);
-            w[0] = mod2pi(-alpha + tmp); w[1] = sqrt(p2); w[2] = mod2pi(beta - tmp);
-            return true;
-        case 1:
-            p2 = 2 + d2 - (2 * cab) + (2 * d * (sb - sa));
-            if (p2 < 0) return false;
-            tmp = crm_atan2((ca - cb), d - sa + sb);
-            w[0] = mod2pi(alpha - tmp); w[1] = sqrt(p2); w[2] = mod2pi(-beta + tmp);
-            return true;
-        case 2:
-            p2 = -2 + d2 + (2 * cab) + (2 * d * (sa + sb));
-            if (p2 < 0) return false;
-            d1 = sqrt(p2);
-            tmp = crm_atan2((-ca - cb), (d + sa + sb)) - crm_atan2(-2.0, d1);
-            w[0] = mod2pi(-alpha + tmp); w[1] = d1; w[2] = mod2pi(-mod2pi(beta) + tmp);
-            return true;
-        case 3:
-            p2 = d2 - 2 + (2 * cab) - (2 * d * (sa + sb));
-            if (p2 < 0) return false;
-            d1 = sqrt(p2);
-            tmp = crm_atan2((ca + cb), (d - sa - sb)) - crm_atan2(2.0, d1);
-            w[0] = mod2pi(alpha - tmp); w[1] = d1; w[2] = mod2pi(beta - tmp);
-            return true;
-        case 4:
-            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
-            if (fabs(tmp) > 1.0) return false;
-            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
-            w[0] = mod2pi(alpha - crm_atan2(ca - cb, d - sa + sb) + w[1] / 2.0);
-            w[2] = mod2pi(alpha - beta - w[0] + w[1]);
-            return true;
-        default:
-            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (-sa + sb)) / 8.0;
-            if (fabs(tmp) > 1.0) return false;
-            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
-            w[0] = mod2pi(-alpha - crm_atan2(ca - cb, d + sa - sb) + w[1] / 2.0);
-            w[2] = mod2pi(mod2pi(beta) - alpha - w[0] + mod2pi(w[1]));
-            return true;
-    }
-}
-
-// segment type of word `mode` at position k: 0 = L, 1 = S, 2 = R
-__device__ __forceinline__ int seg_type(int mode, int k) {
-    // LSL RSR LSR RSL RLR LRL
-    const int t[6][3] = {{0, 1, 0}, {2, 1, 2}, {0, 1, 2}, {2, 1, 0}, {2, 0, 2}, {0, 2, 0}};
-    return t[mode][k];
-}
-
-// _interpolate (rrt_05:1232-1255); so/co = sin/cos(origin_yaw), sm/cm = sin/cos(-origin_yaw)
-__device__ __forceinline__ void interp(double length, int type, double kappa, double ox, double oy, double oyaw,
-                                       double so, double co, double sm, double cm, double *x, double *y,
-                                       double *yaw) {
-    if (type == 1) {
-        *x = ox + length / kappa * co;
-        *y = oy + length / kappa * so;
-        *yaw = oyaw;
-    } else {
-        double sl, cl;
-        sincos_cr(length, &sl, &cl);
-        const double ldx = sl / kappa;
-        const double ldy = type == 0 ? (1.0 - cl) / kappa : (1.0 - cl) / -kappa;
-        const double gdx = cm * ldx + sm * ldy;
-        const double gdy = -sm * ldx + cm * ldy;
-        *x = ox + gdx;
-        *y = oy + gdy;
-        *yaw = type == 0 ? oyaw + length : oyaw - length;
-    }
-}
 
 extern "C" __global__ void __launch_bounds__(128)
 dubins_steer_kernel(int n_req, double kappa, double step, const double *__restrict__ from3,

@@ -1,0 +1,198 @@
+// rrtk_dubins.cuh -- device functions of the Dubins local planner (rrt_05:935-1278 == dub00), shared by the
+// batched steering kernel and the RRT*-Dubins planner kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "crmath.h"
+#include "rrtk_device.cuh"
+
+namespace rrtk {
+
+constexpr double D_TWO_PI = 6.283185307179586;  // 2 * math.pi
+constexpr double D_PI = 3.141592653589793;
+
+// Python float `%` / numpy mod
+static __device__ __forceinline__ double py_mod(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0) { if ((b < 0) != (r < 0)) r += b; }
+    else r = copysign(0.0, b);
+    return r;
+}
+static __device__ __forceinline__ double mod2pi(double t) { return py_mod(t, D_TWO_PI); }
+static __device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
+
+static __device__ __forceinline__ void sincos_cr(double x, double *s, double *c) {
+    crm_dd sd, cd;
+    crm_sincos_dd(x, &sd, &cd);
+    *s = x == 0.0 ? x : sd.hi;
+    *c = cd.hi;
+}
+
+// rot_mat_2d(angle) = [[c, -s], [s, c]] via SciPy's quaternion: c = w*w - z*z, s = 2*(z*w)
+static __device__ __forceinline__ void rot2d(double angle, double *c, double *s) {
+    double z, w;
+    sincos_cr(angle / 2, &z, &w);
+    *c = w * w - z * z;
+    *s = 2 * (z * w);
+}
+
+// word k in _PATH_TYPE_MAP order; false = infeasible
+static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, double *w) {
+    double sa, ca, sb, cb;
+    sincos_cr(alpha, &sa, &ca);
+    sincos_cr(beta, &sb, &cb);
+    const double cab = crm_cos(alpha - beta);
+    const double d2 = d * d;
+    double p2, tmp, d1;
+    switch (k) {
+        case 0:
+            p2 = 2 + d2 - (2 * cab) + (2 * d * (sa - sb));
+            if (p2 < 0) return false;
+            tmp = crm_atan2((cb - ca), d + sa - sb);
+            w[0] = mod2pi(-alpha + tmp); w[1] = sqrt(p2); w[2] = mod2pi(beta - tmp);
+            return true;
+        case 1:
+            p2 = 2 + d2 - (2 * cab) + (2 * d * (sb - sa));
+            if (p2 < 0) return false;
+            tmp = crm_atan2((ca - cb), d - sa + sb);
+            w[0] = mod2pi(alpha - tmp); w[1] = sqrt(p2); w[2] = mod2pi(-beta + tmp);
+            return true;
+        case 2:
+            p2 = -2 + d2 + (2 * cab) + (2 * d * (sa + sb));
+            if (p2 < 0) return false;
+            d1 = sqrt(p2);
+            tmp = crm_atan2((-ca - cb), (d + sa + sb)) - crm_atan2(-2.0, d1);
+            w[0] = mod2pi(-alpha + tmp); w[1] = d1; w[2] = mod2pi(-mod2pi(beta) + tmp);
+            return true;
+        case 3:
+            p2 = d2 - 2 + (2 * cab) - (2 * d * (sa + sb));
+            if (p2 < 0) return false;
+            d1 = sqrt(p2);
+            tmp = crm_atan2((ca + cb), (d - sa - sb)) - crm_atan2(2.0, d1);
+            w[0] = mod2pi(alpha - tmp); w[1] = d1; w[2] = mod2pi(beta - tmp);
+            return true;
+        case 4:
+            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
+            if (fabs(tmp) > 1.0) return false;
+            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
+            w[0] = mod2pi(alpha - crm_atan2(ca - cb, d - sa + sb) + w[1] / 2.0);
+            w[2] = mod2pi(alpha - beta - w[0] + w[1]);
+            return true;
+        default:
+            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (-sa + sb)) / 8.0;
+            if (fabs(tmp) > 1.0) return false;
+            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
+            w[0] = mod2pi(-alpha - crm_atan2(ca - cb, d + sa - sb) + w[1] / 2.0);
+            w[2] = mod2pi(mod2pi(beta) - alpha - w[0] + mod2pi(w[1]));
+            return true;
+    }
+}
+
+// segment type of word `mode` at position k: 0 = L, 1 = S, 2 = R
+static __device__ __forceinline__ int seg_type(int mode, int k) {
+    // LSL RSR LSR RSL RLR LRL
+    const int t[6][3] = {{0, 1, 0}, {2, 1, 2}, {0, 1, 2}, {2, 1, 0}, {2, 0, 2}, {0, 2, 0}};
+    return t[mode][k];
+}
+
+// _interpolate (rrt_05:1232-1255); so/co = sin/cos(origin_yaw), sm/cm = sin/cos(-origin_yaw)
+static __device__ __forceinline__ void interp(double length, int type, double kappa, double ox, double oy, double oyaw,
+                                       double so, double co, double sm, double cm, double *x, double *y,
+                                       double *yaw) {
+    if (type == 1) {
+        *x = ox + length / kappa * co;
+        *y = oy + length / kappa * so;
+        *yaw = oyaw;
+    } else {
+        double sl, cl;
+        sincos_cr(length, &sl, &cl);
+        const double ldx = sl / kappa;
+        const double ldy = type == 0 ? (1.0 - cl) / kappa : (1.0 - cl) / -kappa;
+        const double gdx = cm * ldx + sm * ldy;
+        const double gdy = -sm * ldx + cm * ldy;
+        *x = ox + gdx;
+        *y = oy + gdy;
+        *yaw = type == 0 ? oyaw + length : oyaw - length;
+    }
+}
+
+
+struct DubEdge {
+    double ex, ey, eyaw;  // last course point (the node pose steer returns, rrt_05:1469-1471)
+    int npts;             // len(px): steer returns None when <= 1
+    bool free_;           // check_collision over the course points (rrt_05:1625-1638)
+};
+
+// One Dubins edge evaluated by ONE lane: plan_dubins_path + sampled collision test.
+// obs rows: x, y, size + robot_radius, (size + robot_radius)**2
+static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, double s_yaw, double g_x, double g_y,
+                                                        double g_yaw, double kappa, double step,
+                                                        const double4 *obs, int n_obs) {
+    DubEdge e;
+    e.ex = e.ey = e.eyaw = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    double c, s;
+    rot2d(s_yaw, &c, &s);
+    const double vx = g_x - s_x, vy = g_y - s_y;
+    const double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s);
+    const double lgyaw = g_yaw - s_yaw;
+    const double d = crm_hypot(lgx, lgy) * kappa;
+    const double theta = mod2pi(crm_atan2(lgy, lgx));
+    const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
+    double len[3] = {0.0, 0.0, 0.0}, best = CUDART_INF;
+    int bi = -1;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        double w[3];
+        if (!dubins_word(k, alpha, beta, d, w)) continue;
+        double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+        if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
+    }
+    if (bi < 0) return e;
+    double c2, s2;
+    rot2d(-s_yaw, &c2, &s2);
+    bool hit = false;
+    double lx = 0.0, ly = 0.0, lyaw = 0.0;
+    int np = 0;
+    auto emit = [&](double px, double py) {
+        const double wx = fma(py, s2, px * c2) + s_x;
+        const double wy = fma(py, c2, px * -s2) + s_y;
+        for (int o = 0; o < n_obs && !hit; o++) {
+            const double4 ob = obs[o];
+            const double dx = ob.x - wx, dy = ob.y - wy;
+            if (dx * dx + dy * dy <= ob.w) hit = true;
+        }
+        np++;
+    };
+    emit(lx, ly);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const double length = len[k];
+        if (length == 0.0) continue;
+        const int type = seg_type(bi, k);
+        const double ox = lx, oy = ly, oyaw = lyaw;
+        double so, co, sm, cm;
+        sincos_cr(oyaw, &so, &co);
+        sincos_cr(-oyaw, &sm, &cm);
+        double cur = step;
+#pragma unroll 1
+        while (fabs(cur + step) <= fabs(length)) {
+            double x, y, yaw;
+            interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
+            emit(x, y);
+            cur += step;
+        }
+        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+        emit(lx, ly);
+    }
+    e.npts = np;
+    e.free_ = !hit;
+    e.ex = fma(ly, s2, lx * c2) + s_x;
+    e.ey = fma(ly, c2, lx * -s2) + s_y;
+    e.eyaw = angle_mod_pi(lyaw + s_yaw);
+    return e;
+}
+
+}  // namespace rrtk

@@ -1,0 +1,266 @@
+// rrtk_rrtstar_dubins.cu -- batched RRT*-Dubins: the `planning()` loop of rrt_05:1416-1456 for Q independent
+// queries, one warp per query, persistent grid.  Reference quirks kept:
+//   * steer = full Dubins course to the sample, no expand_dis clamp (:1458-1479); near / nearest use xy only;
+//   * no play-area checks (:1430-1432); a node is appended only when choose_parent succeeds, and BEFORE rewire;
+//   * choose_parent / rewire / propagate costs are EUCLIDEAN (the second calc_new_cost, :1777-1779, wins);
+//   * every successful rewire moves the node to the end pose of the new Dubins edge (:1771);
+//   * goal test by xy and yaw thresholds, minimum cost, index 0 counts as "not found" (:1445, :1691-1712).
+// Each edge (6 words + sampled course + collision) is evaluated by one lane (rrtk_dubins.cuh); the first steer
+// of an iteration is uniform, choose_parent and rewire run one lane per near candidate.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrtk.h"
+#include "crmath.h"
+#include "rrtk_device.cuh"
+#include "rrtk_planner.cuh"
+#include "rrtk_dubins.cuh"
+
+namespace rrtk {
+
+constexpr int DUB_WARPS_PER_CTA = 4;
+
+__host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap) {
+    size_t words = (size_t)(node_cap + 31) / 32;
+    // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | 2 bitsets
+    size_t b = (size_t)near_cap * (4 + 4 + 8 + 24) + words * 4 * 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+extern "C" __global__ void __launch_bounds__(DUB_WARPS_PER_CTA * 32, 3)
+rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goal6,
+                      const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
+                      const double *__restrict__ near_r2, const double *__restrict__ stream3, double2 *xy_all,
+                      double *yaw_all, double *cost_all, int32_t *parent_all, double *edge_from_all,
+                      double *edge_to_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+                      int32_t *status_out, int32_t *workspace, unsigned int *counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int near_cap = p.near_cap;
+    const int words = (p.node_cap + 31) / 32;
+    unsigned char *base = smem_raw + (size_t)(threadIdx.x >> 5) * dub_warp_smem_bytes(near_cap, p.node_cap);
+    double *nd = reinterpret_cast<double *>(base);
+    double *s_end = nd + near_cap;  // [near_cap][3]
+    int *near_idx = reinterpret_cast<int *>(s_end + 3 * near_cap);
+    int *flags = near_idx + near_cap;
+    uint32_t *bits_cur = reinterpret_cast<uint32_t *>(flags + near_cap);
+    uint32_t *bits_nxt = bits_cur + words;
+    const double INF = CUDART_INF;
+    const double kappa = p.curvature, step = p.step_size;
+
+    for (;;) {
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= (unsigned)p.n_queries) break;
+        const double *sg = start_goal6 + 6 * (size_t)q;
+        const double sx = sg[0], sy = sg[1], syaw = sg[2], gx = sg[3], gy = sg[4], gyaw = sg[5];
+        const double4 *obs = obstacles + (size_t)q * p.obs_stride;
+        const int n_obs = n_obs_arr[q];
+        double2 *xy = xy_all + (size_t)q * p.node_cap;
+        double *yaw = yaw_all + (size_t)q * p.node_cap;
+        double *cost = cost_all + (size_t)q * p.node_cap;
+        int32_t *parent = parent_all + (size_t)q * p.node_cap;
+        double *efrom = edge_from_all + (size_t)q * p.node_cap * 3;
+        double *eto = edge_to_all + (size_t)q * p.node_cap * 3;
+        int32_t *nchild = workspace + (size_t)q * p.node_cap;
+        const double *stream = stream3 + (size_t)q * p.max_iter * 3;
+        if (lane == 0) {
+            xy[0] = make_double2(sx, sy); yaw[0] = syaw; cost[0] = 0.0; parent[0] = -1; nchild[0] = 0;
+            for (int k = 0; k < 3; k++) { efrom[k] = 0.0; eto[k] = 0.0; }
+        }
+        __syncwarp();
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
+        bool done = false;
+
+        // search_best_goal_node (rrt_05:1691-1712): uniform result, -1 = none
+        auto best_goal = [&]() {
+            double bc = INF;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                double2 a = xy[i];
+                if (crm_hypot(a.x - gx, a.y - gy) <= p.goal_xy_th && fabs(yaw[i] - gyaw) <= p.goal_yaw_th) {
+                    double c = cost[i];
+                    if (c < bc) { bc = c; bi = i; }
+                }
+            }
+            warp_argmin(bc, bi);
+            return bi == 0x7fffffff ? -1 : bi;
+        };
+
+        for (it = 0; it < p.max_iter; it++) {
+            const double rx = stream[3 * it], ry = stream[3 * it + 1], ryaw = stream[3 * it + 2];
+            // nearest on xy (rrt_05:1605-1610)
+            double bd = INF;
+            int bi = 0x7fffffff;
+#pragma unroll 1
+            for (int i = lane; i < n; i += 32) {
+                double2 a = xy[i];
+                double ddx = a.x - rx, ddy = a.y - ry;
+                double d = ddx * ddx + ddy * ddy;
+                if (d < bd) { bd = d; bi = i; }
+            }
+            warp_argmin(bd, bi);
+            const int ni = bi;
+            const double2 from = xy[ni];
+            const double fyaw = yaw[ni];
+            DubEdge e0 = dubins_edge_lane(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs);  // uniform
+            bool truthy = e0.npts > 1;
+            if (truthy && e0.free_) {
+                const double nx = e0.ex, ny = e0.ey, nyaw = e0.eyaw;
+                truthy = false;
+                if (n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
+                // find_near_nodes (rrt_05:1715-1739)
+                const double r2 = near_r2[n + 1];
+                int count = 0;
+#pragma unroll 1
+                for (int b0 = 0; b0 < n; b0 += 32) {
+                    int i = b0 + lane;
+                    bool hit = false;
+                    double d = 0.0;
+                    if (i < n) {
+                        double2 a = xy[i];
+                        double ddx = a.x - nx, ddy = a.y - ny;
+                        d = ddx * ddx + ddy * ddy;
+                        hit = d <= r2;
+                    }
+                    unsigned mask = __ballot_sync(FULL, hit);
+                    int pos = count + __popc(mask & ((1u << lane) - 1u));
+                    if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+                    count += __popc(mask);
+                }
+                __syncwarp();
+                if (count > near_cap) { status |= RRTK_Q_NEAR_OVERFLOW; break; }
+                for (int k = lane; k < count; k += 32) {  // `.index()` first-occurrence mapping
+                    double dk = nd[k];
+                    int f = k;
+                    for (int j = 0; j < k; j++)
+                        if (nd[j] == dk) { f = j; break; }
+                    flags[k] = near_idx[f];
+                }
+                __syncwarp();
+                for (int k = lane; k < count; k += 32) near_idx[k] = flags[k];
+                __syncwarp();
+                // choose_parent (rrt_05:1648-1689): one lane per candidate
+                double mc = INF, bex = 0.0, bey = 0.0, beyaw = 0.0;
+                int bk = 0x7fffffff;
+#pragma unroll 1
+                for (int k = lane; k < count; k += 32) {
+                    const int i = near_idx[k];
+                    const double2 a = xy[i];
+                    DubEdge e = dubins_edge_lane(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
+                    if (e.npts > 1 && e.free_) {
+                        const double c = cost[i] + crm_hypot(nx - a.x, ny - a.y);
+                        if (c < mc) { mc = c; bk = k; bex = e.ex; bey = e.ey; beyaw = e.eyaw; }
+                    }
+                }
+                warp_argmin(mc, bk);
+                if (bk != 0x7fffffff) {
+                    const int src = bk & 31;
+                    const double cx = __shfl_sync(FULL, bex, src), cy = __shfl_sync(FULL, bey, src);
+                    const double cyaw = __shfl_sync(FULL, beyaw, src);
+                    const int best = near_idx[bk];
+                    const int newi = n;
+                    __syncwarp();
+                    if (lane == 0) {
+                        const double2 b = xy[best];
+                        efrom[3 * newi] = b.x; efrom[3 * newi + 1] = b.y; efrom[3 * newi + 2] = yaw[best];
+                        eto[3 * newi] = nx; eto[3 * newi + 1] = ny; eto[3 * newi + 2] = nyaw;
+                        xy[newi] = make_double2(cx, cy); yaw[newi] = cyaw; cost[newi] = mc; parent[newi] = best;
+                        nchild[newi] = 0;
+                        nchild[best]++;
+                    }
+                    n++;
+                    truthy = true;
+                    __syncwarp();
+                    // rewire (rrt_05:1741-1775), phase A: every entry's edge in parallel
+#pragma unroll 1
+                    for (int k = lane; k < count; k += 32) {
+                        const int i = near_idx[k];
+                        const double2 a = xy[i];
+                        DubEdge e = dubins_edge_lane(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
+                        flags[k] = (e.npts > 1 ? 1 : 0) | (e.free_ ? 2 : 0);
+                        nd[k] = mc + crm_hypot(a.x - cx, a.y - cy);
+                        s_end[3 * k] = e.ex; s_end[3 * k + 1] = e.ey; s_end[3 * k + 2] = e.eyaw;
+                    }
+                    __syncwarp();
+                    // phase B: apply in list order; costs are re-read (propagation can move them either way)
+                    for (int k = 0; k < count; k++) {
+                        const int i = near_idx[k];
+                        int fl = flags[k];
+                        double ecost = nd[k], ex = s_end[3 * k], ey = s_end[3 * k + 1], eyw = s_end[3 * k + 2];
+                        const double2 a = xy[i];
+                        const double ayaw = yaw[i];
+                        if (fl & 4) {  // node i was re-parented (moved) earlier in this call: redo its edge
+                            DubEdge e = dubins_edge_lane(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
+                            fl = (e.npts > 1 ? 1 : 0) | (e.free_ ? 2 : 0);
+                            ecost = mc + crm_hypot(a.x - cx, a.y - cy);
+                            ex = e.ex; ey = e.ey; eyw = e.eyaw;
+                        }
+                        if ((fl & 3) != 3) continue;
+                        if (cost[i] > ecost) {
+                            __syncwarp();
+                            if (lane == 0) {
+                                nchild[parent[i]]--;
+                                nchild[newi]++;
+                                efrom[3 * i] = cx; efrom[3 * i + 1] = cy; efrom[3 * i + 2] = cyaw;
+                                eto[3 * i] = a.x; eto[3 * i + 1] = a.y; eto[3 * i + 2] = ayaw;
+                                xy[i] = make_double2(ex, ey); yaw[i] = eyw; cost[i] = ecost; parent[i] = newi;
+                            }
+                            __syncwarp();
+                            for (int k2 = k + 1 + lane; k2 < count; k2 += 32)
+                                if (near_idx[k2] == i) flags[k2] |= 4;
+                            __syncwarp();
+                            propagate(i, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
+                        }
+                    }
+                }
+            }
+            if (!p.search_until_max_iter && truthy) {
+                gi = best_goal();
+                if (gi > 0) { it++; done = true; break; }
+            }
+        }
+        if (!done) gi = best_goal();
+        if (gi <= 0) gi = -1;  // `if last_index:` -- index 0 is falsy (rrt_05:1445, :1451)
+        if (lane == 0) {
+            n_nodes[q] = n;
+            iters_done[q] = it;
+            goal_index[q] = gi;
+            status_out[q] = status;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_rrtstar_dubins(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
+                          const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
+                          double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                          int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                          int32_t *workspace, unsigned int *counter, cudaStream_t s) {
+    size_t smem = dub_warp_smem_bytes(p.near_cap, p.node_cap) * DUB_WARPS_PER_CTA;
+    if (smem > 227 * 1024) return set_error(RRTK_ERR_INVALID, "near_cap/node_cap need more than 227 KB of shared memory");
+    cudaError_t e = cudaFuncSetAttribute(rrtstar_dubins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrtstar_dubins_kernel, DUB_WARPS_PER_CTA * 32, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)p.n_queries + DUB_WARPS_PER_CTA - 1) / DUB_WARPS_PER_CTA;
+    long long grid = (long long)sms * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
+    rrtstar_dubins_kernel<<<(unsigned)grid, DUB_WARPS_PER_CTA * 32, smem, s>>>(
+        p, start_goal6, reinterpret_cast<const double4 *>(obstacles), n_obs, near_r2, stream3,
+        reinterpret_cast<double2 *>(xy), yaw, cost, parent, edge_from, edge_to, n_nodes, iters_done, goal_index,
+        status, workspace, counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rrtstar_dubins_kernel launch");
+    return RRTK_OK;
+}
+
+}  // namespace rrtk

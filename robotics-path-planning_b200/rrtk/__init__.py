@@ -5,7 +5,8 @@ from .batch import RRTStarBatch, shard_range  # noqa: F401
 from .informed import InformedRRTStar  # noqa: F401
 from . import dubins  # noqa: F401
 from .dubins import plan_dubins_path  # noqa: F401
+from .dubins_planner import RRTStarDubins  # noqa: F401
 from .arm import NLinkArm, get_occupancy_grid, get_occupancy_grids  # noqa: F401
 
-__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "RrtkError",
+__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "RRTStarDubins", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "RrtkError",
            "lib", "LIB_PATH"]

@@ -34,6 +34,14 @@ class InformedParams(C.Structure):
                 ("expand_dis", C.c_double)]
 
 
+class DubinsParams(C.Structure):
+    """struct rrtk_dubins_params (include/rrtk.h)."""
+    _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
+                ("obs_stride", C.c_int32), ("near_cap", C.c_int32), ("search_until_max_iter", C.c_int32),
+                ("curvature", C.c_double), ("step_size", C.c_double), ("goal_xy_th", C.c_double),
+                ("goal_yaw_th", C.c_double)]
+
+
 _lib = None
 
 _VP = C.c_void_p
@@ -47,6 +55,7 @@ _SIGS = {
     "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 16),
     "rrtk_rrtstar_run_host": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 14),
     "rrtk_informed_run_dev": (C.c_int, [C.POINTER(InformedParams)] + [_VP] * 18),
+    "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),

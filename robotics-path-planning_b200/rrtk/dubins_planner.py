@@ -1,0 +1,167 @@
+"""RRT*-Dubins (10_path_planning_01_rrt_05_rrt_star_dubins_path.py) behind the reference's API.
+
+`RRTStarDubins` is the class rrt_05 calls `RRT` (rrt_05:1335-1779): same constructor keywords,
+`planning(animation=True, search_until_max_iter=True)` returns the sampled final course (goal -> start) or
+None.  The reference's quirks are kept (see csrc/rrtk_rrtstar_dubins.cu); in particular `planning` always uses
+the uniform sampler whatever `sobol_sampler` says (rrt_05:1426).  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from math import pi
+
+import numpy as np
+
+from . import _lib, dubins, engine
+
+
+class Node:
+    """rrt_05:1336-1349.  path_x / path_y / path_yaw are regenerated on first access from the pose pair
+    the edge was planned between."""
+
+    def __init__(self, x, y, yaw):
+        self.x, self.y, self.yaw = x, y, yaw
+        self.parent = None
+        self.cost = 0.0
+        self._edge = None      # (from pose, to pose, curvature)
+        self._course = None
+
+    def _pts(self):
+        if self._course is None:
+            if self._edge is None:
+                self._course = ([], [], [])
+            else:
+                f, t, kappa = self._edge
+                x, y, yaw, _, _ = dubins.plan_dubins_path(f[0], f[1], f[2], t[0], t[1], t[2], kappa)
+                self._course = (list(x), list(y), list(yaw))
+        return self._course
+
+    path_x = property(lambda self: self._pts()[0])
+    path_y = property(lambda self: self._pts()[1])
+    path_yaw = property(lambda self: self._pts()[2])
+
+
+def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0,
+              connect_circle_dist=50.0, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5,
+              search_until_max_iter=True, near_cap=256, device=None):
+    """Q RRT*-Dubins queries in one launch.  starts/goals [Q, 3]; streams [Q, max_iter, 3].
+    Returns a list of dicts (numpy arrays trimmed to n_nodes)."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
+    goals = np.asarray(goals, dtype=np.float64).reshape(-1, 3)
+    q = starts.shape[0]
+    cap = max_iter + 1
+    rows, counts = engine.pack_obstacles(obstacle_lists, robot_radius)
+    p = _lib.DubinsParams()
+    p.n_queries, p.max_iter, p.node_cap, p.obs_stride, p.near_cap = q, max_iter, cap, rows.shape[1], near_cap
+    p.search_until_max_iter = int(bool(search_until_max_iter))
+    p.curvature, p.step_size = float(curvature), 0.1
+    p.goal_xy_th, p.goal_yaw_th = float(goal_xy_th), float(goal_yaw_th)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        d_sg, d_obs, d_cnt = t(np.hstack([starts, goals])), t(rows), t(counts)
+        d_r2 = t(engine.near_r2_table(cap, connect_circle_dist, expand_dis))
+        d_st = t(np.asarray(streams, dtype=np.float64).reshape(q, max_iter, 3))
+        f64 = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)    # noqa: E731
+        xy, yaw, cost, parent = f64(q, cap, 2), f64(q, cap), f64(q, cap), i32(q, cap)
+        ef, et = f64(q, cap, 3), f64(q, cap, 3)
+        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, cap)
+        rc = _lib.lib().rrtk_rrtstar_dubins_run_dev(
+            C.byref(p), d_sg.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_r2.data_ptr(), d_st.data_ptr(),
+            xy.data_ptr(), yaw.data_ptr(), cost.data_ptr(), parent.data_ptr(), ef.data_ptr(), et.data_ptr(),
+            n_nodes.data_ptr(), iters.data_ptr(), gi.data_ptr(), status.data_ptr(), ws.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_rrtstar_dubins_run_dev")
+        h = {k: v.cpu().numpy() for k, v in dict(xy=xy, yaw=yaw, cost=cost, parent=parent, ef=ef, et=et, n=n_nodes,
+                                                 it=iters, gi=gi, st=status).items()}
+    out = []
+    for i in range(q):
+        k = int(h["n"][i])
+        out.append(dict(x=h["xy"][i, :k, 0].copy(), y=h["xy"][i, :k, 1].copy(), yaw=h["yaw"][i, :k].copy(),
+                        cost=h["cost"][i, :k].copy(), parent=h["parent"][i, :k].copy(),
+                        edge_from=h["ef"][i, :k].copy(), edge_to=h["et"][i, :k].copy(), n=k,
+                        iters_done=int(h["it"][i]), goal_index=int(h["gi"][i]), status=int(h["st"][i])))
+    return out
+
+
+def final_course(tree, start, goal, curvature):
+    """generate_final_course (rrt_05:1512-1521): the reversed course samples of every edge from the goal node up
+    to the root, regenerated on the GPU from the stored pose pairs."""
+    gi = tree["goal_index"]
+    if gi < 0:
+        return None
+    chain = []
+    i = gi
+    while tree["parent"][i] >= 0:
+        chain.append(i)
+        i = int(tree["parent"][i])
+    path = [[float(goal[0]), float(goal[1])]]
+    if chain:
+        r = dubins.steer_batch(tree["edge_from"][chain], tree["edge_to"][chain], curvature, 0.1, max_pts=1)
+        mp = int(r["n_pts"].max())
+        r = dubins.steer_batch(tree["edge_from"][chain], tree["edge_to"][chain], curvature, 0.1, max_pts=mp)
+        for j in range(len(chain)):
+            pts = r["pts"][j, :int(r["n_pts"][j])]
+            path.extend(pts[::-1, 0:2].tolist())
+    path.append([float(start[0]), float(start[1])])
+    return path
+
+
+class RRTStarDubins:
+    """rrt_05's `RRT`: RRT* with Dubins steering, same constructor keywords and defaults (rrt_05:1358-1375)."""
+
+    Node = Node
+
+    def __init__(self, start, goal, obstacle_list, rand_area, expand_dis=3.0, path_resolution=0.5,
+                 goal_sample_rate=5, max_iter=500, play_area=None, robot_radius=0.0, sobol_sampler=True,
+                 connect_circle_dist=50.0, search_until_max_iter=False, curvature=1.0,
+                 goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5, near_cap=256):
+        self.start = Node(start[0], start[1], start[2])
+        self.end = Node(goal[0], goal[1], goal[2])
+        self.min_rand, self.max_rand = rand_area[0], rand_area[1]
+        self.play_area = play_area           # accepted; rrt_05 never checks it (:1430-1432)
+        self.expand_dis, self.path_resolution = expand_dis, path_resolution
+        self.goal_sample_rate, self.max_iter = goal_sample_rate, max_iter
+        self.obstacle_list = obstacle_list
+        self.node_list = []
+        self.robot_radius = robot_radius
+        self.sobol_sampler, self.sobol_inter_ = sobol_sampler, 0
+        self.connect_circle_dist = connect_circle_dist
+        self.search_until_max_iter = search_until_max_iter
+        self.curvature, self.goal_yaw_th, self.goal_xy_th = curvature, goal_yaw_th, goal_xy_th
+        self.near_cap = near_cap
+        self._tree = None
+
+    def get_random_node(self):
+        """rrt_05:1528-1538 (the sampler `planning` uses)."""
+        if random.randint(0, 100) > self.goal_sample_rate:
+            return (random.uniform(self.min_rand, self.max_rand), random.uniform(self.min_rand, self.max_rand),
+                    random.uniform(-pi, pi))
+        return (self.end.x, self.end.y, self.end.yaw)
+
+    def planning(self, animation=True, search_until_max_iter=True, sample_stream=None):
+        n = int(self.max_iter)
+        if sample_stream is None:
+            sample_stream = np.array([self.get_random_node() for _ in range(n)], dtype=np.float64)
+        stream = np.asarray(sample_stream, dtype=np.float64).reshape(-1, 3)[:n]
+        start = (self.start.x, self.start.y, self.start.yaw)
+        goal = (self.end.x, self.end.y, self.end.yaw)
+        t = run_batch([start], [goal], [list(self.obstacle_list)], self.expand_dis, n, stream[None],
+                      self.robot_radius, self.connect_circle_dist, self.curvature, self.goal_yaw_th,
+                      self.goal_xy_th, search_until_max_iter, self.near_cap)[0]
+        if t["status"] & _lib.Q_NEAR_OVERFLOW:
+            raise _lib.RrtkError("near list overflow: raise near_cap")
+        self._tree = t
+        nodes = [Node(float(x), float(y), float(w)) for x, y, w in zip(t["x"], t["y"], t["yaw"])]
+        for i, nd in enumerate(nodes):
+            nd.cost = float(t["cost"][i])
+            if t["parent"][i] >= 0:
+                nd.parent = nodes[t["parent"][i]]
+                nd._edge = (t["edge_from"][i], t["edge_to"][i], self.curvature)
+        self.node_list = nodes
+        return final_course(t, start, goal, self.curvature)
+
+    def tree_arrays(self):
+        return self._tree

@@ -99,3 +99,57 @@ def test_degenerate_same_pose_and_acos(oracle_lib):
                                                 torch.cuda.current_stream().cuda_stream))
     want = np.array([oracle_lib.lib().orc_cr_acos(float(v)) for v in x])
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+# ---- RRT*-Dubins planning loop (rrt_05:1416-1779) ----
+from conftest import golden_names  # noqa: E402
+
+RRT05 = golden_names("rrt05_")
+
+
+def _dub_planner(m):
+    import rrtk
+    return rrtk.RRTStarDubins(m["start"], m["goal"], m["obstacle_list"], m["rand_area"], m["expand_dis"],
+                              goal_sample_rate=m["goal_sample_rate"], max_iter=m["max_iter"],
+                              robot_radius=m["robot_radius"], connect_circle_dist=m["connect_circle_dist"],
+                              curvature=m["curvature"], goal_yaw_th=m["goal_yaw_th"], goal_xy_th=m["goal_xy_th"])
+
+
+@pytest.mark.parametrize("name", RRT05)
+def test_rrtstar_dubins_bitwise_vs_oracle_cr(name, oracle_lib):
+    O = oracle_lib
+    g, m = load_golden(name)
+    ref = O.rrtstar_dubins_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"],
+                               m["robot_radius"], m["connect_circle_dist"], m["curvature"], m["goal_yaw_th"],
+                               m["goal_xy_th"], m["search_until_max_iter"], g["stream"], O.MATH_CR)
+    r = _dub_planner(m)
+    path = r.planning(animation=False, search_until_max_iter=m["search_until_max_iter"], sample_stream=g["stream"])
+    t = r.tree_arrays()
+    assert t["n"] == ref["n"] and t["iters_done"] == ref["iters_done"] and t["goal_index"] == ref["goal_index"]
+    assert np.array_equal(t["parent"], ref["parent"])
+    for k in ("x", "y", "yaw", "cost"):
+        assert np.array_equal(t[k], ref[k]), k
+    assert np.array_equal(t["edge_from"][1:], ref["edge_from"][1:]) and np.array_equal(t["edge_to"][1:], ref["edge_to"][1:])
+    assert (path is None) == (ref["path"] is None)
+    if path is not None:
+        assert path == ref["path"]
+
+
+@pytest.mark.parametrize("name", RRT05)
+def test_rrtstar_dubins_vs_reference_fixture(name):
+    """Against the unmodified reference: identical node count, parents and path length; poses, costs and path
+    points within 1e-9 (Dubins poses carry ulp-level libm differences; north_star allows 1e-5 relative)."""
+    g, m = load_golden(name)
+    r = _dub_planner(m)
+    path = r.planning(animation=False, search_until_max_iter=m["search_until_max_iter"], sample_stream=g["stream"])
+    t = r.tree_arrays()
+    assert t["n"] == len(g["x"]) and np.array_equal(t["parent"], g["parent"])
+    for k in ("x", "y", "yaw", "cost"):
+        assert np.allclose(t[k], g[k], rtol=0, atol=1e-9), k
+    if len(g["path"]) == 0:
+        assert path is None
+    else:
+        assert len(path) == len(g["path"]) and np.allclose(np.array(path), g["path"], rtol=0, atol=1e-9)
+        # Node objects expose the sampled edges like the reference's
+        nd = r.node_list[t["goal_index"]]
+        assert len(nd.path_x) == len(nd.path_y) == len(nd.path_yaw) > 1 and nd.parent is not None

@@ -210,3 +210,39 @@ def test_acos_correctly_rounded(oracle_lib):
     diff = sum(L.orc_cr_acos(float(x)) != math.acos(float(x)) for x in xs)
     assert diff <= 40
     assert all(abs(L.orc_cr_acos(float(x)) - math.acos(float(x))) <= 4.5e-16 for x in xs[:2000])
+
+
+# ---- RRT*-Dubins loop (rrt_05:1416-1779) ----
+RRT05 = golden_names("rrt05_")
+
+
+@pytest.mark.parametrize("name", ["rrt05_builtin_500", "rrt05_early_exit_600"])
+def test_dubins_loop_python_port_bit_identical_to_reference(name):
+    import pyport
+    g, m = load_golden(name)
+    p = pyport.RRTStarDubinsPort(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"],
+                                 m["robot_radius"], m["connect_circle_dist"], m["curvature"], m["goal_yaw_th"],
+                                 m["goal_xy_th"], m["search_until_max_iter"])
+    path = p.planning([tuple(r) for r in g["stream"]])
+    for k, v in (("x", p.x), ("y", p.y), ("yaw", p.yaw), ("cost", p.cost), ("parent", p.parent)):
+        assert np.array_equal(np.array(v), g[k]), k
+    assert (path is None and len(g["path"]) == 0) or np.array_equal(np.array(path, float), g["path"])
+
+
+@pytest.mark.parametrize("name", RRT05)
+def test_dubins_loop_c_oracle(name, oracle_lib):
+    """libm mode: bit-identical to the reference (tree and sampled path).  cr mode: same tree topology,
+    poses within 1e-12."""
+    O = oracle_lib
+    g, m = load_golden(name)
+    args = (m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["robot_radius"],
+            m["connect_circle_dist"], m["curvature"], m["goal_yaw_th"], m["goal_xy_th"], m["search_until_max_iter"],
+            g["stream"])
+    r = O.rrtstar_dubins_run(*args, O.MATH_LIBM)
+    for k in ("x", "y", "yaw", "cost", "parent"):
+        assert np.array_equal(r[k], g[k]), k
+    assert (r["path"] is None and len(g["path"]) == 0) or np.array_equal(np.array(r["path"], float), g["path"])
+    c = O.rrtstar_dubins_run(*args, O.MATH_CR)
+    assert c["n"] == r["n"] and np.array_equal(c["parent"], r["parent"]) and c["goal_index"] == r["goal_index"]
+    for k in ("x", "y", "yaw", "cost"):
+        assert np.allclose(c[k], r[k], rtol=0, atol=1e-12), k
