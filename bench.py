@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--obstacles", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nn-nodes", type=int, default=1 << 26, help="nodes in the NN-search roofline run")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (arm grid, Dubins, informed)")
     return ap.parse_args()
 
 
@@ -373,6 +374,8 @@ def main():
                                   "no explicit flush"),
                    clocks=clk, e2e=e2e, gpu_launches=args.steps, roofline=roofline, roofline_nn=nn,
                    paths_found=found, mean_nodes=float(n_nodes.mean()))
+        if not args.no_extras:
+            out["extras"] = extras(torch, dev)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(iters, n_obs)
             out["cpu_baseline_c"] = cpu_baseline_c(iters, n_obs)
@@ -381,6 +384,97 @@ def main():
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
+
+
+def _timed(torch, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 1e3 / reps
+
+
+def extras(torch, dev):
+    """The other BASELINE configs, each a short device-timed run (inputs resident; parity is in tests/)."""
+    import math
+    import numpy as np
+    import ctypes as C
+    from rrtk import _lib, arm as A, dubins, dubins_planner as DP, informed as INF, engine
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    out = {}
+    try:   # config 5: arm C-space grid, M = 8192, 64 obstacle sets, script arm (arm02:298-304)
+        M, S = 8192, 64
+        rng = np.random.default_rng(5)
+        sets = np.concatenate([rng.uniform(-2, 2, (S, 5, 2)), rng.uniform(0.2, 0.7, (S, 5, 1))], axis=2)
+        sets[0] = [[1.75, 0.75, 0.6], [0.55, 1.5, 0.5], [0, -1, 0.7], [0, -0.6, 0.4], [-1, 1., 0.3]]
+        link = np.array([0.5, 0.5, 0.3, 0.5, 0.1])
+        theta = torch.from_numpy(A.theta_list(M)).to(dev)
+        d_obs = torch.from_numpy(sets).to(dev)
+        grid = torch.empty((S, M, M), dtype=torch.uint8, device=dev)
+        t = _timed(torch, lambda: L.rrtk_arm_grid_dev(M, theta.data_ptr(), 0, M, 5, link.ctypes.data, d_obs.data_ptr(),
+                                                      S, 5, grid.data_ptr(), s), reps=2)
+        out["c5_arm_grid"] = dict(cells_per_s=M * M * S / t, ms=t * 1e3, M=M, sets=S, out_gb=M * M * S / 1e9,
+                                  occupied_set0=int(grid[0].sum().item()))
+        del grid
+    except Exception as e:  # noqa: BLE001
+        out["c5_arm_grid"] = dict(error=repr(e))
+    try:   # Dubins steering primitive: 262144 edges among 16 circles
+        n = 1 << 18
+        rng = np.random.default_rng(6)
+        f = np.column_stack([rng.uniform(0, 12, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+        tt = np.column_stack([f[:, 0:2] + rng.uniform(-4, 4, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+        obs = np.zeros((1, 16, 4)); o = rng.uniform(0, 12, (16, 2)); r = rng.uniform(0.2, 0.8, 16)
+        obs[0, :, 0:2] = o; obs[0, :, 2] = r; obs[0, :, 3] = r * r
+        d_f, d_t, d_o = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (f, tt, obs))
+        d_c = torch.tensor([16], dtype=torch.int32, device=dev)
+        mode = torch.empty(n, dtype=torch.int32, device=dev); ln = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        end = torch.empty((n, 3), dtype=torch.float64, device=dev); npt = torch.empty(n, dtype=torch.int32, device=dev)
+        fr = torch.empty(n, dtype=torch.uint8, device=dev)
+        t = _timed(torch, lambda: L.rrtk_dubins_steer_dev(n, 1.0, 0.1, d_f.data_ptr(), d_t.data_ptr(), None, d_o.data_ptr(),
+                                                          16, d_c.data_ptr(), mode.data_ptr(), ln.data_ptr(), end.data_ptr(),
+                                                          npt.data_ptr(), fr.data_ptr(), None, 0, s))
+        out["dubins_steer"] = dict(edges_per_s=n / t, ms=t * 1e3, edges=n,
+                                   course_points_per_s=float(npt.sum().item()) / t)
+    except Exception as e:  # noqa: BLE001
+        out["dubins_steer"] = dict(error=repr(e))
+    try:   # config 4: RRT*-Dubins, 1024 queries x 500 iterations, built-in scenario (rrt_05:1804-1859)
+        Q, iters = 1024, 500
+        rng = np.random.default_rng(7)
+        st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+        coin = rng.integers(0, 101, (Q, iters)) <= 10
+        st[coin] = (10.0, 10.0, 0.0)
+        obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)]] * Q
+        t0 = time.perf_counter()
+        res = DP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 10.0, 0.0]] * Q, obs, 3.0, iters, st)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        out["c4_rrtstar_dubins"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+                                        mean_nodes=float(np.mean([r["n"] for r in res])),
+                                        solved=int(sum(r["goal_index"] >= 0 for r in res)))
+    except Exception as e:  # noqa: BLE001
+        out["c4_rrtstar_dubins"] = dict(error=repr(e))
+    try:   # Informed RRT* (rrt_07 semantics), 512 queries x 1000 iterations, built-in scenario
+        Q, iters = 512, 1000
+        rng = np.random.default_rng(8)
+        free = rng.uniform(-2, 15, (Q, iters, 2)); coin = rng.integers(0, 101, (Q, iters)) <= 10
+        free[coin] = (6.0, 10.0)
+        ball = rng.random((Q, iters, 2))
+        obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]] * Q
+        t0 = time.perf_counter()
+        res = INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, obs, 0.5, iters, free, ball)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        out["informed_rrtstar"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+                                       mean_nodes=float(np.mean([r["n"] for r in res])),
+                                       solved=int(sum(r["path"] is not None for r in res)))
+    except Exception as e:  # noqa: BLE001
+        out["informed_rrtstar"] = dict(error=repr(e))
+    return out
 
 
 def algorithmic_work(iters, n_obs, n_sample=4):
