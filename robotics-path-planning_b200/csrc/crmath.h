@@ -236,9 +236,42 @@ CRM_FN double crm_atan2_guess(double y, double x) {
     return y < 0.0 ? -a : a;
 }
 
-/* theta = RN(atan2(y, x)); *s = RN(sin(theta)); *c = RN(cos(theta)).
- * Newton: theta = t0 + atan(u), u = (y cos t0 - x sin t0) / (x cos t0 + y sin t0), all double-double;
- * then sin/cos(theta) by rotating (sin t0, cos t0) through eps = theta - t0 (exact, |eps| < 1e-9). */
+/* Double-double atan2 of (my, mx) given as double-doubles with 0 <= my <= mx (first octant):
+ * t = my / mx, table entry atan(i/128), u = (t - i/128) / (1 + t i/128), |u| <= 2^-8, and
+ * atan(u) = u - u^3/3 + u^5/5 - ... (two leading corrections in double-double, the tail in double). */
+CRM_NOINLINE crm_dd crm_atan_octant_dd(crm_dd my, crm_dd mx) {
+    crm_dd t = crm_div(my, mx);
+    int i = (int)rint(t.hi * 128.0);
+    double ti = (double)i * 0.0078125;
+    crm_dd num = crm_fast_two_sum(t.hi - ti, t.lo);          /* t.hi - ti exact (Sterbenz) */
+    crm_dd den = crm_add_d(crm_mul_d(t, ti), 1.0);
+    crm_dd u = i == 0 ? t : crm_div(num, den);
+    crm_dd z = crm_mul(u, u);
+    double tail = -1.0 / 7.0 + z.hi * (1.0 / 9.0 - z.hi * (1.0 / 11.0));
+    crm_dd p = crm_add(crm_mul_d(z, tail), crm_mk(CRM_FIFTH_H, CRM_FIFTH_L));
+    p = crm_sub(crm_mul(z, p), crm_mk(CRM_THIRD_H, CRM_THIRD_L));
+    crm_dd at = crm_add(u, crm_mul(u, crm_mul(z, p)));
+    return i == 0 ? at : crm_add(crm_mk(crm_atan_tab[i][0], crm_atan_tab[i][1]), at);
+}
+
+/* full-circle double-double atan2 for finite (y, x), y != 0 */
+CRM_FN crm_dd crm_atan2_dd(double y, double x) {
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax;
+    crm_dd a = crm_atan_octant_dd(crm_mk(swap ? ax : ay, 0.0), crm_mk(swap ? ay : ax, 0.0));
+    if (swap) a = crm_sub(crm_mk(CRM_PIO2_H, CRM_PIO2_L), a);
+    if (x < 0.0) a = crm_sub(crm_mk(CRM_PI_H, CRM_PI_L), a);
+    return y < 0.0 ? crm_neg(a) : a;
+}
+
+/* theta = RN(atan2(y, x)); *s = RN(sin(theta)); *c = RN(cos(theta)) -- the three calls of
+ * rrt_04:1236 and :1100-1101.  With A the exact angle and e = theta - A (|e| <= ulp(theta) / 2):
+ *   cos(theta) = x/d - e * y/d,  sin(theta) = y/d + e * x/d,  d = sqrt(x^2 + y^2)
+ * (e^2 < 2^-104 is dropped); x/d and y/d are formed in double-double, no sin/cos series needed.
+ * Near the axes cos or sin of theta is itself of the order of e, so e must be known to ~2^-53
+ * relative, not absolute: |A| = k pi/2 + sa * a with a = atan(min/max) in [0, pi/4] from the octant core
+ * (relative error 2^-100), and e = (|theta| - k PIO2_H) - sa a.hi - k PIO2_L - sa a.lo - k PIO2_LL is
+ * summed in double-double (the first difference is exact by Sterbenz). */
 CRM_FN double crm_atan2_sincos(double y, double x, double *s, double *c) {
     if (y == 0.0) { /* includes (0, 0): atan2 = +-0 or +-pi */
         int neg = (x < 0.0) || (x == 0.0 && signbit(x));
@@ -248,35 +281,47 @@ CRM_FN double crm_atan2_sincos(double y, double x, double *s, double *c) {
         *c = -1.0;
         return th;
     }
-    double t0 = crm_atan2_guess(y, x);
-    crm_dd s0, c0;
-    crm_sincos_dd(t0, &s0, &c0);
-    crm_dd num = crm_sub(crm_mul_d(c0, y), crm_mul_d(s0, x));
-    crm_dd den = crm_add(crm_mul_d(c0, x), crm_mul_d(s0, y));
-    crm_dd u = crm_div(num, den);
-    crm_dd u3 = crm_mul(crm_mul(u, u), u);
-    crm_dd del = crm_sub(u, crm_mul(u3, crm_mk(CRM_THIRD_H, CRM_THIRD_L)));
-    crm_dd th = crm_add_d(del, t0);
-    double theta = th.hi;
-    double eps = theta - t0; /* exact */
-    /* sin(eps) = eps - eps^3/6, cos(eps) = 1 - eps^2/2 (next terms < 1e-37) */
-    crm_dd e2 = crm_two_prod(eps, eps);
-    crm_dd se = crm_sub(crm_mk(eps, 0.0), crm_mul_d(crm_mul_d(e2, eps), 1.0 / 6.0));
-    crm_dd ce = crm_add_d(crm_mul_d(e2, -0.5), 1.0);
-    crm_dd st = crm_add(crm_mul(s0, ce), crm_mul(c0, se));
-    crm_dd ct = crm_sub(crm_mul(c0, ce), crm_mul(s0, se));
-    *s = st.hi;
-    *c = ct.hi;
-    return theta;
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax, xneg = x < 0.0;
+    crm_dd a = crm_atan_octant_dd(crm_mk(swap ? ax : ay, 0.0), crm_mk(swap ? ay : ax, 0.0));
+    if (swap != xneg) a = crm_neg(a);                 /* sa * a */
+    double ch = swap ? CRM_PIO2_H : CRM_PI_H, cl = swap ? CRM_PIO2_L : CRM_PI_L;
+    double cll = swap ? CRM_PIO2_LL : CRM_PI_LL;
+    double tabs;
+    crm_dd e;
+    if (swap || xneg) {
+        tabs = crm_add(crm_mk(ch, cl), a).hi;
+        e = crm_add(crm_two_sum(tabs - ch, -a.hi), crm_two_sum(-cl, -a.lo));
+        e = crm_add_d(e, -cll);
+    } else {
+        tabs = a.hi;
+        e = crm_mk(-a.lo, 0.0);
+    }
+    if (y < 0.0) e = crm_neg(e);
+    /* d = sqrt(x*x + y*y) and 1/d in double-double */
+    crm_dd d2 = crm_add(crm_two_prod(x, x), crm_two_prod(y, y));
+    double d0 = sqrt(d2.hi);
+    crm_dd r = crm_sub(d2, crm_two_prod(d0, d0));
+    crm_dd d = crm_fast_two_sum(d0, r.hi / (2.0 * d0));
+    double i0 = 1.0 / d.hi;
+    r = crm_sub(crm_mk(1.0, 0.0), crm_mul_d(d, i0));
+    crm_dd inv = crm_fast_two_sum(i0, r.hi * i0);
+    crm_dd cd = crm_mul_d(inv, x), sd = crm_mul_d(inv, y);
+    *c = crm_sub(cd, crm_mul(e, sd)).hi;
+    *s = crm_add(sd, crm_mul(e, cd)).hi;
+    return y < 0.0 ? -tabs : tabs;
 }
 
 CRM_FN double crm_atan2(double y, double x) {
-    double s, c;
-    return crm_atan2_sincos(y, x, &s, &c);
+    if (y == 0.0) {
+        int neg = (x < 0.0) || (x == 0.0 && signbit(x));
+        return neg ? copysign(CRM_PI_H, y) : y;
+    }
+    return crm_atan2_dd(y, x).hi;
 }
 
 /* RN(acos(x)) for |x| <= 1 (NaN outside): acos(x) = atan2(sqrt((1 - x)(1 + x)), x) with the square root
- * carried in double-double and the same Newton step as crm_atan2_sincos. */
+ * carried in double-double into the same octant core as crm_atan2. */
 CRM_FN double crm_acos(double x) {
     if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
     if (x == 1.0) return 0.0;
@@ -286,16 +331,12 @@ CRM_FN double crm_acos(double x) {
     double s0 = sqrt(p.hi);
     crm_dd e = crm_sub(p, crm_two_prod(s0, s0));
     crm_dd y = crm_fast_two_sum(s0, e.hi / (2.0 * s0)); /* sqrt(p) to ~2^-104 */
-    double t0 = crm_atan2_guess(y.hi, x);
-    crm_dd s0d, c0d;
-    crm_sincos_dd(t0, &s0d, &c0d);
-    crm_dd num = crm_sub(crm_mul(c0d, y), crm_mul_d(s0d, x));
-    crm_dd den = crm_add(crm_mul_d(c0d, x), crm_mul(s0d, y));
-    crm_dd u = crm_div(num, den);
-    crm_dd u3 = crm_mul(crm_mul(u, u), u);
-    crm_dd del = crm_sub(u, crm_mul(u3, crm_mk(CRM_THIRD_H, CRM_THIRD_L)));
-    crm_dd th = crm_add_d(del, t0);
-    return th.hi;
+    crm_dd ax = crm_mk(fabs(x), 0.0);
+    int swap = y.hi > ax.hi;
+    crm_dd at = crm_atan_octant_dd(swap ? ax : y, swap ? y : ax);
+    if (swap) at = crm_sub(crm_mk(CRM_PIO2_H, CRM_PIO2_L), at);
+    if (x < 0.0) at = crm_sub(crm_mk(CRM_PI_H, CRM_PI_L), at);
+    return at.hi;
 }
 
 #endif /* RRTK_CRMATH_H */

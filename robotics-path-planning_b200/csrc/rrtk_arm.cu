@@ -40,7 +40,9 @@ __device__ __noinline__ bool detect_collision_exact(double ax, double ay, double
     return !(dist > r);
 }
 
-extern "C" __global__ void __launch_bounds__(ARM_THREADS)
+// MAXL = compile-time bound on the number of links (the per-cell joint positions live in registers)
+template <int MAXL>
+__global__ void __launch_bounds__(ARM_THREADS)
 arm_grid_kernel(ArmParams p, const double *__restrict__ theta, const double *__restrict__ obstacles,
                 uint8_t *__restrict__ grid) {
     extern __shared__ double s_obs[];  // [S * O][4]: x, y, r, r * r
@@ -58,10 +60,10 @@ arm_grid_kernel(ArmParams p, const double *__restrict__ theta, const double *__r
         // forward kinematics (arm02:257-262): joint k uses theta1 (k = 1) or theta1 + theta2 (k >= 2)
         const double a1 = theta[i], a2 = theta[i] + theta[j];
         const double c1 = crm_cos(a1), s1 = crm_sin(a1), c2 = crm_cos(a2), s2 = crm_sin(a2);
-        double px[ARM_MAX_LINKS + 1], py[ARM_MAX_LINKS + 1], l2[ARM_MAX_LINKS];
+        double px[MAXL + 1], py[MAXL + 1], l2[MAXL];
         px[0] = 0.0; py[0] = 0.0;
 #pragma unroll
-        for (int k = 1; k <= ARM_MAX_LINKS; k++) {
+        for (int k = 1; k <= MAXL; k++) {
             if (k <= p.n_links) {
                 px[k] = px[k - 1] + p.link[k - 1] * (k == 1 ? c1 : c2);
                 py[k] = py[k - 1] + p.link[k - 1] * (k == 1 ? s1 : s2);
@@ -73,7 +75,7 @@ arm_grid_kernel(ArmParams p, const double *__restrict__ theta, const double *__r
             const double *ob = s_obs + (size_t)s * p.O * 4;
             bool hit = false;
 #pragma unroll
-            for (int k = 0; k < ARM_MAX_LINKS; k++) {
+            for (int k = 0; k < MAXL; k++) {
                 if (k < p.n_links && !hit) {
                     const double ax = px[k], ay = py[k], bx = px[k + 1], by = py[k + 1];
                     const double l0 = bx - ax, l1 = by - ay, L2 = l2[k];
@@ -109,19 +111,28 @@ int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_link
     for (int k = 0; k < ARM_MAX_LINKS; k++) p.link[k] = k < n_links ? link_host[k] : 0.0;
     size_t smem = (size_t)S * O * 4 * sizeof(double);
     if (smem > 200 * 1024) return set_error(RRTK_ERR_INVALID, "S * O circles do not fit in shared memory (max 6400)");
-    cudaError_t e = cudaFuncSetAttribute(arm_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ARM_THREADS, smem);
+        if (per_sm < 1) per_sm = 1;
+        long long cells = (long long)n_rows * M;
+        long long want = (cells + ARM_THREADS - 1) / ARM_THREADS;
+        long long grid_dim = (long long)sms * per_sm;  // persistent, a multiple of the SM count
+        if (grid_dim > want) grid_dim = want;
+        if (grid_dim < 1) grid_dim = 1;
+        kernel<<<(unsigned)grid_dim, ARM_THREADS, smem, s>>>(p, theta, obstacles, grid);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (n_links <= 2) e = launch(arm_grid_kernel<2>);
+    else if (n_links <= 5) e = launch(arm_grid_kernel<5>);
+    else if (n_links <= 8) e = launch(arm_grid_kernel<8>);
+    else e = launch(arm_grid_kernel<ARM_MAX_LINKS>);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(arm_grid_kernel)");
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arm_grid_kernel, ARM_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    long long cells = (long long)n_rows * M;
-    long long want = (cells + ARM_THREADS - 1) / ARM_THREADS;
-    long long grid_dim = (long long)sms * per_sm;  // persistent, a multiple of the SM count
-    if (grid_dim > want) grid_dim = want;
-    if (grid_dim < 1) grid_dim = 1;
-    arm_grid_kernel<<<(unsigned)grid_dim, ARM_THREADS, smem, s>>>(p, theta, obstacles, grid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "arm_grid_kernel launch");
     return RRTK_OK;
