@@ -170,6 +170,53 @@ RRTK_API int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *
                                    double *ws_d, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Informed RRT* on ONE large tree (BASELINE config 3: grow to ~10^6 nodes): the same search as
+ * rrtk_informed_run_dev (rrt_07:1044-1108), bit-identical results, but the whole GPU works on a single query:
+ * get_nearest_list_index (:1210-1214) and find_near_nodes (:1137-1143) stream the FP64 node array (16 B / node)
+ * across all SMs in one fused pass per iteration, choose_parent (:1110-1135) and rewire (:1232-1246) are
+ * spread over the SMs that own the near nodes; one grid-wide reduction per iteration (persistent cooperative
+ * kernel, one CTA per SM).
+ *   obstacles [n_obs][4] = x, y, size, size**2 (n_obs <= 512);  near_rr2 [node_cap + 1][2] = (r, r**2) as above;
+ *   free_samples, ball_draws [max_iter][2] as for rrtk_informed_run_dev;
+ *   coord_bound: an upper bound on |coordinate| of anything in the scene (sets the tolerance band inside which a
+ *     near edge falls back to the reference's exact end-point arithmetic; results do not depend on it);
+ *   grid: 0 = one CTA per SM; tests pass small values to exercise the multi-pass scans on small trees.
+ * outputs: xy [node_cap][2], cost [node_cap], parent [node_cap], path [path_cap][2] (best-path snapshot),
+ *   result (device struct).  workspace: rrtk_informed_tree_workspace_bytes(node_cap) bytes of device memory.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rrtk_informed_tree_params {
+    int32_t max_iter;
+    int32_t node_cap;
+    int32_t n_obs;
+    int32_t path_cap;
+    int32_t grid;
+    int32_t pad_;
+    double expand_dis;
+    double start_goal[4]; /* sx, sy, gx, gy */
+    double rot[4];        /* c00, c01, c10, c11 of C (rrt_07:1063-1068) */
+    double coord_bound;
+} rrtk_informed_tree_params;
+
+typedef struct rrtk_informed_tree_result {
+    int32_t n_nodes, path_len, status, iters_done;
+    double c_best;
+    int64_t total_hits;   /* sum over iterations of len(near_inds) */
+    int32_t slow_paths;   /* iterations that needed the exact equal-d^2 resolution */
+    int32_t goal_events;  /* iterations whose new node connected to the goal */
+    int32_t resamples;    /* iterations after which c_best changed (next sample and nearest redone) */
+    int32_t grid;         /* CTAs used */
+    int64_t cycles[6];    /* SM clock cycles CTA 0 spent in each phase (new node, collision + cull, scan,
+                             candidates, grid reduce, append + rewire + goal); diagnostics for profiles/ */
+} rrtk_informed_tree_result;
+
+RRTK_API int64_t rrtk_informed_tree_workspace_bytes(int32_t node_cap, int32_t grid);
+RRTK_API int rrtk_informed_tree_run_dev(const rrtk_informed_tree_params *p, const double *obstacles,
+                                        const double *near_rr2, const double *free_samples,
+                                        const double *ball_draws, double *xy, double *cost, int32_t *parent,
+                                        double *path, rrtk_informed_tree_result *result, void *workspace,
+                                        int64_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Batched Dubins steering: plan_dubins_path (rrt_05:1021-1109 == dub00) + the sampled collision test of
  * the course (check_collision rrt_05:1625-1638) -- one edge of RRT*-Dubins' `steer` (rrt_05:1458-1479).
  *   from3, to3 [N][3] = x, y, yaw;  curvature, step_size (0.1 in the reference)

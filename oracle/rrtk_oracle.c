@@ -574,6 +574,11 @@ ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *ob
     int cap = p->max_iter + 1, n = 1;
     double *dl = (double *)malloc(sizeof(double) * cap);
     int *near = (int *)malloc(sizeof(int) * cap);
+    int hb = 10;
+    while ((1 << hb) < 4 * cap && hb < 28) hb++;
+    uint32_t *hgen = (uint32_t *)calloc((size_t)1 << hb, sizeof(uint32_t));
+    uint64_t *hkey = (uint64_t *)malloc(sizeof(uint64_t) << hb);
+    int *hidx = (int *)malloc(sizeof(int) << hb);
     x[0] = p->sx; y[0] = p->sy; cost[0] = 0.0; parent[0] = -1;
     double c_best = INFINITY;
     const double c_min = orc_hypot(p->sx - p->gx, p->sy - p->gy);
@@ -613,10 +618,21 @@ ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *ob
         double r2 = sq_libm(r); /* per-size constant: host libm in the product too */
         int n_near = 0;
         for (int i = 0; i < n; i++) dl[i] = sq(mode, x[i] - nx) + sq(mode, y[i] - ny);
+        /* near_inds = [d_list.index(v) for v in d_list if v <= r ** 2]: `.index` returns the FIRST position
+         * holding an equal value; that position is itself a hit, so it is found through a hash of the hits'
+         * bit patterns (generation-stamped, no clearing) instead of a scan from 0 -- same result, O(1). */
         for (int i = 0; i < n; i++)
             if (dl[i] <= r2) {
-                int f = 0;
-                while (dl[f] != dl[i]) f++;
+                uint64_t key;
+                memcpy(&key, &dl[i], 8);
+                uint64_t h = key * 0x9E3779B97F4A7C15ull;
+                uint32_t slot = (uint32_t)(h >> (64 - hb));
+                int f = i;
+                for (;;) {
+                    if (hgen[slot] != (uint32_t)(it + 1)) { hgen[slot] = (uint32_t)(it + 1); hkey[slot] = key; hidx[slot] = i; break; }
+                    if (hkey[slot] == key) { f = hidx[slot]; break; }
+                    slot = (slot + 1) & ((1u << hb) - 1u);
+                }
                 near[n_near++] = f;
             }
         /* choose_parent rrt_07:1110-1135 */
@@ -671,7 +687,7 @@ ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *ob
     }
     *n_nodes = n;
     *c_best_out = c_best;
-    free(dl); free(near);
+    free(dl); free(near); free(hgen); free(hkey); free(hidx);
     return 0;
 }
 

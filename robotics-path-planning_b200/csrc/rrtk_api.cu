@@ -54,6 +54,11 @@ int launch_informed(const rrtk_informed_params &p, const double *start_goal, con
                     const double *ball, double *xy, double *cost, int32_t *parent, int32_t *n_nodes, double *path,
                     int32_t *path_len, double *c_best, int32_t *status, int32_t *ws_idx, double *ws_d,
                     unsigned int *counter, cudaStream_t s);
+int informed_tree_workspace_bytes(int node_cap, int grid, size_t *bytes);
+int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obstacles, const double *near_rr2,
+                         const double *free_s, const double *ball, double *xy, double *cost, int32_t *parent,
+                         double *path, rrtk_informed_tree_result *res, void *workspace, size_t workspace_bytes,
+                         cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -166,6 +171,32 @@ int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goa
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
     return launch_informed(*p, start_goal, rot, obstacles, n_obs, near_rr2, free_samples, ball_draws, xy, cost, parent,
                            n_nodes, path, path_len, c_best, status, ws_idx, ws_d, ctr.ptr, s);
+}
+
+int64_t rrtk_informed_tree_workspace_bytes(int32_t node_cap, int32_t grid) {
+    if (node_cap < 1 || grid < 0) return set_error(RRTK_ERR_INVALID, "node_cap < 1 or grid < 0");
+    size_t b = 0;
+    int rc = informed_tree_workspace_bytes(node_cap, grid, &b);
+    return rc ? rc : (int64_t)b;
+}
+
+int rrtk_informed_tree_run_dev(const rrtk_informed_tree_params *p, const double *obstacles, const double *near_rr2,
+                               const double *free_samples, const double *ball_draws, double *xy, double *cost,
+                               int32_t *parent, double *path, rrtk_informed_tree_result *result, void *workspace,
+                               int64_t workspace_bytes, void *stream) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->max_iter < 0 || p->node_cap < 1 || p->path_cap < 2 || p->n_obs < 0 || p->grid < 0)
+        return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (p->n_obs > 512) return set_error(RRTK_ERR_INVALID, "n_obs > 512 (shared-memory obstacle stage)");
+    if (!(p->expand_dis > 0.0)) return set_error(RRTK_ERR_INVALID, "expand_dis must be > 0");
+    if (!(p->coord_bound > 0.0)) return set_error(RRTK_ERR_INVALID, "coord_bound must be > 0");
+    if (!near_rr2 || !xy || !cost || !parent || !path || !result || !workspace ||
+        (p->max_iter > 0 && (!free_samples || !ball_draws)) || (p->n_obs > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)xy | (uintptr_t)path | (uintptr_t)workspace) & 15)
+        return set_error(RRTK_ERR_INVALID, "xy, path and workspace must be 16-byte aligned");
+    return launch_informed_tree(*p, obstacles, near_rr2, free_samples, ball_draws, xy, cost, parent, path, result,
+                                workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
 }
 
 int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_size, const double *from3,

@@ -34,6 +34,21 @@ class InformedParams(C.Structure):
                 ("expand_dis", C.c_double)]
 
 
+class InformedTreeParams(C.Structure):
+    """struct rrtk_informed_tree_params (include/rrtk.h)."""
+    _fields_ = [("max_iter", C.c_int32), ("node_cap", C.c_int32), ("n_obs", C.c_int32), ("path_cap", C.c_int32),
+                ("grid", C.c_int32), ("pad_", C.c_int32), ("expand_dis", C.c_double),
+                ("start_goal", C.c_double * 4), ("rot", C.c_double * 4), ("coord_bound", C.c_double)]
+
+
+class InformedTreeResult(C.Structure):
+    """struct rrtk_informed_tree_result (include/rrtk.h)."""
+    _fields_ = [("n_nodes", C.c_int32), ("path_len", C.c_int32), ("status", C.c_int32), ("iters_done", C.c_int32),
+                ("c_best", C.c_double), ("total_hits", C.c_int64), ("slow_paths", C.c_int32),
+                ("goal_events", C.c_int32), ("resamples", C.c_int32), ("grid", C.c_int32),
+                ("cycles", C.c_int64 * 6)]
+
+
 class DubinsParams(C.Structure):
     """struct rrtk_dubins_params (include/rrtk.h)."""
     _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
@@ -55,6 +70,8 @@ _SIGS = {
     "rrtk_rrtstar_run_dev": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 16),
     "rrtk_rrtstar_run_host": (C.c_int, [C.POINTER(RRTStarParams)] + [_VP] * 14),
     "rrtk_informed_run_dev": (C.c_int, [C.POINTER(InformedParams)] + [_VP] * 18),
+    "rrtk_informed_tree_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "rrtk_informed_tree_run_dev": (C.c_int, [C.POINTER(InformedTreeParams)] + [_VP] * 10 + [C.c_int64, _VP]),
     "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

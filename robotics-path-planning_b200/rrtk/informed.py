@@ -112,6 +112,83 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples,
     return out
 
 
+class TreeRun:
+    """Device-resident result of `run_tree` (one large Informed RRT* tree)."""
+
+    def __init__(self, xy, cost, parent, path, res, max_iter):
+        self.xy, self.cost, self.parent, self.path_dev, self._res, self.max_iter = xy, cost, parent, path, res, max_iter
+        self._info = None
+
+    @property
+    def info(self) -> dict:
+        """The kernel's result struct (synchronises)."""
+        if self._info is None:
+            raw = bytes(self._res.cpu().numpy().tobytes())
+            r = _lib.InformedTreeResult.from_buffer_copy(raw)
+            self._info = {k: getattr(r, k) for k, _ in _lib.InformedTreeResult._fields_}
+            self._info["cycles"] = list(self._info["cycles"])
+        return self._info
+
+    def arrays(self) -> dict:
+        """Host copies trimmed to n_nodes, same keys as `run_batch` entries."""
+        i = self.info
+        k = i["n_nodes"]
+        xy = self.xy[:k].cpu().numpy()
+        pl = i["path_len"]
+        return dict(x=xy[:, 0].copy(), y=xy[:, 1].copy(), cost=self.cost[:k].cpu().numpy(),
+                    parent=self.parent[:k].cpu().numpy(), n=k, c_best=i["c_best"], status=i["status"],
+                    path=None if pl == 0 else self.path_dev[:min(pl, self.path_dev.shape[0])].cpu().numpy().tolist())
+
+
+def run_tree(start, goal, obstacle_list, expand_dis, max_iter, free_samples, ball_draws, node_cap=None,
+             path_cap=4096, grid=0, device=None) -> TreeRun:
+    """ONE informed search with the whole GPU on it (BASELINE config 3; rrtk_informed_tree_run_dev).
+    free_samples / ball_draws: [max_iter, 2] (numpy or CUDA tensors).  Enqueues and returns; results stay on the GPU."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    cap = int(max_iter) + 1 if node_cap is None else int(node_cap)
+    rows = np.array([[ox, oy, size, size ** 2] for ox, oy, size in obstacle_list], dtype=np.float64).reshape(-1, 4)
+    p = _lib.InformedTreeParams()
+    p.max_iter, p.node_cap, p.n_obs, p.path_cap, p.grid = int(max_iter), cap, rows.shape[0], int(path_cap), int(grid)
+    p.expand_dis = float(expand_dis)
+    sg = [float(start[0]), float(start[1]), float(goal[0]), float(goal[1])]
+    rot = rotation_to_world_frame(start, goal)
+    for i in range(4):
+        p.start_goal[i] = sg[i]
+        p.rot[i] = rot[i]
+
+    def t(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(dev, torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    with torch.cuda.device(dev):
+        d_free, d_ball = t(free_samples).reshape(-1, 2), t(ball_draws).reshape(-1, 2)
+        if d_free.shape[0] < max_iter or d_ball.shape[0] < max_iter:
+            raise _lib.RrtkError("run_tree: need max_iter rows of free_samples and ball_draws")
+        bound = max([abs(v) for v in sg] + [float(d_free.abs().max().item()) if max_iter else 0.0] +
+                    [abs(float(v)) for v in rows[:, :3].ravel()] + [1.0])
+        p.coord_bound = 2.0 * bound + 4.0 * float(expand_dis)
+        d_obs = t(rows)
+        d_near = t(near_table(cap))
+        xy = torch.empty((cap, 2), dtype=torch.float64, device=dev)
+        cost = torch.empty((cap,), dtype=torch.float64, device=dev)
+        parent = torch.empty((cap,), dtype=torch.int32, device=dev)
+        path = torch.zeros((path_cap, 2), dtype=torch.float64, device=dev)
+        res = torch.zeros((C.sizeof(_lib.InformedTreeResult),), dtype=torch.uint8, device=dev)
+        nbytes = _lib.lib().rrtk_informed_tree_workspace_bytes(cap, int(grid))
+        if nbytes < 0:
+            _lib.check(int(nbytes), "rrtk_informed_tree_workspace_bytes")
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = _lib.lib().rrtk_informed_tree_run_dev(
+            C.byref(p), d_obs.data_ptr() if rows.shape[0] else None, d_near.data_ptr(), d_free.data_ptr(),
+            d_ball.data_ptr(), xy.data_ptr(), cost.data_ptr(), parent.data_ptr(), path.data_ptr(), res.data_ptr(),
+            ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_informed_tree_run_dev")
+        run = TreeRun(xy, cost, parent, path, res, max_iter)
+        run._keep = (d_free, d_ball, d_obs, d_near, ws)   # inputs stay alive until the kernel has run
+    return run
+
+
 class InformedRRTStar:
     """rrt_07's `RRT` (Informed RRT*), same constructor keywords and defaults (rrt_07:1029-1042)."""
 
