@@ -205,8 +205,12 @@ typedef struct rrtk_informed_tree_result {
     int32_t goal_events;  /* iterations whose new node connected to the goal */
     int32_t resamples;    /* iterations after which c_best changed (next sample and nearest redone) */
     int32_t grid;         /* CTAs used */
-    int64_t cycles[6];    /* SM clock cycles CTA 0 spent in each phase (new node, collision + cull, scan,
-                             candidates, grid reduce, append + rewire + goal); diagnostics for profiles/ */
+    int32_t reextends;    /* iterations whose new node was itself the nearest of the next sample */
+    int32_t pad_;
+    int64_t cycles[6];    /* SM clock cycles CTA 0 spent in each phase (cull, scan, candidate extension + hits,
+                             exchange, append + rewire, goal / redo); diagnostics for profiles/ */
+    int64_t cycles_max[6];    /* the same, maximum over the CTAs */
+    int64_t cycles_negmin[6]; /* minus the minimum over the CTAs */
 } rrtk_informed_tree_result;
 
 RRTK_API int64_t rrtk_informed_tree_workspace_bytes(int32_t node_cap, int32_t grid);
@@ -215,6 +219,11 @@ RRTK_API int rrtk_informed_tree_run_dev(const rrtk_informed_tree_params *p, cons
                                         const double *ball_draws, double *xy, double *cost, int32_t *parent,
                                         double *path, rrtk_informed_tree_result *result, void *workspace,
                                         int64_t workspace_bytes, void *stream);
+
+/* Diagnostic: the kernel's grid-wide exchange (one 128-byte record per CTA, all-to-all) run `iters` times on its
+ * own; cycles_per_exchange [grid] (device) gets each CTA's average SM cycles per exchange.  workspace as above. */
+RRTK_API int rrtk_tree_exchange_probe_dev(int32_t grid, int32_t iters, int64_t *cycles_per_exchange, void *workspace,
+                                          int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched Dubins steering: plan_dubins_path (rrt_05:1021-1109 == dub00) + the sampled collision test of

@@ -59,6 +59,7 @@ int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obsta
                          const double *free_s, const double *ball, double *xy, double *cost, int32_t *parent,
                          double *path, rrtk_informed_tree_result *res, void *workspace, size_t workspace_bytes,
                          cudaStream_t s);
+int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *workspace, size_t workspace_bytes, cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -197,6 +198,13 @@ int rrtk_informed_tree_run_dev(const rrtk_informed_tree_params *p, const double 
         return set_error(RRTK_ERR_INVALID, "xy, path and workspace must be 16-byte aligned");
     return launch_informed_tree(*p, obstacles, near_rr2, free_samples, ball_draws, xy, cost, parent, path, result,
                                 workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
+}
+
+int rrtk_tree_exchange_probe_dev(int32_t grid, int32_t iters, int64_t *cycles_per_exchange, void *workspace,
+                                 int64_t workspace_bytes, void *stream) {
+    if (grid < 0 || iters < 1 || !cycles_per_exchange || !workspace) return set_error(RRTK_ERR_INVALID, "bad arguments");
+    return launch_tree_exchange_probe(grid, iters, (long long *)cycles_per_exchange, workspace, (size_t)workspace_bytes,
+                                      (cudaStream_t)stream);
 }
 
 int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_size, const double *from3,

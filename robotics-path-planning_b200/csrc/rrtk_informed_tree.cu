@@ -7,21 +7,25 @@
 // Execution model: a persistent grid of G co-resident CTAs (cooperative launch, one per SM) runs the
 // iterations in lockstep.  Node i is OWNED by CTA (i / T) % G: only the owner scans it, evaluates it as a
 // near candidate and rewires it, so cost[] / parent[] of a node are read and written by one CTA only.
-// Per iteration there is ONE grid-wide reduction (a hand-rolled barrier over an L2 counter + one 32-byte
-// record per CTA), because the near scan for the new node of iteration `it` and the nearest scan for the
-// sample of iteration `it + 1` share one pass over the tree:
-//   A  warp 0: new node = nearest + expand_dis * (cos, sin)(atan2(..))  (exact, crmath.h);  warp 1: sample it+1
-//   B  CTA-wide: check_collision(nearest, theta, d) and the goal segment against all circles; obstacle cull
-//   C  scan of the owned nodes: d^2 to the new node (near hits -> shared-memory list) and to sample it+1 (argmin)
-//   D  owned hits: hypot, segment-vs-circle verdict, candidate cost  -> CTA partial (min cost, lowest index)
-//   E  grid barrier + reduce of the G partial records (nearest of it+1, best parent of it, flags)
-//   F  owner appends the node; every CTA rewires its own hits; goal bookkeeping (c_best, path snapshot)
-// The sample of it+1 depends on c_best; when c_best changes in F (rare) the speculative nearest is redone.
+// One iteration = one pass + one grid-wide exchange:
+//   cull   obstacles that can touch an edge into the new node                      (all threads)
+//   scan   owned nodes: d^2 to the new node of iteration `it` (near hits -> shared-memory list) and to the
+//          sample of iteration `it + 1` (argmin, lowest index)                       (all threads)
+//   cand   the CTA's nearest candidate for sample it+1 is extended SPECULATIVELY: exact atan2/cos/sin, new
+//          position, check_collision of that edge and of the goal segment          (one warp)
+//   hits   choose_parent candidates of the owned hits: hypot, segment verdict, cost (the other warps)
+//   xchg   every CTA publishes one 128-byte record of self-validating 16-byte pieces (value, index, tag) and
+//          polls the G records: nearest of it+1 WITH its already-extended node, best parent of it, flags.
+//          No counter, no second round trip: a piece is valid when its tag equals the exchange number.
+//   apply  owner appends the node; every CTA rewires its own hits; goal bookkeeping (c_best, path snapshot)
+// so the serial leaf math of iteration it+1 overlaps the candidate evaluation of iteration it.  The sample of
+// it+1 depends on c_best and the new node of `it` may itself be the nearest of it+1: both cases are detected
+// and redone exactly (a nearest-only pass, or a re-extension from the new node).
 //
 // Exactness (results equal the sequential reference bit for bit):
 //   * the `.index()` quirk of find_near_nodes maps a near node to the FIRST node with an equal d^2, so a node is
 //     "shadowed" (never a parent candidate, never rewired) iff a lower-index node has the same d^2 to the new
-//     node.  Identical positions are tracked with a per-node flag set at append time; equal d^2 between
+//     node.  Coincident nodes are flagged at append time (owner-local bitset) and skipped; equal d^2 between
 //     different positions is detected with an L2 hash set of the hits' d^2 bit patterns and then resolved
 //     exactly on a slow path (all-pairs over the global hit list);
 //   * choose_parent returns the first minimum of the near list = the lowest unshadowed index among the
@@ -39,32 +43,33 @@
 namespace rrtk {
 
 constexpr int TREE_T = 512;         // threads per CTA
-constexpr int TREE_HCAP = 2048;     // near hits per CTA kept in shared memory (the rest spills to the workspace)
+constexpr int TREE_NW = TREE_T / 32;
+constexpr int TREE_CAND_WARP = TREE_NW - 1;        // extends the speculative next node
+constexpr int TREE_HIT_THREADS = TREE_T - 32;      // evaluate the near hits meanwhile
+constexpr int TREE_HCAP = 1024;     // near hits per CTA kept in shared memory (the rest spills to the workspace)
 constexpr int TREE_OBS_CAP = 512;   // circles staged in shared memory
 constexpr int TREE_TAB_BITS = 18;   // hash set of d^2 bit patterns: 2 tables x 2^18 x 8 B
 constexpr unsigned long long TREE_EMPTY = ~0ull;
 constexpr int TREE_PROBES = 64;
+constexpr int TREE_REC_PIECES = 8;
+  // 128 bytes per record, 5 pieces used
 
 constexpr int FLAG_DUP_NEW = 1;     // the new node coincides with an existing node
 constexpr int FLAG_EQ_D2 = 2;       // two hits at different positions share d^2 (or the hash set is crowded)
+constexpr int CF_BLOCKED = 1;       // candidate flags: edge nearest -> new node hits a circle
+constexpr int CF_NEAR_GOAL = 2;     //                  new node within expand_dis of the goal
+constexpr int CF_GOAL_BLOCKED = 4;  //                  segment new node -> goal hits a circle
 constexpr int HIT_FREE = 1 << 30;   // bits or-ed into a hit's node index
 constexpr int HIT_SHADOW = 1 << 29;
 constexpr int HIT_MASK = HIT_SHADOW - 1;
-
-struct alignas(32) TreePartial {
-    double nn_d2;    // nearest of sample it+1 among the owned nodes
-    double cp_cost;  // best parent candidate among the owned hits
-    int nn_idx, cp_idx;
-    int flags, hits;
-};
+constexpr int NO_IDX = 0x7fffffff;
 
 struct TreeWs {  // carved out of the caller's workspace
-    unsigned long long *bar;
-    TreePartial *partial;       // [2][G]
+    unsigned long long *bar;    // counter barrier (rare paths)
+    uint4 *rec;                 // [2][G][TREE_REC_PIECES] exchange records
     unsigned long long *tab;    // [2][1 << TREE_TAB_BITS]
-    uint8_t *dup;               // [node_cap]
     int *sp_idx, *sp_slot;      // [G][seg_cap] spill of the hit lists
-    double *sp_d;               // [G][seg_cap]
+    double *sp_d, *sp_c;        // [G][seg_cap]
     int *g_idx;                 // [G][seg_cap] slow path: all hits (index, d^2)
     double *g_d2;
     int *g_cnt;                 // [G]
@@ -91,6 +96,21 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ uint4 ld_volatile16(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile16(uint4 *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 piece(double v, int i, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return make_uint4((unsigned)b, (unsigned)(b >> 32), (unsigned)i, tag);
+}
+__device__ __forceinline__ double piece_f64(uint4 p) {
+    return __longlong_as_double((long long)(((unsigned long long)p.y << 32) | p.x));
 }
 
 __device__ __forceinline__ double tdot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
@@ -137,101 +157,135 @@ __device__ __forceinline__ bool edge_free(double ax, double ay, double nx, doubl
 struct TreeSmem {
     double4 obs[TREE_OBS_CAP];
     int cull[TREE_OBS_CAP];
-    int hit_idx[TREE_HCAP];
+    int hit_tag[TREE_HCAP];
     int hit_slot[TREE_HCAP];
-    double hit_d[TREE_HCAP];
-    // block-reduce scratch
-    double r_d[2][TREE_T / 32];
-    int r_i[2][TREE_T / 32];
-    int r_f[TREE_T / 32];
-    int r_h[TREE_T / 32];
-    // broadcast state
-    double nx, ny, ex, ey, fx, fy, rx1, ry1, plen;
-    double g_nn_d2, g_cp_cost;
-    int g_nn_idx, g_cp_idx, g_flags, g_hits;
-    int nhit, ncull, near_goal;
+    double hit_x[TREE_HCAP], hit_y[TREE_HCAP], hit_d[TREE_HCAP], hit_c[TREE_HCAP];
+    // per-warp partials of the pass
+    double w_nd[TREE_NW], w_nx[TREE_NW], w_ny[TREE_NW], w_cc[TREE_NW];
+    int w_ni[TREE_NW], w_ci[TREE_NW], w_fl[TREE_NW], w_hs[TREE_NW];
+    // the CTA's candidate for the next sample
+    double c_d2, c_nx, c_ny;
+    int c_idx, c_cf;
+    // per-warp partials of the exchange
+    double q_nd[TREE_NW], q_nx[TREE_NW], q_ny[TREE_NW], q_cc[TREE_NW];
+    int q_ni[TREE_NW], q_cf[TREE_NW], q_ci[TREE_NW], q_fl[TREE_NW], q_hs[TREE_NW];
+    double s2x, s2y, s1x, s1y, plen;
+    int nhit, ncull;
+    unsigned dupbits[1];  // [seg_cap / 32] coincident-node flags of the owned nodes (dynamic tail)
+};
+
+struct Winner {   // result of one exchange, identical in every thread of every CTA
+    double nn_d2, nx, ny, cp_cost;
+    int nn_idx, cf, cp_idx, flags, hits;
 };
 
 __device__ __forceinline__ void lexmin(double &v, int &i, double ov, int oi) {
     if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
-// CTA-wide reduction of (nn: d2, idx), (cp: cost, idx), flags (or), hits (sum); result valid in warp 0 lane 0
-// and broadcast through shared memory by the caller.
-__device__ __forceinline__ void block_reduce(TreeSmem &S, double &nd, int &ni, double &cd, int &ci, int &fl, int &hs) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        lexmin(nd, ni, __shfl_xor_sync(0xffffffffu, nd, off), __shfl_xor_sync(0xffffffffu, ni, off));
-        lexmin(cd, ci, __shfl_xor_sync(0xffffffffu, cd, off), __shfl_xor_sync(0xffffffffu, ci, off));
-        fl |= __shfl_xor_sync(0xffffffffu, fl, off);
-        hs += __shfl_xor_sync(0xffffffffu, hs, off);
-    }
-    if (lane == 0) { S.r_d[0][w] = nd; S.r_i[0][w] = ni; S.r_d[1][w] = cd; S.r_i[1][w] = ci; S.r_f[w] = fl; S.r_h[w] = hs; }
+// counter barrier for the rare paths (goal walk, equal-d^2 resolution)
+__device__ __forceinline__ void grid_barrier(const TreeWs &ws, unsigned long long &bphase, int G) {
     __syncthreads();
-    if (w == 0) {
-        const bool in = lane < TREE_T / 32;
-        nd = in ? S.r_d[0][lane] : CUDART_INF; ni = in ? S.r_i[0][lane] : 0x7fffffff;
-        cd = in ? S.r_d[1][lane] : CUDART_INF; ci = in ? S.r_i[1][lane] : 0x7fffffff;
-        fl = in ? S.r_f[lane] : 0; hs = in ? S.r_h[lane] : 0;
-#pragma unroll
-        for (int off = 8; off >= 1; off >>= 1) {
-            lexmin(nd, ni, __shfl_xor_sync(0xffffffffu, nd, off), __shfl_xor_sync(0xffffffffu, ni, off));
-            lexmin(cd, ci, __shfl_xor_sync(0xffffffffu, cd, off), __shfl_xor_sync(0xffffffffu, ci, off));
-            fl |= __shfl_xor_sync(0xffffffffu, fl, off);
-            hs += __shfl_xor_sync(0xffffffffu, hs, off);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ws.bar, 1ull);
+        const unsigned long long target = (bphase + 1ull) * (unsigned long long)G;
+        while (ld_acquire(ws.bar) < target) { }
+    }
+    __syncthreads();
+    bphase++;
+}
+
+// warp-wide argmin of (non-negative double, int) with lowest-index ties, via integer redux: 3 REDUX + 2 compares
+// instead of 5 shuffle rounds (code size matters here).  Every lane gets the winning lane id.
+__device__ __forceinline__ int warp_argmin_lane(double v, int i) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);  // v >= 0 or +inf: bits are order-preserving
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool is_min = hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(0xffffffffu, is_min ? (unsigned)i : 0xffffffffu);
+    return __ffs(__ballot_sync(0xffffffffu, is_min && (unsigned)i == mi)) - 1;
+}
+
+// Grid-wide exchange.  In: the per-warp partials S.w_cc / w_ci / w_fl / w_hs and the candidate S.c_* (all written
+// before the caller's last __syncthreads).  Out: the combined result in every thread.
+// Each CTA stores one 64-byte record, then a release (MEMBAR + L2 counter increment); one thread per CTA polls the
+// counter; G threads read the records back and reduce.  Measured on B200 (tools/micro/sync_costs.cu): this counter
+// form costs ~2200 cycles at G = 148, an all-to-all poll of self-tagged records ~2000-4900 depending on the piece
+// count, and the latter collapses under the G^2 polling traffic once real work runs beside it.
+__device__ __noinline__ Winner exchange(TreeSmem &S, const TreeWs &ws, unsigned &seq, int G) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint4 *recs = ws.rec + (size_t)(seq & 1u) * G * TREE_REC_PIECES;
+    if (warp == 0) {
+        const bool in = lane < TREE_NW;
+        const double cc0 = in ? S.w_cc[lane] : CUDART_INF;
+        const int ci0 = in ? S.w_ci[lane] : NO_IDX;
+        const int src = warp_argmin_lane(cc0, ci0);
+        const double cc = __shfl_sync(0xffffffffu, cc0, src);
+        const int ci = __shfl_sync(0xffffffffu, ci0, src);
+        const int fl = (int)__reduce_or_sync(0xffffffffu, in ? (unsigned)S.w_fl[lane] : 0u);
+        const int hs = (int)__reduce_add_sync(0xffffffffu, in ? (unsigned)S.w_hs[lane] : 0u);
+        // lanes 0..3 store one 16-byte piece each (selected without branches)
+        const double pv = lane == 0 ? S.c_d2 : lane == 1 ? cc : lane == 2 ? S.c_nx : S.c_ny;
+        const int pi = lane == 0 ? S.c_idx : lane == 1 ? ci : lane == 2 ? S.c_cf : 0;
+        const int pt = lane == 0 ? fl : lane == 1 ? hs : 0;
+        if (lane < 4) __stcg(recs + (size_t)blockIdx.x * TREE_REC_PIECES + lane, piece(pv, pi, (unsigned)pt));
+        __syncwarp();
+        if (lane == 0) {
+            // release: the record and this CTA's tree writes (ordered before by __syncthreads) precede the count
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            atomicAdd(ws.bar + 8, 1ull);
+            const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
+            unsigned long long v;
+            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
         }
     }
-}
-
-// Grid-wide reduce: publish this CTA's partial, wait for all G, combine them; the result lands in S.g_*.
-// `phase` counts the barriers executed so far (identical in every CTA).
-__device__ __forceinline__ void grid_reduce(TreeSmem &S, const TreeWs &ws, unsigned long long &phase, int G,
-                                            double nd, int ni, double cd, int ci, int fl, int hs) {
-    block_reduce(S, nd, ni, cd, ci, fl, hs);
-    TreePartial *slot = ws.partial + (phase & 1ull) * G;
-    if (threadIdx.x == 0) {
-        double4 a; int4 b;
-        a.x = nd; a.y = cd; b.x = ni; b.y = ci; b.z = fl; b.w = hs;
-        double2 *dp = reinterpret_cast<double2 *>(slot + blockIdx.x);
-        __stcg(dp, make_double2(a.x, a.y));
-        __stcg(reinterpret_cast<int4 *>(dp + 1), b);
-        __threadfence();
-        atomicAdd(ws.bar, 1ull);
-        const unsigned long long target = (phase + 1ull) * (unsigned long long)G;
-        while (ld_acquire(ws.bar) < target) { }
+    __syncthreads();
+    double nd = CUDART_INF, nx = 0.0, ny = 0.0, cc = CUDART_INF;
+    int ni = NO_IDX, cf = 0, ci = NO_IDX, fl = 0, hs = 0;
+    if (tid < G) {   // L2 loads: the records were written before the counter reached its target
+        const uint4 *r = recs + (size_t)tid * TREE_REC_PIECES;
+        const uint4 p0 = __ldcg(r), p1 = __ldcg(r + 1), p2 = __ldcg(r + 2), p3 = __ldcg(r + 3);
+        nd = piece_f64(p0); ni = (int)p0.z; fl = (int)p0.w;
+        cc = piece_f64(p1); ci = (int)p1.z; hs = (int)p1.w;
+        nx = piece_f64(p2); cf = (int)p2.z;
+        ny = piece_f64(p3);
+    }
+    const int nwq = (G + 31) >> 5;
+    if (warp < nwq) {
+        const int sn = warp_argmin_lane(nd, ni), sc = warp_argmin_lane(cc, ci);
+        nd = __shfl_sync(0xffffffffu, nd, sn); ni = __shfl_sync(0xffffffffu, ni, sn);
+        nx = __shfl_sync(0xffffffffu, nx, sn); ny = __shfl_sync(0xffffffffu, ny, sn);
+        cf = __shfl_sync(0xffffffffu, cf, sn);
+        cc = __shfl_sync(0xffffffffu, cc, sc); ci = __shfl_sync(0xffffffffu, ci, sc);
+        fl = (int)__reduce_or_sync(0xffffffffu, (unsigned)fl);
+        hs = (int)__reduce_add_sync(0xffffffffu, (unsigned)hs);
+        if (lane == 0) {
+            S.q_nd[warp] = nd; S.q_ni[warp] = ni; S.q_nx[warp] = nx; S.q_ny[warp] = ny; S.q_cf[warp] = cf;
+            S.q_cc[warp] = cc; S.q_ci[warp] = ci; S.q_fl[warp] = fl; S.q_hs[warp] = hs;
+        }
     }
     __syncthreads();
-    nd = CUDART_INF; ni = 0x7fffffff; cd = CUDART_INF; ci = 0x7fffffff; fl = 0; hs = 0;
-    if ((int)threadIdx.x < G) {
-        const double2 *dp = reinterpret_cast<const double2 *>(slot + threadIdx.x);
-        const double2 a = __ldcg(dp);
-        const int4 b = __ldcg(reinterpret_cast<const int4 *>(dp + 1));
-        nd = a.x; cd = a.y; ni = b.x; ci = b.y; fl = b.z; hs = b.w;
+    Winner W;
+    W.nn_d2 = CUDART_INF; W.nn_idx = NO_IDX; W.nx = 0.0; W.ny = 0.0; W.cf = 0;
+    W.cp_cost = CUDART_INF; W.cp_idx = NO_IDX; W.flags = 0; W.hits = 0;
+    for (int w = 0; w < nwq; w++) {
+        const double ond = S.q_nd[w];
+        const int oni = S.q_ni[w];
+        if (ond < W.nn_d2 || (ond == W.nn_d2 && oni < W.nn_idx)) {
+            W.nn_d2 = ond; W.nn_idx = oni; W.nx = S.q_nx[w]; W.ny = S.q_ny[w]; W.cf = S.q_cf[w];
+        }
+        lexmin(W.cp_cost, W.cp_idx, S.q_cc[w], S.q_ci[w]);
+        W.flags |= S.q_fl[w];
+        W.hits += S.q_hs[w];
     }
-    block_reduce(S, nd, ni, cd, ci, fl, hs);
-    if (threadIdx.x == 0) {
-        S.g_nn_d2 = nd; S.g_nn_idx = ni; S.g_cp_cost = cd; S.g_cp_idx = ci; S.g_flags = fl; S.g_hits = hs;
-    }
-    __syncthreads();
-    phase++;
-}
-
-// plain grid barrier (makes the rewires of this iteration visible before the goal walk)
-__device__ __forceinline__ void grid_barrier(const TreeWs &ws, unsigned long long &phase, int G) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ws.bar, 1ull);
-        const unsigned long long target = (phase + 1ull) * (unsigned long long)G;
-        while (ld_acquire(ws.bar) < target) { }
-    }
-    __syncthreads();
-    phase++;
+    seq++;
+    return W;
 }
 
 // informed_sample (rrt_07:1145-1159) for iteration `it` given c_best
-__device__ __forceinline__ void draw_sample(const TreeArgs &A, int it, double c_best, double c_min, double xc, double yc,
+__device__ __noinline__ void draw_sample(const TreeArgs &A, int it, double c_best, double c_min, double xc, double yc,
                                             double &rx, double &ry) {
     if (c_best < CUDART_INF) {
         const double r0 = c_best / 2.0;
@@ -252,6 +306,28 @@ __device__ __forceinline__ void draw_sample(const TreeArgs &A, int it, double c_
     }
 }
 
+// One warp extends `from` towards the sample: get_new_node (rrt_07:1216-1224), line_cost, check_collision(nearest,
+// theta, d) (:1271-1276), is_near_goal (:1226-1230) and the goal segment test (:1096); lanes split the circles.
+__device__ __noinline__ void extend_candidate(const TreeSmem &S, int n_obs, double fx, double fy, double tx, double ty,
+                                              double ed, double gx, double gy, double &nx, double &ny, int &cf) {
+    const int lane = threadIdx.x & 31;
+    double st, ct;
+    (void)crm_atan2_sincos(ty - fy, tx - fx, &st, &ct);
+    nx = fx + ed * ct; ny = fy + ed * st;
+    const double d0 = crm_hypot(fx - nx, fy - ny);
+    const double ex = fx + ct * d0, ey = fy + st * d0;
+    const bool near_goal = crm_hypot(nx - gx, ny - gy) < ed;
+    bool he = false, hg = false;
+    for (int j = lane; j < n_obs; j += 32) {
+        const double4 o = S.obs[j];
+        he |= seg_dd(fx, fy, ex, ey, o.x, o.y) <= o.w;
+        if (near_goal) hg |= seg_dd(nx, ny, gx, gy, o.x, o.y) <= o.w;
+    }
+    he = __any_sync(0xffffffffu, he);
+    hg = __any_sync(0xffffffffu, hg);
+    cf = (he ? CF_BLOCKED : 0) | (near_goal ? CF_NEAR_GOAL : 0) | (hg ? CF_GOAL_BLOCKED : 0);
+}
+
 __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs A) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     TreeSmem &S = *reinterpret_cast<TreeSmem *>(smem_raw);
@@ -267,80 +343,68 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
     const long long seg = (long long)cta * ws.seg_cap;
 
     for (int j = tid; j < n_obs; j += TREE_T) S.obs[j] = A.obstacles[j];
+    for (int j = tid; j < (ws.seg_cap >> 5); j += TREE_T) S.dupbits[j] = 0u;
     if (cta == 0 && tid == 0) { A.xy[0] = make_double2(sx, sy); A.cost[0] = 0.0; A.parent[0] = -1; }
     __syncthreads();
 
-    unsigned long long phase = 0;
-    grid_barrier(ws, phase, G);  // node 0 visible everywhere
+    unsigned long long bphase = 0;
+    unsigned seq = 0;
+    grid_barrier(ws, bphase, G);  // node 0 visible everywhere
 
     int n = 1, status = RRTK_Q_OK, plen_best = 0, it = 0;
-    int ni = 0;                       // nearest node of the current sample
-    int last_new = -1;                // node appended in the previous iteration (its xy may not be visible yet)
-    double last_x = 0.0, last_y = 0.0;
     double c_best = INF;
     const double c_min = crm_hypot(sx - gx, sy - gy);
     const double xc = (sx + gx) / 2.0, yc = (sy + gy) / 2.0;
-    double rx = 0.0, ry = 0.0;
-    if (A.p.max_iter > 0) draw_sample(A, 0, c_best, c_min, xc, yc, rx, ry);
     long long total_hits = 0;
-    int n_slow = 0, n_goal = 0, n_redo = 0;
-    long long cyc[6] = {0, 0, 0, 0, 0, 0};  // CTA 0's clock per phase: A, B, C, D, E (barrier + reduce), F
+    int n_slow = 0, n_goal = 0, n_redo = 0, n_reext = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};  // CTA 0's clock per phase: cull, scan, cand + hits, exchange, apply, goal / redo
     long long t0 = clock64();
 #define TREE_TICK(k) do { long long t1 = clock64(); cyc[k] += t1 - t0; t0 = t1; } while (0)
 
-    for (; it < A.p.max_iter; it++) {
-        const bool have_next = it + 1 < A.p.max_iter;
-        // ---- A: new node (warp 0) and the speculative sample of it+1 (warp 1) ----
+    // current iteration: nearest index `ni`, its extended node (cur_x, cur_y) and flags; next sample (s1x, s1y)
+    int ni = 0, cur_cf = 0;
+    double cur_x = 0.0, cur_y = 0.0, s1x = 0.0, s1y = 0.0;
+    if (A.p.max_iter > 0) {
         if (warp == 0) {
-            double2 from;
-            if (ni == last_new) from = make_double2(last_x, last_y);
-            else from = ld_xy(A.xy + ni);
-            double st, ct;
-            (void)crm_atan2_sincos(ry - from.y, rx - from.x, &st, &ct);
-            const double nx = from.x + ed * ct, ny = from.y + ed * st;   // get_new_node (rrt_07:1216-1224)
-            const double d0 = crm_hypot(from.x - nx, from.y - ny);       // line_cost (:1205-1207)
-            const double dg = crm_hypot(nx - gx, ny - gy);               // is_near_goal (:1226-1230)
-            if (lane == 0) {
-                S.nx = nx; S.ny = ny; S.fx = from.x; S.fy = from.y;
-                S.ex = from.x + ct * d0; S.ey = from.y + st * d0;        // check_collision end point (:1273-1274)
-                S.near_goal = dg < ed;
-                S.nhit = 0; S.ncull = 0;
-            }
-        } else if (warp == 1) {
-            double a = 0.0, b = 0.0;
-            if (have_next) draw_sample(A, it + 1, c_best, c_min, xc, yc, a, b);
-            if (lane == 0) { S.rx1 = a; S.ry1 = b; }
+            double rx, ry, nx, ny;
+            int cf;
+            draw_sample(A, 0, c_best, c_min, xc, yc, rx, ry);
+            extend_candidate(S, n_obs, sx, sy, rx, ry, ed, gx, gy, nx, ny, cf);
+            if (lane == 0) { S.c_nx = nx; S.c_ny = ny; S.c_cf = cf; }
+        } else if (warp == 1 && A.p.max_iter > 1) {
+            double a, b;
+            draw_sample(A, 1, c_best, c_min, xc, yc, a, b);
+            if (lane == 0) { S.s1x = a; S.s1y = b; }
         }
         __syncthreads();
-        TREE_TICK(0);
-        const double nx = S.nx, ny = S.ny;
-        double rx1 = S.rx1, ry1 = S.ry1;
-        const bool near_goal = S.near_goal != 0;
-        const double2 rr2 = __ldg(A.near_rr2 + n);  // (r, r ** 2) for n_node = n (rrt_07:1138-1139)
+        cur_x = S.c_nx; cur_y = S.c_ny; cur_cf = S.c_cf; s1x = S.s1x; s1y = S.s1y;
+    }
 
-        // ---- B: check_collision(nearest, theta, d), goal segment, obstacle cull around the new node ----
-        int hit_edge = 0, hit_goal = 0;
-        for (int j = tid; j < n_obs; j += TREE_T) {
-            const double4 o = S.obs[j];
-            hit_edge |= seg_dd(S.fx, S.fy, S.ex, S.ey, o.x, o.y) <= o.w;
-            if (near_goal) hit_goal |= seg_dd(nx, ny, gx, gy, o.x, o.y) <= o.w;
-            const double dx = o.x - nx, dy = o.y - ny;
-            const double lim = (rr2.x + o.z) * (1.0 + 1e-9) + 1e-9;
-            if (dx * dx + dy * dy <= lim * lim) S.cull[atomicAdd(&S.ncull, 1)] = j;
+    // One pass over the owned nodes + exchange.  r2 < 0: nearest only.  Leaves the hit list in shared memory.
+    auto pass = [&](double nx, double ny, double r, double r2, bool want_nn, double tx, double ty, int draw_it, int &H,
+                    int &ncull_out) -> Winner {
+        if (tid == 0) { S.nhit = 0; S.ncull = 0; }
+        __syncthreads();
+        if (r2 >= 0.0) {
+            for (int j = tid; j < n_obs; j += TREE_T) {
+                const double4 o = S.obs[j];
+                const double dx = o.x - nx, dy = o.y - ny;
+                const double lim = (r + o.z) * (1.0 + 1e-9) + 1e-9;
+                if (dx * dx + dy * dy <= lim * lim) S.cull[atomicAdd(&S.ncull, 1)] = j;
+            }
         }
-        const int blocked = __syncthreads_or(hit_edge | (hit_goal << 1));
-        const bool accept = !(blocked & 1);
-        const bool goal_event = accept && near_goal && !(blocked & 2);
-        const int ncull = S.ncull;
-        TREE_TICK(1);
-        if (accept && n >= A.p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
-
-        // ---- C: one pass over the owned nodes: near hits of the new node, nearest of sample it+1 ----
-        const double r2 = accept ? rr2.y : -1.0;
-        double bd = INF;
-        int bi = 0x7fffffff;
-        if (accept || have_next) {
-            for (long long base = (long long)cta * TREE_T + tid; base < n; base += 4 * stride) {
+        if (warp == 1 && draw_it >= 0) {  // the sample after next, while the others scan
+            double a, b;
+            draw_sample(A, draw_it, c_best, c_min, xc, yc, a, b);
+            if (lane == 0) { S.s2x = a; S.s2y = b; }
+        }
+        TREE_TICK(0);
+        // ---- scan ----
+        double bd = INF, bx = 0.0, by = 0.0;
+        int bi = NO_IDX, myhits = 0;
+        if (r2 >= 0.0 || want_nn) {
+            int chunk = 0;
+            for (long long base = (long long)cta * TREE_T + tid; base < n; base += 4 * stride, chunk += 4) {
                 double2 a[4];
                 bool ok[4];
 #pragma unroll
@@ -355,92 +419,139 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
                     const int i = (int)(base + u * stride);
                     const double ax = a[u].x - nx, ay = a[u].y - ny;
                     if (ax * ax + ay * ay <= r2) {
-                        const int pos = atomicAdd(&S.nhit, 1);
-                        if (pos < TREE_HCAP) S.hit_idx[pos] = i;
-                        else __stcg(ws.sp_idx + seg + (pos - TREE_HCAP), i);
+                        myhits++;
+                        const int li = (chunk + u) * TREE_T + tid;
+                        if (!((S.dupbits[li >> 5] >> (li & 31)) & 1u)) {   // coincident twins are shadowed: skip
+                            const int pos = atomicAdd(&S.nhit, 1);
+                            if (pos < TREE_HCAP) { S.hit_tag[pos] = i; S.hit_x[pos] = a[u].x; S.hit_y[pos] = a[u].y; }
+                            else __stcg(ws.sp_idx + seg + (pos - TREE_HCAP), i);
+                        }
                     }
-                    const double bx = a[u].x - rx1, by = a[u].y - ry1;
-                    const double e2 = bx * bx + by * by;
-                    if (e2 < bd) { bd = e2; bi = i; }
+                    const double ex = a[u].x - tx, ey = a[u].y - ty;
+                    const double e2 = ex * ex + ey * ey;
+                    if (e2 < bd) { bd = e2; bi = i; bx = a[u].x; by = a[u].y; }
                 }
             }
         }
+        {
+            const int src = warp_argmin_lane(bd, bi);
+            bd = __shfl_sync(0xffffffffu, bd, src); bi = __shfl_sync(0xffffffffu, bi, src);
+            bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src);
+        }
+        if (lane == 0) { S.w_nd[warp] = bd; S.w_ni[warp] = bi; S.w_nx[warp] = bx; S.w_ny[warp] = by; }
         __syncthreads();
-        const int H = S.nhit;
-        TREE_TICK(2);
-
-        // ---- D: choose_parent candidates among the owned hits (rrt_07:1110-1135) ----
+        TREE_TICK(1);
+        H = S.nhit;
+        const int ncull = S.ncull;
+        ncull_out = ncull;
         double cc = INF;
-        int ci = 0x7fffffff, flags = 0;
-        unsigned long long *tab = ws.tab + ((unsigned long long)(it & 1) << TREE_TAB_BITS);
-        for (int e = tid; e < H; e += TREE_T) {
-            const int i = e < TREE_HCAP ? S.hit_idx[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
-            int tag = i, slot = -1;
-            double d = 0.0;
-            if (__ldcg(ws.dup + i)) {
-                tag |= HIT_SHADOW;
-            } else {
-                const double2 a = ld_xy(A.xy + i);
-                const double ax = a.x - nx, ay = a.y - ny;
-                const double d2 = ax * ax + ay * ay;
-                if (d2 == 0.0) flags |= FLAG_DUP_NEW;
+        int ci = NO_IDX, flags = 0;
+        if (warp == TREE_CAND_WARP) {
+            // ---- cand: extend the CTA's nearest candidate for the next sample ----
+            bd = lane < TREE_NW ? S.w_nd[lane] : INF; bi = lane < TREE_NW ? S.w_ni[lane] : NO_IDX;
+            bx = lane < TREE_NW ? S.w_nx[lane] : 0.0; by = lane < TREE_NW ? S.w_ny[lane] : 0.0;
+            {
+                const int src = warp_argmin_lane(bd, bi);
+                bd = __shfl_sync(0xffffffffu, bd, src); bi = __shfl_sync(0xffffffffu, bi, src);
+                bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src);
+            }
+            double cx = 0.0, cy = 0.0;
+            int cf = 0;
+            if (want_nn && bi != NO_IDX) extend_candidate(S, n_obs, bx, by, tx, ty, ed, gx, gy, cx, cy, cf);
+            if (lane == 0) { S.c_d2 = want_nn ? bd : INF; S.c_idx = want_nn ? bi : NO_IDX; S.c_nx = cx; S.c_ny = cy; S.c_cf = cf; }
+        } else {
+            // ---- hits: choose_parent candidates among the owned hits (rrt_07:1110-1135) ----
+            unsigned long long *tab = ws.tab + ((unsigned long long)(it & 1) << TREE_TAB_BITS);
+            for (int e = tid; e < H; e += TREE_HIT_THREADS) {
+                const bool in_s = e < TREE_HCAP;
+                int i;
+                double ax, ay;
+                if (in_s) { i = S.hit_tag[e]; ax = S.hit_x[e]; ay = S.hit_y[e]; }
+                else { i = ld_i32(ws.sp_idx + seg + (e - TREE_HCAP)); const double2 a = ld_xy(A.xy + i); ax = a.x; ay = a.y; }
+                const double c_i = ld_f64(A.cost + i);
+                const double qx = ax - nx, qy = ay - ny;
+                const double d2 = qx * qx + qy * qy;
                 // hash set of d^2 bit patterns: a repeated key means two different positions at equal d^2
                 const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
                 unsigned h = (unsigned)(splitmix64(key) >> (64 - TREE_TAB_BITS));
-                int probe = 0;
-                for (; probe < TREE_PROBES; probe++) {
-                    const unsigned long long old = atomicCAS(tab + h, TREE_EMPTY, key);
+                unsigned long long old = atomicCAS(tab + h, TREE_EMPTY, key);
+                const double d = crm_hypot(nx - ax, ny - ay);
+                const bool free_e = edge_free(ax, ay, nx, ny, d, band_k, S.obs, S.cull, ncull);
+                int slot = -1, tag = i;
+                if (d2 == 0.0) flags |= FLAG_DUP_NEW;
+                for (int probe = 0;; probe++) {
                     if (old == TREE_EMPTY) { slot = (int)h; break; }
-                    if (old == key) { flags |= FLAG_EQ_D2; break; }
+                    if (old == key || probe == TREE_PROBES) { flags |= FLAG_EQ_D2; break; }
                     h = (h + 1) & ((1u << TREE_TAB_BITS) - 1u);
+                    old = atomicCAS(tab + h, TREE_EMPTY, key);
                 }
-                if (probe == TREE_PROBES) flags |= FLAG_EQ_D2;
-                d = crm_hypot(nx - a.x, ny - a.y);
-                if (edge_free(a.x, a.y, nx, ny, d, band_k, S.obs, S.cull, ncull)) {
-                    tag |= HIT_FREE;
-                    lexmin(cc, ci, ld_f64(A.cost + i) + d, i);
+                if (free_e) { tag |= HIT_FREE; lexmin(cc, ci, c_i + d, i); }
+                if (in_s) { S.hit_tag[e] = tag; S.hit_slot[e] = slot; S.hit_d[e] = d; S.hit_c[e] = c_i; }
+                else {
+                    __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
+                    __stcg(ws.sp_slot + seg + (e - TREE_HCAP), slot);
+                    __stcg(ws.sp_d + seg + (e - TREE_HCAP), d);
+                    __stcg(ws.sp_c + seg + (e - TREE_HCAP), c_i);
                 }
-            }
-            if (e < TREE_HCAP) { S.hit_idx[e] = tag; S.hit_slot[e] = slot; S.hit_d[e] = d; }
-            else {
-                __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
-                __stcg(ws.sp_slot + seg + (e - TREE_HCAP), slot);
-                __stcg(ws.sp_d + seg + (e - TREE_HCAP), d);
             }
         }
-
-        // ---- E: grid-wide reduce ----
+        {
+            const int src = warp_argmin_lane(cc, ci);
+            cc = __shfl_sync(0xffffffffu, cc, src); ci = __shfl_sync(0xffffffffu, ci, src);
+            flags = (int)__reduce_or_sync(0xffffffffu, (unsigned)flags);
+            myhits = (int)__reduce_add_sync(0xffffffffu, (unsigned)myhits);
+        }
+        if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = flags; S.w_hs[warp] = myhits; }
         __syncthreads();
+        TREE_TICK(2);
+        const Winner W = exchange(S, ws, seq, G);
         TREE_TICK(3);
-        grid_reduce(S, ws, phase, G, bd, bi, cc, ci, flags, tid == 0 ? H : 0);
-        TREE_TICK(4);
-        flags = S.g_flags;
-        total_hits += S.g_hits;
-        int nn1 = S.g_nn_idx;
-        const double nn1_d2 = S.g_nn_d2;
+        return W;
+    };
 
-        if (!accept) {  // collision: nothing is added (rrt_07:1080-1082)
-            if (have_next) { ni = nn1; rx = rx1; ry = ry1; }
+    // `redo`: the pass is a nearest-only repeat for iteration it+1 after c_best changed (one call site keeps the
+    // hot code small: the kernel is instruction-fetch sensitive, L1.5 I-cache = 32 KB)
+    bool redo = false;
+    while (redo || it < A.p.max_iter) {
+        const bool have1 = it + 1 < A.p.max_iter, have2 = it + 2 < A.p.max_iter;
+        const bool accept = !redo && !(cur_cf & CF_BLOCKED);
+        const bool goal_event = accept && (cur_cf & CF_NEAR_GOAL) && !(cur_cf & CF_GOAL_BLOCKED);
+        if (accept && n >= A.p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
+        const double nx = cur_x, ny = cur_y;
+        const double2 rr2 = __ldg(A.near_rr2 + n);  // (r, r ** 2) for n_node = n (rrt_07:1138-1139)
+        int H = 0, ncull = 0;
+        Winner W = pass(nx, ny, rr2.x, accept ? rr2.y : -1.0, redo || have1, s1x, s1y, have2 ? it + 2 : -1, H, ncull);
+        const double s2x = S.s2x, s2y = S.s2y;
+        total_hits += W.hits;
+
+        if (!accept) {  // collision: nothing is added (rrt_07:1080-1082); or the nearest-only repeat
+            ni = W.nn_idx; cur_x = W.nx; cur_y = W.ny; cur_cf = W.cf;
+            s1x = s2x; s1y = s2y;
+            redo = false;
+            it++;
             continue;
         }
-        struct Tick { long long *c, *t; __device__ ~Tick() { long long t1 = clock64(); c[5] += t1 - *t; *t = t1; } } tickF{cyc, &t0};
+        const int flags = W.flags;
 
         // ---- slow path: equal d^2 at different positions -> exact shadow flags from the global hit list ----
         if (flags & FLAG_EQ_D2) {
             n_slow++;
             for (int e = tid; e < H; e += TREE_T) {
-                const int tag = e < TREE_HCAP ? S.hit_idx[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
-                const int i = tag & HIT_MASK;
-                const double2 a = ld_xy(A.xy + i);
-                const double ax = a.x - nx, ay = a.y - ny;
+                const bool in_s = e < TREE_HCAP;
+                const int i = (in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP))) & HIT_MASK;
+                double ax, ay;
+                if (in_s) { ax = S.hit_x[e]; ay = S.hit_y[e]; } else { const double2 a = ld_xy(A.xy + i); ax = a.x; ay = a.y; }
+                const double qx = ax - nx, qy = ay - ny;
                 __stcg(ws.g_idx + seg + e, i);
-                __stcg(ws.g_d2 + seg + e, ax * ax + ay * ay);
+                __stcg(ws.g_d2 + seg + e, qx * qx + qy * qy);
             }
             if (tid == 0) __stcg(ws.g_cnt + cta, H);
-            grid_barrier(ws, phase, G);
-            cc = INF; ci = 0x7fffffff;
+            grid_barrier(ws, bphase, G);
+            double cc = INF;
+            int ci = NO_IDX;
             for (int e = tid; e < H; e += TREE_T) {
-                int tag = e < TREE_HCAP ? S.hit_idx[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
+                const bool in_s = e < TREE_HCAP;
+                int tag = in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
                 const int i = tag & HIT_MASK;
                 const double d2 = ld_f64(ws.g_d2 + seg + e);
                 bool shadow = false;
@@ -451,49 +562,66 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
                         if (ld_i32(ws.g_idx + s2 + k) < i && ld_f64(ws.g_d2 + s2 + k) == d2) { shadow = true; break; }
                 }
                 if (shadow) tag |= HIT_SHADOW;
-                if (e < TREE_HCAP) S.hit_idx[e] = tag; else __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
+                if (in_s) S.hit_tag[e] = tag; else __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
                 if (!(tag & HIT_SHADOW) && (tag & HIT_FREE)) {
-                    const double d = e < TREE_HCAP ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP));
-                    lexmin(cc, ci, ld_f64(A.cost + i) + d, i);
+                    const double d = in_s ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP));
+                    const double c_i = in_s ? S.hit_c[e] : ld_f64(ws.sp_c + seg + (e - TREE_HCAP));
+                    lexmin(cc, ci, c_i + d, i);
                 }
             }
-            grid_reduce(S, ws, phase, G, INF, 0x7fffffff, cc, ci, 0, 0);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1)
+                lexmin(cc, ci, __shfl_xor_sync(0xffffffffu, cc, off), __shfl_xor_sync(0xffffffffu, ci, off));
+            if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = 0; S.w_hs[warp] = 0; }
+            if (tid == 0) { S.c_d2 = INF; S.c_idx = NO_IDX; S.c_nx = 0.0; S.c_ny = 0.0; S.c_cf = 0; }
+            __syncthreads();
+            const Winner W2 = exchange(S, ws, seq, G);
+            W.cp_cost = W2.cp_cost; W.cp_idx = W2.cp_idx;
         }
 
-        // ---- F: parent choice, append, rewire (rrt_07:1232-1246) ----
+        // ---- apply: parent choice, append, rewire (rrt_07:1232-1246) ----
         double ncost;
         int npar;
-        if (S.g_cp_idx != 0x7fffffff) { ncost = S.g_cp_cost; npar = S.g_cp_idx; }
+        if (W.cp_idx != NO_IDX) { ncost = W.cp_cost; npar = W.cp_idx; }
         else { ncost = ld_f64(A.cost + ni) + ed; npar = ni; }
         const int newi = n;
         if (cta == (newi / TREE_T) % G && tid == 0) {
             __stcg(A.xy + newi, make_double2(nx, ny));
             __stcg(A.cost + newi, ncost);
             __stcg(A.parent + newi, npar);
-            __stcg(ws.dup + newi, (uint8_t)((flags & FLAG_DUP_NEW) ? 1 : 0));
+            if (flags & FLAG_DUP_NEW) {
+                const int li = (int)(newi / stride) * TREE_T + newi % TREE_T;
+                S.dupbits[li >> 5] |= 1u << (li & 31);
+            }
         }
-        for (int e = tid; e < H; e += TREE_T) {
-            const bool in_s = e < TREE_HCAP;
-            const int tag = in_s ? S.hit_idx[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
-            const int slot = in_s ? S.hit_slot[e] : ld_i32(ws.sp_slot + seg + (e - TREE_HCAP));
-            if (slot >= 0) tab[slot] = TREE_EMPTY;
-            if ((tag & HIT_SHADOW) || !(tag & HIT_FREE)) continue;
-            const int i = tag & HIT_MASK;
-            const double sc = ncost + (in_s ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP)));
-            if (ld_f64(A.cost + i) > sc) { __stcg(A.parent + i, newi); __stcg(A.cost + i, sc); }
+        {
+            unsigned long long *tab = ws.tab + ((unsigned long long)(it & 1) << TREE_TAB_BITS);
+            for (int e = tid; e < H; e += TREE_T) {
+                const bool in_s = e < TREE_HCAP;
+                const int tag = in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
+                const int slot = in_s ? S.hit_slot[e] : ld_i32(ws.sp_slot + seg + (e - TREE_HCAP));
+                if (slot >= 0) tab[slot] = TREE_EMPTY;
+                if ((tag & HIT_SHADOW) || !(tag & HIT_FREE)) continue;
+                const int i = tag & HIT_MASK;
+                const double sc = ncost + (in_s ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP)));
+                const double c_i = in_s ? S.hit_c[e] : ld_f64(ws.sp_c + seg + (e - TREE_HCAP));
+                if (c_i > sc) { __stcg(A.parent + i, newi); __stcg(A.cost + i, sc); }
+            }
         }
         n++;
-        last_new = newi; last_x = nx; last_y = ny;
-        if (have_next) {  // the new node joins the nearest candidates of sample it+1 (highest index: loses ties)
-            const double bx = nx - rx1, by = ny - ry1;
-            if (bx * bx + by * by < nn1_d2) nn1 = newi;
+        // the new node joins the nearest candidates of sample it+1 (highest index: it loses ties)
+        bool reextend = false;
+        if (have1) {
+            const double bx = nx - s1x, by = ny - s1y;
+            reextend = bx * bx + by * by < W.nn_d2;
         }
+        TREE_TICK(4);
 
         // ---- goal bookkeeping (rrt_07:1094-1103) ----
         bool c_changed = false;
         if (goal_event) {
             n_goal++;
-            grid_barrier(ws, phase, G);  // this iteration's rewires are now visible
+            grid_barrier(ws, bphase, G);  // this iteration's rewires are now visible
             if (tid == 0) {
                 double plen = 0.0, qx = gx, qy = gy;
                 int k = newi;
@@ -532,37 +660,77 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
             __syncthreads();
         }
 
-        if (!have_next) continue;
-        if (c_changed) {  // sample it+1 depends on c_best: redo its nearest search over the whole tree
+        if (have1 && c_changed) {  // samples it+1, it+2 depend on c_best: redraw, redo the nearest search (incl. new node)
             n_redo++;
             if (warp == 0) {
                 double a, b;
                 draw_sample(A, it + 1, c_best, c_min, xc, yc, a, b);
-                if (lane == 0) { S.rx1 = a; S.ry1 = b; }
+                if (lane == 0) { S.s1x = a; S.s1y = b; }
             }
             __syncthreads();
-            rx1 = S.rx1; ry1 = S.ry1;
-            bd = INF; bi = 0x7fffffff;
-            for (long long i = (long long)cta * TREE_T + tid; i < n; i += stride) {
-                const double2 a = ld_xy(A.xy + i);
-                const double bx = a.x - rx1, by = a.y - ry1;
-                const double e2 = bx * bx + by * by;
-                if (e2 < bd) { bd = e2; bi = (int)i; }
-            }
-            grid_reduce(S, ws, phase, G, bd, bi, INF, 0x7fffffff, 0, 0);
-            nn1 = S.g_nn_idx;
+            s1x = S.s1x; s1y = S.s1y;
+            redo = true;
+            TREE_TICK(5);
+            continue;
         }
-        ni = nn1; rx = rx1; ry = ry1;
+        if (have1) {
+            if (reextend) {  // the node just appended is the nearest of sample it+1: extend from it
+                n_reext++;
+                if (warp == 0) {
+                    double cx, cy;
+                    int cf;
+                    extend_candidate(S, n_obs, nx, ny, s1x, s1y, ed, gx, gy, cx, cy, cf);
+                    if (lane == 0) { S.c_nx = cx; S.c_ny = cy; S.c_cf = cf; }
+                }
+                __syncthreads();
+                ni = newi; cur_x = S.c_nx; cur_y = S.c_ny; cur_cf = S.c_cf;
+            } else {
+                ni = W.nn_idx; cur_x = W.nx; cur_y = W.ny; cur_cf = W.cf;
+            }
+            s1x = s2x; s1y = s2y;
+        }
+        it++;
+        TREE_TICK(5);
     }
 
+    if (tid == 0) {   // per-phase clocks: CTA 0's own, plus max / min over the CTAs (result struct is zeroed by the launcher)
+        for (int k = 0; k < 6; k++) {
+            atomicMax((long long *)&A.res->cycles_max[k], cyc[k]);
+            atomicMax((long long *)&A.res->cycles_negmin[k], -cyc[k]);
+        }
+    }
     if (cta == 0 && tid == 0) {
         rrtk_informed_tree_result r;
         r.n_nodes = n; r.path_len = plen_best; r.status = status | (plen_best > A.p.path_cap ? RRTK_Q_PATH_OVERFLOW : 0);
         r.iters_done = it; r.c_best = c_best; r.total_hits = total_hits; r.slow_paths = n_slow;
-        r.goal_events = n_goal; r.resamples = n_redo; r.grid = G;
-        for (int k = 0; k < 6; k++) r.cycles[k] = cyc[k];
-        *A.res = r;
+        r.goal_events = n_goal; r.resamples = n_redo; r.grid = G; r.reextends = n_reext; r.pad_ = 0;
+        A.res->n_nodes = r.n_nodes; A.res->path_len = r.path_len; A.res->status = r.status; A.res->iters_done = r.iters_done;
+        A.res->c_best = r.c_best; A.res->total_hits = r.total_hits; A.res->slow_paths = r.slow_paths;
+        A.res->goal_events = r.goal_events; A.res->resamples = r.resamples; A.res->grid = r.grid;
+        A.res->reextends = r.reextends; A.res->pad_ = 0;
+        for (int k = 0; k < 6; k++) A.res->cycles[k] = cyc[k];
     }
+}
+
+
+// Diagnostic: the grid-wide exchange alone, `iters` times on a co-resident grid; out[cta] = cycles per exchange.
+__global__ void __launch_bounds__(TREE_T, 1) tree_exchange_probe_kernel(TreeWs ws, int iters, long long *out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    TreeSmem &S = *reinterpret_cast<TreeSmem *>(smem_raw);
+    const int tid = threadIdx.x, G = gridDim.x;
+    if (tid < TREE_NW) { S.w_cc[tid] = 1.0 + tid; S.w_ci[tid] = tid; S.w_fl[tid] = 0; S.w_hs[tid] = 1; }
+    if (tid == 0) { S.c_d2 = 1.0 + blockIdx.x; S.c_idx = blockIdx.x; S.c_nx = 0.5; S.c_ny = 0.25; S.c_cf = 0; }
+    __syncthreads();
+    unsigned seq = 0;
+    double acc = 0.0;
+    const long long t0 = clock64();
+    for (int k = 0; k < iters; k++) {
+        const Winner W = exchange(S, ws, seq, G);
+        acc += W.nn_d2 + W.hits;
+        __syncthreads();
+    }
+    const long long t1 = clock64();
+    if (tid == 0) out[blockIdx.x] = (t1 - t0) / (iters > 0 ? iters : 1) + (acc < 0.0 ? 1 : 0);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -574,12 +742,12 @@ static size_t carve(TreeWs &ws, char *base, int node_cap, int G) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
     ws.bar = (unsigned long long *)take(256);
-    ws.partial = (TreePartial *)take(sizeof(TreePartial) * 2 * G);
+    ws.rec = (uint4 *)take(sizeof(uint4) * 2 * TREE_REC_PIECES * G);
     ws.tab = (unsigned long long *)take(sizeof(unsigned long long) * 2 * (1ull << TREE_TAB_BITS));
-    ws.dup = (uint8_t *)take((size_t)node_cap);
     ws.sp_idx = (int *)take(sizeof(int) * (size_t)G * seg_cap);
     ws.sp_slot = (int *)take(sizeof(int) * (size_t)G * seg_cap);
     ws.sp_d = (double *)take(sizeof(double) * (size_t)G * seg_cap);
+    ws.sp_c = (double *)take(sizeof(double) * (size_t)G * seg_cap);
     ws.g_idx = (int *)take(sizeof(int) * (size_t)G * seg_cap);
     ws.g_d2 = (double *)take(sizeof(double) * (size_t)G * seg_cap);
     ws.g_cnt = (int *)take(sizeof(int) * G);
@@ -587,16 +755,14 @@ static size_t carve(TreeWs &ws, char *base, int node_cap, int G) {
     return off;
 }
 
+static size_t tree_smem_bytes(int seg_cap) { return sizeof(TreeSmem) + sizeof(unsigned) * (size_t)(seg_cap / 32 + 1); }
+
 static int tree_grid(int want, int *grid_out) {
-    int dev = 0, sms = 0, per_sm = 0;
+    int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDevice");
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaFuncSetAttribute(informed_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem));
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(smem)");
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, informed_tree_kernel, TREE_T, sizeof(TreeSmem));
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (per_sm < 1) return set_error(RRTK_ERR_CUDA, "informed_tree_kernel does not fit on an SM");
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute");
     int g = sms;  // one CTA per SM
     if (want > 0 && want < g) g = want;
     if (g > TREE_T) g = TREE_T;
@@ -632,13 +798,39 @@ int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obsta
     A.res = res;
     const size_t need = carve(A.ws, (char *)workspace, p.node_cap, G);
     if (need > workspace_bytes) return set_error(RRTK_ERR_INVALID, "workspace too small (rrtk_informed_tree_workspace_bytes)");
-    cudaError_t e = cudaMemsetAsync(A.ws.bar, 0, 256, s);
+    const size_t smem = tree_smem_bytes(A.ws.seg_cap);
+    int per_sm = 0;
+    cudaError_t e = cudaFuncSetAttribute(informed_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(smem): node_cap too large for the owner-local flags");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, informed_tree_kernel, TREE_T, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) return set_error(RRTK_ERR_CUDA, "informed_tree_kernel does not fit on an SM");
+    e = cudaMemsetAsync(res, 0, sizeof(*res), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.bar, 0, 256, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.rec, 0, sizeof(uint4) * 2 * TREE_REC_PIECES * G, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.tab, 0xff, sizeof(unsigned long long) * 2 * (1ull << TREE_TAB_BITS), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.dup, 0, (size_t)p.node_cap, s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(workspace)");
     void *args[] = {(void *)&A};
-    e = cudaLaunchCooperativeKernel((const void *)informed_tree_kernel, dim3(G), dim3(TREE_T), args, sizeof(TreeSmem), s);
+    e = cudaLaunchCooperativeKernel((const void *)informed_tree_kernel, dim3(G), dim3(TREE_T), args, smem, s);
     if (e != cudaSuccess) return set_cuda_error(e, "informed_tree_kernel cooperative launch");
+    return RRTK_OK;
+}
+
+int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+    int G = 0;
+    int rc = tree_grid(grid, &G);
+    if (rc) return rc;
+    TreeWs ws;
+    const size_t need = carve(ws, (char *)workspace, TREE_T, G);
+    if (need > workspace_bytes) return set_error(RRTK_ERR_INVALID, "workspace too small");
+    const size_t smem = tree_smem_bytes(ws.seg_cap);
+    cudaError_t e = cudaFuncSetAttribute(tree_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.bar, 0, 256, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.rec, 0, sizeof(uint4) * 2 * TREE_REC_PIECES * G, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "tree_exchange_probe setup");
+    void *args[] = {(void *)&ws, (void *)&iters, (void *)&out_dev};
+    e = cudaLaunchCooperativeKernel((const void *)tree_exchange_probe_kernel, dim3(G), dim3(TREE_T), args, smem, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "tree_exchange_probe_kernel launch");
     return RRTK_OK;
 }
 

@@ -46,7 +46,8 @@ class InformedTreeResult(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("path_len", C.c_int32), ("status", C.c_int32), ("iters_done", C.c_int32),
                 ("c_best", C.c_double), ("total_hits", C.c_int64), ("slow_paths", C.c_int32),
                 ("goal_events", C.c_int32), ("resamples", C.c_int32), ("grid", C.c_int32),
-                ("cycles", C.c_int64 * 6)]
+                ("reextends", C.c_int32), ("pad_", C.c_int32), ("cycles", C.c_int64 * 6),
+                ("cycles_max", C.c_int64 * 6), ("cycles_negmin", C.c_int64 * 6)]
 
 
 class DubinsParams(C.Structure):
@@ -72,6 +73,7 @@ _SIGS = {
     "rrtk_informed_run_dev": (C.c_int, [C.POINTER(InformedParams)] + [_VP] * 18),
     "rrtk_informed_tree_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "rrtk_informed_tree_run_dev": (C.c_int, [C.POINTER(InformedTreeParams)] + [_VP] * 10 + [C.c_int64, _VP]),
+    "rrtk_tree_exchange_probe_dev": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, C.c_int64, _VP]),
     "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

@@ -126,7 +126,8 @@ class TreeRun:
             raw = bytes(self._res.cpu().numpy().tobytes())
             r = _lib.InformedTreeResult.from_buffer_copy(raw)
             self._info = {k: getattr(r, k) for k, _ in _lib.InformedTreeResult._fields_}
-            self._info["cycles"] = list(self._info["cycles"])
+            for k in ("cycles", "cycles_max", "cycles_negmin"):
+                self._info[k] = list(self._info[k])
         return self._info
 
     def arrays(self) -> dict:

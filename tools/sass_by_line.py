@@ -1,0 +1,24 @@
+"""SASS bytes per source file / per N-line bucket of one file, from -lineinfo.  usage: sass_by_line.py obj.o [file.cu [bucket]]"""
+import re, collections, subprocess, sys, tempfile, os, glob
+obj = os.path.abspath(sys.argv[1])
+d = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=d, capture_output=True)
+cub = glob.glob(os.path.join(d, "*.cubin"))[0]
+out = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
+cur = None; cnt = collections.Counter()
+for ln in out.splitlines():
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
+    if m:
+        cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
+    if re.match(r'\s+/\*[0-9a-f]{4,6}\*/', ln) and cur:
+        cnt[cur] += 16
+byfile = collections.Counter()
+for (f, l), c in cnt.items():
+    byfile[f] += c
+print("by file:", byfile.most_common())
+if len(sys.argv) > 2:
+    f0 = sys.argv[2]; bk = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    b = collections.Counter()
+    for (f, l), c in cnt.items():
+        if f == f0: b[l // bk * bk] += c
+    print(" ".join(f"{k}:{b[k]}" for k in sorted(b)))
