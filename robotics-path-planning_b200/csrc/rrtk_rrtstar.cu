@@ -99,6 +99,45 @@ __device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &s
     return true;
 }
 
+// Cheap verdict of the edge f -> t steered with extend_length = inf (choose_parent / rewire candidates), WITHOUT the
+// correctly rounded atan2/cos/sin: the reference's path points are f, f + k * res * (cos, sin)(theta) (k = 1..n,
+// accumulated) and -- when the last one lies within `res` of t -- t itself (rrt_04:1099-1113).  n = floor(d / res)
+// is computed exactly as steer does; the first and last points are f and t exactly; the intermediate points are
+// reproduced to within eps_pos with the direction (t - f) / d, so a point-circle test whose margin exceeds the
+// error band has the reference's verdict.  Returns 1 = free and snapped (end point == t), 0 = blocked,
+// -1 = too close to call (a test inside the band, or the snap decision within 1e-9 of its threshold): the caller
+// runs the exact steer + edge_free_lane.
+__device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, double ty, double d, double res,
+                                              const ObsList &L) {
+    if (!(d > 0.0)) return -1;
+    const double q = floor(d / res);
+    if (!(q < 1.0e6)) return -1;
+    const int n = (int)q;
+    const double rem = d - q * res;                    // distance left after n steps
+    if (!(rem <= res * (1.0 - 1e-9))) return -1;       // snap (d2 <= res, rrt_04:1107) must be certain
+    const double inv = res / d;
+    const double ux = (tx - fx) * inv, uy = (ty - fy) * inv;
+    const double e4 = 4.0 * ((double)(n + 8) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
+    bool unsure = false;
+    for (int j = 0; j < L.m; j++) {
+        const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
+        double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
+        if (dx * dx + dy * dy <= r2) return 0;
+        dx = ox - tx; dy = oy - ty;                    // last point: t itself (snapped), exact test
+        if (dx * dx + dy * dy <= r2) return 0;
+        double x = fx, y = fy;
+        for (int k = 1; k <= n; k++) {
+            x += ux; y += uy;
+            dx = ox - x; dy = oy - y;
+            const double dd = dx * dx + dy * dy;
+            const double t = dd - r2, band = (2.0 + dd + r2) * e4;
+            if (t <= -band) return 0;                  // certainly inside: blocked whatever the others say
+            unsure |= t <= band;
+        }
+    }
+    return unsure ? -1 : 1;
+}
+
 // the same verdict computed by the whole warp (lanes split the obstacles); uniform result
 __device__ __forceinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
                                                double ty, const ObsList &L, int lane) {
@@ -369,14 +408,21 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                             int i = near_idx[k];
                             double2 a = xy[i];
                             double ci = cost[i];
-                            Steer st = steer(a.x, a.y, nx, ny, INF, res);
-                            bool ok = edge_free_lane(a.x, a.y, st, nx, ny, L) && inside_play(p, st.ex, st.ey);
-                            nd[k] = st.d;   // = hypot(new - node), calc_new_cost's distance (rrt_04:1375-1377)
+                            const double dk = crm_hypot(nx - a.x, ny - a.y);  // what steer's calc_distance_and_angle returns
+                            double ex = nx, ey = ny;                          // a snapped edge ends on the new node
+                            const int v = edge_verdict_fast(a.x, a.y, nx, ny, dk, res, L);
+                            bool ok = v == 1;                                 // (the new node is inside the play area)
+                            if (v < 0) {
+                                Steer st = steer(a.x, a.y, nx, ny, INF, res);
+                                ok = edge_free_lane(a.x, a.y, st, nx, ny, L) && inside_play(p, st.ex, st.ey);
+                                ex = st.ex; ey = st.ey;
+                            }
+                            nd[k] = dk;     // = hypot(new - node), calc_new_cost's distance (rrt_04:1375-1377)
                             s_nc[k] = ci;
                             if (ok) {
                                 t_cpok++;
-                                double c = ci + st.d;
-                                if (c < bc) { bc = c; bk = k; bex = st.ex; bey = st.ey; }
+                                double c = ci + dk;
+                                if (c < bc) { bc = c; bk = k; bex = ex; bey = ey; }
                             }
                         }
                         warp_argmin(bc, bk);  // first minimum of the cost list
@@ -409,18 +455,25 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                 bool want = false, ok = false;
                                 Steer st;
                                 st.ex = st.ey = 0.0;
+                                double dk = 0.0;
                                 if (k < count) {
                                     i = near_idx[k];
                                     a = xy[i];
                                     snc = s_nc[k];
                                     // hypot(node - c) == the forward edge's d when c is the sample point itself
-                                    double dk = c_is_new ? nd[k] : crm_hypot(a.x - cx, a.y - cy);
+                                    dk = c_is_new ? nd[k] : crm_hypot(a.x - cx, a.y - cy);
                                     ecost = ccost + dk;
                                     want = (trace != nullptr) || (snc > ecost);
                                 }
                                 if (want) {
-                                    st = steer(cx, cy, a.x, a.y, INF, res);
-                                    ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
+                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, res, L);
+                                    if (v < 0) {
+                                        st = steer(cx, cy, a.x, a.y, INF, res);
+                                        ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
+                                    } else {   // snapped: the edge ends on the node itself (it does not move)
+                                        st.ex = a.x; st.ey = a.y;
+                                        ok = v == 1 && inside_play(p, a.x, a.y);
+                                    }
                                 }
                                 const unsigned okmask = __ballot_sync(FULL, ok);
                                 t_rwok += __popc(okmask);
