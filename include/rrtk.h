@@ -110,7 +110,8 @@ typedef struct rrtk_rrtstar_params {
  *   n_nodes [Q], iters_done [Q], goal_index [Q] (-1 = no path), status [Q],
  *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
  * scratch (caller allocated, contents undefined afterwards):
- *   workspace [Q][node_cap] int32   (children-per-node counts used by propagate_cost_to_leaves)
+ *   workspace [Q][4][node_cap] int32   (children lists -- first child, next / previous sibling -- and the
+ *                                       breadth-first frontier of propagate_cost_to_leaves)
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,

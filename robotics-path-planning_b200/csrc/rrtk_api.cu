@@ -142,7 +142,7 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
     if (!start_goal || !n_obs || !xy || !cost || !parent || !n_nodes || !iters_done || !goal_index || !status)
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if (!p->rrt_only && !near_r2) return set_error(RRTK_ERR_INVALID, "near_r2 is NULL");
-    if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * node_cap int32)");
+    if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * 4 * node_cap int32)");
     if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
     if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
@@ -321,7 +321,7 @@ int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal
     const size_t b_sg = Q * 4 * 8, b_obs = Q * (size_t)p->obs_stride * 4 * 8, b_no = Q * 4,
                  b_r2 = (cap + 2) * 8, b_st = sample_stream ? Q * it * 16 : 0,
                  b_so = sobol_offset ? Q * 8 : 0, b_xy = Q * cap * 16, b_c = Q * cap * 8,
-                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * cap * 4;
+                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * cap * 16;
     char *d = nullptr;
     size_t off[16], total = 0;
     const size_t sizes[15] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr, b_ws};

@@ -96,4 +96,47 @@ static __device__ __noinline__ void propagate(int root, int n, double2 *xy, doub
     }
 }
 
+
+// ---- children lists (first child / next sibling / previous sibling, -1 = none): O(subtree) cost propagation ----
+static __device__ __forceinline__ void link_child(int32_t *fc, int32_t *nxs, int32_t *pvs, int p, int c) {
+    const int f = fc[p];
+    nxs[c] = f; pvs[c] = -1;
+    if (f >= 0) pvs[f] = c;
+    fc[p] = c;
+}
+static __device__ __forceinline__ void unlink_child(int32_t *fc, int32_t *nxs, int32_t *pvs, int p, int c) {
+    const int a = pvs[c], b = nxs[c];
+    if (a >= 0) nxs[a] = b; else fc[p] = b;
+    if (b >= 0) pvs[b] = a;
+}
+
+// propagate_cost_to_leaves (rrt_04:1379-1384) over the children lists: breadth-first from `root`, one lane per
+// frontier node walking its child list; a node's cost depends only on its parent's, so any top-down order gives
+// the reference's values.  `queue` holds the frontier (global scratch, node_cap ints), `tail` is a shared-memory int.
+static __device__ __noinline__ void propagate_lists(int root, const double2 *xy, double *cost, const int32_t *fc,
+                                                    const int32_t *nxs, int32_t *queue, int *tail, int lane) {
+    if (fc[root] < 0) return;
+    if (lane == 0) { queue[0] = root; *tail = 1; }
+    __syncwarp();
+    // every queued node already has its final cost, so the queue is simply consumed 32 entries at a time
+    for (int head = 0;;) {
+        const int end = *tail;
+        if (head >= end) break;
+        const int k = head + lane;
+        __syncwarp();
+        if (k < end) {
+            const int p = queue[k];
+            const double2 a = xy[p];
+            const double cp = cost[p];
+            for (int c = fc[p]; c >= 0; c = nxs[c]) {
+                const double2 b = xy[c];
+                cost[c] = cp + crm_hypot(b.x - a.x, b.y - a.y);
+                if (fc[c] >= 0) queue[atomicAdd(tail, 1)] = c;
+            }
+        }
+        __syncwarp();
+        head = end < head + 32 ? end : head + 32;
+    }
+}
+
 }  // namespace rrtk

@@ -169,14 +169,16 @@ __device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double
 struct WarpSmem {
     // obstacles near the new node of the current iteration (re-used for the goal by best_goal)
     double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];
+    int qtail;      // frontier length of propagate_lists
+    int pad_[3];
 };
 
 // layout of the dynamic shared memory of one warp:
 //   WarpSmem | nd[near_cap] double (d2, then edge length) | nc[near_cap] double (node cost)
-//   | near_idx[near_cap] int | near_ok[near_cap] int | bits_cur[words] | bits_next[words]
+//   | near_idx[near_cap] int | near_ok[near_cap] int
 __host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
-    size_t words = (size_t)(node_cap + 31) / 32;
-    size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 2) + words * 4 * 2;
+    (void)node_cap;
+    size_t b = sizeof(WarpSmem) + (size_t)near_cap * (4 + 4 + 8 * 2);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -285,15 +287,12 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int near_cap = p.near_cap;
-    const int words = (p.node_cap + 31) / 32;
     unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(near_cap, p.node_cap);
     WarpSmem *ws = reinterpret_cast<WarpSmem *>(base);
     double *nd = reinterpret_cast<double *>(base + sizeof(WarpSmem));
     double *s_nc = nd + near_cap;
     int *near_idx = reinterpret_cast<int *>(s_nc + near_cap);
     int *near_ok = near_idx + near_cap;
-    uint32_t *bits_cur = reinterpret_cast<uint32_t *>(near_ok + near_cap);
-    uint32_t *bits_nxt = bits_cur + words;
     const double res = p.path_resolution;
     const double INF = CUDART_INF;
 
@@ -314,12 +313,14 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         int32_t *trace = trace_all ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
-        int32_t *nchild = workspace + (size_t)q * p.node_cap;
+        // children lists + the propagate frontier: 4 * node_cap ints of scratch per query
+        int32_t *fc = workspace + (size_t)q * 4 * p.node_cap;
+        int32_t *nxs = fc + p.node_cap, *pvs = nxs + p.node_cap, *queue = pvs + p.node_cap;
         if (lane == 0) {
             xy[0] = make_double2(sg.x, sg.y);
             cost[0] = 0.0;
             parent[0] = -1;
-            nchild[0] = 0;
+            fc[0] = -1;
         }
         __syncwarp();
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
@@ -363,7 +364,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     n++;
                     __syncwarp();
                 } else if (accept) {
-                    if (lane == 0) nchild[n] = 0;  // children arrive through rewire, before the append
+                    if (lane == 0) fc[n] = -1;  // children arrive through rewire, before the append
                     const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
                     const double r2 = near_r2[n + 1];
@@ -491,15 +492,15 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                         const bool moved = (ax != ex) || (ay != ey);
                                         __syncwarp();
                                         if (lane == 0) {
-                                            nchild[parent[ii]]--;
-                                            nchild[n]++;
+                                            unlink_child(fc, nxs, pvs, parent[ii], ii);
+                                            link_child(fc, nxs, pvs, n, ii);
                                             xy[ii] = make_double2(ex, ey);
                                             cost[ii] = ec;
                                             parent[ii] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate(ii, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
+                                        propagate_lists(ii, xy, cost, fc, nxs, queue, &ws->qtail, lane);
                                         dirty = true;
                                         if (moved) {
                                             // the node no longer sits where the parallel pass saw it, and the
@@ -524,22 +525,22 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                     if (ok && cost[i] > ec) {
                                         __syncwarp();
                                         if (lane == 0) {
-                                            nchild[parent[i]]--;
-                                            nchild[n]++;
+                                            unlink_child(fc, nxs, pvs, parent[i], i);
+                                            link_child(fc, nxs, pvs, n, i);
                                             xy[i] = make_double2(st.ex, st.ey);
                                             cost[i] = ec;
                                             parent[i] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate(i, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
+                                        propagate_lists(i, xy, cost, fc, nxs, queue, &ws->qtail, lane);
                                     }
                                 }
                             }
-                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; nchild[best]++; }
+                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(fc, nxs, pvs, best, n); }
                             t_status = 3; t_par = best;
                         } else {
-                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; nchild[ni]++; }
+                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; link_child(fc, nxs, pvs, ni, n); }
                             t_status = 2; t_par = ni;
                         }
                         n++;

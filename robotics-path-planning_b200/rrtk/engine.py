@@ -63,7 +63,7 @@ class BatchResult:
     status: "object"      # [Q] int32 (RRTK_Q_* bits)
     trace: "object"       # [Q, max_iter, 8] int32 or None
     start_goal: "object"  # [Q, 4] float64
-    workspace: "object" = None  # [Q, node_cap] int32 scratch of the kernel
+    workspace: "object" = None  # [Q, 4, node_cap] int32 scratch of the kernel (children lists, frontier)
 
     def paths_device(self, path_cap: int | None = None):
         """generate_final_course for every query on the GPU -> (path [Q, path_cap, 2], length [Q])."""
@@ -126,7 +126,7 @@ def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample
             status=torch.empty((q,), dtype=torch.int32, device=dev),
             trace=torch.zeros((q, p.max_iter, 8), dtype=torch.int32, device=dev) if want_trace else None,
             start_goal=start_goal,
-            workspace=torch.empty((q, cap), dtype=torch.int32, device=dev))
+            workspace=torch.empty((q, 4, cap), dtype=torch.int32, device=dev))
     ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     rc = _lib.lib().rrtk_rrtstar_run_dev(
         C.byref(p), ptr(start_goal), ptr(obstacles), ptr(n_obs), ptr(near_r2), ptr(sample_stream),
