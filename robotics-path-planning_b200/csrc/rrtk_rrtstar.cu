@@ -106,11 +106,12 @@ __device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &s
 // reproduced to within eps_pos with the direction (t - f) / d, so a point-circle test whose margin exceeds the
 // error band has the reference's verdict.  Returns 1 = free and snapped (end point == t), 0 = blocked,
 // -1 = too close to call (a test inside the band, or the snap decision within 1e-9 of its threshold): the caller
-// runs the exact steer + edge_free_lane.
-__device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, double ty, double d, double res,
-                                              const ObsList &L) {
+// runs the exact steer + edge_free_lane.  `extend` = steer's extend_length (inf for choose_parent / rewire,
+// expand_dis for the first edge); obstacles j0, j0 + jstep, ... are tested (lanes can split them).
+__device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, double ty, double d, double extend,
+                                              double res, const ObsList &L, int j0, int jstep) {
     if (!(d > 0.0)) return -1;
-    const double q = floor(d / res);
+    const double q = floor((extend > d ? d : extend) / res);   // steer's n_expand (rrt_04:1096-1099)
     if (!(q < 1.0e6)) return -1;
     const int n = (int)q;
     const double rem = d - q * res;                    // distance left after n steps
@@ -119,7 +120,7 @@ __device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, d
     const double ux = (tx - fx) * inv, uy = (ty - fy) * inv;
     const double e4 = 4.0 * ((double)(n + 8) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
     bool unsure = false;
-    for (int j = 0; j < L.m; j++) {
+    for (int j = j0; j < L.m; j += jstep) {
         const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
         double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
         if (dx * dx + dy * dy <= r2) return 0;
@@ -333,30 +334,70 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         for (it = 0; it < p.max_iter; it++) {
             Sample smp = draw_sample(p, (int)q, it, gx, gy, stream, sob);
             const double rx = smp.x, ry = smp.y;
-            // ---- get_nearest_node_index (rrt_04:1196-1202) ----
+            // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the
+            // sample: when the steered node snaps onto the sample (the common case once the tree is dense) the near
+            // scan would compute exactly these d^2 again ----
             double bd = INF;
-            int bi = 0x7fffffff;
+            int bi = 0x7fffffff, count = 0;
+            const double r2 = p.rrt_only ? -1.0 : near_r2[n + 1];
 RRTK_UNROLL(RRTK_UNROLL_NEAREST)
-            for (int i = lane; i < n; i += 32) {
-                double2 a = xy[i];
-                double ddx = a.x - rx, ddy = a.y - ry;
-                double d = ddx * ddx + ddy * ddy;
-                if (d < bd) { bd = d; bi = i; }
+            for (int b0 = 0; b0 < n; b0 += 32) {
+                const int i = b0 + lane;
+                bool hit = false;
+                double d = 0.0;
+                if (i < n) {
+                    double2 a = xy[i];
+                    double ddx = a.x - rx, ddy = a.y - ry;
+                    d = ddx * ddx + ddy * ddy;
+                    if (d < bd) { bd = d; bi = i; }
+                    hit = d <= r2;
+                }
+                unsigned mask = __ballot_sync(FULL, hit);
+                int pos = count + __popc(mask & ((1u << lane) - 1u));
+                if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+                count += __popc(mask);
             }
             warp_argmin(bd, bi);
             const int ni = bi;
             const double2 from = xy[ni];
-            // ---- steer towards the sample (rrt_04:1051-1052) ----
-            Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
-            const double nx = e0.ex, ny = e0.ey;
             int t_status = 0, t_near = 0, t_par = -1, t_cpok = 0, t_rwok = 0, t_rwap = 0;
-            bool accept = false;
-            if (inside_play(p, nx, ny)) {
-                t_status = 1;
-                double reach = p.expand_dis > res ? p.expand_dis : res;
-                ObsList L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y,
-                                           ws->cull_r2, lane);
-                accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
+            bool accept = false, near_valid = false;
+            // every path point of this iteration's edges lies within expand_dis + res of the new node (a snapped
+            // first edge starts up to expand_dis + res away; near nodes are within the near radius <= expand_dis)
+            const double reach = p.expand_dis + res;
+            ObsList L;
+            L.ox = L.oy = L.r2 = nullptr; L.stride = 1; L.m = 0;
+            // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the
+            // sample the new node IS the sample and only the collision verdict is needed (edge_verdict_fast);
+            // otherwise, or when the verdict is too close to call, the exact steer runs ----
+            double nx = rx, ny = ry;
+            const double d0 = crm_hypot(rx - from.x, ry - from.y);
+            int v = -1;
+            {
+                const double ext = p.expand_dis > d0 ? d0 : p.expand_dis;
+                const double q0 = floor(ext / res);
+                if (d0 > 0.0 && d0 - q0 * res <= res * (1.0 - 1e-9)) {   // same snap test as edge_verdict_fast
+                    if (inside_play(p, nx, ny)) {
+                        L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                        const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, p.expand_dis, res, L, lane, 32);
+                        const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
+                        v = blocked ? 0 : (unsure ? -1 : 1);
+                        if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
+                    } else {
+                        v = 0;  // outside the play area: rejected before the collision check (rrt_04:1054)
+                    }
+                }
+            }
+            if (v < 0) {
+                Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
+                nx = e0.ex; ny = e0.ey;
+                if (inside_play(p, nx, ny)) {
+                    t_status = 1;
+                    L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                    accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
+                }
+            }
+            {
                 if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
                 if (accept && p.rrt_only) {
                     if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni; }
@@ -367,23 +408,24 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     if (lane == 0) fc[n] = -1;  // children arrive through rewire, before the append
                     const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
-                    const double r2 = near_r2[n + 1];
-                    int count = 0;
+                    if (!near_valid) {
+                        count = 0;
 RRTK_UNROLL(RRTK_UNROLL_NEAR)
-                    for (int b0 = 0; b0 < n; b0 += 32) {
-                        int i = b0 + lane;
-                        bool hit = false;
-                        double d = 0.0;
-                        if (i < n) {
-                            double2 a = xy[i];
-                            double ddx = a.x - nx, ddy = a.y - ny;
-                            d = ddx * ddx + ddy * ddy;
-                            hit = d <= r2;
+                        for (int b0 = 0; b0 < n; b0 += 32) {
+                            int i = b0 + lane;
+                            bool hit = false;
+                            double d = 0.0;
+                            if (i < n) {
+                                double2 a = xy[i];
+                                double ddx = a.x - nx, ddy = a.y - ny;
+                                d = ddx * ddx + ddy * ddy;
+                                hit = d <= r2;
+                            }
+                            unsigned mask = __ballot_sync(FULL, hit);
+                            int pos = count + __popc(mask & ((1u << lane) - 1u));
+                            if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+                            count += __popc(mask);
                         }
-                        unsigned mask = __ballot_sync(FULL, hit);
-                        int pos = count + __popc(mask & ((1u << lane) - 1u));
-                        if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
-                        count += __popc(mask);
                     }
                     __syncwarp();
                     if (count > near_cap) {
@@ -411,7 +453,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                             double ci = cost[i];
                             const double dk = crm_hypot(nx - a.x, ny - a.y);  // what steer's calc_distance_and_angle returns
                             double ex = nx, ey = ny;                          // a snapped edge ends on the new node
-                            const int v = edge_verdict_fast(a.x, a.y, nx, ny, dk, res, L);
+                            const int v = edge_verdict_fast(a.x, a.y, nx, ny, dk, INF, res, L, 0, 1);
                             bool ok = v == 1;                                 // (the new node is inside the play area)
                             if (v < 0) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
@@ -467,7 +509,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                     want = (trace != nullptr) || (snc > ecost);
                                 }
                                 if (want) {
-                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, res, L);
+                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, INF, res, L, 0, 1);
                                     if (v < 0) {
                                         st = steer(cx, cy, a.x, a.y, INF, res);
                                         ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
