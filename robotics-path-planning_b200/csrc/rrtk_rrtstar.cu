@@ -120,20 +120,29 @@ __device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, d
     const double ux = (tx - fx) * inv, uy = (ty - fy) * inv;
     const double e4 = 4.0 * ((double)(n + 8) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
     bool unsure = false;
+    const double wx = tx - fx, wy = ty - fy, invl2 = 1.0 / (d * d);
     for (int j = j0; j < L.m; j += jstep) {
         const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
         double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
         if (dx * dx + dy * dy <= r2) return 0;
+        const double bj = (2.02 + 2.02 * r2) * e4;     // >= (2 + dd + r2) * e4 wherever |dd - r2| is that small
+        // every path point lies on the segment f-t (to within eps_pos): a circle farther than its radius (plus
+        // the band) from the segment cannot contain one
+        double sp = (dx * wx + dy * wy) * invl2;
+        sp = sp < 0.0 ? 0.0 : (sp > 1.0 ? 1.0 : sp);
+        const double px = dx - sp * wx, py = dy - sp * wy;
+        if (px * px + py * py - r2 > bj + 1e-9 * (1.0 + r2)) continue;
         dx = ox - tx; dy = oy - ty;                    // last point: t itself (snapped), exact test
         if (dx * dx + dy * dy <= r2) return 0;
         double x = fx, y = fy;
         for (int k = 1; k <= n; k++) {
             x += ux; y += uy;
             dx = ox - x; dy = oy - y;
-            const double dd = dx * dx + dy * dy;
-            const double t = dd - r2, band = (2.0 + dd + r2) * e4;
-            if (t <= -band) return 0;                  // certainly inside: blocked whatever the others say
-            unsure |= t <= band;
+            const double t = dx * dx + dy * dy - r2;
+            if (t <= bj) {
+                if (t <= -bj) return 0;                // certainly inside: blocked whatever the others say
+                unsure = true;
+            }
         }
     }
     return unsure ? -1 : 1;
@@ -340,13 +349,19 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             double bd = INF;
             int bi = 0x7fffffff, count = 0;
             const double r2 = p.rrt_only ? -1.0 : near_r2[n + 1];
+            // two chunks of node positions are kept in flight ahead of the one being processed (the scan is bound by
+            // load latency: the live trees of the ~16 resident queries exceed L1)
+            double2 a1 = lane < n ? xy[lane] : make_double2(0.0, 0.0);
+            double2 a2 = lane + 32 < n ? xy[lane + 32] : make_double2(0.0, 0.0);
 RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             for (int b0 = 0; b0 < n; b0 += 32) {
                 const int i = b0 + lane;
+                const double2 a = a1;
+                a1 = a2;
+                if (i + 64 < n) a2 = xy[i + 64];
                 bool hit = false;
                 double d = 0.0;
                 if (i < n) {
-                    double2 a = xy[i];
                     double ddx = a.x - rx, ddy = a.y - ry;
                     d = ddx * ddx + ddy * ddy;
                     if (d < bd) { bd = d; bi = i; }
