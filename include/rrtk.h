@@ -94,7 +94,16 @@ typedef struct rrtk_rrtstar_params {
     double min_rand, max_rand;
     double play_area[4];            /* xmin, xmax, ymin, ymax */
     uint64_t seed;                  /* counter-based RNG key for the in-kernel samplers */
+    /* optional uniform cell grid over the obstacles of each query (0 x 0 = off): the per-iteration obstacle cull
+     * then reads one cell's list instead of scanning all circles.  The grid must cover every point a node can
+     * take (samples, starts, goals); nodes outside it fall back to the full scan, so results never depend on it. */
+    int32_t grid_nx, grid_ny;       /* cells, each <= 64 */
+    double grid_x0, grid_y0;        /* lower-left corner */
+    double grid_cell;               /* cell edge */
 } rrtk_rrtstar_params;
+
+/* ints of workspace per query for rrtk_rrtstar_run_dev */
+#define RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny) (4 * (size_t)(node_cap) + 17 * (size_t)(grid_nx) * (size_t)(grid_ny))
 
 /* Device-pointer entry point.
  *   start_goal   [Q][4]                 sx, sy, gx, gy
@@ -110,8 +119,9 @@ typedef struct rrtk_rrtstar_params {
  *   n_nodes [Q], iters_done [Q], goal_index [Q] (-1 = no path), status [Q],
  *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
  * scratch (caller allocated, contents undefined afterwards):
- *   workspace [Q][4][node_cap] int32   (children lists -- first child, next / previous sibling -- and the
- *                                       breadth-first frontier of propagate_cost_to_leaves)
+ *   workspace [Q][RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny)] int32: children lists (first child, next /
+ *             previous sibling), the breadth-first frontier of propagate_cost_to_leaves, and the obstacle cell
+ *             lists (per cell a count + 32 uint16 indices)
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,

@@ -71,7 +71,10 @@ static int check_params(const rrtk_rrtstar_params *p) {
     if (!(p->path_resolution > 0.0)) return set_error(RRTK_ERR_INVALID, "path_resolution must be > 0");
     if (!(p->expand_dis >= 0.0)) return set_error(RRTK_ERR_INVALID, "expand_dis must be >= 0");
     if (p->sampler < 0 || p->sampler > 2) return set_error(RRTK_ERR_INVALID, "unknown sampler");
-    if (p->obs_stride < 0) return set_error(RRTK_ERR_INVALID, "obs_stride negative");
+    if (p->obs_stride < 0 || p->obs_stride > 65535) return set_error(RRTK_ERR_INVALID, "obs_stride out of range");
+    if (p->grid_nx < 0 || p->grid_ny < 0 || p->grid_nx > 64 || p->grid_ny > 64 || ((p->grid_nx == 0) != (p->grid_ny == 0)))
+        return set_error(RRTK_ERR_INVALID, "grid_nx / grid_ny must both be 0 or both in 1..64");
+    if (p->grid_nx > 0 && !(p->grid_cell > 0.0)) return set_error(RRTK_ERR_INVALID, "grid_cell must be > 0");
     return RRTK_OK;
 }
 
@@ -142,7 +145,7 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
     if (!start_goal || !n_obs || !xy || !cost || !parent || !n_nodes || !iters_done || !goal_index || !status)
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if (!p->rrt_only && !near_r2) return set_error(RRTK_ERR_INVALID, "near_r2 is NULL");
-    if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * 4 * node_cap int32)");
+    if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * RRTK_RRTSTAR_WS_INTS int32)");
     if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
     if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
@@ -321,7 +324,7 @@ int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal
     const size_t b_sg = Q * 4 * 8, b_obs = Q * (size_t)p->obs_stride * 4 * 8, b_no = Q * 4,
                  b_r2 = (cap + 2) * 8, b_st = sample_stream ? Q * it * 16 : 0,
                  b_so = sobol_offset ? Q * 8 : 0, b_xy = Q * cap * 16, b_c = Q * cap * 8,
-                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * cap * 16;
+                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * RRTK_RRTSTAR_WS_INTS(cap, p->grid_nx, p->grid_ny) * 4;
     char *d = nullptr;
     size_t off[16], total = 0;
     const size_t sizes[15] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr, b_ws};

@@ -97,6 +97,77 @@ static __device__ __noinline__ void propagate(int root, int n, double2 *xy, doub
 }
 
 
+// ---- obstacle cell grid (rrtk_rrtstar_params.grid_*): per cell the circles that can pass the cull test of ANY point
+// of the cell.  cnt[cell] counts them (more than GRID_CELL_CAP = the cell overflowed: callers scan all circles),
+// lists[cell][k] holds their indices.  Built once per query by its warp; read with ld.cg (the counts are bumped by
+// L2 atomics, which L1 does not see). ----
+constexpr int GRID_CELL_CAP = 32;
+struct ObsGrid {
+    int nx, ny;
+    double x0, y0, cell, inv_cell;
+    int32_t *cnt;
+    uint16_t *lists;
+};
+
+static __device__ __noinline__ void build_obstacle_grid(const ObsGrid &g, const double4 *obs, int n_obs, double reach,
+                                                    int lane) {
+    const int cells = g.nx * g.ny;
+    for (int c = lane; c < cells; c += 32) atomicExch(&g.cnt[c], 0);   // (atomics: the counts live in L2 only)
+    __syncwarp();
+    __threadfence_block();
+    for (int j = lane; j < n_obs; j += 32) {
+        const double4 o = obs[j];
+        const double lim = ((reach + o.z) * (1.0 + 1e-9) + 1e-9) * (1.0 + 1e-9) + 1e-9;  // cull limit + cell-edge rounding
+        int ix0 = (int)floor((o.x - lim - g.x0) * g.inv_cell) - 1, ix1 = (int)floor((o.x + lim - g.x0) * g.inv_cell) + 1;
+        int iy0 = (int)floor((o.y - lim - g.y0) * g.inv_cell) - 1, iy1 = (int)floor((o.y + lim - g.y0) * g.inv_cell) + 1;
+        ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0;
+        ix1 = ix1 > g.nx - 1 ? g.nx - 1 : ix1; iy1 = iy1 > g.ny - 1 ? g.ny - 1 : iy1;
+        for (int iy = iy0; iy <= iy1; iy++) {
+            const double ry0 = g.y0 + iy * g.cell, ry1 = g.y0 + (iy + 1) * g.cell;
+            const double dy = o.y < ry0 ? ry0 - o.y : (o.y > ry1 ? o.y - ry1 : 0.0);
+            for (int ix = ix0; ix <= ix1; ix++) {
+                const double rx0 = g.x0 + ix * g.cell, rx1 = g.x0 + (ix + 1) * g.cell;
+                const double dx = o.x < rx0 ? rx0 - o.x : (o.x > rx1 ? o.x - rx1 : 0.0);
+                if (dx * dx + dy * dy <= lim * lim) {
+                    const int c = iy * g.nx + ix;
+                    const int pos = atomicAdd(&g.cnt[c], 1);
+                    if (pos < GRID_CELL_CAP) g.lists[c * GRID_CELL_CAP + pos] = (uint16_t)j;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// cull through the grid: exact same keep test as cull_obstacles on the cell's candidates.  Falls back to the full scan
+// when the point is outside the grid or its cell overflowed.
+static __device__ __noinline__ ObsList cull_obstacles_grid(const ObsGrid &g, const double4 *obs, int n_obs, double cx,
+                                                       double cy, double reach, double *sx, double *sy, double *sr2,
+                                                       int lane) {
+    const double fx = floor((cx - g.x0) * g.inv_cell), fy = floor((cy - g.y0) * g.inv_cell);
+    int m = GRID_CELL_CAP + 1, c = 0;
+    if (g.nx > 0 && fx >= 0.0 && fy >= 0.0 && fx < (double)g.nx && fy < (double)g.ny) {
+        c = (int)fy * g.nx + (int)fx;
+        m = __ldcg(g.cnt + c);
+    }
+    if (m > GRID_CELL_CAP) return cull_obstacles(obs, n_obs, cx, cy, reach, sx, sy, sr2, lane);
+    bool keep = false;
+    double4 o = make_double4(0, 0, 0, 0);
+    if (lane < m) {
+        o = obs[__ldcg(g.lists + c * GRID_CELL_CAP + lane)];
+        const double dx = o.x - cx, dy = o.y - cy;
+        const double lim = (reach + o.z) * (1.0 + 1e-9) + 1e-9;
+        keep = dx * dx + dy * dy <= lim * lim;
+    }
+    const unsigned mask = __ballot_sync(FULL, keep);
+    const int pos = __popc(mask & ((1u << lane) - 1u));
+    if (keep) { sx[pos] = o.x; sy[pos] = o.y; sr2[pos] = o.w; }
+    __syncwarp();
+    ObsList L;
+    L.ox = sx; L.oy = sy; L.r2 = sr2; L.stride = 1; L.m = __popc(mask);
+    return L;
+}
+
 // ---- children lists (first child / next sibling / previous sibling, -1 = none): O(subtree) cost propagation ----
 static __device__ __forceinline__ void link_child(int32_t *fc, int32_t *nxs, int32_t *pvs, int p, int c) {
     const int f = fc[p];

@@ -324,8 +324,15 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
         // children lists + the propagate frontier: 4 * node_cap ints of scratch per query
-        int32_t *fc = workspace + (size_t)q * 4 * p.node_cap;
+        const int grid_cells = p.grid_nx * p.grid_ny;
+        int32_t *fc = workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny);
         int32_t *nxs = fc + p.node_cap, *pvs = nxs + p.node_cap, *queue = pvs + p.node_cap;
+        ObsGrid grid;
+        grid.nx = p.grid_nx; grid.ny = p.grid_ny; grid.x0 = p.grid_x0; grid.y0 = p.grid_y0;
+        grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
+        grid.cnt = queue + p.node_cap;
+        grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
+        if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, p.expand_dis + res, lane);
         if (lane == 0) {
             xy[0] = make_double2(sg.x, sg.y);
             cost[0] = 0.0;
@@ -393,7 +400,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 const double q0 = floor(ext / res);
                 if (d0 > 0.0 && d0 - q0 * res <= res * (1.0 - 1e-9)) {   // same snap test as edge_verdict_fast
                     if (inside_play(p, nx, ny)) {
-                        L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                        L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                         const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, p.expand_dis, res, L, lane, 32);
                         const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                         v = blocked ? 0 : (unsure ? -1 : 1);
@@ -408,7 +415,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 nx = e0.ex; ny = e0.ey;
                 if (inside_play(p, nx, ny)) {
                     t_status = 1;
-                    L = cull_obstacles(obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                    L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                     accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
                 }
             }

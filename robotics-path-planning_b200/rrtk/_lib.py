@@ -24,7 +24,9 @@ class RRTStarParams(C.Structure):
                 ("goal_sample_rate", C.c_int32), ("has_play_area", C.c_int32),
                 ("rrt_only", C.c_int32), ("expand_dis", C.c_double),
                 ("path_resolution", C.c_double), ("min_rand", C.c_double),
-                ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64)]
+                ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64),
+                ("grid_nx", C.c_int32), ("grid_ny", C.c_int32), ("grid_x0", C.c_double),
+                ("grid_y0", C.c_double), ("grid_cell", C.c_double)]
 
 
 class InformedParams(C.Structure):

@@ -41,6 +41,16 @@ class RRTStarBatch:
                                          path_resolution, play_area, search_until_max_iter,
                                          self.sampler, goal_sample_rate, rand_area[0], rand_area[1],
                                          seed, near_cap)
+        # obstacle cell grid: box of everything a node can be (samples, starts, goals)
+        pts = [starts, goals]
+        if sample_stream is not None:
+            ss_ = np.asarray(sample_stream, dtype=np.float64).reshape(-1, 2)
+            pts.append(np.array([ss_.min(axis=0), ss_.max(axis=0)]))
+        else:
+            pts.append(np.array([[rand_area[0]] * 2, [rand_area[1]] * 2], dtype=np.float64))
+        allp = np.vstack(pts)
+        engine.set_obstacle_grid(self.params, float(allp[:, 0].min()), float(allp[:, 0].max()),
+                                 float(allp[:, 1].min()), float(allp[:, 1].max()))
         # pinned host staging (inputs of the end-to-end path) + device copies
         self.h_start_goal = torch.from_numpy(np.ascontiguousarray(np.hstack([starts, goals]))).pin_memory()
         self.h_obstacles = torch.from_numpy(rows).pin_memory()

@@ -63,7 +63,7 @@ class BatchResult:
     status: "object"      # [Q] int32 (RRTK_Q_* bits)
     trace: "object"       # [Q, max_iter, 8] int32 or None
     start_goal: "object"  # [Q, 4] float64
-    workspace: "object" = None  # [Q, 4, node_cap] int32 scratch of the kernel (children lists, frontier)
+    workspace: "object" = None  # [Q, workspace_ints(p)] int32 scratch (children lists, frontier, obstacle cells)
 
     def paths_device(self, path_cap: int | None = None):
         """generate_final_course for every query on the GPU -> (path [Q, path_cap, 2], length [Q])."""
@@ -106,6 +106,26 @@ def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_reso
     return p
 
 
+def set_obstacle_grid(p: _lib.RRTStarParams, xmin, xmax, ymin, ymax) -> None:
+    """Cell grid for the per-iteration obstacle cull (struct rrtk_rrtstar_params.grid_*).  The box must contain
+    every sample, start and goal; nodes outside it are handled by the full scan, so this only affects speed."""
+    reach = p.expand_dis + p.path_resolution
+    if not (math.isfinite(xmin) and math.isfinite(xmax) and math.isfinite(ymin) and math.isfinite(ymax)) \
+            or not reach > 0.0 or xmax < xmin or ymax < ymin:
+        p.grid_nx = p.grid_ny = 0
+        return
+    pad = 1e-6 * (1.0 + abs(xmin) + abs(xmax) + abs(ymin) + abs(ymax))
+    xmin, ymin, w, h = xmin - pad, ymin - pad, (xmax - xmin) + 2 * pad, (ymax - ymin) + 2 * pad
+    cell = max(reach, w / 64.0, h / 64.0)
+    p.grid_nx, p.grid_ny = max(1, min(64, math.ceil(w / cell))), max(1, min(64, math.ceil(h / cell)))
+    p.grid_x0, p.grid_y0, p.grid_cell = xmin, ymin, cell
+
+
+def workspace_ints(p: _lib.RRTStarParams) -> int:
+    """RRTK_RRTSTAR_WS_INTS (include/rrtk.h)."""
+    return 4 * p.node_cap + 17 * p.grid_nx * p.grid_ny
+
+
 def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample_stream=None,
             sobol_offset=None, want_trace=False, out: BatchResult | None = None) -> BatchResult:
     """Launch the planning kernel on device tensors (float64 / int32 / int64, contiguous, CUDA)."""
@@ -126,7 +146,7 @@ def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample
             status=torch.empty((q,), dtype=torch.int32, device=dev),
             trace=torch.zeros((q, p.max_iter, 8), dtype=torch.int32, device=dev) if want_trace else None,
             start_goal=start_goal,
-            workspace=torch.empty((q, 4, cap), dtype=torch.int32, device=dev))
+            workspace=torch.empty((q, workspace_ints(p)), dtype=torch.int32, device=dev))
     ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     rc = _lib.lib().rrtk_rrtstar_run_dev(
         C.byref(p), ptr(start_goal), ptr(obstacles), ptr(n_obs), ptr(near_r2), ptr(sample_stream),

@@ -137,6 +137,10 @@ class RRT:
                                self._search_until_max_iter(), _lib.SAMPLER_STREAM,
                                self.goal_sample_rate, self.min_rand, self.max_rand,
                                near_cap=self._near_cap(node_cap), rrt_only=self._rrt_only)
+        if max_iter > 0:   # obstacle cell grid over everything a node can be (samples, start, goal)
+            bx = [float(stream[:, 0].min()), float(stream[:, 0].max()), float(self.start.x), goal[0]]
+            by = [float(stream[:, 1].min()), float(stream[:, 1].max()), float(self.start.y), goal[1]]
+            engine.set_obstacle_grid(p, min(bx), max(bx), min(by), max(by))
         dev = torch.device("cuda")
         sg = torch.tensor([[float(self.start.x), float(self.start.y), goal[0], goal[1]]],
                           dtype=torch.float64, device=dev)

@@ -38,9 +38,9 @@ def test_version_and_error_string():
 
 
 def test_params_struct_layout_matches_header():
-    """sizeof(rrtk_rrtstar_params) = 10 int32 + 8 double + uint64 = 112 bytes on LP64."""
+    """sizeof(rrtk_rrtstar_params) = 10 int32 + 8 double + uint64 + 2 int32 + 3 double = 144 bytes on LP64."""
     from rrtk import _lib
-    assert C.sizeof(_lib.RRTStarParams) == 112
+    assert C.sizeof(_lib.RRTStarParams) == 144
 
 
 def test_bad_params_rejected_without_gpu():
