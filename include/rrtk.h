@@ -103,7 +103,8 @@ typedef struct rrtk_rrtstar_params {
 } rrtk_rrtstar_params;
 
 /* ints of workspace per query for rrtk_rrtstar_run_dev */
-#define RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny) (4 * (size_t)(node_cap) + 17 * (size_t)(grid_nx) * (size_t)(grid_ny))
+#define RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny) \
+    (4 * (size_t)(node_cap) + 4 * ((17 * (size_t)(grid_nx) * (size_t)(grid_ny) + 3) / 4)) /* multiple of 4: 16-byte rows */
 
 /* Device-pointer entry point.
  *   start_goal   [Q][4]                 sx, sy, gx, gy
@@ -121,7 +122,7 @@ typedef struct rrtk_rrtstar_params {
  * scratch (caller allocated, contents undefined afterwards):
  *   workspace [Q][RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny)] int32: children lists (first child, next /
  *             previous sibling), the breadth-first frontier of propagate_cost_to_leaves, and the obstacle cell
- *             lists (per cell a count + 32 uint16 indices)
+ *             lists (per cell a count + 32 uint16 indices); the workspace must be 16-byte aligned
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,

@@ -146,6 +146,7 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if (!p->rrt_only && !near_r2) return set_error(RRTK_ERR_INVALID, "near_r2 is NULL");
     if (!workspace) return set_error(RRTK_ERR_INVALID, "workspace is NULL (need n_queries * RRTK_RRTSTAR_WS_INTS int32)");
+    if ((uintptr_t)workspace & 15) return set_error(RRTK_ERR_INVALID, "workspace must be 16-byte aligned");
     if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
     if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");

@@ -168,26 +168,29 @@ static __device__ __noinline__ ObsList cull_obstacles_grid(const ObsGrid &g, con
     return L;
 }
 
-// ---- children lists (first child / next sibling / previous sibling, -1 = none): O(subtree) cost propagation ----
-static __device__ __forceinline__ void link_child(int32_t *fc, int32_t *nxs, int32_t *pvs, int p, int c) {
-    const int f = fc[p];
-    nxs[c] = f; pvs[c] = -1;
-    if (f >= 0) pvs[f] = c;
-    fc[p] = c;
+// ---- children lists: links[i] = (first child, next sibling, previous sibling, frontier slot i), -1 = none; one
+// 16-byte load gives all links of a node; the .w components together are the breadth-first queue of
+// propagate_lists.  O(subtree) cost propagation. ----
+static __device__ __forceinline__ void link_child(int4 *links, int p, int c) {
+    const int f = links[p].x;
+    links[c].y = f; links[c].z = -1;
+    if (f >= 0) links[f].z = c;
+    links[p].x = c;
 }
-static __device__ __forceinline__ void unlink_child(int32_t *fc, int32_t *nxs, int32_t *pvs, int p, int c) {
-    const int a = pvs[c], b = nxs[c];
-    if (a >= 0) nxs[a] = b; else fc[p] = b;
-    if (b >= 0) pvs[b] = a;
+static __device__ __forceinline__ void unlink_child(int4 *links, int p, int c) {
+    const int4 lc = links[c];
+    const int a = lc.z, b = lc.y;
+    if (a >= 0) links[a].y = b; else links[p].x = b;
+    if (b >= 0) links[b].z = a;
 }
 
 // propagate_cost_to_leaves (rrt_04:1379-1384) over the children lists: breadth-first from `root`, one lane per
 // frontier node walking its child list; a node's cost depends only on its parent's, so any top-down order gives
-// the reference's values.  `queue` holds the frontier (global scratch, node_cap ints), `tail` is a shared-memory int.
-static __device__ __noinline__ void propagate_lists(int root, const double2 *xy, double *cost, const int32_t *fc,
-                                                    const int32_t *nxs, int32_t *queue, int *tail, int lane) {
-    if (fc[root] < 0) return;
-    if (lane == 0) { queue[0] = root; *tail = 1; }
+// the reference's values.  The frontier lives in links[.].w, `tail` is a shared-memory int.
+static __device__ __noinline__ void propagate_lists(int root, const double2 *xy, double *cost, int4 *links, int *tail,
+                                                    int lane) {
+    if (links[root].x < 0) return;
+    if (lane == 0) { links[0].w = root; *tail = 1; }
     __syncwarp();
     // every queued node already has its final cost, so the queue is simply consumed 32 entries at a time
     for (int head = 0;;) {
@@ -196,13 +199,15 @@ static __device__ __noinline__ void propagate_lists(int root, const double2 *xy,
         const int k = head + lane;
         __syncwarp();
         if (k < end) {
-            const int p = queue[k];
+            const int p = links[k].w;
             const double2 a = xy[p];
             const double cp = cost[p];
-            for (int c = fc[p]; c >= 0; c = nxs[c]) {
+            for (int c = links[p].x; c >= 0;) {
+                const int4 lc = links[c];
                 const double2 b = xy[c];
                 cost[c] = cp + crm_hypot(b.x - a.x, b.y - a.y);
-                if (fc[c] >= 0) queue[atomicAdd(tail, 1)] = c;
+                if (lc.x >= 0) links[atomicAdd(tail, 1)].w = c;
+                c = lc.y;
             }
         }
         __syncwarp();

@@ -286,7 +286,12 @@ __device__ unsigned int g_query_counter;
 #ifndef RRTK_MIN_BLOCKS
 #define RRTK_MIN_BLOCKS 4
 #endif
-extern "C" __global__ void __launch_bounds__(WARPS_PER_CTA * 32, RRTK_MIN_BLOCKS)
+// RRT_ONLY / TRACE are compile-time so the planning launch carries neither the basic-RRT branches nor the trace
+// bookkeeping in its instruction stream (the loop is instruction-fetch sensitive)
+// NC > 0: the per-warp shared-memory arrays are laid out for a near list of NC entries (p.near_cap <= NC stays the
+// logical capacity), so every shared-memory address is an immediate; NC = 0: laid out for p.near_cap at run time.
+template <bool RRT_ONLY, bool TRACE, int NC>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, RRTK_MIN_BLOCKS)
 rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
                const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
@@ -297,12 +302,13 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int near_cap = p.near_cap;
-    unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(near_cap, p.node_cap);
+    const int lay = NC > 0 ? NC : near_cap;   // layout capacity
+    unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(lay, p.node_cap);
     WarpSmem *ws = reinterpret_cast<WarpSmem *>(base);
     double *nd = reinterpret_cast<double *>(base + sizeof(WarpSmem));
-    double *s_nc = nd + near_cap;
-    int *near_idx = reinterpret_cast<int *>(s_nc + near_cap);
-    int *near_ok = near_idx + near_cap;
+    double *s_nc = nd + lay;
+    int *near_idx = reinterpret_cast<int *>(s_nc + lay);
+    int *near_ok = near_idx + lay;
     const double res = p.path_resolution;
     const double INF = CUDART_INF;
 
@@ -320,24 +326,23 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         double *cost = cost_all + (size_t)q * p.node_cap;
         int32_t *parent = parent_all + (size_t)q * p.node_cap;
         const double2 *stream = sample_stream ? sample_stream + (size_t)q * p.max_iter : nullptr;
-        int32_t *trace = trace_all ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
+        int32_t *trace = TRACE ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
         // children lists + the propagate frontier: 4 * node_cap ints of scratch per query
         const int grid_cells = p.grid_nx * p.grid_ny;
-        int32_t *fc = workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny);
-        int32_t *nxs = fc + p.node_cap, *pvs = nxs + p.node_cap, *queue = pvs + p.node_cap;
+        int4 *links = reinterpret_cast<int4 *>(workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny));
         ObsGrid grid;
         grid.nx = p.grid_nx; grid.ny = p.grid_ny; grid.x0 = p.grid_x0; grid.y0 = p.grid_y0;
         grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
-        grid.cnt = queue + p.node_cap;
+        grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
         if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, p.expand_dis + res, lane);
         if (lane == 0) {
             xy[0] = make_double2(sg.x, sg.y);
             cost[0] = 0.0;
             parent[0] = -1;
-            fc[0] = -1;
+            links[0] = make_int4(-1, -1, -1, 0);
         }
         __syncwarp();
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
@@ -355,7 +360,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             // scan would compute exactly these d^2 again ----
             double bd = INF;
             int bi = 0x7fffffff, count = 0;
-            const double r2 = p.rrt_only ? -1.0 : near_r2[n + 1];
+            const double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];
             // two chunks of node positions are kept in flight ahead of the one being processed (the scan is bound by
             // load latency: the live trees of the ~16 resident queries exceed L1)
             double2 a1 = lane < n ? xy[lane] : make_double2(0.0, 0.0);
@@ -421,13 +426,13 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             }
             {
                 if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
-                if (accept && p.rrt_only) {
+                if (accept && RRT_ONLY) {
                     if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni; }
                     t_status = 2; t_par = ni;
                     n++;
                     __syncwarp();
                 } else if (accept) {
-                    if (lane == 0) fc[n] = -1;  // children arrive through rewire, before the append
+                    if (lane == 0) links[n] = make_int4(-1, -1, -1, 0);  // children arrive through rewire, before the append
                     const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
                     if (!near_valid) {
@@ -495,7 +500,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                             bex = __shfl_sync(FULL, bex, bk & 31);  // k = lane (mod 32): the winner's lane
                             bey = __shfl_sync(FULL, bey, bk & 31);
                         }
-                        if (trace) {
+                        if (TRACE) {
 #pragma unroll
                             for (int off = 16; off >= 1; off >>= 1) t_cpok += __shfl_xor_sync(FULL, t_cpok, off);
                         }
@@ -528,7 +533,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                     // hypot(node - c) == the forward edge's d when c is the sample point itself
                                     dk = c_is_new ? nd[k] : crm_hypot(a.x - cx, a.y - cy);
                                     ecost = ccost + dk;
-                                    want = (trace != nullptr) || (snc > ecost);
+                                    want = TRACE || (snc > ecost);
                                 }
                                 if (want) {
                                     const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, INF, res, L, 0, 1);
@@ -556,15 +561,15 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                         const bool moved = (ax != ex) || (ay != ey);
                                         __syncwarp();
                                         if (lane == 0) {
-                                            unlink_child(fc, nxs, pvs, parent[ii], ii);
-                                            link_child(fc, nxs, pvs, n, ii);
+                                            unlink_child(links, parent[ii], ii);
+                                            link_child(links, n, ii);
                                             xy[ii] = make_double2(ex, ey);
                                             cost[ii] = ec;
                                             parent[ii] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate_lists(ii, xy, cost, fc, nxs, queue, &ws->qtail, lane);
+                                        propagate_lists(ii, xy, cost, links, &ws->qtail, lane);
                                         dirty = true;
                                         if (moved) {
                                             // the node no longer sits where the parallel pass saw it, and the
@@ -589,22 +594,22 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                     if (ok && cost[i] > ec) {
                                         __syncwarp();
                                         if (lane == 0) {
-                                            unlink_child(fc, nxs, pvs, parent[i], i);
-                                            link_child(fc, nxs, pvs, n, i);
+                                            unlink_child(links, parent[i], i);
+                                            link_child(links, n, i);
                                             xy[i] = make_double2(st.ex, st.ey);
                                             cost[i] = ec;
                                             parent[i] = n;
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        propagate_lists(i, xy, cost, fc, nxs, queue, &ws->qtail, lane);
+                                        propagate_lists(i, xy, cost, links, &ws->qtail, lane);
                                     }
                                 }
                             }
-                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(fc, nxs, pvs, best, n); }
+                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(links, best, n); }
                             t_status = 3; t_par = best;
                         } else {
-                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; link_child(fc, nxs, pvs, ni, n); }
+                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; link_child(links, ni, n); }
                             t_status = 2; t_par = ni;
                         }
                         n++;
@@ -612,13 +617,13 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                     }
                 }
             }
-            if (trace && lane == 0) {
+            if (TRACE && lane == 0) {
                 int32_t *tr = trace + (size_t)it * 8;
                 tr[0] = ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = t_cpok;
                 tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
             }
             if (done) { it++; break; }
-            if (p.rrt_only) {
+            if (RRT_ONLY) {
                 // goal test on the last node (rrt_01:90-96)
                 double2 last = xy[n - 1];
                 if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
@@ -637,7 +642,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                 if (gi >= 0) { it++; done = true; break; }
             }
         }
-        if (!done && !p.rrt_only) {
+        if (!done && !RRT_ONLY) {
             bool ovf = false;
             ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
             gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
@@ -725,15 +730,24 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
                    const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
                    int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                    int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s) {
-    size_t per_warp = warp_smem_bytes(p.near_cap, p.node_cap);
+    const bool fixed_nc = p.near_cap <= 256;
+    size_t per_warp = warp_smem_bytes(fixed_nc ? 256 : p.near_cap, p.node_cap);
     size_t smem = per_warp * WARPS_PER_CTA;
     if (smem > 227 * 1024) return set_error(RRTK_ERR_INVALID, "near_cap/node_cap need more than 227 KB of shared memory");
-    cudaError_t e = cudaFuncSetAttribute(rrtstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    typedef void (*kernel_t)(rrtk_rrtstar_params, const double4 *, const double4 *, const int32_t *, const double *,
+                             const double2 *, const int64_t *, double2 *, double *, int32_t *, int32_t *, int32_t *,
+                             int32_t *, int32_t *, int32_t *, int32_t *, unsigned int *);
+    const kernel_t kern =
+        fixed_nc ? (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 256> : rrtstar_kernel<true, false, 256>)
+                               : (trace ? rrtstar_kernel<false, true, 256> : rrtstar_kernel<false, false, 256>))
+                 : (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 0> : rrtstar_kernel<true, false, 0>)
+                               : (trace ? rrtstar_kernel<false, true, 0> : rrtstar_kernel<false, false, 0>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_kernel)");
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrtstar_kernel, WARPS_PER_CTA * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (per_sm < 1) per_sm = 1;
     long long want = ((long long)p.n_queries + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -742,7 +756,7 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
-    rrtstar_kernel<<<(unsigned)grid, WARPS_PER_CTA * 32, smem, s>>>(
+    kern<<<(unsigned)grid, WARPS_PER_CTA * 32, smem, s>>>(
         p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(obstacles),
         n_obs, near_r2, reinterpret_cast<const double2 *>(sample_stream), sobol_offset,
         reinterpret_cast<double2 *>(xy), cost, parent, n_nodes, iters_done, goal_index, status, trace,

@@ -123,7 +123,7 @@ def set_obstacle_grid(p: _lib.RRTStarParams, xmin, xmax, ymin, ymax) -> None:
 
 def workspace_ints(p: _lib.RRTStarParams) -> int:
     """RRTK_RRTSTAR_WS_INTS (include/rrtk.h)."""
-    return 4 * p.node_cap + 17 * p.grid_nx * p.grid_ny
+    return 4 * p.node_cap + 4 * ((17 * p.grid_nx * p.grid_ny + 3) // 4)
 
 
 def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample_stream=None,
