@@ -16,14 +16,18 @@ struct ObsList {  // SoA view of the obstacles an edge must be tested against
     int m;
 };
 
-// warp argmin of (value, index): smaller value wins, ties -> smaller index (list.index(min(..)))
+// warp argmin of (value, index): smaller value wins, ties -> smaller index (list.index(min(..))).  Values are
+// non-negative or +inf, so their bit patterns order like the values: three integer REDUX ops find the minimum
+// (hi word, lo word, index) instead of five shuffle rounds over 12 bytes (less code in the hot loop).
 static __device__ __forceinline__ void warp_argmin(double &v, int &i) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        double ov = __shfl_xor_sync(FULL, v, off);
-        int oi = __shfl_xor_sync(FULL, i, off);
-        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mhi = __reduce_min_sync(FULL, hi);
+    const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool is_min = hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(FULL, is_min ? (unsigned)i : 0xffffffffu);
+    v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    i = (int)mi;
 }
 
 // Conservative exact cull: keep obstacle o iff |o - c| <= (reach + R_o) * (1 + 1e-9) + 1e-9.

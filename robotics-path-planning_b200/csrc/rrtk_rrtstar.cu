@@ -149,7 +149,7 @@ __device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, d
 }
 
 // the same verdict computed by the whole warp (lanes split the obstacles); uniform result
-__device__ __forceinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
+__device__ __noinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
                                                double ty, const ObsList &L, int lane) {
     bool hit = false;
     for (int j = lane; j < L.m && !hit; j += 32) {
@@ -173,6 +173,58 @@ __device__ __forceinline__ bool edge_free_warp(double fx, double fy, const Steer
 __device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double x, double y) {
     if (!p.has_play_area) return true;  // rrt_04:1207-1208
     return !(x < p.play_area[0] || x > p.play_area[1] || y < p.play_area[2] || y > p.play_area[3]);
+}
+
+// find_near_nodes (rrt_04:1314-1338) around (cx, cy): ballot compaction in ascending index order.  Only used when the
+// new node is not the sample (the merged scan of the main loop covers the common case).
+__device__ __noinline__ int near_scan(const double2 *xy, int n, double cx, double cy, double r2, int *near_idx, double *nd,
+                                     int near_cap, int lane) {
+    int count = 0;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        int i = b0 + lane;
+        bool hit = false;
+        double d = 0.0;
+        if (i < n) {
+            double2 a = xy[i];
+            double ddx = a.x - cx, ddy = a.y - cy;
+            d = ddx * ddx + ddy * ddy;
+            hit = d <= r2;
+        }
+        unsigned mask = __ballot_sync(FULL, hit);
+        int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
+        count += __popc(mask);
+    }
+    return count;
+}
+
+// rewire entries [from, count) one at a time against the current tree (after a re-parented node MOVED, rrt_04:1365-1371:
+// the parallel pass's view of positions and costs is stale).  Out of line: rare.
+__device__ __noinline__ void rewire_serial(const rrtk_rrtstar_params &p, int from, int count, const int *near_idx, double2 *xy,
+                                          double *cost, int32_t *parent, int4 *links, int n, double cx, double cy,
+                                          double ccost, const ObsList &L, int *qtail, int lane, int &t_rwok, int &t_rwap) {
+    const double res = p.path_resolution;
+    for (int k = from; k < count; k++) {
+        const int i = near_idx[k];
+        const double2 a = xy[i];
+        Steer st = steer(cx, cy, a.x, a.y, CUDART_INF, res);
+        const bool ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) && inside_play(p, st.ex, st.ey);
+        const double ec = ccost + st.d;
+        t_rwok += ok ? 1 : 0;
+        if (ok && cost[i] > ec) {
+            __syncwarp();
+            if (lane == 0) {
+                unlink_child(links, parent[i], i);
+                link_child(links, n, i);
+                xy[i] = make_double2(st.ex, st.ey);
+                cost[i] = ec;
+                parent[i] = n;
+            }
+            __syncwarp();
+            t_rwap++;
+            propagate_lists(i, xy, cost, links, qtail, lane);
+        }
+    }
 }
 
 // per-warp shared memory
@@ -435,25 +487,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     if (lane == 0) links[n] = make_int4(-1, -1, -1, 0);  // children arrive through rewire, before the append
                     const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
-                    if (!near_valid) {
-                        count = 0;
-RRTK_UNROLL(RRTK_UNROLL_NEAR)
-                        for (int b0 = 0; b0 < n; b0 += 32) {
-                            int i = b0 + lane;
-                            bool hit = false;
-                            double d = 0.0;
-                            if (i < n) {
-                                double2 a = xy[i];
-                                double ddx = a.x - nx, ddy = a.y - ny;
-                                d = ddx * ddx + ddy * ddy;
-                                hit = d <= r2;
-                            }
-                            unsigned mask = __ballot_sync(FULL, hit);
-                            int pos = count + __popc(mask & ((1u << lane) - 1u));
-                            if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
-                            count += __popc(mask);
-                        }
-                    }
+                    if (!near_valid) count = near_scan(xy, n, nx, ny, r2, near_idx, nd, near_cap, lane);
                     __syncwarp();
                     if (count > near_cap) {
                         status |= RRTK_Q_NEAR_OVERFLOW;
@@ -582,30 +616,9 @@ RRTK_UNROLL(RRTK_UNROLL_NEAR)
                                     }
                                 }
                             }
-                            if (fallback_from >= 0) {
-                                for (int k = fallback_from; k < count; k++) {
-                                    const int i = near_idx[k];
-                                    const double2 a = xy[i];
-                                    Steer st = steer(cx, cy, a.x, a.y, INF, res);
-                                    const bool ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) &&
-                                                    inside_play(p, st.ex, st.ey);
-                                    const double ec = ccost + st.d;
-                                    t_rwok += ok ? 1 : 0;
-                                    if (ok && cost[i] > ec) {
-                                        __syncwarp();
-                                        if (lane == 0) {
-                                            unlink_child(links, parent[i], i);
-                                            link_child(links, n, i);
-                                            xy[i] = make_double2(st.ex, st.ey);
-                                            cost[i] = ec;
-                                            parent[i] = n;
-                                        }
-                                        __syncwarp();
-                                        t_rwap++;
-                                        propagate_lists(i, xy, cost, links, &ws->qtail, lane);
-                                    }
-                                }
-                            }
+                            if (fallback_from >= 0)
+                                rewire_serial(p, fallback_from, count, near_idx, xy, cost, parent, links, n, cx, cy, ccost, L,
+                                              &ws->qtail, lane, t_rwok, t_rwap);
                             if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(links, best, n); }
                             t_status = 3; t_par = best;
                         } else {
