@@ -164,6 +164,9 @@ typedef struct rrtk_informed_params {
     int32_t path_cap;    /* capacity of each best-path snapshot */
     int32_t pad_;
     double expand_dis;
+    double coord_bound;  /* upper bound on |coordinate| of anything in the scenes (samples, nodes, circles): sets the
+                            tolerance band inside which a near edge falls back to the reference's exact end-point
+                            arithmetic; results do not depend on it */
 } rrtk_informed_params;
 
 /*   start_goal [Q][4]; rot [Q][4] = c00, c01, c10, c11 of the rotation matrix C (rrt_07:1063-1068, host SVD);

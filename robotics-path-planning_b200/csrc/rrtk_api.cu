@@ -166,6 +166,7 @@ int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goa
     if (p->n_queries < 0 || p->max_iter < 0 || p->node_cap < 1 || p->path_cap < 2 || p->obs_stride < 0)
         return set_error(RRTK_ERR_INVALID, "bad sizes");
     if (!(p->expand_dis > 0.0)) return set_error(RRTK_ERR_INVALID, "expand_dis must be > 0");
+    if (!(p->coord_bound > 0.0)) return set_error(RRTK_ERR_INVALID, "coord_bound must be > 0");
     if (p->n_queries == 0) return RRTK_OK;
     if (!start_goal || !rot || !n_obs || !near_rr2 || !xy || !cost || !parent || !n_nodes || !path || !path_len ||
         !c_best || !status || !ws_idx || !ws_d || (p->max_iter > 0 && (!free_samples || !ball_draws)) ||

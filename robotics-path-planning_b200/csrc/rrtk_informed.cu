@@ -56,6 +56,42 @@ __device__ __forceinline__ bool seg_free_warp(double x1, double y1, double x2, d
     return __ballot_sync(FULL, hit) == 0u;
 }
 
+// distance_squared_point_to_segment for one circle, value only
+__device__ __forceinline__ double seg_dd(double x1, double y1, double x2, double y2, double ox, double oy) {
+    if (x1 == x2 && y1 == y2) return idot2(ox - x1, oy - y1, ox - x1, oy - y1);
+    double wx = x2 - x1, wy = y2 - y1;
+    double l2 = idot2(wx, wy, wx, wy);
+    double t = idot2(ox - x1, oy - y1, wx, wy) / l2;
+    t = t < 1.0 ? t : 1.0;
+    t = t > 0.0 ? t : 0.0;
+    double px = x1 + t * wx, py = y1 + t * wy;
+    return idot2(ox - px, oy - py, ox - px, oy - py);
+}
+
+// the reference's verdict for the edge a -> new node: check_collision(node, theta, d) (rrt_07:1271-1276) ends the
+// segment at a + (cos, sin)(theta) * d, a few ulp from the new node itself
+__device__ __noinline__ bool near_edge_free_exact(double ax, double ay, double nx, double ny, double d, const ObsList &L) {
+    double s, c;
+    (void)crm_atan2_sincos(ny - ay, nx - ax, &s, &c);
+    return seg_free_lane(ax, ay, ax + c * d, ay + s * d, L);
+}
+
+// Same verdict without the trigonometry whenever it is certain: the segment a -> new node differs from the reference's
+// by a few ulp at one end, so |dd - size^2| above an error band decides; inside the band the exact form runs.
+// band_k = 1e-12 * (coordinate bound)^2.
+__device__ __forceinline__ bool near_edge_free(double ax, double ay, double nx, double ny, double d, double band_k,
+                                               const ObsList &L) {
+    bool hit = false, unsure = !(d > 1e-9);
+    for (int j = 0; j < L.m; j++) {
+        const double r2 = L.r2[j * L.stride];
+        const double dd = seg_dd(ax, ay, nx, ny, L.ox[j * L.stride], L.oy[j * L.stride]);
+        hit |= dd <= r2;
+        unsure |= fabs(dd - r2) <= band_k + 1e-12 * (dd + r2);
+    }
+    if (unsure) return near_edge_free_exact(ax, ay, nx, ny, d, L);
+    return !hit;
+}
+
 struct InfWarpSmem {
     double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];
 };
@@ -95,6 +131,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
         __syncwarp();
         int n = 1, status = RRTK_Q_OK, plen_best = 0;
         double c_best = INF;
+        const double band_k = 1e-12 * p.coord_bound * p.coord_bound;
         const double c_min = crm_hypot(sx - gx, sy - gy);
         const double xc = (sx + gx) / 2.0, yc = (sy + gy) / 2.0;
 
@@ -177,9 +214,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 const double2 a = xy[i];
                 const double dx = nx - a.x, dy = ny - a.y;
                 const double dd = crm_hypot(dx, dy);
-                double s2, c2;
-                (void)crm_atan2_sincos(dy, dx, &s2, &c2);
-                if (seg_free_lane(a.x, a.y, a.x + c2 * dd, a.y + s2 * dd, L)) {
+                if (near_edge_free(a.x, a.y, nx, ny, dd, band_k, L)) {
                     const double c = cost[i] + dd;
                     if (c < mc) { mc = c; bk = k; bnode = i; }
                 }
@@ -208,9 +243,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                     const double dd = crm_hypot(a.x - nx, a.y - ny);
                     const double sc = ncost + dd;
                     if (cost[i] > sc) {
-                        double s2, c2;
-                        (void)crm_atan2_sincos(ny - a.y, nx - a.x, &s2, &c2);
-                        if (seg_free_lane(a.x, a.y, a.x + c2 * dd, a.y + s2 * dd, L)) {
+                        if (near_edge_free(a.x, a.y, nx, ny, dd, band_k, L)) {
                             parent[i] = newi;
                             cost[i] = sc;
                         }

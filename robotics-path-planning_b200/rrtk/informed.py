@@ -76,6 +76,10 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples,
     p = _lib.InformedParams()
     p.n_queries, p.max_iter, p.node_cap, p.obs_stride, p.path_cap = q, max_iter, cap, stride, path_cap
     p.expand_dis = float(expand_dis)
+    fs = np.asarray(free_samples, dtype=np.float64)
+    bound = max(float(np.abs(starts).max()), float(np.abs(goals).max()), float(np.abs(fs).max()) if fs.size else 0.0,
+                float(np.abs(rows[:, :, :3]).max()) if rows.size else 0.0, 1.0)
+    p.coord_bound = 2.0 * bound + 4.0 * float(expand_dis)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     with torch.cuda.device(dev):
         d_sg, d_rot, d_obs, d_cnt = t(np.hstack([starts, goals])), t(rot), t(rows), t(counts)
