@@ -51,6 +51,7 @@ constexpr int TREE_OBS_CAP = 512;   // circles staged in shared memory
 constexpr int TREE_TAB_BITS = 18;   // hash set of d^2 bit patterns: 2 tables x 2^18 x 8 B
 constexpr unsigned long long TREE_EMPTY = ~0ull;
 constexpr int TREE_PROBES = 64;
+constexpr int TREE_UNROLL = 2;      // node chunks in flight per thread in the scan (code size vs latency hiding)
 constexpr int TREE_REC_PIECES = 8;
   // 128 bytes per record, 5 pieces used
 
@@ -328,6 +329,58 @@ __device__ __noinline__ void extend_candidate(const TreeSmem &S, int n_obs, doub
     cf = (he ? CF_BLOCKED : 0) | (near_goal ? CF_NEAR_GOAL : 0) | (hg ? CF_GOAL_BLOCKED : 0);
 }
 
+// Exact `.index()` resolution when two hits at different positions have a bit-equal d^2 (rare): every CTA publishes
+// its hit list, each hit looks for a lower-index hit with the same d^2 (-> shadowed), the best-parent partials are
+// recomputed and exchanged again.
+__device__ __noinline__ void resolve_equal_d2(TreeSmem &S, const TreeArgs &A, const TreeWs &ws, unsigned long long &bphase,
+                                             unsigned &seq, int G, int H, long long seg, double nx, double ny, Winner &W) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    const double INF = CUDART_INF;
+    {
+            for (int e = tid; e < H; e += TREE_T) {
+                const bool in_s = e < TREE_HCAP;
+                const int i = (in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP))) & HIT_MASK;
+                double ax, ay;
+                if (in_s) { ax = S.hit_x[e]; ay = S.hit_y[e]; } else { const double2 a = ld_xy(A.xy + i); ax = a.x; ay = a.y; }
+                const double qx = ax - nx, qy = ay - ny;
+                __stcg(ws.g_idx + seg + e, i);
+                __stcg(ws.g_d2 + seg + e, qx * qx + qy * qy);
+            }
+            if (tid == 0) __stcg(ws.g_cnt + cta, H);
+            grid_barrier(ws, bphase, G);
+            double cc = INF;
+            int ci = NO_IDX;
+            for (int e = tid; e < H; e += TREE_T) {
+                const bool in_s = e < TREE_HCAP;
+                int tag = in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
+                const int i = tag & HIT_MASK;
+                const double d2 = ld_f64(ws.g_d2 + seg + e);
+                bool shadow = false;
+                for (int c2 = 0; c2 < G && !shadow; c2++) {
+                    const int cnt = ld_i32(ws.g_cnt + c2);
+                    const long long s2 = (long long)c2 * ws.seg_cap;
+                    for (int k = 0; k < cnt; k++)
+                        if (ld_i32(ws.g_idx + s2 + k) < i && ld_f64(ws.g_d2 + s2 + k) == d2) { shadow = true; break; }
+                }
+                if (shadow) tag |= HIT_SHADOW;
+                if (in_s) S.hit_tag[e] = tag; else __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
+                if (!(tag & HIT_SHADOW) && (tag & HIT_FREE)) {
+                    const double d = in_s ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP));
+                    const double c_i = in_s ? S.hit_c[e] : ld_f64(ws.sp_c + seg + (e - TREE_HCAP));
+                    lexmin(cc, ci, c_i + d, i);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1)
+                lexmin(cc, ci, __shfl_xor_sync(0xffffffffu, cc, off), __shfl_xor_sync(0xffffffffu, ci, off));
+            if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = 0; S.w_hs[warp] = 0; }
+            if (tid == 0) { S.c_d2 = INF; S.c_idx = NO_IDX; S.c_nx = 0.0; S.c_ny = 0.0; S.c_cf = 0; }
+            __syncthreads();
+            const Winner W2 = exchange(S, ws, seq, G);
+            W.cp_cost = W2.cp_cost; W.cp_idx = W2.cp_idx;
+    }
+}
+
 __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs A) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     TreeSmem &S = *reinterpret_cast<TreeSmem *>(smem_raw);
@@ -339,7 +392,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
     const double sx = A.p.start_goal[0], sy = A.p.start_goal[1], gx = A.p.start_goal[2], gy = A.p.start_goal[3];
     const int n_obs = A.p.n_obs;
     const double band_k = 1e-12 * A.p.coord_bound * A.p.coord_bound;
-    const long long stride = (long long)G * TREE_T;
+    const int stride = G * TREE_T;   // nodes per ownership round
     const long long seg = (long long)cta * ws.seg_cap;
 
     for (int j = tid; j < n_obs; j += TREE_T) S.obs[j] = A.obstacles[j];
@@ -404,19 +457,19 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
         int bi = NO_IDX, myhits = 0;
         if (r2 >= 0.0 || want_nn) {
             int chunk = 0;
-            for (long long base = (long long)cta * TREE_T + tid; base < n; base += 4 * stride, chunk += 4) {
-                double2 a[4];
-                bool ok[4];
+            for (long long base = (long long)cta * TREE_T + tid; base < n; base += (long long)TREE_UNROLL * stride, chunk += TREE_UNROLL) {
+                double2 a[TREE_UNROLL];
+                bool ok[TREE_UNROLL];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const long long i = base + u * stride;
+                for (int u = 0; u < TREE_UNROLL; u++) {
+                    const long long i = base + (long long)u * stride;
                     ok[u] = i < n;
                     a[u] = ok[u] ? ld_xy(A.xy + i) : make_double2(0.0, 0.0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < TREE_UNROLL; u++) {
                     if (!ok[u]) continue;
-                    const int i = (int)(base + u * stride);
+                    const int i = (int)(base + (long long)u * stride);
                     const double ax = a[u].x - nx, ay = a[u].y - ny;
                     if (ax * ax + ay * ay <= r2) {
                         myhits++;
@@ -536,47 +589,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
         // ---- slow path: equal d^2 at different positions -> exact shadow flags from the global hit list ----
         if (flags & FLAG_EQ_D2) {
             n_slow++;
-            for (int e = tid; e < H; e += TREE_T) {
-                const bool in_s = e < TREE_HCAP;
-                const int i = (in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP))) & HIT_MASK;
-                double ax, ay;
-                if (in_s) { ax = S.hit_x[e]; ay = S.hit_y[e]; } else { const double2 a = ld_xy(A.xy + i); ax = a.x; ay = a.y; }
-                const double qx = ax - nx, qy = ay - ny;
-                __stcg(ws.g_idx + seg + e, i);
-                __stcg(ws.g_d2 + seg + e, qx * qx + qy * qy);
-            }
-            if (tid == 0) __stcg(ws.g_cnt + cta, H);
-            grid_barrier(ws, bphase, G);
-            double cc = INF;
-            int ci = NO_IDX;
-            for (int e = tid; e < H; e += TREE_T) {
-                const bool in_s = e < TREE_HCAP;
-                int tag = in_s ? S.hit_tag[e] : ld_i32(ws.sp_idx + seg + (e - TREE_HCAP));
-                const int i = tag & HIT_MASK;
-                const double d2 = ld_f64(ws.g_d2 + seg + e);
-                bool shadow = false;
-                for (int c2 = 0; c2 < G && !shadow; c2++) {
-                    const int cnt = ld_i32(ws.g_cnt + c2);
-                    const long long s2 = (long long)c2 * ws.seg_cap;
-                    for (int k = 0; k < cnt; k++)
-                        if (ld_i32(ws.g_idx + s2 + k) < i && ld_f64(ws.g_d2 + s2 + k) == d2) { shadow = true; break; }
-                }
-                if (shadow) tag |= HIT_SHADOW;
-                if (in_s) S.hit_tag[e] = tag; else __stcg(ws.sp_idx + seg + (e - TREE_HCAP), tag);
-                if (!(tag & HIT_SHADOW) && (tag & HIT_FREE)) {
-                    const double d = in_s ? S.hit_d[e] : ld_f64(ws.sp_d + seg + (e - TREE_HCAP));
-                    const double c_i = in_s ? S.hit_c[e] : ld_f64(ws.sp_c + seg + (e - TREE_HCAP));
-                    lexmin(cc, ci, c_i + d, i);
-                }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1)
-                lexmin(cc, ci, __shfl_xor_sync(0xffffffffu, cc, off), __shfl_xor_sync(0xffffffffu, ci, off));
-            if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = 0; S.w_hs[warp] = 0; }
-            if (tid == 0) { S.c_d2 = INF; S.c_idx = NO_IDX; S.c_nx = 0.0; S.c_ny = 0.0; S.c_cf = 0; }
-            __syncthreads();
-            const Winner W2 = exchange(S, ws, seq, G);
-            W.cp_cost = W2.cp_cost; W.cp_idx = W2.cp_idx;
+            resolve_equal_d2(S, A, ws, bphase, seq, G, H, seg, nx, ny, W);
         }
 
         // ---- apply: parent choice, append, rewire (rrt_07:1232-1246) ----
