@@ -377,6 +377,23 @@ def main():
                    paths_found=found, mean_nodes=float(n_nodes.mean()))
         if not args.no_extras:
             out["extras"] = extras(torch, dev)
+            try:   # path_smoothing (rrt_04:1447-1479) of the 4096 final courses, on the device
+                from rrtk import smoothing
+                sm_iters = 1000
+                sp, sl = res.paths_device(64 + sm_iters)
+                obs3 = batch.obstacles[:, :, :3].contiguous()          # robot_radius = 0: column 2 is the size
+                draws = torch.rand((len(qids), sm_iters, 2), dtype=torch.float64, device=dev)
+                len0 = float(sl.double().mean().item())
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                st, _ = smoothing.smooth_batch(sp, sl, sm_iters, obs3, batch.n_obs, draws)
+                b.record()
+                torch.cuda.synchronize()
+                out["extras"]["path_smoothing"] = dict(paths=len(qids), iters=sm_iters, ms=a.elapsed_time(b),
+                                                       mean_points_before=len0, mean_points_after=float(sl.double().mean().item()),
+                                                       failed=int((st != 0).sum().item()))
+            except Exception as e:  # noqa: BLE001
+                out["extras"]["path_smoothing"] = dict(error=repr(e))
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(iters, n_obs)
             out["cpu_baseline_c"] = cpu_baseline_c(iters, n_obs)

@@ -49,6 +49,7 @@ extern "C" {
 #define RRTK_Q_NEAR_OVERFLOW 1 /* |near| exceeded near_cap; the query stopped at that iteration */
 #define RRTK_Q_NODE_OVERFLOW 2 /* tree reached node_cap */
 #define RRTK_Q_PATH_OVERFLOW 4 /* best path longer than path_cap (length is still reported) */
+#define RRTK_Q_DIV_ZERO 8      /* path smoothing: the reference would raise ZeroDivisionError at this iteration */
 
 /* sampler kinds (get_random_node / get_random_node_sobol, rrt_04:1132-1153) */
 #define RRTK_SAMPLER_STREAM 0  /* read (x, y) per iteration from `sample_stream` */
@@ -143,6 +144,19 @@ RRTK_API int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *s
 RRTK_API int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
                            const double *start_goal, const double *xy, const int32_t *parent,
                            const int32_t *goal_index, double *path, int32_t *path_len, void *stream);
+
+/* path_smoothing (rrt_04:1447-1479, with get_path_length :1390-1398, get_target_point :1401-1420 and
+ * line_collision_check :1423-1444) for Q paths at once, in place: random shortcutting of the final course.
+ *   path [Q][path_cap][2] in/out (goal -> start as generate_final_course returns it), path_len [Q] in/out (<= 512);
+ *   draws [Q][max_iter][2]: the unit uniforms behind the two `random.uniform(0, le)` calls of each iteration
+ *   (CPython evaluates uniform(a, b) as a + (b - a) * random());
+ *   obstacles3 [Q][obs_stride][3] = x, y, size (no robot radius: the reference passes obstacle_list as is); n_obs [Q];
+ *   status [Q]: RRTK_Q_PATH_OVERFLOW / RRTK_Q_DIV_ZERO bits; iters_done [Q].  A path can grow by one point per
+ *   accepted shortcut, so path_cap >= path_len + max_iter is always enough. */
+RRTK_API int rrtk_path_smoothing_dev(int32_t n_queries, int32_t path_cap, int32_t max_iter, double *path,
+                                     int32_t *path_len, const double *draws, const double *obstacles3,
+                                     int32_t obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
+                                     void *stream);
 
 /* The in-kernel samplers, exposed so a sample stream can be materialised (tests, CPU baseline):
  *   out [Q][max_iter][2]; uses p->sampler, seed, goal_sample_rate, min/max_rand, start_goal */

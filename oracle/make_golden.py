@@ -284,7 +284,43 @@ def _rand_arm_obs(seed, n=5):
             zip(rng.uniform(-2, 2, (n, 2)), rng.uniform(0.2, 0.7, n))]
 
 
+class _InjectedRandom:
+    """Stands in for the `random` module inside the reference namespace: uniform(a, b) = a + (b - a) * next draw,
+    which is CPython's own formula, so the reference consumes a recorded stream."""
+
+    def __init__(self, draws):
+        self.it = iter(draws)
+
+    def uniform(self, a, b):
+        return a + (b - a) * next(self.it)
+
+
+def run_smoothing(name, src_fixture, max_iter, seed, obstacle_list=None):
+    """path_smoothing (rrt_04:1447-1479) of the final course of an existing rrt_04 fixture."""
+    ns = ref_loader.load("rrt_04")
+    g = np.load(os.path.join(GOLDEN, src_fixture + ".npz"))
+    m = json.loads(str(g["meta"]))
+    path = [[float(x), float(y)] for x, y in g["path"]]
+    obs = [tuple(float(v) for v in o) for o in (obstacle_list if obstacle_list is not None else m["obstacle_list"])]
+    rng = np.random.default_rng(seed)
+    draws = rng.random((max_iter, 2))
+    ns["random"] = _InjectedRandom(draws.ravel().tolist())
+    with ref_loader.quiet():
+        out = ns["path_smoothing"]([list(pt) for pt in path], max_iter, obs)
+    meta = dict(source=src_fixture, max_iter=max_iter, obstacle_list=[list(o) for o in obs])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), path_in=np.array(path),
+                        draws=draws, path_out=np.array(out, dtype=np.float64),
+                        length_in=ns["get_path_length"](path), length_out=ns["get_path_length"](out))
+    print(f"{name}: {len(path)} -> {len(out)} points, length {ns['get_path_length'](path):.6f} -> "
+          f"{ns['get_path_length'](out):.6f}")
+
+
 CASES = {
+    "smooth_c1_sobol_1000": lambda: run_smoothing("smooth_c1_sobol_1000", "rrt04_c1_sobol_500", 1000, 31),
+    "smooth_c1_sobol2000_300": lambda: run_smoothing("smooth_c1_sobol2000_300", "rrt04_c1_sobol_2000", 300, 32),
+    "smooth_c1_uniform_1000": lambda: run_smoothing("smooth_c1_uniform_1000", "rrt04_c1_uniform_500", 1000, 33),
+    "smooth_c2_o256_500": lambda: run_smoothing("smooth_c2_o256_500", "rrt04_c2_o256_2000", 500, 34),
+    "smooth_c2_o64_free_200": lambda: run_smoothing("smooth_c2_o64_free_200", "rrt04_c2_o64_600", 200, 35, obstacle_list=[]),
     "rrt05_builtin_500": lambda: run_rrt05("rrt05_builtin_500", C5D, 1),
     "rrt05_builtin_1500": lambda: run_rrt05("rrt05_builtin_1500", dict(C5D, max_iter=1500), 2),
     "rrt05_loose_goal_800": lambda: run_rrt05("rrt05_loose_goal_800", dict(

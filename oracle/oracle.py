@@ -282,3 +282,19 @@ def dubins_final_course(res, start, goal, curvature, math_mode):
         i = int(res["parent"][i])
     path.append([float(start[0]), float(start[1])])
     return path
+
+
+def path_smoothing(path, draws, obstacle_list, cap=None):
+    """rrt_04:1447-1479 with injected uniform draws -> (path list, status: 0 ok, 1 = reference raises ZeroDivisionError)."""
+    path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, 2)
+    draws = np.ascontiguousarray(draws, dtype=np.float64).reshape(-1, 2)
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    cap = cap or (path.shape[0] + draws.shape[0] + 2)
+    buf = np.zeros((cap, 2))
+    buf[:path.shape[0]] = path
+    n = C.c_int32(path.shape[0]); done = C.c_int32()
+    L = lib()
+    L.orc_path_smoothing.restype = C.c_int
+    rc = L.orc_path_smoothing(_p(buf, C.c_double), C.byref(n), cap, _p(draws, C.c_double), draws.shape[0],
+                              _p(obs, C.c_double), obs.shape[0], C.byref(done))
+    return buf[:n.value].tolist(), rc

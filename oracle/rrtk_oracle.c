@@ -692,6 +692,75 @@ ORC_EXPORT int orc_informed_run(const orc_informed_params_t *p, const double *ob
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* path smoothing (rrt_04:1390-1479): random shortcutting of the final course             */
+/* ------------------------------------------------------------------------------------ */
+static double sm_path_length(const double *path, int len) { /* rrt_04:1390-1398 */
+    double le = 0.0;
+    for (int i = 0; i + 1 < len; i++) le += orc_hypot(path[2 * (i + 1)] - path[2 * i], path[2 * (i + 1) + 1] - path[2 * i + 1]);
+    return le;
+}
+/* get_target_point (rrt_04:1401-1420), ti = i - 1 quirk included; returns 0, or 1 for the reference's ZeroDivisionError */
+static int sm_target_point(const double *path, int len, double target, double *x, double *y, int *ti_out) {
+    double le = 0.0, last = 0.0;
+    int ti = 0;
+    for (int i = 0; i + 1 < len; i++) {
+        double d = orc_hypot(path[2 * (i + 1)] - path[2 * i], path[2 * (i + 1) + 1] - path[2 * i + 1]);
+        le += d;
+        if (le >= target) { ti = i - 1; last = d; break; }
+    }
+    if (last == 0.0) return 1;
+    double ratio = (le - target) / last;
+    int a = ti < 0 ? len + ti : ti; /* Python negative index */
+    *x = path[2 * a] + (path[2 * (ti + 1)] - path[2 * a]) * ratio;
+    *y = path[2 * a + 1] + (path[2 * (ti + 1) + 1] - path[2 * a + 1]) * ratio;
+    *ti_out = ti;
+    return 0;
+}
+/* path [cap][2] in/out, *len in/out; draws [max_iter][2] in [0,1); obs [n_obs][3] = x, y, size.
+ * returns 0, 1 = the reference would raise ZeroDivisionError (path as of that iteration), 2 = cap too small */
+ORC_EXPORT int orc_path_smoothing(double *path, int32_t *len_io, int32_t cap, const double *draws, int32_t max_iter,
+                                  const double *obs, int32_t n_obs, int32_t *iters_done) {
+    int len = *len_io;
+    double *tmp = (double *)malloc(sizeof(double) * 2 * (size_t)cap);
+    double le = sm_path_length(path, len);
+    int rc = 0, it = 0;
+    for (it = 0; it < max_iter; it++) {
+        double p0 = 0 + (le - 0) * draws[2 * it], p1 = 0 + (le - 0) * draws[2 * it + 1];
+        if (p1 < p0) { double t = p0; p0 = p1; p1 = t; }
+        double fx, fy, sx, sy;
+        int t1, t2;
+        if (sm_target_point(path, len, p0, &fx, &fy, &t1) || sm_target_point(path, len, p1, &sx, &sy, &t2)) { rc = 1; break; }
+        if (t1 <= 0 || t2 <= 0) continue;
+        if (t2 + 1 > len) continue;
+        if (t2 == t1) continue;
+        /* line_collision_check rrt_04:1423-1444 */
+        double a = sy - fy, b = -(sx - fx), c = sy * (sx - fx) - sx * (sy - fy);
+        int ok = 1;
+        for (int o = 0; o < n_obs && ok; o++) {
+            double h = orc_hypot(a, b);
+            if (h == 0.0) { rc = 1; ok = -1; break; }
+            double d = fabs(a * obs[3 * o] + b * obs[3 * o + 1] + c) / h;
+            if (d <= obs[3 * o + 2]) ok = 0;
+        }
+        if (ok < 0) break;
+        if (!ok) continue;
+        int nl = (t1 + 1) + 2 + (len - t2 - 1);
+        if (nl > cap) { rc = 2; break; }
+        memcpy(tmp, path, sizeof(double) * 2 * (size_t)(t1 + 1));
+        tmp[2 * (t1 + 1)] = fx; tmp[2 * (t1 + 1) + 1] = fy;
+        tmp[2 * (t1 + 2)] = sx; tmp[2 * (t1 + 2) + 1] = sy;
+        memcpy(tmp + 2 * (t1 + 3), path + 2 * (t2 + 1), sizeof(double) * 2 * (size_t)(len - t2 - 1));
+        memcpy(path, tmp, sizeof(double) * 2 * (size_t)nl);
+        len = nl;
+        le = sm_path_length(path, len);
+    }
+    *len_io = len;
+    *iters_done = it;
+    free(tmp);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Dubins local planner (rrt_05:935-1278 == dub00)                                       */
 /* ------------------------------------------------------------------------------------ */
 #define ORC_TWO_PI 6.283185307179586 /* 2 * math.pi */

@@ -60,6 +60,9 @@ int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obsta
                          double *path, rrtk_informed_tree_result *res, void *workspace, size_t workspace_bytes,
                          cudaStream_t s);
 int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *workspace, size_t workspace_bytes, cudaStream_t s);
+int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
+                        const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
+                        cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -255,6 +258,18 @@ int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_extract_paths(n_queries, node_cap, path_cap, start_goal, xy, parent, goal_index, path,
                                 path_len, (cudaStream_t)stream);
+}
+
+int rrtk_path_smoothing_dev(int32_t n_queries, int32_t path_cap, int32_t max_iter, double *path, int32_t *path_len,
+                            const double *draws, const double *obstacles3, int32_t obs_stride, const int32_t *n_obs,
+                            int32_t *status, int32_t *iters_done, void *stream) {
+    if (n_queries < 0 || path_cap < 1 || max_iter < 0 || obs_stride < 0) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (n_queries == 0) return RRTK_OK;
+    if (!path || !path_len || !status || !iters_done || (max_iter > 0 && !draws) || (n_obs && obs_stride > 0 && !obstacles3))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)path & 15) return set_error(RRTK_ERR_INVALID, "path must be 16-byte aligned");
+    return launch_smooth_paths(n_queries, path_cap, max_iter, path, path_len, draws, obstacles3, obs_stride, n_obs, status,
+                               iters_done, (cudaStream_t)stream);
 }
 
 int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRTK_LIB", os.path.join(HERE, "librrtk.so"))  # override: tuning builds only
 
 SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
-Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW = 0, 1, 2, 4
+Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW, Q_DIV_ZERO = 0, 1, 2, 4, 8
 
 
 class RrtkError(RuntimeError):
@@ -80,6 +80,7 @@ _SIGS = {
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
+    "rrtk_path_smoothing_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
