@@ -441,6 +441,29 @@ def extras(torch, dev):
         del grid
     except Exception as e:  # noqa: BLE001
         out["c5_arm_grid"] = dict(error=repr(e))
+    try:   # astar_torus (arm02:113-184) over 64 occupancy grids of the 2-link arm, M = 512, grid -> route on the GPU
+        M, S = 512, 64
+        rng = np.random.default_rng(15)
+        ang, rad = rng.uniform(0, 2 * math.pi, (S, 5)), rng.uniform(0.9, 2.0, (S, 5))
+        sets = np.stack([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(0.15, 0.45, (S, 5))], axis=2)
+        grids = A.occupancy_grids_device([1.0, 1.0], sets, M)
+        host = grids.cpu().numpy()
+        st, gl = [], []
+        for k in range(S):
+            free = np.argwhere(host[k] == 0)
+            st.append(free[rng.integers(len(free))]); gl.append(free[rng.integers(len(free))])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        routes, rlen, expanded = A.astar_torus_batch(grids, np.array(st), np.array(gl))
+        b.record()
+        torch.cuda.synchronize()
+        out["astar_torus"] = dict(M=M, queries=S, ms=a.elapsed_time(b), routes_found=int((rlen > 0).sum().item()),
+                                  mean_route_cells=float(rlen.double().mean().item()),
+                                  cells_expanded=int(expanded.sum().item()))
+        del grids, routes
+    except Exception as e:  # noqa: BLE001
+        out["astar_torus"] = dict(error=repr(e))
     try:   # Dubins steering primitive: 262144 edges among 16 circles
         n = 1 << 18
         rng = np.random.default_rng(6)

@@ -335,6 +335,21 @@ RRTK_API int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int
                                int32_t n_obs, uint8_t *grid, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * astar_torus (arm02:113-184, with calc_heuristic_map :221-233 and find_neighbors :187-209) for Q queries at once:
+ * the reference's greedy best-first search on the M x M joint-space torus, same expansion order (smallest
+ * heuristic, ties to the smallest row-major index), same route, same marks left in the grid.
+ *   start_goal [Q][4] int32 = start row, start col, goal row, goal col
+ *   grids [Q][M][M] uint8 in/out: 0 free, 1 occupied on entry; on return 2 expanded, 3 frontier, 4 start, 5 goal,
+ *         6 route (what the reference leaves in `grid`)
+ *   routes [Q][route_cap][2] int32: cells from start to goal; route_len [Q] (0 = "No route found", negative = the
+ *         route has -route_len cells and did not fit); expanded [Q] = cells expanded
+ *   scratch (device): heur [Q][M*M] int32, parents [Q][M*M] int32, heaps [Q][M*M + 8] uint64
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_astar_torus_dev(int32_t M, int32_t n_queries, const int32_t *start_goal, uint8_t *grids,
+                                  int32_t *routes, int32_t route_cap, int32_t *route_len, int32_t *expanded,
+                                  int32_t *heur, int32_t *parents, uint64_t *heaps, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)

@@ -315,7 +315,45 @@ def run_smoothing(name, src_fixture, max_iter, seed, obstacle_list=None):
           f"{ns['get_path_length'](out):.6f}")
 
 
+class _Dummy:
+    """Absorbs any attribute access / call (matplotlib stand-in for astar_torus' drawing loop)."""
+
+    def __getattr__(self, name):
+        return self
+
+    def __call__(self, *a, **k):
+        return self
+
+
+def run_astar(name, src_fixture, start, goal):
+    """astar_torus (arm02:113-233) of the unmodified reference on the occupancy grid of an arm02 fixture."""
+    ns = ref_loader.load("arm02")
+    g = np.load(os.path.join(GOLDEN, src_fixture + ".npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    grid = np.unpackbits(g["grid_bits"])[:shape[0] * shape[1]].reshape(shape).astype(np.int64)
+    ns["M"] = shape[0]
+    ns["plt"] = _Dummy()
+    ns["from_levels_and_colors"] = lambda *a, **k: (None, None)
+    work = grid.copy()
+    with ref_loader.quiet():
+        route = ns["astar_torus"](work, tuple(start), tuple(goal))
+        hmap = ns["calc_heuristic_map"](shape[0], tuple(goal))
+    meta = dict(source=src_fixture, M=shape[0], start=list(start), goal=list(goal))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta),
+                        route=np.array([[int(a), int(b)] for a, b in route], dtype=np.int64).reshape(-1, 2),
+                        grid_after=work.astype(np.uint8), heuristic=np.asarray(hmap, dtype=np.int64))
+    print(f"{name}: M={shape[0]}, route of {len(route)} cells, {int((work == 2).sum())} expanded")
+
+
 CASES = {
+    "astar_script_m100": lambda: run_astar("astar_script_m100", "arm02_script_m100", (10, 50), (58, 56)),   # arm02:309-310
+    "astar_script_m100_b": lambda: run_astar("astar_script_m100_b", "arm02_script_m100", (95, 3), (40, 80)),
+    "astar_2link_m100": lambda: run_astar("astar_2link_m100", "arm02_2link_m100", (10, 50), (58, 56)),
+    "astar_rand_m51": lambda: run_astar("astar_rand_m51", "arm02_script_m51_rand", (2, 2), (30, 44)),
+    "astar_3link_m64_enclosed": lambda: run_astar("astar_3link_m64_enclosed", "arm02_3link_m64_rand", (1, 62), (60, 3)),
+    "astar_rand_m51_wrap2": lambda: run_astar("astar_rand_m51_wrap2", "arm02_script_m51_rand", (15, 42), (42, 35)),
+    "astar_2link_m100_wrap": lambda: run_astar("astar_2link_m100_wrap", "arm02_2link_m100", (88, 23), (96, 54)),
+    "astar_same_cell": lambda: run_astar("astar_same_cell", "arm02_script_m51_rand", (7, 9), (7, 9)),
     "smooth_c1_sobol_1000": lambda: run_smoothing("smooth_c1_sobol_1000", "rrt04_c1_sobol_500", 1000, 31),
     "smooth_c1_sobol2000_300": lambda: run_smoothing("smooth_c1_sobol2000_300", "rrt04_c1_sobol_2000", 300, 32),
     "smooth_c1_uniform_1000": lambda: run_smoothing("smooth_c1_uniform_1000", "rrt04_c1_uniform_500", 1000, 33),

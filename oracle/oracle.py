@@ -298,3 +298,29 @@ def path_smoothing(path, draws, obstacle_list, cap=None):
     rc = L.orc_path_smoothing(_p(buf, C.c_double), C.byref(n), cap, _p(draws, C.c_double), draws.shape[0],
                               _p(obs, C.c_double), obs.shape[0], C.byref(done))
     return buf[:n.value].tolist(), rc
+
+
+def astar_torus(grid, start, goal, cap=None):
+    """arm02:113-184 -> (route [n, 2] int32 start -> goal (empty = none), final grid uint8 with the 2..6 marks)."""
+    g = np.ascontiguousarray(np.asarray(grid), dtype=np.uint8).copy()
+    M = g.shape[0]
+    cap = cap or M * M
+    route = np.zeros((cap, 2), dtype=np.int32)
+    L = lib()
+    L.orc_astar_torus.restype = C.c_int
+    n = L.orc_astar_torus(_p(g, C.c_uint8), M, int(start[0]), int(start[1]), int(goal[0]), int(goal[1]),
+                          _p(route, C.c_int32), cap)
+    return route[:max(n, 0)].copy(), g
+
+
+def astar_heuristic(M, goal):
+    out = np.zeros((M, M), dtype=np.int64)
+    lib().orc_astar_heuristic(M, int(goal[0]), int(goal[1]), _p(out, C.c_int64))
+    return out
+
+
+def astar_heuristic_closed(M, goal):
+    L = lib()
+    L.orc_astar_heuristic_closed.restype = C.c_int64
+    return np.array([[L.orc_astar_heuristic_closed(M, int(goal[0]), int(goal[1]), i, j) for j in range(M)]
+                     for i in range(M)], dtype=np.int64)

@@ -761,6 +761,100 @@ ORC_EXPORT int orc_path_smoothing(double *path, int32_t *len_io, int32_t cap, co
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* astar_torus (arm02:113-233): greedy best-first search on the joint-space torus         */
+/* ------------------------------------------------------------------------------------ */
+static int64_t at_orig(int M, int gi, int gj, int i, int j) { (void)M; return (int64_t)abs(j - gj) + (int64_t)abs(i - gi); }
+/* calc_heuristic_map (arm02:221-233): the value cell (i, j) ends with, in-place update order included */
+static int64_t at_new(int M, int gi, int gj, int i, int j, int depth) {
+    int64_t v = at_orig(M, gi, gj, i, j), t;
+    int64_t row0 = (i > 0 && depth == 0) ? at_new(M, gi, gj, 0, j, 1) : at_orig(M, gi, gj, 0, j);
+    int64_t col0 = (j > 0) ? at_new(M, gi, gj, i, 0, 2) : at_orig(M, gi, gj, i, 0);
+    if (depth == 2 && i > 0) row0 = at_new(M, gi, gj, 0, 0, 1); /* column-0 cell of a later row reads updated (0, 0) */
+    if (depth == 1) row0 = at_orig(M, gi, gj, 0, j);            /* a row-0 cell reads its own (original) value */
+    t = i + 1 + at_orig(M, gi, gj, M - 1, j); if (t < v) v = t;
+    t = M - i + row0; if (t < v) v = t;
+    t = j + 1 + at_orig(M, gi, gj, i, M - 1); if (t < v) v = t;
+    t = M - j + col0; if (t < v) v = t;
+    return v;
+}
+ORC_EXPORT void orc_astar_heuristic(int32_t M, int32_t gi, int32_t gj, int64_t *out) {
+    /* plain sequential restatement (the recursive closed form above is what the GPU uses; tests compare the two) */
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < M; j++) out[(size_t)i * M + j] = at_orig(M, gi, gj, i, j);
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < M; j++) {
+            int64_t v = out[(size_t)i * M + j], t;
+            t = i + 1 + out[(size_t)(M - 1) * M + j]; if (t < v) v = t;
+            t = M - i + out[j]; if (t < v) v = t;
+            t = j + 1 + out[(size_t)i * M + M - 1]; if (t < v) v = t;
+            t = M - j + out[(size_t)i * M]; if (t < v) v = t;
+            out[(size_t)i * M + j] = v;
+        }
+}
+ORC_EXPORT int64_t orc_astar_heuristic_closed(int32_t M, int32_t gi, int32_t gj, int32_t i, int32_t j) {
+    return at_new(M, gi, gj, i, j, 0);
+}
+static void at_push(uint64_t *heap, int *n, uint64_t key) {
+    int k = (*n)++;
+    while (k > 0) { int p = (k - 1) / 2; if (heap[p] <= key) break; heap[k] = heap[p]; k = p; }
+    heap[k] = key;
+}
+static void at_pop(uint64_t *heap, int *n) {
+    uint64_t key = heap[--(*n)];
+    int k = 0;
+    for (;;) {
+        int c = 2 * k + 1;
+        if (c >= *n) break;
+        if (c + 1 < *n && heap[c + 1] < heap[c]) c++;
+        if (heap[c] >= key) break;
+        heap[k] = heap[c]; k = c;
+    }
+    if (*n > 0) heap[k] = key;
+}
+/* grid [M][M] uint8 in/out (0 free, 1 occupied -> marks 2..6); route [cap][2] start -> goal; returns route length
+ * (0 = no route), or -1 if the route does not fit */
+ORC_EXPORT int orc_astar_torus(uint8_t *grid, int32_t M, int32_t si, int32_t sj, int32_t gi, int32_t gj, int32_t *route,
+                               int32_t cap) {
+    size_t cells = (size_t)M * M;
+    int64_t *h = (int64_t *)malloc(sizeof(int64_t) * cells);
+    int32_t *parent = (int32_t *)malloc(sizeof(int32_t) * cells);
+    uint64_t *heap = (uint64_t *)malloc(sizeof(uint64_t) * (cells + 8));
+    int nheap = 0, found = 0, s = si * M + sj, g = gi * M + gj;
+    orc_astar_heuristic(M, gi, gj, h);
+    for (size_t k = 0; k < cells; k++) parent[k] = -1;
+    grid[s] = 4; grid[g] = 5;
+    at_push(heap, &nheap, ((uint64_t)h[s] << 32) | (uint32_t)s);
+    for (;;) {
+        grid[s] = 4; grid[g] = 5;
+        if (nheap == 0) break;
+        int cur = (int)(heap[0] & 0xffffffffu);
+        if (cur == g) { found = 1; break; }
+        at_pop(heap, &nheap);
+        grid[cur] = 2;
+        int i = cur / M, j = cur % M;
+        int nb[4] = {(i - 1 >= 0 ? i - 1 : M - 1) * M + j, (i + 1 < M ? i + 1 : 0) * M + j,
+                     i * M + (j - 1 >= 0 ? j - 1 : M - 1), i * M + (j + 1 < M ? j + 1 : 0)};
+        for (int k = 0; k < 4; k++)
+            if (grid[nb[k]] == 0 || grid[nb[k]] == 5) {
+                at_push(heap, &nheap, ((uint64_t)h[nb[k]] << 32) | (uint32_t)nb[k]);
+                parent[nb[k]] = cur;
+                grid[nb[k]] = 3;
+            }
+    }
+    int len = 0;
+    if (found) {
+        for (int k = g; k >= 0; k = parent[k]) len++;
+        if (len > cap) len = -1;
+        else {
+            int w = len - 1;
+            for (int k = g; k >= 0; k = parent[k], w--) { route[2 * w] = k / M; route[2 * w + 1] = k % M; if (w >= 1) grid[k] = 6; }
+        }
+    }
+    free(h); free(parent); free(heap);
+    return len;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Dubins local planner (rrt_05:935-1278 == dub00)                                       */
 /* ------------------------------------------------------------------------------------ */
 #define ORC_TWO_PI 6.283185307179586 /* 2 * math.pi */

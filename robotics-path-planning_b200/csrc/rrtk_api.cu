@@ -63,6 +63,9 @@ int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *wo
 int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
                         const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
                         cudaStream_t s);
+int launch_astar_torus(int M, int n_queries, const int32_t *start_goal, uint8_t *grids, int32_t *heur, int32_t *parents,
+                       unsigned long long *heaps, int32_t *routes, int route_cap, int32_t *route_len, int32_t *expanded,
+                       cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -315,6 +318,17 @@ int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int32_t n_ro
     if (!theta || !link_lengths || !grid || (n_obs > 0 && !obstacles)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_arm_grid(M, theta, row0, n_rows, n_links, link_lengths, obstacles, n_sets, n_obs, grid,
                            (cudaStream_t)stream);
+}
+
+int rrtk_astar_torus_dev(int32_t M, int32_t n_queries, const int32_t *start_goal, uint8_t *grids, int32_t *routes,
+                         int32_t route_cap, int32_t *route_len, int32_t *expanded, int32_t *heur, int32_t *parents,
+                         uint64_t *heaps, void *stream) {
+    if (M < 1 || M > 46340 || n_queries < 0 || route_cap < 1) return set_error(RRTK_ERR_INVALID, "need 1 <= M <= 46340, route_cap >= 1");
+    if (n_queries == 0) return RRTK_OK;
+    if (!start_goal || !grids || !routes || !route_len || !expanded || !heur || !parents || !heaps)
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_astar_torus(M, n_queries, start_goal, grids, heur, parents, (unsigned long long *)heaps, routes, route_cap,
+                              route_len, expanded, (cudaStream_t)stream);
 }
 
 int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *out, void *stream) {

@@ -85,6 +85,7 @@ _SIGS = {
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_near_f32_dev": (C.c_int, [_VP, C.c_int64, C.c_float, C.c_float, C.c_float, _VP, C.c_int32, _VP, _VP]),
+    "rrtk_astar_torus_dev": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rrtk_fma_peak_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _VP, _VP]),
     "rrtk_arm_grid_dev": (C.c_int, [C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.c_int32,
                                     C.c_int32, _VP, _VP]),

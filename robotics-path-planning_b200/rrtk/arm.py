@@ -73,3 +73,49 @@ def get_occupancy_grid(arm, obstacles, M):
     """Drop-in for arm02:79-110: M x M numpy int array, 1 = collision."""
     obs = np.asarray(obstacles, dtype=np.float64).reshape(1, -1, 3)
     return get_occupancy_grids(arm, obs, M)[0]
+
+
+def astar_torus_batch(grids, starts, goals, route_cap=None):
+    """astar_torus (arm02:113-184) for Q queries on the GPU.  grids: uint8 CUDA tensor [Q, M, M] (0 free, 1 occupied),
+    updated in place with the reference's marks (2 expanded, 3 frontier, 4 start, 5 goal, 6 route); starts / goals [Q, 2]
+    (row, col).  Returns (routes [Q, route_cap, 2] int32, route_len [Q], expanded [Q]) device tensors."""
+    torch = _lib.require_cuda()
+    if grids.dtype != torch.uint8 or not grids.is_cuda or not grids.is_contiguous() or grids.dim() != 3:
+        raise _lib.RrtkError("astar_torus_batch: grids must be a contiguous uint8 CUDA tensor [Q, M, M]")
+    q, M = grids.shape[0], grids.shape[1]
+    dev = grids.device
+    sg = np.ascontiguousarray(np.hstack([np.asarray(starts, dtype=np.int32).reshape(q, 2),
+                                         np.asarray(goals, dtype=np.int32).reshape(q, 2)]))
+    if (sg < 0).any() or (sg >= M).any():
+        raise IndexError("start / goal cell outside the grid")
+    route_cap = M * M if route_cap is None else int(route_cap)
+    with torch.cuda.device(dev):
+        d_sg = torch.from_numpy(sg).to(dev)
+        routes = torch.zeros((q, route_cap, 2), dtype=torch.int32, device=dev)
+        rlen = torch.empty((q,), dtype=torch.int32, device=dev)
+        expanded = torch.empty((q,), dtype=torch.int32, device=dev)
+        heur = torch.empty((q, M * M), dtype=torch.int32, device=dev)
+        parents = torch.empty((q, M * M), dtype=torch.int32, device=dev)
+        heaps = torch.empty((q, M * M + 8), dtype=torch.int64, device=dev)
+        _lib.check(_lib.lib().rrtk_astar_torus_dev(M, q, d_sg.data_ptr(), grids.data_ptr(), routes.data_ptr(), route_cap,
+                                                   rlen.data_ptr(), expanded.data_ptr(), heur.data_ptr(),
+                                                   parents.data_ptr(), heaps.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream), "rrtk_astar_torus_dev")
+    return routes, rlen, expanded
+
+
+def astar_torus(grid, start_node, goal_node):
+    """Drop-in for arm02:113-184: returns the route as a list of (row, col) tuples from start to goal ([] if none) and
+    leaves the reference's marks in `grid` (a numpy array, modified in place)."""
+    torch = _lib.require_cuda()
+    g = np.asarray(grid)
+    d_grid = torch.from_numpy(np.ascontiguousarray(g, dtype=np.uint8)[None]).cuda()
+    routes, rlen, _ = astar_torus_batch(d_grid, [list(start_node)], [list(goal_node)])
+    n = int(rlen[0].item())
+    grid[...] = d_grid[0].cpu().numpy().astype(g.dtype)
+    if n == 0:
+        print("No route found.")
+        return []
+    route = [(int(a), int(b)) for a, b in routes[0, :n].cpu().numpy()]
+    print("The route found covers %d grid cells." % len(route))
+    return route
