@@ -295,7 +295,7 @@ typedef struct rrtk_dubins_params {
  * outputs: xy [Q][node_cap][2], yaw, cost, parent [Q][node_cap]; edge_from / edge_to [Q][node_cap][3]: the pose pair
  *   whose Dubins course is the node's path_x / path_y / path_yaw (rrtk_dubins_steer_dev regenerates it);
  *   n_nodes, iters_done, goal_index (-1 = none; index 0 counts as none like the reference), status [Q];
- *   scratch workspace [Q][node_cap] int32 */
+ *   scratch workspace [Q][4][node_cap] int32, 16-byte aligned (children lists + propagation frontier) */
 RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6,
                                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
                                          const double *stream3, double *xy, double *yaw, double *cost,

@@ -68,39 +68,6 @@ static __device__ __noinline__ ObsList cull_obstacles(const double4 *obs, int n_
     return L;
 }
 
-// propagate_cost_to_leaves (rrt_04:1379-1384): level-synchronous sweeps over the parent array.
-// nchild[] (children per node, maintained on append / re-parent) prunes the work: a childless root
-// costs nothing, and the sweeps stop as soon as no node updated in the last level has children.
-static __device__ __noinline__ void propagate(int root, int n, double2 *xy, double *cost, const int32_t *parent,
-                                       const int32_t *nchild, uint32_t *cur, uint32_t *nxt, int words, int lane) {
-    if (nchild[root] == 0) return;
-    for (int w = lane; w < words; w += 32) { cur[w] = 0u; nxt[w] = 0u; }
-    __syncwarp();
-    if (lane == 0) cur[root >> 5] = 1u << (root & 31);
-    __syncwarp();
-    for (;;) {
-        bool more = false;
-#pragma unroll 1
-        for (int c = lane; c < n; c += 32) {
-            int p = parent[c];
-            if (p >= 0 && ((cur[p >> 5] >> (p & 31)) & 1u)) {
-                double2 a = xy[p], b = xy[c];
-                cost[c] = cost[p] + crm_hypot(b.x - a.x, b.y - a.y);
-                if (nchild[c] > 0) {
-                    atomicOr(&nxt[c >> 5], 1u << (c & 31));
-                    more = true;
-                }
-            }
-        }
-        more = __any_sync(FULL, more);
-        __syncwarp();
-        if (!more) break;
-        for (int w = lane; w < words; w += 32) { cur[w] = nxt[w]; nxt[w] = 0u; }
-        __syncwarp();
-    }
-}
-
-
 // ---- obstacle cell grid (rrtk_rrtstar_params.grid_*): per cell the circles that can pass the cull test of ANY point
 // of the cell.  cnt[cell] counts them (more than GRID_CELL_CAP = the cell overflowed: callers scan all circles),
 // lists[cell][k] holds their indices.  Built once per query by its warp; read with ld.cg (the counts are bumped by

@@ -21,9 +21,9 @@ namespace rrtk {
 constexpr int DUB_WARPS_PER_CTA = 4;
 
 __host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap) {
-    size_t words = (size_t)(node_cap + 31) / 32;
-    // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | 2 bitsets
-    size_t b = (size_t)near_cap * (4 + 4 + 8 + 24) + words * 4 * 2;
+    (void)node_cap;
+    // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | frontier length of propagate_lists
+    size_t b = (size_t)near_cap * (4 + 4 + 8 + 24) + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -37,14 +37,12 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int near_cap = p.near_cap;
-    const int words = (p.node_cap + 31) / 32;
     unsigned char *base = smem_raw + (size_t)(threadIdx.x >> 5) * dub_warp_smem_bytes(near_cap, p.node_cap);
     double *nd = reinterpret_cast<double *>(base);
     double *s_end = nd + near_cap;  // [near_cap][3]
     int *near_idx = reinterpret_cast<int *>(s_end + 3 * near_cap);
     int *flags = near_idx + near_cap;
-    uint32_t *bits_cur = reinterpret_cast<uint32_t *>(flags + near_cap);
-    uint32_t *bits_nxt = bits_cur + words;
+    int *qtail = flags + near_cap;
     const double INF = CUDART_INF;
     const double kappa = p.curvature, step = p.step_size;
 
@@ -63,10 +61,10 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
         int32_t *parent = parent_all + (size_t)q * p.node_cap;
         double *efrom = edge_from_all + (size_t)q * p.node_cap * 3;
         double *eto = edge_to_all + (size_t)q * p.node_cap * 3;
-        int32_t *nchild = workspace + (size_t)q * p.node_cap;
+        int4 *links = reinterpret_cast<int4 *>(workspace + (size_t)q * 4 * p.node_cap);   // children lists (rrtk_planner.cuh)
         const double *stream = stream3 + (size_t)q * p.max_iter * 3;
         if (lane == 0) {
-            xy[0] = make_double2(sx, sy); yaw[0] = syaw; cost[0] = 0.0; parent[0] = -1; nchild[0] = 0;
+            xy[0] = make_double2(sx, sy); yaw[0] = syaw; cost[0] = 0.0; parent[0] = -1; links[0] = make_int4(-1, -1, -1, 0);
             for (int k = 0; k < 3; k++) { efrom[k] = 0.0; eto[k] = 0.0; }
         }
         __syncwarp();
@@ -167,8 +165,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         efrom[3 * newi] = b.x; efrom[3 * newi + 1] = b.y; efrom[3 * newi + 2] = yaw[best];
                         eto[3 * newi] = nx; eto[3 * newi + 1] = ny; eto[3 * newi + 2] = nyaw;
                         xy[newi] = make_double2(cx, cy); yaw[newi] = cyaw; cost[newi] = mc; parent[newi] = best;
-                        nchild[newi] = 0;
-                        nchild[best]++;
+                        links[newi] = make_int4(-1, -1, -1, 0);
+                        link_child(links, best, newi);
                     }
                     n++;
                     truthy = true;
@@ -201,8 +199,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         if (cost[i] > ecost) {
                             __syncwarp();
                             if (lane == 0) {
-                                nchild[parent[i]]--;
-                                nchild[newi]++;
+                                unlink_child(links, parent[i], i);
+                                link_child(links, newi, i);
                                 efrom[3 * i] = cx; efrom[3 * i + 1] = cy; efrom[3 * i + 2] = cyaw;
                                 eto[3 * i] = a.x; eto[3 * i + 1] = a.y; eto[3 * i + 2] = ayaw;
                                 xy[i] = make_double2(ex, ey); yaw[i] = eyw; cost[i] = ecost; parent[i] = newi;
@@ -211,7 +209,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                             for (int k2 = k + 1 + lane; k2 < count; k2 += 32)
                                 if (near_idx[k2] == i) flags[k2] |= 4;
                             __syncwarp();
-                            propagate(i, n, xy, cost, parent, nchild, bits_cur, bits_nxt, words, lane);
+                            propagate_lists(i, xy, cost, links, qtail, lane);
                         }
                     }
                 }

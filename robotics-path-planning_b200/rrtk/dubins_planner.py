@@ -67,7 +67,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)    # noqa: E731
         xy, yaw, cost, parent = f64(q, cap, 2), f64(q, cap), f64(q, cap), i32(q, cap)
         ef, et = f64(q, cap, 3), f64(q, cap, 3)
-        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, cap)
+        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, 4 * cap)
         rc = _lib.lib().rrtk_rrtstar_dubins_run_dev(
             C.byref(p), d_sg.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_r2.data_ptr(), d_st.data_ptr(),
             xy.data_ptr(), yaw.data_ptr(), cost.data_ptr(), parent.data_ptr(), ef.data_ptr(), et.data_ptr(),

@@ -20,7 +20,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 h_path = torch.empty((Q, 256, 2), dtype=torch.float64).pin_memory()
 h_plen = torch.empty((Q,), dtype=torch.int32).pin_memory()
-for k in range(6):
+for k in range(14):
     t = [time.perf_counter()]
     batch.upload(); torch.cuda.synchronize(); t.append(time.perf_counter())
     r = batch.run(); torch.cuda.synchronize(); t.append(time.perf_counter())
