@@ -483,6 +483,28 @@ def extras(torch, dev):
                                    course_points_per_s=float(npt.sum().item()) / t)
     except Exception as e:  # noqa: BLE001
         out["dubins_steer"] = dict(error=repr(e))
+    try:   # Reeds-Shepp steering primitive, 262144 edges among 16 circles
+        from rrtk import _lib as LL
+        n = 1 << 18
+        rng = np.random.default_rng(16)
+        f = np.column_stack([rng.uniform(0, 12, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+        tt = np.column_stack([f[:, 0:2] + rng.uniform(-4, 4, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+        obs = np.zeros((1, 16, 4)); o = rng.uniform(0, 12, (16, 2)); r = rng.uniform(0.2, 0.8, 16)
+        obs[0, :, 0:2] = o; obs[0, :, 2] = r; obs[0, :, 3] = r * r
+        d_f, d_t, d_o = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (f, tt, obs))
+        d_c = torch.tensor([16], dtype=torch.int32, device=dev)
+        ty = torch.empty((n, 5), dtype=torch.int32, device=dev); ln = torch.empty((n, 5), dtype=torch.float64, device=dev)
+        Lt = torch.empty(n, dtype=torch.float64, device=dev); npa = torch.empty(n, dtype=torch.int32, device=dev)
+        end = torch.empty((n, 3), dtype=torch.float64, device=dev); npt = torch.empty(n, dtype=torch.int32, device=dev)
+        fr = torch.empty(n, dtype=torch.uint8, device=dev)
+        t = _timed(torch, lambda: L.rrtk_reeds_shepp_steer_dev(n, 1.0, 0.1, d_f.data_ptr(), d_t.data_ptr(), None, d_o.data_ptr(),
+                                                               16, d_c.data_ptr(), ty.data_ptr(), ln.data_ptr(), Lt.data_ptr(),
+                                                               npa.data_ptr(), end.data_ptr(), npt.data_ptr(), fr.data_ptr(),
+                                                               None, 0, s))
+        out["reeds_shepp_steer"] = dict(edges_per_s=n / t, ms=t * 1e3, edges=n, course_points_per_s=float(npt.sum().item()) / t,
+                                        words_per_s=48 * n / t)
+    except Exception as e:  # noqa: BLE001
+        out["reeds_shepp_steer"] = dict(error=repr(e))
     try:   # config 4: RRT*-Dubins, 1024 queries x 500 iterations, built-in scenario (rrt_05:1804-1859)
         Q, iters = 1024, 500
         rng = np.random.default_rng(7)

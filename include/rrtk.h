@@ -272,6 +272,23 @@ RRTK_API int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_
                                    int32_t max_pts, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched Reeds-Shepp steering: reeds_shepp_path_planning (rs00:496-515 == rrt_06:1426-1437) -- the 12 path functions
+ * (rs00:166-363) under the 4 symmetries of generate_path (:366-428), set_path's de-duplication (:141-160), the first
+ * shortest path and its sampled course (:431-493) -- plus the sampled collision test of the course, one edge of
+ * RRT*-Reeds-Shepp's steer (rrt_06:1584-1606).
+ *   from3, to3 [N][3] = x, y, yaw;  maxc = max curvature, step_size (0.2 default in the reference)
+ *   obs_set / obstacles / obs_stride / n_obs as for rrtk_dubins_steer_dev
+ * outputs: types [N][5] (0 = L, 1 = S, 2 = R, -1 = unused; all -1 when the reference returns None), lengths [N][5]
+ *   (signed, / maxc), L [N] (total length / maxc), n_paths [N] = len(paths), end [N][3] (last course point),
+ *   n_pts [N] = len(x), free [N], pts [N][max_pts][4] or NULL = x, y, yaw, direction (+1 / -1)
+ * ------------------------------------------------------------------------------------------- */
+RRTK_API int rrtk_reeds_shepp_steer_dev(int32_t n_req, double maxc, double step_size, const double *from3,
+                                        const double *to3, const int32_t *obs_set, const double *obstacles,
+                                        int32_t obs_stride, const int32_t *n_obs, int32_t *types, double *lengths,
+                                        double *L, int32_t *n_paths, double *end, int32_t *n_pts, uint8_t *free_flag,
+                                        double *pts, int32_t max_pts, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Batched RRT*-Dubins -- `planning()` of rrt_05:1416-1456 for Q independent queries: nearest on xy
  * (:1605-1610), steer = full Dubins course (:1458-1479), check_collision over the course (:1625-1638),
  * find_near_nodes (:1715-1739), choose_parent (:1648-1689), rewire + propagate with the EUCLIDEAN
@@ -353,7 +370,7 @@ RRTK_API int rrtk_astar_torus_dev(int32_t M, int32_t n_queries, const int32_t *s
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)
- *   kind 6: acos(a[i])
+ *   kind 6: acos(a[i])                    kind 7: asin(a[i])
  * ------------------------------------------------------------------------------------------- */
 RRTK_API int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out,
                           void *stream);

@@ -14,6 +14,7 @@ stream, and `check_collision` is wrapped to log its verdicts.
 from __future__ import annotations
 
 import json
+import math
 import os
 import random
 import sys
@@ -345,7 +346,38 @@ def run_astar(name, src_fixture, start, goal):
     print(f"{name}: M={shape[0]}, route of {len(route)} cells, {int((work == 2).sum())} expanded")
 
 
+def run_reeds_shepp(name, n, seed):
+    """reeds_shepp_path_planning (rs00:496-515) of the unmodified reference on n random pose pairs."""
+    ns = ref_loader.load("rs00")
+    rng = np.random.default_rng(seed)
+    starts, goals, maxcs, steps = [], [], [], []
+    types = np.full((n, 5), -1, dtype=np.int32); lengths = np.zeros((n, 5)); npts = np.zeros(n, dtype=np.int32)
+    xs, ys, yaws = [], [], []
+    for k in range(n):
+        s = [rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-math.pi, math.pi)]
+        g = [s[0] + rng.uniform(-6, 6), s[1] + rng.uniform(-6, 6), rng.uniform(-math.pi, math.pi)]
+        if k % 7 == 0:
+            g = [s[0] + rng.uniform(-0.5, 0.5), s[1] + rng.uniform(-0.5, 0.5), s[2] + rng.uniform(-0.3, 0.3)]
+        if k % 11 == 0:
+            g = [s[0] + 3.0, s[1], s[2]] if k % 2 else [s[0], s[1] + 2.0, s[2] + math.pi]
+        maxc, step = [1.0, 0.5, 2.0, 0.1][k % 4], [0.2, 0.1, 0.05][k % 3]
+        with ref_loader.quiet():
+            r = ns["reeds_shepp_path_planning"](*s, *g, maxc, step)
+        starts.append(s); goals.append(g); maxcs.append(maxc); steps.append(step)
+        if r[0] is not None:
+            m = len(r[3])
+            types[k, :m] = ["LSR".index(c) for c in r[3]]
+            lengths[k, :m] = [float(v) for v in r[4]]
+            npts[k] = len(r[0])
+            xs += [float(v) for v in r[0]]; ys += [float(v) for v in r[1]]; yaws += [float(v) for v in r[2]]
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(dict(kind="rs00", n=n)),
+                        start=np.array(starts), goal=np.array(goals), maxc=np.array(maxcs), step=np.array(steps),
+                        types=types, lengths=lengths, n_pts=npts, x=np.array(xs), y=np.array(ys), yaw=np.array(yaws))
+    print(f"{name}: {n} pairs, {int((npts == 0).sum())} without a path, {len(xs)} course points")
+
+
 CASES = {
+    "rs_pairs_400": lambda: run_reeds_shepp("rs_pairs_400", 400, 41),
     "astar_script_m100": lambda: run_astar("astar_script_m100", "arm02_script_m100", (10, 50), (58, 56)),   # arm02:309-310
     "astar_script_m100_b": lambda: run_astar("astar_script_m100_b", "arm02_script_m100", (95, 3), (40, 80)),
     "astar_2link_m100": lambda: run_astar("astar_2link_m100", "arm02_2link_m100", (10, 50), (58, 56)),

@@ -45,7 +45,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB_PATH)
         for name, nargs in (("orc_hypot", 2), ("orc_cr_hypot", 2), ("orc_cr_sin", 1),
-                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2), ("orc_cr_acos", 1)):
+                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2), ("orc_cr_acos", 1), ("orc_cr_asin", 1)):
             f = getattr(_lib, name)
             f.restype = C.c_double
             f.argtypes = [C.c_double] * nargs
@@ -324,3 +324,24 @@ def astar_heuristic_closed(M, goal):
     L.orc_astar_heuristic_closed.restype = C.c_int64
     return np.array([[L.orc_astar_heuristic_closed(M, int(goal[0]), int(goal[1]), i, j) for j in range(M)]
                      for i in range(M)], dtype=np.int64)
+
+
+RS_TYPES = "LSR"
+
+
+def reeds_shepp(s, g, maxc, step_size=0.2, math_mode=MATH_LIBM, max_pts=4096):
+    """reeds_shepp_path_planning (rs00:496-515) -> dict(types, lengths, L, n_paths, pts [n, 4] = x, y, yaw, direction) or None."""
+    L = lib()
+    L.orc_reeds_shepp.restype = C.c_int
+    L.orc_reeds_shepp.argtypes = [C.c_double] * 8 + [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                                    C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int32]
+    types = np.zeros(5, dtype=np.int32); lengths = np.zeros(5); nseg = C.c_int32(); bl = C.c_double(); npaths = C.c_int32()
+    pts = np.zeros((max_pts, 4))
+    n = L.orc_reeds_shepp(float(s[0]), float(s[1]), float(s[2]), float(g[0]), float(g[1]), float(g[2]), float(maxc),
+                          float(step_size), int(math_mode), _p(types, C.c_int32), _p(lengths, C.c_double), C.byref(nseg),
+                          C.byref(bl), C.byref(npaths), _p(pts, C.c_double), max_pts)
+    if n == 0:
+        return None
+    k = nseg.value
+    return dict(types=[RS_TYPES[t] for t in types[:k]], lengths=lengths[:k].tolist(), L=bl.value, n_paths=npaths.value,
+                pts=pts[:min(n, max_pts)].copy(), n=n)

@@ -91,6 +91,7 @@ ORC_EXPORT double orc_cr_cos(double x) { return crm_cos(x); }
 ORC_EXPORT double orc_cr_atan2(double y, double x) { return crm_atan2(y, x); }
 ORC_EXPORT double orc_cr_hypot(double a, double b) { return crm_hypot(a, b); }
 ORC_EXPORT double orc_cr_acos(double x) { return crm_acos(x); }
+ORC_EXPORT double orc_cr_asin(double x) { return crm_asin(x); }
 ORC_EXPORT double orc_cr_atan2_sincos(double y, double x, double *s, double *c) {
     return crm_atan2_sincos(y, x, s, c);
 }
@@ -1148,4 +1149,215 @@ ORC_EXPORT int orc_rrtstar_dubins_run(const orc_dubins_params_t *p, const double
     *n_nodes = n; *iters_done = it; *goal_index = gi;
     free(buf); free(dl); free(near);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Reeds-Shepp local planner (rs00:73-515 == rrt_06:1021-1437)                             */
+/* ------------------------------------------------------------------------------------ */
+static inline double m_asin(int m, double x) { return m == ORC_MATH_LIBM ? asin(x) : crm_asin(x); }
+static inline double m_hyp(int m, double a, double b) { return m == ORC_MATH_LIBM ? orc_hypot(a, b) : crm_hypot(a, b); }
+static double rs_mod2pi(double x) { /* rs00:130-139 */
+    double m = copysign(2.0 * ORC_PI, x);
+    double v = fmod(x, m);
+    if (v == 0.0) v = copysign(0.0, m);
+    if (v < -ORC_PI) v += 2.0 * ORC_PI;
+    else if (v > ORC_PI) v -= 2.0 * ORC_PI;
+    return v;
+}
+/* base segment types of the 12 path functions (0 = L, 1 = S, 2 = R) and their lengths */
+static const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1},
+                                   {0, 2, 0, 2, -1}, {0, 2, 0, 2, -1},   {0, 2, 1, 0, -1},  {0, 2, 1, 2, -1},  {0, 1, 2, 0, -1},
+                                   {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
+static const int RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
+/* the path functions of rs00:166-363 in path_functions order; returns 1 and the travel distances, or 0 */
+static int rs_word(int m, int f, double x, double y, double phi, double *d) {
+    const double pi = ORC_PI;
+    double u, t, v, u1, theta, A, zeta, eeta;
+    if (f == 0) {
+        u = m_hyp(m, x - m_sin(m, phi), y - 1.0 + m_cos(m, phi));
+        t = m_atan2(m, y - 1.0 + m_cos(m, phi), x - m_sin(m, phi));
+        if (0.0 <= t && t <= pi) {
+            v = rs_mod2pi(phi - t);
+            if (0.0 <= v && v <= pi) { d[0] = t; d[1] = u; d[2] = v; return 1; }
+        }
+        return 0;
+    }
+    if (f == 1) {
+        u1 = m_hyp(m, x + m_sin(m, phi), y - 1.0 - m_cos(m, phi));
+        double t1 = m_atan2(m, y - 1.0 - m_cos(m, phi), x + m_sin(m, phi));
+        u1 = sq(m, u1);
+        if (u1 >= 4.0) {
+            u = sqrt(u1 - 4.0);
+            theta = m_atan2(m, 2.0, u);
+            t = rs_mod2pi(t1 + theta);
+            v = rs_mod2pi(t - phi);
+            if (t >= 0.0 && v >= 0.0) { d[0] = t; d[1] = u; d[2] = v; return 1; }
+        }
+        return 0;
+    }
+    if (f == 2 || f == 3 || f == 4 || f == 7 || f == 9) { zeta = x - m_sin(m, phi); eeta = y - 1 + m_cos(m, phi); }
+    else { zeta = x + m_sin(m, phi); eeta = y - 1 - m_cos(m, phi); }
+    u1 = m_hyp(m, zeta, eeta);
+    theta = m_atan2(m, eeta, zeta);
+    switch (f) {
+        case 2:
+            if (u1 <= 4.0) {
+                A = m_acos(m, 0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(phi - t - u);
+                d[0] = t; d[1] = -u; d[2] = v; return 1;
+            }
+            return 0;
+        case 3:
+            if (u1 <= 4.0) {
+                A = m_acos(m, 0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(-phi + t + u);
+                d[0] = t; d[1] = -u; d[2] = -v; return 1;
+            }
+            return 0;
+        case 4:
+            if (u1 <= 4.0) {
+                u = m_acos(m, 1 - sq(m, u1) * 0.125);
+                A = m_asin(m, 2 * m_sin(m, u) / u1);
+                t = rs_mod2pi(-A + theta + pi / 2); v = rs_mod2pi(t - u - phi);
+                d[0] = t; d[1] = u; d[2] = -v; return 1;
+            }
+            return 0;
+        case 5:
+            if (u1 <= 2) {
+                A = m_acos(m, (u1 + 2) * 0.25);
+                t = rs_mod2pi(theta + A + pi / 2); u = rs_mod2pi(A); v = rs_mod2pi(phi - t + 2 * u);
+                if (t >= 0 && u >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = -u; d[3] = -v; return 1; }
+            }
+            return 0;
+        case 6: {
+            double u2 = (20 - sq(m, u1)) / 16;
+            if (0 <= u2 && u2 <= 1) {
+                u = m_acos(m, u2);
+                A = m_asin(m, 2 * m_sin(m, u) / u1);
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -u; d[2] = -u; d[3] = v; return 1; }
+            }
+            return 0;
+        }
+        case 7:
+            if (u1 >= 2.0) {
+                u = sqrt(sq(m, u1) - 4) - 2;
+                A = m_atan2(m, 2, sqrt(sq(m, u1) - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi + pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return 1; }
+            }
+            return 0;
+        case 8:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta + pi / 2); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return 1; }
+            }
+            return 0;
+        case 9:
+            if (u1 >= 2.0) {
+                u = sqrt(sq(m, u1) - 4) - 2;
+                A = m_atan2(m, sqrt(sq(m, u1) - 4), 2);
+                t = rs_mod2pi(theta - A + pi / 2); v = rs_mod2pi(t - phi - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return 1; }
+            }
+            return 0;
+        case 10:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return 1; }
+            }
+            return 0;
+        default:
+            if (u1 >= 4.0) {
+                u = sqrt(sq(m, u1) - 4) - 4;
+                A = m_atan2(m, 2, sqrt(sq(m, u1) - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -pi / 2; d[4] = v; return 1; }
+            }
+            return 0;
+    }
+}
+/* reeds_shepp_path_planning (rs00:496-515).  Returns the number of course points (0 = None); types [5] (0 L, 1 S, 2 R,
+ * -1 pad), lengths [5] (already / maxc), pts [max_pts][4] = x, y, yaw, direction; *n_paths = len(paths) */
+ORC_EXPORT int orc_reeds_shepp(double sx, double sy, double syaw, double gx, double gy, double gyaw, double maxc,
+                               double step_size, int mode, int32_t *types, double *lengths, int32_t *n_seg, double *best_L,
+                               int32_t *n_paths, double *pts, int32_t max_pts) {
+    const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
+    const double c = m_cos(mode, syaw), s = m_sin(mode, syaw);
+    const double x = (c * dx + s * dy) * maxc, y = (-s * dx + c * dy) * maxc;
+    const double step = step_size * maxc;
+    double pl[48][5], pL[48];
+    int pt[48][5], pn[48], np_ = 0;
+    for (int f = 0; f < 12; f++)
+        for (int k = 0; k < 4; k++) {
+            double d[5];
+            const double ax = (k & 1) ? -x : x, ay = (k & 2) ? -y : y, aphi = (k == 1 || k == 2) ? -dth : dth;
+            if (!rs_word(mode, f, ax, ay, aphi, d)) continue;
+            const int n = RS_N[f];
+            double tot = 0;
+            for (int i = 0; i < n; i++) tot += fabs(d[i]);
+            for (int i = 0; i < n; i++)
+                if (0.1 * tot < fabs(d[i]) && fabs(d[i]) < step) { *n_paths = 0; return 0; } /* "Step size too large" */
+            int ty[5];
+            for (int i = 0; i < n; i++) {
+                if (k == 1 || k == 3) d[i] = -d[i];                                 /* timeflip */
+                ty[i] = (k >= 2 && RS_T[f][i] != 1) ? 2 - RS_T[f][i] : RS_T[f][i];  /* reflect */
+            }
+            double L = 0.0;
+            for (int i = 0; i < n; i++) L += fabs(d[i]);
+            int same = 0;
+            for (int j = 0; j < np_ && !same; j++) {
+                if (pn[j] != n) continue;
+                int eq = 1;
+                for (int i = 0; i < n; i++) eq &= pt[j][i] == ty[i];
+                if (eq && (pL[j] - L) <= step) same = 1;
+            }
+            if (same || L <= step) continue;
+            for (int i = 0; i < n; i++) { pl[np_][i] = d[i]; pt[np_][i] = ty[i]; }
+            pn[np_] = n; pL[np_] = L; np_++;
+        }
+    *n_paths = np_;
+    if (np_ == 0) return 0;
+    int best = 0;
+    for (int j = 1; j < np_; j++)
+        if (fabs(pL[j] / maxc) < fabs(pL[best] / maxc)) best = j;
+    const int n = pn[best];
+    *n_seg = n; *best_L = pL[best] / maxc;
+    for (int i = 0; i < 5; i++) { types[i] = i < n ? pt[best][i] : -1; lengths[i] = i < n ? pl[best][i] / maxc : 0.0; }
+    /* generate_local_course (rs00:431-447) + the world transform of calc_paths (:481-487) */
+    const double cm = m_cos(mode, -syaw), sm = m_sin(mode, -syaw);
+    double ox = 0.0, oy = 0.0, oyaw = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const double length = pl[best][i];
+        const int type = pt[best][i];
+        const double dd = length >= 0.0 ? step : -step;
+        long na = length != 0.0 ? (long)ceil((length - 0.0) / dd) : 0; /* np.arange(0.0, length, d_dist) */
+        if (na < 0) na = 0;
+        double lx = 0, ly = 0, lyaw = 0;
+        for (long j = 0; j <= na; j++) {
+            const double dist = j < na ? 0.0 + (double)j * dd : length;
+            if (type == 1) {
+                lx = ox + dist / maxc * m_cos(mode, oyaw);
+                ly = oy + dist / maxc * m_sin(mode, oyaw);
+                lyaw = oyaw;
+            } else {
+                const double ldx = m_sin(mode, dist) / maxc;
+                const double ldy = type == 0 ? (1.0 - m_cos(mode, dist)) / maxc : (1.0 - m_cos(mode, dist)) / -maxc;
+                lyaw = type == 0 ? oyaw + dist : oyaw - dist;
+                const double gdx = m_cos(mode, -oyaw) * ldx + m_sin(mode, -oyaw) * ldy;
+                const double gdy = -m_sin(mode, -oyaw) * ldx + m_cos(mode, -oyaw) * ldy;
+                lx = ox + gdx; ly = oy + gdy;
+            }
+            if (cnt < max_pts) {
+                pts[4 * cnt] = cm * lx + sm * ly + sx;
+                pts[4 * cnt + 1] = -sm * lx + cm * ly + sy;
+                pts[4 * cnt + 2] = angle_mod_pi(lyaw + syaw);
+                pts[4 * cnt + 3] = length > 0.0 ? 1.0 : -1.0;
+            }
+            cnt++;
+        }
+        ox = lx; oy = ly; oyaw = lyaw;
+    }
+    return cnt;
 }

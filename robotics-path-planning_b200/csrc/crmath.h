@@ -349,4 +349,21 @@ CRM_FN double crm_acos(double x) {
     return at.hi;
 }
 
+/* RN(asin(x)) for |x| <= 1 (NaN outside): asin(x) = atan2(x, sqrt((1 - x)(1 + x))), same double-double core as acos. */
+CRM_FN double crm_asin(double x) {
+    if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
+    if (x == 0.0) return x;
+    if (fabs(x) == 1.0) return copysign(CRM_PIO2_H, x);
+    crm_dd a = crm_two_sum(1.0, -x), b = crm_two_sum(1.0, x); /* exact */
+    crm_dd p = crm_mul(a, b);
+    double s0 = sqrt(p.hi);
+    crm_dd e = crm_sub(p, crm_two_prod(s0, s0));
+    crm_dd c = crm_fast_two_sum(s0, e.hi / (2.0 * s0)); /* sqrt(1 - x^2) to ~2^-104 */
+    crm_dd ax = crm_mk(fabs(x), 0.0);
+    int swap = ax.hi > c.hi;                               /* |x| > cos: angle above pi/4 */
+    crm_dd at = crm_atan_octant_dd(swap ? c : ax, swap ? ax : c);
+    if (swap) at = crm_sub(crm_mk(CRM_PIO2_H, CRM_PIO2_L), at);
+    return x < 0.0 ? -at.hi : at.hi;
+}
+
 #endif /* RRTK_CRMATH_H */

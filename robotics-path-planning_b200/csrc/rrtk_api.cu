@@ -66,6 +66,9 @@ int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path,
 int launch_astar_torus(int M, int n_queries, const int32_t *start_goal, uint8_t *grids, int32_t *heur, int32_t *parents,
                        unsigned long long *heaps, int32_t *routes, int route_cap, int32_t *route_len, int32_t *expanded,
                        cudaStream_t s);
+int launch_rs_steer(int n_req, double maxc, double step_size, const double *from3, const double *to3, const int32_t *obs_set,
+                    const double *obstacles, int obs_stride, const int32_t *n_obs, int32_t *types, double *lengths, double *L,
+                    int32_t *n_paths, double *end, int32_t *n_pts, uint8_t *free_flag, double *pts, int max_pts, cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
                     const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
 
@@ -231,6 +234,20 @@ int rrtk_dubins_steer_dev(int32_t n_req, double curvature, double step_size, con
                                lengths, end, n_pts, free_flag, pts, max_pts, (cudaStream_t)stream);
 }
 
+int rrtk_reeds_shepp_steer_dev(int32_t n_req, double maxc, double step_size, const double *from3, const double *to3,
+                               const int32_t *obs_set, const double *obstacles, int32_t obs_stride, const int32_t *n_obs,
+                               int32_t *types, double *lengths, double *L, int32_t *n_paths, double *end, int32_t *n_pts,
+                               uint8_t *free_flag, double *pts, int32_t max_pts, void *stream) {
+    if (n_req < 0 || obs_stride < 0 || max_pts < 0) return set_error(RRTK_ERR_INVALID, "negative size");
+    if (!(maxc > 0.0) || !(step_size > 0.0)) return set_error(RRTK_ERR_INVALID, "maxc and step_size must be > 0");
+    if (n_req == 0) return RRTK_OK;
+    if (!from3 || !to3 || !types || !lengths || !L || !n_paths || !end || !n_pts || !free_flag)
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (n_obs && !obstacles) return set_error(RRTK_ERR_INVALID, "n_obs given without obstacles");
+    return launch_rs_steer(n_req, maxc, step_size, from3, to3, obs_set, obstacles, obs_stride, n_obs, types, lengths, L,
+                           n_paths, end, n_pts, free_flag, pts, max_pts, (cudaStream_t)stream);
+}
+
 int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
                                 const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
                                 double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
@@ -286,7 +303,7 @@ int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goa
 }
 
 int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out, void *stream) {
-    if (kind < 0 || kind > 6 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
+    if (kind < 0 || kind > 7 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
     if (n == 0) return RRTK_OK;
     if (!a || !out || (!b && (kind == 0 || kind == 1 || kind == 4 || kind == 5))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_crmath_probe(kind, n, a, b, out, (cudaStream_t)stream);

@@ -727,6 +727,7 @@ extern "C" __global__ void crmath_probe_kernel(int kind, int64_t n, const double
         case 4: (void)crm_atan2_sincos(a[i], b[i], &s, &c); r = s; break;
         case 5: (void)crm_atan2_sincos(a[i], b[i], &s, &c); r = c; break;
         case 6: r = crm_acos(a[i]); break;
+        case 7: r = crm_asin(a[i]); break;
     }
     out[i] = r;
 }

@@ -1,0 +1,314 @@
+// rrtk_rs.cu -- batched Reeds-Shepp steering (reeds_shepp_path_planning rs00:496-515 == rrt_06:1426-1437; SURVEY.md 8f
+// rank 3): the 12 path functions (rs00:166-363) under the 4 symmetries of generate_path (:366-428) = 48 candidate
+// words, set_path's order-dependent de-duplication (:141-160), the first shortest path, its sampled course
+// (generate_local_course / interpolate :431-470 with np.arange's  start + i * step  distances) rotated to the world
+// frame (calc_paths :473-493), and the sampled collision test of RRT*-Reeds-Shepp's check_collision over the course.
+//
+// One warp per request.  The 48 words are solved one per lane (two rounds): their atan2 / acos / asin / sin / cos are
+// the correctly rounded crmath.h functions, so the lengths -- and with them every `>= 0`, `<= step_size` and
+// minimum decision -- are platform independent.  The insertion logic then runs in the reference's order (uniformly,
+// 48 cheap steps over shared memory) and the course points of each segment are spread over the lanes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrtk.h"
+#include "crmath.h"
+#include "rrtk_device.cuh"
+#include "rrtk_planner.cuh"
+#include "rrtk_dubins.cuh"
+
+namespace rrtk {
+
+constexpr int RS_WARPS = 4;
+
+// rs00:130-139: C fmod semantics, then wrap into [-pi, pi]
+static __device__ __forceinline__ double rs_mod2pi(double x) {
+    const double m = copysign(2.0 * D_PI, x);
+    double v = fmod(x, m);
+    if (v == 0.0) v = copysign(0.0, m);
+    if (v < -D_PI) v += 2.0 * D_PI;
+    else if (v > D_PI) v -= 2.0 * D_PI;
+    return v;
+}
+
+__device__ const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1},
+                                       {0, 2, 0, 2, -1}, {0, 2, 0, 2, -1},   {0, 2, 1, 0, -1},  {0, 2, 1, 2, -1},  {0, 1, 2, 0, -1},
+                                       {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
+__device__ const int8_t RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
+
+// the path functions of rs00:166-363 in path_functions order; true + travel distances, or false
+static __device__ __noinline__ bool rs_word(int f, double x, double y, double phi, double *d) {
+    const double pi = D_PI;
+    double sp, cp;
+    sincos_cr(phi, &sp, &cp);
+    double u, t, v, u1, theta, A;
+    if (f == 0) {
+        u = crm_hypot(x - sp, y - 1.0 + cp);
+        t = crm_atan2(y - 1.0 + cp, x - sp);
+        if (0.0 <= t && t <= pi) {
+            v = rs_mod2pi(phi - t);
+            if (0.0 <= v && v <= pi) { d[0] = t; d[1] = u; d[2] = v; return true; }
+        }
+        return false;
+    }
+    if (f == 1) {
+        u1 = crm_hypot(x + sp, y - 1.0 - cp);
+        const double t1 = crm_atan2(y - 1.0 - cp, x + sp);
+        u1 = u1 * u1;
+        if (u1 >= 4.0) {
+            u = sqrt(u1 - 4.0);
+            theta = crm_atan2(2.0, u);
+            t = rs_mod2pi(t1 + theta);
+            v = rs_mod2pi(t - phi);
+            if (t >= 0.0 && v >= 0.0) { d[0] = t; d[1] = u; d[2] = v; return true; }
+        }
+        return false;
+    }
+    const bool minus = f == 2 || f == 3 || f == 4 || f == 7 || f == 9;
+    const double zeta = minus ? x - sp : x + sp, eeta = minus ? y - 1 + cp : y - 1 - cp;
+    u1 = crm_hypot(zeta, eeta);
+    theta = crm_atan2(eeta, zeta);
+    switch (f) {
+        case 2:
+            if (u1 <= 4.0) {
+                A = crm_acos(0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(phi - t - u);
+                d[0] = t; d[1] = -u; d[2] = v; return true;
+            }
+            return false;
+        case 3:
+            if (u1 <= 4.0) {
+                A = crm_acos(0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(-phi + t + u);
+                d[0] = t; d[1] = -u; d[2] = -v; return true;
+            }
+            return false;
+        case 4:
+            if (u1 <= 4.0) {
+                u = crm_acos(1 - u1 * u1 * 0.125);
+                A = crm_asin(2 * crm_sin(u) / u1);
+                t = rs_mod2pi(-A + theta + pi / 2); v = rs_mod2pi(t - u - phi);
+                d[0] = t; d[1] = u; d[2] = -v; return true;
+            }
+            return false;
+        case 5:
+            if (u1 <= 2) {
+                A = crm_acos((u1 + 2) * 0.25);
+                t = rs_mod2pi(theta + A + pi / 2); u = rs_mod2pi(A); v = rs_mod2pi(phi - t + 2 * u);
+                if (t >= 0 && u >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 6: {
+            const double u2 = (20 - u1 * u1) / 16;
+            if (0 <= u2 && u2 <= 1) {
+                u = crm_acos(u2);
+                A = crm_asin(2 * crm_sin(u) / u1);
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -u; d[2] = -u; d[3] = v; return true; }
+            }
+            return false;
+        }
+        case 7:
+            if (u1 >= 2.0) {
+                u = sqrt(u1 * u1 - 4) - 2;
+                A = crm_atan2(2, sqrt(u1 * u1 - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi + pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 8:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta + pi / 2); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 9:
+            if (u1 >= 2.0) {
+                u = sqrt(u1 * u1 - 4) - 2;
+                A = crm_atan2(sqrt(u1 * u1 - 4), 2);
+                t = rs_mod2pi(theta - A + pi / 2); v = rs_mod2pi(t - phi - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
+            }
+            return false;
+        case 10:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
+            }
+            return false;
+        default:
+            if (u1 >= 4.0) {
+                u = sqrt(u1 * u1 - 4) - 4;
+                A = crm_atan2(2, sqrt(u1 * u1 - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -pi / 2; d[4] = v; return true; }
+            }
+            return false;
+    }
+}
+
+struct RsWarp {
+    double d[48][5];
+    int ok[48];
+};
+
+// interpolate (rs00:449-470); sm / cm = sin / cos(-origin_yaw), so / co = sin / cos(origin_yaw)
+static __device__ __forceinline__ void rs_interp(double dist, int type, double maxc, double ox, double oy, double oyaw,
+                                                 double so, double co, double sm, double cm, double *x, double *y, double *yaw) {
+    if (type == 1) {
+        *x = ox + dist / maxc * co;
+        *y = oy + dist / maxc * so;
+        *yaw = oyaw;
+    } else {
+        double sl, cl;
+        sincos_cr(dist, &sl, &cl);
+        const double ldx = sl / maxc;
+        const double ldy = type == 0 ? (1.0 - cl) / maxc : (1.0 - cl) / -maxc;
+        *yaw = type == 0 ? oyaw + dist : oyaw - dist;
+        const double gdx = cm * ldx + sm * ldy;
+        const double gdy = -sm * ldx + cm * ldy;
+        *x = ox + gdx;
+        *y = oy + gdy;
+    }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restrict__ from3, const double *__restrict__ to3,
+                const int32_t *__restrict__ obs_set, const double4 *__restrict__ obstacles, int obs_stride,
+                const int32_t *__restrict__ n_obs_arr, int32_t *types_out, double *lengths_out, double *L_out,
+                int32_t *n_paths_out, double *end_out, int32_t *n_pts_out, uint8_t *free_out, double *pts_out, int max_pts) {
+    __shared__ RsWarp smem[RS_WARPS];
+    const int lane = threadIdx.x & 31;
+    RsWarp &W = smem[threadIdx.x >> 5];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const double step = step_size * maxc;
+    for (int r = warp; r < n_req; r += n_warps) {
+        const double sx = from3[3 * r], sy = from3[3 * r + 1], syaw = from3[3 * r + 2];
+        const double gx = to3[3 * r], gy = to3[3 * r + 1], gyaw = to3[3 * r + 2];
+        const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
+        double s0, c0;
+        sincos_cr(syaw, &s0, &c0);
+        const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;   // rs00:369-374
+        __syncwarp();
+        for (int cand = lane; cand < 48; cand += 32) {
+            const int f = cand >> 2, k = cand & 3;
+            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const bool ok = rs_word(f, (k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, d);
+#pragma unroll
+            for (int i = 0; i < 5; i++) W.d[cand][i] = d[i];
+            W.ok[cand] = ok ? 1 : 0;
+        }
+        __syncwarp();
+        // generate_path's loop + set_path, in the reference's order (uniform across the warp)
+        int n_ins = 0, best = -1, too_large = 0;
+        double ins_L[48], best_L = CUDART_INF;
+        int ins_code[48];
+        // (local arrays: 48 entries each; indexed uniformly)
+        for (int cand = 0; cand < 48; cand++) {
+            if (!W.ok[cand]) continue;
+            const int f = cand >> 2, k = cand & 3, n = RS_N[f];
+            double tot = 0.0;
+            for (int i = 0; i < n; i++) tot += fabs(W.d[cand][i]);
+            for (int i = 0; i < n; i++) {
+                const double a = fabs(W.d[cand][i]);
+                if (0.1 * tot < a && a < step) too_large = 1;   // "Step size too large for Reeds-Shepp paths." -> []
+            }
+            int code = n;
+            for (int i = 0; i < n; i++) {
+                const int t0 = RS_T[f][i];
+                const int ty = (k >= 2 && t0 != 1) ? 2 - t0 : t0;   // reflect
+                code = code * 3 + ty;
+            }
+            const double L = tot;   // timeflip only negates: sum(np.abs(lengths)) is the same left-to-right sum
+            bool same = false;
+            for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - L) <= step;
+            if (same || L <= step) continue;
+            ins_code[n_ins] = code; ins_L[n_ins] = L; n_ins++;
+            if (fabs(L / maxc) < best_L) { best_L = fabs(L / maxc); best = cand; }   // first minimum of abs(p.L)
+        }
+        if (too_large) { n_ins = 0; best = -1; }
+        if (best < 0) {
+            if (lane == 0) {
+                n_paths_out[r] = 0; n_pts_out[r] = 0; free_out[r] = 0; L_out[r] = 0.0;
+                for (int i = 0; i < 5; i++) { types_out[5 * r + i] = -1; lengths_out[5 * r + i] = 0.0; }
+            }
+            continue;
+        }
+        const int f = best >> 2, k = best & 3, n = RS_N[f];
+        const int set = obs_set ? obs_set[r] : 0;
+        const double4 *obs = obstacles + (size_t)set * obs_stride;
+        const int n_obs = n_obs_arr ? n_obs_arr[set] : 0;
+        double *pts = pts_out ? pts_out + (size_t)r * max_pts * 4 : nullptr;
+        double sm0, cm0;
+        sincos_cr(-syaw, &sm0, &cm0);
+        bool hit = false;
+        int np = 0;
+        double ox = 0.0, oy = 0.0, oyaw = 0.0, lastx = sx, lasty = sy, lastyaw = syaw;
+        for (int i = 0; i < n; i++) {
+            double length = W.d[best][i];
+            if (k == 1 || k == 3) length = -length;              // timeflip
+            const int t0 = RS_T[f][i];
+            const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;  // reflect
+            const double dd = length >= 0.0 ? step : -step;
+            long long na = length != 0.0 ? (long long)ceil((length - 0.0) / dd) : 0;   // len(np.arange(0.0, length, d_dist))
+            if (na < 0) na = 0;
+            double so, co, sm, cm;
+            sincos_cr(oyaw, &so, &co);
+            sincos_cr(-oyaw, &sm, &cm);
+            const double dirn = length > 0.0 ? 1.0 : -1.0;
+            for (long long j = lane; j <= na; j += 32) {
+                const double dist = j < na ? 0.0 + (double)j * dd : length;
+                double lx, ly, lyaw;
+                rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+                const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;   // rs00:481-485
+                const long long idx = np + j;
+                if (pts && idx < max_pts) {
+                    pts[4 * idx] = wx; pts[4 * idx + 1] = wy; pts[4 * idx + 2] = angle_mod_pi(lyaw + syaw); pts[4 * idx + 3] = dirn;
+                }
+                for (int o = 0; o < n_obs && !hit; o++) {
+                    const double4 ob = obs[o];
+                    const double ex = ob.x - wx, ey = ob.y - wy;
+                    if (ex * ex + ey * ey <= ob.w) hit = true;
+                }
+            }
+            double lx, ly, lyaw;   // the segment's last point is the next origin (uniform)
+            rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+            ox = lx; oy = ly; oyaw = lyaw;
+            lastx = cm0 * lx + sm0 * ly + sx; lasty = -sm0 * lx + cm0 * ly + sy; lastyaw = angle_mod_pi(lyaw + syaw);
+            np += (int)(na + 1);
+        }
+        const bool any_hit = __ballot_sync(FULL, hit) != 0u;
+        if (lane == 0) {
+            n_paths_out[r] = n_ins; n_pts_out[r] = np; free_out[r] = any_hit ? 0 : 1; L_out[r] = best_L;
+            for (int i = 0; i < 5; i++) {
+                double length = i < n ? W.d[best][i] : 0.0;
+                if (k == 1 || k == 3) length = -length;
+                const int t0 = i < n ? RS_T[f][i] : -1;
+                types_out[5 * r + i] = i < n ? ((k >= 2 && t0 != 1) ? 2 - t0 : t0) : -1;
+                lengths_out[5 * r + i] = i < n ? length / maxc : 0.0;
+            }
+            end_out[3 * r] = lastx; end_out[3 * r + 1] = lasty; end_out[3 * r + 2] = lastyaw;
+        }
+    }
+}
+
+int launch_rs_steer(int n_req, double maxc, double step_size, const double *from3, const double *to3, const int32_t *obs_set,
+                    const double *obstacles, int obs_stride, const int32_t *n_obs, int32_t *types, double *lengths, double *L,
+                    int32_t *n_paths, double *end, int32_t *n_pts, uint8_t *free_flag, double *pts, int max_pts, cudaStream_t s) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = ((long long)n_req + RS_WARPS - 1) / RS_WARPS;
+    long long grid = (long long)sms * 8;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    rs_steer_kernel<<<(unsigned)grid, RS_WARPS * 32, 0, s>>>(n_req, maxc, step_size, from3, to3, obs_set,
+                                                            reinterpret_cast<const double4 *>(obstacles), obs_stride, n_obs,
+                                                            types, lengths, L, n_paths, end, n_pts, free_flag, pts, max_pts);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rs_steer_kernel launch");
+    return RRTK_OK;
+}
+
+}  // namespace rrtk

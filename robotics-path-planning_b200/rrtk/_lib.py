@@ -79,6 +79,8 @@ _SIGS = {
     "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
+    "rrtk_reeds_shepp_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
+                                             _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_path_smoothing_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
