@@ -359,7 +359,10 @@ def main():
         flop_per_launch = alg["flop_per_iter"] * Q * iters
         achieved = flop_per_launch / (t_dev / args.steps) / 1e12
         roofline = dict(kernel="rrtstar_kernel", bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
-                        frac=achieved / fp64_peak, traffic=None,
+                        frac=achieved / fp64_peak,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the
+                        # committed ncu capture (profiles/r1i_rrtstar_kernel_ncu_summary.txt): 5.76 + 2.40 GB
+                        traffic=8.16e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
                         peak_source="FMA-loop probe measured in this run (rrtk_fma_peak_dev); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                         algorithmic_flop_per_iter=alg["flop_per_iter"], algorithmic_note=alg["note"],
@@ -630,7 +633,9 @@ def nn_roofline(torch, L, dev, n, peaks):
     peak = peaks["hbm_gbs"] if peaks else 6650.0
     best = out["B1"]["gbs"]
     return dict(kernel="nearest_kernel<1>", bound="hbm", achieved=best, peak=peak, unit="GB/s", frac=best / peak,
-                traffic=None, nodes=n, bytes_per_node=8,
+                # ncu (profiles/r1_secondary_kernels_ncu_summary.txt): 536.9 MB read + 6.4 MB written per launch at
+                # n = 2^26, i.e. 1.012 x the algorithmic 8 * n bytes
+                traffic=543.24e6 if n == (1 << 26) else None, traffic_unit="bytes/launch", nodes=n, bytes_per_node=8,
                 peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", detail=out)
 
 
