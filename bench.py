@@ -554,6 +554,23 @@ def extras(torch, dev):
         del run, d_free, d_ball
     except Exception as e:  # noqa: BLE001
         out["c3_informed_single_tree"] = dict(error=repr(e))
+    try:   # RRT*-Reeds-Shepp (rrt_06), 512 queries x 300 iterations, built-in scenario (rrt_06:2015-2083)
+        from rrtk import rs_planner as RP
+        Q, iters = 512, 300
+        rng = np.random.default_rng(17)
+        st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+        obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]] * Q
+        for rep in range(2):
+            t0 = time.perf_counter()
+            res = RP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 9.0, 0.0]] * Q, obs, 3.0, iters, st, robot_radius=0.6,
+                               curvature=2.0, step_size=0.1)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+        out["rrtstar_reeds_shepp"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+                                          mean_nodes=float(np.mean([r["n"] for r in res])),
+                                          solved=int(sum(r["goal_index"] >= 0 for r in res)))
+    except Exception as e:  # noqa: BLE001
+        out["rrtstar_reeds_shepp"] = dict(error=repr(e))
     try:   # Informed RRT* (rrt_07 semantics), 512 queries x 1000 iterations, built-in scenario
         Q, iters = 512, 1000
         rng = np.random.default_rng(8)

@@ -320,6 +320,17 @@ RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const doub
                                          int32_t *iters_done, int32_t *goal_index, int32_t *status,
                                          int32_t *workspace, void *stream);
 
+/* Batched RRT*-Reeds-Shepp -- `planning()` of rrt_06:1530-1570 for Q independent queries: the same loop as RRT*-Dubins
+ * with reeds_shepp_path_planning as steer (:1584-1604; p->step_size is its step_size, 0.2 by default in the reference),
+ * a sampler without goal bias (:1658-1666, the caller's stream), and try_goal_path after every append (:1572-1582), which
+ * can add a second node per iteration: node_cap >= 2 * max_iter + 1.  Arguments as for rrtk_rrtstar_dubins_run_dev;
+ * edge_from / edge_to regenerate a node's course with rrtk_reeds_shepp_steer_dev. */
+RRTK_API int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
+                                     const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
+                                     double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                                     int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                                     int32_t *workspace, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.
  *   rrtk_nearest_f32_dev: get_nearest_node_index (rrt_04:1196-1202, rrt_07:1210-1214) for B samples in

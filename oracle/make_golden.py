@@ -249,6 +249,40 @@ def run_rrt05(name, params, seed, search_until_max_iter=True):
           f"{wall:.2f} s ({n / wall:.1f} it/s)")
 
 
+def run_rrt06(name, params, seed, search_until_max_iter=True):
+    """Drive rrt_06's RRT.planning (RRT*-Reeds-Shepp) with an injected (x, y, yaw) sample stream."""
+    ns = ref_loader.load("rrt_06")
+    R = ns["RRT"]
+    rng = np.random.default_rng(seed)
+    n = params["max_iter"]
+    lo, hi = params["rand_area"]
+    stream = np.column_stack([rng.uniform(lo, hi, (n, 2)), rng.uniform(-math.pi, math.pi, n)])   # no goal bias (:1658)
+    rrt = R(**params)
+    it = iter(stream)
+    rrt.get_random_node = lambda: rrt.Node(*[float(v) for v in next(it)])
+    sys.setrecursionlimit(100000)
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        path = rrt.planning(animation=False, search_until_max_iter=search_until_max_iter)
+    wall = time.perf_counter() - t0
+    x, y, c, par = tree_arrays(rrt.node_list)
+    yaw = np.array([float(nd.yaw) for nd in rrt.node_list])
+    meta = dict(params)
+    meta.update(kind="rrt_06", seed=seed, reference_wall_s=wall, search_until_max_iter=search_until_max_iter,
+                goal_yaw_th=float(params.get("goal_yaw_th", np.deg2rad(1.0))))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), stream=stream,
+                        x=x, y=y, yaw=yaw, cost=c, parent=par,
+                        path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 3)))
+    print(f"{name}: {len(x)} nodes, {n} iterations, path {0 if path is None else len(path)} points, "
+          f"{wall:.2f} s ({n / wall:.1f} it/s)")
+
+
+C6 = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 9.0, 0.0],
+          obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
+          rand_area=[-2, 15], expand_dis=3.0, max_iter=300, robot_radius=0.6, connect_circle_dist=50.0,
+          curvature=2.0, goal_xy_th=0.5, step_size=0.1)                      # rrt_06:2015-2083
+
+
 C5D = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 10.0, 0.0],
            obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)],
            rand_area=[-2, 15], expand_dis=3.0, goal_sample_rate=10, max_iter=500, robot_radius=0.0,
@@ -377,6 +411,12 @@ def run_reeds_shepp(name, n, seed):
 
 
 CASES = {
+    "rrt06_builtin_300": lambda: run_rrt06("rrt06_builtin_300", C6, 1),
+    "rrt06_builtin_700": lambda: run_rrt06("rrt06_builtin_700", dict(C6, max_iter=700), 2),
+    "rrt06_loose_400": lambda: run_rrt06("rrt06_loose_400", dict(
+        C6, max_iter=400, curvature=1.0, step_size=0.2, robot_radius=0.3, goal_yaw_th=float(np.deg2rad(15.0)), goal_xy_th=1.0,
+        obstacle_list=[(5, 5, 1), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]), 3),
+    "rrt06_early_exit_500": lambda: run_rrt06("rrt06_early_exit_500", dict(C6, max_iter=500), 4, False),
     "rs_pairs_400": lambda: run_reeds_shepp("rs_pairs_400", 400, 41),
     "astar_script_m100": lambda: run_astar("astar_script_m100", "arm02_script_m100", (10, 50), (58, 56)),   # arm02:309-310
     "astar_script_m100_b": lambda: run_astar("astar_script_m100_b", "arm02_script_m100", (95, 3), (40, 80)),

@@ -345,3 +345,51 @@ def reeds_shepp(s, g, maxc, step_size=0.2, math_mode=MATH_LIBM, max_pts=4096):
     k = nseg.value
     return dict(types=[RS_TYPES[t] for t in types[:k]], lengths=lengths[:k].tolist(), L=bl.value, n_paths=npaths.value,
                 pts=pts[:min(n, max_pts)].copy(), n=n)
+
+
+class RSParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("sx", "sy", "syaw", "gx", "gy", "gyaw", "expand_dis", "robot_radius",
+                                          "connect_circle_dist", "kappa", "goal_yaw_th", "goal_xy_th", "step_size")] + \
+               [(k, C.c_int32) for k in ("max_iter", "n_obs", "search_until_max_iter", "math_mode")]
+
+
+def rrtstar_rs_run(start, goal, obstacle_list, expand_dis, max_iter, robot_radius, connect_circle_dist, curvature,
+                   goal_yaw_th, goal_xy_th, search_until_max_iter, stream3, step_size=0.2, math_mode=MATH_LIBM):
+    """rrt_06 planning() with an injected (x, y, yaw) stream -> tree arrays, goal_index and the final course [n, 3]."""
+    p = RSParams()
+    p.sx, p.sy, p.syaw = [float(v) for v in start]
+    p.gx, p.gy, p.gyaw = [float(v) for v in goal]
+    p.expand_dis, p.robot_radius, p.connect_circle_dist = float(expand_dis), float(robot_radius), float(connect_circle_dist)
+    p.kappa, p.goal_yaw_th, p.goal_xy_th, p.step_size = float(curvature), float(goal_yaw_th), float(goal_xy_th), float(step_size)
+    p.max_iter, p.search_until_max_iter, p.math_mode = int(max_iter), int(bool(search_until_max_iter)), int(math_mode)
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    p.n_obs = obs.shape[0]
+    st = np.ascontiguousarray(stream3, dtype=np.float64).reshape(-1, 3)
+    cap = 2 * max_iter + 1
+    x = np.zeros(cap); y = np.zeros(cap); yaw = np.zeros(cap); cost = np.zeros(cap)
+    parent = np.full(cap, -1, np.int32)
+    ef = np.zeros((cap, 3)); et = np.zeros((cap, 3))
+    n = C.c_int32(); it = C.c_int32(); gi = C.c_int32()
+    lib().orc_rrtstar_rs_run(C.byref(p), _p(obs, C.c_double), _p(st, C.c_double), _p(x, C.c_double), _p(y, C.c_double),
+                             _p(yaw, C.c_double), _p(cost, C.c_double), _p(parent, C.c_int32), _p(ef, C.c_double),
+                             _p(et, C.c_double), C.byref(n), C.byref(it), C.byref(gi))
+    k = n.value
+    res = dict(x=x[:k], y=y[:k], yaw=yaw[:k], cost=cost[:k], parent=parent[:k], edge_from=ef[:k], edge_to=et[:k],
+               n=k, iters_done=it.value, goal_index=gi.value)
+    res["path"] = rs_final_course(res, start, goal, curvature, step_size, math_mode)
+    return res
+
+
+def rs_final_course(res, start, goal, curvature, step_size, math_mode):
+    """generate_final_course (rrt_06:1643-1651): reversed (x, y, yaw) course samples of every edge up to the root."""
+    gi = res["goal_index"]
+    if gi < 0:
+        return None
+    path = [[float(goal[0]), float(goal[1]), float(goal[2])]]
+    i = gi
+    while res["parent"][i] >= 0:
+        r = reeds_shepp(res["edge_from"][i], res["edge_to"][i], curvature, step_size, math_mode, max_pts=8192)
+        path.extend(r["pts"][::-1, 0:3].tolist())
+        i = int(res["parent"][i])
+    path.append([float(start[0]), float(start[1]), float(start[2])])
+    return path

@@ -28,6 +28,7 @@ FILES = {
     "rrt_07": ("10_path_planning_01_rrt_07_informed_rrt_star.py", 1330),
     "arm02": ("02_arm_obstacle_navigation.py", 283),
     "dub00": ("10_path_planning_00_dubins_path.py", 423),
+    "rrt_06": ("10_path_planning_01_rrt_06_rrt_star_reeds_shepp_path.py", 2005),
     "rs00": ("10_path_planning_00_reeds_shepp_path.py", 515),
 }
 

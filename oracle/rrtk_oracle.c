@@ -1361,3 +1361,140 @@ ORC_EXPORT int orc_reeds_shepp(double sx, double sy, double syaw, double gx, dou
     }
     return cnt;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* RRT*-Reeds-Shepp planning loop (rrt_06:1444-1913)                                      */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    double sx, sy, syaw, gx, gy, gyaw;
+    double expand_dis, robot_radius, connect_circle_dist, kappa, goal_yaw_th, goal_xy_th, step_size;
+    int32_t max_iter, n_obs, search_until_max_iter, math_mode;
+} orc_rs_params_t;
+#define RS_MAXPTS 8192
+typedef struct { int npts, free_; double end[3], lsum; } rs_edge_t;
+
+/* steer (rrt_06:1584-1604) + check_collision (:1749-1762) of one edge */
+static rs_edge_t rs_edge(const orc_rs_params_t *p, const double *obs3, const double *f, const double *t, double *buf) {
+    rs_edge_t e;
+    int32_t types[5], nseg = 0, npaths = 0;
+    double lengths[5], bl = 0.0;
+    int n = orc_reeds_shepp(f[0], f[1], f[2], t[0], t[1], t[2], p->kappa, p->step_size, p->math_mode, types, lengths, &nseg,
+                            &bl, &npaths, buf, RS_MAXPTS);
+    e.npts = n; e.free_ = 0; e.lsum = 0.0;
+    e.end[0] = e.end[1] = e.end[2] = 0.0;
+    if (n == 0) return e;
+    if (n > RS_MAXPTS) n = RS_MAXPTS;
+    e.end[0] = buf[4 * (n - 1)]; e.end[1] = buf[4 * (n - 1) + 1]; e.end[2] = buf[4 * (n - 1) + 2];
+    for (int i = 0; i < nseg; i++) e.lsum = e.lsum + fabs(lengths[i]); /* sum([abs(l) ...]) over np.float64 items: plain adds */
+    int ok = 1;
+    for (int o = 0; o < p->n_obs && ok; o++) {
+        double ox = obs3[3 * o], oy = obs3[3 * o + 1], size = obs3[3 * o + 2], mn = INFINITY;
+        for (int k = 0; k < n; k++) {
+            double dx = ox - buf[4 * k], dy = oy - buf[4 * k + 1], dd = dx * dx + dy * dy;
+            if (dd < mn) mn = dd;
+        }
+        if (mn <= sq_libm(size + p->robot_radius)) ok = 0;
+    }
+    e.free_ = ok;
+    return e;
+}
+static int rs_best_goal(const orc_rs_params_t *p, int n, const double *x, const double *y, const double *yaw, const double *cost) {
+    int gi = -1;
+    double mc = INFINITY;
+    for (int i = 0; i < n; i++)
+        if (orc_hypot(x[i] - p->gx, y[i] - p->gy) <= p->goal_xy_th && fabs(yaw[i] - p->gyaw) <= p->goal_yaw_th && cost[i] < mc) {
+            mc = cost[i]; gi = i;
+        }
+    return gi;
+}
+/* arrays sized 2 * max_iter + 1 (try_goal_path can append a second node per iteration) */
+ORC_EXPORT int orc_rrtstar_rs_run(const orc_rs_params_t *p, const double *obs3, const double *stream3, double *x, double *y,
+                                  double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                                  int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index) {
+    const int mode = p->math_mode;
+    int cap = 2 * p->max_iter + 1, n = 1, it, gi = -1, done = 0;
+    double *buf = (double *)malloc(sizeof(double) * 4 * RS_MAXPTS);
+    double *dl = (double *)malloc(sizeof(double) * cap);
+    int *near = (int *)malloc(sizeof(int) * cap);
+    const double goal[3] = {p->gx, p->gy, p->gyaw};
+    x[0] = p->sx; y[0] = p->sy; yaw[0] = p->syaw; cost[0] = 0.0; parent[0] = -1;
+    for (it = 0; it < p->max_iter; it++) {
+        const double *rnd = stream3 + 3 * it;
+        int ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(mode, x[i] - rnd[0]) + sq(mode, y[i] - rnd[1]);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double from[3] = {x[ni], y[ni], yaw[ni]};
+        rs_edge_t e0 = rs_edge(p, obs3, from, rnd, buf);
+        int truthy = e0.npts > 0;
+        if (e0.npts > 0 && e0.free_) {
+            double nw[3] = {e0.end[0], e0.end[1], e0.end[2]};
+            double nnode = (double)(n + 1);
+            double r = p->connect_circle_dist * sqrt(log(nnode) / nnode);
+            if (p->expand_dis < r) r = p->expand_dis;
+            double r2 = sq_libm(r);
+            int n_near = 0;
+            for (int i = 0; i < n; i++) dl[i] = sq(mode, x[i] - nw[0]) + sq(mode, y[i] - nw[1]);
+            for (int i = 0; i < n; i++)
+                if (dl[i] <= r2) {
+                    int f = 0;
+                    while (dl[f] != dl[i]) f++;
+                    near[n_near++] = f;
+                }
+            truthy = 0;
+            int best = -1;
+            double mc = INFINITY;
+            for (int k = 0; k < n_near; k++) {
+                int i = near[k];
+                double fi[3] = {x[i], y[i], yaw[i]};
+                rs_edge_t e = rs_edge(p, obs3, fi, nw, buf);
+                double c = (e.npts > 0 && e.free_) ? cost[i] + orc_hypot(nw[0] - x[i], nw[1] - y[i]) : INFINITY;
+                if (c < mc) { mc = c; best = i; }
+            }
+            if (best >= 0) {
+                double fb[3] = {x[best], y[best], yaw[best]};
+                rs_edge_t e = rs_edge(p, obs3, fb, nw, buf);
+                int newi = n;
+                x[newi] = e.end[0]; y[newi] = e.end[1]; yaw[newi] = e.end[2]; cost[newi] = mc; parent[newi] = best;
+                memcpy(edge_from + 3 * newi, fb, sizeof fb);
+                memcpy(edge_to + 3 * newi, nw, sizeof nw);
+                n++;
+                truthy = 1;
+                double cp[3] = {e.end[0], e.end[1], e.end[2]};
+                for (int k = 0; k < n_near; k++) { /* rewire (:1865-1899), after the append */
+                    int i = near[k];
+                    double ti[3] = {x[i], y[i], yaw[i]};
+                    rs_edge_t ed = rs_edge(p, obs3, cp, ti, buf);
+                    if (ed.npts == 0) continue;
+                    double ecost = mc + orc_hypot(x[i] - cp[0], y[i] - cp[1]);
+                    if (ed.free_ && cost[i] > ecost) {
+                        x[i] = ed.end[0]; y[i] = ed.end[1]; yaw[i] = ed.end[2]; cost[i] = ecost; parent[i] = newi;
+                        memcpy(edge_from + 3 * i, cp, sizeof cp);
+                        memcpy(edge_to + 3 * i, ti, sizeof ti);
+                        dub_propagate(n, x, y, cost, parent, i);
+                    }
+                }
+                /* try_goal_path (:1572-1582): from the node as it is now */
+                double np_[3] = {x[newi], y[newi], yaw[newi]};
+                rs_edge_t eg = rs_edge(p, obs3, np_, goal, buf);
+                if (eg.npts > 0 && eg.free_) {
+                    x[n] = eg.end[0]; y[n] = eg.end[1]; yaw[n] = eg.end[2]; cost[n] = cost[newi] + eg.lsum; parent[n] = newi;
+                    memcpy(edge_from + 3 * n, np_, sizeof np_);
+                    memcpy(edge_to + 3 * n, goal, sizeof goal);
+                    n++;
+                }
+            }
+        }
+        if (!p->search_until_max_iter && truthy) {
+            gi = rs_best_goal(p, n, x, y, yaw, cost);
+            if (gi > 0) { it++; done = 1; break; }
+        }
+    }
+    if (!done) gi = rs_best_goal(p, n, x, y, yaw, cost);
+    if (gi <= 0) gi = -1; /* `if last_index:` -- index 0 is falsy */
+    *n_nodes = n; *iters_done = it; *goal_index = gi;
+    free(buf); free(dl); free(near);
+    return 0;
+}

@@ -15,6 +15,7 @@
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
 #include "rrtk_dubins.cuh"
+#include "rrtk_rs.cuh"
 
 namespace rrtk {
 
@@ -27,7 +28,30 @@ __host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap
     return (b + 15) & ~(size_t)15;
 }
 
-extern "C" __global__ void __launch_bounds__(DUB_WARPS_PER_CTA * 32, 3)
+// One steering edge by one lane, for either local planner.  STEER = 0: Dubins (rrt_05, steer returns None when
+// len(px) <= 1); STEER = 1: Reeds-Shepp (rrt_06, None when no course, `step` = its step_size).
+struct PEdge {
+    double ex, ey, eyaw, lsum;
+    bool valid, free_;
+};
+template <int STEER>
+__device__ __forceinline__ PEdge plan_edge(double sx, double sy, double syaw, double gx, double gy, double gyaw, double kappa,
+                                           double step, const double4 *obs, int n_obs) {
+    PEdge r;
+    if (STEER == 0) {
+        const DubEdge e = dubins_edge_lane(sx, sy, syaw, gx, gy, gyaw, kappa, step, obs, n_obs);
+        r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = 0.0; r.valid = e.npts > 1; r.free_ = e.free_;
+    } else {
+        const RsEdge e = rs_edge_lane(sx, sy, syaw, gx, gy, gyaw, kappa, step, obs, n_obs);
+        r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = e.lsum; r.valid = e.npts > 0; r.free_ = e.free_;
+    }
+    return r;
+}
+
+// STEER = 1 also runs rrt_06's try_goal_path after every append (:1572-1582): the new node is steered to the goal and
+// that node is appended too when its course is free, costing the Reeds-Shepp length (:1601).
+template <int STEER>
+__global__ void __launch_bounds__(DUB_WARPS_PER_CTA * 32, 3)
 rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goal6,
                       const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
                       const double *__restrict__ near_r2, const double *__restrict__ stream3, double2 *xy_all,
@@ -102,12 +126,12 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
             const int ni = bi;
             const double2 from = xy[ni];
             const double fyaw = yaw[ni];
-            DubEdge e0 = dubins_edge_lane(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs);  // uniform
-            bool truthy = e0.npts > 1;
+            const PEdge e0 = plan_edge<STEER>(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs);  // uniform
+            bool truthy = e0.valid;
             if (truthy && e0.free_) {
                 const double nx = e0.ex, ny = e0.ey, nyaw = e0.eyaw;
                 truthy = false;
-                if (n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
+                if (n + (STEER == 1 ? 1 : 0) >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
                 // find_near_nodes (rrt_05:1715-1739)
                 const double r2 = near_r2[n + 1];
                 int count = 0;
@@ -146,8 +170,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                 for (int k = lane; k < count; k += 32) {
                     const int i = near_idx[k];
                     const double2 a = xy[i];
-                    DubEdge e = dubins_edge_lane(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
-                    if (e.npts > 1 && e.free_) {
+                    const PEdge e = plan_edge<STEER>(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
+                    if (e.valid && e.free_) {
                         const double c = cost[i] + crm_hypot(nx - a.x, ny - a.y);
                         if (c < mc) { mc = c; bk = k; bex = e.ex; bey = e.ey; beyaw = e.eyaw; }
                     }
@@ -176,8 +200,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     for (int k = lane; k < count; k += 32) {
                         const int i = near_idx[k];
                         const double2 a = xy[i];
-                        DubEdge e = dubins_edge_lane(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
-                        flags[k] = (e.npts > 1 ? 1 : 0) | (e.free_ ? 2 : 0);
+                        const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
+                        flags[k] = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
                         nd[k] = mc + crm_hypot(a.x - cx, a.y - cy);
                         s_end[3 * k] = e.ex; s_end[3 * k + 1] = e.ey; s_end[3 * k + 2] = e.eyaw;
                     }
@@ -190,8 +214,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         const double2 a = xy[i];
                         const double ayaw = yaw[i];
                         if (fl & 4) {  // node i was re-parented (moved) earlier in this call: redo its edge
-                            DubEdge e = dubins_edge_lane(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
-                            fl = (e.npts > 1 ? 1 : 0) | (e.free_ ? 2 : 0);
+                            const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
+                            fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
                             ecost = mc + crm_hypot(a.x - cx, a.y - cy);
                             ex = e.ex; ey = e.ey; eyw = e.eyaw;
                         }
@@ -210,6 +234,22 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                                 if (near_idx[k2] == i) flags[k2] |= 4;
                             __syncwarp();
                             propagate_lists(i, xy, cost, links, qtail, lane);
+                        }
+                    }
+                    if (STEER == 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
+                        const double2 a = xy[newi];
+                        const double ayaw = yaw[newi];
+                        const PEdge eg = plan_edge<STEER>(a.x, a.y, ayaw, gx, gy, gyaw, kappa, step, obs, n_obs);  // uniform
+                        if (eg.valid && eg.free_) {
+                            if (lane == 0) {
+                                efrom[3 * n] = a.x; efrom[3 * n + 1] = a.y; efrom[3 * n + 2] = ayaw;
+                                eto[3 * n] = gx; eto[3 * n + 1] = gy; eto[3 * n + 2] = gyaw;
+                                xy[n] = make_double2(eg.ex, eg.ey); yaw[n] = eg.eyaw; cost[n] = cost[newi] + eg.lsum; parent[n] = newi;
+                                links[n] = make_int4(-1, -1, -1, 0);
+                                link_child(links, newi, n);
+                            }
+                            n++;
+                            __syncwarp();
                         }
                     }
                 }
@@ -231,19 +271,23 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
     }
 }
 
-int launch_rrtstar_dubins(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
+int launch_rrtstar_steer(int steer, const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
                           const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
                           double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
                           int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                           int32_t *workspace, unsigned int *counter, cudaStream_t s) {
     size_t smem = dub_warp_smem_bytes(p.near_cap, p.node_cap) * DUB_WARPS_PER_CTA;
     if (smem > 227 * 1024) return set_error(RRTK_ERR_INVALID, "near_cap/node_cap need more than 227 KB of shared memory");
-    cudaError_t e = cudaFuncSetAttribute(rrtstar_dubins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    typedef void (*kernel_t)(rrtk_dubins_params, const double *, const double4 *, const int32_t *, const double *, const double *,
+                             double2 *, double *, double *, int32_t *, double *, double *, int32_t *, int32_t *, int32_t *,
+                             int32_t *, int32_t *, unsigned int *);
+    const kernel_t kern = steer == 1 ? rrtstar_dubins_kernel<1> : rrtstar_dubins_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrtstar_dubins_kernel, DUB_WARPS_PER_CTA * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DUB_WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (per_sm < 1) per_sm = 1;
     long long want = ((long long)p.n_queries + DUB_WARPS_PER_CTA - 1) / DUB_WARPS_PER_CTA;
@@ -252,13 +296,30 @@ int launch_rrtstar_dubins(const rrtk_dubins_params &p, const double *start_goal6
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
-    rrtstar_dubins_kernel<<<(unsigned)grid, DUB_WARPS_PER_CTA * 32, smem, s>>>(
+    kern<<<(unsigned)grid, DUB_WARPS_PER_CTA * 32, smem, s>>>(
         p, start_goal6, reinterpret_cast<const double4 *>(obstacles), n_obs, near_r2, stream3,
         reinterpret_cast<double2 *>(xy), yaw, cost, parent, edge_from, edge_to, n_nodes, iters_done, goal_index,
         status, workspace, counter);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "rrtstar_dubins_kernel launch");
     return RRTK_OK;
+}
+
+int launch_rrtstar_dubins(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
+                          const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
+                          double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                          int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                          int32_t *workspace, unsigned int *counter, cudaStream_t s) {
+    return launch_rrtstar_steer(0, p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from, edge_to,
+                                n_nodes, iters_done, goal_index, status, workspace, counter, s);
+}
+int launch_rrtstar_rs(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
+                      const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
+                      double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                      int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                      int32_t *workspace, unsigned int *counter, cudaStream_t s) {
+    return launch_rrtstar_steer(1, p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from, edge_to,
+                                n_nodes, iters_done, goal_index, status, workspace, counter, s);
 }
 
 }  // namespace rrtk

@@ -16,161 +16,16 @@
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
 #include "rrtk_dubins.cuh"
+#include "rrtk_rs.cuh"
 
 namespace rrtk {
 
 constexpr int RS_WARPS = 4;
 
-// rs00:130-139: C fmod semantics, then wrap into [-pi, pi]
-static __device__ __forceinline__ double rs_mod2pi(double x) {
-    const double m = copysign(2.0 * D_PI, x);
-    double v = fmod(x, m);
-    if (v == 0.0) v = copysign(0.0, m);
-    if (v < -D_PI) v += 2.0 * D_PI;
-    else if (v > D_PI) v -= 2.0 * D_PI;
-    return v;
-}
-
-__device__ const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1},
-                                       {0, 2, 0, 2, -1}, {0, 2, 0, 2, -1},   {0, 2, 1, 0, -1},  {0, 2, 1, 2, -1},  {0, 1, 2, 0, -1},
-                                       {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
-__device__ const int8_t RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
-
-// the path functions of rs00:166-363 in path_functions order; true + travel distances, or false
-static __device__ __noinline__ bool rs_word(int f, double x, double y, double phi, double *d) {
-    const double pi = D_PI;
-    double sp, cp;
-    sincos_cr(phi, &sp, &cp);
-    double u, t, v, u1, theta, A;
-    if (f == 0) {
-        u = crm_hypot(x - sp, y - 1.0 + cp);
-        t = crm_atan2(y - 1.0 + cp, x - sp);
-        if (0.0 <= t && t <= pi) {
-            v = rs_mod2pi(phi - t);
-            if (0.0 <= v && v <= pi) { d[0] = t; d[1] = u; d[2] = v; return true; }
-        }
-        return false;
-    }
-    if (f == 1) {
-        u1 = crm_hypot(x + sp, y - 1.0 - cp);
-        const double t1 = crm_atan2(y - 1.0 - cp, x + sp);
-        u1 = u1 * u1;
-        if (u1 >= 4.0) {
-            u = sqrt(u1 - 4.0);
-            theta = crm_atan2(2.0, u);
-            t = rs_mod2pi(t1 + theta);
-            v = rs_mod2pi(t - phi);
-            if (t >= 0.0 && v >= 0.0) { d[0] = t; d[1] = u; d[2] = v; return true; }
-        }
-        return false;
-    }
-    const bool minus = f == 2 || f == 3 || f == 4 || f == 7 || f == 9;
-    const double zeta = minus ? x - sp : x + sp, eeta = minus ? y - 1 + cp : y - 1 - cp;
-    u1 = crm_hypot(zeta, eeta);
-    theta = crm_atan2(eeta, zeta);
-    switch (f) {
-        case 2:
-            if (u1 <= 4.0) {
-                A = crm_acos(0.25 * u1);
-                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(phi - t - u);
-                d[0] = t; d[1] = -u; d[2] = v; return true;
-            }
-            return false;
-        case 3:
-            if (u1 <= 4.0) {
-                A = crm_acos(0.25 * u1);
-                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(-phi + t + u);
-                d[0] = t; d[1] = -u; d[2] = -v; return true;
-            }
-            return false;
-        case 4:
-            if (u1 <= 4.0) {
-                u = crm_acos(1 - u1 * u1 * 0.125);
-                A = crm_asin(2 * crm_sin(u) / u1);
-                t = rs_mod2pi(-A + theta + pi / 2); v = rs_mod2pi(t - u - phi);
-                d[0] = t; d[1] = u; d[2] = -v; return true;
-            }
-            return false;
-        case 5:
-            if (u1 <= 2) {
-                A = crm_acos((u1 + 2) * 0.25);
-                t = rs_mod2pi(theta + A + pi / 2); u = rs_mod2pi(A); v = rs_mod2pi(phi - t + 2 * u);
-                if (t >= 0 && u >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = -u; d[3] = -v; return true; }
-            }
-            return false;
-        case 6: {
-            const double u2 = (20 - u1 * u1) / 16;
-            if (0 <= u2 && u2 <= 1) {
-                u = crm_acos(u2);
-                A = crm_asin(2 * crm_sin(u) / u1);
-                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -u; d[2] = -u; d[3] = v; return true; }
-            }
-            return false;
-        }
-        case 7:
-            if (u1 >= 2.0) {
-                u = sqrt(u1 * u1 - 4) - 2;
-                A = crm_atan2(2, sqrt(u1 * u1 - 4));
-                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi + pi / 2);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
-            }
-            return false;
-        case 8:
-            if (u1 >= 2.0) {
-                t = rs_mod2pi(theta + pi / 2); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
-            }
-            return false;
-        case 9:
-            if (u1 >= 2.0) {
-                u = sqrt(u1 * u1 - 4) - 2;
-                A = crm_atan2(sqrt(u1 * u1 - 4), 2);
-                t = rs_mod2pi(theta - A + pi / 2); v = rs_mod2pi(t - phi - pi / 2);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
-            }
-            return false;
-        case 10:
-            if (u1 >= 2.0) {
-                t = rs_mod2pi(theta); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
-            }
-            return false;
-        default:
-            if (u1 >= 4.0) {
-                u = sqrt(u1 * u1 - 4) - 4;
-                A = crm_atan2(2, sqrt(u1 * u1 - 4));
-                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
-                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -pi / 2; d[4] = v; return true; }
-            }
-            return false;
-    }
-}
-
 struct RsWarp {
     double d[48][5];
     int ok[48];
 };
-
-// interpolate (rs00:449-470); sm / cm = sin / cos(-origin_yaw), so / co = sin / cos(origin_yaw)
-static __device__ __forceinline__ void rs_interp(double dist, int type, double maxc, double ox, double oy, double oyaw,
-                                                 double so, double co, double sm, double cm, double *x, double *y, double *yaw) {
-    if (type == 1) {
-        *x = ox + dist / maxc * co;
-        *y = oy + dist / maxc * so;
-        *yaw = oyaw;
-    } else {
-        double sl, cl;
-        sincos_cr(dist, &sl, &cl);
-        const double ldx = sl / maxc;
-        const double ldy = type == 0 ? (1.0 - cl) / maxc : (1.0 - cl) / -maxc;
-        *yaw = type == 0 ? oyaw + dist : oyaw - dist;
-        const double gdx = cm * ldx + sm * ldy;
-        const double gdy = -sm * ldx + cm * ldy;
-        *x = ox + gdx;
-        *y = oy + gdy;
-    }
-}
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restrict__ from3, const double *__restrict__ to3,

@@ -1,0 +1,250 @@
+// rrtk_rs.cuh -- device functions of the Reeds-Shepp local planner (rs00:73-515 == rrt_06:1021-1437), shared by the batched
+// steering kernel (rrtk_rs.cu) and the RRT*-Reeds-Shepp planner kernel (rrtk_rrtstar_dubins.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "crmath.h"
+#include "rrtk_device.cuh"
+#include "rrtk_dubins.cuh"
+
+namespace rrtk {
+
+// rs00:130-139: C fmod semantics, then wrap into [-pi, pi]
+static __device__ __forceinline__ double rs_mod2pi(double x) {
+    const double m = copysign(2.0 * D_PI, x);
+    double v = fmod(x, m);
+    if (v == 0.0) v = copysign(0.0, m);
+    if (v < -D_PI) v += 2.0 * D_PI;
+    else if (v > D_PI) v -= 2.0 * D_PI;
+    return v;
+}
+
+static __device__ const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1}, {0, 2, 0, -1, -1},
+                                       {0, 2, 0, 2, -1}, {0, 2, 0, 2, -1},   {0, 2, 1, 0, -1},  {0, 2, 1, 2, -1},  {0, 1, 2, 0, -1},
+                                       {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
+static __device__ const int8_t RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
+
+// the path functions of rs00:166-363 in path_functions order; true + travel distances, or false
+static __device__ __noinline__ bool rs_word(int f, double x, double y, double phi, double *d) {
+    const double pi = D_PI;
+    double sp, cp;
+    sincos_cr(phi, &sp, &cp);
+    double u, t, v, u1, theta, A;
+    if (f == 0) {
+        u = crm_hypot(x - sp, y - 1.0 + cp);
+        t = crm_atan2(y - 1.0 + cp, x - sp);
+        if (0.0 <= t && t <= pi) {
+            v = rs_mod2pi(phi - t);
+            if (0.0 <= v && v <= pi) { d[0] = t; d[1] = u; d[2] = v; return true; }
+        }
+        return false;
+    }
+    if (f == 1) {
+        u1 = crm_hypot(x + sp, y - 1.0 - cp);
+        const double t1 = crm_atan2(y - 1.0 - cp, x + sp);
+        u1 = u1 * u1;
+        if (u1 >= 4.0) {
+            u = sqrt(u1 - 4.0);
+            theta = crm_atan2(2.0, u);
+            t = rs_mod2pi(t1 + theta);
+            v = rs_mod2pi(t - phi);
+            if (t >= 0.0 && v >= 0.0) { d[0] = t; d[1] = u; d[2] = v; return true; }
+        }
+        return false;
+    }
+    const bool minus = f == 2 || f == 3 || f == 4 || f == 7 || f == 9;
+    const double zeta = minus ? x - sp : x + sp, eeta = minus ? y - 1 + cp : y - 1 - cp;
+    u1 = crm_hypot(zeta, eeta);
+    theta = crm_atan2(eeta, zeta);
+    switch (f) {
+        case 2:
+            if (u1 <= 4.0) {
+                A = crm_acos(0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(phi - t - u);
+                d[0] = t; d[1] = -u; d[2] = v; return true;
+            }
+            return false;
+        case 3:
+            if (u1 <= 4.0) {
+                A = crm_acos(0.25 * u1);
+                t = rs_mod2pi(A + theta + pi / 2); u = rs_mod2pi(pi - 2 * A); v = rs_mod2pi(-phi + t + u);
+                d[0] = t; d[1] = -u; d[2] = -v; return true;
+            }
+            return false;
+        case 4:
+            if (u1 <= 4.0) {
+                u = crm_acos(1 - u1 * u1 * 0.125);
+                A = crm_asin(2 * crm_sin(u) / u1);
+                t = rs_mod2pi(-A + theta + pi / 2); v = rs_mod2pi(t - u - phi);
+                d[0] = t; d[1] = u; d[2] = -v; return true;
+            }
+            return false;
+        case 5:
+            if (u1 <= 2) {
+                A = crm_acos((u1 + 2) * 0.25);
+                t = rs_mod2pi(theta + A + pi / 2); u = rs_mod2pi(A); v = rs_mod2pi(phi - t + 2 * u);
+                if (t >= 0 && u >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 6: {
+            const double u2 = (20 - u1 * u1) / 16;
+            if (0 <= u2 && u2 <= 1) {
+                u = crm_acos(u2);
+                A = crm_asin(2 * crm_sin(u) / u1);
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -u; d[2] = -u; d[3] = v; return true; }
+            }
+            return false;
+        }
+        case 7:
+            if (u1 >= 2.0) {
+                u = sqrt(u1 * u1 - 4) - 2;
+                A = crm_atan2(2, sqrt(u1 * u1 - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi + pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 8:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta + pi / 2); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -v; return true; }
+            }
+            return false;
+        case 9:
+            if (u1 >= 2.0) {
+                u = sqrt(u1 * u1 - 4) - 2;
+                A = crm_atan2(sqrt(u1 * u1 - 4), 2);
+                t = rs_mod2pi(theta - A + pi / 2); v = rs_mod2pi(t - phi - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
+            }
+            return false;
+        case 10:
+            if (u1 >= 2.0) {
+                t = rs_mod2pi(theta); u = u1 - 2; v = rs_mod2pi(phi - t - pi / 2);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = u; d[2] = pi / 2; d[3] = -v; return true; }
+            }
+            return false;
+        default:
+            if (u1 >= 4.0) {
+                u = sqrt(u1 * u1 - 4) - 4;
+                A = crm_atan2(2, sqrt(u1 * u1 - 4));
+                t = rs_mod2pi(theta + A + pi / 2); v = rs_mod2pi(t - phi);
+                if (t >= 0 && v >= 0) { d[0] = t; d[1] = -pi / 2; d[2] = -u; d[3] = -pi / 2; d[4] = v; return true; }
+            }
+            return false;
+    }
+}
+
+// interpolate (rs00:449-470); sm / cm = sin / cos(-origin_yaw), so / co = sin / cos(origin_yaw)
+static __device__ __forceinline__ void rs_interp(double dist, int type, double maxc, double ox, double oy, double oyaw,
+                                                 double so, double co, double sm, double cm, double *x, double *y, double *yaw) {
+    if (type == 1) {
+        *x = ox + dist / maxc * co;
+        *y = oy + dist / maxc * so;
+        *yaw = oyaw;
+    } else {
+        double sl, cl;
+        sincos_cr(dist, &sl, &cl);
+        const double ldx = sl / maxc;
+        const double ldy = type == 0 ? (1.0 - cl) / maxc : (1.0 - cl) / -maxc;
+        *yaw = type == 0 ? oyaw + dist : oyaw - dist;
+        const double gdx = cm * ldx + sm * ldy;
+        const double gdy = -sm * ldx + cm * ldy;
+        *x = ox + gdx;
+        *y = oy + gdy;
+    }
+}
+
+
+// One Reeds-Shepp edge evaluated by ONE lane: reeds_shepp_path_planning + the sampled collision test -- steer
+// (rrt_06:1584-1604) and check_collision (:1749-1762).  npts = len(px) (0: steer returns None), lsum = sum(|lengths|).
+struct RsEdge {
+    double ex, ey, eyaw, lsum;
+    int npts;
+    bool free_;
+};
+
+static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                   double maxc, double step_size, const double4 *obs, int n_obs) {
+    RsEdge e;
+    e.ex = e.ey = e.eyaw = e.lsum = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    const double step = step_size * maxc;
+    const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
+    double s0, c0;
+    sincos_cr(syaw, &s0, &c0);
+    const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;
+    // generate_path + set_path in the reference's order; keep the first shortest inserted word
+    double ins_L[48], best_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, best_L = CUDART_INF;
+    int ins_code[48], n_ins = 0, best = -1;
+#pragma unroll 1
+    for (int cand = 0; cand < 48; cand++) {
+        const int f = cand >> 2, k = cand & 3, n = RS_N[f];
+        double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (!rs_word(f, (k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, d)) continue;
+        double tot = 0.0;
+        for (int i = 0; i < n; i++) tot += fabs(d[i]);
+        for (int i = 0; i < n; i++) {
+            const double a = fabs(d[i]);
+            if (0.1 * tot < a && a < step) return e;   // "Step size too large for Reeds-Shepp paths." -> no path at all
+        }
+        int code = n;
+        for (int i = 0; i < n; i++) {
+            const int t0 = RS_T[f][i];
+            code = code * 3 + ((k >= 2 && t0 != 1) ? 2 - t0 : t0);
+        }
+        bool same = false;
+        for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - tot) <= step;
+        if (same || tot <= step) continue;
+        ins_code[n_ins] = code; ins_L[n_ins] = tot; n_ins++;
+        if (fabs(tot / maxc) < best_L) {
+            best_L = fabs(tot / maxc); best = cand;
+            for (int i = 0; i < 5; i++) best_d[i] = (k == 1 || k == 3) ? -d[i] : d[i];   // timeflip
+        }
+    }
+    if (best < 0) return e;
+    const int f = best >> 2, k = best & 3, n = RS_N[f];
+    double sm0, cm0;
+    sincos_cr(-syaw, &sm0, &cm0);
+    bool hit = false;
+    int np = 0;
+    double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const double length = best_d[i];
+        lsum = lsum + fabs(length / maxc);
+        const int t0 = RS_T[f][i];
+        const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;
+        const double dd = length >= 0.0 ? step : -step;
+        long long na = length != 0.0 ? (long long)ceil((length - 0.0) / dd) : 0;
+        if (na < 0) na = 0;
+        double so, co, sm, cm;
+        sincos_cr(oyaw, &so, &co);
+        sincos_cr(-oyaw, &sm, &cm);
+        double lx = 0.0, ly = 0.0, lyaw = 0.0;
+#pragma unroll 1
+        for (long long j = 0; j <= na; j++) {
+            const double dist = j < na ? 0.0 + (double)j * dd : length;
+            rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+            const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
+            for (int o = 0; o < n_obs && !hit; o++) {
+                const double4 ob = obs[o];
+                const double ex = ob.x - wx, ey = ob.y - wy;
+                if (ex * ex + ey * ey <= ob.w) hit = true;
+            }
+        }
+        ox = lx; oy = ly; oyaw = lyaw;
+        np += (int)(na + 1);
+    }
+    e.npts = np;
+    e.free_ = !hit;
+    e.lsum = lsum;
+    e.ex = cm0 * ox + sm0 * oy + sx;
+    e.ey = -sm0 * ox + cm0 * oy + sy;
+    e.eyaw = angle_mod_pi(oyaw + syaw);
+    return e;
+}
+
+}  // namespace rrtk

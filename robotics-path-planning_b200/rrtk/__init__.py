@@ -6,10 +6,11 @@ from .informed import InformedRRTStar  # noqa: F401
 from . import dubins  # noqa: F401
 from .dubins import plan_dubins_path  # noqa: F401
 from .dubins_planner import RRTStarDubins  # noqa: F401
+from .rs_planner import RRTStarReedsShepp  # noqa: F401
 from .arm import NLinkArm, get_occupancy_grid, get_occupancy_grids, astar_torus, astar_torus_batch  # noqa: F401
 from . import smoothing, reeds_shepp  # noqa: F401
 from .reeds_shepp import reeds_shepp_path_planning  # noqa: F401
 from .smoothing import path_smoothing, get_path_length  # noqa: F401
 
-__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "RRTStarDubins", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "astar_torus", "astar_torus_batch", "path_smoothing", "get_path_length", "smoothing", "reeds_shepp", "reeds_shepp_path_planning", "RrtkError",
+__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "RRTStarDubins", "RRTStarReedsShepp", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "astar_torus", "astar_torus_batch", "path_smoothing", "get_path_length", "smoothing", "reeds_shepp", "reeds_shepp_path_planning", "RrtkError",
            "lib", "LIB_PATH"]

@@ -77,6 +77,7 @@ _SIGS = {
     "rrtk_informed_tree_run_dev": (C.c_int, [C.POINTER(InformedTreeParams)] + [_VP] * 10 + [C.c_int64, _VP]),
     "rrtk_tree_exchange_probe_dev": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, C.c_int64, _VP]),
     "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
+    "rrtk_rrtstar_rs_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_reeds_shepp_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,

@@ -43,20 +43,20 @@ class Node:
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0,
               connect_circle_dist=50.0, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5,
-              search_until_max_iter=True, near_cap=256, device=None):
-    """Q RRT*-Dubins queries in one launch.  starts/goals [Q, 3]; streams [Q, max_iter, 3].
-    Returns a list of dicts (numpy arrays trimmed to n_nodes)."""
+              search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1):
+    """Q RRT*-Dubins (steer="dubins") or RRT*-Reeds-Shepp (steer="rs", rrt_06) queries in one launch.
+    starts/goals [Q, 3]; streams [Q, max_iter, 3].  Returns a list of dicts (numpy arrays trimmed to n_nodes)."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
     goals = np.asarray(goals, dtype=np.float64).reshape(-1, 3)
     q = starts.shape[0]
-    cap = max_iter + 1
+    cap = max_iter + 1 if steer == "dubins" else 2 * max_iter + 1   # try_goal_path can append a second node
     rows, counts = engine.pack_obstacles(obstacle_lists, robot_radius)
     p = _lib.DubinsParams()
     p.n_queries, p.max_iter, p.node_cap, p.obs_stride, p.near_cap = q, max_iter, cap, rows.shape[1], near_cap
     p.search_until_max_iter = int(bool(search_until_max_iter))
-    p.curvature, p.step_size = float(curvature), 0.1
+    p.curvature, p.step_size = float(curvature), 0.1 if steer == "dubins" else float(step_size)
     p.goal_xy_th, p.goal_yaw_th = float(goal_xy_th), float(goal_yaw_th)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     with torch.cuda.device(dev):
@@ -68,12 +68,13 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
         xy, yaw, cost, parent = f64(q, cap, 2), f64(q, cap), f64(q, cap), i32(q, cap)
         ef, et = f64(q, cap, 3), f64(q, cap, 3)
         n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, 4 * cap)
-        rc = _lib.lib().rrtk_rrtstar_dubins_run_dev(
+        entry = _lib.lib().rrtk_rrtstar_dubins_run_dev if steer == "dubins" else _lib.lib().rrtk_rrtstar_rs_run_dev
+        rc = entry(
             C.byref(p), d_sg.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_r2.data_ptr(), d_st.data_ptr(),
             xy.data_ptr(), yaw.data_ptr(), cost.data_ptr(), parent.data_ptr(), ef.data_ptr(), et.data_ptr(),
             n_nodes.data_ptr(), iters.data_ptr(), gi.data_ptr(), status.data_ptr(), ws.data_ptr(),
             torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "rrtk_rrtstar_dubins_run_dev")
+        _lib.check(rc, "rrtk_rrtstar_dubins_run_dev" if steer == "dubins" else "rrtk_rrtstar_rs_run_dev")
         h = {k: v.cpu().numpy() for k, v in dict(xy=xy, yaw=yaw, cost=cost, parent=parent, ef=ef, et=et, n=n_nodes,
                                                  it=iters, gi=gi, st=status).items()}
     out = []
