@@ -60,6 +60,10 @@ RRTK_API int rrtk_version(void);
 RRTK_API const char *rrtk_last_error(void);
 /* number of CUDA devices visible, or a negative status */
 RRTK_API int rrtk_device_count(void);
+/* sizeof of the parameter / result structs as this library was compiled (bindings check their own layout against it):
+ * 0 rrtk_rrtstar_params, 1 rrtk_informed_params, 2 rrtk_informed_tree_params, 3 rrtk_informed_tree_result,
+ * 4 rrtk_dubins_params; -1 for an unknown index */
+RRTK_API int rrtk_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
  * Sobol generator: i4_sobol (rrt_04:230-503) in closed form (Gray-code order, 30 bits, <= 40 dims,

@@ -116,6 +116,17 @@ int rrtk_device_count(void) {
     return n;
 }
 
+int rrtk_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(rrtk_rrtstar_params);
+        case 1: return (int)sizeof(rrtk_informed_params);
+        case 2: return (int)sizeof(rrtk_informed_tree_params);
+        case 3: return (int)sizeof(rrtk_informed_tree_result);
+        case 4: return (int)sizeof(rrtk_dubins_params);
+        default: return -1;
+    }
+}
+
 int rrtk_sobol_table(int dim, uint32_t *v_host) {
     if (dim < 1 || dim > SOBOL_DIM_MAX || !v_host) return set_error(RRTK_ERR_INVALID, "1 <= dim <= 40");
     static const SobolTable t = make_sobol_table();

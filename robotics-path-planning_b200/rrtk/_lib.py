@@ -67,6 +67,7 @@ _SIGS = {
     "rrtk_version": (C.c_int, []),
     "rrtk_last_error": (C.c_char_p, []),
     "rrtk_device_count": (C.c_int, []),
+    "rrtk_sizeof": (C.c_int, [C.c_int]),
     "rrtk_sobol_fill_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP, _VP]),
     "rrtk_sobol_fill_host": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _VP]),
     "rrtk_sobol_table": (C.c_int, [C.c_int, _VP]),

@@ -43,6 +43,15 @@ def test_params_struct_layout_matches_header():
     assert C.sizeof(_lib.RRTStarParams) == 144
 
 
+def test_every_struct_layout_matches_the_compiled_library():
+    from rrtk import _lib
+    L = _lib.lib()
+    for which, cls in enumerate((_lib.RRTStarParams, _lib.InformedParams, _lib.InformedTreeParams, _lib.InformedTreeResult,
+                                 _lib.DubinsParams)):
+        assert L.rrtk_sizeof(which) == C.sizeof(cls), cls.__name__
+    assert L.rrtk_sizeof(99) == -1
+
+
 def test_bad_params_rejected_without_gpu():
     from rrtk import _lib, engine
     L = _lib.lib()
