@@ -214,6 +214,7 @@ RRTK_API int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *
  *   coord_bound: an upper bound on |coordinate| of anything in the scene (sets the tolerance band inside which a
  *     near edge falls back to the reference's exact end-point arithmetic; results do not depend on it);
  *   grid: 0 = one CTA per SM; tests pass small values to exercise the multi-pass scans on small trees.
+ *   In batched mode result.reextends counts the batches cut short, result.cycles[0] the batches run.
  * outputs: xy [node_cap][2], cost [node_cap], parent [node_cap], path [path_cap][2] (best-path snapshot),
  *   result (device struct).  workspace: rrtk_informed_tree_workspace_bytes(node_cap) bytes of device memory.
  * ------------------------------------------------------------------------------------------- */
@@ -223,7 +224,9 @@ typedef struct rrtk_informed_tree_params {
     int32_t n_obs;
     int32_t path_cap;
     int32_t grid;
-    int32_t pad_;
+    int32_t batch;        /* samples per pass: 0 / 1 = one (speculative-extension kernel); 2..8 = batched kernel, which
+                             advances up to `batch` iterations per pair of tree scans and cuts a batch short wherever the
+                             sequential semantics would differ (results are identical for every value) */
     double expand_dis;
     double start_goal[4]; /* sx, sy, gx, gy */
     double rot[4];        /* c00, c01, c10, c11 of C (rrt_07:1063-1068) */

@@ -309,7 +309,7 @@ __device__ __noinline__ void draw_sample(const TreeArgs &A, int it, double c_bes
 
 // One warp extends `from` towards the sample: get_new_node (rrt_07:1216-1224), line_cost, check_collision(nearest,
 // theta, d) (:1271-1276), is_near_goal (:1226-1230) and the goal segment test (:1096); lanes split the circles.
-__device__ __noinline__ void extend_candidate(const TreeSmem &S, int n_obs, double fx, double fy, double tx, double ty,
+__device__ __noinline__ void extend_candidate(const double4 *s_obs, int n_obs, double fx, double fy, double tx, double ty,
                                               double ed, double gx, double gy, double &nx, double &ny, int &cf) {
     const int lane = threadIdx.x & 31;
     double st, ct;
@@ -320,7 +320,7 @@ __device__ __noinline__ void extend_candidate(const TreeSmem &S, int n_obs, doub
     const bool near_goal = crm_hypot(nx - gx, ny - gy) < ed;
     bool he = false, hg = false;
     for (int j = lane; j < n_obs; j += 32) {
-        const double4 o = S.obs[j];
+        const double4 o = s_obs[j];
         he |= seg_dd(fx, fy, ex, ey, o.x, o.y) <= o.w;
         if (near_goal) hg |= seg_dd(nx, ny, gx, gy, o.x, o.y) <= o.w;
     }
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
             double rx, ry, nx, ny;
             int cf;
             draw_sample(A, 0, c_best, c_min, xc, yc, rx, ry);
-            extend_candidate(S, n_obs, sx, sy, rx, ry, ed, gx, gy, nx, ny, cf);
+            extend_candidate(S.obs, n_obs, sx, sy, rx, ry, ed, gx, gy, nx, ny, cf);
             if (lane == 0) { S.c_nx = nx; S.c_ny = ny; S.c_cf = cf; }
         } else if (warp == 1 && A.p.max_iter > 1) {
             double a, b;
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
             }
             double cx = 0.0, cy = 0.0;
             int cf = 0;
-            if (want_nn && bi != NO_IDX) extend_candidate(S, n_obs, bx, by, tx, ty, ed, gx, gy, cx, cy, cf);
+            if (want_nn && bi != NO_IDX) extend_candidate(S.obs, n_obs, bx, by, tx, ty, ed, gx, gy, cx, cy, cf);
             if (lane == 0) { S.c_d2 = want_nn ? bd : INF; S.c_idx = want_nn ? bi : NO_IDX; S.c_nx = cx; S.c_ny = cy; S.c_cf = cf; }
         } else {
             // ---- hits: choose_parent candidates among the owned hits (rrt_07:1110-1135) ----
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
                 if (warp == 0) {
                     double cx, cy;
                     int cf;
-                    extend_candidate(S, n_obs, nx, ny, s1x, s1y, ed, gx, gy, cx, cy, cf);
+                    extend_candidate(S.obs, n_obs, nx, ny, s1x, s1y, ed, gx, gy, cx, cy, cf);
                     if (lane == 0) { S.c_nx = cx; S.c_ny = cy; S.c_cf = cf; }
                 }
                 __syncthreads();
@@ -726,6 +726,529 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
 }
 
 
+// ================================================================================================================
+// Batched form: B samples per pass ("batch-parallel sampling", BASELINE config 3).  The sequential semantics are kept
+// exactly by only batching samples that provably do not interact, and cutting the batch short where they might:
+//   pass A   nearest of the B samples among the nodes that exist at the batch start (one scan, B argmins);
+//   exchange winners; warp k extends winner k (exact leaf math, B warps in parallel on the same code);
+//   cut #1   sample j leaves the batch (and everything after it) if an accepted new node i < j is nearer to s_j than
+//            its winner (its nearest would be an in-batch node), or lies within the near radius of new node j (it would be
+//            in j's near list); the batch also ends right after the first sample that connects to the goal (c_best, and
+//            with it every later sample, may change);
+//   pass B   near hits of all accepted new nodes in one scan; a node hit by two samples marks the later one;
+//   exchange best parent per sample + the masks (overlap, equal-d^2, coincident);
+//   cut #2   the batch ends before the first sample whose near list overlaps an earlier one (its costs could have been
+//            rewired) or that needs the exact equal-d^2 resolution (then it runs alone, first in the next batch);
+//   apply    appends and rewires of the surviving samples (disjoint near lists: any order), goal bookkeeping.
+// Samples cut from a batch are simply redone by the next one, against the tree as it then is.
+// ================================================================================================================
+constexpr int TB_MAX = 8;
+constexpr int TB_REC = 16;           // 16-byte pieces per CTA record
+constexpr int TB_SUB_BITS = TREE_TAB_BITS - 3;   // one hash sub-table per sample
+constexpr int TB_HCAP = 4096;        // near hits of one batch owned by one CTA (shared memory); a fuller batch is retried smaller
+
+struct BatchSmem {
+    double4 obs[TREE_OBS_CAP];
+    short cull[TB_MAX][TREE_OBS_CAP];
+    int hit_tag[TB_HCAP], hit_slot[TB_HCAP];
+    unsigned char hit_k[TB_HCAP];
+    double hit_x[TB_HCAP], hit_y[TB_HCAP], hit_d[TB_HCAP], hit_c[TB_HCAP];
+    double w_d[TB_MAX][TREE_NW];      // per-warp partial (value, index) per sample
+    int w_i[TB_MAX][TREE_NW];
+    int w_m[TREE_NW], w_h[TB_MAX][TREE_NW];
+    double q_d[TB_MAX][TREE_NW];      // per-warp partial of the cross-CTA reduce
+    int q_i[TB_MAX][TREE_NW], q_h[TB_MAX][TREE_NW], q_m[TREE_NW];
+    double sx[TB_MAX], sy[TB_MAX];    // samples
+    double fx[TB_MAX], fy[TB_MAX];    // nearest node position
+    double nx[TB_MAX], ny[TB_MAX];    // extended node
+    double nn_d2[TB_MAX], cp_cost[TB_MAX], plen;
+    int nn_idx[TB_MAX], cf[TB_MAX], cp_idx[TB_MAX], hits[TB_MAX], ncull[TB_MAX];
+    int nhit, g_mask, gcount;
+    unsigned dupbits[1];
+};
+
+// counter barrier of the batch kernel (records were stored before by this CTA's warps)
+__device__ __forceinline__ void batch_sync(const TreeWs &ws, unsigned &seq, int G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        atomicAdd(ws.bar + 8, 1ull);
+        const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
+        unsigned long long v;
+        do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+    seq++;
+}
+
+// Cross-CTA argmin per sample.  In: S.w_d / w_i [k][warp] per-warp partials of this CTA (and S.w_h hit counts, S.w_m
+// masks when `with_masks`).  Out: S.q_d[k][0], S.q_i[k][0] (+ S.hits[k], S.g_mask), valid for every thread after return.
+__device__ __noinline__ void batch_exchange(BatchSmem &S, const TreeWs &ws, unsigned &seq, int G, int B, bool with_masks) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint4 *recs = ws.rec + (size_t)(seq & 1u) * G * TB_REC;
+    if (warp < B) {   // warp k reduces the CTA's partials of sample k and stores its piece
+        const bool in = lane < TREE_NW;
+        const double v = in ? S.w_d[warp][lane] : CUDART_INF;
+        const int i = in ? S.w_i[warp][lane] : NO_IDX;
+        const int src = warp_argmin_lane(v, i);
+        const double bv = __shfl_sync(0xffffffffu, v, src);
+        const int bi = __shfl_sync(0xffffffffu, i, src);
+        const int hs = with_masks ? (int)__reduce_add_sync(0xffffffffu, in ? (unsigned)S.w_h[warp][lane] : 0u) : 0;
+        if (lane == 0) __stcg(recs + (size_t)blockIdx.x * TB_REC + warp, piece(bv, bi, (unsigned)hs));
+    } else if (warp == TB_MAX && with_masks) {
+        const int m = (int)__reduce_or_sync(0xffffffffu, lane < TREE_NW ? (unsigned)S.w_m[lane] : 0u);
+        if (lane == 0) __stcg(recs + (size_t)blockIdx.x * TB_REC + TB_MAX, make_uint4((unsigned)m, 0u, 0u, 0u));
+    }
+    batch_sync(ws, seq, G);
+    double v[TB_MAX];
+    int i[TB_MAX], h[TB_MAX], m = 0;
+#pragma unroll
+    for (int k = 0; k < TB_MAX; k++) { v[k] = CUDART_INF; i[k] = NO_IDX; h[k] = 0; }
+    if (tid < G) {
+        const uint4 *r = recs + (size_t)tid * TB_REC;
+#pragma unroll
+        for (int k = 0; k < TB_MAX; k++)
+            if (k < B) { const uint4 pc = __ldcg(r + k); v[k] = piece_f64(pc); i[k] = (int)pc.z; h[k] = (int)pc.w; }
+        if (with_masks) m = (int)__ldcg(r + TB_MAX).x;
+    }
+    const int nwq = (G + 31) >> 5;
+    if (warp < nwq) {
+#pragma unroll
+        for (int k = 0; k < TB_MAX; k++) {
+            if (k >= B) break;
+            const int src = warp_argmin_lane(v[k], i[k]);
+            const double bv = __shfl_sync(0xffffffffu, v[k], src);
+            const int bi = __shfl_sync(0xffffffffu, i[k], src);
+            const int hs = with_masks ? (int)__reduce_add_sync(0xffffffffu, (unsigned)h[k]) : 0;
+            if (lane == 0) { S.q_d[k][warp] = bv; S.q_i[k][warp] = bi; S.q_h[k][warp] = hs; }
+        }
+        if (with_masks) { m = (int)__reduce_or_sync(0xffffffffu, (unsigned)m); if (lane == 0) S.q_m[warp] = m; }
+    }
+    __syncthreads();
+    if (tid < B) {   // thread k combines sample k
+        double bv = CUDART_INF;
+        int bi = NO_IDX, hs = 0;
+        for (int w = 0; w < nwq; w++) { lexmin(bv, bi, S.q_d[tid][w], S.q_i[tid][w]); hs += S.q_h[tid][w]; }
+        S.q_d[tid][0] = bv; S.q_i[tid][0] = bi; S.hits[tid] = hs;
+    } else if (tid == TB_MAX && with_masks) {
+        int mm = 0;
+        for (int w = 0; w < nwq; w++) mm |= S.q_m[w];
+        S.g_mask = mm;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const TreeArgs A) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    BatchSmem &S = *reinterpret_cast<BatchSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const TreeWs &ws = A.ws;
+    const double INF = CUDART_INF;
+    const double ed = A.p.expand_dis;
+    const double sx0 = A.p.start_goal[0], sy0 = A.p.start_goal[1], gx = A.p.start_goal[2], gy = A.p.start_goal[3];
+    const int n_obs = A.p.n_obs;
+    const int BMAX = A.p.batch < 1 ? 1 : (A.p.batch > TB_MAX ? TB_MAX : A.p.batch);
+    const double band_k = 1e-12 * A.p.coord_bound * A.p.coord_bound;
+    const int stride = G * TREE_T;
+    const long long seg = (long long)cta * ws.seg_cap;
+
+    for (int j = tid; j < n_obs; j += TREE_T) S.obs[j] = A.obstacles[j];
+    for (int j = tid; j < (ws.seg_cap >> 5); j += TREE_T) S.dupbits[j] = 0u;
+    if (cta == 0 && tid == 0) { A.xy[0] = make_double2(sx0, sy0); A.cost[0] = 0.0; A.parent[0] = -1; }
+    __syncthreads();
+    unsigned long long bphase = 0;
+    unsigned seq = 0;
+    grid_barrier(ws, bphase, G);
+
+    int n = 1, status = RRTK_Q_OK, plen_best = 0, it = 0;
+    double c_best = INF;
+    const double c_min = crm_hypot(sx0 - gx, sy0 - gy);
+    const double xc = (sx0 + gx) / 2.0, yc = (sy0 + gy) / 2.0;
+    long long total_hits = 0, n_batches = 0;
+    int n_slow = 0, n_goal = 0, n_redo = 0, n_cut = 0;
+    bool stop = false;
+    int blimit = BMAX;   // halved after a batch whose hit list did not fit, restored after a good one
+
+    while (it < A.p.max_iter && !stop) {
+        const int B = min(blimit, A.p.max_iter - it);
+        n_batches++;
+        // ---- samples (informed_sample, rrt_07:1145-1159) ----
+        if (warp < B) {
+            double a, b;
+            draw_sample(A, it + warp, c_best, c_min, xc, yc, a, b);
+            if (lane == 0) { S.sx[warp] = a; S.sy[warp] = b; }
+        }
+        if (tid == 0) { S.nhit = 0; S.gcount = 0; }
+        if (tid < TB_MAX) S.ncull[tid] = 0;
+        __syncthreads();
+        // ---- pass A: nearest of every sample among the owned nodes ----
+        {
+            double bd[TB_MAX], qx[TB_MAX], qy[TB_MAX];
+            int bi[TB_MAX];
+#pragma unroll
+            for (int k = 0; k < TB_MAX; k++) { bd[k] = INF; bi[k] = NO_IDX; qx[k] = k < B ? S.sx[k] : 0.0; qy[k] = k < B ? S.sy[k] : 0.0; }
+            for (long long base = (long long)cta * TREE_T + tid; base < n; base += (long long)TREE_UNROLL * stride) {
+                double2 a[TREE_UNROLL];
+                bool ok[TREE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < TREE_UNROLL; u++) {
+                    const long long i = base + (long long)u * stride;
+                    ok[u] = i < n;
+                    a[u] = ok[u] ? ld_xy(A.xy + i) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < TREE_UNROLL; u++) {
+                    if (!ok[u]) continue;
+                    const int i = (int)(base + (long long)u * stride);
+#pragma unroll
+                    for (int k = 0; k < TB_MAX; k++) {
+                        if (k >= B) break;
+                        const double ex = a[u].x - qx[k], ey = a[u].y - qy[k];
+                        const double e2 = ex * ex + ey * ey;
+                        if (e2 < bd[k]) { bd[k] = e2; bi[k] = i; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TB_MAX; k++) {
+                if (k >= B) break;
+                const int src = warp_argmin_lane(bd[k], bi[k]);
+                const double v = __shfl_sync(0xffffffffu, bd[k], src);
+                const int i = __shfl_sync(0xffffffffu, bi[k], src);
+                if (lane == 0) { S.w_d[k][warp] = v; S.w_i[k][warp] = i; }
+            }
+        }
+        __syncthreads();
+        batch_exchange(S, ws, seq, G, B, false);
+        // ---- warp k extends winner k (get_new_node + check_collision + goal tests, exact leaf math) ----
+        if (warp < B) {
+            const int wi = S.q_i[warp][0];
+            const double2 f = ld_xy(A.xy + wi);
+            double cx, cy;
+            int cf;
+            extend_candidate(S.obs, n_obs, f.x, f.y, S.sx[warp], S.sy[warp], ed, gx, gy, cx, cy, cf);
+            if (lane == 0) {
+                S.nn_idx[warp] = wi; S.nn_d2[warp] = S.q_d[warp][0]; S.fx[warp] = f.x; S.fy[warp] = f.y;
+                S.nx[warp] = cx; S.ny[warp] = cy; S.cf[warp] = cf;
+            }
+        }
+        __syncthreads();
+        // ---- cut #1 (uniform): in-batch dependencies, goal connection, capacity ----
+        int B1 = B, acc = 0, idx_of[TB_MAX], acc_mask = 0;
+        double r2_of[TB_MAX], r_of[TB_MAX];
+        bool goal_last = false;
+#pragma unroll
+        for (int j = 0; j < TB_MAX; j++) { idx_of[j] = -1; r2_of[j] = -1.0; r_of[j] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < TB_MAX; j++) {
+            if (j >= B1) break;
+            const bool acc_j = !(S.cf[j] & CF_BLOCKED);
+            const double2 rr2 = __ldg(A.near_rr2 + (n + acc));
+            bool dep = false;
+#pragma unroll
+            for (int i = 0; i < TB_MAX; i++) {
+                if (i >= j) break;
+                if (!((acc_mask >> i) & 1)) continue;
+                const double ax = S.nx[i] - S.sx[j], ay = S.ny[i] - S.sy[j];
+                dep |= ax * ax + ay * ay < S.nn_d2[j];                       // node i would be the nearest of sample j
+                if (acc_j) {
+                    const double bx = S.nx[i] - S.nx[j], by = S.ny[i] - S.ny[j];
+                    dep |= bx * bx + by * by <= rr2.y;                       // node i would be in the near list of node j
+                }
+            }
+            if (dep) { B1 = j; n_cut++; break; }
+            if (acc_j) {
+                if (n + acc >= A.p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; stop = true; B1 = j; break; }
+                idx_of[j] = n + acc; r2_of[j] = rr2.y; r_of[j] = rr2.x; acc_mask |= 1 << j; acc++;
+                if ((S.cf[j] & CF_NEAR_GOAL) && !(S.cf[j] & CF_GOAL_BLOCKED)) { B1 = j + 1; goal_last = true; break; }
+            }
+        }
+        if (B1 == 0) break;   // only when the tree is full
+        // ---- obstacle cull per accepted sample ----
+        for (int j = tid; j < n_obs; j += TREE_T) {
+            const double4 o = S.obs[j];
+#pragma unroll
+            for (int k = 0; k < TB_MAX; k++) {
+                if (k >= B1) break;
+                if (!((acc_mask >> k) & 1)) continue;
+                const double dx = o.x - S.nx[k], dy = o.y - S.ny[k];
+                const double lim = (r_of[k] + o.z) * (1.0 + 1e-9) + 1e-9;
+                if (dx * dx + dy * dy <= lim * lim) S.cull[k][atomicAdd(&S.ncull[k], 1)] = (short)j;
+            }
+        }
+        // ---- pass B: near hits of every accepted new node; a node hit twice marks the later sample ----
+        int ovl = 0, myhits[TB_MAX];
+#pragma unroll
+        for (int k = 0; k < TB_MAX; k++) myhits[k] = 0;
+        if (acc_mask) {
+            double px[TB_MAX], py[TB_MAX];
+#pragma unroll
+            for (int k = 0; k < TB_MAX; k++) { px[k] = k < B1 ? S.nx[k] : 0.0; py[k] = k < B1 ? S.ny[k] : 0.0; }
+            int chunk = 0;
+            for (long long base = (long long)cta * TREE_T + tid; base < n; base += (long long)TREE_UNROLL * stride, chunk += TREE_UNROLL) {
+                double2 a[TREE_UNROLL];
+                bool ok[TREE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < TREE_UNROLL; u++) {
+                    const long long i = base + (long long)u * stride;
+                    ok[u] = i < n;
+                    a[u] = ok[u] ? ld_xy(A.xy + i) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < TREE_UNROLL; u++) {
+                    if (!ok[u]) continue;
+                    const int i = (int)(base + (long long)u * stride);
+                    int m = 0;
+#pragma unroll
+                    for (int k = 0; k < TB_MAX; k++) {
+                        if (k >= B1) break;
+                        const double ax = a[u].x - px[k], ay = a[u].y - py[k];
+                        if (ax * ax + ay * ay <= r2_of[k]) { m |= 1 << k; myhits[k]++; }
+                    }
+                    if (m) {
+                        ovl |= m & (m - 1);
+                        const int li = (chunk + u) * TREE_T + tid;
+                        if (!((S.dupbits[li >> 5] >> (li & 31)) & 1u)) {
+                            for (int mm = m; mm; mm &= mm - 1) {
+                                const int k = __ffs(mm) - 1;
+                                const int pos = atomicAdd(&S.nhit, 1);
+                                if (pos < TB_HCAP) { S.hit_tag[pos] = i; S.hit_k[pos] = (unsigned char)k; S.hit_x[pos] = a[u].x; S.hit_y[pos] = a[u].y; }
+                                else ovl |= 1 << 24;   // hit list of this CTA is full: reported through the mask
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int H = min(S.nhit, TB_HCAP);
+        // ---- choose_parent candidates of the owned hits (rrt_07:1110-1135), per sample ----
+        int eq = 0, dupn = 0;
+        unsigned long long *tab = ws.tab + ((unsigned long long)(n_batches & 1) << TREE_TAB_BITS);
+#pragma unroll
+        for (int k = 0; k < TB_MAX; k++) if (lane == 0) { S.w_d[k][warp] = INF; S.w_i[k][warp] = NO_IDX; }
+        __syncwarp();
+        for (int e0 = 0; e0 < H; e0 += TREE_T) {
+            const int e = e0 + tid;
+            int k = -1, i = NO_IDX;
+            double c = INF;
+            if (e < H) {
+                i = S.hit_tag[e]; k = S.hit_k[e];
+                const double ax = S.hit_x[e], ay = S.hit_y[e], nx = S.nx[k], ny = S.ny[k];
+                const double c_i = ld_f64(A.cost + i);
+                const double qx = ax - nx, qy = ay - ny;
+                const double d2 = qx * qx + qy * qy;
+                const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
+                unsigned long long *sub = tab + ((unsigned long long)k << TB_SUB_BITS);
+                unsigned h = (unsigned)(splitmix64(key) >> (64 - TB_SUB_BITS));
+                unsigned long long old = atomicCAS(sub + h, TREE_EMPTY, key);
+                const double d = crm_hypot(nx - ax, ny - ay);
+                bool unsure = !(d > 1e-9), hitc = false;
+                for (int j = 0; j < S.ncull[k]; j++) {
+                    const double4 o = S.obs[S.cull[k][j]];
+                    const double dd = seg_dd(ax, ay, nx, ny, o.x, o.y);
+                    hitc |= dd <= o.w;
+                    unsure |= fabs(dd - o.w) <= band_k + 1e-12 * (dd + o.w);
+                }
+                bool free_e = !hitc;
+                if (unsure) {   // exact end point (rare)
+                    double s, cth;
+                    (void)crm_atan2_sincos(ny - ay, nx - ax, &s, &cth);
+                    const double ex = ax + cth * d, ey = ay + s * d;
+                    free_e = true;
+                    for (int j = 0; j < S.ncull[k] && free_e; j++) {
+                        const double4 o = S.obs[S.cull[k][j]];
+                        free_e = !(seg_dd(ax, ay, ex, ey, o.x, o.y) <= o.w);
+                    }
+                }
+                int slot = -1, tag = i;
+                if (d2 == 0.0) dupn |= 1 << k;
+                for (int probe = 0;; probe++) {
+                    if (old == TREE_EMPTY) { slot = (int)(((unsigned)k << TB_SUB_BITS) + h); break; }
+                    if (old == key || probe == TREE_PROBES) { eq |= 1 << k; break; }
+                    h = (h + 1) & ((1u << TB_SUB_BITS) - 1u);
+                    old = atomicCAS(sub + h, TREE_EMPTY, key);
+                }
+                if (free_e) { tag |= HIT_FREE; c = c_i + d; }
+                S.hit_tag[e] = tag; S.hit_slot[e] = slot; S.hit_d[e] = d; S.hit_c[e] = c_i;
+            }
+            // per-sample partial minimum of this round, folded into the warp's running partial
+#pragma unroll
+            for (int kk = 0; kk < TB_MAX; kk++) {
+                if (kk >= B1) break;
+                const double v = k == kk ? c : INF;
+                const int src = warp_argmin_lane(v, k == kk ? i : NO_IDX);
+                const double bv = __shfl_sync(0xffffffffu, v, src);
+                const int bi = __shfl_sync(0xffffffffu, k == kk ? i : NO_IDX, src);
+                if (lane == 0) lexmin(S.w_d[kk][warp], S.w_i[kk][warp], bv, bv < INF ? bi : NO_IDX);
+            }
+        }
+        {
+            const int mk = (int)__reduce_or_sync(0xffffffffu, (unsigned)(ovl | (eq << 8) | (dupn << 16)));
+#pragma unroll
+            for (int k = 0; k < TB_MAX; k++) {
+                const int hs = (int)__reduce_add_sync(0xffffffffu, (unsigned)myhits[k]);
+                if (lane == 0) S.w_h[k][warp] = hs;
+            }
+            if (lane == 0) S.w_m[warp] = mk;
+        }
+        __syncthreads();
+        batch_exchange(S, ws, seq, G, B1, true);
+        const int gm = S.g_mask;
+        if ((gm >> 24) & 1) {   // some CTA's hit list overflowed: nothing was applied yet -- undo the hash inserts and retry smaller
+            for (int e = tid; e < H; e += TREE_T) { const int slot = S.hit_slot[e]; if (slot >= 0) tab[slot] = TREE_EMPTY; }
+            if (B == 1) { status |= RRTK_Q_NEAR_OVERFLOW; break; }
+            blimit = B / 2;
+            __syncthreads();
+            continue;
+        }
+        blimit = BMAX;
+        // ---- cut #2: overlapping near lists / equal-d^2 resolution ----
+        int Be = B1;
+        {
+            const int bad = ((gm & 0xff) | ((gm >> 8) & 0xff)) & ~1;   // sample 0 cannot overlap; its equal-d^2 case is below
+            if (bad) { Be = __ffs(bad) - 1; if (Be < B1) n_cut++; }
+        }
+        if (tid < TB_MAX) { S.cp_cost[tid] = S.q_d[tid][0]; S.cp_idx[tid] = S.q_i[tid][0]; }
+        __syncthreads();
+        if ((gm >> 8) & 1) {   // sample 0 has two hits at different positions with equal d^2: exact `.index()` shadowing
+            n_slow++;
+            Be = 1;
+            for (int e = tid; e < H; e += TREE_T)
+                if (S.hit_k[e] == 0) {
+                    const int i = S.hit_tag[e] & HIT_MASK;
+                    const double qx = S.hit_x[e] - S.nx[0], qy = S.hit_y[e] - S.ny[0];
+                    const int pos = atomicAdd(&S.gcount, 1);
+                    __stcg(ws.g_idx + seg + pos, i);
+                    __stcg(ws.g_d2 + seg + pos, qx * qx + qy * qy);
+                }
+            __syncthreads();
+            if (tid == 0) __stcg(ws.g_cnt + cta, S.gcount);
+            grid_barrier(ws, bphase, G);
+            double cc = INF;
+            int ci = NO_IDX;
+            for (int e = tid; e < H; e += TREE_T) {
+                if (S.hit_k[e] != 0) continue;
+                int tag = S.hit_tag[e];
+                const int i = tag & HIT_MASK;
+                const double qx = S.hit_x[e] - S.nx[0], qy = S.hit_y[e] - S.ny[0];
+                const double d2 = qx * qx + qy * qy;
+                bool shadow = false;
+                for (int c2 = 0; c2 < G && !shadow; c2++) {
+                    const int cnt = ld_i32(ws.g_cnt + c2);
+                    const long long s2 = (long long)c2 * ws.seg_cap;
+                    for (int q = 0; q < cnt; q++)
+                        if (ld_i32(ws.g_idx + s2 + q) < i && ld_f64(ws.g_d2 + s2 + q) == d2) { shadow = true; break; }
+                }
+                if (shadow) { tag |= HIT_SHADOW; S.hit_tag[e] = tag; }
+                if (!(tag & HIT_SHADOW) && (tag & HIT_FREE)) lexmin(cc, ci, S.hit_c[e] + S.hit_d[e], i);
+            }
+            {
+                const int src = warp_argmin_lane(cc, ci);
+                cc = __shfl_sync(0xffffffffu, cc, src); ci = __shfl_sync(0xffffffffu, ci, src);
+                if (lane == 0) { S.w_d[0][warp] = cc; S.w_i[0][warp] = cc < INF ? ci : NO_IDX; S.w_h[0][warp] = 0; S.w_m[warp] = 0; }
+            }
+            __syncthreads();
+            batch_exchange(S, ws, seq, G, 1, true);
+            if (tid == 0) { S.cp_cost[0] = S.q_d[0][0]; S.cp_idx[0] = S.q_i[0][0]; }
+            __syncthreads();
+        }
+        // ---- apply: append + rewire (rrt_07:1232-1246) for the surviving samples ----
+        double ncost_of[TB_MAX];
+        int npar_of[TB_MAX], n_acc = 0;
+#pragma unroll
+        for (int k = 0; k < TB_MAX; k++) {
+            ncost_of[k] = INF; npar_of[k] = -1;
+            if (k >= Be) continue;
+            total_hits += S.hits[k];
+            if (!((acc_mask >> k) & 1)) continue;
+            if (S.cp_idx[k] != NO_IDX && S.cp_cost[k] < INF) { ncost_of[k] = S.cp_cost[k]; npar_of[k] = S.cp_idx[k]; }
+            else { ncost_of[k] = ld_f64(A.cost + S.nn_idx[k]) + ed; npar_of[k] = S.nn_idx[k]; }
+            const int newi = idx_of[k];
+            if (cta == (newi / TREE_T) % G && tid == 0) {
+                __stcg(A.xy + newi, make_double2(S.nx[k], S.ny[k]));
+                __stcg(A.cost + newi, ncost_of[k]);
+                __stcg(A.parent + newi, npar_of[k]);
+                if ((gm >> (16 + k)) & 1) {
+                    const int li = (newi / stride) * TREE_T + newi % TREE_T;
+                    S.dupbits[li >> 5] |= 1u << (li & 31);
+                }
+            }
+            n_acc++;
+        }
+        for (int e = tid; e < H; e += TREE_T) {
+            const int tag = S.hit_tag[e], slot = S.hit_slot[e], k = S.hit_k[e];
+            if (slot >= 0) tab[slot] = TREE_EMPTY;
+            if (k >= Be || (tag & HIT_SHADOW) || !(tag & HIT_FREE)) continue;
+            const int i = tag & HIT_MASK;
+            double nc = INF;
+            int ni = -1;
+#pragma unroll
+            for (int kk = 0; kk < TB_MAX; kk++) if (kk == k) { nc = ncost_of[kk]; ni = idx_of[kk]; }
+            const double sc = nc + S.hit_d[e];
+            if (S.hit_c[e] > sc) { __stcg(A.parent + i, ni); __stcg(A.cost + i, sc); }
+        }
+        // ---- goal bookkeeping (rrt_07:1094-1103): only the last surviving sample can have connected ----
+        if (goal_last && Be == B1) {
+            n_goal++;
+            const int k = B1 - 1;
+            int newi = -1, npar = -1;
+#pragma unroll
+            for (int kk = 0; kk < TB_MAX; kk++) if (kk == k) { newi = idx_of[kk]; npar = npar_of[kk]; }
+            const double nx = S.nx[k], ny = S.ny[k];
+            grid_barrier(ws, bphase, G);
+            if (tid == 0) {
+                double plen = 0.0, qx = gx, qy = gy;
+                int c = newi;
+                for (int guard = 0; guard <= A.p.node_cap; guard++) {
+                    const int pk = c == newi ? npar : ld_i32(A.parent + c);
+                    if (pk < 0) break;
+                    const double2 a = c == newi ? make_double2(nx, ny) : ld_xy(A.xy + c);
+                    plen += crm_hypot(a.x - qx, a.y - qy);
+                    qx = a.x; qy = a.y;
+                    c = pk;
+                }
+                plen += crm_hypot(sx0 - qx, sy0 - qy);
+                S.plen = plen;
+            }
+            __syncthreads();
+            const double plen = S.plen;
+            if (plen < c_best) {
+                c_best = plen;
+                n_redo++;
+                if (cta == 0 && tid == 0) {
+                    int w = 0;
+                    if (w < A.p.path_cap) A.path[w] = make_double2(gx, gy);
+                    w++;
+                    int c = newi;
+                    for (int guard = 0; guard <= A.p.node_cap; guard++, w++) {
+                        const int pk = c == newi ? npar : ld_i32(A.parent + c);
+                        if (pk < 0) break;
+                        if (w < A.p.path_cap) A.path[w] = c == newi ? make_double2(nx, ny) : ld_xy(A.xy + c);
+                        c = pk;
+                    }
+                    if (w < A.p.path_cap) A.path[w] = make_double2(sx0, sy0);
+                    w++;
+                    plen_best = w;
+                }
+            }
+        }
+        n += n_acc;
+        it += Be;
+        __syncthreads();
+    }
+
+    if (cta == 0 && tid == 0) {
+        A.res->n_nodes = n; A.res->path_len = plen_best;
+        A.res->status = status | (plen_best > A.p.path_cap ? RRTK_Q_PATH_OVERFLOW : 0);
+        A.res->iters_done = it; A.res->c_best = c_best; A.res->total_hits = total_hits; A.res->slow_paths = n_slow;
+        A.res->goal_events = n_goal; A.res->resamples = n_redo; A.res->grid = G; A.res->reextends = n_cut; A.res->pad_ = 0;
+        A.res->cycles[0] = n_batches;
+    }
+}
+
+
 // Diagnostic: the grid-wide exchange alone, `iters` times on a co-resident grid; out[cta] = cycles per exchange.
 __global__ void __launch_bounds__(TREE_T, 1) tree_exchange_probe_kernel(TreeWs ws, int iters, long long *out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -755,7 +1278,7 @@ static size_t carve(TreeWs &ws, char *base, int node_cap, int G) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
     ws.bar = (unsigned long long *)take(256);
-    ws.rec = (uint4 *)take(sizeof(uint4) * 2 * TREE_REC_PIECES * G);
+    ws.rec = (uint4 *)take(sizeof(uint4) * 2 * (TB_REC > TREE_REC_PIECES ? TB_REC : TREE_REC_PIECES) * G);
     ws.tab = (unsigned long long *)take(sizeof(unsigned long long) * 2 * (1ull << TREE_TAB_BITS));
     ws.sp_idx = (int *)take(sizeof(int) * (size_t)G * seg_cap);
     ws.sp_slot = (int *)take(sizeof(int) * (size_t)G * seg_cap);
@@ -768,7 +1291,9 @@ static size_t carve(TreeWs &ws, char *base, int node_cap, int G) {
     return off;
 }
 
-static size_t tree_smem_bytes(int seg_cap) { return sizeof(TreeSmem) + sizeof(unsigned) * (size_t)(seg_cap / 32 + 1); }
+static size_t tree_smem_bytes(int seg_cap, bool batch = false) {
+    return (batch ? sizeof(BatchSmem) : sizeof(TreeSmem)) + sizeof(unsigned) * (size_t)(seg_cap / 32 + 1);
+}
 
 static int tree_grid(int want, int *grid_out) {
     int dev = 0, sms = 0;
@@ -811,20 +1336,22 @@ int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obsta
     A.res = res;
     const size_t need = carve(A.ws, (char *)workspace, p.node_cap, G);
     if (need > workspace_bytes) return set_error(RRTK_ERR_INVALID, "workspace too small (rrtk_informed_tree_workspace_bytes)");
-    const size_t smem = tree_smem_bytes(A.ws.seg_cap);
+    const bool batched = p.batch > 1;
+    const void *kern = batched ? (const void *)informed_tree_batch_kernel : (const void *)informed_tree_kernel;
+    const size_t smem = tree_smem_bytes(A.ws.seg_cap, batched);
     int per_sm = 0;
-    cudaError_t e = cudaFuncSetAttribute(informed_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(smem): node_cap too large for the owner-local flags");
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, informed_tree_kernel, TREE_T, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TREE_T, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (per_sm < 1) return set_error(RRTK_ERR_CUDA, "informed_tree_kernel does not fit on an SM");
+    if (per_sm < 1) return set_error(RRTK_ERR_CUDA, "informed tree kernel does not fit on an SM");
     e = cudaMemsetAsync(res, 0, sizeof(*res), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.bar, 0, 256, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.rec, 0, sizeof(uint4) * 2 * TREE_REC_PIECES * G, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.rec, 0, sizeof(uint4) * 2 * TB_REC * G, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(A.ws.tab, 0xff, sizeof(unsigned long long) * 2 * (1ull << TREE_TAB_BITS), s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(workspace)");
     void *args[] = {(void *)&A};
-    e = cudaLaunchCooperativeKernel((const void *)informed_tree_kernel, dim3(G), dim3(TREE_T), args, smem, s);
+    e = cudaLaunchCooperativeKernel(kern, dim3(G), dim3(TREE_T), args, smem, s);
     if (e != cudaSuccess) return set_cuda_error(e, "informed_tree_kernel cooperative launch");
     return RRTK_OK;
 }

@@ -39,7 +39,7 @@ class InformedParams(C.Structure):
 class InformedTreeParams(C.Structure):
     """struct rrtk_informed_tree_params (include/rrtk.h)."""
     _fields_ = [("max_iter", C.c_int32), ("node_cap", C.c_int32), ("n_obs", C.c_int32), ("path_cap", C.c_int32),
-                ("grid", C.c_int32), ("pad_", C.c_int32), ("expand_dis", C.c_double),
+                ("grid", C.c_int32), ("batch", C.c_int32), ("expand_dis", C.c_double),
                 ("start_goal", C.c_double * 4), ("rot", C.c_double * 4), ("coord_bound", C.c_double)]
 
 

@@ -146,7 +146,7 @@ class TreeRun:
 
 
 def run_tree(start, goal, obstacle_list, expand_dis, max_iter, free_samples, ball_draws, node_cap=None,
-             path_cap=4096, grid=0, device=None) -> TreeRun:
+             path_cap=4096, grid=0, device=None, batch=8) -> TreeRun:
     """ONE informed search with the whole GPU on it (BASELINE config 3; rrtk_informed_tree_run_dev).
     free_samples / ball_draws: [max_iter, 2] (numpy or CUDA tensors).  Enqueues and returns; results stay on the GPU."""
     torch = _lib.require_cuda()
@@ -155,6 +155,7 @@ def run_tree(start, goal, obstacle_list, expand_dis, max_iter, free_samples, bal
     rows = np.array([[ox, oy, size, size ** 2] for ox, oy, size in obstacle_list], dtype=np.float64).reshape(-1, 4)
     p = _lib.InformedTreeParams()
     p.max_iter, p.node_cap, p.n_obs, p.path_cap, p.grid = int(max_iter), cap, rows.shape[0], int(path_cap), int(grid)
+    p.batch = int(batch)   # samples per pass (identical results for every value, see include/rrtk.h)
     p.expand_dis = float(expand_dis)
     sg = [float(start[0]), float(start[1]), float(goal[0]), float(goal[1])]
     rot = rotation_to_world_frame(start, goal)

@@ -20,16 +20,17 @@ def _same(a, ref):
     assert a["path"] == ref["path"]
 
 
+@pytest.mark.parametrize("batch", [1, 8])
 @pytest.mark.parametrize("grid", [0, 3])
 @pytest.mark.parametrize("name", NAMES)
-def test_tree_bitwise_vs_oracle_cr(name, grid, oracle_lib):
+def test_tree_bitwise_vs_oracle_cr(name, grid, batch, oracle_lib):
     from rrtk import informed
     O = oracle_lib
     g, m = load_golden(name)
     ref = O.informed_run(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"], m["rot"],
                          g["free"], g["ball"], O.MATH_CR)
     run = informed.run_tree(m["start"], m["goal"], m["obstacle_list"], m["expand_dis"], m["max_iter"],
-                            g["free"], g["ball"], grid=grid)
+                            g["free"], g["ball"], grid=grid, batch=batch)
     a = run.arrays()
     assert a["status"] == 0 and run.info["iters_done"] == m["max_iter"]
     _same(a, ref)
@@ -54,8 +55,9 @@ def _draws(rng, iters, goal, lo=-2.0, hi=15.0, rate=10):
     return free, rng.random((iters, 2))
 
 
+@pytest.mark.parametrize("batch", [1, 3, 8])
 @pytest.mark.parametrize("grid,iters,seed", [(0, 6000, 1), (5, 12000, 2), (2, 5000, 3)])
-def test_tree_random_scenes_vs_oracle(grid, iters, seed, oracle_lib):
+def test_tree_random_scenes_vs_oracle(grid, iters, seed, batch, oracle_lib):
     """More circles, multi-pass scans (small grids wrap the ownership chunks), thousands of near hits."""
     from rrtk import informed
     O = oracle_lib
@@ -66,7 +68,7 @@ def test_tree_random_scenes_vs_oracle(grid, iters, seed, oracle_lib):
     free, ball = _draws(rng, iters, goal)
     rot = informed.rotation_to_world_frame(start, goal)
     ref = O.informed_run(start, goal, obs, 0.5, iters, rot, free, ball, O.MATH_CR)
-    run = informed.run_tree(start, goal, obs, 0.5, iters, free, ball, grid=grid)
+    run = informed.run_tree(start, goal, obs, 0.5, iters, free, ball, grid=grid, batch=batch)
     a = run.arrays()
     assert a["status"] == 0
     _same(a, ref)
@@ -88,8 +90,8 @@ def test_tree_duplicate_positions_and_equal_d2(oracle_lib):
     free[200:260:2] = (0.1, 0.0)
     rot = informed.rotation_to_world_frame(start, goal)
     ref = O.informed_run(start, goal, obs, 0.5, iters, rot, free, ball, O.MATH_CR)
-    for grid in (0, 2):
-        run = informed.run_tree(start, goal, obs, 0.5, iters, free, ball, grid=grid)
+    for grid, batch in ((0, 1), (2, 1), (0, 8), (2, 4)):
+        run = informed.run_tree(start, goal, obs, 0.5, iters, free, ball, grid=grid, batch=batch)
         _same(run.arrays(), ref)
         assert run.info["slow_paths"] >= 1
     xy = np.column_stack([ref["x"], ref["y"]])
@@ -103,8 +105,9 @@ def test_tree_matches_batched_kernel():
     iters = 4000
     free, ball = _draws(rng, iters, [6.0, 10.0])
     b = informed.run_batch([[0.0, 0.0]], [[6.0, 10.0]], [BUILTIN_OBS], 0.5, iters, free[None], ball[None])[0]
-    a = informed.run_tree([0.0, 0.0], [6.0, 10.0], BUILTIN_OBS, 0.5, iters, free, ball).arrays()
-    _same(a, b)
+    for batch in (1, 8):
+        a = informed.run_tree([0.0, 0.0], [6.0, 10.0], BUILTIN_OBS, 0.5, iters, free, ball, batch=batch).arrays()
+        _same(a, b)
 
 
 def test_tree_large_grid_independence_and_invariants():
@@ -116,10 +119,13 @@ def test_tree_large_grid_independence_and_invariants():
     iters = 150_000
     start, goal = [0.0, 0.0], [6.0, 10.0]
     free, ball = _draws(rng, iters, goal)
-    runs = [informed.run_tree(start, goal, BUILTIN_OBS, 0.5, iters, free, ball, grid=g) for g in (0, 37)]
+    runs = [informed.run_tree(start, goal, BUILTIN_OBS, 0.5, iters, free, ball, grid=g, batch=bt)
+            for g, bt in ((0, 1), (37, 1), (0, 8), (37, 5))]
     torch.cuda.synchronize()
     a, b = runs[0].arrays(), runs[1].arrays()
     _same(a, b)
+    _same(runs[2].arrays(), a)
+    _same(runs[3].arrays(), a)
     i = runs[0].info
     assert i["status"] == 0 and i["iters_done"] == iters and i["n_nodes"] > 100_000
     n, par = a["n"], a["parent"]

@@ -17,7 +17,7 @@ for iters in sizes:
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    run = informed.run_tree([0.0, 0.0], [6.0, 10.0], OBS, 0.5, iters, d_free, d_ball)
+    run = informed.run_tree([0.0, 0.0], [6.0, 10.0], OBS, 0.5, iters, d_free, d_ball, batch=int(os.environ.get("RRTK_TREE_BATCH", "8")))
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
