@@ -71,4 +71,36 @@ ob = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10
 for _ in range(REPS):
     INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, ob, 0.5, iters, free, ball)
 torch.cuda.synchronize()
+
+# round-1 additions: single-tree informed kernel (batched and unbatched), Reeds-Shepp steering and planner, smoothing, astar
+from rrtk import reeds_shepp as RS, rs_planner as RP, smoothing, workloads as W  # noqa: E402
+import rrtk  # noqa: E402
+it = 30000
+fr = rng.uniform(-2, 15, (it, 2)); fr[rng.integers(0, 101, it) <= 10] = (6.0, 10.0); bl = rng.random((it, 2))
+OB = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+for b in (8, 1):
+    INF.run_tree([0.0, 0.0], [6.0, 10.0], OB, 0.5, it, fr, bl, batch=b)
+torch.cuda.synchronize()
+RS.steer_batch(f, t, 1.0, 0.1, obstacle_sets=obs)
+Q, iters = 256, 200
+st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+RP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 9.0, 0.0]] * Q, [OB] * Q, 3.0, iters, st, robot_radius=0.6, curvature=2.0, step_size=0.1)
+cfg = W.C2
+Q = 1024
+rows = W.c2_rows(list(range(Q)), 256)
+bt = rrtk.RRTStarBatch(np.tile(cfg["start"], (Q, 1)), np.tile(cfg["goal"], (Q, 1)), rows, cfg["rand_area"], cfg["expand_dis"],
+                       cfg["path_resolution"], cfg["goal_sample_rate"], 1000, None, 0.0, "sobol", cfg["connect_circle_dist"], True, seed=1)
+res = bt.run()
+sp, sl = res.paths_device(64 + 500)
+smoothing.smooth_batch(sp, sl, 500, bt.obstacles[:, :, :3].contiguous(), bt.n_obs)
+ang, rad = rng.uniform(0, 2 * np.pi, (32, 5)), rng.uniform(0.9, 2.0, (32, 5))
+sets2 = np.stack([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(0.15, 0.45, (32, 5))], axis=2)
+grids = A.occupancy_grids_device([1.0, 1.0], sets2, 256)
+host = grids.cpu().numpy()
+stt, gl = [], []
+for k in range(32):
+    fc = np.argwhere(host[k] == 0)
+    stt.append(fc[rng.integers(len(fc))]); gl.append(fc[rng.integers(len(fc))])
+A.astar_torus_batch(grids, np.array(stt), np.array(gl))
+torch.cuda.synchronize()
 print("ok")
