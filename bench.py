@@ -306,23 +306,34 @@ def main():
     h_path = torch.empty((len(qids), path_cap, 2), dtype=torch.float64).pin_memory()
     h_plen = torch.empty((len(qids),), dtype=torch.int32).pin_memory()
 
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def e2e_step():
+        """One user-level call; returns (device ms from the first H2D byte to the last D2H byte, wall ms)."""
+        w0 = time.perf_counter()
+        ea.record()
         batch.upload()                                   # pinned host -> device (start/goal, obstacles, counts)
         r = batch.run()
         path, plen = r.paths_device(path_cap)            # generate_final_course on the device
         h_path.copy_(path, non_blocking=True)            # device -> pinned host: what planning() returns
         h_plen.copy_(plen, non_blocking=True)
-        torch.cuda.synchronize()
-    for _ in range(max(1, args.warmup)):                 # untimed: allocator / pinned-buffer warm-up, and the
-        e2e_step()                                       # clocks ramp back up after the idle host-side setup
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+        eb.record()
+        eb.synchronize()                                 # the caller holds the paths in host memory here
+        return ea.elapsed_time(eb), (time.perf_counter() - w0) * 1e3
+    for _ in range(max(3, args.warmup)):                 # untimed: allocator / pinned-buffer warm-up
         e2e_step()
     barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_ms = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    # timed on the device (CUDA events on the launching stream, copies inside), max over ranks; the wall clock of the
+    # same calls is reported next to it -- on a freshly started box the host thread can be descheduled for
+    # 0.1 - 2 s inside cudaStreamSynchronize while the device timeline stays at kernel + copies (tools/probe_e2e.py)
+    t_e2e = max_over_ranks(sum(m[0] for m in e2e_ms) / 1e3)
+    t_e2e_wall = max_over_ranks(sum(m[1] for m in e2e_ms) / 1e3)
     e2e = dict(value=total_iters / t_e2e, unit=UNIT, h2d_bytes_per_step=batch.h2d_bytes() * world,
                d2h_bytes_per_step=(h_path.numel() * 8 + h_plen.numel() * 4) * world,
+               ms_per_step=1e3 * t_e2e / args.steps, timing="CUDA events around upload + kernel + path extraction + D2H",
+               wall_value=total_iters / t_e2e_wall, wall_ms_per_step=1e3 * t_e2e_wall / args.steps,
                result="paths [Q, 256, 2] + lengths, pinned host buffers")
     found = int((h_plen.numpy() > 0).sum())
 
@@ -515,11 +526,14 @@ def extras(torch, dev):
         coin = rng.integers(0, 101, (Q, iters)) <= 10
         st[coin] = (10.0, 10.0, 0.0)
         obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)]] * Q
-        t0 = time.perf_counter()
-        res = DP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 10.0, 0.0]] * Q, obs, 3.0, iters, st)
-        torch.cuda.synchronize()
-        t = time.perf_counter() - t0
-        out["c4_rrtstar_dubins"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+        tm = {}
+        for rep in range(2):                                  # the second, warm call is the one reported
+            t0 = time.perf_counter()
+            res = DP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 10.0, 0.0]] * Q, obs, 3.0, iters, st, timing=tm)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+        out["c4_rrtstar_dubins"] = dict(tree_iters_per_s=Q * iters / (tm["kernel_ms"] / 1e3), kernel_ms=tm["kernel_ms"],
+                                        tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
                                         mean_nodes=float(np.mean([r["n"] for r in res])),
                                         solved=int(sum(r["goal_index"] >= 0 for r in res)))
     except Exception as e:  # noqa: BLE001
@@ -548,7 +562,7 @@ def extras(torch, dev):
             tree_iters_per_s=i["iters_done"] / t, c_best=i["c_best"], mean_near=i["total_hits"] / max(1, i["iters_done"]),
             reached_node_cap=bool(i["status"] & 2), scan_gbs_algorithmic=alg_bytes / t / 1e9,
             goal_events=i["goal_events"], resamples=i["resamples"], grid=i["grid"],
-            cycles_per_iter=[round(c / max(1, i["iters_done"])) for c in i["cycles"]],
+            cycles_per_iter=([round(c / max(1, i["iters_done"])) for c in i["cycles"]] if any(i["cycles"]) else None),
             note="one fused FP64 pass (16 B/node) per iteration over an L2-resident tree; latency-bound by the "
                  "grid-wide exchange and the serial leaf math, see DESIGN.md 5.5")
         del run, d_free, d_ball
@@ -560,13 +574,15 @@ def extras(torch, dev):
         rng = np.random.default_rng(17)
         st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
         obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]] * Q
+        tm = {}
         for rep in range(2):
             t0 = time.perf_counter()
             res = RP.run_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 9.0, 0.0]] * Q, obs, 3.0, iters, st, robot_radius=0.6,
-                               curvature=2.0, step_size=0.1)
+                               curvature=2.0, step_size=0.1, timing=tm)
             torch.cuda.synchronize()
             t = time.perf_counter() - t0
-        out["rrtstar_reeds_shepp"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+        out["rrtstar_reeds_shepp"] = dict(tree_iters_per_s=Q * iters / (tm["kernel_ms"] / 1e3), kernel_ms=tm["kernel_ms"],
+                                          tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
                                           mean_nodes=float(np.mean([r["n"] for r in res])),
                                           solved=int(sum(r["goal_index"] >= 0 for r in res)))
     except Exception as e:  # noqa: BLE001
@@ -578,10 +594,11 @@ def extras(torch, dev):
         free[coin] = (6.0, 10.0)
         ball = rng.random((Q, iters, 2))
         obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]] * Q
-        t0 = time.perf_counter()
-        res = INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, obs, 0.5, iters, free, ball)
-        torch.cuda.synchronize()
-        t = time.perf_counter() - t0
+        for rep in range(2):
+            t0 = time.perf_counter()
+            res = INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, obs, 0.5, iters, free, ball)
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
         out["informed_rrtstar"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
                                        mean_nodes=float(np.mean([r["n"] for r in res])),
                                        solved=int(sum(r["path"] is not None for r in res)))

@@ -43,9 +43,10 @@ class Node:
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0,
               connect_circle_dist=50.0, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5,
-              search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1):
+              search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1, timing=None):
     """Q RRT*-Dubins (steer="dubins") or RRT*-Reeds-Shepp (steer="rs", rrt_06) queries in one launch.
-    starts/goals [Q, 3]; streams [Q, max_iter, 3].  Returns a list of dicts (numpy arrays trimmed to n_nodes)."""
+    starts/goals [Q, 3]; streams [Q, max_iter, 3].  Returns a list of dicts (numpy arrays trimmed to n_nodes).
+    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch)."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
@@ -69,12 +70,19 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
         ef, et = f64(q, cap, 3), f64(q, cap, 3)
         n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, 4 * cap)
         entry = _lib.lib().rrtk_rrtstar_dubins_run_dev if steer == "dubins" else _lib.lib().rrtk_rrtstar_rs_run_dev
+        if timing is not None:
+            ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev[0].record()
         rc = entry(
             C.byref(p), d_sg.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_r2.data_ptr(), d_st.data_ptr(),
             xy.data_ptr(), yaw.data_ptr(), cost.data_ptr(), parent.data_ptr(), ef.data_ptr(), et.data_ptr(),
             n_nodes.data_ptr(), iters.data_ptr(), gi.data_ptr(), status.data_ptr(), ws.data_ptr(),
             torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "rrtk_rrtstar_dubins_run_dev" if steer == "dubins" else "rrtk_rrtstar_rs_run_dev")
+        if timing is not None:
+            ev[1].record()
+            ev[1].synchronize()
+            timing["kernel_ms"] = ev[0].elapsed_time(ev[1])
         h = {k: v.cpu().numpy() for k, v in dict(xy=xy, yaw=yaw, cost=cost, parent=parent, ef=ef, et=et, n=n_nodes,
                                                  it=iters, gi=gi, st=status).items()}
     out = []

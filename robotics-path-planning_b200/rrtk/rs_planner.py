@@ -43,11 +43,11 @@ class Node:
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0, connect_circle_dist=50.0,
               curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5, search_until_max_iter=True, step_size=0.2,
-              near_cap=256, device=None):
+              near_cap=256, device=None, timing=None):
     """Q RRT*-Reeds-Shepp queries in one launch (rrtk_rrtstar_rs_run_dev).  starts / goals [Q, 3]; streams [Q, max_iter, 3]."""
     return _run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius, connect_circle_dist,
                       curvature, goal_yaw_th, goal_xy_th, search_until_max_iter, near_cap, device, steer="rs",
-                      step_size=step_size)
+                      step_size=step_size, timing=timing)
 
 
 def final_course(tree, start, goal, curvature, step_size):
