@@ -388,7 +388,7 @@ RRTK_API int rrtk_astar_torus_dev(int32_t M, int32_t n_queries, const int32_t *s
  * Leaf-function probes (tests): the correctly-rounded device functions of csrc/crmath.h.
  *   kind 0: out[i] = hypot(a[i], b[i])   kind 1: atan2(a[i], b[i])   kind 2: sin(a[i])
  *   kind 3: cos(a[i])                     kind 4/5: sin/cos(atan2(a[i], b[i])) (fused steer form)
- *   kind 6: acos(a[i])                    kind 7: asin(a[i])
+ *   kind 6: acos(a[i])                    kind 7: asin(a[i])                kind 8: tan(a[i])
  * ------------------------------------------------------------------------------------------- */
 RRTK_API int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out,
                           void *stream);

@@ -277,6 +277,52 @@ def run_rrt06(name, params, seed, search_until_max_iter=True):
           f"{wall:.2f} s ({n / wall:.1f} it/s)")
 
 
+def run_rrt10(name, params, seed):
+    """rrt_10's ClosedLoopRRTStar.planning (:1478-1492) with an injected sample stream: the RRT*-Reeds-Shepp tree with
+    Reeds-Shepp-length costs, the goal indexes, and the closed-loop prediction of EVERY candidate course."""
+    ns = ref_loader.load("rrt_10")
+    rng = np.random.default_rng(seed)
+    n = params["max_iter"]
+    lo, hi = params["rand_area"]
+    stream = np.column_stack([rng.uniform(lo, hi, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+    c = ns["ClosedLoopRRTStar"](**params)
+    it = iter(stream)
+    c.get_random_node = lambda: c.Node(*[float(v) for v in next(it)])
+    sys.setrecursionlimit(100000)
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        ns["RRTStarReedsShepp"].planning(c, animation=False)
+        wall_plan = time.perf_counter() - t0
+        gi = c.get_goal_indexes()
+        courses = [c.generate_final_course(i) for i in gi]
+        t1 = time.perf_counter()
+        res = [c.check_tracking_path_is_feasible(p) for p in courses]
+        wall_filter = time.perf_counter() - t1
+        best = c.search_best_feasible_path(gi)
+    x, y, cst, par = tree_arrays(c.node_list)
+    yaw = np.array([float(nd.yaw) for nd in c.node_list])
+    traj = [np.array([r[1], r[2], r[3], r[4], r[5], r[6], r[7]], dtype=np.float64).T for r in res]   # x y yaw v t a d
+    off = np.cumsum([0] + [len(t) for t in traj])
+    coff = np.cumsum([0] + [len(p) for p in courses])
+    meta = dict(params)
+    meta.update(kind="rrt_10", seed=seed, reference_wall_plan_s=wall_plan, reference_wall_filter_s=wall_filter,
+                flag=bool(best[0]))
+    win = np.zeros((0, 4)) if not best[0] else np.array([best[1], best[2], best[3]], dtype=np.float64).T
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), stream=stream,
+                        x=x, y=y, yaw=yaw, cost=cst, parent=par, goal_idx=np.array(gi, dtype=np.int32),
+                        course=np.concatenate([np.array(p, dtype=np.float64) for p in courses]) if courses else np.zeros((0, 3)),
+                        course_off=coff, found=np.array([bool(r[0]) for r in res]), traj=np.concatenate(traj) if traj else
+                        np.zeros((0, 7)), traj_off=off, winner_xyyaw=win)
+    print(f"{name}: {len(x)} nodes, {len(gi)} goal candidates, {int(sum(bool(r[0]) for r in res))} feasible, flag {best[0]}, "
+          f"plan {wall_plan:.1f} s, filter {wall_filter:.1f} s")
+
+
+C10 = dict(start=[0.0, 0.0, 0.0], goal=[6.0, 9.0, float(np.deg2rad(90.0))],
+           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
+           rand_area=[-2, 20], max_iter=150, connect_circle_dist=50.0, robot_radius=0.0, target_speed=10.0 / 3.6,
+           yaw_th=float(np.deg2rad(3.0)), xy_th=0.5, invalid_travel_ratio=5.0)        # rrt_10:1610-1660
+
+
 C6 = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 9.0, 0.0],
           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)],
           rand_area=[-2, 15], expand_dis=3.0, max_iter=300, robot_radius=0.6, connect_circle_dist=50.0,
@@ -411,6 +457,10 @@ def run_reeds_shepp(name, n, seed):
 
 
 CASES = {
+    "rrt10_cl_60": lambda: run_rrt10("rrt10_cl_60", dict(C10, max_iter=60), 5),
+    "rrt10_cl_builtin_150": lambda: run_rrt10("rrt10_cl_builtin_150", C10, 11),
+    "rrt10_cl_radius_100": lambda: run_rrt10("rrt10_cl_radius_100", dict(C10, max_iter=100, robot_radius=0.3,
+                                                                         goal=[8.0, 7.5, 0.0]), 23),
     "rrt06_builtin_300": lambda: run_rrt06("rrt06_builtin_300", C6, 1),
     "rrt06_builtin_700": lambda: run_rrt06("rrt06_builtin_700", dict(C6, max_iter=700), 2),
     "rrt06_loose_400": lambda: run_rrt06("rrt06_loose_400", dict(

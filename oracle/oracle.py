@@ -45,7 +45,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB_PATH)
         for name, nargs in (("orc_hypot", 2), ("orc_cr_hypot", 2), ("orc_cr_sin", 1),
-                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2), ("orc_cr_acos", 1), ("orc_cr_asin", 1)):
+                            ("orc_cr_cos", 1), ("orc_cr_atan2", 2), ("orc_cr_acos", 1), ("orc_cr_asin", 1), ("orc_cr_tan", 1)):
             f = getattr(_lib, name)
             f.restype = C.c_double
             f.argtypes = [C.c_double] * nargs
@@ -350,13 +350,15 @@ def reeds_shepp(s, g, maxc, step_size=0.2, math_mode=MATH_LIBM, max_pts=4096):
 class RSParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("sx", "sy", "syaw", "gx", "gy", "gyaw", "expand_dis", "robot_radius",
                                           "connect_circle_dist", "kappa", "goal_yaw_th", "goal_xy_th", "step_size")] + \
-               [(k, C.c_int32) for k in ("max_iter", "n_obs", "search_until_max_iter", "math_mode")]
+               [(k, C.c_int32) for k in ("max_iter", "n_obs", "search_until_max_iter", "math_mode", "cost_mode", "pad_")]
 
 
 def rrtstar_rs_run(start, goal, obstacle_list, expand_dis, max_iter, robot_radius, connect_circle_dist, curvature,
-                   goal_yaw_th, goal_xy_th, search_until_max_iter, stream3, step_size=0.2, math_mode=MATH_LIBM):
-    """rrt_06 planning() with an injected (x, y, yaw) stream -> tree arrays, goal_index and the final course [n, 3]."""
+                   goal_yaw_th, goal_xy_th, search_until_max_iter, stream3, step_size=0.2, math_mode=MATH_LIBM, rs_cost=False):
+    """rrt_06 planning() with an injected (x, y, yaw) stream -> tree arrays, goal_index and the final course [n, 3].
+    rs_cost=True: rrt_10's RRTStarReedsShepp (Reeds-Shepp length costs; pass expand_dis=inf for its unclipped radius)."""
     p = RSParams()
+    p.cost_mode = int(bool(rs_cost))
     p.sx, p.sy, p.syaw = [float(v) for v in start]
     p.gx, p.gy, p.gyaw = [float(v) for v in goal]
     p.expand_dis, p.robot_radius, p.connect_circle_dist = float(expand_dis), float(robot_radius), float(connect_circle_dist)
@@ -393,3 +395,37 @@ def rs_final_course(res, start, goal, curvature, step_size, math_mode):
         i = int(res["parent"][i])
     path.append([float(start[0]), float(start[1]), float(start[2])])
     return path
+
+
+class CLParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("target_speed", "yaw_th", "invalid_travel_ratio", "robot_radius")] + \
+               [(k, C.c_int32) for k in ("n_obs", "math_mode", "traj_cap", "pad_")]
+
+
+def closed_loop(course, obstacle_list, robot_radius=0.0, target_speed=10.0 / 3.6, yaw_th=np.deg2rad(3.0),
+                invalid_travel_ratio=5.0, math_mode=MATH_LIBM, traj_cap=2048):
+    """check_tracking_path_is_feasible (rrt_10:1521-1559) for one final course given in DRIVING order (start -> goal,
+    rows x, y, yaw).  Returns dict(bits, traj [n, 7] = x, y, yaw, v, t, a, d)."""
+    c = np.ascontiguousarray(course, dtype=np.float64).reshape(-1, 3)
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    p = CLParams()
+    p.target_speed, p.yaw_th, p.invalid_travel_ratio, p.robot_radius = float(target_speed), float(yaw_th), \
+        float(invalid_travel_ratio), float(robot_radius)
+    p.n_obs, p.math_mode, p.traj_cap = obs.shape[0], int(math_mode), int(traj_cap)
+    traj = np.zeros((traj_cap, 7))
+    n = C.c_int32(); bits = C.c_int32()
+    rc = lib().orc_closed_loop(C.byref(p), c.shape[0], _p(c, C.c_double), _p(obs, C.c_double), _p(traj, C.c_double),
+                               C.byref(n), C.byref(bits))
+    if rc:
+        raise RuntimeError("traj_cap too small")
+    return dict(bits=bits.value, traj=traj[:n.value].copy())
+
+
+def closed_loop_best(courses, *a, **k):
+    """search_best_feasible_path (rrt_10:1494-1519): position of the winning course (-1 = none) and every result."""
+    res = [closed_loop(c, *a, **k) for c in courses]
+    best, best_time = -1, float("inf")
+    for i, r in enumerate(res):
+        if r["bits"] == 0 and best_time >= r["traj"][-1, 4]:
+            best_time, best = r["traj"][-1, 4], i
+    return best, res

@@ -30,6 +30,7 @@ FILES = {
     "dub00": ("10_path_planning_00_dubins_path.py", 423),
     "rrt_06": ("10_path_planning_01_rrt_06_rrt_star_reeds_shepp_path.py", 2005),
     "rs00": ("10_path_planning_00_reeds_shepp_path.py", 515),
+    "rrt_10": ("10_path_planning_01_rrt_10_closed_loop_rrt_star.py", 1608),   # classes + the constants :1592-1607
 }
 
 
@@ -68,6 +69,8 @@ def load(alias: str) -> dict:
     ns: dict = {"__name__": "ref_" + alias, "__file__": path}
     with contextlib.redirect_stdout(io.StringIO()):
         exec(compile(src, path, "exec"), ns)
+    if alias == "rrt_10":
+        ns["animation"] = False        # module global read by closed_loop_prediction (:1350), set at :1637 in the script
     return ns
 
 

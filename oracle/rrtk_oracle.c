@@ -92,6 +92,7 @@ ORC_EXPORT double orc_cr_atan2(double y, double x) { return crm_atan2(y, x); }
 ORC_EXPORT double orc_cr_hypot(double a, double b) { return crm_hypot(a, b); }
 ORC_EXPORT double orc_cr_acos(double x) { return crm_acos(x); }
 ORC_EXPORT double orc_cr_asin(double x) { return crm_asin(x); }
+ORC_EXPORT double orc_cr_tan(double x) { return crm_tan(x); }
 ORC_EXPORT double orc_cr_atan2_sincos(double y, double x, double *s, double *c) {
     return crm_atan2_sincos(y, x, s, c);
 }
@@ -1369,6 +1370,7 @@ typedef struct {
     double sx, sy, syaw, gx, gy, gyaw;
     double expand_dis, robot_radius, connect_circle_dist, kappa, goal_yaw_th, goal_xy_th, step_size;
     int32_t max_iter, n_obs, search_until_max_iter, math_mode;
+    int32_t cost_mode, pad_; /* 0: rrt_06 (Euclidean costs), 1: rrt_10:1005-1207 (Reeds-Shepp length costs, calc_new_cost :1153-1161) */
 } orc_rs_params_t;
 #define RS_MAXPTS 8192
 typedef struct { int npts, free_; double end[3], lsum; } rs_edge_t;
@@ -1397,6 +1399,18 @@ static rs_edge_t rs_edge(const orc_rs_params_t *p, const double *obs3, const dou
     }
     e.free_ = ok;
     return e;
+}
+/* propagate_cost_to_leaves with rrt_10's calc_new_cost (:572-577, :1153-1161): parent cost + Reeds-Shepp length, inf when
+ * there is no course */
+static void rs_propagate(const orc_rs_params_t *p, const double *obs3, int n, const double *x, const double *y, const double *yaw,
+                         double *cost, const int32_t *parent, int q, double *buf) {
+    for (int c = 0; c < n; c++)
+        if (parent[c] == q) {
+            double f[3] = {x[q], y[q], yaw[q]}, t[3] = {x[c], y[c], yaw[c]};
+            rs_edge_t e = rs_edge(p, obs3, f, t, buf);
+            cost[c] = e.npts > 0 ? cost[q] + e.lsum : INFINITY;
+            rs_propagate(p, obs3, n, x, y, yaw, cost, parent, c, buf);
+        }
 }
 static int rs_best_goal(const orc_rs_params_t *p, int n, const double *x, const double *y, const double *yaw, const double *cost) {
     int gi = -1;
@@ -1450,7 +1464,7 @@ ORC_EXPORT int orc_rrtstar_rs_run(const orc_rs_params_t *p, const double *obs3, 
                 int i = near[k];
                 double fi[3] = {x[i], y[i], yaw[i]};
                 rs_edge_t e = rs_edge(p, obs3, fi, nw, buf);
-                double c = (e.npts > 0 && e.free_) ? cost[i] + orc_hypot(nw[0] - x[i], nw[1] - y[i]) : INFINITY;
+                double c = (e.npts > 0 && e.free_) ? cost[i] + (p->cost_mode ? e.lsum : orc_hypot(nw[0] - x[i], nw[1] - y[i])) : INFINITY;
                 if (c < mc) { mc = c; best = i; }
             }
             if (best >= 0) {
@@ -1468,12 +1482,13 @@ ORC_EXPORT int orc_rrtstar_rs_run(const orc_rs_params_t *p, const double *obs3, 
                     double ti[3] = {x[i], y[i], yaw[i]};
                     rs_edge_t ed = rs_edge(p, obs3, cp, ti, buf);
                     if (ed.npts == 0) continue;
-                    double ecost = mc + orc_hypot(x[i] - cp[0], y[i] - cp[1]);
+                    double ecost = mc + (p->cost_mode ? ed.lsum : orc_hypot(x[i] - cp[0], y[i] - cp[1]));
                     if (ed.free_ && cost[i] > ecost) {
                         x[i] = ed.end[0]; y[i] = ed.end[1]; yaw[i] = ed.end[2]; cost[i] = ecost; parent[i] = newi;
                         memcpy(edge_from + 3 * i, cp, sizeof cp);
                         memcpy(edge_to + 3 * i, ti, sizeof ti);
-                        dub_propagate(n, x, y, cost, parent, i);
+                        if (p->cost_mode) rs_propagate(p, obs3, n, x, y, yaw, cost, parent, i, buf);
+                        else dub_propagate(n, x, y, cost, parent, i);
                     }
                 }
                 /* try_goal_path (:1572-1582): from the node as it is now */
@@ -1497,4 +1512,138 @@ ORC_EXPORT int orc_rrtstar_rs_run(const orc_rs_params_t *p, const double *obs3, 
     *n_nodes = n; *iters_done = it; *goal_index = gi;
     free(buf); free(dl); free(near);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Closed-loop RRT* (rrt_10:1215-1582): unicycle model + pure pursuit over one course and  */
+/* the feasibility checks of check_tracking_path_is_feasible.  Constants: rrt_10:1592-1607 */
+/* ------------------------------------------------------------------------------------ */
+static inline double m_tan(int m, double x) { return m == ORC_MATH_LIBM ? tan(x) : crm_tan(x); }
+static inline double m_nphyp(int m, double a, double b) { return m == ORC_MATH_LIBM ? hypot(a, b) : crm_hypot(a, b); } /* np.hypot */
+#define CL_DT 0.05
+#define CL_WB 0.9          /* L */
+#define CL_ACCEL_MAX 5.0
+#define CL_KP 2.0
+#define CL_LF 0.5
+#define CL_T 100.0
+#define CL_GOAL_DIS 0.5
+#define CL_STOP_SPEED 0.5
+#define CL_EXTEND 6        /* int(Lf / 0.1) + 1 */
+typedef struct {
+    double target_speed, yaw_th, invalid_travel_ratio, robot_radius;
+    int32_t n_obs, math_mode, traj_cap, pad_;
+} orc_cl_params_t;
+
+/* calc_target_index (:1285-1304) */
+static int cl_target_index(int m, double sx, double sy, const double *cx, const double *cy, int n, double *mindis) {
+    int ind = 0;
+    double best = INFINITY;
+    for (int i = 0; i < n; i++) {
+        double d = m_nphyp(m, sx - cx[i], sy - cy[i]);
+        if (d < best) { best = d; ind = i; }
+    }
+    *mindis = best;
+    double le = 0.0;
+    while (CL_LF > le && ind + 1 < n) {
+        le += m_hyp(m, cx[ind + 1] - cx[ind], cy[ind + 1] - cy[ind]);
+        ind++;
+    }
+    return ind;
+}
+
+/* course3: the final course in driving order (start -> goal), rows x, y, yaw, n_course >= 3.
+ * traj7 [traj_cap][7] = x, y, yaw, v, t, a, d of closed_loop_prediction (yaw after the extra angle_mod of :1533);
+ * bits: 1 goal not reached, 2 final angle, 4 too long, 8 collision (0 = feasible).  Returns 0, or -1 when traj_cap is too small. */
+ORC_EXPORT int orc_closed_loop(const orc_cl_params_t *p, int32_t n_course, const double *course3, const double *obs3,
+                               double *traj7, int32_t *n_traj, int32_t *bits_out) {
+    const int m = p->math_mode;
+    const double steer_max = 40.0 * (ORC_PI / 180.0); /* np.deg2rad(40.0) = 40 * (pi / 180) */
+    int n = n_course + CL_EXTEND;
+    double *cx = (double *)malloc(sizeof(double) * 4 * (size_t)n), *cy = cx + n, *cyaw = cy + n, *sp = cyaw + n;
+    for (int i = 0; i < n_course; i++) { cx[i] = course3[3 * i]; cy[i] = course3[3 * i + 1]; cyaw[i] = course3[3 * i + 2]; }
+    const double goal[3] = {cx[n_course - 1], cy[n_course - 1], cyaw[n_course - 1]};
+    { /* extend_path (:1432-1447) */
+        const int l = n_course - 1;
+        const double md = m_atan2(m, cy[l] - cy[l - 2], cx[l] - cx[l - 2]);
+        const int back = fabs(md - cyaw[l]) >= ORC_PI / 2.0;
+        const double idl = back ? -0.1 : 0.1;
+        for (int k = n_course; k < n; k++) {
+            cx[k] = cx[k - 1] + idl * m_cos(m, cyaw[k - 1]);
+            cy[k] = cy[k - 1] + idl * m_sin(m, cyaw[k - 1]);
+            cyaw[k] = cyaw[k - 1];
+        }
+    }
+    { /* set_stop_point (:1375-1419) */
+        int forward = 1, back = 0;
+        for (int i = 0; i < n; i++) sp[i] = p->target_speed;
+        for (int i = 0; i < n - 1; i++) {
+            const double dx = cx[i + 1] - cx[i], dy = cy[i + 1] - cy[i];
+            back = fabs(m_atan2(m, dy, dx) - cyaw[i]) >= ORC_PI / 2.0;
+            if (dx == 0.0 && dy == 0.0) continue;
+            sp[i] = back ? -p->target_speed : p->target_speed;
+            if (back && forward) { sp[i] = 0.0; forward = 0; }
+            else if (!back && !forward) { sp[i] = 0.0; forward = 1; }
+        }
+        sp[0] = 0.0;
+        sp[n - 1] = back ? -CL_STOP_SPEED : CL_STOP_SPEED;
+    }
+    /* closed_loop_prediction (:1307-1372) */
+    double sx = -0.0, sy = -0.0, syaw = 0.0, sv = 0.0, time = 0.0, dis = 0.0, travel = 0.0;
+    int cnt = 0, find_goal = 0, rc = 0;
+    const double maxdis = 0.5, dcap = maxdis - 0.1;
+    double *r = traj7;
+    r[0] = sx; r[1] = sy; r[2] = syaw; r[3] = sv; r[4] = 0.0; r[5] = 0.0; r[6] = 0.0;
+    cnt = 1;
+    int target_ind = cl_target_index(m, sx, sy, cx, cy, n, &dis);
+    while (CL_T >= time) {
+        int ind = cl_target_index(m, sx, sy, cx, cy, n, &dis); /* pure_pursuit_control (:1255-1283) */
+        if (target_ind >= ind) ind = target_ind;
+        double tx, ty;
+        if (ind < n) { tx = cx[ind]; ty = cy[ind]; }
+        else { tx = cx[n - 1]; ty = cy[n - 1]; ind = n - 1; }
+        double alpha = m_atan2(m, ty - sy, tx - sx) - syaw;
+        if (sv <= 0.0) alpha = ORC_PI - alpha;
+        double di = m_atan2(m, 2.0 * CL_WB * m_sin(m, alpha) / CL_LF, 1.0);
+        if (di > steer_max) di = steer_max;
+        else if (di < -steer_max) di = -steer_max;
+        target_ind = ind;
+        double ts = sp[target_ind];
+        ts = ts * (maxdis - (dcap < dis ? dcap : dis)) / maxdis;
+        double ai = CL_KP * (ts - sv); /* PIDControl (:1243-1252) */
+        if (ai > CL_ACCEL_MAX) ai = CL_ACCEL_MAX;
+        else if (ai < -CL_ACCEL_MAX) ai = -CL_ACCEL_MAX;
+        const double nx = sx + sv * m_cos(m, syaw) * CL_DT; /* update (:1224-1232) */
+        const double ny = sy + sv * m_sin(m, syaw) * CL_DT;
+        const double nyaw = angle_mod_pi(syaw + sv / CL_WB * m_tan(m, di) * CL_DT);
+        sv = sv + ai * CL_DT;
+        sx = nx; sy = ny; syaw = nyaw;
+        if (fabs(sv) <= CL_STOP_SPEED && target_ind <= n - 2) target_ind++;
+        time = time + CL_DT;
+        if (m_hyp(m, sx - goal[0], sy - goal[1]) <= CL_GOAL_DIS) { find_goal = 1; break; }
+        if (cnt >= p->traj_cap) { rc = -1; break; }
+        r = traj7 + 7 * (size_t)cnt;
+        r[0] = sx; r[1] = sy; r[2] = syaw; r[3] = sv; r[4] = time; r[5] = ai; r[6] = di;
+        cnt++;
+    }
+    /* check_tracking_path_is_feasible (:1521-1559) */
+    int bits = find_goal ? 0 : 1;
+    for (int k = 0; k < cnt; k++) traj7[7 * (size_t)k + 2] = angle_mod_pi(traj7[7 * (size_t)k + 2]);
+    if (fabs(traj7[7 * (size_t)(cnt - 1) + 2] - goal[2]) >= p->yaw_th * 10.0) bits |= 2;
+    for (int k = 0; k < cnt; k++) travel = travel + fabs(traj7[7 * (size_t)k + 3]);
+    travel = CL_DT * travel;
+    double origin = 0.0;
+    for (int i = 0; i < n - 1; i++) origin = origin + m_nphyp(m, cx[i + 1] - cx[i], cy[i + 1] - cy[i]);
+    if (travel / origin >= p->invalid_travel_ratio) bits |= 4;
+    for (int o = 0; o < p->n_obs; o++) { /* check_collision (rrt_10:279-293) */
+        const double ox = obs3[3 * o], oy = obs3[3 * o + 1], lim = sq_libm(obs3[3 * o + 2] + p->robot_radius);
+        double mn = INFINITY;
+        for (int k = 0; k < cnt; k++) {
+            const double dx = ox - traj7[7 * (size_t)k], dy = oy - traj7[7 * (size_t)k + 1], dd = dx * dx + dy * dy;
+            if (dd < mn) mn = dd;
+        }
+        if (mn <= lim) { bits |= 8; break; }
+    }
+    *n_traj = cnt; *bits_out = bits;
+    free(cx);
+    return rc;
 }

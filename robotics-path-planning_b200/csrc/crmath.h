@@ -229,6 +229,14 @@ CRM_FN double crm_cos(double x) {
     return c.hi;
 }
 
+/* RN(tan(x)): the double-double quotient of crm_sincos_dd (relative error ~2^-100 before the final rounding) */
+CRM_FN double crm_tan(double x) {
+    if (x == 0.0) return x;
+    crm_dd s, c;
+    crm_sincos_dd(x, &s, &c);
+    return crm_div(s, c).hi;
+}
+
 /* crude atan2 (|error| < 1e-10), plain double, same op sequence everywhere */
 CRM_FN double crm_atan2_guess(double y, double x) {
     double ax = fabs(x), ay = fabs(y);

@@ -340,7 +340,7 @@ int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goa
 }
 
 int rrtk_crmath_probe_dev(int kind, int64_t n, const double *a, const double *b, double *out, void *stream) {
-    if (kind < 0 || kind > 7 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
+    if (kind < 0 || kind > 8 || n < 0) return set_error(RRTK_ERR_INVALID, "bad kind/n");
     if (n == 0) return RRTK_OK;
     if (!a || !out || (!b && (kind == 0 || kind == 1 || kind == 4 || kind == 5))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_crmath_probe(kind, n, a, b, out, (cudaStream_t)stream);

@@ -728,6 +728,7 @@ extern "C" __global__ void crmath_probe_kernel(int kind, int64_t n, const double
         case 5: (void)crm_atan2_sincos(a[i], b[i], &s, &c); r = c; break;
         case 6: r = crm_acos(a[i]); break;
         case 7: r = crm_asin(a[i]); break;
+        case 8: r = crm_tan(a[i]); break;
     }
     out[i] = r;
 }
