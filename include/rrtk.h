@@ -62,7 +62,7 @@ RRTK_API const char *rrtk_last_error(void);
 RRTK_API int rrtk_device_count(void);
 /* sizeof of the parameter / result structs as this library was compiled (bindings check their own layout against it):
  * 0 rrtk_rrtstar_params, 1 rrtk_informed_params, 2 rrtk_informed_tree_params, 3 rrtk_informed_tree_result,
- * 4 rrtk_dubins_params; -1 for an unknown index */
+ * 4 rrtk_dubins_params, 5 rrtk_closed_loop_params; -1 for an unknown index */
 RRTK_API int rrtk_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
@@ -311,6 +311,10 @@ typedef struct rrtk_dubins_params {
     double curvature;
     double step_size;               /* 0.1 in the reference (rrt_05:1022) */
     double goal_xy_th, goal_yaw_th;
+    int32_t rs_cost;                /* rrtk_rrtstar_rs_run_dev only.  0: rrt_06 (Euclidean costs, the later calc_new_cost wins);
+                                     * 1: rrt_10:1005-1207 -- choose_parent / rewire / propagate_cost_to_leaves cost an edge by
+                                     * its Reeds-Shepp length (calc_new_cost :1153-1161) */
+    int32_t pad_;
 } rrtk_dubins_params;
 
 /*   start_goal6 [Q][6] = sx, sy, syaw, gx, gy, gyaw;  obstacles [Q][obs_stride][4] = x, y, size + rr, (size + rr)**2;
@@ -331,12 +335,42 @@ RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const doub
  * with reeds_shepp_path_planning as steer (:1584-1604; p->step_size is its step_size, 0.2 by default in the reference),
  * a sampler without goal bias (:1658-1666, the caller's stream), and try_goal_path after every append (:1572-1582), which
  * can add a second node per iteration: node_cap >= 2 * max_iter + 1.  Arguments as for rrtk_rrtstar_dubins_run_dev;
- * edge_from / edge_to regenerate a node's course with rrtk_reeds_shepp_steer_dev. */
+ * edge_from / edge_to regenerate a node's course with rrtk_reeds_shepp_steer_dev.
+ * p->rs_cost = 1 is `RRTStarReedsShepp.planning` of rrt_10:1050-1090, the planner under ClosedLoopRRTStar: same loop,
+ * Reeds-Shepp-length costs; its find_near_nodes does not clip the radius (rrt_10:521-523), so the caller's near_r2 table
+ * is (ccd * sqrt(log(k) / k))**2. */
 RRTK_API int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
                                      const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
                                      double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
                                      int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                                      int32_t *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Closed-loop RRT* feasibility filter -- check_tracking_path_is_feasible of rrt_10:1521-1559 for P candidate courses:
+ * extend_path (:1432-1447), calc_speed_profile / set_stop_point (:1375-1429), closed_loop_prediction (:1307-1372, unicycle
+ * `update` :1224-1232 + pure_pursuit_control :1255-1283 + PIDControl :1243-1252; constants :1592-1607) and the four
+ * checks (goal reached, final angle, travel ratio, collision of the tracked trajectory).
+ *   course     [P][course_cap][3]  x, y, yaw in DRIVING order (start -> goal: generate_final_course reversed), n_course [P] >= 3
+ *   obstacles  rows x, y, size + rr, (size + rr)**2;  course k tests rows obs_offset[k] .. obs_offset[k] + n_obs[k] - 1
+ *   work       [P][course_cap + 6][4] doubles of scratch (the extended course and its speed profile)
+ *   traj       [P][traj_cap][7]    x, y, yaw, v, t, a, d of the prediction (traj_cap >= 2003 always suffices: T / dt steps)
+ *   n_traj [P], bits [P]: RRTK_CL_* reject reasons, 0 = feasible.
+ * search_best_feasible_path (:1494-1519) is then: the LAST course with bits == 0 and minimal traj[n_traj - 1][4].
+ * ------------------------------------------------------------------------------------------- */
+#define RRTK_CL_NOT_REACHED 1
+#define RRTK_CL_BAD_ANGLE 2
+#define RRTK_CL_TOO_LONG 4
+#define RRTK_CL_COLLISION 8
+#define RRTK_CL_TRAJ_OVERFLOW 16
+typedef struct rrtk_closed_loop_params {
+    int32_t n_courses, course_cap, traj_cap, pad_;
+    double target_speed;            /* 10 / 3.6 in the script */
+    double yaw_th;                  /* the final-angle check is |yaw - goal yaw| >= 10 * yaw_th (:1538) */
+    double invalid_travel_ratio;
+} rrtk_closed_loop_params;
+RRTK_API int rrtk_closed_loop_dev(const rrtk_closed_loop_params *p, const double *course, const int32_t *n_course,
+                                  const double *obstacles, const int32_t *obs_offset, const int32_t *n_obs, double *work,
+                                  double *traj, int32_t *n_traj, int32_t *bits, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.

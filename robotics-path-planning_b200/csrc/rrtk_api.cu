@@ -65,6 +65,9 @@ int launch_informed_tree(const rrtk_informed_tree_params &p, const double *obsta
                          double *path, rrtk_informed_tree_result *res, void *workspace, size_t workspace_bytes,
                          cudaStream_t s);
 int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *workspace, size_t workspace_bytes, cudaStream_t s);
+int launch_closed_loop(const rrtk_closed_loop_params &p, const double *course, const int32_t *n_course, const double *obstacles,
+                       const int32_t *obs_offset, const int32_t *n_obs, double *work, double *traj, int32_t *n_traj,
+                       int32_t *bits, cudaStream_t s);
 int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
                         const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
                         cudaStream_t s);
@@ -123,6 +126,7 @@ int rrtk_sizeof(int which) {
         case 2: return (int)sizeof(rrtk_informed_tree_params);
         case 3: return (int)sizeof(rrtk_informed_tree_result);
         case 4: return (int)sizeof(rrtk_dubins_params);
+        case 5: return (int)sizeof(rrtk_closed_loop_params);
         default: return -1;
     }
 }
@@ -302,6 +306,7 @@ int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goa
     cudaStream_t s = (cudaStream_t)stream;
     DevCounter ctr(s);
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    if (p->rs_cost != 0 && p->rs_cost != 1) return set_error(RRTK_ERR_INVALID, "rs_cost must be 0 or 1");
     return launch_rrtstar_rs(*p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from,
                                  edge_to, n_nodes, iters_done, goal_index, status, workspace, ctr.ptr, s);
 }
@@ -327,6 +332,18 @@ int rrtk_path_smoothing_dev(int32_t n_queries, int32_t path_cap, int32_t max_ite
     if ((uintptr_t)path & 15) return set_error(RRTK_ERR_INVALID, "path must be 16-byte aligned");
     return launch_smooth_paths(n_queries, path_cap, max_iter, path, path_len, draws, obstacles3, obs_stride, n_obs, status,
                                iters_done, (cudaStream_t)stream);
+}
+
+int rrtk_closed_loop_dev(const rrtk_closed_loop_params *p, const double *course, const int32_t *n_course,
+                         const double *obstacles, const int32_t *obs_offset, const int32_t *n_obs, double *work, double *traj,
+                         int32_t *n_traj, int32_t *bits, void *stream) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->n_courses < 0 || p->course_cap < 3 || p->traj_cap < 1) return set_error(RRTK_ERR_INVALID, "bad sizes (course_cap >= 3, traj_cap >= 1)");
+    if (p->n_courses == 0) return RRTK_OK;
+    if (!course || !n_course || !obs_offset || !n_obs || !work || !traj || !n_traj || !bits)
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)obstacles & 15) return set_error(RRTK_ERR_INVALID, "obstacles must be 16-byte aligned");
+    return launch_closed_loop(*p, course, n_course, obstacles, obs_offset, n_obs, work, traj, n_traj, bits, (cudaStream_t)stream);
 }
 
 int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,

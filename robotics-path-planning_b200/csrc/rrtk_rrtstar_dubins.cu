@@ -48,6 +48,39 @@ __device__ __forceinline__ PEdge plan_edge(double sx, double sy, double syaw, do
     return r;
 }
 
+// propagate_cost_to_leaves with rrt_10's calc_new_cost (:572-577, :1153-1161): cost = parent cost + Reeds-Shepp length of
+// the course parent pose -> child pose (inf when there is none).  Breadth-first over the children lists like
+// propagate_lists; one lane per frontier node.
+static __device__ __noinline__ void propagate_lists_rs(int root, const double2 *xy, const double *yaw, double *cost, int4 *links,
+                                                       int *tail, int lane, double kappa, double step) {
+    if (links[root].x < 0) return;
+    if (lane == 0) { links[0].w = root; *tail = 1; }
+    __syncwarp();
+    for (int head = 0;;) {
+        const int end = *tail;
+        if (head >= end) break;
+        const int k = head + lane;
+        __syncwarp();
+        if (k < end) {
+            const int p = links[k].w;
+            const double2 a = xy[p];
+            const double ayaw = yaw[p], cp = cost[p];
+            for (int c = links[p].x; c >= 0;) {
+                const int4 lc = links[c];
+                const double2 b = xy[c];
+                const RsEdge e = rs_edge_lane(a.x, a.y, ayaw, b.x, b.y, yaw[c], kappa, step, nullptr, 0, true);
+                cost[c] = e.npts > 0 ? cp + e.lsum : CUDART_INF;
+                if (lc.x >= 0) links[atomicAdd(tail, 1)].w = c;
+                c = lc.y;
+            }
+        }
+        __syncwarp();
+        head = end < head + 32 ? end : head + 32;
+    }
+}
+
+// STEER = 2: rrt_10's RRTStarReedsShepp (rrt_10:1005-1207) -- the STEER = 1 loop with Reeds-Shepp-length costs in
+// choose_parent / rewire / propagate (the host passes an unclipped near radius table, rrt_10:521-523).
 // STEER = 1 also runs rrt_06's try_goal_path after every append (:1572-1582): the new node is steered to the goal and
 // that node is appended too when its course is free, costing the Reeds-Shepp length (:1601).
 template <int STEER>
@@ -131,7 +164,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
             if (truthy && e0.free_) {
                 const double nx = e0.ex, ny = e0.ey, nyaw = e0.eyaw;
                 truthy = false;
-                if (n + (STEER == 1 ? 1 : 0) >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
+                if (n + (STEER >= 1 ? 1 : 0) >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; break; }
                 // find_near_nodes (rrt_05:1715-1739)
                 const double r2 = near_r2[n + 1];
                 int count = 0;
@@ -172,7 +205,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     const double2 a = xy[i];
                     const PEdge e = plan_edge<STEER>(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
                     if (e.valid && e.free_) {
-                        const double c = cost[i] + crm_hypot(nx - a.x, ny - a.y);
+                        const double c = cost[i] + (STEER == 2 ? e.lsum : crm_hypot(nx - a.x, ny - a.y));
                         if (c < mc) { mc = c; bk = k; bex = e.ex; bey = e.ey; beyaw = e.eyaw; }
                     }
                 }
@@ -202,7 +235,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         const double2 a = xy[i];
                         const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
                         flags[k] = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
-                        nd[k] = mc + crm_hypot(a.x - cx, a.y - cy);
+                        nd[k] = mc + (STEER == 2 ? e.lsum : crm_hypot(a.x - cx, a.y - cy));
                         s_end[3 * k] = e.ex; s_end[3 * k + 1] = e.ey; s_end[3 * k + 2] = e.eyaw;
                     }
                     __syncwarp();
@@ -216,7 +249,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         if (fl & 4) {  // node i was re-parented (moved) earlier in this call: redo its edge
                             const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
                             fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
-                            ecost = mc + crm_hypot(a.x - cx, a.y - cy);
+                            ecost = mc + (STEER == 2 ? e.lsum : crm_hypot(a.x - cx, a.y - cy));
                             ex = e.ex; ey = e.ey; eyw = e.eyaw;
                         }
                         if ((fl & 3) != 3) continue;
@@ -233,10 +266,11 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                             for (int k2 = k + 1 + lane; k2 < count; k2 += 32)
                                 if (near_idx[k2] == i) flags[k2] |= 4;
                             __syncwarp();
-                            propagate_lists(i, xy, cost, links, qtail, lane);
+                            if (STEER == 2) propagate_lists_rs(i, xy, yaw, cost, links, qtail, lane, kappa, step);
+                            else propagate_lists(i, xy, cost, links, qtail, lane);
                         }
                     }
-                    if (STEER == 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
+                    if (STEER >= 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
                         const double2 a = xy[newi];
                         const double ayaw = yaw[newi];
                         const PEdge eg = plan_edge<STEER>(a.x, a.y, ayaw, gx, gy, gyaw, kappa, step, obs, n_obs);  // uniform
@@ -281,7 +315,7 @@ int launch_rrtstar_steer(int steer, const rrtk_dubins_params &p, const double *s
     typedef void (*kernel_t)(rrtk_dubins_params, const double *, const double4 *, const int32_t *, const double *, const double *,
                              double2 *, double *, double *, int32_t *, double *, double *, int32_t *, int32_t *, int32_t *,
                              int32_t *, int32_t *, unsigned int *);
-    const kernel_t kern = steer == 1 ? rrtstar_dubins_kernel<1> : rrtstar_dubins_kernel<0>;
+    const kernel_t kern = steer == 2 ? rrtstar_dubins_kernel<2> : steer == 1 ? rrtstar_dubins_kernel<1> : rrtstar_dubins_kernel<0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
     int dev = 0, sms = 0, per_sm = 0;
@@ -318,7 +352,7 @@ int launch_rrtstar_rs(const rrtk_dubins_params &p, const double *start_goal6, co
                       double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
                       int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                       int32_t *workspace, unsigned int *counter, cudaStream_t s) {
-    return launch_rrtstar_steer(1, p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from, edge_to,
+    return launch_rrtstar_steer(p.rs_cost ? 2 : 1, p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from, edge_to,
                                 n_nodes, iters_done, goal_index, status, workspace, counter, s);
 }
 

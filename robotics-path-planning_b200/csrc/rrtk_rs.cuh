@@ -165,8 +165,11 @@ struct RsEdge {
     bool free_;
 };
 
+// lengths_only: stop after the word selection (npts = 1 marks "a course exists", lsum = its length) -- what
+// rrt_10's calc_new_cost (:1153-1161) needs from reeds_shepp_path_planning.
 static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
-                                                   double maxc, double step_size, const double4 *obs, int n_obs) {
+                                                   double maxc, double step_size, const double4 *obs, int n_obs,
+                                                   bool lengths_only = false) {
     RsEdge e;
     e.ex = e.ey = e.eyaw = e.lsum = 0.0;
     e.npts = 0;
@@ -206,6 +209,13 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
     }
     if (best < 0) return e;
     const int f = best >> 2, k = best & 3, n = RS_N[f];
+    if (lengths_only) {
+        double ls = 0.0;
+        for (int i = 0; i < n; i++) ls = ls + fabs(best_d[i] / maxc);
+        e.lsum = ls;
+        e.npts = 1;
+        return e;
+    }
     double sm0, cm0;
     sincos_cr(-syaw, &sm0, &cm0);
     bool hit = false;
@@ -226,6 +236,7 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         double lx = 0.0, ly = 0.0, lyaw = 0.0;
 #pragma unroll 1
         for (long long j = 0; j <= na; j++) {
+            if (hit && j < na) continue;   // verdict known: only the segment end (the next origin / the end pose) is needed
             const double dist = j < na ? 0.0 + (double)j * dd : length;
             rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
             const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;

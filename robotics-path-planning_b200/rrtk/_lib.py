@@ -57,8 +57,16 @@ class DubinsParams(C.Structure):
     _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
                 ("obs_stride", C.c_int32), ("near_cap", C.c_int32), ("search_until_max_iter", C.c_int32),
                 ("curvature", C.c_double), ("step_size", C.c_double), ("goal_xy_th", C.c_double),
-                ("goal_yaw_th", C.c_double)]
+                ("goal_yaw_th", C.c_double), ("rs_cost", C.c_int32), ("pad_", C.c_int32)]
 
+
+class ClosedLoopParams(C.Structure):
+    """struct rrtk_closed_loop_params (include/rrtk.h)."""
+    _fields_ = [("n_courses", C.c_int32), ("course_cap", C.c_int32), ("traj_cap", C.c_int32), ("pad_", C.c_int32),
+                ("target_speed", C.c_double), ("yaw_th", C.c_double), ("invalid_travel_ratio", C.c_double)]
+
+
+CL_NOT_REACHED, CL_BAD_ANGLE, CL_TOO_LONG, CL_COLLISION, CL_TRAJ_OVERFLOW = 1, 2, 4, 8, 16
 
 _lib = None
 
@@ -85,6 +93,7 @@ _SIGS = {
                                              _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_path_smoothing_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "rrtk_closed_loop_dev": (C.c_int, [C.POINTER(ClosedLoopParams), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),

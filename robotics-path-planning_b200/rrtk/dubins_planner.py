@@ -43,7 +43,8 @@ class Node:
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0,
               connect_circle_dist=50.0, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5,
-              search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1, timing=None):
+              search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1, timing=None,
+              rs_cost=False):
     """Q RRT*-Dubins (steer="dubins") or RRT*-Reeds-Shepp (steer="rs", rrt_06) queries in one launch.
     starts/goals [Q, 3]; streams [Q, max_iter, 3].  Returns a list of dicts (numpy arrays trimmed to n_nodes).
     `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch)."""
@@ -59,6 +60,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
     p.search_until_max_iter = int(bool(search_until_max_iter))
     p.curvature, p.step_size = float(curvature), 0.1 if steer == "dubins" else float(step_size)
     p.goal_xy_th, p.goal_yaw_th = float(goal_xy_th), float(goal_yaw_th)
+    p.rs_cost = int(bool(rs_cost))          # rrt_10's RRTStarReedsShepp: Reeds-Shepp-length costs (steer="rs" only)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     with torch.cuda.device(dev):
         d_sg, d_obs, d_cnt = t(np.hstack([starts, goals])), t(rows), t(counts)
