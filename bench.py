@@ -562,7 +562,8 @@ def extras(torch, dev):
             tree_iters_per_s=i["iters_done"] / t, c_best=i["c_best"], mean_near=i["total_hits"] / max(1, i["iters_done"]),
             reached_node_cap=bool(i["status"] & 2), scan_gbs_algorithmic=alg_bytes / t / 1e9,
             goal_events=i["goal_events"], resamples=i["resamples"], grid=i["grid"],
-            cycles_per_iter=([round(c / max(1, i["iters_done"])) for c in i["cycles"]] if any(i["cycles"]) else None),
+            cycles_per_iter=([round(c / max(1, i["iters_done"])) for c in i["cycles"]]
+                             if any(c >= i["iters_done"] for c in i["cycles"]) else None),   # only the unbatched kernel records them
             note="one fused FP64 pass (16 B/node) per iteration over an L2-resident tree; latency-bound by the "
                  "grid-wide exchange and the serial leaf math, see DESIGN.md 5.5")
         del run, d_free, d_ball
@@ -587,6 +588,33 @@ def extras(torch, dev):
                                           solved=int(sum(r["goal_index"] >= 0 for r in res)))
     except Exception as e:  # noqa: BLE001
         out["rrtstar_reeds_shepp"] = dict(error=repr(e))
+    try:   # Closed-loop RRT* (rrt_10): 256 RRT*-RS trees with Reeds-Shepp-length costs x 100 iterations
+        #        (built-in scenario, rrt_10:1610-1660), then pure-pursuit tracking of EVERY goal-reaching course
+        from rrtk import closed_loop as CL, rs_planner as RP
+        Q, iters = 256, 100
+        rng = np.random.default_rng(19)
+        st = np.concatenate([rng.uniform(-2, 20, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+        obs1 = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+        start, goal = [0.0, 0.0, 0.0], [6.0, 9.0, math.radians(90.0)]
+        tm, tf = {}, {}
+        for rep in range(2):
+            t0 = time.perf_counter()
+            trees = RP.run_batch([start] * Q, [goal] * Q, [obs1] * Q, float("inf"), iters, st, curvature=1.0, step_size=0.2,
+                                 near_cap=224, timing=tm, rs_cost=True)
+            courses = []
+            for tr in trees:
+                gi = [i for i in range(tr["n"]) if math.hypot(tr["x"][i] - goal[0], tr["y"][i] - goal[1]) <= 0.5
+                      and abs(tr["yaw"][i] - goal[2]) <= math.radians(3.0)]
+                courses += [np.asarray(c)[::-1] for c in CL.final_courses(tr, gi[:8], start, goal, 1.0, 0.2)]
+            res = CL.closed_loop_batch(courses, obs1, timing=tf)
+            t = time.perf_counter() - t0
+        steps = int(sum(len(r["traj"]) for r in res))
+        out["closed_loop_rrtstar"] = dict(
+            queries=Q, iters=iters, planner_kernel_ms=tm["kernel_ms"], planner_tree_iters_per_s=Q * iters / (tm["kernel_ms"] / 1e3),
+            courses=len(courses), feasible=int(sum(r["bits"] == 0 for r in res)), filter_kernel_ms=tf["kernel_ms"],
+            tracking_steps_per_s=steps / (tf["kernel_ms"] / 1e3), s_e2e=t)
+    except Exception as e:  # noqa: BLE001
+        out["closed_loop_rrtstar"] = dict(error=repr(e))
     try:   # Informed RRT* (rrt_07 semantics), 512 queries x 1000 iterations, built-in scenario
         Q, iters = 512, 1000
         rng = np.random.default_rng(8)
