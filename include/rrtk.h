@@ -62,7 +62,7 @@ RRTK_API const char *rrtk_last_error(void);
 RRTK_API int rrtk_device_count(void);
 /* sizeof of the parameter / result structs as this library was compiled (bindings check their own layout against it):
  * 0 rrtk_rrtstar_params, 1 rrtk_informed_params, 2 rrtk_informed_tree_params, 3 rrtk_informed_tree_result,
- * 4 rrtk_dubins_params, 5 rrtk_closed_loop_params; -1 for an unknown index */
+ * 4 rrtk_dubins_params, 5 rrtk_closed_loop_params, 6 rrtk_bitstar_params; -1 for an unknown index */
 RRTK_API int rrtk_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
@@ -371,6 +371,40 @@ typedef struct rrtk_closed_loop_params {
 RRTK_API int rrtk_closed_loop_dev(const rrtk_closed_loop_params *p, const double *course, const int32_t *n_course,
                                   const double *obstacles, const int32_t *obs_offset, const int32_t *n_obs, double *work,
                                   double *traj, int32_t *n_traj, int32_t *bits, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BIT* -- `BITStar.plan` of rrt_08:236-331 (+ setup_planning :186-216, setup_sample :218-234, informed_sample :385-419,
+ * the queue scoring :439-474, expand_vertex :476-501, connect / _collision_check :359-383, update_graph :524-552,
+ * remove_queue :343-351, find_final_path :333-341, and RTree's id <-> coordinate maps :65-135) for Q independent queries.
+ *   start_goal [Q][4]; rot [Q][4] = the 2 x 2 block of C (:205-213, host-evaluated); obstacles [Q][obs_stride][4] = x, y,
+ *   size, size**2; n_obs [Q]; draws [Q][n_draws] = the unit draws `random.random()` returns, in the reference's order of
+ *   consumption (`random.uniform(a, b)` is a + (b - a) * draw); num_cells = np.ceil((randArea[1] - randArea[0]) / 0.01).
+ * outputs: path [Q][path_cap][2] start -> goal (find_final_path), counts [Q][12] = vertices, edges, parent entries, sample
+ *   slots, vertex queue, edge queue, path length (0 = "cannot find Path"), draws used, batches, "Nothing good" resets,
+ *   skipped edges, vertex expansions; g_goal [Q] = g_scores[goalId]; status [Q] = RRTK_BIT_* bits (INDEX_ERROR is where
+ *   the reference raises IndexError: both queues ran empty inside the expansion loop).
+ * workspace: ws_d [Q][RRTK_BITSTAR_WS_DOUBLES], ws_i [Q][RRTK_BITSTAR_WS_INTS] -- the ordered containers of the run (samples,
+ *   score table, tree, queues), left in place for inspection (layout: csrc/rrtk_bitstar.cu).
+ * ------------------------------------------------------------------------------------------- */
+#define RRTK_BIT_SAMPLE_OVERFLOW 1
+#define RRTK_BIT_EDGE_OVERFLOW 2
+#define RRTK_BIT_VERTEX_OVERFLOW 4
+#define RRTK_BIT_DRAWS_EXHAUSTED 8
+#define RRTK_BIT_INDEX_ERROR 16
+#define RRTK_BIT_PATH_OVERFLOW 32
+#define RRTK_BIT_LIVELOCK 64        /* every edge of the first batch was skipped: `iterations` stays 0, the reference loops forever */
+typedef struct rrtk_bitstar_params {
+    int32_t n_queries, max_iter;
+    int32_t vertex_cap;             /* >= max_iter + 1 (one vertex per counted iteration at most) */
+    int32_t sample_cap, edge_cap, path_cap, obs_stride, n_draws;
+    double min_rand, max_rand, num_cells;
+} rrtk_bitstar_params;
+#define RRTK_BITSTAR_WS_DOUBLES(vertex_cap, sample_cap, edge_cap) \
+    (3 * (size_t)(sample_cap) + 4 * ((size_t)(vertex_cap) + 2) + (size_t)(edge_cap))
+#define RRTK_BITSTAR_WS_INTS(vertex_cap, sample_cap, edge_cap) (8 * ((size_t)(vertex_cap) + 2) + (size_t)(edge_cap))
+RRTK_API int rrtk_bitstar_run_dev(const rrtk_bitstar_params *p, const double *start_goal, const double *rot,
+                                  const double *obstacles, const int32_t *n_obs, const double *draws, double *ws_d,
+                                  int32_t *ws_i, double *path, int32_t *counts, double *g_goal, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Large-tree mode (BASELINE config 3): brute-force searches over an HBM-resident float2 node array.

@@ -376,6 +376,60 @@ class _InjectedRandom:
         return a + (b - a) * next(self.it)
 
 
+class _InjectedRandom2(_InjectedRandom):
+    """+ random() for sample_unit_ball (rrt_08:421-430); counts the draws consumed."""
+
+    def __init__(self, draws):
+        super().__init__(draws)
+        self.used = 0
+
+    def uniform(self, a, b):
+        self.used += 1
+        return super().uniform(a, b)
+
+    def random(self):
+        self.used += 1
+        return next(self.it)
+
+
+def run_rrt08(name, params, seed, n_draws=40000):
+    """BITStar.plan (rrt_08:236-331) of the unmodified reference on a recorded stream of unit draws."""
+    ns = ref_loader.load("rrt_08")
+    draws = np.random.default_rng(seed).random(n_draws)
+    inj = _InjectedRandom2(draws.tolist())
+    ns["random"] = inj
+    b = ns["BITStar"](**params)
+    t0 = time.perf_counter()
+    err = ""
+    with ref_loader.quiet():
+        try:
+            path = b.plan(animation=False)
+        except IndexError as e:                       # both queues ran empty (best_in_vertex_queue on an empty list)
+            path, err = [], "IndexError"
+    wall = time.perf_counter() - t0
+    vid = np.array([float(k) for k in b.tree.vertices.keys()])
+    meta = dict(params)
+    meta.update(kind="rrt_08", seed=seed, reference_wall_s=wall, draws_used=inj.used, error=err,
+                g_goal=float(b.g_scores[b.goalId]), start_id=float(b.startId), goal_id=float(b.goalId))
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), draws=draws[:inj.used],
+        path=np.array([[float(x), float(y)] for x, y in path]) if len(path) else np.zeros((0, 2)),
+        vertices=vid, g_vertices=np.array([float(b.g_scores[k]) for k in b.tree.vertices.keys()]),
+        edges=np.array([[float(v), float(x)] for v, x in b.tree.edges]).reshape(-1, 2),
+        parent_of=np.array([[float(k), float(v)] for k, v in b.nodes.items()]).reshape(-1, 2),
+        sample_ids=np.array([float(k) for k in b.samples.keys()]),
+        sample_xy=np.array([[float(v[0]), float(v[1])] for v in b.samples.values()]).reshape(-1, 2),
+        vertex_queue=np.array([float(v) for v in b.vertex_queue]),
+        edge_queue=np.array([[float(v), float(x)] for v, x in b.edge_queue]).reshape(-1, 2))
+    print(f"{name}: {len(vid)} vertices, {len(b.tree.edges)} edges, path {len(path)} points, g(goal) {meta['g_goal']:.6f}, "
+          f"{inj.used} draws, {wall:.1f} s {err}")
+
+
+C8 = dict(start=[-1.0, 0.0], goal=[3.0, 8.0],
+          obstacleList=[(5, 5, 0.5), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)],
+          randArea=[-2, 15], maxIter=80)                                          # rrt_08:644-679
+
+
 def run_smoothing(name, src_fixture, max_iter, seed, obstacle_list=None):
     """path_smoothing (rrt_04:1447-1479) of the final course of an existing rrt_04 fixture."""
     ns = ref_loader.load("rrt_04")
@@ -457,6 +511,13 @@ def run_reeds_shepp(name, n, seed):
 
 
 CASES = {
+    "rrt08_builtin_80": lambda: run_rrt08("rrt08_builtin_80", C8, 31),
+    "rrt08_builtin_200": lambda: run_rrt08("rrt08_builtin_200", dict(C8, maxIter=200), 32),
+    "rrt08_dense_120": lambda: run_rrt08("rrt08_dense_120", dict(
+        C8, start=[0.0, 0.0], goal=[9.0, 9.0], maxIter=120,
+        obstacleList=[(5, 5, 1.0), (3, 6, 1.5), (3, 8, 1.0), (7, 5, 1.5), (6, 8, 1.0), (8, 2, 1.0), (2, 3, 0.8)]), 33),
+    "rrt08_far_goal_300": lambda: run_rrt08("rrt08_far_goal_300", dict(
+        C8, start=[0.0, 0.0], goal=[14.0, 14.0], maxIter=300, obstacleList=[(5, 5, 1.0), (10, 10, 2.0)]), 100),
     "rrt10_cl_60": lambda: run_rrt10("rrt10_cl_60", dict(C10, max_iter=60), 5),
     "rrt10_cl_builtin_150": lambda: run_rrt10("rrt10_cl_builtin_150", C10, 11),
     "rrt10_cl_radius_100": lambda: run_rrt10("rrt10_cl_radius_100", dict(C10, max_iter=100, robot_radius=0.3,

@@ -7,6 +7,7 @@ is not using it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseli
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 
@@ -429,3 +430,49 @@ def closed_loop_best(courses, *a, **k):
         if r["bits"] == 0 and best_time >= r["traj"][-1, 4]:
             best_time, best = r["traj"][-1, 4], i
     return best, res
+
+
+class BitParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("sx", "sy", "gx", "gy", "min_rand", "max_rand", "lower", "resolution", "num_cells")] + \
+               [("rot", C.c_double * 4)] + [(k, C.c_int32) for k in ("max_iter", "n_obs", "math_mode", "n_draws")]
+
+
+def bit_rotation(start, goal):
+    """The 2 x 2 block of C in BITStar.setup_planning (rrt_08:199-213), evaluated with numpy like the reference."""
+    c_min = math.hypot(start[0] - goal[0], start[1] - goal[1]) / 1.5
+    a1 = np.array([[(goal[0] - start[0]) / c_min], [(goal[1] - start[1]) / c_min], [0]])
+    m = np.dot(a1, np.array([1.0, 0.0, 0.0]).reshape(1, 3))
+    u, _, vh = np.linalg.svd(m, True, True)
+    c = np.dot(np.dot(u, np.diag([1.0, 1.0, np.linalg.det(u) * np.linalg.det(np.transpose(vh))])), vh)
+    return [float(c[0, 0]), float(c[0, 1]), float(c[1, 0]), float(c[1, 1])]
+
+
+def bitstar_plan(start, goal, obstacle_list, rand_area, max_iter, draws, math_mode=MATH_LIBM, vcap=None, scap=8192,
+                 ecap=1 << 18):
+    """BITStar.plan (rrt_08:236-331) on a recorded stream of unit draws.  Returns dict(path, vertices, g_vertices, edges,
+    parent_of, sample_ids, sample_xy, vertex_queue, edge_queue, g_goal, draws_used, status)."""
+    p = BitParams()
+    p.sx, p.sy, p.gx, p.gy = float(start[0]), float(start[1]), float(goal[0]), float(goal[1])
+    p.min_rand, p.max_rand = float(rand_area[0]), float(rand_area[1])
+    p.lower, p.resolution = float(rand_area[0]), 0.01
+    p.num_cells = float(np.ceil((rand_area[1] - rand_area[0]) / 0.01))
+    p.rot[:] = bit_rotation(start, goal)
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    d = np.ascontiguousarray(draws, dtype=np.float64)
+    p.max_iter, p.n_obs, p.math_mode, p.n_draws = int(max_iter), obs.shape[0], int(math_mode), d.size
+    vcap = max_iter + 2 if vcap is None else vcap
+    pcap = vcap + 2
+    vert = np.zeros(vcap); gv = np.zeros(vcap); edges = np.zeros((vcap, 2)); par = np.zeros((vcap, 2))
+    sid = np.zeros(scap); sxy = np.zeros((scap, 2)); vq = np.zeros(vcap); eq = np.zeros((ecap, 2)); path = np.zeros((pcap, 2))
+    counts = np.zeros(12, np.int32)
+    gg = C.c_double()
+    f = lib().orc_bitstar_plan
+    f.restype = C.c_int
+    rc = f(C.byref(p), _p(obs, C.c_double), _p(d, C.c_double), vcap, scap, ecap, pcap, _p(vert, C.c_double),
+           _p(gv, C.c_double), _p(edges, C.c_double), _p(par, C.c_double), _p(sid, C.c_double), _p(sxy, C.c_double),
+           _p(vq, C.c_double), _p(eq, C.c_double), _p(path, C.c_double), _p(counts, C.c_int32), C.byref(gg))
+    nv, ne, npar, ns, nvq, neq, plen, used = [int(v) for v in counts[:8]]
+    return dict(status=rc, path=path[:plen].copy(), vertices=vert[:nv].copy(), g_vertices=gv[:nv].copy(),
+                edges=edges[:ne].copy(), parent_of=par[:npar].copy(), sample_ids=sid[:ns].copy(), sample_xy=sxy[:ns].copy(),
+                vertex_queue=vq[:nvq].copy(), edge_queue=eq[:neq].copy(), g_goal=gg.value, draws_used=used,
+                batches=int(counts[8]), resets=int(counts[9]), skipped=int(counts[10]), expansions=int(counts[11]))

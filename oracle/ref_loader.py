@@ -30,6 +30,7 @@ FILES = {
     "dub00": ("10_path_planning_00_dubins_path.py", 423),
     "rrt_06": ("10_path_planning_01_rrt_06_rrt_star_reeds_shepp_path.py", 2005),
     "rs00": ("10_path_planning_00_reeds_shepp_path.py", 515),
+    "rrt_08": ("10_path_planning_01_rrt_08_batch_informed_rrt_star.py", 611),
     "rrt_10": ("10_path_planning_01_rrt_10_closed_loop_rrt_star.py", 1608),   # classes + the constants :1592-1607
 }
 

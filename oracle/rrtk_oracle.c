@@ -1647,3 +1647,359 @@ ORC_EXPORT int orc_closed_loop(const orc_cl_params_t *p, int32_t n_course, const
     free(cx);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* BIT* (rrt_08:138-611, RTree :29-135): batch informed trees as the reference implements  */
+/* them -- ids are cells of a 0.01 grid over randArea, every cost is taken between the      */
+/* QUANTISED coordinates of two ids (only expand_vertex's radius test reads a sample's raw  */
+/* coordinates), dicts and lists keep Python's insertion order.  Quirks kept: informed_sample */
+/* draws m + 1 samples; best_edge_queue_value is the MAXIMUM (sort(reverse=True)[0], :455-463); */
+/* add_vertex_to_edge_queue pairs vid with itself and never appends (:503-522); the two      */
+/* `continue`s in plan skip `iterations += 1` (:286, :293); remove_queue removes from the list */
+/* it iterates (:343-351); cMin = |start - goal| / 1.5 (:199-200).                           */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    double sx, sy, gx, gy, min_rand, max_rand;
+    double lower, resolution, num_cells; /* RTree: lowerLimit = randArea[0], 0.01, np.ceil((upper - lower) / resolution) */
+    double rot[4];                       /* 2 x 2 block of C (:205-213), host-evaluated */
+    int32_t max_iter, n_obs, math_mode, n_draws;
+} orc_bit_params_t;
+
+typedef struct { double *id, *x, *y; int n, cap; } bit_samples_t;
+typedef struct { const orc_bit_params_t *p; } bit_ctx_t;
+
+static double bit_id_of(const orc_bit_params_t *p, double x, double y) { /* real_world_to_node_id (:65-101) */
+    const double c0 = (double)(long long)rint((x - p->lower) / p->resolution);
+    const double c1 = (double)(long long)rint((y - p->lower) / p->resolution);
+    return (0.0 + c1 * p->num_cells) + c0;
+}
+static void bit_coord_of(const orc_bit_params_t *p, double id, double *x, double *y) { /* node_id_to_real_world_coord (:115-135) */
+    const double c1 = floor(id / p->num_cells);
+    id = id - c1 * p->num_cells;
+    const double c0 = floor(id / 1.0);
+    *x = p->lower + p->resolution * c0;
+    *y = p->lower + p->resolution * c1;
+}
+/* np.linalg.norm(v, 2) of a 2-vector = sqrt(v.dot(v)): BLAS ddot, whose scalar tail loop is compiled with FMA contraction on
+ * this platform -> sqrt(fma(y, y, x * x)) (checked against numpy on 20 000 random vectors: 20 000 / 20 000, the plain
+ * x*x + y*y form matches 16 669) */
+static inline double bit_norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+static double bit_dist(const orc_bit_params_t *p, double a, double b) { /* np.linalg.norm(coord(b) - coord(a), 2) */
+    double ax, ay, bx, by;
+    bit_coord_of(p, a, &ax, &ay);
+    bit_coord_of(p, b, &bx, &by);
+    const double dx = bx - ax, dy = by - ay;
+    return bit_norm2(dx, dy);
+}
+static void bit_samples_set(bit_samples_t *s, double id, double x, double y) {
+    for (int i = 0; i < s->n; i++)
+        if (s->id[i] == id) { s->x[i] = x; s->y[i] = y; return; }
+    if (s->n == s->cap) {
+        s->cap *= 2;
+        s->id = (double *)realloc(s->id, sizeof(double) * s->cap);
+        s->x = (double *)realloc(s->x, sizeof(double) * s->cap);
+        s->y = (double *)realloc(s->y, sizeof(double) * s->cap);
+    }
+    s->id[s->n] = id; s->x[s->n] = x; s->y[s->n] = y; s->n++;
+}
+static void bit_samples_del(bit_samples_t *s, double id) {
+    for (int i = 0; i < s->n; i++)
+        if (s->id[i] == id) {
+            for (int j = i; j + 1 < s->n; j++) { s->id[j] = s->id[j + 1]; s->x[j] = s->x[j + 1]; s->y[j] = s->y[j + 1]; }
+            s->n--;
+            return;
+        }
+}
+/* informed_sample (:385-419) merged into self.samples; returns 0, or -1 when the draws run out */
+static int bit_informed_sample(const orc_bit_params_t *p, bit_samples_t *s, int m, double c_max, double c_min, double xc,
+                               double yc, const double *draws, int *used) {
+    const int mode = p->math_mode;
+    for (int i = 0; i < m + 1; i++) {
+        double rx, ry;
+        if (*used + 2 > p->n_draws) return -1;
+        const double u0 = draws[*used], u1 = draws[*used + 1];
+        *used += 2;
+        if (c_max < INFINITY) {
+            const double r0 = c_max / 2.0, r1 = sqrt(sq(mode, c_max) - sq(mode, c_min)) / 2.0;
+            double a = u0, b = u1; /* sample_unit_ball (:421-430) */
+            if (b < a) { double t = a; a = b; b = t; }
+            const double ang = 2 * 3.141592653589793 * a / b;
+            const double bx = b * m_cos(mode, ang), by = b * m_sin(mode, ang);
+            const double m00 = p->rot[0] * r0, m01 = p->rot[1] * r1, m10 = p->rot[2] * r0, m11 = p->rot[3] * r1;
+            rx = fma(m00, bx, m01 * by) + xc; /* np.dot(np.dot(C, L), xBall) + xCenter, as in orc_informed_run */
+            ry = fma(m10, bx, m11 * by) + yc;
+        } else { /* sample_free_space (:432-435): random.uniform(a, b) = a + (b - a) * u */
+            rx = p->min_rand + (p->max_rand - p->min_rand) * u0;
+            ry = p->min_rand + (p->max_rand - p->min_rand) * u1;
+        }
+        bit_samples_set(s, bit_id_of(p, rx, ry), rx, ry);
+    }
+    return 0;
+}
+
+/* outputs: vertices [vcap] ids in insertion order, g_vertices, edges [vcap][2], parent_of [vcap][2] (id, parent id; in
+ * the dict's insertion order), samples (ids + xy) [scap], vertex_queue [vcap], edge_queue [ecap][2], path [pcap][2];
+ * counts[8] = n_vertices, n_edges, n_parent, n_samples, n_vq, n_eq, path_len, draws_used;  g_goal.
+ * returns 0, 1 = the reference raises IndexError (both queues empty), 2 = the reference loops forever (every edge of the
+ * first batch is skipped, so `iterations` stays 0 and the same batch is replayed), -1 = a capacity or the draw stream ran out. */
+ORC_EXPORT int orc_bitstar_plan(const orc_bit_params_t *p, const double *obs3, const double *draws, int32_t vcap, int32_t scap,
+                                int32_t ecap, int32_t pcap, double *vertices, double *g_vertices, double *edges, double *parent_of,
+                                double *sample_ids, double *sample_xy, double *vertex_queue, double *edge_queue, double *path,
+                                int32_t *counts, double *g_goal_out) {
+    const int mode = p->math_mode;
+    int rc = 0, used = 0;
+    bit_samples_t S;
+    S.cap = 512; S.n = 0;
+    S.id = (double *)malloc(sizeof(double) * S.cap); S.x = (double *)malloc(sizeof(double) * S.cap); S.y = (double *)malloc(sizeof(double) * S.cap);
+    /* score table: slot 0 = goal, slot 1 = start, then the tree vertices as they appear */
+    const int kcap = vcap + 2;
+    double *k_id = (double *)malloc(sizeof(double) * 4 * kcap), *k_g = k_id + kcap, *k_f = k_g + kcap, *k_par = k_f + kcap;
+    int *k_haspar = (int *)calloc(kcap, sizeof(int)), *par_order = (int *)malloc(sizeof(int) * kcap), n_k = 0, n_par = 0;
+    int *old = (int *)calloc(kcap, sizeof(int));
+    /* tree: vertex list (slot indexes into k_*), add_edge calls in order */
+    int *tv = (int *)malloc(sizeof(int) * kcap), n_v = 0;
+    int *te_v = (int *)malloc(sizeof(int) * 2 * kcap), *te_x = te_v + kcap, n_te = 0;
+    int *vq = (int *)malloc(sizeof(int) * kcap), n_vq = 0;
+    int eqcap = 4096, n_eq = 0;
+    int *eq_v = (int *)malloc(sizeof(int) * eqcap);
+    double *eq_x = (double *)malloc(sizeof(double) * eqcap); /* edge = (tree vertex slot, target id) */
+    int *open_ = (int *)malloc(sizeof(int) * 2 * kcap), *closed = open_ + kcap;
+
+    const double start_id = bit_id_of(p, p->sx, p->sy), goal_id = bit_id_of(p, p->gx, p->gy);
+#define BIT_SLOT(idv, out) do { out = -1; for (int q_ = 0; q_ < n_k; q_++) if (k_id[q_] == (idv)) { out = q_; break; } } while (0)
+    /* setup_planning (:186-216) */
+    bit_samples_set(&S, goal_id, p->gx, p->gy);
+    k_id[0] = goal_id; k_g[0] = INFINITY; k_f[0] = 0.0; n_k = 1;
+    int s_slot;
+    BIT_SLOT(start_id, s_slot);
+    if (s_slot < 0) { s_slot = n_k; k_id[n_k] = start_id; n_k++; }
+    tv[n_v++] = s_slot;
+    k_g[s_slot] = 0.0; k_f[s_slot] = bit_dist(p, start_id, goal_id);
+    const double c_min = m_hyp(mode, p->sx - p->gx, p->sy - p->gy) / 1.5;
+    const double xc = (p->sx + p->gx) / 2.0, yc = (p->sy + p->gy) / 2.0;
+    if (bit_informed_sample(p, &S, 200, INFINITY, c_min, xc, yc, draws, &used)) rc = -1;
+    double r = INFINITY;
+    int iterations = 0, found_goal = 0, n_batches = 0, n_reset = 0, n_skipped = 0, n_expand = 0;
+    while (rc == 0 && iterations < p->max_iter) {
+        /* setup_sample (:218-234) */
+        if (n_vq == 0 && n_eq == 0) {
+            r = 2.0;
+            n_batches++;
+            if (n_batches >= 2 && iterations == 0) { rc = 2; break; } /* same samples, same edges, all skipped again: the reference never returns */
+            if (iterations != 0) {
+                int m = 100;
+                if (found_goal) { m = 200; S.n = 0; bit_samples_set(&S, goal_id, p->gx, p->gy); }
+                if (bit_informed_sample(p, &S, m, k_g[0], c_min, xc, yc, draws, &used)) { rc = -1; break; }
+            }
+            for (int i = 0; i < n_v; i++) old[tv[i]] = 1;
+            for (int i = 0; i < n_v; i++) {
+                int in = 0;
+                for (int j = 0; j < n_vq; j++) if (vq[j] == tv[i]) { in = 1; break; }
+                if (!in) vq[n_vq++] = tv[i];
+            }
+        }
+        /* expand while best_vertex_queue_value() <= best_edge_queue_value() (:244-246) */
+        for (;;) {
+            double vmin = INFINITY, emax = INFINITY;
+            int vbest = -1;
+            for (int j = 0; j < n_vq; j++) {
+                const double v = k_g[vq[j]] + bit_dist(p, k_id[vq[j]], goal_id);
+                if (vbest < 0 || v < vmin) { vmin = v; vbest = j; }
+            }
+            if (n_vq == 0) vmin = INFINITY;
+            if (n_eq > 0) {
+                emax = -INFINITY;
+                for (int j = 0; j < n_eq; j++) {
+                    const double v = k_g[eq_v[j]] + bit_dist(p, k_id[eq_v[j]], eq_x[j]) + bit_dist(p, eq_x[j], goal_id);
+                    if (v > emax) emax = v;
+                }
+            }
+            if (!(vmin <= emax)) break;
+            if (n_vq == 0) { rc = 1; break; } /* best_in_vertex_queue on an empty list: IndexError */
+            /* expand_vertex (:476-501) */
+            const int vs = vq[vbest];
+            const double vid = k_id[vs];
+            n_expand++;
+            for (int j = vbest; j + 1 < n_vq; j++) vq[j] = vq[j + 1];
+            n_vq--;
+            double cx, cy;
+            bit_coord_of(p, vid, &cx, &cy);
+            const double d_sv = bit_dist(p, start_id, vid);
+            for (int i = 0; i < S.n; i++) {
+                const double dx = S.x[i] - cx, dy = S.y[i] - cy;
+                if (bit_norm2(dx, dy) <= r && S.id[i] != vid) {
+                    const double est = d_sv + bit_dist(p, S.id[i], goal_id) + bit_dist(p, vid, S.id[i]);
+                    if (est < k_g[0]) {
+                        if (n_eq == eqcap) {
+                            eqcap *= 2;
+                            eq_v = (int *)realloc(eq_v, sizeof(int) * eqcap);
+                            eq_x = (double *)realloc(eq_x, sizeof(double) * eqcap);
+                        }
+                        eq_v[n_eq] = vs; eq_x[n_eq] = S.id[i]; n_eq++;
+                    }
+                }
+            }
+            /* add_vertex_to_edge_queue (:503-522) pairs vid with itself: g[vid] + 0 < g[vid] never holds -> no append */
+        }
+        if (rc) break;
+        /* best_in_edge_queue (:469-474): first minimum */
+        int eb = 0;
+        double ebv = INFINITY;
+        for (int j = 0; j < n_eq; j++) {
+            const double v = k_g[eq_v[j]] + bit_dist(p, k_id[eq_v[j]], eq_x[j]) + bit_dist(p, eq_x[j], goal_id);
+            if (j == 0 || v < ebv) { ebv = v; eb = j; }
+        }
+        const int e0s = eq_v[eb];
+        const double e0 = k_id[e0s], e1 = eq_x[eb];
+        for (int j = eb; j + 1 < n_eq; j++) { eq_v[j] = eq_v[j + 1]; eq_x[j] = eq_x[j + 1]; }
+        n_eq--;
+        const double d01 = bit_dist(p, e0, e1), h1 = bit_dist(p, e1, goal_id);
+        const double est_v = k_g[e0s] + d01 + h1;
+        const double est_e = bit_dist(p, start_id, e0) + bit_dist(p, e0, e1) + h1;
+        const double actual = k_g[e0s] + d01;
+        if (est_v < k_g[0] && est_e < k_g[0] && actual < k_g[0]) {
+            double fx, fy, tx, ty;
+            bit_coord_of(p, e0, &fx, &fy);
+            bit_coord_of(p, e1, &tx, &ty);
+            /* connect (:359-374): np.linspace samples, stop before the first colliding one */
+            const long steps = (long)(bit_dist(p, bit_id_of(p, fx, fy), bit_id_of(p, tx, ty)) * 10);
+            const double last_edge = bit_id_of(p, tx, ty);
+            long n_free = 0;
+            double lx = 0.0, ly = 0.0;
+            int none = 0;
+            if (steps > 0) {
+                const double div = (double)(steps - 1), ddx = tx - fx, ddy = ty - fy;
+                const double stx = steps > 1 ? ddx / div : 0.0, sty = steps > 1 ? ddy / div : 0.0;
+                for (long i = 0; i < steps; i++) {
+                    double px, py;
+                    if (steps > 1 && i == steps - 1) { px = tx; py = ty; }
+                    else {
+                        px = (steps > 1 ? (stx == 0.0 ? ((double)i / div) * ddx : (double)i * stx) : 0.0 * ddx) + fx;
+                        py = (steps > 1 ? (sty == 0.0 ? ((double)i / div) * ddy : (double)i * sty) : 0.0 * ddy) + fy;
+                    }
+                    int hit = 0;
+                    for (int o = 0; o < p->n_obs; o++) {
+                        const double ex = obs3[3 * o] - px, ey = obs3[3 * o + 1] - py;
+                        if (ex * ex + ey * ey <= sq_libm(obs3[3 * o + 2])) { hit = 1; break; }
+                    }
+                    if (hit) { if (i == 0) none = 1; break; }
+                    lx = px; ly = py; n_free++;
+                }
+            }
+            if (none || n_free == 0) { n_skipped++; continue; } /* `continue` before iterations += 1 */
+            const double nid = bit_id_of(p, lx, ly);
+            int exists;
+            BIT_SLOT(nid, exists);
+            int in_tree = 0;
+            if (exists >= 0) for (int i = 0; i < n_v; i++) if (tv[i] == exists) { in_tree = 1; break; }
+            if (in_tree) { n_skipped++; continue; }
+            bit_samples_del(&S, nid);
+            if (n_v >= vcap) { rc = -1; break; }
+            int ns = exists;
+            if (ns < 0) { ns = n_k; k_id[n_k] = nid; k_haspar[n_k] = 0; n_k++; }
+            tv[n_v++] = ns;
+            vq[n_vq++] = ns;
+            if (nid == goal_id || e0 == goal_id) found_goal = 1;
+            te_v[n_te] = e0s; te_x[n_te] = ns; n_te++;
+            const double gsc = bit_dist(p, e0, nid);
+            k_g[ns] = gsc + k_g[e0s];
+            k_f[ns] = gsc + bit_dist(p, nid, goal_id);
+            { /* update_graph (:524-552) */
+                int n_open = 0, n_closed = 0;
+                open_[n_open++] = s_slot;
+                while (n_open) {
+                    int bi = 0;
+                    for (int j = 1; j < n_open; j++) if (k_f[open_[j]] < k_f[open_[bi]]) bi = j;
+                    const int cur = open_[bi];
+                    for (int j = bi; j + 1 < n_open; j++) open_[j] = open_[j + 1];
+                    n_open--;
+                    if (k_id[cur] == goal_id) break;
+                    int inc = 0;
+                    for (int j = 0; j < n_closed; j++) if (closed[j] == cur) { inc = 1; break; }
+                    if (!inc) closed[n_closed++] = cur;
+                    for (int c = 0; c < n_te; c++) {
+                        int suc;
+                        if (te_v[c] == cur) suc = te_x[c];
+                        else if (te_x[c] == cur) suc = te_v[c];
+                        else continue;
+                        int isc = 0;
+                        for (int j = 0; j < n_closed; j++) if (closed[j] == suc) { isc = 1; break; }
+                        if (isc) continue;
+                        const double gs = k_g[cur] + bit_dist(p, k_id[cur], k_id[suc]);
+                        int ino = 0;
+                        for (int j = 0; j < n_open; j++) if (open_[j] == suc) { ino = 1; break; }
+                        if (!ino) open_[n_open++] = suc;
+                        else if (gs >= k_g[suc]) continue;
+                        k_g[suc] = gs;
+                        k_f[suc] = gs + bit_dist(p, k_id[suc], goal_id);
+                        if (!k_haspar[suc]) { k_haspar[suc] = 1; par_order[n_par++] = suc; }
+                        k_par[suc] = k_id[cur];
+                    }
+                }
+            }
+            /* remove_queue(lastEdge, bestEdge) (:343-351): the list is mutated while it is iterated */
+            for (int i = 0; i < n_eq; i++) {
+                if (eq_x[i] == nid && k_g[ns] + bit_dist(p, eq_x[i], nid) >= k_g[0]) {
+                    int le;
+                    BIT_SLOT(last_edge, le);
+                    if (le >= 0)
+                        for (int j = 0; j < n_eq; j++)
+                            if (eq_v[j] == le && eq_x[j] == nid) {
+                                for (int t = j; t + 1 < n_eq; t++) { eq_v[t] = eq_v[t + 1]; eq_x[t] = eq_x[t + 1]; }
+                                n_eq--;
+                                break;
+                            }
+                }
+            }
+        } else {
+            n_eq = 0; n_vq = 0; /* "Nothing good" */
+            n_reset++;
+        }
+        iterations++;
+    }
+    /* find_final_path (:333-341) */
+    int plen = 0;
+    if (rc == 0) {
+        double cur = goal_id;
+        int ok = 1;
+        if (plen < pcap) { path[0] = p->gx; path[1] = p->gy; }
+        plen = 1;
+        while (cur != start_id) {
+            double x, y;
+            bit_coord_of(p, cur, &x, &y);
+            if (plen < pcap) { path[2 * plen] = x; path[2 * plen + 1] = y; }
+            plen++;
+            int sl;
+            BIT_SLOT(cur, sl);
+            if (sl < 0 || !k_haspar[sl]) { ok = 0; break; }
+            cur = k_par[sl];
+        }
+        if (!ok) plen = 0;
+        else {
+            if (plen < pcap) { path[2 * plen] = p->sx; path[2 * plen + 1] = p->sy; }
+            plen++;
+            if (plen <= pcap)
+                for (int i = 0, j = plen - 1; i < j; i++, j--) {
+                    double t0 = path[2 * i], t1 = path[2 * i + 1];
+                    path[2 * i] = path[2 * j]; path[2 * i + 1] = path[2 * j + 1];
+                    path[2 * j] = t0; path[2 * j + 1] = t1;
+                }
+            else rc = -1;
+        }
+    }
+    for (int i = 0; i < n_v; i++) { vertices[i] = k_id[tv[i]]; g_vertices[i] = k_g[tv[i]]; }
+    for (int i = 0; i < n_te; i++) { edges[2 * i] = k_id[te_v[i]]; edges[2 * i + 1] = k_id[te_x[i]]; }
+    for (int i = 0; i < n_par; i++) { parent_of[2 * i] = k_id[par_order[i]]; parent_of[2 * i + 1] = k_par[par_order[i]]; }
+    int ns_out = S.n < scap ? S.n : scap, ne_out = n_eq < ecap ? n_eq : ecap;
+    if (S.n > scap || n_eq > ecap) rc = rc ? rc : -1;
+    for (int i = 0; i < ns_out; i++) { sample_ids[i] = S.id[i]; sample_xy[2 * i] = S.x[i]; sample_xy[2 * i + 1] = S.y[i]; }
+    for (int i = 0; i < n_vq; i++) vertex_queue[i] = k_id[vq[i]];
+    for (int i = 0; i < ne_out; i++) { edge_queue[2 * i] = k_id[eq_v[i]]; edge_queue[2 * i + 1] = eq_x[i]; }
+    counts[0] = n_v; counts[1] = n_te; counts[2] = n_par; counts[3] = S.n; counts[4] = n_vq; counts[5] = n_eq; counts[6] = plen;
+    counts[7] = used; counts[8] = n_batches; counts[9] = n_reset; counts[10] = n_skipped; counts[11] = n_expand;
+    *g_goal_out = k_g[0];
+#undef BIT_SLOT
+    free(S.id); free(S.x); free(S.y); free(k_id); free(k_haspar); free(par_order); free(old); free(tv); free(te_v); free(vq);
+    free(eq_v); free(eq_x); free(open_);
+    return rc;
+}

@@ -68,6 +68,9 @@ int launch_tree_exchange_probe(int grid, int iters, long long *out_dev, void *wo
 int launch_closed_loop(const rrtk_closed_loop_params &p, const double *course, const int32_t *n_course, const double *obstacles,
                        const int32_t *obs_offset, const int32_t *n_obs, double *work, double *traj, int32_t *n_traj,
                        int32_t *bits, cudaStream_t s);
+int launch_bitstar(const rrtk_bitstar_params &p, const double *start_goal, const double *rot, const double *obstacles,
+                   const int32_t *n_obs, const double *draws, double *ws_d, int32_t *ws_i, double *path, int32_t *counts,
+                   double *g_goal, int32_t *status, cudaStream_t s);
 int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
                         const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
                         cudaStream_t s);
@@ -127,6 +130,7 @@ int rrtk_sizeof(int which) {
         case 3: return (int)sizeof(rrtk_informed_tree_result);
         case 4: return (int)sizeof(rrtk_dubins_params);
         case 5: return (int)sizeof(rrtk_closed_loop_params);
+        case 6: return (int)sizeof(rrtk_bitstar_params);
         default: return -1;
     }
 }
@@ -344,6 +348,23 @@ int rrtk_closed_loop_dev(const rrtk_closed_loop_params *p, const double *course,
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     if ((uintptr_t)obstacles & 15) return set_error(RRTK_ERR_INVALID, "obstacles must be 16-byte aligned");
     return launch_closed_loop(*p, course, n_course, obstacles, obs_offset, n_obs, work, traj, n_traj, bits, (cudaStream_t)stream);
+}
+
+int rrtk_bitstar_run_dev(const rrtk_bitstar_params *p, const double *start_goal, const double *rot, const double *obstacles,
+                         const int32_t *n_obs, const double *draws, double *ws_d, int32_t *ws_i, double *path, int32_t *counts,
+                         double *g_goal, int32_t *status, void *stream) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->n_queries < 0 || p->max_iter < 0 || p->vertex_cap < 2 || p->sample_cap < 1 || p->edge_cap < 1 || p->path_cap < 2 ||
+        p->obs_stride < 0 || p->n_draws < 0)
+        return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (!(p->num_cells >= 1.0) || !(p->max_rand > p->min_rand)) return set_error(RRTK_ERR_INVALID, "bad randArea / num_cells");
+    if (p->n_queries == 0) return RRTK_OK;
+    if (!start_goal || !rot || !n_obs || !draws || !ws_d || !ws_i || !path || !counts || !g_goal || !status ||
+        (p->obs_stride > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)obstacles & 15) return set_error(RRTK_ERR_INVALID, "obstacles must be 16-byte aligned");
+    return launch_bitstar(*p, start_goal, rot, obstacles, n_obs, draws, ws_d, ws_i, path, counts, g_goal, status,
+                          (cudaStream_t)stream);
 }
 
 int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,

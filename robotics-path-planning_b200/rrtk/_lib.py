@@ -66,6 +66,15 @@ class ClosedLoopParams(C.Structure):
                 ("target_speed", C.c_double), ("yaw_th", C.c_double), ("invalid_travel_ratio", C.c_double)]
 
 
+class BitStarParams(C.Structure):
+    """struct rrtk_bitstar_params (include/rrtk.h)."""
+    _fields_ = [(k, C.c_int32) for k in ("n_queries", "max_iter", "vertex_cap", "sample_cap", "edge_cap", "path_cap",
+                                         "obs_stride", "n_draws")] + \
+               [(k, C.c_double) for k in ("min_rand", "max_rand", "num_cells")]
+
+
+BIT_SAMPLE_OVERFLOW, BIT_EDGE_OVERFLOW, BIT_VERTEX_OVERFLOW, BIT_DRAWS_EXHAUSTED, BIT_INDEX_ERROR, BIT_PATH_OVERFLOW, \
+    BIT_LIVELOCK = 1, 2, 4, 8, 16, 32, 64
 CL_NOT_REACHED, CL_BAD_ANGLE, CL_TOO_LONG, CL_COLLISION, CL_TRAJ_OVERFLOW = 1, 2, 4, 8, 16
 
 _lib = None
@@ -94,6 +103,7 @@ _SIGS = {
     "rrtk_extract_paths_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_VP] * 7),
     "rrtk_path_smoothing_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_closed_loop_dev": (C.c_int, [C.POINTER(ClosedLoopParams), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rrtk_bitstar_run_dev": (C.c_int, [C.POINTER(BitStarParams)] + [_VP] * 12),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),

@@ -47,7 +47,7 @@ def test_every_struct_layout_matches_the_compiled_library():
     from rrtk import _lib
     L = _lib.lib()
     for which, cls in enumerate((_lib.RRTStarParams, _lib.InformedParams, _lib.InformedTreeParams, _lib.InformedTreeResult,
-                                 _lib.DubinsParams, _lib.ClosedLoopParams)):
+                                 _lib.DubinsParams, _lib.ClosedLoopParams, _lib.BitStarParams)):
         assert L.rrtk_sizeof(which) == C.sizeof(cls), cls.__name__
     assert L.rrtk_sizeof(99) == -1
 
