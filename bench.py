@@ -615,6 +615,25 @@ def extras(torch, dev):
             tracking_steps_per_s=steps / (tf["kernel_ms"] / 1e3), s_e2e=t)
     except Exception as e:  # noqa: BLE001
         out["closed_loop_rrtstar"] = dict(error=repr(e))
+    try:   # BIT* (rrt_08), 1024 queries x 200 counted iterations, built-in scenario (rrt_08:644-679)
+        from rrtk import bitstar as BS
+        Q, iters = 1024, 200
+        rng = np.random.default_rng(23)
+        draws = rng.random((Q, 6000))
+        obs1 = [(5, 5, 0.5), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]
+        tm = {}
+        for rep in range(2):
+            t0 = time.perf_counter()
+            res = BS.run_batch([[-1.0, 0.0]] * Q, [[3.0, 8.0]] * Q, [obs1] * Q, [-2, 15], iters, draws, timing=tm)
+            t = time.perf_counter() - t0
+        ok = [r for r in res if r["status"] == 0]
+        out["bitstar"] = dict(queries=Q, iters=iters, kernel_ms=tm["kernel_ms"], iters_per_s=Q * iters / (tm["kernel_ms"] / 1e3),
+                              s_e2e=t, solved=int(sum(r["path_len"] > 0 for r in ok)), failed_status=Q - len(ok),
+                              mean_batches=float(np.mean([r["batches"] for r in ok])),
+                              edges_scored=float(np.mean([r["skipped"] + iters for r in ok])),
+                              mean_expansions=float(np.mean([r["expansions"] for r in ok])))
+    except Exception as e:  # noqa: BLE001
+        out["bitstar"] = dict(error=repr(e))
     try:   # Informed RRT* (rrt_07 semantics), 512 queries x 1000 iterations, built-in scenario
         Q, iters = 512, 1000
         rng = np.random.default_rng(8)
