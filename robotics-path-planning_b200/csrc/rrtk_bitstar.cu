@@ -57,20 +57,30 @@ static __device__ __noinline__ int bit_find(const double *ids, int n, double id,
     return -1;
 }
 
+// Every cost is a function of two ids, so the decoded (quantised) coordinates and the heuristic to the goal are cached next
+// to each id when it enters a container: same operations on the same values, evaluated once.
 struct BitState {
     double *s_id, *s_x, *s_y;            // samples, dict order; deleted entries: id = BIT_DEAD_ID, x = inf
+    double *s_qx, *s_qy, *s_h;           //   quantised coordinates of the id, h(id, goal)
     double *k_id, *k_g, *k_f, *k_par;    // score table: slot 0 = goal, 1 = start, then tree vertices
+    double *k_x, *k_y, *k_h;             //   quantised coordinates, h(id, goal)
     int *k_haspar, *par_order, *tv, *te_v, *te_x, *vq, *eq_v, *open_, *flag;
-    double *eq_x;
+    double *eq_x, *eq_c, *eq_h;          // edge queue: target id, dist(e0, e1), h(e1, goal)
     int n_s, n_k, n_par, n_v, n_te, n_vq, n_eq;
 };
 
-static __device__ __noinline__ void bit_samples_set(BitState &S, int scap, double id, double x, double y, int lane, int *status) {
+static __device__ __noinline__ void bit_samples_set(BitState &S, const BitGrid &g, int scap, double id, double x, double y,
+                                                    int lane, int *status) {
     const int f = bit_find(S.s_id, S.n_s, id, lane);
     if (f >= 0) {
         if (lane == 0) { S.s_x[f] = x; S.s_y[f] = y; }
     } else if (S.n_s < scap) {
-        if (lane == 0) { S.s_id[S.n_s] = id; S.s_x[S.n_s] = x; S.s_y[S.n_s] = y; }
+        if (lane == 0) {
+            double qx, qy;
+            bit_coord_of(g, id, &qx, &qy);
+            S.s_id[S.n_s] = id; S.s_x[S.n_s] = x; S.s_y[S.n_s] = y;
+            S.s_qx[S.n_s] = qx; S.s_qy[S.n_s] = qy; S.s_h[S.n_s] = bit_norm2(qx - S.k_x[0], qy - S.k_y[0]);
+        }
         S.n_s++;
     } else {
         *status |= RRTK_BIT_SAMPLE_OVERFLOW;
@@ -101,16 +111,14 @@ static __device__ __noinline__ bool bit_informed_sample(BitState &S, const rrtk_
             rx = min_rand + (max_rand - min_rand) * u0;
             ry = min_rand + (max_rand - min_rand) * u1;
         }
-        bit_samples_set(S, p.sample_cap, bit_id_of(g, rx, ry), rx, ry, lane, status);
+        bit_samples_set(S, g, p.sample_cap, bit_id_of(g, rx, ry), rx, ry, lane, status);
     }
     return true;
 }
 
 // value of edge j of the queue: g[e0] + dist(e0, e1) + h(e1, goal)
-static __device__ __forceinline__ double bit_edge_value(const BitState &S, const BitGrid &g, double goal_id, int j) {
-    const int v = S.eq_v[j];
-    const double x = S.eq_x[j];
-    return S.k_g[v] + bit_dist(g, S.k_id[v], x) + bit_dist(g, x, goal_id);
+static __device__ __forceinline__ double bit_edge_value(const BitState &S, int j) {
+    return S.k_g[S.eq_v[j]] + S.eq_c[j] + S.eq_h[j];
 }
 
 // remove position `pos` from an int list / (int, double) list of length n, keeping the order
@@ -124,20 +132,21 @@ static __device__ __noinline__ void bit_erase_int(int *a, int n, int pos, int la
         __syncwarp();
     }
 }
-static __device__ __noinline__ void bit_erase_edge(int *a, double *b, int n, int pos, int lane) {
+static __device__ __noinline__ void bit_erase_edge(BitState &S, int pos, int lane) {
+    const int n = S.n_eq;
     for (int b0 = pos; b0 + 1 < n; b0 += 32) {
         const int j = b0 + lane;
         int t = 0;
-        double u = 0.0;
-        if (j + 1 < n) { t = a[j + 1]; u = b[j + 1]; }
+        double u = 0.0, c = 0.0, h = 0.0;
+        if (j + 1 < n) { t = S.eq_v[j + 1]; u = S.eq_x[j + 1]; c = S.eq_c[j + 1]; h = S.eq_h[j + 1]; }
         __syncwarp();
-        if (j + 1 < n) { a[j] = t; b[j] = u; }
+        if (j + 1 < n) { S.eq_v[j] = t; S.eq_x[j] = u; S.eq_c[j] = c; S.eq_h[j] = h; }
         __syncwarp();
     }
 }
 
 // update_graph (:524-552).  flag[slot]: bit 0 = in closedSet, bit 1 = in openSet.
-static __device__ __noinline__ void bit_update_graph(BitState &S, const BitGrid &g, double goal_id, int s_slot, int lane) {
+static __device__ __noinline__ void bit_update_graph(BitState &S, double goal_id, int s_slot, int lane) {
     for (int i = lane; i < S.n_k; i += 32) S.flag[i] = 0;
     __syncwarp();
     int n_open = 1;
@@ -161,7 +170,7 @@ static __device__ __noinline__ void bit_update_graph(BitState &S, const BitGrid 
         if (S.k_id[cur] == goal_id) break;
         if (lane == 0) S.flag[cur] |= 1;
         __syncwarp();
-        const double gcur = S.k_g[cur], idcur = S.k_id[cur];
+        const double gcur = S.k_g[cur], idcur = S.k_id[cur], xcur = S.k_x[cur], ycur = S.k_y[cur];
         for (int b0 = 0; b0 < S.n_te; b0 += 32) {  // adjacency of `cur` in add_edge order
             const int c = b0 + lane;
             int suc = -1;
@@ -173,7 +182,7 @@ static __device__ __noinline__ void bit_update_graph(BitState &S, const BitGrid 
             bool set_ = false, app = false;
             double gs = 0.0;
             if (act) {
-                gs = gcur + bit_dist(g, idcur, S.k_id[suc]);
+                gs = gcur + bit_norm2(S.k_x[suc] - xcur, S.k_y[suc] - ycur);
                 if (!(S.flag[suc] & 2)) { app = true; set_ = true; }
                 else if (!(gs >= S.k_g[suc])) set_ = true;
             }
@@ -185,7 +194,7 @@ static __device__ __noinline__ void bit_update_graph(BitState &S, const BitGrid 
             if (set_) {
                 if (!S.k_haspar[suc]) { S.par_order[S.n_par + __popc(nm & ((1u << lane) - 1u))] = suc; S.k_haspar[suc] = 1; }
                 S.k_g[suc] = gs;
-                S.k_f[suc] = gs + bit_dist(g, S.k_id[suc], goal_id);
+                S.k_f[suc] = gs + S.k_h[suc];
                 S.k_par[suc] = idcur;
             }
             S.n_par += __popc(nm);
@@ -207,7 +216,10 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         double *d = ws_d + (size_t)q * RRTK_BITSTAR_WS_DOUBLES(vcap, scap, ecap);
         S.s_id = d; d += scap; S.s_x = d; d += scap; S.s_y = d; d += scap;
         S.k_id = d; d += kcap; S.k_g = d; d += kcap; S.k_f = d; d += kcap; S.k_par = d; d += kcap;
-        S.eq_x = d;
+        S.eq_x = d; d += ecap;
+        S.s_qx = d; d += scap; S.s_qy = d; d += scap; S.s_h = d; d += scap;
+        S.k_x = d; d += kcap; S.k_y = d; d += kcap; S.k_h = d; d += kcap;
+        S.eq_c = d; d += ecap; S.eq_h = d;
         int *w = ws_i + (size_t)q * RRTK_BITSTAR_WS_INTS(vcap, scap, ecap);
         S.k_haspar = w; w += kcap; S.par_order = w; w += kcap; S.tv = w; w += kcap; S.te_v = w; w += kcap; S.te_x = w; w += kcap;
         S.vq = w; w += kcap; S.open_ = w; w += kcap; S.flag = w; w += kcap; S.eq_v = w;
@@ -226,13 +238,21 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
 
     const double start_id = bit_id_of(g, sx, sy), goal_id = bit_id_of(g, gx, gy);
     // setup_planning (:186-216)
-    bit_samples_set(S, scap, goal_id, gx, gy, lane, &status);
-    if (lane == 0) { S.k_id[0] = goal_id; S.k_g[0] = CUDART_INF; S.k_f[0] = 0.0; }
+    if (lane == 0) {
+        S.k_id[0] = goal_id; S.k_g[0] = CUDART_INF; S.k_f[0] = 0.0;
+        bit_coord_of(g, goal_id, &S.k_x[0], &S.k_y[0]);
+        S.k_h[0] = bit_norm2(S.k_x[0] - S.k_x[0], S.k_y[0] - S.k_y[0]);
+    }
     S.n_k = 1;
     __syncwarp();
+    bit_samples_set(S, g, scap, goal_id, gx, gy, lane, &status);
     int s_slot = start_id == goal_id ? 0 : 1;
     if (lane == 0) {
-        if (s_slot == 1) S.k_id[1] = start_id;
+        if (s_slot == 1) {
+            S.k_id[1] = start_id;
+            bit_coord_of(g, start_id, &S.k_x[1], &S.k_y[1]);
+            S.k_h[1] = bit_norm2(S.k_x[1] - S.k_x[0], S.k_y[1] - S.k_y[0]);
+        }
         S.tv[0] = s_slot;
         S.k_g[s_slot] = 0.0; S.k_f[s_slot] = bit_dist(g, start_id, goal_id);
     }
@@ -251,7 +271,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             if (n_batches >= 2 && iterations == 0) { status |= RRTK_BIT_LIVELOCK; break; }  // the reference never returns
             if (iterations != 0) {
                 int m = 100;
-                if (found_goal) { m = 200; S.n_s = 0; bit_samples_set(S, scap, goal_id, gx, gy, lane, &status); }
+                if (found_goal) { m = 200; S.n_s = 0; bit_samples_set(S, g, scap, goal_id, gx, gy, lane, &status); }
                 ok = bit_informed_sample(S, p, g, m, S.k_g[0], c_min, xc, yc, rot, p.min_rand, p.max_rand, draws, &used, lane, &status);
                 if (!ok || status) break;
             }
@@ -264,7 +284,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             int vbest = 0x7fffffff;
             for (int j = lane; j < S.n_vq; j += 32) {
                 const int v = S.vq[j];
-                const double val = S.k_g[v] + bit_dist(g, S.k_id[v], goal_id);
+                const double val = S.k_g[v] + S.k_h[v];
                 if (vbest == 0x7fffffff || val < vmin) { vmin = val; vbest = j; }
             }
             warp_argmin(vmin, vbest);
@@ -273,7 +293,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             if (S.n_eq > 0) {
                 emax = -CUDART_INF;
                 for (int j = lane; j < S.n_eq; j += 32) {
-                    const double val = bit_edge_value(S, g, goal_id, j);
+                    const double val = bit_edge_value(S, j);
                     emax = val > emax ? val : emax;
                 }
 #pragma unroll
@@ -291,24 +311,24 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             __syncwarp();
             bit_erase_int(S.vq, S.n_vq, vbest, lane);
             S.n_vq--;
-            double cx, cy;
-            bit_coord_of(g, vid, &cx, &cy);
-            const double d_sv = bit_dist(g, start_id, vid), g_goal = S.k_g[0];
+            const double cx = S.k_x[vs], cy = S.k_y[vs];
+            const double d_sv = bit_norm2(cx - S.k_x[s_slot], cy - S.k_y[s_slot]), g_goal = S.k_g[0];
             for (int b0 = 0; b0 < S.n_s; b0 += 32) {
                 const int i = b0 + lane;
                 bool take = false;
-                double sid = 0.0;
+                double sid = 0.0, dvs = 0.0, hs = 0.0;
                 if (i < S.n_s) {
                     sid = S.s_id[i];
                     const double dx = S.s_x[i] - cx, dy = S.s_y[i] - cy;
                     if (bit_norm2(dx, dy) <= r && sid != vid && sid != BIT_DEAD_ID) {
-                        const double est = d_sv + bit_dist(g, sid, goal_id) + bit_dist(g, vid, sid);
-                        take = est < g_goal;
+                        hs = S.s_h[i];
+                        dvs = bit_norm2(S.s_qx[i] - cx, S.s_qy[i] - cy);
+                        take = d_sv + hs + dvs < g_goal;
                     }
                 }
                 const unsigned m = __ballot_sync(FULL, take);
                 const int pos = S.n_eq + __popc(m & ((1u << lane) - 1u));
-                if (take && pos < ecap) { S.eq_v[pos] = vs; S.eq_x[pos] = sid; }
+                if (take && pos < ecap) { S.eq_v[pos] = vs; S.eq_x[pos] = sid; S.eq_c[pos] = dvs; S.eq_h[pos] = hs; }
                 S.n_eq += __popc(m);
             }
             __syncwarp();
@@ -319,18 +339,18 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         double ebv = CUDART_INF;
         int eb = 0x7fffffff;
         for (int j = lane; j < S.n_eq; j += 32) {
-            const double val = bit_edge_value(S, g, goal_id, j);
+            const double val = bit_edge_value(S, j);
             if (eb == 0x7fffffff || val < ebv) { ebv = val; eb = j; }
         }
         warp_argmin(ebv, eb);
         const int e0s = S.eq_v[eb];
         const double e0 = S.k_id[e0s], e1 = S.eq_x[eb];
+        const double d01 = S.eq_c[eb], h1 = S.eq_h[eb];
         __syncwarp();
-        bit_erase_edge(S.eq_v, S.eq_x, S.n_eq, eb, lane);
+        bit_erase_edge(S, eb, lane);
         S.n_eq--;
-        const double d01 = bit_dist(g, e0, e1), h1 = bit_dist(g, e1, goal_id);
         const double est_v = S.k_g[e0s] + d01 + h1;
-        const double est_e = bit_dist(g, start_id, e0) + bit_dist(g, e0, e1) + h1;
+        const double est_e = bit_norm2(S.k_x[e0s] - S.k_x[s_slot], S.k_y[e0s] - S.k_y[s_slot]) + d01 + h1;
         const double actual = S.k_g[e0s] + d01, gg = S.k_g[0];
         if (est_v < gg && est_e < gg && actual < gg) {
             double fx, fy, tx, ty;
@@ -390,7 +410,11 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             int ns = exists;
             if (ns < 0) {
                 ns = S.n_k;
-                if (lane == 0) { S.k_id[ns] = nid; S.k_haspar[ns] = 0; }
+                if (lane == 0) {
+                    S.k_id[ns] = nid; S.k_haspar[ns] = 0;
+                    bit_coord_of(g, nid, &S.k_x[ns], &S.k_y[ns]);
+                    S.k_h[ns] = bit_norm2(S.k_x[ns] - S.k_x[0], S.k_y[ns] - S.k_y[0]);
+                }
                 S.n_k++;
             }
             const double gsc = bit_dist(g, e0, nid);
@@ -403,7 +427,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             S.n_v++; S.n_vq++; S.n_te++;
             if (nid == goal_id || e0 == goal_id) found_goal = 1;
             __syncwarp();
-            bit_update_graph(S, g, goal_id, s_slot, lane);
+            bit_update_graph(S, goal_id, s_slot, lane);
             __syncwarp();
             // remove_queue (:343-351).  Edges of the queue are unique (a vertex is expanded once per queue lifetime), so
             // the loop over the mutating list reduces to: if g[nid] (+ 0) >= g[goal], drop (lastEdge, nid) when present
@@ -416,7 +440,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
                         const unsigned m = __ballot_sync(FULL, j < S.n_eq && S.eq_v[j] == le && S.eq_x[j] == nid);
                         if (m) pos = b0 + __ffs(m) - 1;
                     }
-                    if (pos >= 0) { bit_erase_edge(S.eq_v, S.eq_x, S.n_eq, pos, lane); S.n_eq--; }
+                    if (pos >= 0) { bit_erase_edge(S, pos, lane); S.n_eq--; }
                 }
             }
         } else {  // "Nothing good"
