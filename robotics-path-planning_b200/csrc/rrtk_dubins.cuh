@@ -119,8 +119,8 @@ static __device__ __forceinline__ void interp(double length, int type, double ka
 
 
 struct DubEdge {
-    double ex, ey, eyaw;  // last course point (the node pose steer returns, rrt_05:1469-1471)
-    int npts;             // len(px): steer returns None when <= 1
+    double ex, ey, eyaw;  // last course point (the node pose steer returns, rrt_05:1469-1471); free edges only
+    int npts;             // len(px): steer returns None when <= 1 (for a blocked edge only "<= 1 or not" is kept)
     bool free_;           // check_collision over the course points (rrt_05:1625-1638)
 };
 
@@ -168,7 +168,7 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
     };
     emit(lx, ly);
 #pragma unroll 1
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 3 && !hit; k++) {
         const double length = len[k];
         if (length == 0.0) continue;
         const int type = seg_type(bi, k);
@@ -182,13 +182,111 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
             double x, y, yaw;
             interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
             emit(x, y);
+            if (hit) break;
             cur += step;
         }
+        if (hit) break;
         interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
         emit(lx, ly);
     }
+    if (hit) {
+        // blocked: the callers only ask whether steer returned a node at all (len(px) > 1, i.e. some segment is non-zero);
+        // the rest of the course, its point count and its end pose are never read for a blocked edge
+        e.npts = (len[0] != 0.0 || len[1] != 0.0 || len[2] != 0.0) ? 2 : 1;
+        return e;
+    }
     e.npts = np;
     e.free_ = !hit;
+    e.ex = fma(ly, s2, lx * c2) + s_x;
+    e.ey = fma(ly, c2, lx * -s2) + s_y;
+    e.eyaw = angle_mod_pi(lyaw + s_yaw);
+    return e;
+}
+
+// The same edge evaluated by the WHOLE warp (uniform arguments, uniform result): the six words on six lanes, the interior
+// points of each segment spread over the lanes (each lane reaches its first distance by the reference's repeated
+// `cur += step`), as dubins_steer_kernel does.  Used where the planner has one edge to evaluate (first steer, re-planned
+// rewire edges).
+static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, double s_yaw, double g_x, double g_y,
+                                                        double g_yaw, double kappa, double step, const double4 *obs,
+                                                        int n_obs, int lane) {
+    DubEdge e;
+    e.ex = e.ey = e.eyaw = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    double c, s;
+    rot2d(s_yaw, &c, &s);
+    const double vx = g_x - s_x, vy = g_y - s_y;
+    const double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s);
+    const double lgyaw = g_yaw - s_yaw;
+    const double d = crm_hypot(lgx, lgy) * kappa;
+    const double theta = mod2pi(crm_atan2(lgy, lgx));
+    const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
+    double w[3] = {0.0, 0.0, 0.0};
+    double cost = CUDART_INF;
+    int bi = 0x7fffffff;
+    if (lane < 6 && dubins_word(lane, alpha, beta, d, w)) {
+        cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+        bi = lane;
+    }
+    warp_argmin(cost, bi);   // first minimum in _PATH_TYPE_MAP order, like `best > cost` over k = 0..5
+    if (bi == 0x7fffffff) return e;
+    double len[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, w[k], bi);
+    double c2, s2;
+    rot2d(-s_yaw, &c2, &s2);
+    bool hit = false;
+    auto test = [&](double px, double py) {
+        const double wx = fma(py, s2, px * c2) + s_x;
+        const double wy = fma(py, c2, px * -s2) + s_y;
+        for (int o = 0; o < n_obs && !hit; o++) {
+            const double4 ob = obs[o];
+            const double dx = ob.x - wx, dy = ob.y - wy;
+            if (dx * dx + dy * dy <= ob.w) hit = true;
+        }
+    };
+    double lx = 0.0, ly = 0.0, lyaw = 0.0;
+    int np = 1;
+    if (lane == 0) test(lx, ly);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const double length = len[k];
+        if (length == 0.0) continue;
+        const int type = seg_type(bi, k);
+        const double ox = lx, oy = ly, oyaw = lyaw;
+        double so, co, sm, cm;
+        sincos_cr(oyaw, &so, &co);
+        sincos_cr(-oyaw, &sm, &cm);
+        int cnt = 0;
+        {
+            double cur = step;
+            while (fabs(cur + step) <= fabs(length)) { cnt++; cur += step; }
+        }
+        double cur = step;
+        for (int t = 0; t < lane; t++) cur += step;
+#pragma unroll 1
+        for (int j = lane; j < cnt; j += 32) {
+            double x, y, yaw;
+            interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
+            test(x, y);
+#pragma unroll 1
+            for (int t = 0; t < 32; t++) cur += step;
+        }
+        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+        if (lane == 0) test(lx, ly);
+        np += cnt + 1;
+        if (__any_sync(FULL, hit)) {   // blocked: see dubins_edge_lane
+            e.npts = 2;
+            return e;
+        }
+    }
+    if (__any_sync(FULL, hit)) {       // only the origin can have been tested here
+        e.npts = (len[0] != 0.0 || len[1] != 0.0 || len[2] != 0.0) ? 2 : 1;
+        return e;
+    }
+    e.npts = np;
+    e.free_ = true;
     e.ex = fma(ly, s2, lx * c2) + s_x;
     e.ey = fma(ly, c2, lx * -s2) + s_y;
     e.eyaw = angle_mod_pi(lyaw + s_yaw);

@@ -25,7 +25,8 @@ __host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap
     (void)node_cap;
     // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | frontier length of propagate_lists
     size_t b = (size_t)near_cap * (4 + 4 + 8 + 24) + 16;
-    return (b + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    return b + ((sizeof(RsWarp) + 15) & ~(size_t)15);   // + the 48 candidate words of a warp-cooperative Reeds-Shepp edge
 }
 
 // One steering edge by one lane, for either local planner.  STEER = 0: Dubins (rrt_05, steer returns None when
@@ -43,6 +44,21 @@ __device__ __forceinline__ PEdge plan_edge(double sx, double sy, double syaw, do
         r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = 0.0; r.valid = e.npts > 1; r.free_ = e.free_;
     } else {
         const RsEdge e = rs_edge_lane(sx, sy, syaw, gx, gy, gyaw, kappa, step, obs, n_obs);
+        r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = e.lsum; r.valid = e.npts > 0; r.free_ = e.free_;
+    }
+    return r;
+}
+
+// The same edge by the WHOLE warp (uniform arguments and result): used where an iteration has a single edge to evaluate.
+template <int STEER>
+__device__ __forceinline__ PEdge plan_edge_warp(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                double kappa, double step, const double4 *obs, int n_obs, int lane, RsWarp &W) {
+    PEdge r;
+    if (STEER == 0) {
+        const DubEdge e = dubins_edge_warp(sx, sy, syaw, gx, gy, gyaw, kappa, step, obs, n_obs, lane);
+        r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = 0.0; r.valid = e.npts > 1; r.free_ = e.free_;
+    } else {
+        const RsEdge e = rs_edge_warp(sx, sy, syaw, gx, gy, gyaw, kappa, step, obs, n_obs, lane, W);
         r.ex = e.ex; r.ey = e.ey; r.eyaw = e.eyaw; r.lsum = e.lsum; r.valid = e.npts > 0; r.free_ = e.free_;
     }
     return r;
@@ -100,6 +116,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
     int *near_idx = reinterpret_cast<int *>(s_end + 3 * near_cap);
     int *flags = near_idx + near_cap;
     int *qtail = flags + near_cap;
+    RsWarp &rsw = *reinterpret_cast<RsWarp *>(base + dub_warp_smem_bytes(near_cap, p.node_cap) - ((sizeof(RsWarp) + 15) & ~(size_t)15));
     const double INF = CUDART_INF;
     const double kappa = p.curvature, step = p.step_size;
 
@@ -159,7 +176,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
             const int ni = bi;
             const double2 from = xy[ni];
             const double fyaw = yaw[ni];
-            const PEdge e0 = plan_edge<STEER>(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs);  // uniform
+            const PEdge e0 = plan_edge_warp<STEER>(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs, lane, rsw);
             bool truthy = e0.valid;
             if (truthy && e0.free_) {
                 const double nx = e0.ex, ny = e0.ey, nyaw = e0.eyaw;
@@ -247,7 +264,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         const double2 a = xy[i];
                         const double ayaw = yaw[i];
                         if (fl & 4) {  // node i was re-parented (moved) earlier in this call: redo its edge
-                            const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
+                            const PEdge e = plan_edge_warp<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs, lane, rsw);
                             fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
                             ecost = mc + (STEER == 2 ? e.lsum : crm_hypot(a.x - cx, a.y - cy));
                             ex = e.ex; ey = e.ey; eyw = e.eyaw;
@@ -273,7 +290,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     if (STEER >= 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
                         const double2 a = xy[newi];
                         const double ayaw = yaw[newi];
-                        const PEdge eg = plan_edge<STEER>(a.x, a.y, ayaw, gx, gy, gyaw, kappa, step, obs, n_obs);  // uniform
+                        const PEdge eg = plan_edge_warp<STEER>(a.x, a.y, ayaw, gx, gy, gyaw, kappa, step, obs, n_obs, lane, rsw);
                         if (eg.valid && eg.free_) {
                             if (lane == 0) {
                                 efrom[3 * n] = a.x; efrom[3 * n + 1] = a.y; efrom[3 * n + 2] = ayaw;

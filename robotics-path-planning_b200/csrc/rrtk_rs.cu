@@ -22,11 +22,6 @@ namespace rrtk {
 
 constexpr int RS_WARPS = 4;
 
-struct RsWarp {
-    double d[48][5];
-    int ok[48];
-};
-
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restrict__ from3, const double *__restrict__ to3,
                 const int32_t *__restrict__ obs_set, const double4 *__restrict__ obstacles, int obs_stride,

@@ -236,7 +236,6 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         double lx = 0.0, ly = 0.0, lyaw = 0.0;
 #pragma unroll 1
         for (long long j = 0; j <= na; j++) {
-            if (hit && j < na) continue;   // verdict known: only the segment end (the next origin / the end pose) is needed
             const double dist = j < na ? 0.0 + (double)j * dd : length;
             rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
             const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
@@ -245,12 +244,121 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
                 const double ex = ob.x - wx, ey = ob.y - wy;
                 if (ex * ex + ey * ey <= ob.w) hit = true;
             }
+            if (hit) {   // blocked: the callers read neither the end pose nor the length of a blocked edge, only that a course exists
+                e.npts = 1;
+                return e;
+            }
         }
         ox = lx; oy = ly; oyaw = lyaw;
         np += (int)(na + 1);
     }
     e.npts = np;
     e.free_ = !hit;
+    e.lsum = lsum;
+    e.ex = cm0 * ox + sm0 * oy + sx;
+    e.ey = -sm0 * ox + cm0 * oy + sy;
+    e.eyaw = angle_mod_pi(oyaw + syaw);
+    return e;
+}
+
+// Shared-memory scratch of a warp-cooperative Reeds-Shepp evaluation: the 48 candidate words.
+struct RsWarp {
+    double d[48][5];
+    int ok[48];
+};
+
+// The same edge evaluated by the WHOLE warp (uniform arguments, uniform result), as rs_steer_kernel does: the 48 words one
+// per lane in two rounds, set_path's insertion logic uniformly in the reference's order, the np.arange points of each
+// segment spread over the lanes.
+static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                   double maxc, double step_size, const double4 *obs, int n_obs, int lane,
+                                                   RsWarp &W) {
+    RsEdge e;
+    e.ex = e.ey = e.eyaw = e.lsum = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    const double step = step_size * maxc;
+    const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
+    double s0, c0;
+    sincos_cr(syaw, &s0, &c0);
+    const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;
+    __syncwarp();
+#pragma unroll 1
+    for (int cand = lane; cand < 48; cand += 32) {
+        const int f = cand >> 2, k = cand & 3;
+        double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const bool ok = rs_word(f, (k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, d);
+#pragma unroll
+        for (int i = 0; i < 5; i++) W.d[cand][i] = d[i];
+        W.ok[cand] = ok ? 1 : 0;
+    }
+    __syncwarp();
+    double ins_L[48], best_L = CUDART_INF;
+    int ins_code[48], n_ins = 0, best = -1;
+#pragma unroll 1
+    for (int cand = 0; cand < 48; cand++) {
+        if (!W.ok[cand]) continue;
+        const int f = cand >> 2, k = cand & 3, n = RS_N[f];
+        double tot = 0.0;
+        for (int i = 0; i < n; i++) tot += fabs(W.d[cand][i]);
+        for (int i = 0; i < n; i++) {
+            const double a = fabs(W.d[cand][i]);
+            if (0.1 * tot < a && a < step) return e;   // "Step size too large for Reeds-Shepp paths." -> no path at all
+        }
+        int code = n;
+        for (int i = 0; i < n; i++) {
+            const int t0 = RS_T[f][i];
+            code = code * 3 + ((k >= 2 && t0 != 1) ? 2 - t0 : t0);
+        }
+        bool same = false;
+        for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - tot) <= step;
+        if (same || tot <= step) continue;
+        ins_code[n_ins] = code; ins_L[n_ins] = tot; n_ins++;
+        if (fabs(tot / maxc) < best_L) { best_L = fabs(tot / maxc); best = cand; }
+    }
+    if (best < 0) return e;
+    const int f = best >> 2, k = best & 3, n = RS_N[f];
+    double sm0, cm0;
+    sincos_cr(-syaw, &sm0, &cm0);
+    bool hit = false;
+    int np = 0;
+    double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        double length = W.d[best][i];
+        if (k == 1 || k == 3) length = -length;   // timeflip
+        lsum = lsum + fabs(length / maxc);
+        const int t0 = RS_T[f][i];
+        const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;
+        const double dd = length >= 0.0 ? step : -step;
+        long long na = length != 0.0 ? (long long)ceil((length - 0.0) / dd) : 0;
+        if (na < 0) na = 0;
+        double so, co, sm, cm;
+        sincos_cr(oyaw, &so, &co);
+        sincos_cr(-oyaw, &sm, &cm);
+#pragma unroll 1
+        for (long long j = lane; j <= na; j += 32) {
+            const double dist = j < na ? 0.0 + (double)j * dd : length;
+            double lx, ly, lyaw;
+            rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+            const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
+            for (int o = 0; o < n_obs && !hit; o++) {
+                const double4 ob = obs[o];
+                const double ex = ob.x - wx, ey = ob.y - wy;
+                if (ex * ex + ey * ey <= ob.w) hit = true;
+            }
+        }
+        if (__any_sync(FULL, hit)) {   // blocked: see rs_edge_lane
+            e.npts = 1;
+            return e;
+        }
+        double lx, ly, lyaw;   // the segment's last point is the next origin (uniform)
+        rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+        ox = lx; oy = ly; oyaw = lyaw;
+        np += (int)(na + 1);
+    }
+    e.npts = np;
+    e.free_ = true;
     e.lsum = lsum;
     e.ex = cm0 * ox + sm0 * oy + sx;
     e.ey = -sm0 * ox + cm0 * oy + sy;
