@@ -118,6 +118,37 @@ static __device__ __forceinline__ void interp(double length, int type, double ka
 }
 
 
+// ---- collision pre-test of the interior course points (the planners' edge evaluators only) ----
+// A blocked / free verdict needs a course point only to within the margin by which it clears the circles.  The arc point
+// is first taken with libdevice's sincos (<= 2 ulp; the same formula otherwise), which places it within ~1e-13 of the
+// correctly rounded one for coordinates below 1e4; the verdict is accepted when every circle is cleared (or one is
+// entered) by more than a band of 1e-9 * (1 + R^2) in squared distance, and the point is re-evaluated with the correctly
+// rounded functions otherwise.  Segment end points (the next origin, the end pose) are always exact.
+static __device__ __forceinline__ void arc_fast(double length, int type, double kappa, double ox, double oy, double sm,
+                                                double cm, double *x, double *y) {
+    double sl, cl;
+    sincos(length, &sl, &cl);
+    const double ldx = sl / kappa;
+    const double ldy = type == 0 ? (1.0 - cl) / kappa : (1.0 - cl) / -kappa;
+    *x = ox + (cm * ldx + sm * ldy);
+    *y = oy + (-sm * ldx + cm * ldy);
+}
+// 1: inside some circle beyond the band, 0: outside every circle beyond the band, -1: too close to call
+static __device__ __forceinline__ int circle_verdict(double wx, double wy, const double4 *obs, int n_obs) {
+    int v = 0;
+    for (int o = 0; o < n_obs; o++) {
+        const double4 ob = obs[o];
+        const double dx = ob.x - wx, dy = ob.y - wy;
+        const double d2 = dx * dx + dy * dy, band = 1e-9 * (1.0 + ob.w);
+        if (d2 <= ob.w - band) return 1;
+        if (d2 <= ob.w + band) v = -1;
+    }
+    return v;
+}
+static __device__ __forceinline__ bool prefilter_ok(double s_x, double s_y, double g_x, double g_y, double kappa) {
+    return fabs(s_x) < 1e4 && fabs(s_y) < 1e4 && fabs(g_x) < 1e4 && fabs(g_y) < 1e4 && kappa > 1e-3;
+}
+
 struct DubEdge {
     double ex, ey, eyaw;  // last course point (the node pose steer returns, rrt_05:1469-1471); free edges only
     int npts;             // len(px): steer returns None when <= 1 (for a blocked edge only "<= 1 or not" is kept)
@@ -153,6 +184,7 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
     if (bi < 0) return e;
     double c2, s2;
     rot2d(-s_yaw, &c2, &s2);
+    const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
     bool hit = false;
     double lx = 0.0, ly = 0.0, lyaw = 0.0;
     int np = 0;
@@ -179,9 +211,20 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
         double cur = step;
 #pragma unroll 1
         while (fabs(cur + step) <= fabs(length)) {
-            double x, y, yaw;
-            interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
-            emit(x, y);
+            int v = -1;
+            if (filt && type != 1) {
+                double x, y;
+                arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
+                v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
+            }
+            if (v < 0) {
+                double x, y, yaw;
+                interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
+                emit(x, y);
+            } else {
+                hit = v == 1;
+                np++;
+            }
             if (hit) break;
             cur += step;
         }
@@ -236,6 +279,7 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, w[k], bi);
     double c2, s2;
     rot2d(-s_yaw, &c2, &s2);
+    const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
     bool hit = false;
     auto test = [&](double px, double py) {
         const double wx = fma(py, s2, px * c2) + s_x;
@@ -267,9 +311,19 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
         for (int t = 0; t < lane; t++) cur += step;
 #pragma unroll 1
         for (int j = lane; j < cnt; j += 32) {
-            double x, y, yaw;
-            interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
-            test(x, y);
+            int v = -1;
+            if (filt && type != 1) {
+                double x, y;
+                arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
+                v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
+            }
+            if (v < 0) {
+                double x, y, yaw;
+                interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
+                test(x, y);
+            } else if (v == 1) {
+                hit = true;
+            }
 #pragma unroll 1
             for (int t = 0; t < 32; t++) cur += step;
         }
