@@ -38,11 +38,18 @@ static __device__ __forceinline__ void rot2d(double angle, double *c, double *s)
 }
 
 // word k in _PATH_TYPE_MAP order; false = infeasible
-static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, double *w) {
-    double sa, ca, sb, cb;
-    sincos_cr(alpha, &sa, &ca);
-    sincos_cr(beta, &sb, &cb);
-    const double cab = crm_cos(alpha - beta);
+// sin / cos of alpha and beta and cos(alpha - beta): every word function of the reference recomputes them (rrt_05:1125-1198);
+// they depend on the edge only, so they are evaluated once per edge
+struct DubTrig { double sa, ca, sb, cb, cab; };
+static __device__ __forceinline__ DubTrig dubins_trig(double alpha, double beta) {
+    DubTrig t;
+    sincos_cr(alpha, &t.sa, &t.ca);
+    sincos_cr(beta, &t.sb, &t.cb);
+    t.cab = crm_cos(alpha - beta);
+    return t;
+}
+static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, const DubTrig &t, double *w) {
+    const double sa = t.sa, ca = t.ca, sb = t.sb, cb = t.cb, cab = t.cab;
     const double d2 = d * d;
     double p2, tmp, d1;
     switch (k) {
@@ -172,12 +179,13 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
     const double d = crm_hypot(lgx, lgy) * kappa;
     const double theta = mod2pi(crm_atan2(lgy, lgx));
     const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
+    const DubTrig trig = dubins_trig(alpha, beta);
     double len[3] = {0.0, 0.0, 0.0}, best = CUDART_INF;
     int bi = -1;
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
         double w[3];
-        if (!dubins_word(k, alpha, beta, d, w)) continue;
+        if (!dubins_word(k, alpha, beta, d, trig, w)) continue;
         double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
         if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
     }
@@ -268,7 +276,8 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     double w[3] = {0.0, 0.0, 0.0};
     double cost = CUDART_INF;
     int bi = 0x7fffffff;
-    if (lane < 6 && dubins_word(lane, alpha, beta, d, w)) {
+    const DubTrig trig = dubins_trig(alpha, beta);
+    if (lane < 6 && dubins_word(lane, alpha, beta, d, trig, w)) {
         cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
         bi = lane;
     }
