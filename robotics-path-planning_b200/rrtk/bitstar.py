@@ -118,18 +118,33 @@ class BITStar:
         self.result = None
 
     def plan(self, animation=True, draws=None):
-        if draws is None:
-            # `random.random()` draw for draw like the reference (uniform(a, b) = a + (b - a) * random()); every batch
-            # consumes at most 402 draws and a batch starts at most once per counted iteration
-            n = self.n_draws if self.n_draws is not None else 402 * (min(int(self.max_iIter), 60) + 2)
+        """`draws`: the unit draws to consume instead of Python's `random` (tests).  Without it the stream is taken from
+        `random.random()` draw for draw like the reference (`uniform(a, b)` = a + (b - a) * random()); a run that needs
+        more draws, samples or queue slots than provisioned is repeated from the start with more (same prefix of draws,
+        so the same result)."""
+        own = draws is None
+        if own:
+            n = self.n_draws if self.n_draws is not None else 402 * 8
             draws = [random.random() for _ in range(n)]
-        r = run_batch([self.start], [self.goal], [list(self.obstacleList)], [self.min_rand, self.max_rand], self.max_iIter,
-                      np.asarray(draws, dtype=np.float64)[None])[0]
+        draws = list(np.asarray(draws, dtype=np.float64))
+        sample_cap, edge_cap = 2048, 16384
+        while True:
+            r = run_batch([self.start], [self.goal], [list(self.obstacleList)], [self.min_rand, self.max_rand], self.max_iIter,
+                          np.asarray(draws, dtype=np.float64)[None], sample_cap=sample_cap, edge_cap=edge_cap)[0]
+            st = r["status"]
+            if own and st & _lib.BIT_DRAWS_EXHAUSTED:
+                draws += [random.random() for _ in range(len(draws))]
+            elif st & _lib.BIT_SAMPLE_OVERFLOW and sample_cap < (1 << 20):
+                sample_cap *= 4
+            elif st & _lib.BIT_EDGE_OVERFLOW and edge_cap < (1 << 24):
+                edge_cap *= 4
+            else:
+                break
         self.result = r
-        if r["status"] & _lib.BIT_INDEX_ERROR:
+        if st & _lib.BIT_INDEX_ERROR:
             raise IndexError("list index out of range")          # what the reference raises (best_in_vertex_queue :465)
-        if r["status"] & _lib.BIT_LIVELOCK:
+        if st & _lib.BIT_LIVELOCK:
             raise _lib.RrtkError("every edge of the first batch is blocked: the reference planner never returns here")
-        if r["status"]:
-            raise _lib.RrtkError(f"BIT* capacity exceeded (status {r['status']})")
+        if st:
+            raise _lib.RrtkError(f"BIT* run failed (status {st}: draws exhausted = 8, capacity = 1 / 2 / 4 / 32)")
         return [[float(x), float(y)] for x, y in r["path"]]
