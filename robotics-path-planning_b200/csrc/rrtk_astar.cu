@@ -18,6 +18,8 @@
 
 namespace rrtk {
 
+constexpr unsigned FULL = 0xffffffffu;
+
 __device__ __forceinline__ long long at_abs(long long v) { return v < 0 ? -v : v; }
 __device__ __forceinline__ long long at_orig(int gi, int gj, int i, int j) { return at_abs((long long)j - gj) + at_abs((long long)i - gi); }
 // one in-place update step of arm02:226-231 given the (possibly updated) row-0 and column-0 values it reads
@@ -45,35 +47,49 @@ __global__ void astar_heuristic_kernel(int M, int n_queries, const int32_t *__re
     heur[t] = (int32_t)heuristic_cell(M, start_goal[4 * q + 2], start_goal[4 * q + 3], (int)(c / M), (int)(c % M));
 }
 
-__device__ __forceinline__ void heap_push(unsigned long long *heap, int &n, unsigned long long key) {
+// Frontier = a 32-ary min-heap of (heuristic << 32 | flat index) keys in global memory, one WARP per query: a node's 32
+// children are one coalesced 256-byte load and their minimum one pair of warp reductions, so a pop walks log32(n) <= 4
+// levels (a binary heap walked by one thread took ~18 dependent L2 round trips per pop).  Keys are unique (the index is
+// part of the key), so any correct priority queue pops the reference's np.argmin order.
+__device__ __forceinline__ void heap_push(unsigned long long *heap, int &n, unsigned long long key, int lane) {
     int k = n++;
     while (k > 0) {
-        const int p = (k - 1) >> 1;
+        const int p = (k - 1) >> 5;
         const unsigned long long pk = heap[p];
         if (pk <= key) break;
-        heap[k] = pk; k = p;
+        if (lane == 0) heap[k] = pk;
+        k = p;
     }
-    heap[k] = key;
+    if (lane == 0) heap[k] = key;
+    __syncwarp();
 }
-__device__ __forceinline__ void heap_pop(unsigned long long *heap, int &n) {
+__device__ __forceinline__ void heap_pop(unsigned long long *heap, int &n, int lane) {
     const unsigned long long key = heap[--n];
     int k = 0;
     for (;;) {
-        int c = 2 * k + 1;
-        if (c >= n) break;
-        unsigned long long ck = heap[c];
-        if (c + 1 < n) { const unsigned long long c2 = heap[c + 1]; if (c2 < ck) { ck = c2; c++; } }
-        if (ck >= key) break;
-        heap[k] = ck; k = c;
+        const int c = 32 * k + 1 + lane;
+        const unsigned long long ck = c < n ? heap[c] : ~0ull;
+        const unsigned hi = (unsigned)(ck >> 32), lo = (unsigned)ck;
+        const unsigned mhi = __reduce_min_sync(FULL, hi);
+        const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+        const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+        if (mk >= key) break;                      // also when there are no children (all ~0)
+        const int src = __ffs(__ballot_sync(FULL, ck == mk)) - 1;
+        if (lane == 0) heap[k] = mk;
+        k = 32 * k + 1 + src;
     }
-    if (n > 0) heap[k] = key;
+    if (n > 0 && lane == 0) heap[k] = key;
+    __syncwarp();
 }
 
-// one thread per query
-__global__ void astar_torus_kernel(int M, int n_queries, const int32_t *__restrict__ start_goal, const int32_t *__restrict__ heur,
-                                   uint8_t *grids, int32_t *parents, unsigned long long *heaps, int32_t *routes,
-                                   int route_cap, int32_t *route_len, int32_t *expanded) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per query
+constexpr int ASTAR_WARPS = 4;
+__global__ void __launch_bounds__(ASTAR_WARPS * 32)
+astar_torus_kernel(int M, int n_queries, const int32_t *__restrict__ start_goal, const int32_t *__restrict__ heur,
+                   uint8_t *grids, int32_t *parents, unsigned long long *heaps, int32_t *routes,
+                   int route_cap, int32_t *route_len, int32_t *expanded) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * ASTAR_WARPS + (threadIdx.x >> 5);
     if (q >= n_queries) return;
     const size_t cells = (size_t)M * M;
     uint8_t *grid = grids + q * cells;
@@ -84,44 +100,65 @@ __global__ void astar_torus_kernel(int M, int n_queries, const int32_t *__restri
     const int s = start_goal[4 * q] * M + start_goal[4 * q + 1], g = start_goal[4 * q + 2] * M + start_goal[4 * q + 3];
     int nheap = 0, n_exp = 0;
     bool found = false;
-    grid[s] = 4; grid[g] = 5;
-    heap_push(heap, nheap, ((unsigned long long)(unsigned)h[s] << 32) | (unsigned)s);
+    if (lane == 0) { grid[s] = 4; grid[g] = 5; }
+    __syncwarp();
+    heap_push(heap, nheap, ((unsigned long long)(unsigned)h[s] << 32) | (unsigned)s, lane);
     for (;;) {
-        grid[s] = 4; grid[g] = 5;                       // arm02:140-141
+        if (lane == 0) { grid[s] = 4; grid[g] = 5; }     // arm02:140-141
+        __syncwarp();
         if (nheap == 0) break;                           // min is inf: no route
         const int cur = (int)(heap[0] & 0xffffffffull);  // np.argmin: smallest (heuristic, row-major index)
         if (cur == g) { found = true; break; }
-        heap_pop(heap, nheap);
-        grid[cur] = 2;
+        heap_pop(heap, nheap, lane);
         n_exp++;
         const int i = cur / M, j = cur - i * M;
-        const int nb[4] = {(i - 1 >= 0 ? i - 1 : M - 1) * M + j, (i + 1 < M ? i + 1 : 0) * M + j,
-                           i * M + (j - 1 >= 0 ? j - 1 : M - 1), i * M + (j + 1 < M ? j + 1 : 0)};   // find_neighbors :187-209
+        // find_neighbors (:187-209): up, down, left, right on the torus; lanes 0..3 read one neighbour each
+        int nb = 0;
+        if (lane == 0) nb = (i - 1 >= 0 ? i - 1 : M - 1) * M + j;
+        else if (lane == 1) nb = (i + 1 < M ? i + 1 : 0) * M + j;
+        else if (lane == 2) nb = i * M + (j - 1 >= 0 ? j - 1 : M - 1);
+        else if (lane == 3) nb = i * M + (j + 1 < M ? j + 1 : 0);
+        if (lane == 0) grid[cur] = 2;
+        __syncwarp();
+        uint8_t v = 1;
+        int hv = 0;
+        if (lane < 4) { v = grid[nb]; hv = h[nb]; }
+        // on a 1- or 2-wide torus two of the four neighbours coincide: the first occurrence enters the frontier, the later one
+        // then sees value 3 -- resolve duplicates in the reference's order
+        bool take = lane < 4 && (v == 0 || v == 5);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int onb = __shfl_sync(FULL, nb, k);
+            const bool otake = __shfl_sync(FULL, (int)take, k) != 0;
+            if (lane > k && lane < 4 && otake && onb == nb) take = false;
+        }
+        if (take) { parent[nb] = cur; grid[nb] = 3; }
+        const unsigned tm = __ballot_sync(FULL, take);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint8_t v = grid[nb[k]];
-            if (v == 0 || v == 5) {
-                heap_push(heap, nheap, ((unsigned long long)(unsigned)h[nb[k]] << 32) | (unsigned)nb[k]);
-                parent[nb[k]] = cur;
-                grid[nb[k]] = 3;
+            if (tm & (1u << k)) {
+                const int knb = __shfl_sync(FULL, nb, k), khv = __shfl_sync(FULL, hv, k);
+                heap_push(heap, nheap, ((unsigned long long)(unsigned)khv << 32) | (unsigned)knb, lane);
             }
         }
     }
     int len = 0;
-    if (found) {
-        for (int k = g; k >= 0; k = parent[k]) len++;
-        if (len <= route_cap) {
-            int w = len - 1;
-            for (int k = g; k >= 0; k = parent[k], w--) {
-                route[2 * w] = k / M; route[2 * w + 1] = k % M;
-                if (w >= 1) grid[k] = 6;                 // arm02:172-173
+    if (lane == 0) {
+        if (found) {
+            for (int k = g; k >= 0; k = parent[k]) len++;
+            if (len <= route_cap) {
+                int w = len - 1;
+                for (int k = g; k >= 0; k = parent[k], w--) {
+                    route[2 * w] = k / M; route[2 * w + 1] = k % M;
+                    if (w >= 1) grid[k] = 6;                 // arm02:172-173
+                }
+            } else {
+                len = -len;                                  // does not fit: report the length negated
             }
-        } else {
-            len = -len;                                  // does not fit: report the length negated
         }
+        route_len[q] = len;
+        expanded[q] = n_exp;
     }
-    route_len[q] = len;
-    expanded[q] = n_exp;
 }
 
 int launch_astar_torus(int M, int n_queries, const int32_t *start_goal, uint8_t *grids, int32_t *heur, int32_t *parents,
@@ -132,8 +169,8 @@ int launch_astar_torus(int M, int n_queries, const int32_t *start_goal, uint8_t 
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(parents)");
     const long long total = (long long)cells * n_queries;
     astar_heuristic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(M, n_queries, start_goal, heur);
-    astar_torus_kernel<<<(unsigned)((n_queries + 31) / 32), 32, 0, s>>>(M, n_queries, start_goal, heur, grids, parents, heaps,
-                                                                      routes, route_cap, route_len, expanded);
+    astar_torus_kernel<<<(unsigned)((n_queries + ASTAR_WARPS - 1) / ASTAR_WARPS), ASTAR_WARPS * 32, 0, s>>>(
+        M, n_queries, start_goal, heur, grids, parents, heaps, routes, route_cap, route_len, expanded);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "astar_torus kernels launch");
     return RRTK_OK;
