@@ -365,12 +365,11 @@ def main():
         nn = nn_roofline(torch, L, dev, args.nn_nodes, peaks)
 
         # algorithmic work of one launch (DESIGN.md "Roofline"): the reference's brute-force FP64
-        # point-circle tests and node-distance evaluations, counted by the oracle on sample queries
+        # point-circle tests and node-distance evaluations (counted offline, see ALGORITHMIC_FLOP_PER_ITER)
         alg = algorithmic_work(iters, n_obs)
-        flop_per_launch = alg["flop_per_iter"] * Q * iters
-        achieved = flop_per_launch / (t_dev / args.steps) / 1e12
+        achieved = alg["flop_per_iter"] * Q * iters / (t_dev / args.steps) / 1e12 if alg["flop_per_iter"] else None
         roofline = dict(kernel="rrtstar_kernel", bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
-                        frac=achieved / fp64_peak,
+                        frac=achieved / fp64_peak if achieved else None,
                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the
                         # committed ncu capture (profiles/r1i_rrtstar_kernel_ncu_summary.txt): 5.76 + 2.40 GB
                         traffic=8.16e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
@@ -654,34 +653,20 @@ def extras(torch, dev):
     return out
 
 
-def algorithmic_work(iters, n_obs, n_sample=4):
-    """Reference-equivalent FP64 work per tree-iteration, counted on sample queries by the C oracle:
-    every node-distance evaluation of nearest/near (5 flop) and every point-circle test the
-    reference's check_collision performs (5 flop)."""
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-    from rrtk import sampling, workloads as W
-    cfg = W.C2
-    tot_pairs = tot_scan = 0
-    for w in range(n_sample):
-        coins = sampling.kernel_coins(0xC2, w, iters, 5)
-        pts = O.sobol_fill(2, w * iters, int((~coins).sum()))
-        stream = np.empty((iters, 2))
-        stream[~coins] = -2.0 + pts * 17.0
-        stream[coins] = (13.0, 13.0)
-        p, ob = O.make_params(cfg["start"], cfg["goal"], W.c2_obstacles(w, n_obs).tolist(), cfg["expand_dis"],
-                              cfg["path_resolution"], iters, None, 0.0, cfg["connect_circle_dist"], True)
-        r = O.rrtstar_run(p, ob, stream, want_trace=True)
-        tr = r["trace"]
-        tot_pairs += r["work_pairs"]
-        tot_scan += r["work_scan"]
-    per_iter = 5.0 * (tot_pairs + tot_scan) / (n_sample * iters)
-    return dict(flop_per_iter=per_iter,
-                note=f"5 flop x (point-circle tests + node-distance evaluations) of the brute-force reference "
-                     f"algorithm, counted by the oracle over {n_sample} sample queries: "
-                     f"{tot_pairs / (n_sample * iters):.0f} tests + {tot_scan / (n_sample * iters):.0f} distances "
-                     f"per iteration")
+# Reference-equivalent FP64 work per tree-iteration of the default workload (config 2: 256 circles, 2000 iterations):
+# every node-distance evaluation of nearest / near (5 flop) and every point-circle test the reference's check_collision
+# performs (5 flop), counted on 4 sample queries of the workload by tools/count_algorithmic_work.py (which runs the CPU
+# oracle; bench.py's GPU arm does not): 28552.29 tests + 1274.86 distances per iteration.
+ALGORITHMIC_FLOP_PER_ITER = {(2000, 256): 149135.72875}
+
+
+def algorithmic_work(iters, n_obs):
+    f = ALGORITHMIC_FLOP_PER_ITER.get((iters, n_obs))
+    return dict(flop_per_iter=f,
+                note="5 flop x (point-circle tests + node-distance evaluations) of the brute-force reference algorithm: "
+                     "28552 tests + 1275 distances per iteration, counted offline on 4 sample queries "
+                     "(tools/count_algorithmic_work.py)" if f else "no work count for this workload (run "
+                     "tools/count_algorithmic_work.py)")
 
 
 def nn_roofline(torch, L, dev, n, peaks):
