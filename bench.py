@@ -561,8 +561,10 @@ def extras(torch, dev):
             tree_iters_per_s=i["iters_done"] / t, c_best=i["c_best"], mean_near=i["total_hits"] / max(1, i["iters_done"]),
             reached_node_cap=bool(i["status"] & 2), scan_gbs_algorithmic=alg_bytes / t / 1e9,
             goal_events=i["goal_events"], resamples=i["resamples"], grid=i["grid"],
-            cycles_per_iter=([round(c / max(1, i["iters_done"])) for c in i["cycles"]]
-                             if any(c >= i["iters_done"] for c in i["cycles"]) else None),   # only the unbatched kernel records them
+            # batched kernel: cycles[0] = batches, cycles[1..5] = CTA 0's clocks in pass A | exchange A | extend + cut + pass B +
+            # candidates | exchange B + cut #2 | apply + goal
+            batches=int(i["cycles"][0]), samples_per_batch=i["iters_done"] / max(1, i["cycles"][0]),
+            cycles_per_batch=[round(c / max(1, i["cycles"][0])) for c in i["cycles"][1:]],
             note="one fused FP64 pass (16 B/node) per iteration over an L2-resident tree; latency-bound by the "
                  "grid-wide exchange and the serial leaf math, see DESIGN.md 5.5")
         del run, d_free, d_ball

@@ -758,7 +758,8 @@ struct BatchSmem {
     int w_m[TREE_NW], w_h[TB_MAX][TREE_NW];
     double q_d[TB_MAX][TREE_NW];      // per-warp partial of the cross-CTA reduce
     int q_i[TB_MAX][TREE_NW], q_h[TB_MAX][TREE_NW], q_m[TREE_NW];
-    double sx[TB_MAX], sy[TB_MAX];    // samples
+    double sx[2 * TB_MAX], sy[2 * TB_MAX];   // sample window: [k] = sample of iteration it + k; [0, B) is the batch, the
+                                             // rest is drawn ahead by the idle warps of the extend phase
     double fx[TB_MAX], fy[TB_MAX];    // nearest node position
     double nx[TB_MAX], ny[TB_MAX];    // extended node
     double nn_d2[TB_MAX], cp_cost[TB_MAX], plen;
@@ -869,19 +870,34 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
     int n_slow = 0, n_goal = 0, n_redo = 0, n_cut = 0;
     bool stop = false;
     int blimit = BMAX;   // halved after a batch whose hit list did not fit, restored after a good one
+    int win_n = 0;       // valid entries of the sample window S.sx / S.sy (iterations it .. it + win_n - 1) ...
+    double win_cb = 0.0; // ... drawn with this c_best
+    // per-phase clocks of CTA 0 (reported in res->cycles[1..5]): pass A | exchange A | extend + cut + pass B + candidates |
+    // exchange B + cut #2 | apply + goal
+    long long tc[6] = {0, 0, 0, 0, 0, 0}, t_prev = clock64();
+#define TB_TICK(k) do { const long long t_ = clock64(); tc[k] += t_ - t_prev; t_prev = t_; } while (0)
+    // finer split (res->cycles_max[0..5]): samples | scan A | (argmin A = cycles[1] - these two) | extend | cut #1 + cull +
+    // scan B | (candidates = cycles[3] - these two); slot 2 and 5 are left 0
+    long long ts[6] = {0, 0, 0, 0, 0, 0}, t_sub = t_prev;
+#define TB_SUB(k) do { const long long t_ = clock64(); ts[k] += t_ - t_sub; t_sub = t_; } while (0)
+#define TB_SUB_RESET() do { t_sub = clock64(); } while (0)
 
     while (it < A.p.max_iter && !stop) {
         const int B = min(blimit, A.p.max_iter - it);
         n_batches++;
         // ---- samples (informed_sample, rrt_07:1145-1159) ----
-        if (warp < B) {
-            double a, b;
-            draw_sample(A, it + warp, c_best, c_min, xc, yc, a, b);
-            if (lane == 0) { S.sx[warp] = a; S.sy[warp] = b; }
+        if (!(win_n >= B && win_cb == c_best)) {   // window empty or drawn for another ellipse: draw the batch now
+            if (warp < B) {
+                double a, b;
+                draw_sample(A, it + warp, c_best, c_min, xc, yc, a, b);
+                if (lane == 0) { S.sx[warp] = a; S.sy[warp] = b; }
+            }
+            win_n = B; win_cb = c_best;
         }
         if (tid == 0) { S.nhit = 0; S.gcount = 0; }
         if (tid < TB_MAX) S.ncull[tid] = 0;
         __syncthreads();
+        TB_SUB(0);
         // ---- pass A: nearest of every sample among the owned nodes ----
         {
             double bd[TB_MAX], qx[TB_MAX], qy[TB_MAX];
@@ -910,6 +926,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
                     }
                 }
             }
+            TB_SUB(1);
 #pragma unroll
             for (int k = 0; k < TB_MAX; k++) {
                 if (k >= B) break;
@@ -920,7 +937,10 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
             }
         }
         __syncthreads();
+        TB_TICK(1);
         batch_exchange(S, ws, seq, G, B, false);
+        TB_TICK(2);
+        TB_SUB_RESET();
         // ---- warp k extends winner k (get_new_node + check_collision + goal tests, exact leaf math) ----
         if (warp < B) {
             const int wi = S.q_i[warp][0];
@@ -932,8 +952,18 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
                 S.nn_idx[warp] = wi; S.nn_d2[warp] = S.q_d[warp][0]; S.fx[warp] = f.x; S.fy[warp] = f.y;
                 S.nx[warp] = cx; S.ny[warp] = cy; S.cf[warp] = cf;
             }
+        } else if (warp >= TB_MAX) {
+            // look-ahead sampling by the warps that have no winner to extend: warp j draws the sample of iteration it + j,
+            // so informed_sample's load + sqrt / sin / cos chain is off the critical path of the next batch
+            if (win_n >= TB_MAX && warp >= win_n && it + warp < A.p.max_iter) {
+                double a, b;
+                draw_sample(A, it + warp, c_best, c_min, xc, yc, a, b);
+                if (lane == 0) { S.sx[warp] = a; S.sy[warp] = b; }
+            }
         }
+        if (win_n >= TB_MAX) win_n = max(win_n, min(2 * TB_MAX, A.p.max_iter - it));
         __syncthreads();
+        TB_SUB(3);
         // ---- cut #1 (uniform): in-batch dependencies, goal connection, capacity ----
         int B1 = B, acc = 0, idx_of[TB_MAX], acc_mask = 0;
         double r2_of[TB_MAX], r_of[TB_MAX];
@@ -1022,6 +1052,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
             }
         }
         __syncthreads();
+        TB_SUB(4);
         const int H = min(S.nhit, TB_HCAP);
         // ---- choose_parent candidates of the owned hits (rrt_07:1110-1135), per sample ----
         int eq = 0, dupn = 0;
@@ -1094,6 +1125,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
             if (lane == 0) S.w_m[warp] = mk;
         }
         __syncthreads();
+        TB_TICK(3);
         batch_exchange(S, ws, seq, G, B1, true);
         const int gm = S.g_mask;
         if ((gm >> 24) & 1) {   // some CTA's hit list overflowed: nothing was applied yet -- undo the hash inserts and retry smaller
@@ -1154,6 +1186,7 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
             if (tid == 0) { S.cp_cost[0] = S.q_d[0][0]; S.cp_idx[0] = S.q_i[0][0]; }
             __syncthreads();
         }
+        TB_TICK(4);
         // ---- apply: append + rewire (rrt_07:1232-1246) for the surviving samples ----
         double ncost_of[TB_MAX];
         int npar_of[TB_MAX], n_acc = 0;
@@ -1237,7 +1270,21 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
         n += n_acc;
         it += Be;
         __syncthreads();
+        {   // slide the sample window by the Be iterations just consumed
+            double vx = 0.0, vy = 0.0;
+            const bool mv = tid + Be < win_n;
+            if (mv) { vx = S.sx[tid + Be]; vy = S.sy[tid + Be]; }
+            __syncthreads();
+            if (mv) { S.sx[tid] = vx; S.sy[tid] = vy; }
+            win_n = win_n > Be ? win_n - Be : 0;
+            __syncthreads();
+        }
+        TB_TICK(5);
+        TB_SUB_RESET();
     }
+#undef TB_TICK
+#undef TB_SUB
+#undef TB_SUB_RESET
 
     if (cta == 0 && tid == 0) {
         A.res->n_nodes = n; A.res->path_len = plen_best;
@@ -1245,6 +1292,8 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
         A.res->iters_done = it; A.res->c_best = c_best; A.res->total_hits = total_hits; A.res->slow_paths = n_slow;
         A.res->goal_events = n_goal; A.res->resamples = n_redo; A.res->grid = G; A.res->reextends = n_cut; A.res->pad_ = 0;
         A.res->cycles[0] = n_batches;
+        for (int k = 1; k < 6; k++) A.res->cycles[k] = tc[k];
+        for (int k = 0; k < 6; k++) A.res->cycles_max[k] = ts[k];
     }
 }
 

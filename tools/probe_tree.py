@@ -25,5 +25,7 @@ for iters in sizes:
     print(f"iters {iters}: {ms:.1f} ms, {ms * 1e3 / iters:.2f} us/iter, nodes {i['n_nodes']}, c_best {i['c_best']:.6f}, "
           f"hits/iter {i['total_hits'] / iters:.1f}, goal_events {i['goal_events']}, resamples {i['resamples']}, "
           f"slow {i['slow_paths']}, reext/cuts {i['reextends']}, batches {i['cycles'][0] if int(os.environ.get('RRTK_TREE_BATCH', '8')) > 1 else '-'}, status {i['status']}, grid {i['grid']}, "
+          f"cycles/batch {[round(c / max(1, i['cycles'][0])) for c in i['cycles'][1:]]} "
+          f"sub/batch {[round(c / max(1, i['cycles'][0])) for c in i['cycles_max']]} "
           f"cycles/iter {[round(c / iters) for c in i['cycles']]} max {[round(c / iters) for c in i['cycles_max']]} "
           f"min {[round(-c / iters) for c in i['cycles_negmin']]}", flush=True)
