@@ -758,6 +758,8 @@ struct BatchSmem {
     int w_m[TREE_NW], w_h[TB_MAX][TREE_NW];
     double q_d[TB_MAX][TREE_NW];      // per-warp partial of the cross-CTA reduce
     int q_i[TB_MAX][TREE_NW], q_h[TB_MAX][TREE_NW], q_m[TREE_NW];
+    double c_r2[TB_MAX], c_r[TB_MAX];        // cut #1 results per sample: near radius^2, radius (idx in c_idx)
+    int c_idx[TB_MAX];
     double sx[2 * TB_MAX], sy[2 * TB_MAX];   // sample window: [k] = sample of iteration it + k; [0, B) is the batch, the
                                              // rest is drawn ahead by the idle warps of the extend phase
     double fx[TB_MAX], fy[TB_MAX];    // nearest node position
@@ -965,35 +967,41 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
         __syncthreads();
         TB_SUB(3);
         // ---- cut #1 (uniform): in-batch dependencies, goal connection, capacity ----
+        // A rolled loop over shared memory that every thread runs identically (its 28 unrolled pair tests were 29 KB of
+        // straight-line code per batch); the per-sample results go through shared memory into the register arrays.
         int B1 = B, acc = 0, idx_of[TB_MAX], acc_mask = 0;
         double r2_of[TB_MAX], r_of[TB_MAX];
         bool goal_last = false;
-#pragma unroll
-        for (int j = 0; j < TB_MAX; j++) { idx_of[j] = -1; r2_of[j] = -1.0; r_of[j] = 0.0; }
-#pragma unroll
-        for (int j = 0; j < TB_MAX; j++) {
-            if (j >= B1) break;
+        if (tid < TB_MAX) { S.c_idx[tid] = -1; S.c_r2[tid] = -1.0; S.c_r[tid] = 0.0; }
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j < B; j++) {
             const bool acc_j = !(S.cf[j] & CF_BLOCKED);
             const double2 rr2 = __ldg(A.near_rr2 + (n + acc));
+            const double sxj = S.sx[j], syj = S.sy[j], nxj = S.nx[j], nyj = S.ny[j], nnd = S.nn_d2[j];
             bool dep = false;
-#pragma unroll
-            for (int i = 0; i < TB_MAX; i++) {
-                if (i >= j) break;
+#pragma unroll 1
+            for (int i = 0; i < j; i++) {
                 if (!((acc_mask >> i) & 1)) continue;
-                const double ax = S.nx[i] - S.sx[j], ay = S.ny[i] - S.sy[j];
-                dep |= ax * ax + ay * ay < S.nn_d2[j];                       // node i would be the nearest of sample j
+                const double nxi = S.nx[i], nyi = S.ny[i];
+                const double ax = nxi - sxj, ay = nyi - syj;
+                dep |= ax * ax + ay * ay < nnd;                              // node i would be the nearest of sample j
                 if (acc_j) {
-                    const double bx = S.nx[i] - S.nx[j], by = S.ny[i] - S.ny[j];
+                    const double bx = nxi - nxj, by = nyi - nyj;
                     dep |= bx * bx + by * by <= rr2.y;                       // node i would be in the near list of node j
                 }
             }
             if (dep) { B1 = j; n_cut++; break; }
             if (acc_j) {
                 if (n + acc >= A.p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; stop = true; B1 = j; break; }
-                idx_of[j] = n + acc; r2_of[j] = rr2.y; r_of[j] = rr2.x; acc_mask |= 1 << j; acc++;
+                if (tid == 0) { S.c_idx[j] = n + acc; S.c_r2[j] = rr2.y; S.c_r[j] = rr2.x; }
+                acc_mask |= 1 << j; acc++;
                 if ((S.cf[j] & CF_NEAR_GOAL) && !(S.cf[j] & CF_GOAL_BLOCKED)) { B1 = j + 1; goal_last = true; break; }
             }
         }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < TB_MAX; j++) { idx_of[j] = S.c_idx[j]; r2_of[j] = S.c_r2[j]; r_of[j] = S.c_r[j]; }
         if (B1 == 0) break;   // only when the tree is full
         // ---- obstacle cull per accepted sample ----
         for (int j = tid; j < n_obs; j += TREE_T) {
