@@ -25,15 +25,16 @@ static __device__ const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -
                                        {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
 static __device__ const int8_t RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
 
-// the path functions of rs00:166-363 in path_functions order; true + travel distances, or false
-static __device__ __noinline__ bool rs_word(int f, double x, double y, double phi, double *d) {
+// the path functions of rs00:166-363 in path_functions order; true + travel distances, or false.
+// Every one of them starts from polar(x -/+ sin(phi), y - 1 +/- cos(phi)) (rs00:163-166): (um, thm) is the "minus" pair
+// (x - sin, y - 1 + cos), (up, thp) the "plus" pair (x + sin, y - 1 - cos).  The twelve functions of one symmetry share
+// these two polars, so an evaluator that walks all 48 candidates computes them 8 times instead of 48 (rs_edge_lane).
+static __device__ __forceinline__ bool rs_word_core(int f, double phi, double um, double thm, double up, double thp, double *d) {
     const double pi = D_PI;
-    double sp, cp;
-    sincos_cr(phi, &sp, &cp);
     double u, t, v, u1, theta, A;
     if (f == 0) {
-        u = crm_hypot(x - sp, y - 1.0 + cp);
-        t = crm_atan2(y - 1.0 + cp, x - sp);
+        u = um;
+        t = thm;
         if (0.0 <= t && t <= pi) {
             v = rs_mod2pi(phi - t);
             if (0.0 <= v && v <= pi) { d[0] = t; d[1] = u; d[2] = v; return true; }
@@ -41,9 +42,8 @@ static __device__ __noinline__ bool rs_word(int f, double x, double y, double ph
         return false;
     }
     if (f == 1) {
-        u1 = crm_hypot(x + sp, y - 1.0 - cp);
-        const double t1 = crm_atan2(y - 1.0 - cp, x + sp);
-        u1 = u1 * u1;
+        const double t1 = thp;
+        u1 = up * up;
         if (u1 >= 4.0) {
             u = sqrt(u1 - 4.0);
             theta = crm_atan2(2.0, u);
@@ -54,9 +54,8 @@ static __device__ __noinline__ bool rs_word(int f, double x, double y, double ph
         return false;
     }
     const bool minus = f == 2 || f == 3 || f == 4 || f == 7 || f == 9;
-    const double zeta = minus ? x - sp : x + sp, eeta = minus ? y - 1 + cp : y - 1 - cp;
-    u1 = crm_hypot(zeta, eeta);
-    theta = crm_atan2(eeta, zeta);
+    u1 = minus ? um : up;
+    theta = minus ? thm : thp;
     switch (f) {
         case 2:
             if (u1 <= 4.0) {
@@ -136,6 +135,21 @@ static __device__ __noinline__ bool rs_word(int f, double x, double y, double ph
     }
 }
 
+
+static __device__ __forceinline__ void rs_polars(double x, double y, double phi, bool want_minus, bool want_plus, double *um,
+                                                 double *thm, double *up, double *thp) {
+    double sp, cp;
+    sincos_cr(phi, &sp, &cp);
+    if (want_minus) { *um = crm_hypot(x - sp, y - 1.0 + cp); *thm = crm_atan2(y - 1.0 + cp, x - sp); }
+    if (want_plus) { *up = crm_hypot(x + sp, y - 1.0 - cp); *thp = crm_atan2(y - 1.0 - cp, x + sp); }
+}
+static __device__ __noinline__ bool rs_word(int f, double x, double y, double phi, double *d) {
+    const bool minus = f == 0 || f == 2 || f == 3 || f == 4 || f == 7 || f == 9;
+    double um = 0.0, thm = 0.0, up = 0.0, thp = 0.0;
+    rs_polars(x, y, phi, minus, !minus, &um, &thm, &up, &thp);
+    return rs_word_core(f, phi, um, thm, up, thp, d);
+}
+
 // interpolate (rs00:449-470); sm / cm = sin / cos(-origin_yaw), so / co = sin / cos(origin_yaw)
 static __device__ __forceinline__ void rs_interp(double dist, int type, double maxc, double ox, double oy, double oyaw,
                                                  double so, double co, double sm, double cm, double *x, double *y, double *yaw) {
@@ -182,11 +196,16 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
     // generate_path + set_path in the reference's order; keep the first shortest inserted word
     double ins_L[48], best_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, best_L = CUDART_INF;
     int ins_code[48], n_ins = 0, best = -1;
+    double pol[4][4];   // per symmetry: um, thm, up, thp
+#pragma unroll 1
+    for (int k = 0; k < 4; k++)
+        rs_polars((k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, true, true, &pol[k][0], &pol[k][1],
+                  &pol[k][2], &pol[k][3]);
 #pragma unroll 1
     for (int cand = 0; cand < 48; cand++) {
         const int f = cand >> 2, k = cand & 3, n = RS_N[f];
         double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        if (!rs_word(f, (k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, d)) continue;
+        if (!rs_word_core(f, (k == 1 || k == 2) ? -dth : dth, pol[k][0], pol[k][1], pol[k][2], pol[k][3], d)) continue;
         double tot = 0.0;
         for (int i = 0; i < n; i++) tot += fabs(d[i]);
         for (int i = 0; i < n; i++) {
