@@ -143,6 +143,19 @@ RRTK_API int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *s
                           double *cost, int32_t *parent, int32_t *n_nodes, int32_t *iters_done,
                           int32_t *goal_index, int32_t *status, int32_t *trace);
 
+/* The per-step primitive: steer (rrt_04:1086-1115, with calc_distance_and_angle :1232-1238) + check_collision (:1216-1230)
+ * + check_if_outside_play_area (:1204-1214) for N independent edges -- what an overridden `steer` / `check_collision`
+ * pair of a subclass calls; the planner kernels run the same device functions inside their iterations.
+ *   from_xy, to_xy [N][2]; extend_length (+inf = the reference's default); obstacles: rows x, y, R, R**2 in sets of
+ *   obs_stride rows, request r tests set obs_set[r] (NULL = set 0) with n_obs[set] rows; play_area = xmin, xmax, ymin,
+ *   ymax on the device, or NULL.
+ * outputs: new_xy [N][2] (the new node), dist [N] = hypot(to - from), n_points [N] = len(path_x), free_flag [N] (1 = no
+ *   path point inside a circle), inside_flag [N] (1 = the new node is inside the play area, or there is none). */
+RRTK_API int rrtk_steer_collide_dev(int64_t n_req, const double *from_xy, const double *to_xy, double extend_length,
+                                    double path_resolution, const int32_t *obs_set, const double *obstacles,
+                                    int32_t obs_stride, const int32_t *n_obs, const double *play_area, double *new_xy,
+                                    double *dist, int32_t *n_points, uint8_t *free_flag, uint8_t *inside_flag, void *stream);
+
 /* generate_final_course (rrt_04:1117-1125) for every query on the device:
  *   path [Q][path_cap][2] = goal, node(goal_index), ..., root;  path_len [Q] (0 = no path) */
 RRTK_API int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,

@@ -71,6 +71,9 @@ int launch_closed_loop(const rrtk_closed_loop_params &p, const double *course, c
 int launch_bitstar(const rrtk_bitstar_params &p, const double *start_goal, const double *rot, const double *obstacles,
                    const int32_t *n_obs, const double *draws, double *ws_d, int32_t *ws_i, double *path, int32_t *counts,
                    double *g_goal, int32_t *status, cudaStream_t s);
+int launch_steer_collide(long long n_req, const double *from_xy, const double *to_xy, double extend, double res,
+                         const int32_t *obs_set, const double *obstacles, int obs_stride, const int32_t *n_obs, const double *play,
+                         double *new_xy, double *dist, int32_t *n_points, uint8_t *free_flag, uint8_t *inside_flag, cudaStream_t s);
 int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
                         const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
                         cudaStream_t s);
@@ -365,6 +368,21 @@ int rrtk_bitstar_run_dev(const rrtk_bitstar_params *p, const double *start_goal,
     if ((uintptr_t)obstacles & 15) return set_error(RRTK_ERR_INVALID, "obstacles must be 16-byte aligned");
     return launch_bitstar(*p, start_goal, rot, obstacles, n_obs, draws, ws_d, ws_i, path, counts, g_goal, status,
                           (cudaStream_t)stream);
+}
+
+int rrtk_steer_collide_dev(int64_t n_req, const double *from_xy, const double *to_xy, double extend_length, double path_resolution,
+                           const int32_t *obs_set, const double *obstacles, int32_t obs_stride, const int32_t *n_obs,
+                           const double *play_area, double *new_xy, double *dist, int32_t *n_points, uint8_t *free_flag,
+                           uint8_t *inside_flag, void *stream) {
+    if (n_req < 0 || obs_stride < 0) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (!(path_resolution > 0.0) || !(extend_length >= 0.0)) return set_error(RRTK_ERR_INVALID, "path_resolution must be > 0, extend_length >= 0");
+    if (n_req == 0) return RRTK_OK;
+    if (!from_xy || !to_xy || !new_xy || !dist || !n_points || !free_flag || !inside_flag || (n_obs && obs_stride > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)from_xy | (uintptr_t)to_xy | (uintptr_t)new_xy | (uintptr_t)obstacles) & 15)
+        return set_error(RRTK_ERR_INVALID, "from_xy / to_xy / new_xy / obstacles must be 16-byte aligned");
+    return launch_steer_collide(n_req, from_xy, to_xy, extend_length, path_resolution, obs_set, obstacles, obs_stride, n_obs,
+                                play_area, new_xy, dist, n_points, free_flag, inside_flag, (cudaStream_t)stream);
 }
 
 int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,

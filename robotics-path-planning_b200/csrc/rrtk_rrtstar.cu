@@ -804,6 +804,42 @@ int launch_sample_stream(const rrtk_rrtstar_params &p, const double *start_goal,
     return RRTK_OK;
 }
 
+// steer (rrt_04:1086-1115) + check_collision (:1216-1230) + check_if_outside_play_area (:1204-1214) of N independent edges,
+// one lane each: the stand-alone form of what the planner kernel does inside an iteration.
+__global__ void steer_collide_kernel(long long n_req, const double2 *__restrict__ from_xy, const double2 *__restrict__ to_xy,
+                                     double extend, double res, const int32_t *__restrict__ obs_set,
+                                     const double4 *__restrict__ obstacles, int obs_stride, const int32_t *__restrict__ n_obs_arr,
+                                     const double *__restrict__ play, double2 *new_xy, double *dist, int32_t *n_points,
+                                     uint8_t *free_flag, uint8_t *inside_flag) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_req) return;
+    const double2 f = from_xy[r], t = to_xy[r];
+    const Steer st = steer(f.x, f.y, t.x, t.y, extend, res);
+    const int set = obs_set ? obs_set[r] : 0;
+    const double4 *obs = obstacles + (size_t)set * obs_stride;
+    ObsList L;
+    L.ox = &obs->x; L.oy = &obs->y; L.r2 = &obs->w; L.stride = 4; L.m = n_obs_arr ? n_obs_arr[set] : 0;
+    new_xy[r] = make_double2(st.ex, st.ey);
+    dist[r] = st.d;
+    n_points[r] = 1 + st.n + (st.snap ? 1 : 0);   // len(path_x): the start, n_expand steps, the target when snapped
+    free_flag[r] = edge_free_lane(f.x, f.y, st, t.x, t.y, L) ? 1 : 0;
+    // check_if_outside_play_area: True (ok) without a play area, else xmin <= x <= xmax and ymin <= y <= ymax
+    inside_flag[r] = (!play || !(st.ex < play[0] || st.ex > play[1] || st.ey < play[2] || st.ey > play[3])) ? 1 : 0;
+}
+
+int launch_steer_collide(long long n_req, const double *from_xy, const double *to_xy, double extend, double res,
+                         const int32_t *obs_set, const double *obstacles, int obs_stride, const int32_t *n_obs, const double *play,
+                         double *new_xy, double *dist, int32_t *n_points, uint8_t *free_flag, uint8_t *inside_flag, cudaStream_t s) {
+    const int threads = 128;
+    steer_collide_kernel<<<(unsigned)((n_req + threads - 1) / threads), threads, 0, s>>>(
+        n_req, reinterpret_cast<const double2 *>(from_xy), reinterpret_cast<const double2 *>(to_xy), extend, res, obs_set,
+        reinterpret_cast<const double4 *>(obstacles), obs_stride, n_obs, play, reinterpret_cast<double2 *>(new_xy), dist,
+        n_points, free_flag, inside_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "steer_collide_kernel launch");
+    return RRTK_OK;
+}
+
 int launch_crmath_probe(int kind, int64_t n, const double *a, const double *b, double *out, cudaStream_t s) {
     int threads = 128;
     crmath_probe_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(kind, n, a, b, out);

@@ -104,6 +104,8 @@ _SIGS = {
     "rrtk_path_smoothing_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "rrtk_closed_loop_dev": (C.c_int, [C.POINTER(ClosedLoopParams), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rrtk_bitstar_run_dev": (C.c_int, [C.POINTER(BitStarParams)] + [_VP] * 12),
+    "rrtk_steer_collide_dev": (C.c_int, [C.c_int64, _VP, _VP, C.c_double, C.c_double, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
+                                         _VP, _VP, _VP]),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),

@@ -166,3 +166,36 @@ def sample_stream_dev(p: _lib.RRTStarParams, start_goal, sobol_offset=None):
                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "rrtk_sample_stream_dev")
     return out
+
+
+def steer_collide(from_xy, to_xy, obstacle_lists, extend_length=float("inf"), path_resolution=0.5, robot_radius=0.0,
+                  play_area=None, obs_set=None, device=None):
+    """steer (rrt_04:1086-1115) + check_collision (:1216-1230) + check_if_outside_play_area (:1204-1214) for N edges in
+    one launch (rrtk_steer_collide_dev).  from_xy / to_xy [N, 2]; obstacle_lists: one list of (x, y, r) for all edges, or
+    several with `obs_set[r]` choosing the list of edge r.  Returns dict(new_xy [N, 2], dist, n_points, free, inside)."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    f = np.ascontiguousarray(from_xy, dtype=np.float64).reshape(-1, 2)
+    t = np.ascontiguousarray(to_xy, dtype=np.float64).reshape(-1, 2)
+    n = f.shape[0]
+    if len(obstacle_lists) == 0 or (len(obstacle_lists[0]) == 3 and np.ndim(obstacle_lists[0][0]) == 0):
+        obstacle_lists = [obstacle_lists]
+    rows, counts = pack_obstacles([list(o) for o in obstacle_lists], robot_radius)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        d_f, d_t, d_rows, d_cnt = up(f), up(t), up(rows if rows.size else np.zeros((1, 1, 4))), up(counts)
+        d_set = up(np.asarray(obs_set, dtype=np.int32)) if obs_set is not None else None
+        d_play = up(np.asarray(play_area, dtype=np.float64)) if play_area is not None else None
+        new_xy = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        dist = torch.empty(n, dtype=torch.float64, device=dev)
+        npts = torch.empty(n, dtype=torch.int32, device=dev)
+        free = torch.empty(n, dtype=torch.uint8, device=dev)
+        inside = torch.empty(n, dtype=torch.uint8, device=dev)
+        rc = _lib.lib().rrtk_steer_collide_dev(
+            n, d_f.data_ptr(), d_t.data_ptr(), float(extend_length), float(path_resolution),
+            d_set.data_ptr() if d_set is not None else None, d_rows.data_ptr(), rows.shape[1], d_cnt.data_ptr(),
+            d_play.data_ptr() if d_play is not None else None, new_xy.data_ptr(), dist.data_ptr(), npts.data_ptr(),
+            free.data_ptr(), inside.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_steer_collide_dev")
+        return dict(new_xy=new_xy.cpu().numpy(), dist=dist.cpu().numpy(), n_points=npts.cpu().numpy(),
+                    free=free.cpu().numpy().astype(bool), inside=inside.cpu().numpy().astype(bool))

@@ -9,6 +9,7 @@ so wherever the cr arithmetic reproduces the fixture, the GPU is also compared w
 own output directly.  Bar: positions, costs, parents, traces and paths are compared with
 array_equal -- no tolerance."""
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -260,3 +261,28 @@ def test_host_buffer_entry_point(torch_cuda, oracle_lib):
     n = ref["n"]
     assert nn[0] == n and np.array_equal(parent[0, :n], ref["parent"])
     assert np.array_equal(xy[0, :n, 0], ref["x"]) and np.array_equal(cost[0, :n], ref["cost"])
+
+
+@pytest.mark.gpu
+def test_steer_collide_primitive_matches_the_port():
+    """rrtk_steer_collide_dev against the Python port of steer / check_collision / check_if_outside_play_area (which is
+    bit-identical to the reference): same point counts and verdicts, new nodes equal up to the last bit of cos / sin."""
+    import pyport as P
+    from rrtk import engine
+    rng = np.random.default_rng(21)
+    n = 4000
+    f = rng.uniform(-2, 15, (n, 2)); t = f + rng.uniform(-4, 4, (n, 2))
+    t[:50] = f[:50]                                              # zero-length edges
+    obs = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+    play = [0.0, 10.0, 0.0, 14.0]
+    for ext, res, rr in ((1.0, 0.1, 0.6), (float("inf"), 0.5, 0.0), (3.0, 1.0, 0.0)):
+        r = engine.steer_collide(f, t, obs, ext, res, rr, play)
+        bad = 0
+        for k in range(n):
+            ex, ey, px, py = P.steer_points(f[k, 0], f[k, 1], t[k, 0], t[k, 1], ext, res)
+            assert r["n_points"][k] == len(px)
+            assert abs(r["new_xy"][k, 0] - ex) <= 1e-12 and abs(r["new_xy"][k, 1] - ey) <= 1e-12
+            assert r["dist"][k] == math.hypot(t[k, 0] - f[k, 0], t[k, 1] - f[k, 1])
+            bad += r["free"][k] != P.collision_free(px, py, obs, rr)
+            bad += r["inside"][k] != P.inside_play_area(ex, ey, play)
+        assert bad == 0
