@@ -105,6 +105,11 @@ typedef struct rrtk_rrtstar_params {
     int32_t grid_nx, grid_ny;       /* cells, each <= 64 */
     double grid_x0, grid_y0;        /* lower-left corner */
     double grid_cell;               /* cell edge */
+    /* incremental planning: resume = 1 continues the trees a previous call left in xy / cost / parent / n_nodes for
+     * max_iter MORE iterations; iter_offset = iterations already done (keeps the in-kernel coin / Sobol streams going;
+     * with RRTK_SAMPLER_STREAM the caller simply passes the next max_iter samples).  k calls of m iterations build the
+     * tree of one call of k * m iterations, bit for bit. */
+    int32_t resume, iter_offset;
 } rrtk_rrtstar_params;
 
 /* ints of workspace per query for rrtk_rrtstar_run_dev */

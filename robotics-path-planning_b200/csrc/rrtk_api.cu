@@ -98,6 +98,7 @@ static int check_params(const rrtk_rrtstar_params *p) {
     if (p->grid_nx < 0 || p->grid_ny < 0 || p->grid_nx > 64 || p->grid_ny > 64 || ((p->grid_nx == 0) != (p->grid_ny == 0)))
         return set_error(RRTK_ERR_INVALID, "grid_nx / grid_ny must both be 0 or both in 1..64");
     if (p->grid_nx > 0 && !(p->grid_cell > 0.0)) return set_error(RRTK_ERR_INVALID, "grid_cell must be > 0");
+    if ((p->resume != 0 && p->resume != 1) || p->iter_offset < 0) return set_error(RRTK_ERR_INVALID, "resume must be 0 / 1, iter_offset >= 0");
     return RRTK_OK;
 }
 
@@ -186,6 +187,7 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
     if (p->obs_stride > 0 && !obstacles) return set_error(RRTK_ERR_INVALID, "obstacles is NULL");
     if (p->sampler == RRTK_SAMPLER_STREAM && !sample_stream && p->max_iter > 0)
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
+    if (p->resume && trace) return set_error(RRTK_ERR_INVALID, "trace is not recorded with resume = 1");
     cudaStream_t s = (cudaStream_t)stream;
     DevCounter ctr(s);
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");

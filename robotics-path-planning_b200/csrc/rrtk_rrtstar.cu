@@ -254,7 +254,7 @@ struct SobolState {
 };
 
 // get_random_node / get_random_node_sobol (rrt_04:1132-1153) with a counter-based coin
-__device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, double gx,
+__device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, int it_key, double gx,
                                               double gy, const double2 *stream, SobolState &sob) {
     Sample s;
     if (p.sampler == RRTK_SAMPLER_STREAM) {
@@ -262,7 +262,7 @@ __device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int 
         s.x = v.x; s.y = v.y;
         return s;
     }
-    uint64_t k0 = rng_key(p.seed, (uint64_t)q, (uint64_t)it);
+    uint64_t k0 = rng_key(p.seed, (uint64_t)q, (uint64_t)it_key);   // it_key = iteration counter of the whole run
     int coin = (int)(splitmix64(k0) % 101ull);  // random.randint(0, 100)
     if (coin > p.goal_sample_rate) {
         double w = p.max_rand - p.min_rand;
@@ -342,7 +342,10 @@ __device__ unsigned int g_query_counter;
 // bookkeeping in its instruction stream (the loop is instruction-fetch sensitive)
 // NC > 0: the per-warp shared-memory arrays are laid out for a near list of NC entries (p.near_cap <= NC stays the
 // logical capacity), so every shared-memory address is an immediate; NC = 0: laid out for p.near_cap at run time.
-template <bool RRT_ONLY, bool TRACE, int NC>
+// RESUME: continue the trees of a previous call (p.resume); a separate instantiation so that the default path keeps its
+// register allocation (the kernel sits at the 128-register cap: the few extra live values cost 4 % when they were a
+// run-time branch).
+template <bool RRT_ONLY, bool TRACE, int NC, bool RESUME = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, RRTK_MIN_BLOCKS)
 rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
@@ -390,22 +393,40 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
         if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, p.expand_dis + res, lane);
-        if (lane == 0) {
-            xy[0] = make_double2(sg.x, sg.y);
-            cost[0] = 0.0;
-            parent[0] = -1;
-            links[0] = make_int4(-1, -1, -1, 0);
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
+        SobolState sob;
+        sob.n = sobol_base < 0 ? 0 : sobol_base;
+        if (!RESUME) {
+            if (lane == 0) {
+                xy[0] = make_double2(sg.x, sg.y);
+                cost[0] = 0.0;
+                parent[0] = -1;
+                links[0] = make_int4(-1, -1, -1, 0);
+            }
+        } else {
+            // continue the tree a previous call left in xy / cost / parent (rows 0 .. n_nodes[q] - 1): rebuild the children
+            // lists from the parent array (their order only fixes the traversal order of propagate, not its values) and
+            // skip the Sobol points the earlier iterations consumed (one per non-goal coin)
+            n = n_nodes[q];
+            if (n < 1 || n > p.node_cap) { n = 1; status |= RRTK_Q_NODE_OVERFLOW; }
+            for (int i = lane; i < n; i += 32) links[i] = make_int4(-1, -1, -1, 0);
+            __syncwarp();
+            if (lane == 0)
+                for (int i = 1; i < n; i++) { const int pp = parent[i]; if (pp >= 0 && pp < n) link_child(links, pp, i); }
+            if (p.sampler == RRTK_SAMPLER_SOBOL) {
+                int used = 0;
+                for (int k = lane; k < p.iter_offset; k += 32)
+                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)q, (uint64_t)k)) % 101ull) > p.goal_sample_rate;
+                sob.n += (int64_t)__reduce_add_sync(FULL, (unsigned)used);
+            }
         }
         __syncwarp();
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
-        SobolState sob;
-        sob.n = sobol_base < 0 ? 0 : sobol_base;
         sobol2(sob.n, sob.q0, sob.q1);
-        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
         bool done = false;
 
         for (it = 0; it < p.max_iter; it++) {
-            Sample smp = draw_sample(p, (int)q, it, gx, gy, stream, sob);
+            Sample smp = draw_sample(p, (int)q, it, RESUME ? it + p.iter_offset : it, gx, gy, stream, sob);
             const double rx = smp.x, ry = smp.y;
             // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the
             // sample: when the steered node snaps onto the sample (the common case once the tree is dense) the near
@@ -709,7 +730,7 @@ extern "C" __global__ void sample_stream_kernel(rrtk_rrtstar_params p, const dou
     sob.n = sobol_offset ? (sobol_offset[q] < 0 ? 0 : sobol_offset[q]) : 0;
     sobol2(sob.n, sob.q0, sob.q1);
     for (int it = 0; it < p.max_iter; it++) {
-        Sample s = draw_sample(p, q, it, sg.z, sg.w, nullptr, sob);
+        Sample s = draw_sample(p, q, it, it + p.iter_offset, sg.z, sg.w, nullptr, sob);
         out[(size_t)q * p.max_iter + it] = make_double2(s.x, s.y);
     }
 }
@@ -753,10 +774,13 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
                              const double2 *, const int64_t *, double2 *, double *, int32_t *, int32_t *, int32_t *,
                              int32_t *, int32_t *, int32_t *, int32_t *, unsigned int *);
     const kernel_t kern =
-        fixed_nc ? (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 256> : rrtstar_kernel<true, false, 256>)
-                               : (trace ? rrtstar_kernel<false, true, 256> : rrtstar_kernel<false, false, 256>))
-                 : (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 0> : rrtstar_kernel<true, false, 0>)
-                               : (trace ? rrtstar_kernel<false, true, 0> : rrtstar_kernel<false, false, 0>));
+        p.resume
+            ? (fixed_nc ? (p.rrt_only ? rrtstar_kernel<true, false, 256, true> : rrtstar_kernel<false, false, 256, true>)
+                        : (p.rrt_only ? rrtstar_kernel<true, false, 0, true> : rrtstar_kernel<false, false, 0, true>))
+            : fixed_nc ? (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 256> : rrtstar_kernel<true, false, 256>)
+                                     : (trace ? rrtstar_kernel<false, true, 256> : rrtstar_kernel<false, false, 256>))
+                       : (p.rrt_only ? (trace ? rrtstar_kernel<true, true, 0> : rrtstar_kernel<true, false, 0>)
+                                     : (trace ? rrtstar_kernel<false, true, 0> : rrtstar_kernel<false, false, 0>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_kernel)");
     int dev = 0, sms = 0, per_sm = 0;

@@ -66,6 +66,7 @@ class RRTStarBatch:
             self.sample_stream = torch.from_numpy(ss).to(self.device)
         self.upload()
         self.result = None
+        self._iters_done = 0
 
     # ---- data movement ----
     def upload(self):
@@ -84,6 +85,28 @@ class RRTStarBatch:
                                      self.near_r2, self.sample_stream, self.sobol_offset,
                                      want_trace=want_trace,
                                      out=self.result if (self.result is not None and not want_trace) else None)
+        return self.result
+
+    def step(self, iters: int):
+        """Incremental planning: `iters` MORE iterations on the trees the previous step() left on the GPU (the first call
+        starts them).  The constructor's max_iter is the total budget; k steps of m iterations build exactly the tree of
+        one run of k * m iterations (same in-kernel coin / Sobol streams, or the next slice of the given sample stream)."""
+        done = getattr(self, "_iters_done", 0)
+        iters = int(iters)
+        if iters < 0 or done + iters > self.max_iter:
+            raise _lib.RrtkError("step: the total would exceed the max_iter the batch was built for")
+        p = self.params
+        total = p.max_iter
+        stream = None
+        if self.sample_stream is not None:
+            stream = self.sample_stream[:, done:done + iters].contiguous()
+        p.max_iter, p.resume, p.iter_offset = iters, int(done > 0), done
+        try:
+            self.result = engine.run_dev(p, self.start_goal, self.obstacles, self.n_obs, self.near_r2, stream,
+                                         self.sobol_offset, out=self.result if done > 0 else None)
+        finally:
+            p.max_iter, p.resume, p.iter_offset = total, 0, 0
+        self._iters_done = done + iters
         return self.result
 
     def planning(self, animation=False):

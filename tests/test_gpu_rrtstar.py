@@ -286,3 +286,35 @@ def test_steer_collide_primitive_matches_the_port():
             bad += r["free"][k] != P.collision_free(px, py, obs, rr)
             bad += r["inside"][k] != P.inside_play_area(ex, ey, play)
         assert bad == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler", ["sobol", "uniform", "stream"])
+def test_incremental_steps_build_the_same_trees(sampler):
+    """rrtk_rrtstar_run_dev with resume = 1: 4 steps of 150 iterations == one run of 600, bit for bit."""
+    import rrtk
+    from rrtk import workloads as W
+    cfg = W.C2
+    Q, iters = 12, 600
+    rows = W.c2_rows(list(range(Q)), 64)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1)); goals = np.tile(np.array(cfg["goal"]), (Q, 1))
+    stream = None
+    if sampler == "stream":
+        stream = np.random.default_rng(3).uniform(-2, 15, (Q, iters, 2))
+    mk = lambda: rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],  # noqa: E731
+                                   cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], sampler,
+                                   cfg["connect_circle_dist"], True, seed=7, sample_stream=stream)
+    a = mk(); ra = a.run()
+    b = mk()
+    for _ in range(4):
+        rb = b.step(150)
+    n = ra.n_nodes.cpu().numpy()
+    assert np.array_equal(n, rb.n_nodes.cpu().numpy()) and n.min() > 100
+    assert np.array_equal(ra.goal_index.cpu().numpy(), rb.goal_index.cpu().numpy())
+    xa, xb = ra.xy.cpu().numpy(), rb.xy.cpu().numpy()
+    ca, cb = ra.cost.cpu().numpy(), rb.cost.cpu().numpy()
+    pa, pb = ra.parent.cpu().numpy(), rb.parent.cpu().numpy()
+    for q in range(Q):
+        k = n[q]
+        assert np.array_equal(xa[q, :k], xb[q, :k]) and np.array_equal(ca[q, :k], cb[q, :k]) and np.array_equal(pa[q, :k], pb[q, :k])
+    assert a.planning() == b.result.paths()
