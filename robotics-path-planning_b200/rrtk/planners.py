@@ -233,3 +233,13 @@ class RRTStar(RRT):
     def search_best_goal_node(self):
         """Index chosen by the kernel's search_best_goal_node (rrt_04:1284-1312), or None."""
         return self.goal_index
+
+    @staticmethod
+    def planning_batch(starts, goals, obstacle_lists, rand_area, **kw):
+        """Q independent queries in one launch: the constructor's keywords with starts / goals [Q, 2] and one
+        obstacle list per query; returns the list of paths `planning()` would return query by query (goal -> start, or
+        None).  Sampling is in-kernel (`sampler="sobol"` / `"uniform"`, per-query streams), see rrtk.RRTStarBatch."""
+        from .batch import RRTStarBatch
+        if "sobol_sampler" in kw:
+            kw["sampler"] = "sobol" if kw.pop("sobol_sampler") else "uniform"
+        return RRTStarBatch(starts, goals, obstacle_lists, rand_area, **kw).planning()

@@ -318,3 +318,14 @@ def test_incremental_steps_build_the_same_trees(sampler):
         k = n[q]
         assert np.array_equal(xa[q, :k], xb[q, :k]) and np.array_equal(ca[q, :k], cb[q, :k]) and np.array_equal(pa[q, :k], pb[q, :k])
     assert a.planning() == b.result.paths()
+
+
+@pytest.mark.gpu
+def test_planning_batch_entry_point():
+    import rrtk
+    obs = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+    paths = rrtk.RRTStar.planning_batch([[0.0, 0.0]] * 4, [[6.0, 10.0]] * 4, [obs] * 4, [-2, 15], expand_dis=1.0,
+                                        path_resolution=0.1, max_iter=400, robot_radius=0.6, sobol_sampler=True,
+                                        search_until_max_iter=True, play_area=[0, 10, 0, 14])
+    assert len(paths) == 4 and all(p is None or (p[0] == [6.0, 10.0] and p[-1] == [0.0, 0.0]) for p in paths)
+    assert any(p is not None for p in paths)
