@@ -66,7 +66,7 @@ struct BitState {
     double *k_x, *k_y, *k_h;             //   quantised coordinates, h(id, goal)
     int *k_haspar, *par_order, *tv, *te_v, *te_x, *vq, *eq_v, *open_, *flag;
     double *eq_x, *eq_c, *eq_h;          // edge queue: target id, dist(e0, e1), h(e1, goal)
-    int n_s, n_k, n_par, n_v, n_te, n_vq, n_eq;
+    int n_s, n_k, n_par, n_v, n_te, n_vq, n_eq, n_eq_live;
 };
 
 static __device__ __noinline__ void bit_samples_set(BitState &S, const BitGrid &g, int scap, double id, double x, double y,
@@ -132,17 +132,13 @@ static __device__ __noinline__ void bit_erase_int(int *a, int n, int pos, int la
         __syncwarp();
     }
 }
-static __device__ __noinline__ void bit_erase_edge(BitState &S, int pos, int lane) {
-    const int n = S.n_eq;
-    for (int b0 = pos; b0 + 1 < n; b0 += 32) {
-        const int j = b0 + lane;
-        int t = 0;
-        double u = 0.0, c = 0.0, h = 0.0;
-        if (j + 1 < n) { t = S.eq_v[j + 1]; u = S.eq_x[j + 1]; c = S.eq_c[j + 1]; h = S.eq_h[j + 1]; }
-        __syncwarp();
-        if (j + 1 < n) { S.eq_v[j] = t; S.eq_x[j] = u; S.eq_c[j] = c; S.eq_h[j] = h; }
-        __syncwarp();
-    }
+// edge_queue.remove(edge): the slot becomes a tombstone (eq_v = -1) -- order is kept without shifting the queue; n_eq counts
+// slots, n_eq_live the edges.  Every scan skips tombstones; "Nothing good" empties the slots; the slots are compacted once at
+// the end of the run.
+static __device__ __forceinline__ void bit_erase_edge(BitState &S, int pos, int lane) {
+    if (lane == 0) S.eq_v[pos] = -1;
+    S.n_eq_live--;
+    __syncwarp();
 }
 
 // update_graph (:524-552).  flag[slot]: bit 0 = in closedSet, bit 1 = in openSet.
@@ -224,7 +220,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         S.k_haspar = w; w += kcap; S.par_order = w; w += kcap; S.tv = w; w += kcap; S.te_v = w; w += kcap; S.te_x = w; w += kcap;
         S.vq = w; w += kcap; S.open_ = w; w += kcap; S.flag = w; w += kcap; S.eq_v = w;
     }
-    S.n_s = S.n_k = S.n_par = S.n_v = S.n_te = S.n_vq = S.n_eq = 0;
+    S.n_s = S.n_k = S.n_par = S.n_v = S.n_te = S.n_vq = S.n_eq = S.n_eq_live = 0;
     const double sx = start_goal[4 * q], sy = start_goal[4 * q + 1], gx = start_goal[4 * q + 2], gy = start_goal[4 * q + 3];
     const double *rot = rot_all + 4 * (size_t)q;
     const double4 *obs = obstacles + (size_t)q * p.obs_stride;
@@ -265,7 +261,8 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
     int iterations = 0, found_goal = 0, n_batches = 0, n_reset = 0, n_skipped = 0, n_expand = 0;
     bool index_error = false;
     while (ok && !status && iterations < p.max_iter) {
-        if (S.n_vq == 0 && S.n_eq == 0) {  // setup_sample (:218-234)
+        if (S.n_vq == 0 && S.n_eq_live == 0) {  // setup_sample (:218-234)
+            S.n_eq = 0;
             r = 2.0;
             n_batches++;
             if (n_batches >= 2 && iterations == 0) { status |= RRTK_BIT_LIVELOCK; break; }  // the reference never returns
@@ -290,9 +287,10 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             warp_argmin(vmin, vbest);
             if (S.n_vq == 0) vmin = CUDART_INF;
             double emax = CUDART_INF;
-            if (S.n_eq > 0) {
+            if (S.n_eq_live > 0) {
                 emax = -CUDART_INF;
                 for (int j = lane; j < S.n_eq; j += 32) {
+                    if (S.eq_v[j] < 0) continue;
                     const double val = bit_edge_value(S, j);
                     emax = val > emax ? val : emax;
                 }
@@ -330,6 +328,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
                 const int pos = S.n_eq + __popc(m & ((1u << lane) - 1u));
                 if (take && pos < ecap) { S.eq_v[pos] = vs; S.eq_x[pos] = sid; S.eq_c[pos] = dvs; S.eq_h[pos] = hs; }
                 S.n_eq += __popc(m);
+                S.n_eq_live += __popc(m);
             }
             __syncwarp();
             if (S.n_eq > ecap) { status |= RRTK_BIT_EDGE_OVERFLOW; break; }
@@ -339,6 +338,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         double ebv = CUDART_INF;
         int eb = 0x7fffffff;
         for (int j = lane; j < S.n_eq; j += 32) {
+            if (S.eq_v[j] < 0) continue;
             const double val = bit_edge_value(S, j);
             if (eb == 0x7fffffff || val < ebv) { ebv = val; eb = j; }
         }
@@ -348,7 +348,6 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         const double d01 = S.eq_c[eb], h1 = S.eq_h[eb];
         __syncwarp();
         bit_erase_edge(S, eb, lane);
-        S.n_eq--;
         const double est_v = S.k_g[e0s] + d01 + h1;
         const double est_e = bit_norm2(S.k_x[e0s] - S.k_x[s_slot], S.k_y[e0s] - S.k_y[s_slot]) + d01 + h1;
         const double actual = S.k_g[e0s] + d01, gg = S.k_g[0];
@@ -440,11 +439,11 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
                         const unsigned m = __ballot_sync(FULL, j < S.n_eq && S.eq_v[j] == le && S.eq_x[j] == nid);
                         if (m) pos = b0 + __ffs(m) - 1;
                     }
-                    if (pos >= 0) { bit_erase_edge(S, pos, lane); S.n_eq--; }
+                    if (pos >= 0) bit_erase_edge(S, pos, lane);
                 }
             }
         } else {  // "Nothing good"
-            S.n_eq = 0; S.n_vq = 0;
+            S.n_eq = 0; S.n_eq_live = 0; S.n_vq = 0;
             n_reset++;
         }
         iterations++;
@@ -485,6 +484,22 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         }
         plen = __shfl_sync(FULL, plen, 0);
         status = __shfl_sync(FULL, status, 0);
+    }
+    {   // compact the edge queue (drop the tombstones, keep the order) so that the workspace holds the list as it is
+        int w = 0;
+        for (int b0 = 0; b0 < S.n_eq && b0 < ecap; b0 += 32) {
+            const int j = b0 + lane;
+            const bool live = j < S.n_eq && j < ecap && S.eq_v[j] >= 0;
+            int v = 0;
+            double x = 0.0;
+            if (live) { v = S.eq_v[j]; x = S.eq_x[j]; }
+            const unsigned m = __ballot_sync(FULL, live);
+            __syncwarp();
+            if (live) { const int d = w + __popc(m & ((1u << lane) - 1u)); S.eq_v[d] = v; S.eq_x[d] = x; }
+            w += __popc(m);
+            __syncwarp();
+        }
+        S.n_eq = w;
     }
     if (lane == 0) {
         int32_t *c = counts_all + (size_t)q * 12;
