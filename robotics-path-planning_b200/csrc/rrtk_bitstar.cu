@@ -259,7 +259,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
     bool ok = bit_informed_sample(S, p, g, 200, CUDART_INF, c_min, xc, yc, rot, p.min_rand, p.max_rand, draws, &used, lane, &status);
     double r = CUDART_INF;
     int iterations = 0, found_goal = 0, n_batches = 0, n_reset = 0, n_skipped = 0, n_expand = 0;
-    bool index_error = false;
+    bool index_error = false, goal_in_tree = s_slot == 0;
     while (ok && !status && iterations < p.max_iter) {
         if (S.n_vq == 0 && S.n_eq_live == 0) {  // setup_sample (:218-234)
             S.n_eq = 0;
@@ -426,7 +426,21 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             S.n_v++; S.n_vq++; S.n_te++;
             if (nid == goal_id || e0 == goal_id) found_goal = 1;
             __syncwarp();
-            bit_update_graph(S, goal_id, s_slot, lane);
+            // update_graph (:524-552) relabels the TREE from the start: every vertex is reached through its only tree
+            // parent, so g = g[parent] + dist -- the value it already has -- f = g + h and nodes[v] = parent.  Until the goal is a
+            // tree vertex nothing stops the pass, it reaches every vertex, and all of them but the new one already hold exactly
+            // these values: the pass reduces to labelling the new vertex.  Once the goal is in the tree the pass stops when the
+            // goal is popped (vertices behind it keep their stale f / miss their nodes entry), so it is run as written.
+            if (ns == 0) goal_in_tree = true;
+            if (goal_in_tree) {
+                bit_update_graph(S, goal_id, s_slot, lane);
+            } else if (lane == 0) {
+                S.k_f[ns] = S.k_g[ns] + S.k_h[ns];
+                S.k_par[ns] = e0;
+                S.k_haspar[ns] = 1;
+                S.par_order[S.n_par] = ns;
+            }
+            if (!goal_in_tree) S.n_par++;
             __syncwarp();
             // remove_queue (:343-351).  Edges of the queue are unique (a vertex is expanded once per queue lifetime), so
             // the loop over the mutating list reduces to: if g[nid] (+ 0) >= g[goal], drop (lastEdge, nid) when present
