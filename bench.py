@@ -363,6 +363,8 @@ def main():
         fp64_peak, fp32_peak = fma_peak(1), fma_peak(0)
 
         nn = nn_roofline(torch, L, dev, args.nn_nodes, peaks)
+        # SURVEY 8d's second size: 10^6 nodes (8 MB, L2-resident -- launch- and L2-bound, reported as a detail only)
+        nn["detail"]["n_1e6"] = nn_roofline(torch, L, dev, 1_000_000, peaks)["detail"]
 
         # algorithmic work of one launch (DESIGN.md "Roofline"): the reference's brute-force FP64
         # point-circle tests and node-distance evaluations (counted offline, see ALGORITHMIC_FLOP_PER_ITER)
