@@ -320,6 +320,22 @@ def main():
         eb.record()
         eb.synchronize()                                 # the caller holds the paths in host memory here
         return ea.elapsed_time(eb), (time.perf_counter() - w0) * 1e3
+    # the same call recorded once as a CUDA graph (RRTStarBatch.capture): one launch per step instead of ~10 enqueues, so
+    # a descheduled host thread cannot open a gap between the copies and the kernel; falls back to the plain call
+    graph_ok = False
+    try:
+        batch.capture(h_path, h_plen, path_cap)
+        graph_ok = True
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write(f"e2e: CUDA graph capture failed ({exc!r}); timing the plain call\n")
+    if graph_ok:
+        def e2e_step():  # noqa: F811
+            w0 = time.perf_counter()
+            ea.record()
+            batch.replay()
+            eb.record()
+            eb.synchronize()
+            return ea.elapsed_time(eb), (time.perf_counter() - w0) * 1e3
     for _ in range(max(3, args.warmup)):                 # untimed: allocator / pinned-buffer warm-up
         e2e_step()
     barrier()
@@ -333,6 +349,7 @@ def main():
     e2e = dict(value=total_iters / t_e2e, unit=UNIT, h2d_bytes_per_step=batch.h2d_bytes() * world,
                d2h_bytes_per_step=(h_path.numel() * 8 + h_plen.numel() * 4) * world,
                ms_per_step=1e3 * t_e2e / args.steps, timing="CUDA events around upload + kernel + path extraction + D2H",
+               call="RRTStarBatch.replay() (the call captured as a CUDA graph)" if graph_ok else "RRTStarBatch.upload / run / paths_device",
                wall_value=total_iters / t_e2e_wall, wall_ms_per_step=1e3 * t_e2e_wall / args.steps,
                result="paths [Q, 256, 2] + lengths, pinned host buffers")
     found = int((h_plen.numpy() > 0).sum())

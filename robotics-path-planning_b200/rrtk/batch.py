@@ -109,6 +109,29 @@ class RRTStarBatch:
         self._iters_done = done + iters
         return self.result
 
+    # ---- one planning call as a CUDA graph: upload -> kernel -> path extraction -> download ----
+    def capture(self, h_path, h_plen, path_cap: int):
+        """Record `upload(); run(); paths_device(path_cap)` and the copies of the paths into the PINNED host tensors
+        `h_path` [Q, path_cap, 2] / `h_plen` [Q] as one CUDA graph; `replay()` then enqueues the whole call with a single
+        launch, so no host work sits between the copies and the kernel.  Inputs are read from the pinned staging tensors
+        (h_start_goal, h_obstacles, h_n_obs) at replay time: refill them in place to plan a new scenario."""
+        import torch
+        self.run()                                   # allocate the result tensors outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.upload()
+            r = self.run()
+            path, plen = r.paths_device(path_cap)
+            h_path.copy_(path, non_blocking=True)
+            h_plen.copy_(plen, non_blocking=True)
+        self._graph = g
+        return g
+
+    def replay(self):
+        """Enqueue the captured call on the current stream (asynchronous; synchronise before reading the host tensors)."""
+        self._graph.replay()
+
     def planning(self, animation=False):
         """Paths for every query: list of `[[x, y], ...]` (goal -> start) or None."""
         return self.run().paths()

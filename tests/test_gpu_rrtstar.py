@@ -329,3 +329,38 @@ def test_planning_batch_entry_point():
                                         search_until_max_iter=True, play_area=[0, 10, 0, 14])
     assert len(paths) == 4 and all(p is None or (p[0] == [6.0, 10.0] and p[-1] == [0.0, 0.0]) for p in paths)
     assert any(p is not None for p in paths)
+
+
+@pytest.mark.gpu
+def test_captured_graph_replay_matches_plain_call():
+    """RRTStarBatch.capture / replay: the whole call as one CUDA graph gives the plain call's paths, also after the pinned
+    inputs are refilled in place."""
+    import torch
+    import rrtk
+    from rrtk import workloads as W
+    cfg = W.C2
+    Q, iters, cap = 16, 300, 128
+    rows = W.c2_rows(list(range(Q)), 64)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1)); goals = np.tile(np.array(cfg["goal"]), (Q, 1))
+    mk = lambda: rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],  # noqa: E731
+                                   cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol",
+                                   cfg["connect_circle_dist"], True, seed=3)
+    a = mk()
+    want_path, want_len = a.run().paths_device(cap)
+    b = mk()
+    h_path = torch.empty((Q, cap, 2), dtype=torch.float64).pin_memory()
+    h_plen = torch.empty((Q,), dtype=torch.int32).pin_memory()
+    b.capture(h_path, h_plen, cap)
+    for _ in range(2):
+        h_plen.zero_()
+        b.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(h_plen, want_len.cpu())
+        for q in range(Q):
+            k = int(h_plen[q])
+            assert torch.equal(h_path[q, :k], want_path[q, :k].cpu())
+    # a new scenario through the same graph: swap two queries' obstacle rows in the pinned staging tensor
+    b.h_obstacles[[0, 1]] = b.h_obstacles[[1, 0]]
+    b.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(h_plen[2:], want_len.cpu()[2:])
