@@ -307,6 +307,7 @@ int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goa
     if (p->n_queries < 0 || p->max_iter < 0 || p->node_cap < 1 || p->obs_stride < 0) return set_error(RRTK_ERR_INVALID, "bad sizes");
     if (p->near_cap < 32 || (p->near_cap & 31)) return set_error(RRTK_ERR_INVALID, "near_cap must be a positive multiple of 32");
     if (!(p->curvature > 0.0) || !(p->step_size > 0.0)) return set_error(RRTK_ERR_INVALID, "curvature and step_size must be > 0");
+    if (p->rs_cost != 0 && p->rs_cost != 1) return set_error(RRTK_ERR_INVALID, "rs_cost must be 0 or 1");
     if (p->n_queries == 0) return RRTK_OK;
     if (!start_goal6 || !n_obs || !near_r2 || !xy || !yaw || !cost || !parent || !edge_from || !edge_to || !n_nodes ||
         !iters_done || !goal_index || !status || !workspace || (p->max_iter > 0 && !stream3) ||
@@ -315,7 +316,6 @@ int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goa
     cudaStream_t s = (cudaStream_t)stream;
     DevCounter ctr(s);
     if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
-    if (p->rs_cost != 0 && p->rs_cost != 1) return set_error(RRTK_ERR_INVALID, "rs_cost must be 0 or 1");
     return launch_rrtstar_rs(*p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from,
                                  edge_to, n_nodes, iters_done, goal_index, status, workspace, ctr.ptr, s);
 }

@@ -107,3 +107,30 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_new_entry_points_reject_bad_arguments_without_gpu():
+    """Argument validation of the round-1 additions happens before any CUDA call."""
+    from rrtk import _lib
+    L = _lib.lib()
+    p = _lib.ClosedLoopParams()
+    p.n_courses, p.course_cap, p.traj_cap = 4, 2, 100                      # extend_path needs 3 course points
+    assert L.rrtk_closed_loop_dev(C.byref(p), *([None] * 10)) == -1 and b"course_cap" in L.rrtk_last_error()
+    p.course_cap = 16
+    assert L.rrtk_closed_loop_dev(C.byref(p), *([None] * 10)) == -1 and b"NULL" in L.rrtk_last_error()
+    p.n_courses = 0
+    assert L.rrtk_closed_loop_dev(C.byref(p), *([None] * 10)) == 0
+    b = _lib.BitStarParams()
+    b.n_queries, b.max_iter, b.vertex_cap, b.sample_cap, b.edge_cap, b.path_cap, b.n_draws = 2, 10, 12, 64, 64, 14, 100
+    b.min_rand, b.max_rand, b.num_cells = 15.0, -2.0, 1700.0               # inverted randArea
+    assert L.rrtk_bitstar_run_dev(C.byref(b), *([None] * 12)) == -1 and b"randArea" in L.rrtk_last_error()
+    b.min_rand, b.max_rand = -2.0, 15.0
+    assert L.rrtk_bitstar_run_dev(C.byref(b), *([None] * 12)) == -1 and b"NULL" in L.rrtk_last_error()
+    assert L.rrtk_steer_collide_dev(4, None, None, 1.0, 0.0, None, None, 0, *([None] * 8)) == -1 and b"path_resolution" in L.rrtk_last_error()
+    assert L.rrtk_steer_collide_dev(0, None, None, 1.0, 0.1, None, None, 0, *([None] * 8)) == 0
+    d = _lib.DubinsParams()
+    d.n_queries, d.max_iter, d.node_cap, d.near_cap, d.curvature, d.step_size, d.rs_cost = 1, 5, 11, 32, 1.0, 0.2, 7
+    assert L.rrtk_rrtstar_rs_run_dev(C.byref(d), *([1] * 16), None) == -1 and b"rs_cost" in L.rrtk_last_error()
+    r = _lib.RRTStarParams()
+    r.n_queries, r.max_iter, r.node_cap, r.near_cap, r.path_resolution, r.expand_dis, r.resume = 1, 5, 6, 32, 0.1, 1.0, 3
+    assert L.rrtk_rrtstar_run_dev(C.byref(r), *([None] * 16)) == -1 and b"resume" in L.rrtk_last_error()
