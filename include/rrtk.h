@@ -419,7 +419,7 @@ typedef struct rrtk_bitstar_params {
 } rrtk_bitstar_params;
 #define RRTK_BITSTAR_WS_DOUBLES(vertex_cap, sample_cap, edge_cap) \
     (6 * (size_t)(sample_cap) + 7 * ((size_t)(vertex_cap) + 2) + 3 * (size_t)(edge_cap))
-#define RRTK_BITSTAR_WS_INTS(vertex_cap, sample_cap, edge_cap) (8 * ((size_t)(vertex_cap) + 2) + (size_t)(edge_cap))
+#define RRTK_BITSTAR_WS_INTS(vertex_cap, sample_cap, edge_cap) (11 * ((size_t)(vertex_cap) + 2) + (size_t)(edge_cap))
 RRTK_API int rrtk_bitstar_run_dev(const rrtk_bitstar_params *p, const double *start_goal, const double *rot,
                                   const double *obstacles, const int32_t *n_obs, const double *draws, double *ws_d,
                                   int32_t *ws_i, double *path, int32_t *counts, double *g_goal, int32_t *status, void *stream);

@@ -65,6 +65,7 @@ struct BitState {
     double *k_id, *k_g, *k_f, *k_par;    // score table: slot 0 = goal, 1 = start, then tree vertices
     double *k_x, *k_y, *k_h;             //   quantised coordinates, h(id, goal)
     int *k_haspar, *par_order, *tv, *te_v, *te_x, *vq, *eq_v, *open_, *flag;
+    int *ch_first, *ch_last, *ch_next;   // children of a tree vertex in add_edge order (= its adjacency list minus the parent)
     double *eq_x, *eq_c, *eq_h;          // edge queue: target id, dist(e0, e1), h(e1, goal)
     int n_s, n_k, n_par, n_v, n_te, n_vq, n_eq, n_eq_live;
 };
@@ -167,35 +168,29 @@ static __device__ __noinline__ void bit_update_graph(BitState &S, double goal_id
         if (lane == 0) S.flag[cur] |= 1;
         __syncwarp();
         const double gcur = S.k_g[cur], idcur = S.k_id[cur], xcur = S.k_x[cur], ycur = S.k_y[cur];
-        for (int b0 = 0; b0 < S.n_te; b0 += 32) {  // adjacency of `cur` in add_edge order
-            const int c = b0 + lane;
-            int suc = -1;
-            if (c < S.n_te) {
-                if (S.te_v[c] == cur) suc = S.te_x[c];
-                else if (S.te_x[c] == cur) suc = S.te_v[c];
-            }
-            bool act = suc >= 0 && !(S.flag[suc] & 1);
-            bool set_ = false, app = false;
-            double gs = 0.0;
-            if (act) {
-                gs = gcur + bit_norm2(S.k_x[suc] - xcur, S.k_y[suc] - ycur);
-                if (!(S.flag[suc] & 2)) { app = true; set_ = true; }
-                else if (!(gs >= S.k_g[suc])) set_ = true;
-            }
-            const unsigned am = __ballot_sync(FULL, app);
-            if (app) { S.open_[n_open + __popc(am & ((1u << lane) - 1u))] = suc; S.flag[suc] |= 2; }
-            n_open += __popc(am);
-            // nodes[successor] = currId: first assignment fixes the dict position (only the order of the output)
-            const unsigned nm = __ballot_sync(FULL, set_ && !S.k_haspar[suc < 0 ? 0 : suc]);
-            if (set_) {
-                if (!S.k_haspar[suc]) { S.par_order[S.n_par + __popc(nm & ((1u << lane) - 1u))] = suc; S.k_haspar[suc] = 1; }
-                S.k_g[suc] = gs;
-                S.k_f[suc] = gs + S.k_h[suc];
-                S.k_par[suc] = idcur;
-            }
-            S.n_par += __popc(nm);
+        // adjacency of `cur` in add_edge order = its parent (closed: `cur` was reached through it) followed by its children
+        for (int suc = S.ch_first[cur]; suc >= 0; suc = S.ch_next[suc]) {
+            const int fl = S.flag[suc];
+            if (fl & 1) continue;
+            const double gs = gcur + bit_norm2(S.k_x[suc] - xcur, S.k_y[suc] - ycur);
+            bool set_ = false;
+            if (!(fl & 2)) set_ = true;
+            else if (!(gs >= S.k_g[suc])) set_ = true;
+            const bool first_par = set_ && !S.k_haspar[suc];
             __syncwarp();
+            if (lane == 0) {
+                if (!(fl & 2)) { S.open_[n_open] = suc; S.flag[suc] = fl | 2; }
+                if (set_) {
+                    if (first_par) { S.par_order[S.n_par] = suc; S.k_haspar[suc] = 1; }
+                    S.k_g[suc] = gs;
+                    S.k_f[suc] = gs + S.k_h[suc];
+                    S.k_par[suc] = idcur;
+                }
+            }
+            if (!(fl & 2)) n_open++;
+            if (first_par) S.n_par++;
         }
+        __syncwarp();
     }
 }
 
@@ -218,7 +213,8 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
         S.eq_c = d; d += ecap; S.eq_h = d;
         int *w = ws_i + (size_t)q * RRTK_BITSTAR_WS_INTS(vcap, scap, ecap);
         S.k_haspar = w; w += kcap; S.par_order = w; w += kcap; S.tv = w; w += kcap; S.te_v = w; w += kcap; S.te_x = w; w += kcap;
-        S.vq = w; w += kcap; S.open_ = w; w += kcap; S.flag = w; w += kcap; S.eq_v = w;
+        S.vq = w; w += kcap; S.open_ = w; w += kcap; S.flag = w; w += kcap; S.eq_v = w; w += ecap;
+        S.ch_first = w; w += kcap; S.ch_last = w; w += kcap; S.ch_next = w;
     }
     S.n_s = S.n_k = S.n_par = S.n_v = S.n_te = S.n_vq = S.n_eq = S.n_eq_live = 0;
     const double sx = start_goal[4 * q], sy = start_goal[4 * q + 1], gx = start_goal[4 * q + 2], gy = start_goal[4 * q + 3];
@@ -229,7 +225,7 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
     BitGrid g;
     g.lower = p.min_rand; g.res = 0.01; g.nc = p.num_cells;
     int status = 0, used = 0;
-    for (int i = lane; i < kcap; i += 32) S.k_haspar[i] = 0;
+    for (int i = lane; i < kcap; i += 32) { S.k_haspar[i] = 0; S.ch_first[i] = -1; S.ch_last[i] = -1; S.ch_next[i] = -1; }
     __syncwarp();
 
     const double start_id = bit_id_of(g, sx, sy), goal_id = bit_id_of(g, gx, gy);
@@ -420,6 +416,8 @@ bitstar_kernel(rrtk_bitstar_params p, const double *__restrict__ start_goal, con
             if (lane == 0) {
                 S.tv[S.n_v] = ns; S.vq[S.n_vq] = ns;
                 S.te_v[S.n_te] = e0s; S.te_x[S.n_te] = ns;
+                if (S.ch_first[e0s] < 0) S.ch_first[e0s] = ns; else S.ch_next[S.ch_last[e0s]] = ns;
+                S.ch_last[e0s] = ns;
                 S.k_g[ns] = gsc + S.k_g[e0s];
                 S.k_f[ns] = gsc + bit_dist(g, nid, goal_id);
             }

@@ -46,7 +46,7 @@ def run_batch(starts, goals, obstacle_lists, rand_area, max_iter, draws, sample_
     p.num_cells = float(np.ceil((rand_area[1] - rand_area[0]) / 0.01))            # RTree.__init__ (:50-52)
     rot = np.array([rotation(s, g) for s, g in zip(starts, goals)], dtype=np.float64)
     nd = 6 * sample_cap + 7 * (vcap + 2) + 3 * edge_cap                           # RRTK_BITSTAR_WS_DOUBLES
-    ni = 8 * (vcap + 2) + edge_cap                                                # RRTK_BITSTAR_WS_INTS
+    ni = 11 * (vcap + 2) + edge_cap                                               # RRTK_BITSTAR_WS_INTS
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     with torch.cuda.device(dev):
         d_sg, d_rot, d_obs, d_cnt, d_draws = t(np.hstack([starts, goals])), t(rot), t(rows), t(counts), t(draws)
