@@ -1,0 +1,175 @@
+"""GPU tests at BASELINE.json's FULL sizes (-m gpu).  The oracle cannot finish these sizes in seconds, so they are
+checked through size-independent properties of the domain plus an oracle spot check on a few whole queries:
+
+  config 2 (4096 queries x 256 circles x 2000 iterations, the bench workload, same seeds):
+    every tree is a tree (root, parents in range, no cycles), every cost is its parent's cost plus the edge length
+    (calc_new_cost, rrt_04:1376-1378; propagate_cost_to_leaves, :1380-1385), no node lies inside a circle
+    (check_collision, rrt_04:1219-1232 tests the end point of every accepted edge), no edge is longer than steer +
+    snap allow (rrt_04:1086-1115), the extracted course runs goal -> start along parents (rrt_04:1117-1125), the
+    launch is deterministic although the work queue hands queries to warps in a different order each time, and
+    four whole queries equal the C oracle bit for bit.
+  config 5 (8192 x 8192 joint grid x 64 obstacle sets):
+    theta_list (arm02:95) of M = 8192 sampled every 8th angle is theta_list of M = 1024 exactly (a power-of-two
+    rescale of `2 * i * pi / M`), so grid_8192[:, ::8, ::8] must equal grid_1024 bit for bit; set 0 at M = 512 is
+    compared with the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2_full():
+    import torch
+    import rrtk
+    from rrtk import workloads as W
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    cfg = W.C2
+    Q, iters, n_obs = cfg["n_queries"], cfg["max_iter"], cfg["n_obs"]
+    qids = list(range(Q))
+    rows = W.c2_rows(qids, n_obs)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1))
+    goals = np.tile(np.array(cfg["goal"]), (Q, 1))
+    batch = rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],
+                              cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol",
+                              cfg["connect_circle_dist"], True, seed=0xC2,
+                              sobol_offset=np.asarray(qids, dtype=np.int64) * iters)
+    res = batch.run()
+    torch.cuda.synchronize()
+    return torch, cfg, batch, res, rows
+
+
+def _valid_mask(torch, res):
+    cap = res.parent.shape[1]
+    return torch.arange(cap, device=res.parent.device)[None, :] < res.n_nodes[:, None].long()
+
+
+def test_c2_full_every_query_ran_to_the_end(c2_full):
+    torch, cfg, batch, res, _ = c2_full
+    assert int((res.status != 0).sum()) == 0
+    assert bool((res.iters_done == cfg["max_iter"]).all())
+    n = res.n_nodes
+    assert int(n.min()) >= 2 and int(n.max()) <= cfg["max_iter"] + 1
+    assert int((res.goal_index >= 0).sum()) == cfg["n_queries"]      # every scene of the workload is solvable
+    assert bool((res.goal_index < n).all())
+
+
+def test_c2_full_trees_are_trees_with_consistent_costs(c2_full):
+    torch, cfg, batch, res, _ = c2_full
+    valid = _valid_mask(torch, res)
+    par = res.parent.long()
+    assert bool((par[:, 0] == -1).all())
+    inner = valid.clone(); inner[:, 0] = False
+    assert bool(((par >= 0) & (par < res.n_nodes[:, None].long()))[inner].all())
+    # no cycles: pointer doubling reaches the root from every node in ceil(log2(cap)) rounds
+    p = torch.where(inner, par, torch.zeros_like(par))
+    for _ in range(int(np.ceil(np.log2(par.shape[1]))) + 1):
+        p = torch.gather(p, 1, p)
+    assert bool((p == 0).all())
+    # cost[i] = cost[parent] + |xy[i] - xy[parent]|.  A rewired node whose steer does not snap back onto its old
+    # position (d / resolution within an ulp of an integer) keeps the cost of the ORIGINAL distance, as in the
+    # reference (rrt_04:1361), so a handful of nodes may differ by up to one resolution step; none by more.
+    pc = torch.where(inner, par, torch.zeros_like(par))
+    pxy = torch.gather(res.xy, 1, pc[:, :, None].expand(-1, -1, 2))
+    d = torch.hypot(res.xy[..., 0] - pxy[..., 0], res.xy[..., 1] - pxy[..., 1])
+    err = (res.cost - (torch.gather(res.cost, 1, pc) + d)).abs()[inner]
+    assert bool((res.cost[:, 0] == 0).all())
+    assert float(err.max()) <= cfg["path_resolution"] + 1e-9
+    assert int((err > 1e-9).sum()) <= 1e-3 * err.numel(), int((err > 1e-9).sum())
+    # edge length: steer reaches expand_dis and may snap one resolution step further (rrt_04:1103-1111); rewire and
+    # choose_parent edges stay within the near radius <= expand_dis; one more step each time a parent was moved
+    assert float(d[inner].max()) <= cfg["expand_dis"] + 3 * cfg["path_resolution"] + 1e-9, float(d[inner].max())
+    assert float((d[inner] <= cfg["expand_dis"] + cfg["path_resolution"] + 1e-9).double().mean()) >= 0.999
+    assert float(res.cost[valid].min()) == 0.0
+
+
+def test_c2_full_no_node_inside_a_circle(c2_full):
+    torch, cfg, batch, res, rows = c2_full
+    valid = _valid_mask(torch, res)
+    valid[:, 0] = False                                   # the start is never collision-checked
+    obs = torch.from_numpy(rows).to(res.xy.device)        # [Q, O, 4] = x, y, r, r^2
+    worst = float("inf")
+    for q0 in range(0, obs.shape[0], 128):
+        xy = res.xy[q0:q0 + 128]
+        o = obs[q0:q0 + 128]
+        dx = xy[:, :, None, 0] - o[:, None, :, 0]
+        dy = xy[:, :, None, 1] - o[:, None, :, 1]
+        margin = ((dx * dx + dy * dy) / o[:, None, :, 3]).amin(dim=2)      # > 1 outside every circle
+        worst = min(worst, float(margin[valid[q0:q0 + 128]].min()))
+    assert worst > 1.0 - 1e-12, worst
+
+
+def test_c2_full_courses_follow_parents(c2_full):
+    torch, cfg, batch, res, _ = c2_full
+    path, plen = res.paths_device(path_cap=256)
+    path = path.cpu().numpy(); plen = plen.cpu().numpy()
+    assert (plen >= 2).all() and (plen <= 256).all()
+    xy = res.xy.cpu().numpy(); par = res.parent.cpu().numpy(); gi = res.goal_index.cpu().numpy()
+    for q in range(0, cfg["n_queries"], 97):
+        want = [list(cfg["goal"])]
+        i = gi[q]
+        while par[q, i] >= 0:
+            want.append(xy[q, i].tolist())
+            i = par[q, i]
+        want.append(xy[q, i].tolist())
+        assert path[q, :plen[q]].tolist() == want
+        assert want[-1] == list(cfg["start"])
+
+
+def test_c2_full_launch_is_deterministic(c2_full):
+    torch, cfg, batch, res, _ = c2_full
+    first = [t.clone() for t in (res.xy, res.cost, res.parent, res.n_nodes, res.goal_index)]
+    valid = _valid_mask(torch, res)
+    again = batch.run()
+    torch.cuda.synchronize()
+    assert torch.equal(first[3], again.n_nodes) and torch.equal(first[4], again.goal_index)
+    assert torch.equal(first[2][valid], again.parent[valid])
+    assert torch.equal(first[1][valid], again.cost[valid])
+    assert torch.equal(first[0][valid], again.xy[valid])
+
+
+def test_c2_full_spot_queries_equal_the_oracle(c2_full, oracle_lib):
+    torch, cfg, batch, res, _ = c2_full
+    from rrtk import workloads as W
+    O = oracle_lib
+    picks = [0, 1777, 2368, 4095]       # first, middle, first of the second wave of resident warps, last
+    stream = batch.materialised_stream()
+    for q in picks:
+        s = stream[q].cpu().numpy()
+        p, obs = O.make_params(cfg["start"], cfg["goal"], W.c2_obstacles(q, cfg["n_obs"]).tolist(), cfg["expand_dis"],
+                               cfg["path_resolution"], cfg["max_iter"], None, cfg["robot_radius"],
+                               cfg["connect_circle_dist"], True, math_mode=O.MATH_CR)
+        ref = O.rrtstar_run(p, obs, s, want_trace=False)
+        n = ref["n"]
+        assert int(res.n_nodes[q]) == n
+        assert np.array_equal(res.parent[q, :n].cpu().numpy(), ref["parent"])
+        xy = res.xy[q, :n].cpu().numpy()
+        assert np.array_equal(xy[:, 0], ref["x"]) and np.array_equal(xy[:, 1], ref["y"])
+        assert np.array_equal(res.cost[q, :n].cpu().numpy(), ref["cost"])
+        assert int(res.goal_index[q]) == ref["goal_index"]
+
+
+def test_c5_full_grid_subsamples_to_the_coarse_grid(oracle_lib):
+    import torch
+    from rrtk import arm as A
+    M, S = 8192, 64
+    rng = np.random.default_rng(5)
+    sets = np.concatenate([rng.uniform(-2, 2, (S, 5, 2)), rng.uniform(0.2, 0.7, (S, 5, 1))], axis=2)
+    sets[0] = [[1.75, 0.75, 0.6], [0.55, 1.5, 0.5], [0, -1, 0.7], [0, -0.6, 0.4], [-1, 1., 0.3]]   # arm02:298
+    link = [0.5, 0.5, 0.3, 0.5, 0.1]
+    assert np.array_equal(A.theta_list(M)[::8], A.theta_list(M // 8))
+    fine = A.occupancy_grids_device(link, sets, M)
+    assert fine.shape == (S, M, M) and fine.dtype == torch.uint8
+    assert int(fine.max()) == 1
+    coarse = A.occupancy_grids_device(link, sets, M // 8)
+    assert torch.equal(fine[:, ::8, ::8], coarse)
+    # rows computed as 8 shards (the multi-GPU partition of config 5) equal the whole grid
+    r0 = 3 * (M // 8)
+    shard = A.occupancy_grids_device(link, sets, M, r0, M // 8)
+    assert torch.equal(shard, fine[:, r0:r0 + M // 8])
+    del shard
+    want = oracle_lib.arm_grid(512, link, sets[0], oracle_lib.MATH_CR)
+    assert np.array_equal(fine[0, ::16, ::16].cpu().numpy(), want)
+    # the occupied fraction is resolution-independent to first order
+    f_fine = float(fine[0].float().mean()); f_coarse = float(coarse[0].float().mean())
+    assert abs(f_fine - f_coarse) < 5e-3
