@@ -174,7 +174,7 @@ def reference_arm(args):
                cpu_baseline=dict(last, value=v),
                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                wall_s=time.perf_counter() - t_all)
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,8 +236,22 @@ def measured_peaks():
         return None
 
 
+def _emit(line: str) -> None:
+    """Write the result line to the process's ORIGINAL stdout (see main)."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # stdout carries exactly ONE line, the JSON result: libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, a child process) are sent to stderr for the whole run
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
     import numpy as np
@@ -441,7 +455,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        _emit(json.dumps(out))
 
 
 def _timed(torch, fn, reps=3):
