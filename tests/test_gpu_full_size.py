@@ -173,3 +173,54 @@ def test_c5_full_grid_subsamples_to_the_coarse_grid(oracle_lib):
     # the occupied fraction is resolution-independent to first order
     f_fine = float(fine[0].float().mean()); f_coarse = float(coarse[0].float().mean())
     assert abs(f_fine - f_coarse) < 5e-3
+
+
+def test_c4_full_rrtstar_dubins_batch(oracle_lib):
+    """Config 4 at its full size (1024 queries x 500 iterations, the bench workload of rrt_05:1804-1859's scene):
+    every tree is a tree whose stored edges join the parent's pose to the node's pose (to rounding: rrt_05 steer takes
+    the node pose from the last course sample), a second launch gives identical trees, and every 43rd query equals
+    the C oracle bit for bit."""
+    import math
+    import torch
+    from rrtk import dubins_planner as DP
+    O = oracle_lib
+    Q, iters = 1024, 500
+    rng = np.random.default_rng(7)
+    st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+    coin = rng.integers(0, 101, (Q, iters)) <= 10
+    st[coin] = (10.0, 10.0, 0.0)
+    scene = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)]
+    start, goal = [0.0, 0.0, 0.0], [10.0, 10.0, 0.0]
+    res = DP.run_batch([start] * Q, [goal] * Q, [scene] * Q, 3.0, iters, st)
+    again = DP.run_batch([start] * Q, [goal] * Q, [scene] * Q, 3.0, iters, st)
+    torch.cuda.synchronize()
+    assert len(res) == Q
+    for q, (t, u) in enumerate(zip(res, again)):
+        n = t["n"]
+        assert t["status"] == 0 and t["iters_done"] == iters and 1 <= n <= iters + 1
+        par = t["parent"]
+        assert par[0] == -1 and (par[1:] >= 0).all() and (par[1:] < n).all()
+        anc = np.where(par < 0, 0, par)
+        for _ in range(10):
+            anc = anc[anc]
+        assert (anc == 0).all()                                     # no cycles
+        pose = np.column_stack([t["x"], t["y"], t["yaw"]])
+        # a node's pose is the last sample of its course (within rounding of the requested pose, rrt_05 steer); a
+        # parent re-wired later is replaced by the end of ITS new course, again within rounding
+        assert np.abs(t["edge_to"][1:] - pose[1:]).max(initial=0.0) < 1e-9
+        assert np.abs(t["edge_from"][1:] - pose[par[1:]]).max(initial=0.0) < 1e-9
+        assert (t["cost"][1:] >= t["cost"][par[1:]]).all() and t["cost"][0] == 0.0   # equal: a second node at the goal pose
+        for c in scene:                                             # the end pose of every accepted course is tested
+            assert ((t["x"][1:] - c[0]) ** 2 + (t["y"][1:] - c[1]) ** 2 > c[2] ** 2 * (1 - 1e-12)).all()
+        assert -1 <= t["goal_index"] < n
+        for k in ("x", "y", "yaw", "cost", "parent", "edge_from", "edge_to"):
+            assert np.array_equal(t[k], u[k]), (q, k)
+        assert t["goal_index"] == u["goal_index"]
+    for q in range(0, Q, 43):
+        ref = O.rrtstar_dubins_run(start, goal, scene, 3.0, iters, 0.0, 50.0, 1.0, np.deg2rad(1.0), 0.5, True, st[q],
+                                   O.MATH_CR)
+        t = res[q]
+        assert t["n"] == ref["n"] and t["goal_index"] == ref["goal_index"], q
+        assert np.array_equal(t["parent"], ref["parent"]), q
+        for k in ("x", "y", "yaw", "cost"):
+            assert np.array_equal(t[k], ref[k]), (q, k)
