@@ -224,3 +224,45 @@ def test_c4_full_rrtstar_dubins_batch(oracle_lib):
         assert np.array_equal(t["parent"], ref["parent"]), q
         for k in ("x", "y", "yaw", "cost"):
             assert np.array_equal(t[k], ref[k]), (q, k)
+
+
+def test_c3_full_single_tree_to_a_million_nodes():
+    """Config 3 at its full size: ONE Informed RRT* tree (rrt_07 semantics, the script's 7 circles) grown to 10^6
+    nodes, the bench workload.  The oracle needs O(n^2) for this, so the tree is checked through what every rrt_07
+    tree satisfies: parents in range and acyclic, costs that only go stale upwards (rewire, rrt_07:1145-1168, does not
+    propagate), every edge clear of every circle (segment test, rrt_07:1216-1260), and a returned course whose
+    length is c_best."""
+    import torch
+    from rrtk import informed as INF
+    cap, iters = 1_000_001, 1_700_000
+    rng = np.random.default_rng(9)
+    free = rng.uniform(-2, 15, (iters, 2)); coin = rng.integers(0, 101, iters) <= 10; free[coin] = (6.0, 10.0)
+    ball = rng.random((iters, 2))
+    obs = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+    run = INF.run_tree([0.0, 0.0], [6.0, 10.0], obs, 0.5, iters, free, ball, node_cap=cap)
+    torch.cuda.synchronize()
+    i = run.info
+    n = i["n_nodes"]
+    assert n == cap and i["iters_done"] <= iters
+    par = run.parent[:n].long(); xy = run.xy[:n]; cost = run.cost[:n]
+    assert int(par[0]) == -1 and bool(((par[1:] >= 0) & (par[1:] < n)).all())
+    anc = par.clamp(min=0)
+    for _ in range(21):                                    # 2^21 > 10^6: pointer doubling reaches the root
+        anc = anc[anc]
+    assert bool((anc == 0).all())
+    p = par[1:]
+    w = xy[1:] - xy[p]
+    d = torch.hypot(w[:, 0], w[:, 1])
+    assert float(cost[0]) == 0.0 and bool((cost[1:] >= cost[p] + d - 1e-9).all())
+    # (no bound on the edge length: rrt_07's near radius 50 * sqrt(log(n) / n) is not capped by expand_dis,
+    # rrt_07:1137-1143, so choose_parent / rewire edges of the early tree are long)
+    l2 = (w * w).sum(dim=1).clamp(min=1e-300)
+    for ox, oy, r in obs:
+        c = torch.tensor([ox, oy], dtype=torch.float64, device=xy.device)
+        t = (((c - xy[p]) * w).sum(dim=1) / l2).clamp(0.0, 1.0)
+        dd = ((c - xy[p] - t[:, None] * w) ** 2).sum(dim=1)
+        assert bool((dd > r * r - 1e-9).all())
+    a = run.arrays()
+    path = np.array(a["path"])
+    assert np.isclose(np.hypot(*(path[1:] - path[:-1]).T).sum(), a["c_best"], rtol=1e-12)
+    assert np.hypot(6.0, 10.0) < a["c_best"] < 17.0        # rrt_07's scenario: optimum ~16.9
