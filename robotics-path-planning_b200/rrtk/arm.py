@@ -12,29 +12,42 @@ import numpy as np
 from . import _lib
 
 
-class NLinkArm(object):
-    """Planar arm with an arbitrary number of links (arm02:236-262)."""
+class NLinkArm:
+    """Planar serial arm: same constructor, attributes (`n_links`, `link_lengths`, `joint_angles`, `points`,
+    `end_effector`, `lim`) and methods as arm02:236-262.  Forward kinematics is one prefix sum instead of the reference's
+    per-joint loop: link k points along the sum of the first k joint angles, and a joint vector SHORTER than the link
+    vector (the script passes 2 angles to a 5-link arm, arm02:98) leaves the remaining links collinear, because the
+    reference's `np.sum(joint_angles[:k])` saturates.  The kernel does its own FK; this class is the host-side API shell."""
 
     def __init__(self, link_lengths, joint_angles):
-        self.n_links = len(link_lengths)
-        if self.n_links != len(joint_angles):
+        if len(link_lengths) != len(joint_angles):
             raise ValueError()
+        self.n_links = len(link_lengths)
         self.link_lengths = np.array(link_lengths)
-        self.joint_angles = np.array(joint_angles)
-        self.points = [[0, 0] for _ in range(self.n_links + 1)]
         self.lim = sum(link_lengths)
-        self.update_points()
+        self.points = [[0, 0] for _ in range(self.n_links + 1)]
+        self.update_joints(np.array(joint_angles))
 
     def update_joints(self, joint_angles):
         self.joint_angles = joint_angles
         self.update_points()
 
+    def _headings(self):
+        # heading of link k = sum of the first min(k, len(angles)) joint angles (sequential adds, like np.sum on a
+        # short slice)
+        ang = np.asarray(self.joint_angles, dtype=np.float64).ravel()
+        prefix = np.concatenate(([0.0], np.cumsum(ang)))
+        return prefix[np.minimum(np.arange(1, self.n_links + 1), ang.size)]
+
     def update_points(self):
-        for i in range(1, self.n_links + 1):
-            self.points[i][0] = self.points[i - 1][0] + \
-                self.link_lengths[i - 1] * np.cos(np.sum(self.joint_angles[:i]))
-            self.points[i][1] = self.points[i - 1][1] + \
-                self.link_lengths[i - 1] * np.sin(np.sum(self.joint_angles[:i]))
+        h = self._headings()
+        lengths = np.asarray(self.link_lengths, dtype=np.float64)
+        xs = np.concatenate(([0.0], np.cumsum(lengths * np.cos(h))))
+        ys = np.concatenate(([0.0], np.cumsum(lengths * np.sin(h))))
+        base = self.points[0]
+        for k in range(1, self.n_links + 1):
+            self.points[k][0] = base[0] + xs[k]
+            self.points[k][1] = base[1] + ys[k]
         self.end_effector = np.array(self.points[self.n_links]).T
 
 
