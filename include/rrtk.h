@@ -110,7 +110,25 @@ typedef struct rrtk_rrtstar_params {
      * with RRTK_SAMPLER_STREAM the caller simply passes the next max_iter samples).  k calls of m iterations build the
      * tree of one call of k * m iterations, bit for bit. */
     int32_t resume, iter_offset;
+    /* upper bound of the near radius sqrt(near_r2[k]) over the table.  0 = expand_dis, which is what the reference's
+     * clip guarantees (rrt_04:1333-1335).  MANDATORY (> expand_dis) when the caller passes an unclipped table: the
+     * per-iteration obstacle cull and the cell grid keep the circles within max(expand_dis, near_r_max) +
+     * path_resolution + R of the new node, and choose_parent / rewire edges are tested against that list only. */
+    double near_r_max;
+    /* how a query is executed (results are bit-identical): RRTK_EXEC_WARP = one warp per query, tree in L2;
+     * RRTK_EXEC_CTA = one CTA of 4 warps per query, tree (positions, children lists, parents) in shared memory --
+     * needs node_cap <= 65535 and 22 B / node + the near list in <= 227 KB; RRTK_EXEC_AUTO picks CTA when it fits. */
+    int32_t exec_mode;
+    int32_t pad_;
 } rrtk_rrtstar_params;
+
+#define RRTK_EXEC_AUTO 0
+#define RRTK_EXEC_WARP 1
+#define RRTK_EXEC_CTA 2
+
+/* every planner workspace ends with this many extra int32 (the work-queue counter of the persistent grid lives there:
+ * the library allocates nothing per call) */
+#define RRTK_WS_TAIL_INTS 4
 
 /* ints of workspace per query for rrtk_rrtstar_run_dev */
 #define RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny) \
@@ -130,9 +148,9 @@ typedef struct rrtk_rrtstar_params {
  *   n_nodes [Q], iters_done [Q], goal_index [Q] (-1 = no path), status [Q],
  *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
  * scratch (caller allocated, contents undefined afterwards):
- *   workspace [Q][RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny)] int32: children lists (first child, next /
- *             previous sibling), the breadth-first frontier of propagate_cost_to_leaves, and the obstacle cell
- *             lists (per cell a count + 32 uint16 indices); the workspace must be 16-byte aligned
+ *   workspace [Q][RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny)] + [RRTK_WS_TAIL_INTS] int32: children lists (first
+ *             child, next / previous sibling), the breadth-first frontier of propagate_cost_to_leaves, the obstacle
+ *             cell lists (per cell a count + 32 uint16 indices), then the work-queue counter; 16-byte aligned
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
@@ -212,7 +230,7 @@ typedef struct rrtk_informed_params {
  *   ball_draws [Q][max_iter][2]   = the two random.random() draws of sample_unit_ball (:1162-1171);
  * outputs: xy [Q][node_cap][2], cost, parent [Q][node_cap], n_nodes [Q],
  *   path [Q][path_cap][2] + path_len [Q] (0 = None): snapshot of the best path, goal -> start; c_best [Q];
- *   status [Q];  scratch: ws_idx [Q][node_cap] int32, ws_d [Q][node_cap] double */
+ *   status [Q];  scratch: ws_idx [Q][node_cap] + [RRTK_WS_TAIL_INTS] int32, ws_d [Q][node_cap] double */
 RRTK_API int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goal, const double *rot,
                                    const double *obstacles, const int32_t *n_obs, const double *near_rr2,
                                    const double *free_samples, const double *ball_draws, double *xy,
@@ -341,7 +359,8 @@ typedef struct rrtk_dubins_params {
  * outputs: xy [Q][node_cap][2], yaw, cost, parent [Q][node_cap]; edge_from / edge_to [Q][node_cap][3]: the pose pair
  *   whose Dubins course is the node's path_x / path_y / path_yaw (rrtk_dubins_steer_dev regenerates it);
  *   n_nodes, iters_done, goal_index (-1 = none; index 0 counts as none like the reference), status [Q];
- *   scratch workspace [Q][4][node_cap] int32, 16-byte aligned (children lists + propagation frontier) */
+ *   scratch workspace [Q][4][node_cap] + [RRTK_WS_TAIL_INTS] int32, 16-byte aligned (children lists + propagation
+ *   frontier, then the work-queue counter) */
 RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6,
                                          const double *obstacles, const int32_t *n_obs, const double *near_r2,
                                          const double *stream3, double *xy, double *yaw, double *cost,

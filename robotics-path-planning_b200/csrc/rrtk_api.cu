@@ -99,16 +99,15 @@ static int check_params(const rrtk_rrtstar_params *p) {
         return set_error(RRTK_ERR_INVALID, "grid_nx / grid_ny must both be 0 or both in 1..64");
     if (p->grid_nx > 0 && !(p->grid_cell > 0.0)) return set_error(RRTK_ERR_INVALID, "grid_cell must be > 0");
     if ((p->resume != 0 && p->resume != 1) || p->iter_offset < 0) return set_error(RRTK_ERR_INVALID, "resume must be 0 / 1, iter_offset >= 0");
+    if (!(p->near_r_max >= 0.0)) return set_error(RRTK_ERR_INVALID, "near_r_max must be >= 0 (0 = expand_dis)");
+    if (p->exec_mode < RRTK_EXEC_AUTO || p->exec_mode > RRTK_EXEC_CTA) return set_error(RRTK_ERR_INVALID, "unknown exec_mode");
     return RRTK_OK;
 }
 
-// a per-call device counter for the persistent kernel's work queue
-struct DevCounter {
-    unsigned int *ptr = nullptr;
-    cudaStream_t s;
-    explicit DevCounter(cudaStream_t st) : s(st) { cudaMallocAsync(&ptr, sizeof(unsigned int), st); }
-    ~DevCounter() { if (ptr) cudaFreeAsync(ptr, s); }
-};
+// the work-queue counter of a persistent planner grid: the RRTK_WS_TAIL_INTS ints that end the caller's workspace
+static inline unsigned int *ws_tail(int32_t *ws, size_t ints_before) {
+    return reinterpret_cast<unsigned int *>(ws + ints_before);
+}
 
 }  // namespace rrtk
 
@@ -189,10 +188,9 @@ int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
         return set_error(RRTK_ERR_INVALID, "sampler = STREAM needs sample_stream");
     if (p->resume && trace) return set_error(RRTK_ERR_INVALID, "trace is not recorded with resume = 1");
     cudaStream_t s = (cudaStream_t)stream;
-    DevCounter ctr(s);
-    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    unsigned int *ctr = ws_tail(workspace, (size_t)p->n_queries * RRTK_RRTSTAR_WS_INTS(p->node_cap, p->grid_nx, p->grid_ny));
     return launch_rrtstar(*p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost,
-                          parent, n_nodes, iters_done, goal_index, status, trace, workspace, ctr.ptr, s);
+                          parent, n_nodes, iters_done, goal_index, status, trace, workspace, ctr, s);
 }
 
 int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goal, const double *rot,
@@ -211,10 +209,9 @@ int rrtk_informed_run_dev(const rrtk_informed_params *p, const double *start_goa
         (p->obs_stride > 0 && !obstacles))
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     cudaStream_t s = (cudaStream_t)stream;
-    DevCounter ctr(s);
-    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
     return launch_informed(*p, start_goal, rot, obstacles, n_obs, near_rr2, free_samples, ball_draws, xy, cost, parent,
-                           n_nodes, path, path_len, c_best, status, ws_idx, ws_d, ctr.ptr, s);
+                           n_nodes, path, path_len, c_best, status, ws_idx, ws_d,
+                           ws_tail(ws_idx, (size_t)p->n_queries * (size_t)p->node_cap), s);
 }
 
 int64_t rrtk_informed_tree_workspace_bytes(int32_t node_cap, int32_t grid) {
@@ -292,10 +289,10 @@ int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start
         (p->obs_stride > 0 && !obstacles))
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     cudaStream_t s = (cudaStream_t)stream;
-    DevCounter ctr(s);
-    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    if ((uintptr_t)workspace & 15) return set_error(RRTK_ERR_INVALID, "workspace must be 16-byte aligned");
     return launch_rrtstar_dubins(*p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from,
-                                 edge_to, n_nodes, iters_done, goal_index, status, workspace, ctr.ptr, s);
+                                 edge_to, n_nodes, iters_done, goal_index, status, workspace,
+                                 ws_tail(workspace, (size_t)p->n_queries * 4 * (size_t)p->node_cap), s);
 }
 
 int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
@@ -314,10 +311,10 @@ int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goa
         (p->obs_stride > 0 && !obstacles))
         return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     cudaStream_t s = (cudaStream_t)stream;
-    DevCounter ctr(s);
-    if (!ctr.ptr) return set_cuda_error(cudaGetLastError(), "cudaMallocAsync(counter)");
+    if ((uintptr_t)workspace & 15) return set_error(RRTK_ERR_INVALID, "workspace must be 16-byte aligned");
     return launch_rrtstar_rs(*p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from,
-                                 edge_to, n_nodes, iters_done, goal_index, status, workspace, ctr.ptr, s);
+                                 edge_to, n_nodes, iters_done, goal_index, status, workspace,
+                                 ws_tail(workspace, (size_t)p->n_queries * 4 * (size_t)p->node_cap), s);
 }
 
 int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,
@@ -467,7 +464,7 @@ int rrtk_rrtstar_run_host(const rrtk_rrtstar_params *p, const double *start_goal
     const size_t b_sg = Q * 4 * 8, b_obs = Q * (size_t)p->obs_stride * 4 * 8, b_no = Q * 4,
                  b_r2 = (cap + 2) * 8, b_st = sample_stream ? Q * it * 16 : 0,
                  b_so = sobol_offset ? Q * 8 : 0, b_xy = Q * cap * 16, b_c = Q * cap * 8,
-                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = Q * RRTK_RRTSTAR_WS_INTS(cap, p->grid_nx, p->grid_ny) * 4;
+                 b_p = Q * cap * 4, b_q = Q * 4, b_tr = trace ? Q * it * 32 : 0, b_ws = (Q * RRTK_RRTSTAR_WS_INTS(cap, p->grid_nx, p->grid_ny) + RRTK_WS_TAIL_INTS) * 4;
     char *d = nullptr;
     size_t off[16], total = 0;
     const size_t sizes[15] = {b_sg, b_obs, b_no, b_r2, b_st, b_so, b_xy, b_c, b_p, b_q, b_q, b_q, b_q, b_tr, b_ws};

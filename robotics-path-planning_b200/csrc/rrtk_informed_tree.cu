@@ -14,9 +14,10 @@
 //   cand   the CTA's nearest candidate for sample it+1 is extended SPECULATIVELY: exact atan2/cos/sin, new
 //          position, check_collision of that edge and of the goal segment          (one warp)
 //   hits   choose_parent candidates of the owned hits: hypot, segment verdict, cost (the other warps)
-//   xchg   every CTA publishes one 128-byte record of self-validating 16-byte pieces (value, index, tag) and
+//   xchg   every CTA publishes one 64-byte record of 16-byte pieces (value, index, tag) and
 //          polls the G records: nearest of it+1 WITH its already-extended node, best parent of it, flags.
-//          No counter, no second round trip: a piece is valid when its tag equals the exchange number.
+//          Release = fence + one L2 counter increment per CTA; one thread per CTA polls the counter (relaxed) and
+//          finishes with an acquire load before the records are read (see exchange()).
 //   apply  owner appends the node; every CTA rewires its own hits; goal bookkeeping (c_best, path snapshot)
 // so the serial leaf math of iteration it+1 overlaps the candidate evaluation of iteration it.  The sample of
 // it+1 depends on c_best and the new node of `it` may itself be the nearest of it+1: both cases are detected
@@ -240,6 +241,7 @@ __device__ __noinline__ Winner exchange(TreeSmem &S, const TreeWs &ws, unsigned 
             const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
             unsigned long long v;
             do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
+            (void)ld_acquire(ws.bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
         }
     }
     __syncthreads();
@@ -779,6 +781,7 @@ __device__ __forceinline__ void batch_sync(const TreeWs &ws, unsigned &seq, int 
         const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
         unsigned long long v;
         do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
+            (void)ld_acquire(ws.bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
     }
     __syncthreads();
     seq++;

@@ -22,6 +22,7 @@
 #include "crmath.h"
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
+#include "rrtk_rrtstar_common.cuh"
 
 namespace rrtk {
 
@@ -37,143 +38,6 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef RRTK_UNROLL_PROP
 #define RRTK_UNROLL_PROP 1
 #endif
-
-struct Steer {
-    double ex, ey;    // end point
-    double stx, sty;  // step vector = res * (cos, sin)
-    double d;         // hypot(to - from): what calc_distance_and_angle returns (rrt_04:1232-1238)
-    int n;            // number of accumulated steps
-    bool snap;        // final point snapped to the target
-};
-
-// steer (rrt_04:1086-1115)
-__device__ __noinline__ Steer steer(double fx, double fy, double tx, double ty, double extend,
-                                    double res) {
-    Steer st;
-    double dx = tx - fx, dy = ty - fy;
-    double d = crm_hypot(dx, dy);
-    st.d = d;
-    double s, c;
-    (void)crm_atan2_sincos(dy, dx, &s, &c);
-    if (extend > d) extend = d;
-    double q = floor(extend / res);
-    int n = q < 2.0e9 ? (int)q : 2000000000;
-    st.stx = res * c;
-    st.sty = res * s;
-    double x = fx, y = fy;
-    for (int k = 0; k < n; k++) {
-        x += st.stx;
-        y += st.sty;
-    }
-    double d2 = crm_hypot(tx - x, ty - y);
-    st.snap = d2 <= res;
-    if (st.snap) {
-        x = tx;
-        y = ty;
-    }
-    st.ex = x;
-    st.ey = y;
-    st.n = n;
-    return st;
-}
-
-// check_collision (rrt_04:1216-1230) of one edge by ONE lane: any path point within any circle.
-__device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
-                                               double ty, const ObsList &L) {
-    double x = fx, y = fy;
-    for (int k = 0;; k++) {
-        for (int j = 0; j < L.m; j++) {
-            double dx = L.ox[j * L.stride] - x, dy = L.oy[j * L.stride] - y;
-            if (dx * dx + dy * dy <= L.r2[j * L.stride]) return false;
-        }
-        if (k == st.n) break;
-        x += st.stx;
-        y += st.sty;
-    }
-    if (st.snap) {
-        for (int j = 0; j < L.m; j++) {
-            double dx = L.ox[j * L.stride] - tx, dy = L.oy[j * L.stride] - ty;
-            if (dx * dx + dy * dy <= L.r2[j * L.stride]) return false;
-        }
-    }
-    return true;
-}
-
-// Cheap verdict of the edge f -> t steered with extend_length = inf (choose_parent / rewire candidates), WITHOUT the
-// correctly rounded atan2/cos/sin: the reference's path points are f, f + k * res * (cos, sin)(theta) (k = 1..n,
-// accumulated) and -- when the last one lies within `res` of t -- t itself (rrt_04:1099-1113).  n = floor(d / res)
-// is computed exactly as steer does; the first and last points are f and t exactly; the intermediate points are
-// reproduced to within eps_pos with the direction (t - f) / d, so a point-circle test whose margin exceeds the
-// error band has the reference's verdict.  Returns 1 = free and snapped (end point == t), 0 = blocked,
-// -1 = too close to call (a test inside the band, or the snap decision within 1e-9 of its threshold): the caller
-// runs the exact steer + edge_free_lane.  `extend` = steer's extend_length (inf for choose_parent / rewire,
-// expand_dis for the first edge); obstacles j0, j0 + jstep, ... are tested (lanes can split them).
-__device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, double ty, double d, double extend,
-                                              double res, const ObsList &L, int j0, int jstep) {
-    if (!(d > 0.0)) return -1;
-    const double q = floor((extend > d ? d : extend) / res);   // steer's n_expand (rrt_04:1096-1099)
-    if (!(q < 1.0e6)) return -1;
-    const int n = (int)q;
-    const double rem = d - q * res;                    // distance left after n steps
-    if (!(rem <= res * (1.0 - 1e-9))) return -1;       // snap (d2 <= res, rrt_04:1107) must be certain
-    const double inv = res / d;
-    const double ux = (tx - fx) * inv, uy = (ty - fy) * inv;
-    const double e4 = 4.0 * ((double)(n + 8) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
-    bool unsure = false;
-    const double wx = tx - fx, wy = ty - fy, invl2 = 1.0 / (d * d);
-    for (int j = j0; j < L.m; j += jstep) {
-        const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
-        double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
-        if (dx * dx + dy * dy <= r2) return 0;
-        const double bj = (2.02 + 2.02 * r2) * e4;     // >= (2 + dd + r2) * e4 wherever |dd - r2| is that small
-        // every path point lies on the segment f-t (to within eps_pos): a circle farther than its radius (plus
-        // the band) from the segment cannot contain one
-        double sp = (dx * wx + dy * wy) * invl2;
-        sp = sp < 0.0 ? 0.0 : (sp > 1.0 ? 1.0 : sp);
-        const double px = dx - sp * wx, py = dy - sp * wy;
-        if (px * px + py * py - r2 > bj + 1e-9 * (1.0 + r2)) continue;
-        dx = ox - tx; dy = oy - ty;                    // last point: t itself (snapped), exact test
-        if (dx * dx + dy * dy <= r2) return 0;
-        double x = fx, y = fy;
-        for (int k = 1; k <= n; k++) {
-            x += ux; y += uy;
-            dx = ox - x; dy = oy - y;
-            const double t = dx * dx + dy * dy - r2;
-            if (t <= bj) {
-                if (t <= -bj) return 0;                // certainly inside: blocked whatever the others say
-                unsure = true;
-            }
-        }
-    }
-    return unsure ? -1 : 1;
-}
-
-// the same verdict computed by the whole warp (lanes split the obstacles); uniform result
-__device__ __noinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
-                                               double ty, const ObsList &L, int lane) {
-    bool hit = false;
-    for (int j = lane; j < L.m && !hit; j += 32) {
-        double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
-        double x = fx, y = fy;
-        for (int k = 0;; k++) {
-            double dx = ox - x, dy = oy - y;
-            if (dx * dx + dy * dy <= r2) { hit = true; break; }
-            if (k == st.n) break;
-            x += st.stx;
-            y += st.sty;
-        }
-        if (!hit && st.snap) {
-            double dx = ox - tx, dy = oy - ty;
-            if (dx * dx + dy * dy <= r2) hit = true;
-        }
-    }
-    return __ballot_sync(FULL, hit) == 0u;
-}
-
-__device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double x, double y) {
-    if (!p.has_play_area) return true;  // rrt_04:1207-1208
-    return !(x < p.play_area[0] || x > p.play_area[1] || y < p.play_area[2] || y > p.play_area[3]);
-}
 
 // find_near_nodes (rrt_04:1314-1338) around (cx, cy): ballot compaction in ascending index order.  Only used when the
 // new node is not the sample (the merged scan of the main loop covers the common case).
@@ -244,97 +108,6 @@ __host__ __device__ inline size_t warp_smem_bytes(int near_cap, int node_cap) {
     return (b + 15) & ~(size_t)15;
 }
 
-struct Sample { double x, y; };
-
-// Sobol state of one query: the current point (30-bit integers) and its index; advanced with the
-// Antonov-Saleev update point(n+1) = point(n) ^ V[lowest zero bit of n] (what i4_sobol does, rrt_04:448-452)
-struct SobolState {
-    int64_t n;
-    uint32_t q0, q1;
-};
-
-// get_random_node / get_random_node_sobol (rrt_04:1132-1153) with a counter-based coin
-__device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, int it_key, double gx,
-                                              double gy, const double2 *stream, SobolState &sob) {
-    Sample s;
-    if (p.sampler == RRTK_SAMPLER_STREAM) {
-        double2 v = stream[it];
-        s.x = v.x; s.y = v.y;
-        return s;
-    }
-    uint64_t k0 = rng_key(p.seed, (uint64_t)q, (uint64_t)it_key);   // it_key = iteration counter of the whole run
-    int coin = (int)(splitmix64(k0) % 101ull);  // random.randint(0, 100)
-    if (coin > p.goal_sample_rate) {
-        double w = p.max_rand - p.min_rand;
-        if (p.sampler == RRTK_SAMPLER_SOBOL) {
-            const double recipd = 1.0 / 1073741824.0;
-            s.x = p.min_rand + ((double)sob.q0 * recipd) * w;
-            s.y = p.min_rand + ((double)sob.q1 * recipd) * w;
-            int c = __ffsll(~sob.n) - 1;  // lowest zero bit of the index just used
-            if (c < SOBOL_BITS) { sob.q0 ^= c_sobol.v[0][c]; sob.q1 ^= c_sobol.v[1][c]; }
-            sob.n++;
-        } else {
-            s.x = p.min_rand + w * u01(splitmix64(k0 + 1));
-            s.y = p.min_rand + w * u01(splitmix64(k0 + 2));
-        }
-    } else {
-        s.x = gx; s.y = gy;
-    }
-    return s;
-}
-
-// search_best_goal_node (rrt_04:1284-1312).  Returns the goal node index or -1.  Uniform result.
-__device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n, const double2 *xy,
-                                      const double *cost, double gx, double gy, const ObsList &G,
-                                      int *near_idx, double *nd, int near_cap, int lane, bool &overflow) {
-    // candidates: dist <= expand_dis, each mapped to the first index with the same dist
-    int count = 0;
-    for (int base = 0; base < n; base += 32) {
-        int i = base + lane;
-        bool hit = false;
-        double d = 0.0;
-        if (i < n) {
-            double2 a = xy[i];
-            d = crm_hypot(a.x - gx, a.y - gy);
-            hit = d <= p.expand_dis;
-        }
-        unsigned mask = __ballot_sync(FULL, hit);
-        int pos = count + __popc(mask & ((1u << lane) - 1u));
-        if (hit && pos < near_cap) { near_idx[pos] = i; nd[pos] = d; }
-        count += __popc(mask);
-    }
-    __syncwarp();
-    if (count > near_cap) { overflow = true; count = near_cap; }
-    double best_c = CUDART_INF;
-    int best_k = 0x7fffffff;
-    for (int k = lane; k < count; k += 32) {
-        double dk = nd[k];
-        int f = k;
-        for (int j = 0; j < k; j++)
-            if (nd[j] == dk) { f = j; break; }
-        int i = near_idx[f];
-        double2 a = xy[i];
-        Steer st = steer(a.x, a.y, gx, gy, CUDART_INF, p.path_resolution);
-        bool ok = edge_free_lane(a.x, a.y, st, gx, gy, G) && inside_play(p, st.ex, st.ey);
-        if (ok) {
-            double c = cost[i] + crm_hypot(a.x - gx, a.y - gy);
-            // first minimum over the candidate list; equal costs keep the earlier list entry
-            if (c < best_c) { best_c = c; best_k = k; }
-        }
-    }
-    // reduce over lanes: min cost, ties -> smaller list position
-    warp_argmin(best_c, best_k);
-    if (best_k == 0x7fffffff) return -1;
-    // map the list position back to the node index (first index with the same distance)
-    double dk = nd[best_k];
-    int f = best_k;
-    for (int j = 0; j < best_k; j++)
-        if (nd[j] == dk) { f = j; break; }
-    return near_idx[f];
-}
-
-__device__ unsigned int g_query_counter;
-
 #ifndef RRTK_MIN_BLOCKS
 #define RRTK_MIN_BLOCKS 4
 #endif
@@ -392,8 +165,10 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
         grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
-        if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, p.expand_dis + res, lane);
-        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
+        // every path point of an iteration's edges lies within `reach` of its new node (a snapped first edge starts up to
+        // expand_dis + res away; near nodes are within the near radius, <= expand_dis unless near_r_max says otherwise)
+        const double reach = (p.near_r_max > p.expand_dis ? p.near_r_max : p.expand_dis) + res;
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0, it_prev = 0;
         SobolState sob;
         sob.n = sobol_base < 0 ? 0 : sobol_base;
         if (!RESUME) {
@@ -407,7 +182,12 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             // continue the tree a previous call left in xy / cost / parent (rows 0 .. n_nodes[q] - 1): rebuild the children
             // lists from the parent array (their order only fixes the traversal order of propagate, not its values) and
             // skip the Sobol points the earlier iterations consumed (one per non-goal coin)
+            // A query that had finished (goal found in early-exit mode, or an overflow) stays as it is.
             n = n_nodes[q];
+            it_prev = iters_done[q];
+            if ((status_out[q] & (RRTK_Q_NEAR_OVERFLOW | RRTK_Q_NODE_OVERFLOW)) ||
+                ((RRT_ONLY || !p.search_until_max_iter) && goal_index[q] >= 0))
+                continue;   // uniform
             if (n < 1 || n > p.node_cap) { n = 1; status |= RRTK_Q_NODE_OVERFLOW; }
             for (int i = lane; i < n; i += 32) links[i] = make_int4(-1, -1, -1, 0);
             __syncwarp();
@@ -421,6 +201,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
             }
         }
         __syncwarp();
+        if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, reach, lane);
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
         sobol2(sob.n, sob.q0, sob.q1);
         bool done = false;
@@ -462,9 +243,6 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             const double2 from = xy[ni];
             int t_status = 0, t_near = 0, t_par = -1, t_cpok = 0, t_rwok = 0, t_rwap = 0;
             bool accept = false, near_valid = false;
-            // every path point of this iteration's edges lies within expand_dis + res of the new node (a snapped
-            // first edge starts up to expand_dis + res away; near nodes are within the near radius <= expand_dis)
-            const double reach = p.expand_dis + res;
             ObsList L;
             L.ox = L.oy = L.r2 = nullptr; L.stride = 1; L.m = 0;
             // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the
@@ -684,7 +462,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
         }
         if (lane == 0) {
             n_nodes[q] = n;
-            iters_done[q] = it;
+            iters_done[q] = it_prev + it;
             goal_index[q] = gi;
             status_out[q] = status;
         }
@@ -761,11 +539,22 @@ extern "C" __global__ void crmath_probe_kernel(int kind, int64_t n, const double
 // ------------------------------------------------------------------------------------------------
 namespace rrtk {
 
+bool rrtstar_cta_fits(const rrtk_rrtstar_params &p);
+int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
+                       const int32_t *n_obs, const double *near_r2, const double *sample_stream,
+                       const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
+                       int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                       int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s);
+
 int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
                    const int32_t *n_obs, const double *near_r2, const double *sample_stream,
                    const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
                    int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                    int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s) {
+    // one CTA per query with the tree in shared memory (rrtk_rrtstar_cta.cu) whenever it fits; one warp per query otherwise
+    if (p.exec_mode == RRTK_EXEC_CTA || (p.exec_mode == RRTK_EXEC_AUTO && rrtstar_cta_fits(p)))
+        return launch_rrtstar_cta(p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost, parent,
+                                  n_nodes, iters_done, goal_index, status, trace, workspace, counter, s);
     const bool fixed_nc = p.near_cap <= 256;
     size_t per_warp = warp_smem_bytes(fixed_nc ? 256 : p.near_cap, p.node_cap);
     size_t smem = per_warp * WARPS_PER_CTA;

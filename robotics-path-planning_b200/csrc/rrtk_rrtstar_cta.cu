@@ -1,0 +1,720 @@
+// rrtk_rrtstar_cta.cu -- batched RRT / RRT*, ONE CTA (4 warps) PER QUERY, the tree in shared memory.
+//
+// Same loop and the same results, bit for bit, as the warp-per-query kernel (rrtk_rrtstar.cu): `planning()` of
+// rrt_04:1036-1084 (and rrt_01:71-101 with RRT_ONLY).  What changes is where the time goes.  One warp per query is a
+// serial chain of L2 round trips (node scan, children lists, candidate loads): 2 400 resident queries hide each other's
+// latency, 512 do not -- and every multi-GPU configuration of BASELINE.json is a small batch per GPU.  Here a query
+// owns a CTA and its working set lives in that CTA's shared memory:
+//   s_xy[node_cap]   double2   node positions (FP64, the scan reads them with one LDS.128 per node)
+//   s_link[node_cap] ushort2   children lists: first child, next sibling (propagate_cost_to_leaves, rrt_04:1379-1384)
+//   s_par[node_cap]  ushort    parent (read when a node is re-parented)
+// 22 B / node = 44 KB at config 2's 2001 nodes, four queries per SM.  Global xy / parent are written through (they are
+// the outputs); node costs stay in global memory only: every read of a cost is either issued long before its use
+// (candidates) or replaced by a value carried in shared memory (the propagate frontier carries the parent's cost).
+// The iteration, with the CTA-wide barriers B1..B5:
+//   all warps   nearest (rrt_04:1196-1202) + speculative near set around the SAMPLE, strided over 128 threads; hits are
+//               appended unordered (shared-memory atomic)                                                         B1
+//   warp 0      first edge: steer + play area + collision (edge_verdict_fast / exact steer)           } concurrently
+//   warp 1      obstacle cull around the NEXT iteration's sample (its L2 latency never shows)         }
+//   warps 2-3   near list: rank by index (ascending order) + the `.index()` first-equal-d2 mapping    }          B2
+//   all warps   choose_parent (rrt_04:1242-1282): 4 lanes per candidate split the culled circles                B3
+//   all warps   rewire edges (rrt_04:1340-1373), same split, only entries that pass node.cost > new.cost + d    B4
+//   warp 0      ordered apply + propagate over the shared-memory children lists, append                         B5
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrtk.h"
+#include "crmath.h"
+#include "rrtk_device.cuh"
+#include "rrtk_planner.cuh"
+#include "rrtk_rrtstar_common.cuh"
+
+namespace rrtk {
+
+constexpr int CTA_W = 4;              // warps per query
+constexpr int CTA_T = CTA_W * 32;
+constexpr int CTA_G = 4;              // lanes per near candidate
+constexpr int CTA_CPR = CTA_T / CTA_G;  // candidates per round
+constexpr int CTA_NC_SMALL = 256;     // layout capacities of the near list (p.near_cap <= NC): batches / single queries
+constexpr int CTA_NC_LARGE = 1024;
+constexpr int CTA_FQ = 128;           // shared-memory slots of propagate's frontier (more spill to the workspace)
+constexpr unsigned short NONE16 = 0xffffu;
+constexpr int BIG = 0x7fffffff;
+
+// fixed part of the CTA's shared memory (every address an immediate); the tree arrays follow it
+template <int NC>
+struct CtaSmemT {
+    double nd[NC];               // d2 to the new node, then hypot(new - node)
+    double s_nc[NC];             // unordered d2 while the list is built, then the candidates' node costs
+    double cull[2][3][CULL_CAP];     // culled circles (x, y, R2) of this iteration [it & 1] and the next
+    double fq_cost[CTA_FQ];
+    double red_d[CTA_W], red_ex[CTA_W], red_ey[CTA_W];
+    double nx, ny;                   // the new node (warp 0 -> all)
+    int near_idx[NC];
+    int near_ok[NC];             // unordered indices while the list is built, then the rewire flags
+    int red_i[CTA_W];
+    int cull_m[2], cull_glob[2];
+    int count, cpok, tail;
+    int accept, near_valid, t_status;
+    int done, gi, status_or;
+    unsigned int q;
+    unsigned short fq_idx[CTA_FQ];
+};
+
+template <int NC>
+__host__ __device__ inline size_t cta_smem_bytes(int node_cap) {
+    size_t b = (sizeof(CtaSmemT<NC>) + 15) & ~(size_t)15;
+    b += (size_t)node_cap * 16;                    // s_xy
+    b += (size_t)node_cap * 4;                     // s_link
+    b += ((size_t)node_cap * 2 + 15) & ~(size_t)15;  // s_par
+    return b;
+}
+
+static __device__ __forceinline__ void cta_link(ushort2 *s_link, int p, int c) {
+    s_link[c].y = s_link[p].x;
+    s_link[p].x = (unsigned short)c;
+}
+static __device__ __forceinline__ void cta_unlink(ushort2 *s_link, int p, int c) {
+    const unsigned short nxt = s_link[c].y;
+    unsigned short x = s_link[p].x;
+    if (x == (unsigned short)c) { s_link[p].x = nxt; return; }
+    for (;;) {
+        const unsigned short y = s_link[x].y;
+        if (y == (unsigned short)c || y == NONE16) break;
+        x = y;
+    }
+    s_link[x].y = nxt;
+}
+
+// propagate_cost_to_leaves (rrt_04:1379-1384) by one warp over the shared-memory children lists; the frontier carries each
+// node's new cost, so no cost is read back from global memory.  Slots >= CTA_FQ spill to the query's workspace.
+template <class SM>
+static __device__ __noinline__ void cta_propagate(int root, double root_cost, const double2 *s_xy, const ushort2 *s_link,
+                                                  double *cost, SM &S, int *g_idx, double *g_cost, int lane) {
+    if (s_link[root].x == NONE16) return;
+    volatile int *tail = &S.tail;
+    if (lane == 0) { S.fq_idx[0] = (unsigned short)root; S.fq_cost[0] = root_cost; *tail = 1; }
+    __syncwarp();
+    for (int head = 0;;) {
+        const int end = *tail;
+        if (head >= end) break;
+        const int k = head + lane;
+        __syncwarp();
+        if (k < end) {
+            const int pn = k < CTA_FQ ? (int)S.fq_idx[k] : g_idx[k];
+            const double cp = k < CTA_FQ ? S.fq_cost[k] : g_cost[k];
+            const double2 a = s_xy[pn];
+            for (unsigned short c = s_link[pn].x; c != NONE16;) {
+                const ushort2 lc = s_link[c];
+                const double2 b = s_xy[c];
+                const double cc = cp + crm_hypot(b.x - a.x, b.y - a.y);
+                cost[c] = cc;
+                if (lc.x != NONE16) {
+                    const int slot = atomicAdd(&S.tail, 1);
+                    if (slot < CTA_FQ) { S.fq_idx[slot] = c; S.fq_cost[slot] = cc; }
+                    else { g_idx[slot] = (int)c; g_cost[slot] = cc; }
+                }
+                c = lc.y;
+            }
+        }
+        __syncwarp();
+        head = end < head + 32 ? end : head + 32;
+    }
+}
+
+// view of every CTA_G-th circle of L starting at `sub` (the share of one lane of a candidate's group)
+static __device__ __forceinline__ ObsList sub_list(const ObsList &L, int sub) {
+    ObsList s;
+    s.ox = L.ox + (size_t)sub * L.stride; s.oy = L.oy + (size_t)sub * L.stride; s.r2 = L.r2 + (size_t)sub * L.stride;
+    s.stride = L.stride * CTA_G;
+    s.m = L.m > sub ? (L.m - sub + CTA_G - 1) / CTA_G : 0;
+    return s;
+}
+
+// rewire entries [from, count) one at a time against the current tree, by warp 0 (a re-parented node MOVED,
+// rrt_04:1365-1371: positions and costs seen by the parallel pass are stale).  Rare.
+template <class SM>
+static __device__ __noinline__ void cta_rewire_serial(const rrtk_rrtstar_params &p, int from, int count, SM &S, double2 *s_xy,
+                                                      ushort2 *s_link, unsigned short *s_par, double2 *xy, double *cost,
+                                                      int32_t *parent, int n, double cx, double cy, double ccost,
+                                                      const ObsList &L, int *g_idx, double *g_cost, int lane, int &t_rwok,
+                                                      int &t_rwap) {
+    const double res = p.path_resolution;
+    for (int k = from; k < count; k++) {
+        const int i = S.near_idx[k];
+        const double2 a = s_xy[i];
+        Steer st = steer(cx, cy, a.x, a.y, CUDART_INF, res);
+        const bool ok = edge_free_warp(cx, cy, st, a.x, a.y, L, lane) && inside_play(p, st.ex, st.ey);
+        const double ec = ccost + st.d;
+        t_rwok += ok ? 1 : 0;
+        if (ok && cost[i] > ec) {
+            __syncwarp();
+            if (lane == 0) {
+                cta_unlink(s_link, (int)s_par[i], i);
+                cta_link(s_link, n, i);
+                s_xy[i] = make_double2(st.ex, st.ey);
+                xy[i] = make_double2(st.ex, st.ey);
+                cost[i] = ec;
+                parent[i] = n;
+                s_par[i] = (unsigned short)n;
+            }
+            __syncwarp();
+            t_rwap++;
+            cta_propagate(i, ec, s_xy, s_link, cost, S, g_idx, g_cost, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// near list of the CTA: the unordered hits (S.near_ok = index, S.s_nc = d2) -> S.near_idx / S.nd in ascending index
+// order, every hit replaced by the FIRST hit (lowest index) with the same d2 -- `dist_list.index(i)` of rrt_04:1336-1337.
+// Threads t0, t0 + nt, ... of the caller take the entries.
+template <class SM>
+static __device__ __forceinline__ void cta_rank_near(SM &S, int count, int t0, int nt) {
+    for (int k = t0; k < count; k += nt) {
+        const int ik = S.near_ok[k];
+        const double dk = S.s_nc[k];
+        int rank = 0, first = ik;
+        for (int j = 0; j < count; j++) {
+            const int ij = S.near_ok[j];
+            rank += ij < ik ? 1 : 0;
+            if (S.s_nc[j] == dk && ij < first) first = ij;
+        }
+        S.near_idx[rank] = first;
+        S.nd[rank] = dk;
+    }
+}
+
+template <bool RRT_ONLY, bool TRACE, bool RESUME, int NC>
+__global__ void __launch_bounds__(CTA_T, 4)
+rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
+                   const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
+                   const double *__restrict__ near_r2, const double2 *__restrict__ sample_stream,
+                   const int64_t *__restrict__ sobol_offset, double2 *xy_all, double *cost_all,
+                   int32_t *parent_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+                   int32_t *status_out, int32_t *trace_all, int32_t *workspace, unsigned int *counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef CtaSmemT<NC> CtaSmem;
+    CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
+    double2 *s_xy = reinterpret_cast<double2 *>(smem_raw + ((sizeof(CtaSmem) + 15) & ~(size_t)15));
+    ushort2 *s_link = reinterpret_cast<ushort2 *>(s_xy + p.node_cap);
+    unsigned short *s_par = reinterpret_cast<unsigned short *>(s_link + p.node_cap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int near_cap = p.near_cap;
+    const double res = p.path_resolution;
+    const double INF = CUDART_INF;
+    const double reach = (p.near_r_max > p.expand_dis ? p.near_r_max : p.expand_dis) + res;
+    const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
+
+    for (;;) {
+        __syncthreads();   // the previous query's shared memory is no longer read
+        if (tid == 0) S.q = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int q = S.q;
+        if (q >= (unsigned)p.n_queries) break;
+
+        const double4 sg = start_goal[q];
+        const double gx = sg.z, gy = sg.w;
+        const double4 *obs = obstacles + (size_t)q * p.obs_stride;
+        const int n_obs = n_obs_arr[q];
+        double2 *xy = xy_all + (size_t)q * p.node_cap;
+        double *cost = cost_all + (size_t)q * p.node_cap;
+        int32_t *parent = parent_all + (size_t)q * p.node_cap;
+        const double2 *stream = sample_stream ? sample_stream + (size_t)q * p.max_iter : nullptr;
+        int32_t *trace = TRACE ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
+        const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
+
+        // workspace of the query: [4 * node_cap ints: spill of the propagate frontier (idx, then cost)] [obstacle cells]
+        const int grid_cells = p.grid_nx * p.grid_ny;
+        int32_t *wsq = workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny);
+        int *g_idx = wsq;
+        double *g_cost = reinterpret_cast<double *>(wsq + 2 * (size_t)((p.node_cap + 1) / 2));
+        ObsGrid grid;
+        grid.nx = p.grid_nx; grid.ny = p.grid_ny; grid.x0 = p.grid_x0; grid.y0 = p.grid_y0;
+        grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
+        grid.cnt = wsq + 4 * (size_t)p.node_cap;
+        grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
+
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0, it_prev = 0;
+        SobolState sob;
+        sob.n = sobol_base < 0 ? 0 : sobol_base;
+        bool skip = false;
+        if (!RESUME) {
+            if (tid == 0) {
+                s_xy[0] = make_double2(sg.x, sg.y);
+                s_link[0] = make_ushort2(NONE16, NONE16);
+                s_par[0] = NONE16;
+                xy[0] = make_double2(sg.x, sg.y);
+                cost[0] = 0.0;
+                parent[0] = -1;
+            }
+        } else {
+            // continue the tree a previous call left in xy / cost / parent: reload it, rebuild the children lists (their
+            // order only fixes the traversal order of propagate, not its values), skip the Sobol points already consumed.
+            // A query that had finished (goal found in early-exit mode, or an overflow) stays as it is.
+            n = n_nodes[q];
+            const int st_prev = status_out[q];
+            it_prev = iters_done[q];
+            if ((st_prev & (RRTK_Q_NEAR_OVERFLOW | RRTK_Q_NODE_OVERFLOW)) ||
+                ((RRT_ONLY || !p.search_until_max_iter) && goal_index[q] >= 0))
+                skip = true;
+            if (n < 1 || n > p.node_cap) { n = 1; status |= RRTK_Q_NODE_OVERFLOW; }
+            for (int i = tid; i < n; i += CTA_T) {
+                s_xy[i] = xy[i];
+                s_link[i] = make_ushort2(NONE16, NONE16);
+                const int pp = parent[i];
+                s_par[i] = pp < 0 ? NONE16 : (unsigned short)pp;
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 1; i < n; i++) { const unsigned short pp = s_par[i]; if (pp != NONE16 && (int)pp < n) cta_link(s_link, (int)pp, i); }
+            if (p.sampler == RRTK_SAMPLER_SOBOL) {
+                int used = 0;
+                for (int k = lane; k < p.iter_offset; k += 32)
+                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)q, (uint64_t)k)) % 101ull) > p.goal_sample_rate;
+                sob.n += (int64_t)__reduce_add_sync(FULL, (unsigned)used);
+            }
+        }
+        if (skip) continue;   // uniform: every thread read the same outputs
+        if (warp == 0 && grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, reach, lane);
+        if (tid == 0) { S.count = 0; S.cpok = 0; S.done = 0; S.gi = -1; S.status_or = 0; }
+        sobol2(sob.n, sob.q0, sob.q1);
+        bool done = false;
+        // near radius of the current tree size, and (loaded one iteration ahead) of the size after an append
+        double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];
+        // the sample of iteration 0, and the circles around it
+        Sample smp_next;
+        smp_next.x = smp_next.y = 0.0;
+        if (p.max_iter > 0) smp_next = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sob);
+        __syncthreads();   // the obstacle cells are built
+        if (warp == 1 && p.max_iter > 0 && inside_play(p, smp_next.x, smp_next.y)) {
+            const ObsList L0 = cull_obstacles_grid(grid, obs, n_obs, smp_next.x, smp_next.y, reach, S.cull[0][0], S.cull[0][1],
+                                                   S.cull[0][2], lane);
+            if (lane == 0) { S.cull_m[0] = L0.m; S.cull_glob[0] = L0.stride == 4 ? 1 : 0; }
+        }
+        __syncthreads();
+
+        for (it = 0; it < p.max_iter; it++) {
+            const int cb = it & 1;
+            const double rx = smp_next.x, ry = smp_next.y;
+            if (it + 1 < p.max_iter)
+                smp_next = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
+            // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the sample
+            // (when the steered node snaps onto the sample -- the common case once the tree is dense -- the near scan
+            // would compute exactly these d2 again) ----
+            double bd = INF;
+            int bi = BIG;
+            const double r2_grown = RRT_ONLY ? -1.0 : near_r2[n + 2 <= p.node_cap + 1 ? n + 2 : p.node_cap + 1];
+            const int n_before = n;
+#pragma unroll 4
+            for (int i = tid; i < n; i += CTA_T) {
+                const double2 a = s_xy[i];
+                const double ddx = a.x - rx, ddy = a.y - ry;
+                const double d = ddx * ddx + ddy * ddy;
+                if (d < bd) { bd = d; bi = i; }
+                if (d <= r2) {
+                    const int slot = atomicAdd(&S.count, 1);
+                    if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
+                }
+            }
+            warp_argmin(bd, bi);
+            if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; }
+            __syncthreads();   // ---- B1
+            bd = S.red_d[0]; bi = S.red_i[0];
+#pragma unroll
+            for (int w = 1; w < CTA_W; w++) {
+                const double dw = S.red_d[w];
+                const int iw = S.red_i[w];
+                if (dw < bd || (dw == bd && iw < bi)) { bd = dw; bi = iw; }
+            }
+            const int ni = bi;
+            int count = S.count;
+            int t_near = 0, t_par = -1, t_rwok = 0, t_rwap = 0;
+            double2 from = make_double2(0.0, 0.0);
+            if (warp == 0) {
+                // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the sample the
+                // new node IS the sample and only the collision verdict is needed; otherwise the exact steer runs ----
+                from = s_xy[ni];
+                int t_status = 0;
+                bool accept = false, near_valid = false;
+                double nx = rx, ny = ry;
+                const double d0 = crm_hypot(rx - from.x, ry - from.y);
+                int v = -1;
+                ObsList L;
+                L.ox = S.cull[cb][0]; L.oy = S.cull[cb][1]; L.r2 = S.cull[cb][2]; L.stride = 1; L.m = 0;
+                {
+                    const double ext = p.expand_dis > d0 ? d0 : p.expand_dis;
+                    const double q0 = floor(ext / res);
+                    if (d0 > 0.0 && d0 - q0 * res <= res * (1.0 - 1e-9)) {   // same snap test as edge_verdict_fast
+                        if (inside_play(p, nx, ny)) {
+                            if (S.cull_glob[cb]) {
+                                const double *g = reinterpret_cast<const double *>(obs);
+                                L.ox = g; L.oy = g + 1; L.r2 = g + 3; L.stride = 4; L.m = n_obs;
+                            } else {
+                                L.m = S.cull_m[cb];
+                            }
+                            const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, p.expand_dis, res, L, lane, 32);
+                            const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
+                            v = blocked ? 0 : (unsure ? -1 : 1);
+                            if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
+                        } else {
+                            v = 0;  // outside the play area: rejected before the collision check (rrt_04:1054)
+                        }
+                    }
+                }
+                if (v < 0) {
+                    Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
+                    nx = e0.ex; ny = e0.ey;
+                    if (inside_play(p, nx, ny)) {
+                        t_status = 1;
+                        // (the list prefetched for the sample only holds if the node landed on it)
+                        L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
+                        if (lane == 0) { S.cull_m[cb] = L.m; S.cull_glob[cb] = L.stride == 4 ? 1 : 0; }
+                        accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
+                    }
+                }
+                if (lane == 0) {
+                    S.nx = nx; S.ny = ny; S.accept = accept ? 1 : 0; S.near_valid = near_valid ? 1 : 0; S.t_status = t_status;
+                    if (accept && n < p.node_cap) s_link[n] = make_ushort2(NONE16, NONE16);  // children arrive through rewire
+                }
+            } else if (warp == 1) {
+                // ---- the circles around the NEXT sample (consumed by iteration it + 1 when its node lands on the sample) ----
+                if (it + 1 < p.max_iter && inside_play(p, smp_next.x, smp_next.y)) {
+                    const ObsList Ln = cull_obstacles_grid(grid, obs, n_obs, smp_next.x, smp_next.y, reach, S.cull[cb ^ 1][0],
+                                                           S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
+                    if (lane == 0) { S.cull_m[cb ^ 1] = Ln.m; S.cull_glob[cb ^ 1] = Ln.stride == 4 ? 1 : 0; }
+                }
+            } else if (!RRT_ONLY) {
+                if (count <= near_cap) cta_rank_near(S, count, tid - 64, CTA_T - 64);
+            }
+            __syncthreads();   // ---- B2
+            bool accept = S.accept != 0;
+            const double nx = S.nx, ny = S.ny;
+            int t_status = S.t_status;
+            if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
+            if (accept && RRT_ONLY) {
+                if (tid == 0) {
+                    s_xy[n] = make_double2(nx, ny); s_par[n] = (unsigned short)ni;
+                    xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni;
+                }
+                t_status = 2; t_par = ni;
+                n++;
+            } else if (accept) {
+                if (!S.near_valid) {
+                    // ---- find_near_nodes (rrt_04:1314-1338) around the new node (it is not the sample) ----
+                    if (tid == 0) S.count = 0;
+                    __syncthreads();
+                    for (int i = tid; i < n; i += CTA_T) {
+                        const double2 a = s_xy[i];
+                        const double ddx = a.x - nx, ddy = a.y - ny;
+                        const double d = ddx * ddx + ddy * ddy;
+                        if (d <= r2) {
+                            const int slot = atomicAdd(&S.count, 1);
+                            if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
+                        }
+                    }
+                    __syncthreads();
+                    count = S.count;
+                    if (count <= near_cap) cta_rank_near(S, count, tid, CTA_T);
+                    __syncthreads();
+                }
+                if (count > near_cap) {
+                    status |= RRTK_Q_NEAR_OVERFLOW;
+                    done = true;
+                } else {
+                    t_near = count;
+                    ObsList L;
+                    if (S.cull_glob[cb]) {
+                        const double *g = reinterpret_cast<const double *>(obs);
+                        L.ox = g; L.oy = g + 1; L.r2 = g + 3; L.stride = 4; L.m = n_obs;
+                    } else {
+                        L.ox = S.cull[cb][0]; L.oy = S.cull[cb][1]; L.r2 = S.cull[cb][2]; L.stride = 1; L.m = S.cull_m[cb];
+                    }
+                    const int sub = tid & (CTA_G - 1), grp = lane & ~(CTA_G - 1);
+                    // ---- choose_parent (rrt_04:1242-1282): CTA_G lanes per candidate, each tests its share of the circles ----
+                    double bc = INF, bex = 0.0, bey = 0.0;
+                    int bk = BIG;
+                    for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
+                        const int k = k0 + tid / CTA_G;
+                        const bool valid = k < count;
+                        double dk = 0.0, ci = 0.0, ex = nx, ey = ny;
+                        bool blocked = false, exact = false;
+                        if (valid) {
+                            const int i = S.near_idx[k];
+                            const double2 a = s_xy[i];
+                            ci = cost[i];
+                            dk = crm_hypot(nx - a.x, ny - a.y);   // what steer's calc_distance_and_angle returns
+                            const int vv = edge_verdict_fast(a.x, a.y, nx, ny, dk, INF, res, L, sub, CTA_G);
+                            blocked = vv == 0;                    // (the new node is inside the play area)
+                            if (vv < 0) {
+                                Steer st = steer(a.x, a.y, nx, ny, INF, res);
+                                blocked = !(edge_free_lane(a.x, a.y, st, nx, ny, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
+                                ex = st.ex; ey = st.ey;
+                                exact = true;
+                            }
+                        }
+                        const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << CTA_G) - 1u);
+                        const unsigned em = (__ballot_sync(FULL, exact) >> grp) & ((1u << CTA_G) - 1u);
+                        const int src = grp + (em ? __ffs(em) - 1 : 0);
+                        ex = __shfl_sync(FULL, ex, src);          // an exactly steered edge ends where ITS steer ends
+                        ey = __shfl_sync(FULL, ey, src);
+                        if (valid && sub == 0) {
+                            S.nd[k] = dk;      // = hypot(new - node), calc_new_cost's distance (rrt_04:1375-1377)
+                            S.s_nc[k] = ci;
+                            if (!bm) {
+                                if (TRACE) atomicAdd(&S.cpok, 1);
+                                const double c = ci + dk;
+                                if (c < bc) { bc = c; bk = k; bex = ex; bey = ey; }
+                            }
+                        }
+                    }
+                    {
+                        const double mine = bc;
+                        const int mk = bk;
+                        warp_argmin(bc, bk);   // first minimum of the cost list (this warp's candidates)
+                        const unsigned wm = __ballot_sync(FULL, mk == bk && mine == bc && bk != BIG);
+                        if (wm) {
+                            const int src = __ffs(wm) - 1;
+                            bex = __shfl_sync(FULL, bex, src);
+                            bey = __shfl_sync(FULL, bey, src);
+                        }
+                        if (lane == 0) { S.red_d[warp] = bc; S.red_i[warp] = bk; S.red_ex[warp] = bex; S.red_ey[warp] = bey; }
+                    }
+                    __syncthreads();   // ---- B3
+                    bc = S.red_d[0]; bk = S.red_i[0]; bex = S.red_ex[0]; bey = S.red_ey[0];
+#pragma unroll
+                    for (int w = 1; w < CTA_W; w++) {
+                        const double dw = S.red_d[w];
+                        const int kw = S.red_i[w];
+                        if (dw < bc || (dw == bc && kw < bk)) { bc = dw; bk = kw; bex = S.red_ex[w]; bey = S.red_ey[w]; }
+                    }
+                    if (bk != BIG) {
+                        const int best = S.near_idx[bk];
+                        // the node is re-steered from the winner (rrt_04:1279): same edge as above
+                        const double cx = bex, cy = bey, ccost = bc;
+                        const bool c_is_new = (cx == nx) && (cy == ny);  // the winner's edge snapped
+                        // ---- rewire (rrt_04:1340-1373), edges.  An entry can only be re-parented if node.cost > new.cost + d
+                        // (:1362); costs never increase while the apply loop runs (unless a node MOVES, handled there), so the
+                        // steer + collision of an entry that fails the test now is dead work.  With a trace every edge is
+                        // evaluated (the trace counts collision-free rewire edges).  Flags: 0 = not applicable, 1 = free and
+                        // ends on the node, 2 = free but the exact steer stops short of it (the node would MOVE). ----
+                        for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
+                            const int k = k0 + tid / CTA_G;
+                            const bool valid = k < count;
+                            double dk = 0.0;
+                            bool want = false, blocked = false, moves = false;
+                            if (valid) {
+                                const int i = S.near_idx[k];
+                                const double2 a = s_xy[i];
+                                // hypot(node - c) == the forward edge's d when c is the sample point itself
+                                dk = c_is_new ? S.nd[k] : crm_hypot(a.x - cx, a.y - cy);
+                                want = TRACE || (S.s_nc[k] > ccost + dk);
+                                if (want) {
+                                    const int vv = edge_verdict_fast(cx, cy, a.x, a.y, dk, INF, res, L, sub, CTA_G);
+                                    if (vv < 0) {
+                                        Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                                        blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
+                                        moves = (st.ex != a.x) || (st.ey != a.y);
+                                    } else {   // snapped: the edge ends on the node itself (it does not move)
+                                        blocked = !(vv == 1 && inside_play(p, a.x, a.y));
+                                    }
+                                }
+                            }
+                            const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << CTA_G) - 1u);
+                            const unsigned mm = (__ballot_sync(FULL, moves) >> grp) & ((1u << CTA_G) - 1u);
+                            if (valid && sub == 0) {
+                                if (!c_is_new) S.nd[k] = dk;
+                                S.near_ok[k] = (want && !bm) ? (mm ? 2 : 1) : 0;
+                            }
+                        }
+                        __syncthreads();   // ---- B4
+                        if (warp == 0) {
+                            // ---- rewire, ordered apply (rrt_04:1361-1371) + propagate_cost_to_leaves ----
+                            bool dirty = false;      // a propagate ran: node costs must be re-read
+                            int fallback_from = -1;  // >= 0: a node moved; redo entries from here serially
+                            for (int b0 = 0; b0 < count && fallback_from < 0; b0 += 32) {
+                                const int k = b0 + lane;
+                                int i = -1, fl = 0;
+                                double ecost = 0.0, snc = 0.0;
+                                if (k < count) {
+                                    i = S.near_idx[k];
+                                    fl = S.near_ok[k];
+                                    snc = S.s_nc[k];
+                                    ecost = ccost + S.nd[k];
+                                }
+                                const unsigned okmask = __ballot_sync(FULL, fl != 0);
+                                t_rwok += __popc(okmask);
+                                unsigned m = __ballot_sync(FULL, fl != 0 && (snc > ecost));
+                                while (m) {  // apply in list order
+                                    const int b = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const int ii = __shfl_sync(FULL, i, b);
+                                    const double ec = __shfl_sync(FULL, ecost, b);
+                                    const double c0 = __shfl_sync(FULL, snc, b);
+                                    const int flb = __shfl_sync(FULL, fl, b);
+                                    const double ci = dirty ? cost[ii] : c0;
+                                    if (ci > ec) {
+                                        const double2 a = s_xy[ii];
+                                        double ex = a.x, ey = a.y;
+                                        if (flb == 2) {   // the exact edge stops short of the node: it moves there
+                                            const Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                                            ex = st.ex; ey = st.ey;
+                                        }
+                                        const bool moved = (a.x != ex) || (a.y != ey);
+                                        __syncwarp();
+                                        if (lane == 0) {
+                                            cta_unlink(s_link, (int)s_par[ii], ii);
+                                            cta_link(s_link, n, ii);
+                                            if (moved) { s_xy[ii] = make_double2(ex, ey); xy[ii] = make_double2(ex, ey); }
+                                            cost[ii] = ec;
+                                            parent[ii] = n;
+                                            s_par[ii] = (unsigned short)n;
+                                        }
+                                        __syncwarp();
+                                        t_rwap++;
+                                        cta_propagate(ii, ec, s_xy, s_link, cost, S, g_idx, g_cost, lane);
+                                        __syncwarp();
+                                        dirty = true;
+                                        if (moved) {
+                                            // the node no longer sits where the parallel pass saw it, and the costs of its
+                                            // descendants may have gone UP: every later entry is re-evaluated from the current
+                                            // tree, one at a time
+                                            fallback_from = b0 + b + 1;
+                                            t_rwok -= __popc(okmask >> b >> 1);  // recounted below
+                                            break;
+                                        }
+                                    }
+                                }
+                            }
+                            if (fallback_from >= 0)
+                                cta_rewire_serial(p, fallback_from, count, S, s_xy, s_link, s_par, xy, cost, parent, n, cx, cy, ccost, L,
+                                                  g_idx, g_cost, lane, t_rwok, t_rwap);
+                            if (lane == 0) {
+                                s_xy[n] = make_double2(cx, cy); s_par[n] = (unsigned short)best;
+                                xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best;
+                                cta_link(s_link, best, n);
+                            }
+                        }
+                        t_status = 3; t_par = best;
+                    } else {
+                        if (tid == 0) {
+                            const double2 f0 = s_xy[ni];
+                            const double ncost = cost[ni] + crm_hypot(nx - f0.x, ny - f0.y);
+                            s_xy[n] = make_double2(nx, ny); s_par[n] = (unsigned short)ni;
+                            xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni;
+                            cta_link(s_link, ni, n);
+                        }
+                        t_status = 2; t_par = ni;
+                    }
+                    n++;
+                }
+            }
+            if (TRACE && tid == 0) {
+                int32_t *tr = trace + (size_t)it * 8;
+                tr[0] = ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = S.cpok;
+                tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
+            }
+            // ---- goal tests, by warp 0 (it wrote the last node itself) ----
+            if (warp == 0 && !done) {
+                __syncwarp();
+                if (RRT_ONLY) {
+                    // goal test on the last node (rrt_01:90-96)
+                    const double2 last = s_xy[n - 1];
+                    if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
+                        ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
+                        Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
+                        if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane) && lane == 0) { S.gi = n - 1; S.done = 1; }
+                    }
+                } else if (!p.search_until_max_iter) {
+                    bool ovf = false;
+                    // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
+                    ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
+                    const int g = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
+                    if (lane == 0) {
+                        if (ovf) S.status_or |= RRTK_Q_NEAR_OVERFLOW;
+                        if (g >= 0) { S.gi = g; S.done = 1; }
+                    }
+                }
+            }
+            if (tid == 0) { S.count = 0; S.cpok = 0; }
+            if (n != n_before) r2 = r2_grown;
+            __syncthreads();   // ---- B5
+            if (S.done) { gi = S.gi; done = true; }
+            if (done) { it++; break; }
+        }
+        status |= S.status_or;
+        if (!done && !RRT_ONLY && warp == 0) {
+            bool ovf = false;
+            ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[0][0], S.cull[0][1], S.cull[0][2], lane);
+            gi = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
+            if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
+        }
+        if (tid == 0) {
+            n_nodes[q] = n;
+            iters_done[q] = it_prev + it;
+            goal_index[q] = gi;
+            status_out[q] = status;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// near-list layout the launch uses: 256 entries (batches: four queries per SM at config 2) or 1024 (what the planner
+// classes ask for, the reference having no cap at all); 0 = does not fit
+static int cta_layout(const rrtk_rrtstar_params &p) {
+    if (p.node_cap > 65535) return 0;
+    if (p.near_cap <= CTA_NC_SMALL && cta_smem_bytes<CTA_NC_SMALL>(p.node_cap) <= 227 * 1024) return CTA_NC_SMALL;
+    if (!p.rrt_only && p.near_cap <= CTA_NC_LARGE && cta_smem_bytes<CTA_NC_LARGE>(p.node_cap) <= 227 * 1024) return CTA_NC_LARGE;
+    return 0;
+}
+bool rrtstar_cta_fits(const rrtk_rrtstar_params &p) { return cta_layout(p) != 0; }
+
+int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
+                       const int32_t *n_obs, const double *near_r2, const double *sample_stream,
+                       const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
+                       int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                       int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s) {
+    const int nc = cta_layout(p);
+    if (!nc)
+        return set_error(RRTK_ERR_INVALID, "exec_mode = CTA needs node_cap <= 65535, near_cap <= 1024 and 22 B / node + the near list "
+                                           "in 227 KB of shared memory");
+    const size_t smem = nc == CTA_NC_SMALL ? cta_smem_bytes<CTA_NC_SMALL>(p.node_cap) : cta_smem_bytes<CTA_NC_LARGE>(p.node_cap);
+    typedef void (*kernel_t)(rrtk_rrtstar_params, const double4 *, const double4 *, const int32_t *, const double *,
+                             const double2 *, const int64_t *, double2 *, double *, int32_t *, int32_t *, int32_t *,
+                             int32_t *, int32_t *, int32_t *, int32_t *, unsigned int *);
+    kernel_t kern;
+    if (p.rrt_only)
+        kern = p.resume ? rrtstar_cta_kernel<true, false, true, CTA_NC_SMALL>
+                        : (trace ? rrtstar_cta_kernel<true, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<true, false, false, CTA_NC_SMALL>);
+    else if (nc == CTA_NC_SMALL)
+        kern = p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_SMALL>
+                        : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<false, false, false, CTA_NC_SMALL>);
+    else
+        kern = p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_LARGE>
+                        : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_LARGE> : rrtstar_cta_kernel<false, false, false, CTA_NC_LARGE>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_cta_kernel)");
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_T, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;  // persistent: a multiple of the SM count
+    if (grid > p.n_queries) grid = p.n_queries;
+    if (grid < 1) grid = 1;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
+    kern<<<(unsigned)grid, CTA_T, smem, s>>>(
+        p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(obstacles),
+        n_obs, near_r2, reinterpret_cast<const double2 *>(sample_stream), sobol_offset,
+        reinterpret_cast<double2 *>(xy), cost, parent, n_nodes, iters_done, goal_index, status, trace,
+        workspace, counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rrtstar_cta_kernel launch");
+    return RRTK_OK;
+}
+
+}  // namespace rrtk

@@ -9,6 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRTK_LIB", os.path.join(HERE, "librrtk.so"))  # override: tuning builds only
 
 SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
+EXEC_AUTO, EXEC_WARP, EXEC_CTA = 0, 1, 2   # rrtk_rrtstar_params.exec_mode / rrtk_dubins_params.exec_mode
+WS_TAIL_INTS = 4                           # RRTK_WS_TAIL_INTS: every planner workspace ends with the work-queue counter
 Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW, Q_DIV_ZERO = 0, 1, 2, 4, 8
 
 
@@ -26,7 +28,8 @@ class RRTStarParams(C.Structure):
                 ("path_resolution", C.c_double), ("min_rand", C.c_double),
                 ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64),
                 ("grid_nx", C.c_int32), ("grid_ny", C.c_int32), ("grid_x0", C.c_double),
-                ("grid_y0", C.c_double), ("grid_cell", C.c_double), ("resume", C.c_int32), ("iter_offset", C.c_int32)]
+                ("grid_y0", C.c_double), ("grid_cell", C.c_double), ("resume", C.c_int32), ("iter_offset", C.c_int32),
+                ("near_r_max", C.c_double), ("exec_mode", C.c_int32), ("pad_", C.c_int32)]
 
 
 class InformedParams(C.Structure):

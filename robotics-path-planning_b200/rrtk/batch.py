@@ -64,16 +64,22 @@ class RRTStarBatch:
         if sample_stream is not None:
             ss = np.ascontiguousarray(np.asarray(sample_stream, dtype=np.float64).reshape(q, self.max_iter, 2))
             self.sample_stream = torch.from_numpy(ss).to(self.device)
+        # device copies of the scenario: allocated ONCE and refilled in place by upload(), so a BatchResult, a captured
+        # CUDA graph and the path extraction all keep reading the tensors the kernel planned against
+        self.start_goal = torch.empty_like(self.h_start_goal, device=self.device)
+        self.obstacles = torch.empty_like(self.h_obstacles, device=self.device)
+        self.n_obs = torch.empty_like(self.h_n_obs, device=self.device)
         self.upload()
         self.result = None
         self._iters_done = 0
 
     # ---- data movement ----
     def upload(self):
-        """Host -> device copy of the scenario (start/goal, obstacle rows, counts)."""
-        self.start_goal = self.h_start_goal.to(self.device, non_blocking=True)
-        self.obstacles = self.h_obstacles.to(self.device, non_blocking=True)
-        self.n_obs = self.h_n_obs.to(self.device, non_blocking=True)
+        """Host -> device copy of the scenario (start/goal, obstacle rows, counts), in place: refill the pinned staging
+        tensors (h_start_goal, h_obstacles, h_n_obs) and call upload() / replay() to plan a new scenario."""
+        self.start_goal.copy_(self.h_start_goal, non_blocking=True)
+        self.obstacles.copy_(self.h_obstacles, non_blocking=True)
+        self.n_obs.copy_(self.h_n_obs, non_blocking=True)
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.h_start_goal, self.h_obstacles, self.h_n_obs))

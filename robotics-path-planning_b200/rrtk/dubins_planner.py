@@ -70,7 +70,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)    # noqa: E731
         xy, yaw, cost, parent = f64(q, cap, 2), f64(q, cap), f64(q, cap), i32(q, cap)
         ef, et = f64(q, cap, 3), f64(q, cap, 3)
-        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q, 4 * cap)
+        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(q * 4 * cap + _lib.WS_TAIL_INTS)
         entry = _lib.lib().rrtk_rrtstar_dubins_run_dev if steer == "dubins" else _lib.lib().rrtk_rrtstar_rs_run_dev
         if timing is not None:
             ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -154,7 +154,9 @@ class RRTStarDubins:
 
     def planning(self, animation=True, search_until_max_iter=True, sample_stream=None):
         n = int(self.max_iter)
+        rng_state = None
         if sample_stream is None:
+            rng_state = random.getstate()
             sample_stream = np.array([self.get_random_node() for _ in range(n)], dtype=np.float64)
         stream = np.asarray(sample_stream, dtype=np.float64).reshape(-1, 3)[:n]
         start = (self.start.x, self.start.y, self.start.yaw)
@@ -165,6 +167,11 @@ class RRTStarDubins:
         if t["status"] & _lib.Q_NEAR_OVERFLOW:
             raise _lib.RrtkError("near list overflow: raise near_cap")
         self._tree = t
+        if rng_state is not None and t["iters_done"] < n:
+            # early exit: leave `random` where the reference's lazily drawing loop would have left it
+            random.setstate(rng_state)
+            for _ in range(t["iters_done"]):
+                self.get_random_node()
         nodes = [Node(float(x), float(y), float(w)) for x, y, w in zip(t["x"], t["y"], t["yaw"])]
         for i, nd in enumerate(nodes):
             nd.cost = float(t["cost"][i])

@@ -63,7 +63,7 @@ class BatchResult:
     status: "object"      # [Q] int32 (RRTK_Q_* bits)
     trace: "object"       # [Q, max_iter, 8] int32 or None
     start_goal: "object"  # [Q, 4] float64
-    workspace: "object" = None  # [Q, workspace_ints(p)] int32 scratch (children lists, frontier, obstacle cells)
+    workspace: "object" = None  # [Q * workspace_ints(p) + WS_TAIL_INTS] int32 scratch (children lists, frontier, obstacle cells, queue counter)
 
     def paths_device(self, path_cap: int | None = None):
         """generate_final_course for every query on the GPU -> (path [Q, path_cap, 2], length [Q])."""
@@ -89,7 +89,7 @@ class BatchResult:
 def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_resolution,
                 play_area=None, search_until_max_iter=True, sampler=_lib.SAMPLER_STREAM,
                 goal_sample_rate=5, min_rand=0.0, max_rand=0.0, seed=0, near_cap=256,
-                rrt_only=False) -> _lib.RRTStarParams:
+                rrt_only=False, near_r_max=0.0, exec_mode=None) -> _lib.RRTStarParams:
     p = _lib.RRTStarParams()
     p.n_queries, p.max_iter, p.node_cap = int(n_queries), int(max_iter), int(node_cap)
     p.obs_stride, p.near_cap = int(obs_stride), int(near_cap)
@@ -103,13 +103,28 @@ def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_reso
     p.expand_dis, p.path_resolution = float(expand_dis), float(path_resolution)
     p.min_rand, p.max_rand = float(min_rand), float(max_rand)
     p.seed = int(seed) & ((1 << 64) - 1)
+    p.near_r_max = float(near_r_max)          # 0 = the table is clipped to expand_dis (rrt_04:1333-1335)
+    p.exec_mode = default_exec_mode() if exec_mode is None else int(exec_mode)
     return p
+
+
+def default_exec_mode() -> int:
+    """RRTK_EXEC_*: AUTO unless the environment variable RRTK_EXEC (auto | warp | cta) says otherwise (tuning, tests)."""
+    import os
+    return {"auto": _lib.EXEC_AUTO, "warp": _lib.EXEC_WARP, "cta": _lib.EXEC_CTA}[os.environ.get("RRTK_EXEC", "auto").lower()]
+
+
+def near_r_max_of(table: np.ndarray, expand_dis) -> float:
+    """Upper bound of the near radius for rrtk_rrtstar_params.near_r_max: 0 when the table is clipped to expand_dis."""
+    if expand_dis is not None or table is None or len(table) < 2:
+        return 0.0
+    return math.sqrt(float(np.max(table[1:]))) * (1.0 + 1e-12)
 
 
 def set_obstacle_grid(p: _lib.RRTStarParams, xmin, xmax, ymin, ymax) -> None:
     """Cell grid for the per-iteration obstacle cull (struct rrtk_rrtstar_params.grid_*).  The box must contain
     every sample, start and goal; nodes outside it are handled by the full scan, so this only affects speed."""
-    reach = p.expand_dis + p.path_resolution
+    reach = max(p.expand_dis, p.near_r_max) + p.path_resolution
     if not (math.isfinite(xmin) and math.isfinite(xmax) and math.isfinite(ymin) and math.isfinite(ymax)) \
             or not reach > 0.0 or xmax < xmin or ymax < ymin:
         p.grid_nx = p.grid_ny = 0
@@ -146,7 +161,7 @@ def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample
             status=torch.empty((q,), dtype=torch.int32, device=dev),
             trace=torch.zeros((q, p.max_iter, 8), dtype=torch.int32, device=dev) if want_trace else None,
             start_goal=start_goal,
-            workspace=torch.empty((q, workspace_ints(p)), dtype=torch.int32, device=dev))
+            workspace=torch.empty((q * workspace_ints(p) + _lib.WS_TAIL_INTS,), dtype=torch.int32, device=dev))
     ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     rc = _lib.lib().rrtk_rrtstar_run_dev(
         C.byref(p), ptr(start_goal), ptr(obstacles), ptr(n_obs), ptr(near_r2), ptr(sample_stream),

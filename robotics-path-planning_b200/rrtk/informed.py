@@ -94,7 +94,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples,
         plen = torch.empty((q,), dtype=torch.int32, device=dev)
         c_best = torch.empty((q,), dtype=torch.float64, device=dev)
         status = torch.empty((q,), dtype=torch.int32, device=dev)
-        ws_idx = torch.empty((q, cap), dtype=torch.int32, device=dev)
+        ws_idx = torch.empty((q * cap + _lib.WS_TAIL_INTS,), dtype=torch.int32, device=dev)
         ws_d = torch.empty((q, cap), dtype=torch.float64, device=dev)
         rc = _lib.lib().rrtk_informed_run_dev(
             C.byref(p), d_sg.data_ptr(), d_rot.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_near.data_ptr(),

@@ -120,7 +120,9 @@ class RRT:
         torch = _lib.require_cuda()
         max_iter = int(self.max_iter)
         goal = (float(self.end.x), float(self.end.y))
+        rng_state, sobol_first = None, self.sobol_inter_
         if sample_stream is None:
+            rng_state = random.getstate()
             stream, _, nxt = sampling.draw_stream(max_iter, goal, self.min_rand, self.max_rand,
                                                   self.goal_sample_rate, self.sobol_sampler,
                                                   self.sobol_inter_, random)
@@ -136,7 +138,8 @@ class RRT:
                                self.path_resolution, self._play_tuple(),
                                self._search_until_max_iter(), _lib.SAMPLER_STREAM,
                                self.goal_sample_rate, self.min_rand, self.max_rand,
-                               near_cap=self._near_cap(node_cap), rrt_only=self._rrt_only)
+                               near_cap=self._near_cap(node_cap), rrt_only=self._rrt_only,
+                               near_r_max=engine.near_r_max_of(self._near_table(node_cap), self.expand_dis))
         if max_iter > 0:   # obstacle cell grid over everything a node can be (samples, start, goal)
             bx = [float(stream[:, 0].min()), float(stream[:, 0].max()), float(self.start.x), goal[0]]
             by = [float(stream[:, 1].min()), float(stream[:, 1].max()), float(self.start.y), goal[1]]
@@ -152,6 +155,13 @@ class RRT:
             want_trace=want_trace)
         n = int(res.n_nodes[0].item())
         self.iters_done = int(res.iters_done[0].item())
+        if rng_state is not None and self.iters_done < max_iter:
+            # early exit (first goal connection): the reference draws lazily, so leave `random` and sobol_inter_ where
+            # ITS loop would have left them -- a seeded script that goes on to path_smoothing / a second planning()
+            # then sees the reference's draws
+            random.setstate(rng_state)
+            self.sobol_inter_ = sobol_first + sampling.consume_draws(
+                self.iters_done, self.goal_sample_rate, self.sobol_sampler, self.min_rand, self.max_rand, random)
         gi = int(res.goal_index[0].item())
         self.goal_index = None if gi < 0 else gi
         self.status = int(res.status[0].item())

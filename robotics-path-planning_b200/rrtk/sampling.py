@@ -51,6 +51,21 @@ def draw_stream(max_iter, goal_xy, min_rand, max_rand, goal_sample_rate, sobol_s
     return stream, is_goal, sobol_first
 
 
+def consume_draws(iters, goal_sample_rate, sobol_sampler, min_rand, max_rand, rng=random):
+    """Advance `rng` by exactly the draws `iters` iterations of the reference's loop make (rrt_04:1132-1153) and return the
+    number of non-goal iterations among them (= how far `sobol_inter_` moves).  Used after an early exit: the stream is
+    pre-drawn for max_iter iterations, the reference draws lazily, so the RNG is rewound and re-advanced to where the
+    reference's would stand."""
+    non_goal = 0
+    for _ in range(iters):
+        if rng.randint(0, 100) > goal_sample_rate:
+            non_goal += 1
+            if not sobol_sampler:
+                rng.uniform(min_rand, max_rand)
+                rng.uniform(min_rand, max_rand)
+    return non_goal
+
+
 # ---- the in-kernel counter-based sampler, restated on the host (tests, CPU baselines) ----
 _M64 = (1 << 64) - 1
 

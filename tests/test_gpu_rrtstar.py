@@ -23,6 +23,14 @@ RRT04 = golden_names("rrt04_")
 CR_EXACT = [n for n in RRT04 if n != "rrt04_c2_o256_800"]
 
 
+@pytest.fixture(autouse=True, params=["cta", "warp"])
+def exec_mode(request, monkeypatch):
+    """Every test of this module runs under both executions of the loop (rrtk_rrtstar_params.exec_mode): one CTA per query
+    with the tree in shared memory, and one warp per query.  RRTK_EXEC is read by engine.make_params."""
+    monkeypatch.setenv("RRTK_EXEC", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
@@ -310,6 +318,7 @@ def test_incremental_steps_build_the_same_trees(sampler):
         rb = b.step(150)
     n = ra.n_nodes.cpu().numpy()
     assert np.array_equal(n, rb.n_nodes.cpu().numpy()) and n.min() > 100
+    assert (rb.iters_done.cpu().numpy() == iters).all()          # cumulative over the steps
     assert np.array_equal(ra.goal_index.cpu().numpy(), rb.goal_index.cpu().numpy())
     xa, xb = ra.xy.cpu().numpy(), rb.xy.cpu().numpy()
     ca, cb = ra.cost.cpu().numpy(), rb.cost.cpu().numpy()
@@ -364,3 +373,103 @@ def test_captured_graph_replay_matches_plain_call():
     b.replay()
     torch.cuda.synchronize()
     assert torch.equal(h_plen[2:], want_len.cpu()[2:])
+
+
+@pytest.mark.gpu
+def test_replay_and_upload_follow_new_goals():
+    """Refilling h_start_goal in place changes what the NEXT replay() / upload() + run() plans to AND the goal waypoint
+    paths_device() writes as path[0] (the result keeps reading the tensor the kernel planned against)."""
+    import torch
+    import rrtk
+    from rrtk import workloads as W
+    cfg = W.C2
+    Q, iters, cap = 8, 400, 160
+    rows = W.c2_rows(list(range(Q)), 32)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1))
+    goals = np.tile(np.array(cfg["goal"]), (Q, 1))
+    goals2 = goals.copy()
+    goals2[:, 0] -= 2.5
+    goals2[:, 1] -= 1.25
+    mk = lambda g: rrtk.RRTStarBatch(starts, g, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],  # noqa: E731
+                                     cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol",
+                                     cfg["connect_circle_dist"], True, seed=5)
+    want_path, want_len = mk(goals2).run().paths_device(cap)
+    assert int((want_len > 0).sum()) > 0
+    # (1) through the captured graph
+    b = mk(goals)
+    h_path = torch.empty((Q, cap, 2), dtype=torch.float64).pin_memory()
+    h_plen = torch.empty((Q,), dtype=torch.int32).pin_memory()
+    b.capture(h_path, h_plen, cap)
+    b.h_start_goal[:, 2:4] = torch.from_numpy(goals2)
+    b.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(h_plen, want_len.cpu())
+    for q in range(Q):
+        k = int(h_plen[q])
+        assert torch.equal(h_path[q, :k], want_path[q, :k].cpu())
+        if k:
+            assert h_path[q, 0].tolist() == goals2[q].tolist()
+    # (2) plain upload() + run() on an existing result
+    c = mk(goals)
+    c.run()
+    c.h_start_goal[:, 2:4] = torch.from_numpy(goals2)
+    c.upload()
+    got_path, got_len = c.run().paths_device(cap)
+    assert torch.equal(got_len, want_len) and torch.equal(got_path[got_len > 0][:, 0], want_path[want_len > 0][:, 0])
+
+
+@pytest.mark.gpu
+def test_incremental_steps_leave_finished_queries_alone():
+    """resume = 1 with search_until_max_iter = False: a query that connected to the goal in an earlier step is not grown
+    any further (its tree, goal index and cumulative iteration count stay), so stepping gives the single run's result."""
+    import rrtk
+    from rrtk import workloads as W
+    cfg = W.C2
+    Q, iters = 10, 900
+    rows = W.c2_rows(list(range(Q)), 24)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1))
+    goals = np.tile(np.array([6.0, 7.0]), (Q, 1))
+    mk = lambda: rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],  # noqa: E731
+                                   cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol",
+                                   cfg["connect_circle_dist"], False, seed=11)
+    ra = mk().run()
+    it_a = ra.iters_done.cpu().numpy()
+    assert (it_a < iters).any(), "the scene should let some queries finish early"
+    b = mk()
+    for _ in range(6):
+        rb = b.step(150)
+    assert np.array_equal(it_a, rb.iters_done.cpu().numpy())
+    assert np.array_equal(ra.n_nodes.cpu().numpy(), rb.n_nodes.cpu().numpy())
+    assert np.array_equal(ra.goal_index.cpu().numpy(), rb.goal_index.cpu().numpy())
+    n = ra.n_nodes.cpu().numpy()
+    xa, xb, pa, pb = ra.xy.cpu().numpy(), rb.xy.cpu().numpy(), ra.parent.cpu().numpy(), rb.parent.cpu().numpy()
+    for q in range(Q):
+        assert np.array_equal(xa[q, :n[q]], xb[q, :n[q]]) and np.array_equal(pa[q, :n[q]], pb[q, :n[q]])
+
+
+@pytest.mark.gpu
+def test_cta_and_warp_executions_agree_on_a_ragged_batch():
+    """The two executions of the loop on one batch with ragged obstacle counts, a play area and a near radius that is not
+    clipped for the first nodes: identical trees, costs and goal indices."""
+    import rrtk
+    from rrtk import _lib, engine, workloads as W
+    cfg = W.C2
+    Q, iters = 40, 700
+    rng = np.random.default_rng(21)
+    rows = W.c2_rows(list(range(Q)), 48)
+    n_obs = rng.integers(0, 49, Q).astype(np.int32)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1)); goals = rng.uniform(4.0, 13.0, (Q, 2))
+    out = {}
+    for mode in ("warp", "cta"):
+        os.environ["RRTK_EXEC"] = mode
+        b = rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], 1.5, 0.25, cfg["goal_sample_rate"], iters,
+                              [-1.0, 14.0, -1.5, 14.5], cfg["robot_radius"], "uniform", 3.0, True, seed=13, n_obs=n_obs)
+        assert b.params.exec_mode == {"warp": _lib.EXEC_WARP, "cta": _lib.EXEC_CTA}[mode]
+        r = b.run()
+        out[mode] = [t.cpu().numpy() for t in (r.n_nodes, r.goal_index, r.status, r.xy, r.cost, r.parent)]
+    a, c = out["warp"], out["cta"]
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]) and np.array_equal(a[2], c[2])
+    for q in range(Q):
+        k = a[0][q]
+        assert np.array_equal(a[3][q, :k], c[3][q, :k]) and np.array_equal(a[4][q, :k], c[4][q, :k])
+        assert np.array_equal(a[5][q, :k], c[5][q, :k])
