@@ -119,7 +119,9 @@ typedef struct rrtk_rrtstar_params {
      * RRTK_EXEC_CTA = one CTA of 4 warps per query, tree (positions, children lists, parents) in shared memory --
      * needs node_cap <= 65535 and 22 B / node + the near list in <= 227 KB; RRTK_EXEC_AUTO picks CTA when it fits. */
     int32_t exec_mode;
-    int32_t pad_;
+    /* global index of this launch's query 0: the in-kernel samplers key their counter-based RNG by (seed, query_base + q,
+     * iteration), so a shard of a larger batch draws exactly what the unsharded batch draws for the same queries */
+    int32_t query_base;
 } rrtk_rrtstar_params;
 
 #define RRTK_EXEC_AUTO 0
@@ -132,7 +134,8 @@ typedef struct rrtk_rrtstar_params {
 
 /* ints of workspace per query for rrtk_rrtstar_run_dev */
 #define RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny) \
-    (4 * (size_t)(node_cap) + 4 * ((17 * (size_t)(grid_nx) * (size_t)(grid_ny) + 3) / 4)) /* multiple of 4: 16-byte rows */
+    (4 * (size_t)(node_cap) + 4 * (((size_t)(node_cap) + 1) / 2) + \
+     4 * ((17 * (size_t)(grid_nx) * (size_t)(grid_ny) + 3) / 4)) /* three parts, each a multiple of 4: 16-byte rows */
 
 /* Device-pointer entry point.
  *   start_goal   [Q][4]                 sx, sy, gx, gy
@@ -149,8 +152,9 @@ typedef struct rrtk_rrtstar_params {
  *   trace [Q][max_iter][8] or NULL: nearest, status, n_near, parent, cp_ok, rw_ok, rw_applied, n_after
  * scratch (caller allocated, contents undefined afterwards):
  *   workspace [Q][RRTK_RRTSTAR_WS_INTS(node_cap, grid_nx, grid_ny)] + [RRTK_WS_TAIL_INTS] int32: children lists (first
- *             child, next / previous sibling), the breadth-first frontier of propagate_cost_to_leaves, the obstacle
- *             cell lists (per cell a count + 32 uint16 indices), then the work-queue counter; 16-byte aligned
+ *             child, next / previous sibling) and the breadth-first frontier of propagate_cost_to_leaves, the cached edge
+ *             lengths hypot(node - parent) (doubles), the obstacle cell lists (per cell a count + 32 uint16 indices),
+ *             then the work-queue counter; 16-byte aligned
  */
 RRTK_API int rrtk_rrtstar_run_dev(const rrtk_rrtstar_params *p, const double *start_goal,
                          const double *obstacles, const int32_t *n_obs, const double *near_r2,

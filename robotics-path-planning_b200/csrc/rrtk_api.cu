@@ -101,6 +101,7 @@ static int check_params(const rrtk_rrtstar_params *p) {
     if ((p->resume != 0 && p->resume != 1) || p->iter_offset < 0) return set_error(RRTK_ERR_INVALID, "resume must be 0 / 1, iter_offset >= 0");
     if (!(p->near_r_max >= 0.0)) return set_error(RRTK_ERR_INVALID, "near_r_max must be >= 0 (0 = expand_dis)");
     if (p->exec_mode < RRTK_EXEC_AUTO || p->exec_mode > RRTK_EXEC_CTA) return set_error(RRTK_ERR_INVALID, "unknown exec_mode");
+    if (p->query_base < 0) return set_error(RRTK_ERR_INVALID, "query_base must be >= 0");
     return RRTK_OK;
 }
 

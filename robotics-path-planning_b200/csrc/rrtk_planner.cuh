@@ -186,4 +186,41 @@ static __device__ __noinline__ void propagate_lists(int root, const double2 *xy,
     }
 }
 
+// The same walk with cached edge lengths: elen[c] = hypot(c - parent(c)), exactly what calc_new_cost (rrt_04:1375-1377)
+// recomputes at every visit -- positions only change when a re-parented node MOVES, so the value is kept from the
+// moment the edge was made (choose_parent / rewire computed it then) and the serial hypot leaves the walk.  NaN = not
+// known (edges made by an exact steer that stopped short, resumed trees): computed here and stored.  `root_moved`: the
+// root's own position just changed, so the lengths of its child edges are stale.
+static __device__ __noinline__ void propagate_lists_elen(int root, bool root_moved, const double2 *xy, double *cost, double *elen,
+                                                         int4 *links, int *tail, int lane) {
+    if (links[root].x < 0) return;
+    if (lane == 0) { links[0].w = root; *tail = 1; }
+    __syncwarp();
+    for (int head = 0;;) {
+        const int end = *tail;
+        if (head >= end) break;
+        const int k = head + lane;
+        __syncwarp();
+        if (k < end) {
+            const int p = links[k].w;
+            const double cp = cost[p];
+            const bool stale = root_moved && p == root;
+            for (int c = links[p].x; c >= 0;) {
+                const int4 lc = links[c];
+                double e = elen[c];
+                if (stale || e != e) {
+                    const double2 a = xy[p], b = xy[c];
+                    e = crm_hypot(b.x - a.x, b.y - a.y);
+                    elen[c] = e;
+                }
+                cost[c] = cp + e;
+                if (lc.x >= 0) links[atomicAdd(tail, 1)].w = c;
+                c = lc.y;
+            }
+        }
+        __syncwarp();
+        head = end < head + 32 ? end : head + 32;
+    }
+}
+
 }  // namespace rrtk

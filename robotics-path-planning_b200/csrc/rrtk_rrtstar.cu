@@ -65,7 +65,7 @@ __device__ __noinline__ int near_scan(const double2 *xy, int n, double cx, doubl
 // rewire entries [from, count) one at a time against the current tree (after a re-parented node MOVED, rrt_04:1365-1371:
 // the parallel pass's view of positions and costs is stale).  Out of line: rare.
 __device__ __noinline__ void rewire_serial(const rrtk_rrtstar_params &p, int from, int count, const int *near_idx, double2 *xy,
-                                          double *cost, int32_t *parent, int4 *links, int n, double cx, double cy,
+                                          double *cost, int32_t *parent, int4 *links, double *elen, int n, double cx, double cy,
                                           double ccost, const ObsList &L, int *qtail, int lane, int &t_rwok, int &t_rwap) {
     const double res = p.path_resolution;
     for (int k = from; k < count; k++) {
@@ -83,10 +83,15 @@ __device__ __noinline__ void rewire_serial(const rrtk_rrtstar_params &p, int fro
                 xy[i] = make_double2(st.ex, st.ey);
                 cost[i] = ec;
                 parent[i] = n;
+                elen[i] = __longlong_as_double(0x7ff8000000000000ll);   // (the node may have moved: recomputed on demand)
             }
             __syncwarp();
             t_rwap++;
+#ifdef RRTK_V_NOELEN
             propagate_lists(i, xy, cost, links, qtail, lane);
+#else
+            propagate_lists_elen(i, true, xy, cost, elen, links, qtail, lane);
+#endif
         }
     }
 }
@@ -157,13 +162,16 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         int32_t *trace = TRACE ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
-        // children lists + the propagate frontier: 4 * node_cap ints of scratch per query
+        // scratch of the query: children lists + the propagate frontier (4 * node_cap ints), the cached edge lengths
+        // elen[i] = hypot(node i - its parent) (node_cap doubles; NaN = not known, recomputed on demand), obstacle cells
         const int grid_cells = p.grid_nx * p.grid_ny;
         int4 *links = reinterpret_cast<int4 *>(workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny));
+        double *elen = reinterpret_cast<double *>(links + p.node_cap);
+        const double NaN = __longlong_as_double(0x7ff8000000000000ll);
         ObsGrid grid;
         grid.nx = p.grid_nx; grid.ny = p.grid_ny; grid.x0 = p.grid_x0; grid.y0 = p.grid_y0;
         grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
-        grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap);
+        grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap) + 4 * (size_t)((p.node_cap + 1) / 2);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
         // every path point of an iteration's edges lies within `reach` of its new node (a snapped first edge starts up to
         // expand_dis + res away; near nodes are within the near radius, <= expand_dis unless near_r_max says otherwise)
@@ -177,6 +185,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                 cost[0] = 0.0;
                 parent[0] = -1;
                 links[0] = make_int4(-1, -1, -1, 0);
+                elen[0] = 0.0;
             }
         } else {
             // continue the tree a previous call left in xy / cost / parent (rows 0 .. n_nodes[q] - 1): rebuild the children
@@ -189,20 +198,21 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
                 ((RRT_ONLY || !p.search_until_max_iter) && goal_index[q] >= 0))
                 continue;   // uniform
             if (n < 1 || n > p.node_cap) { n = 1; status |= RRTK_Q_NODE_OVERFLOW; }
-            for (int i = lane; i < n; i += 32) links[i] = make_int4(-1, -1, -1, 0);
+            for (int i = lane; i < n; i += 32) { links[i] = make_int4(-1, -1, -1, 0); elen[i] = NaN; }
             __syncwarp();
             if (lane == 0)
                 for (int i = 1; i < n; i++) { const int pp = parent[i]; if (pp >= 0 && pp < n) link_child(links, pp, i); }
             if (p.sampler == RRTK_SAMPLER_SOBOL) {
                 int used = 0;
                 for (int k = lane; k < p.iter_offset; k += 32)
-                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)q, (uint64_t)k)) % 101ull) > p.goal_sample_rate;
+                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)(q + p.query_base), (uint64_t)k)) % 101ull) > p.goal_sample_rate;
                 sob.n += (int64_t)__reduce_add_sync(FULL, (unsigned)used);
             }
         }
         __syncwarp();
         if (grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, reach, lane);
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
+        const double inv_res = 1.0 / res, q_expand = floor(p.expand_dis / res);   // steer's n_expand at full extension
         sobol2(sob.n, sob.q0, sob.q1);
         bool done = false;
 
@@ -249,15 +259,21 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             // sample the new node IS the sample and only the collision verdict is needed (edge_verdict_fast);
             // otherwise, or when the verdict is too close to call, the exact steer runs ----
             double nx = rx, ny = ry;
+            // (the verdict keeps a 1e-9 margin on every use of the edge length: a plain sqrt is as good as the correctly
+            // rounded hypot here; the exact steer computes its own)
+#ifdef RRTK_V_HYPOT0
             const double d0 = crm_hypot(rx - from.x, ry - from.y);
+#else
+            const double ddx0 = rx - from.x, ddy0 = ry - from.y;
+            const double d0 = sqrt(ddx0 * ddx0 + ddy0 * ddy0);
+#endif
             int v = -1;
             {
-                const double ext = p.expand_dis > d0 ? d0 : p.expand_dis;
-                const double q0 = floor(ext / res);
-                if (d0 > 0.0 && d0 - q0 * res <= res * (1.0 - 1e-9)) {   // same snap test as edge_verdict_fast
+                if (snap_certain(d0, false, p.expand_dis, q_expand, res, inv_res)) {
                     if (inside_play(p, nx, ny)) {
                         L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
-                        const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, p.expand_dis, res, L, lane, 32);
+                        const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
+                                                         lane, 32, ~0ull).v;
                         const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                         v = blocked ? 0 : (unsure ? -1 : 1);
                         if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
@@ -284,7 +300,8 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     __syncwarp();
                 } else if (accept) {
                     if (lane == 0) links[n] = make_int4(-1, -1, -1, 0);  // children arrive through rewire, before the append
-                    const double ncost = cost[ni] + crm_hypot(nx - from.x, ny - from.y);
+                    const double nlen = crm_hypot(nx - from.x, ny - from.y);
+                    const double ncost = cost[ni] + nlen;
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
                     if (!near_valid) count = near_scan(xy, n, nx, ny, r2, near_idx, nd, near_cap, lane);
                     __syncwarp();
@@ -307,13 +324,17 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                         // ---- choose_parent (rrt_04:1242-1282): one lane per candidate ----
                         double bc = INF, bex = 0.0, bey = 0.0;
                         int bk = 0x7fffffff;
+                        // circles near the segment candidate `lane` - new node (first round), for the reverse edge in rewire
+                        unsigned long long seg_near = ~0ull;
                         for (int k = lane; k < count; k += 32) {
                             int i = near_idx[k];
                             double2 a = xy[i];
                             double ci = cost[i];
                             const double dk = crm_hypot(nx - a.x, ny - a.y);  // what steer's calc_distance_and_angle returns
                             double ex = nx, ey = ny;                          // a snapped edge ends on the new node
-                            const int v = edge_verdict_fast(a.x, a.y, nx, ny, dk, INF, res, L, 0, 1);
+                            const EdgeVerdict ev = edge_verdict_fast(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull);
+                            const int v = ev.v;
+                            if (k < 32) seg_near = v == 1 ? ev.near : ~0ull;
                             bool ok = v == 1;                                 // (the new node is inside the play area)
                             if (v < 0) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
@@ -368,8 +389,18 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                     ecost = ccost + dk;
                                     want = TRACE || (snc > ecost);
                                 }
-                                if (want) {
-                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, INF, res, L, 0, 1);
+                                // the reverse edge runs along the segment choose_parent tested (when the new node is the
+                                // sample): only the circles found near it then can matter, usually none
+#ifdef RRTK_V_NOMASK
+                                const unsigned long long only = ~0ull;
+#else
+                                const unsigned long long only = (c_is_new && b0 == 0) ? seg_near : ~0ull;
+#endif
+                                if (want && only == 0ull) {
+                                    st.ex = a.x; st.ey = a.y;
+                                    ok = inside_play(p, a.x, a.y);
+                                } else if (want) {
+                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, 0, 1, only).v;
                                     if (v < 0) {
                                         st = steer(cx, cy, a.x, a.y, INF, res);
                                         ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
@@ -389,6 +420,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                     const double ex = __shfl_sync(FULL, st.ex, b), ey = __shfl_sync(FULL, st.ey, b);
                                     const double ax = __shfl_sync(FULL, a.x, b), ay = __shfl_sync(FULL, a.y, b);
                                     const double c0 = __shfl_sync(FULL, snc, b);
+                                    const double dkb = __shfl_sync(FULL, dk, b);
                                     const double ci = dirty ? cost[ii] : c0;
                                     if (ci > ec) {
                                         const bool moved = (ax != ex) || (ay != ey);
@@ -399,10 +431,15 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                             xy[ii] = make_double2(ex, ey);
                                             cost[ii] = ec;
                                             parent[ii] = n;
+                                            elen[ii] = moved ? NaN : dkb;   // hypot(node - new node), what propagate would compute
                                         }
                                         __syncwarp();
                                         t_rwap++;
+#ifdef RRTK_V_NOELEN
                                         propagate_lists(ii, xy, cost, links, &ws->qtail, lane);
+#else
+                                        propagate_lists_elen(ii, moved, xy, cost, elen, links, &ws->qtail, lane);
+#endif
                                         dirty = true;
                                         if (moved) {
                                             // the node no longer sits where the parallel pass saw it, and the
@@ -416,12 +453,18 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                 }
                             }
                             if (fallback_from >= 0)
-                                rewire_serial(p, fallback_from, count, near_idx, xy, cost, parent, links, n, cx, cy, ccost, L,
+                                rewire_serial(p, fallback_from, count, near_idx, xy, cost, parent, links, elen, n, cx, cy, ccost, L,
                                               &ws->qtail, lane, t_rwok, t_rwap);
-                            if (lane == 0) { xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(links, best, n); }
+                            if (lane == 0) {
+                                xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(links, best, n);
+                                elen[n] = c_is_new ? nd[bk] : NaN;   // hypot(new node - parent) as long as the node sits on the sample
+                            }
                             t_status = 3; t_par = best;
                         } else {
-                            if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; link_child(links, ni, n); }
+                            if (lane == 0) {
+                                xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; link_child(links, ni, n);
+                                elen[n] = nlen;
+                            }
                             t_status = 2; t_par = ni;
                         }
                         n++;

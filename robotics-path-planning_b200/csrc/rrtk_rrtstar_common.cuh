@@ -76,29 +76,76 @@ static __device__ __noinline__ bool edge_free_lane(double fx, double fy, const S
 // Cheap verdict of the edge f -> t steered with extend_length = inf (choose_parent / rewire candidates), WITHOUT the
 // correctly rounded atan2/cos/sin: the reference's path points are f, f + k * res * (cos, sin)(theta) (k = 1..n,
 // accumulated) and -- when the last one lies within `res` of t -- t itself (rrt_04:1099-1113).  n = floor(d / res)
-// is computed exactly as steer does; the first and last points are f and t exactly; the intermediate points are
-// reproduced to within eps_pos with the direction (t - f) / d, so a point-circle test whose margin exceeds the
-// error band has the reference's verdict.  Returns 1 = free and snapped (end point == t), 0 = blocked,
-// -1 = too close to call (a test inside the band, or the snap decision within 1e-9 of its threshold): the caller
-// runs the exact steer + edge_free_lane.  `extend` = steer's extend_length (inf for choose_parent / rewire,
-// expand_dis for the first edge); obstacles j0, j0 + jstep, ... are tested (lanes can split them).
-static __device__ __noinline__ int edge_verdict_fast(double fx, double fy, double tx, double ty, double d, double extend,
-                                              double res, const ObsList &L, int j0, int jstep) {
-    if (!(d > 0.0)) return -1;
-    const double q = floor((extend > d ? d : extend) / res);   // steer's n_expand (rrt_04:1096-1099)
-    if (!(q < 1.0e6)) return -1;
+// as steer computes it; the first and last points are f and t exactly; the intermediate points are reproduced to
+// within eps_pos with the direction (t - f) / d, so a point-circle test whose margin exceeds the error band has the
+// reference's verdict.  v: 1 = free and snapped (end point == t), 0 = blocked, -1 = too close to call (a test inside
+// the band, or the snap decision within 1e-9 of its threshold): the caller runs the exact steer + edge_free_lane.
+//   d        hypot(t - f): the correctly rounded value (d_exact) or any value within a few ulp of it (the decisions
+//            below keep a 1e-9 margin; near a multiple of the resolution only the exact value can decide)
+//   q_ext    floor(extend / res) for steer's extend_length (huge for inf), used when d >= extend (the first edge)
+//   inv_res  1 / res: n = floor(d * inv_res) wherever d / res is not within 1e-9 of an integer -- one division
+//            (1 / d) per edge instead of four
+//   j0, jstep  circles j0, j0 + jstep, ... are tested (lanes can split them)
+//   only     bit b set = test circle j0 + b * jstep (b < 64; circles beyond 64 are always tested)
+// near: the circles (same bit numbering) that are NOT farther than their radius plus the band from the segment f-t.
+// Every path point of the edge t -> f lies on the same segment, so the reverse edge (rewire, rrt_04:1340-1373) needs
+// only those: `only = near` of a FREE forward edge, and nothing at all when it is empty.  ~0 = unknown (blocked or
+// undecided before every circle was seen, or more than 64 circles).
+// steer's snap onto its target is certain for an edge of length d (the head of edge_verdict_fast, for callers that
+// want to know before they gather the circles)
+static __device__ __forceinline__ bool snap_certain(double d, bool d_exact, double extend, double q_ext, double res,
+                                                    double inv_res) {
+    if (!(d > 0.0)) return false;
+    double q = q_ext;
+    if (extend > d) {
+        q = floor(d * inv_res);
+        const double rem0 = d - q * res;
+        if (!(rem0 >= res * 1e-9 && rem0 <= res * (1.0 - 1e-9))) {
+            if (!d_exact) return false;
+            q = floor(d / res);
+        }
+    }
+    return q < 1.0e6 && d - q * res <= res * (1.0 - 1e-9);
+}
+
+struct EdgeVerdict {
+    int v;
+    unsigned long long near;
+};
+static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double fy, double tx, double ty, double d, bool d_exact,
+                                                             double extend, double q_ext, double res, double inv_res,
+                                                             const ObsList &L, int j0, int jstep, unsigned long long only) {
+    EdgeVerdict r;
+    r.v = -1; r.near = ~0ull;
+    if (!(d > 0.0)) return r;
+    double q = q_ext;                                  // steer's n_expand (rrt_04:1096-1099)
+    if (extend > d) {
+        q = floor(d * inv_res);
+        const double rem0 = d - q * res;
+        if (!(rem0 >= res * 1e-9 && rem0 <= res * (1.0 - 1e-9))) {
+            if (!d_exact) return r;
+            q = floor(d / res);                        // the reference's own quotient decides next to a multiple of res
+        }
+    }
+    if (!(q < 1.0e6)) return r;
     const int n = (int)q;
     const double rem = d - q * res;                    // distance left after n steps
-    if (!(rem <= res * (1.0 - 1e-9))) return -1;       // snap (d2 <= res, rrt_04:1107) must be certain
-    const double inv = res / d;
+    if (!(rem <= res * (1.0 - 1e-9))) return r;        // snap (d2 <= res, rrt_04:1107) must be certain
+    const double inv_d = 1.0 / d;
+    const double inv = res * inv_d;
     const double ux = (tx - fx) * inv, uy = (ty - fy) * inv;
-    const double e4 = 4.0 * ((double)(n + 8) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
+    // position error of the reproduced points: n accumulated roundings + the direction's (res / d as two rounded
+    // operations on a d that may be a few ulp off: 4 of the 12 units)
+    const double e4 = 4.0 * ((double)(n + 12) * 2.3e-16 * (fabs(fx) + fabs(fy) + fabs(tx) + fabs(ty) + 1.0)) + 4e-15;
     bool unsure = false;
-    const double wx = tx - fx, wy = ty - fy, invl2 = 1.0 / (d * d);
-    for (int j = j0; j < L.m; j += jstep) {
+    unsigned long long near = 0ull;
+    const double wx = tx - fx, wy = ty - fy, invl2 = inv_d * inv_d;
+    int b = 0;
+    for (int j = j0; j < L.m; j += jstep, b++) {
+        if (b < 64 && !((only >> b) & 1ull)) continue;
         const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
         double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
-        if (dx * dx + dy * dy <= r2) return 0;
+        if (dx * dx + dy * dy <= r2) { r.v = 0; return r; }
         const double bj = (2.02 + 2.02 * r2) * e4;     // >= (2 + dd + r2) * e4 wherever |dd - r2| is that small
         // every path point lies on the segment f-t (to within eps_pos): a circle farther than its radius (plus
         // the band) from the segment cannot contain one
@@ -106,20 +153,23 @@ static __device__ __noinline__ int edge_verdict_fast(double fx, double fy, doubl
         sp = sp < 0.0 ? 0.0 : (sp > 1.0 ? 1.0 : sp);
         const double px = dx - sp * wx, py = dy - sp * wy;
         if (px * px + py * py - r2 > bj + 1e-9 * (1.0 + r2)) continue;
+        near |= b < 64 ? (1ull << b) : 0ull;
         dx = ox - tx; dy = oy - ty;                    // last point: t itself (snapped), exact test
-        if (dx * dx + dy * dy <= r2) return 0;
+        if (dx * dx + dy * dy <= r2) { r.v = 0; return r; }
         double x = fx, y = fy;
         for (int k = 1; k <= n; k++) {
             x += ux; y += uy;
             dx = ox - x; dy = oy - y;
             const double t = dx * dx + dy * dy - r2;
             if (t <= bj) {
-                if (t <= -bj) return 0;                // certainly inside: blocked whatever the others say
+                if (t <= -bj) { r.v = 0; return r; }   // certainly inside: blocked whatever the others say
                 unsure = true;
             }
         }
     }
-    return unsure ? -1 : 1;
+    r.v = unsure ? -1 : 1;
+    r.near = b > 64 ? ~0ull : near;
+    return r;
 }
 
 // the same verdict computed by the whole warp (lanes split the obstacles); uniform result
@@ -167,7 +217,7 @@ static __device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &
         s.x = v.x; s.y = v.y;
         return s;
     }
-    uint64_t k0 = rng_key(p.seed, (uint64_t)q, (uint64_t)it_key);   // it_key = iteration counter of the whole run
+    uint64_t k0 = rng_key(p.seed, (uint64_t)(q + p.query_base), (uint64_t)it_key);   // it_key = iteration counter of the whole run
     int coin = (int)(splitmix64(k0) % 101ull);  // random.randint(0, 100)
     if (coin > p.goal_sample_rate) {
         double w = p.max_rand - p.min_rand;

@@ -41,6 +41,14 @@ constexpr int CTA_FQ = 128;           // shared-memory slots of propagate's fron
 constexpr unsigned short NONE16 = 0xffffu;
 constexpr int BIG = 0x7fffffff;
 
+// -DRRTK_CTA_PROFILE (tools/probe_cta_phases.py, `make profile`): the TRACE instantiation records thread 0's SM clock per
+// phase of every iteration instead of the decision trace
+#ifdef RRTK_CTA_PROFILE
+#define CTA_CLK(k) do { if (TRACE && tid == 0) clk[k] = clock64(); } while (0)
+#else
+#define CTA_CLK(k) do { } while (0)
+#endif
+
 // fixed part of the CTA's shared memory (every address an immediate); the tree arrays follow it
 template <int NC>
 struct CtaSmemT {
@@ -88,9 +96,12 @@ static __device__ __forceinline__ void cta_unlink(ushort2 *s_link, int p, int c)
 
 // propagate_cost_to_leaves (rrt_04:1379-1384) by one warp over the shared-memory children lists; the frontier carries each
 // node's new cost, so no cost is read back from global memory.  Slots >= CTA_FQ spill to the query's workspace.
+// elen[c] = hypot(c - parent(c)) is cached from the moment the edge was made (see propagate_lists_elen, rrtk_planner.cuh):
+// a level of the walk is a child-list hop, one load and one add.
 template <class SM>
-static __device__ __noinline__ void cta_propagate(int root, double root_cost, const double2 *s_xy, const ushort2 *s_link,
-                                                  double *cost, SM &S, int *g_idx, double *g_cost, int lane) {
+static __device__ __noinline__ void cta_propagate(int root, double root_cost, bool root_moved, const double2 *s_xy,
+                                                  const ushort2 *s_link, double *cost, double *elen, SM &S, int *g_idx,
+                                                  double *g_cost, int lane) {
     if (s_link[root].x == NONE16) return;
     volatile int *tail = &S.tail;
     if (lane == 0) { S.fq_idx[0] = (unsigned short)root; S.fq_cost[0] = root_cost; *tail = 1; }
@@ -103,11 +114,16 @@ static __device__ __noinline__ void cta_propagate(int root, double root_cost, co
         if (k < end) {
             const int pn = k < CTA_FQ ? (int)S.fq_idx[k] : g_idx[k];
             const double cp = k < CTA_FQ ? S.fq_cost[k] : g_cost[k];
-            const double2 a = s_xy[pn];
+            const bool stale = root_moved && pn == root;
             for (unsigned short c = s_link[pn].x; c != NONE16;) {
                 const ushort2 lc = s_link[c];
-                const double2 b = s_xy[c];
-                const double cc = cp + crm_hypot(b.x - a.x, b.y - a.y);
+                double e = elen[c];
+                if (stale || e != e) {
+                    const double2 a = s_xy[pn], b = s_xy[c];
+                    e = crm_hypot(b.x - a.x, b.y - a.y);
+                    elen[c] = e;
+                }
+                const double cc = cp + e;
                 cost[c] = cc;
                 if (lc.x != NONE16) {
                     const int slot = atomicAdd(&S.tail, 1);
@@ -136,7 +152,7 @@ static __device__ __forceinline__ ObsList sub_list(const ObsList &L, int sub) {
 template <class SM>
 static __device__ __noinline__ void cta_rewire_serial(const rrtk_rrtstar_params &p, int from, int count, SM &S, double2 *s_xy,
                                                       ushort2 *s_link, unsigned short *s_par, double2 *xy, double *cost,
-                                                      int32_t *parent, int n, double cx, double cy, double ccost,
+                                                      int32_t *parent, double *elen, int n, double cx, double cy, double ccost,
                                                       const ObsList &L, int *g_idx, double *g_cost, int lane, int &t_rwok,
                                                       int &t_rwap) {
     const double res = p.path_resolution;
@@ -157,10 +173,11 @@ static __device__ __noinline__ void cta_rewire_serial(const rrtk_rrtstar_params 
                 cost[i] = ec;
                 parent[i] = n;
                 s_par[i] = (unsigned short)n;
+                elen[i] = __longlong_as_double(0x7ff8000000000000ll);   // (the node may have moved: recomputed on demand)
             }
             __syncwarp();
             t_rwap++;
-            cta_propagate(i, ec, s_xy, s_link, cost, S, g_idx, g_cost, lane);
+            cta_propagate(i, ec, true, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
             __syncwarp();
         }
     }
@@ -224,7 +241,8 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         int32_t *trace = TRACE ? trace_all + (size_t)q * p.max_iter * 8 : nullptr;
         const int64_t sobol_base = sobol_offset ? sobol_offset[q] : 0;
 
-        // workspace of the query: [4 * node_cap ints: spill of the propagate frontier (idx, then cost)] [obstacle cells]
+        // workspace of the query: [4 * node_cap ints: spill of the propagate frontier (idx, then cost)] [cached edge lengths
+        // elen[i] = hypot(node i - its parent), NaN = not known] [obstacle cells]
         const int grid_cells = p.grid_nx * p.grid_ny;
         int32_t *wsq = workspace + (size_t)q * RRTK_RRTSTAR_WS_INTS(p.node_cap, p.grid_nx, p.grid_ny);
         int *g_idx = wsq;
@@ -232,7 +250,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         ObsGrid grid;
         grid.nx = p.grid_nx; grid.ny = p.grid_ny; grid.x0 = p.grid_x0; grid.y0 = p.grid_y0;
         grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
-        grid.cnt = wsq + 4 * (size_t)p.node_cap;
+        double *elen = reinterpret_cast<double *>(wsq + 4 * (size_t)p.node_cap);
+        const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+        grid.cnt = wsq + 4 * (size_t)p.node_cap + 4 * (size_t)((p.node_cap + 1) / 2);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
 
         int n = 1, status = RRTK_Q_OK, gi = -1, it = 0, it_prev = 0;
@@ -247,6 +267,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 xy[0] = make_double2(sg.x, sg.y);
                 cost[0] = 0.0;
                 parent[0] = -1;
+                elen[0] = 0.0;
             }
         } else {
             // continue the tree a previous call left in xy / cost / parent: reload it, rebuild the children lists (their
@@ -264,6 +285,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 s_link[i] = make_ushort2(NONE16, NONE16);
                 const int pp = parent[i];
                 s_par[i] = pp < 0 ? NONE16 : (unsigned short)pp;
+                elen[i] = NaN;
             }
             __syncthreads();
             if (tid == 0)
@@ -271,7 +293,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             if (p.sampler == RRTK_SAMPLER_SOBOL) {
                 int used = 0;
                 for (int k = lane; k < p.iter_offset; k += 32)
-                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)q, (uint64_t)k)) % 101ull) > p.goal_sample_rate;
+                    used += (int)(splitmix64(rng_key(p.seed, (uint64_t)(q + p.query_base), (uint64_t)k)) % 101ull) > p.goal_sample_rate;
                 sob.n += (int64_t)__reduce_add_sync(FULL, (unsigned)used);
             }
         }
@@ -280,6 +302,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         if (tid == 0) { S.count = 0; S.cpok = 0; S.done = 0; S.gi = -1; S.status_or = 0; }
         sobol2(sob.n, sob.q0, sob.q1);
         bool done = false;
+        const double inv_res = 1.0 / res, q_expand = floor(p.expand_dis / res);   // steer's n_expand at full extension
         // near radius of the current tree size, and (loaded one iteration ahead) of the size after an append
         double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];
         // the sample of iteration 0, and the circles around it
@@ -296,6 +319,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
 
         for (it = 0; it < p.max_iter; it++) {
             const int cb = it & 1;
+#ifdef RRTK_CTA_PROFILE
+            long long clk[10];
+#endif
+            CTA_CLK(0);
             const double rx = smp_next.x, ry = smp_next.y;
             if (it + 1 < p.max_iter)
                 smp_next = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
@@ -319,6 +346,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             }
             warp_argmin(bd, bi);
             if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; }
+            CTA_CLK(1);
             __syncthreads();   // ---- B1
             bd = S.red_d[0]; bi = S.red_i[0];
 #pragma unroll
@@ -331,6 +359,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             int count = S.count;
             int t_near = 0, t_par = -1, t_rwok = 0, t_rwap = 0;
             double2 from = make_double2(0.0, 0.0);
+            CTA_CLK(2);
             if (warp == 0) {
                 // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the sample the
                 // new node IS the sample and only the collision verdict is needed; otherwise the exact steer runs ----
@@ -338,14 +367,15 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 int t_status = 0;
                 bool accept = false, near_valid = false;
                 double nx = rx, ny = ry;
-                const double d0 = crm_hypot(rx - from.x, ry - from.y);
+                // (the verdict keeps a 1e-9 margin on every use of the edge length: a plain sqrt is as good as the correctly
+                // rounded hypot here; the exact steer computes its own)
+                const double ddx0 = rx - from.x, ddy0 = ry - from.y;
+                const double d0 = sqrt(ddx0 * ddx0 + ddy0 * ddy0);
                 int v = -1;
                 ObsList L;
                 L.ox = S.cull[cb][0]; L.oy = S.cull[cb][1]; L.r2 = S.cull[cb][2]; L.stride = 1; L.m = 0;
                 {
-                    const double ext = p.expand_dis > d0 ? d0 : p.expand_dis;
-                    const double q0 = floor(ext / res);
-                    if (d0 > 0.0 && d0 - q0 * res <= res * (1.0 - 1e-9)) {   // same snap test as edge_verdict_fast
+                    if (snap_certain(d0, false, p.expand_dis, q_expand, res, inv_res)) {
                         if (inside_play(p, nx, ny)) {
                             if (S.cull_glob[cb]) {
                                 const double *g = reinterpret_cast<const double *>(obs);
@@ -353,7 +383,8 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             } else {
                                 L.m = S.cull_m[cb];
                             }
-                            const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, p.expand_dis, res, L, lane, 32);
+                            const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
+                                                             lane, 32, ~0ull).v;
                             const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                             v = blocked ? 0 : (unsure ? -1 : 1);
                             if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
@@ -387,7 +418,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             } else if (!RRT_ONLY) {
                 if (count <= near_cap) cta_rank_near(S, count, tid - 64, CTA_T - 64);
             }
+            CTA_CLK(3);
             __syncthreads();   // ---- B2
+            CTA_CLK(4); CTA_CLK(5); CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
             bool accept = S.accept != 0;
             const double nx = S.nx, ny = S.ny;
             int t_status = S.t_status;
@@ -434,6 +467,8 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     // ---- choose_parent (rrt_04:1242-1282): CTA_G lanes per candidate, each tests its share of the circles ----
                     double bc = INF, bex = 0.0, bey = 0.0;
                     int bk = BIG;
+                    // this lane's circles near the segment (its first-round candidate) - (new node), for the reverse edge
+                    unsigned long long seg_near = ~0ull;
                     for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
                         const int k = k0 + tid / CTA_G;
                         const bool valid = k < count;
@@ -444,7 +479,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             const double2 a = s_xy[i];
                             ci = cost[i];
                             dk = crm_hypot(nx - a.x, ny - a.y);   // what steer's calc_distance_and_angle returns
-                            const int vv = edge_verdict_fast(a.x, a.y, nx, ny, dk, INF, res, L, sub, CTA_G);
+                            const EdgeVerdict ev = edge_verdict_fast(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, ~0ull);
+                            const int vv = ev.v;
+                            if (k0 == 0) seg_near = vv == 1 ? ev.near : ~0ull;
                             blocked = vv == 0;                    // (the new node is inside the play area)
                             if (vv < 0) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
@@ -480,7 +517,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         }
                         if (lane == 0) { S.red_d[warp] = bc; S.red_i[warp] = bk; S.red_ex[warp] = bex; S.red_ey[warp] = bey; }
                     }
+                    CTA_CLK(5);
                     __syncthreads();   // ---- B3
+                    CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
                     bc = S.red_d[0]; bk = S.red_i[0]; bex = S.red_ex[0]; bey = S.red_ey[0];
 #pragma unroll
                     for (int w = 1; w < CTA_W; w++) {
@@ -509,8 +548,13 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                 // hypot(node - c) == the forward edge's d when c is the sample point itself
                                 dk = c_is_new ? S.nd[k] : crm_hypot(a.x - cx, a.y - cy);
                                 want = TRACE || (S.s_nc[k] > ccost + dk);
-                                if (want) {
-                                    const int vv = edge_verdict_fast(cx, cy, a.x, a.y, dk, INF, res, L, sub, CTA_G);
+                                // the reverse edge runs along the segment choose_parent tested (when the new node is the sample):
+                                // only the circles found near it then can matter, usually none
+                                const unsigned long long only = (c_is_new && k0 == 0) ? seg_near : ~0ull;
+                                if (want && only == 0ull) {
+                                    blocked = !inside_play(p, a.x, a.y);
+                                } else if (want) {
+                                    const int vv = edge_verdict_fast(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, only).v;
                                     if (vv < 0) {
                                         Steer st = steer(cx, cy, a.x, a.y, INF, res);
                                         blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
@@ -527,7 +571,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                 S.near_ok[k] = (want && !bm) ? (mm ? 2 : 1) : 0;
                             }
                         }
+                        CTA_CLK(7);
                         __syncthreads();   // ---- B4
+                        CTA_CLK(8);
                         if (warp == 0) {
                             // ---- rewire, ordered apply (rrt_04:1361-1371) + propagate_cost_to_leaves ----
                             bool dirty = false;      // a propagate ran: node costs must be re-read
@@ -569,10 +615,11 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                             cost[ii] = ec;
                                             parent[ii] = n;
                                             s_par[ii] = (unsigned short)n;
+                                            elen[ii] = moved ? NaN : S.nd[b0 + b];   // hypot(node - new node), what propagate would compute
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        cta_propagate(ii, ec, s_xy, s_link, cost, S, g_idx, g_cost, lane);
+                                        cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
                                         __syncwarp();
                                         dirty = true;
                                         if (moved) {
@@ -587,11 +634,12 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                 }
                             }
                             if (fallback_from >= 0)
-                                cta_rewire_serial(p, fallback_from, count, S, s_xy, s_link, s_par, xy, cost, parent, n, cx, cy, ccost, L,
+                                cta_rewire_serial(p, fallback_from, count, S, s_xy, s_link, s_par, xy, cost, parent, elen, n, cx, cy, ccost, L,
                                                   g_idx, g_cost, lane, t_rwok, t_rwap);
                             if (lane == 0) {
                                 s_xy[n] = make_double2(cx, cy); s_par[n] = (unsigned short)best;
                                 xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best;
+                                elen[n] = c_is_new ? S.nd[bk] : NaN;   // hypot(new node - parent) as long as the node sits on the sample
                                 cta_link(s_link, best, n);
                             }
                         }
@@ -599,9 +647,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     } else {
                         if (tid == 0) {
                             const double2 f0 = s_xy[ni];
-                            const double ncost = cost[ni] + crm_hypot(nx - f0.x, ny - f0.y);
+                            const double nlen = crm_hypot(nx - f0.x, ny - f0.y);
+                            const double ncost = cost[ni] + nlen;
                             s_xy[n] = make_double2(nx, ny); s_par[n] = (unsigned short)ni;
-                            xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni;
+                            xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; elen[n] = nlen;
                             cta_link(s_link, ni, n);
                         }
                         t_status = 2; t_par = ni;
@@ -609,11 +658,21 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     n++;
                 }
             }
+            CTA_CLK(9);
+#ifdef RRTK_CTA_PROFILE
+            if (TRACE && tid == 0) {   // scan | B1 | first edge | B2 | choose_parent | B3 | rewire edges | B4 ; apply + append in [7]
+                int32_t *tr = trace + (size_t)it * 8;
+                tr[0] = (int)(clk[1] - clk[0]); tr[1] = (int)(clk[2] - clk[1]); tr[2] = (int)(clk[3] - clk[2]);
+                tr[3] = (int)(clk[4] - clk[3]); tr[4] = (int)(clk[5] - clk[4]); tr[5] = (int)(clk[6] - clk[5]);
+                tr[6] = (int)(clk[8] - clk[6]); tr[7] = (int)(clk[9] - clk[8]);
+            }
+#else
             if (TRACE && tid == 0) {
                 int32_t *tr = trace + (size_t)it * 8;
                 tr[0] = ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = S.cpok;
                 tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
             }
+#endif
             // ---- goal tests, by warp 0 (it wrote the last node itself) ----
             if (warp == 0 && !done) {
                 __syncwarp();

@@ -29,7 +29,7 @@ class RRTStarParams(C.Structure):
                 ("max_rand", C.c_double), ("play_area", C.c_double * 4), ("seed", C.c_uint64),
                 ("grid_nx", C.c_int32), ("grid_ny", C.c_int32), ("grid_x0", C.c_double),
                 ("grid_y0", C.c_double), ("grid_cell", C.c_double), ("resume", C.c_int32), ("iter_offset", C.c_int32),
-                ("near_r_max", C.c_double), ("exec_mode", C.c_int32), ("pad_", C.c_int32)]
+                ("near_r_max", C.c_double), ("exec_mode", C.c_int32), ("query_base", C.c_int32)]
 
 
 class InformedParams(C.Structure):

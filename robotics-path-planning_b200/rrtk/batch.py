@@ -14,15 +14,17 @@ class RRTStarBatch:
     obstacle_lists     length-Q sequence of [(x, y, size), ...]  (or a prepared [Q, O, 4] array of
                        x, y, size + rr, (size + rr) ** 2 rows together with `n_obs`)
     sampler            "sobol" | "uniform": in-kernel generator (goal coin from a counter-based RNG
-                       keyed by (seed, query, iteration); Sobol index offset `q * max_iter`)
+                       keyed by (seed, query_base + query, iteration); Sobol index offset `(query_base + q) * max_iter`)
                        or an explicit `sample_stream` [Q, max_iter, 2].
+    query_base         global index of query 0 when this batch is a shard of a larger one: the shard then
+                       plans exactly what the unsharded batch plans for the same queries.
     """
 
     def __init__(self, starts, goals, obstacle_lists, rand_area, expand_dis=3.0,
                  path_resolution=0.5, goal_sample_rate=5, max_iter=500, play_area=None,
                  robot_radius=0.0, sampler="sobol", connect_circle_dist=50.0,
                  search_until_max_iter=True, seed=0, near_cap=256, n_obs=None,
-                 sample_stream=None, sobol_offset=None, device=None):
+                 sample_stream=None, sobol_offset=None, device=None, query_base=0, exec_mode=None):
         torch = _lib.require_cuda()
         self.device = torch.device("cuda" if device is None else device)
         starts = np.asarray(starts, dtype=np.float64).reshape(-1, 2)
@@ -40,7 +42,7 @@ class RRTStarBatch:
         self.params = engine.make_params(q, self.max_iter, self.node_cap, rows.shape[1], expand_dis,
                                          path_resolution, play_area, search_until_max_iter,
                                          self.sampler, goal_sample_rate, rand_area[0], rand_area[1],
-                                         seed, near_cap)
+                                         seed, near_cap, exec_mode=exec_mode, query_base=query_base)
         # obstacle cell grid: box of everything a node can be (samples, starts, goals)
         pts = [starts, goals]
         if sample_stream is not None:
@@ -58,7 +60,7 @@ class RRTStarBatch:
         self.near_r2 = torch.from_numpy(
             engine.near_r2_table(self.node_cap, connect_circle_dist, expand_dis)).to(self.device)
         if sobol_offset is None:
-            sobol_offset = np.arange(q, dtype=np.int64) * self.max_iter
+            sobol_offset = (np.arange(q, dtype=np.int64) + int(query_base)) * self.max_iter
         self.sobol_offset = torch.from_numpy(np.asarray(sobol_offset, dtype=np.int64)).to(self.device)
         self.sample_stream = None
         if sample_stream is not None:

@@ -89,7 +89,7 @@ class BatchResult:
 def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_resolution,
                 play_area=None, search_until_max_iter=True, sampler=_lib.SAMPLER_STREAM,
                 goal_sample_rate=5, min_rand=0.0, max_rand=0.0, seed=0, near_cap=256,
-                rrt_only=False, near_r_max=0.0, exec_mode=None) -> _lib.RRTStarParams:
+                rrt_only=False, near_r_max=0.0, exec_mode=None, query_base=0) -> _lib.RRTStarParams:
     p = _lib.RRTStarParams()
     p.n_queries, p.max_iter, p.node_cap = int(n_queries), int(max_iter), int(node_cap)
     p.obs_stride, p.near_cap = int(obs_stride), int(near_cap)
@@ -105,6 +105,7 @@ def make_params(n_queries, max_iter, node_cap, obs_stride, expand_dis, path_reso
     p.seed = int(seed) & ((1 << 64) - 1)
     p.near_r_max = float(near_r_max)          # 0 = the table is clipped to expand_dis (rrt_04:1333-1335)
     p.exec_mode = default_exec_mode() if exec_mode is None else int(exec_mode)
+    p.query_base = int(query_base)            # global index of query 0 (shards of one batch share the sampler streams)
     return p
 
 
@@ -138,7 +139,7 @@ def set_obstacle_grid(p: _lib.RRTStarParams, xmin, xmax, ymin, ymax) -> None:
 
 def workspace_ints(p: _lib.RRTStarParams) -> int:
     """RRTK_RRTSTAR_WS_INTS (include/rrtk.h)."""
-    return 4 * p.node_cap + 4 * ((17 * p.grid_nx * p.grid_ny + 3) // 4)
+    return 4 * p.node_cap + 4 * ((p.node_cap + 1) // 2) + 4 * ((17 * p.grid_nx * p.grid_ny + 3) // 4)
 
 
 def run_dev(p: _lib.RRTStarParams, start_goal, obstacles, n_obs, near_r2, sample_stream=None,

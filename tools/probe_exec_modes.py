@@ -16,7 +16,7 @@ for Q in sizes:
     rows = W.c2_rows(list(range(Q)), n_obs)
     starts = np.tile(np.array(cfg["start"]), (Q, 1)); goals = np.tile(np.array(cfg["goal"]), (Q, 1))
     sig = {}
-    for mode in ("warp", "cta"):
+    for mode in os.environ.get("RRTK_PROBE_MODES", "warp,cta").split(","):
         os.environ["RRTK_EXEC"] = mode
         b = rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],
                               cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol", cfg["connect_circle_dist"],
@@ -32,5 +32,7 @@ for Q in sizes:
         print(f"Q={Q:5d} {mode:4s} ms min/med/max = {ms[0]:.2f} / {ms[len(ms)//2]:.2f} / {ms[-1]:.2f}   "
               f"{Q * iters / ms[len(ms)//2] / 1e3:.1f} M it/s   mean nodes {sig[mode][0].mean():.0f}", flush=True)
         del b, r
+    if len(sig) < 2:
+        continue
     same = all(np.array_equal(x, y) for x, y in zip(sig["warp"][:3], sig["cta"][:3])) and sig["warp"][3] == sig["cta"][3]
     print(f"Q={Q:5d} identical results: {same}", flush=True)
