@@ -50,6 +50,8 @@ extern "C" {
 #define RRTK_Q_NODE_OVERFLOW 2 /* tree reached node_cap */
 #define RRTK_Q_PATH_OVERFLOW 4 /* best path longer than path_cap (length is still reported) */
 #define RRTK_Q_DIV_ZERO 8      /* path smoothing: the reference would raise ZeroDivisionError at this iteration */
+#define RRTK_Q_NONE_STEER 16   /* RRT-Dubins with a play area: steer returned None and the reference evaluates `node.x` of it
+                                  (AttributeError, rrt_03:1626); the query stopped at that iteration */
 
 /* sampler kinds (get_random_node / get_random_node_sobol, rrt_04:1132-1153) */
 #define RRTK_SAMPLER_STREAM 0  /* read (x, y) per iteration from `sample_stream` */
@@ -371,6 +373,21 @@ RRTK_API int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const doub
                                          int32_t *parent, double *edge_from, double *edge_to, int32_t *n_nodes,
                                          int32_t *iters_done, int32_t *goal_index, int32_t *status,
                                          int32_t *workspace, void *stream);
+
+/* Batched RRT-Dubins -- `planning()` of rrt_03:1402-1456 for Q independent queries: plain RRT whose steer is the whole Dubins
+ * course from the nearest node (xy metric, :1612-1618) to the sample (:1458-1479).  The new node is kept iff its end pose is
+ * inside the play area (check_if_outside_play_area :1621-1631) and no course point is inside a circle (check_collision
+ * :1634-1648); its cost is the parent's plus `sum([abs(c) for c in course_lengths])` (:1470 -- CPython >= 3.12 evaluates that
+ * sum with Neumaier's compensated addition, restated here).  No near / choose_parent / rewire.  search_best_goal_node
+ * (:1491-1512) as for RRT*-Dubins; with search_until_max_iter = 0 it runs after every iteration whose steer returned a node.
+ * p->near_cap is ignored.  play_area: 4 doubles xmin, xmax, ymin, ymax on the device (one box for the launch) or NULL;
+ * with a play area a steer that returns None sets RRTK_Q_NONE_STEER (the reference raises AttributeError there).
+ * Other arguments as for rrtk_rrtstar_dubins_run_dev; workspace [RRTK_WS_TAIL_INTS] int32 (the work-queue counter). */
+RRTK_API int rrtk_rrt_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
+                                     const int32_t *n_obs, const double *play_area, const double *stream3, double *xy,
+                                     double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
+                                     int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
+                                     int32_t *workspace, void *stream);
 
 /* Batched RRT*-Reeds-Shepp -- `planning()` of rrt_06:1530-1570 for Q independent queries: the same loop as RRT*-Dubins
  * with reeds_shepp_path_planning as steer (:1584-1604; p->step_size is its step_size, 0.2 by default in the reference),

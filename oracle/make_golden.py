@@ -249,6 +249,60 @@ def run_rrt05(name, params, seed, search_until_max_iter=True):
           f"{wall:.2f} s ({n / wall:.1f} it/s)")
 
 
+def run_rrt03(name, params, seed, search_until_max_iter=True, own_sampler=False):
+    """Drive rrt_03's RRT.planning (plain RRT + Dubins steering).  own_sampler: the reference samples by itself
+    (sobol_sampler per params, `random.seed(seed)`) and the nodes it draws are recorded; otherwise an (x, y, yaw) stream is
+    injected through get_random_node.  (rrt_03 builds _PATH_TYPE_MAP before the functions it names: see ref_loader.)"""
+    import math
+    ns = ref_loader.load("rrt_03")
+    ref_loader.reset_sobol(ns)
+    R = ns["RRT"]
+    n = params["max_iter"]
+    rrt = R(**params)
+    drawn = []
+    if own_sampler:
+        random.seed(seed)
+        orig = rrt.get_random_node_sobol if params.get("sobol_sampler") else rrt.get_random_node
+
+        def logged():
+            nd = orig()
+            drawn.append([float(nd.x), float(nd.y), float(nd.yaw)])
+            return nd
+        rrt.get_random_node_sobol = logged
+        rrt.get_random_node = logged
+    else:
+        rng = np.random.default_rng(seed)
+        lo, hi = params["rand_area"]
+        stream = np.column_stack([rng.uniform(lo, hi, (n, 2)), rng.uniform(-math.pi, math.pi, n)])
+        coin = rng.integers(0, 101, n) <= params["goal_sample_rate"]
+        stream[coin] = params["goal"]
+        it = iter(stream)
+
+        def pop():
+            v = [float(t) for t in next(it)]
+            drawn.append(v)
+            return rrt.Node(*v)
+        rrt.get_random_node = pop
+        rrt.get_random_node_sobol = pop
+    sys.setrecursionlimit(100000)          # steer deep-copies the whole ancestor chain (rrt_03:1465)
+    t0 = time.perf_counter()
+    with ref_loader.quiet():
+        path = rrt.planning(animation=False, search_until_max_iter=search_until_max_iter)
+    wall = time.perf_counter() - t0
+    x, y, c, par = tree_arrays(rrt.node_list)
+    yaw = np.array([float(nd.yaw) for nd in rrt.node_list])
+    stream = np.array(drawn, dtype=np.float64).reshape(-1, 3)
+    meta = dict(params)
+    meta.update(kind="rrt_03", seed=seed, reference_wall_s=wall, search_until_max_iter=search_until_max_iter,
+                own_sampler=own_sampler, sobol_inter_=int(rrt.sobol_inter_), iters=int(stream.shape[0]),
+                goal_yaw_th=float(params.get("goal_yaw_th", np.deg2rad(1.0))))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), stream=stream,
+                        x=x, y=y, yaw=yaw, cost=c, parent=par,
+                        path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 2)))
+    print(f"{name}: {len(x)} nodes, {stream.shape[0]} iterations, path {0 if path is None else len(path)} points, "
+          f"{wall:.2f} s")
+
+
 def run_rrt06(name, params, seed, search_until_max_iter=True):
     """Drive rrt_06's RRT.planning (RRT*-Reeds-Shepp) with an injected (x, y, yaw) sample stream."""
     ns = ref_loader.load("rrt_06")
@@ -333,6 +387,12 @@ C5D = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 10.0, 0.0],
            obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)],
            rand_area=[-2, 15], expand_dis=3.0, goal_sample_rate=10, max_iter=500, robot_radius=0.0,
            connect_circle_dist=50.0, curvature=1.0, goal_xy_th=0.5)          # rrt_05:1804-1859
+
+
+C3D = dict(start=[0.0, 0.0, 0.0], goal=[10.0, 10.0, 0.0],
+           obstacle_list=[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)],
+           rand_area=[-2, 15], goal_sample_rate=10, max_iter=200, robot_radius=0.6, sobol_sampler=True,
+           curvature=1.0, goal_xy_th=0.5)                                     # rrt_03:1664-1716
 
 
 C7 = dict(start=[0.0, 0.0], goal=[6.0, 10.0],
@@ -549,6 +609,18 @@ CASES = {
         obstacle_list=[(5, 5, 1), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]), 3),
     "rrt05_early_exit_600": lambda: run_rrt05("rrt05_early_exit_600", dict(
         C5D, max_iter=600, goal_yaw_th=float(np.deg2rad(30.0)), goal_xy_th=1.5), 4, False),
+    # rrt_03 (plain RRT + Dubins): the script's own scene with its own 3-D Sobol sampler, then injected streams
+    "rrt03_builtin_sobol_200": lambda: run_rrt03("rrt03_builtin_sobol_200", C3D, 0, True, own_sampler=True),
+    "rrt03_sobol_early_600": lambda: run_rrt03("rrt03_sobol_early_600", dict(
+        C3D, max_iter=600, goal_yaw_th=float(np.deg2rad(6.0)), goal_xy_th=0.9, goal_sample_rate=2), 5, False, own_sampler=True),
+    "rrt03_uniform_own_400": lambda: run_rrt03("rrt03_uniform_own_400", dict(C3D, max_iter=400, sobol_sampler=False), 7, True,
+                                               own_sampler=True),
+    "rrt03_stream_800": lambda: run_rrt03("rrt03_stream_800", dict(
+        C3D, max_iter=800, robot_radius=0.2, curvature=1.5, goal_yaw_th=float(np.deg2rad(20.0)), goal_xy_th=1.0,
+        obstacle_list=[(5, 5, 1), (9, 6, 1), (7, 5, 1), (1, 5, 1), (3, 6, 1), (7, 9, 1)]), 11),
+    "rrt03_play_area_500": lambda: run_rrt03("rrt03_play_area_500", dict(
+        C3D, max_iter=500, play_area=[-1.0, 12.0, -1.0, 13.0], goal_sample_rate=-1), 12),   # (no goal samples: a second one
+    # from a node already ON the goal pose makes steer return None, which rrt_03 turns into an AttributeError at :1626)
     "dubins_pairs_150": lambda: run_dubins("dubins_pairs_150", 150, 21),
     "rrt07_builtin_200": lambda: run_rrt07("rrt07_builtin_200", C7, 1),
     "rrt07_builtin_1000": lambda: run_rrt07("rrt07_builtin_1000", dict(C7, max_iter=1000), 2),

@@ -269,6 +269,40 @@ def rrtstar_dubins_run(start, goal, obstacle_list, expand_dis, max_iter, robot_r
     return res
 
 
+def rrt_dubins_run(start, goal, obstacle_list, max_iter, robot_radius, curvature, goal_yaw_th, goal_xy_th,
+                   search_until_max_iter, stream3, play_area=None, math_mode=MATH_LIBM):
+    """rrt_03 planning() (plain RRT with Dubins steering) with an injected (x, y, yaw) stream.  Raises AttributeError
+    where the reference does (steer returned None while a play area is set)."""
+    p = DubinsParams()
+    p.sx, p.sy, p.syaw = [float(v) for v in start]
+    p.gx, p.gy, p.gyaw = [float(v) for v in goal]
+    p.expand_dis, p.robot_radius, p.connect_circle_dist = 0.0, float(robot_radius), 0.0
+    p.kappa, p.goal_yaw_th, p.goal_xy_th = float(curvature), float(goal_yaw_th), float(goal_xy_th)
+    p.max_iter, p.search_until_max_iter, p.math_mode = int(max_iter), int(bool(search_until_max_iter)), int(math_mode)
+    obs = np.ascontiguousarray(np.asarray(obstacle_list, dtype=np.float64).reshape(-1, 3))
+    p.n_obs = obs.shape[0]
+    st = np.ascontiguousarray(stream3, dtype=np.float64).reshape(-1, 3)
+    play = None if play_area is None else np.ascontiguousarray(play_area, dtype=np.float64)
+    cap = max_iter + 1
+    x = np.zeros(cap); y = np.zeros(cap); yaw = np.zeros(cap); cost = np.zeros(cap)
+    parent = np.full(cap, -1, np.int32)
+    ef = np.zeros((cap, 3)); et = np.zeros((cap, 3))
+    n = C.c_int32(); it = C.c_int32(); gi = C.c_int32()
+    L = lib()
+    L.orc_rrt_dubins_run.restype = C.c_int
+    rc = L.orc_rrt_dubins_run(C.byref(p), _p(obs, C.c_double), _p(st, C.c_double),
+                              None if play is None else _p(play, C.c_double), _p(x, C.c_double), _p(y, C.c_double),
+                              _p(yaw, C.c_double), _p(cost, C.c_double), _p(parent, C.c_int32), _p(ef, C.c_double),
+                              _p(et, C.c_double), C.byref(n), C.byref(it), C.byref(gi))
+    if rc == -2:
+        raise AttributeError("'NoneType' object has no attribute 'x'")
+    k = n.value
+    res = dict(x=x[:k], y=y[:k], yaw=yaw[:k], cost=cost[:k], parent=parent[:k], edge_from=ef[:k], edge_to=et[:k],
+               n=k, iters_done=it.value, goal_index=gi.value)
+    res["path"] = dubins_final_course(res, start, goal, curvature, math_mode)
+    return res
+
+
 def dubins_final_course(res, start, goal, curvature, math_mode):
     """generate_final_course (rrt_05:1512-1521): reversed course samples of every edge up to the root."""
     gi = res["goal_index"]

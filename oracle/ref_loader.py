@@ -23,6 +23,7 @@ REF_DIR = os.environ.get("RRTK_REFERENCE_DIR", "/root/reference/src_path_plannin
 # file alias -> (file name, last line of the definition block)   [SURVEY.md 8c]
 FILES = {
     "rrt_01": ("10_path_planning_01_rrt_01_simple.py", 337),
+    "rrt_03": ("10_path_planning_01_rrt_03_dubins_path.py", 1650),
     "rrt_04": ("10_path_planning_01_rrt_04_rrt_star.py", 1482),
     "rrt_05": ("10_path_planning_01_rrt_05_rrt_star_dubins_path.py", 1797),
     "rrt_07": ("10_path_planning_01_rrt_07_informed_rrt_star.py", 1330),
@@ -66,6 +67,14 @@ def load(alias: str) -> dict:
     path = os.path.join(REF_DIR, fname)
     with open(path, "r") as fh:
         lines = fh.readlines()
+    if alias == "rrt_03":
+        # rrt_03 builds _PATH_TYPE_MAP (:1030-1031) BEFORE the word functions it names are defined (:1138-1212), so the
+        # file raises NameError as shipped; the statement is executed after the definitions instead
+        assert lines[1029].startswith("_PATH_TYPE_MAP"), "rrt_03 layout changed"
+        moved = lines[1029:1031]
+        lines[1029:1031] = ["\n", "\n"]
+        lines = lines[:last] + moved
+        last += 2
     src = "".join(lines[:last])
     ns: dict = {"__name__": "ref_" + alias, "__file__": path}
     with contextlib.redirect_stdout(io.StringIO()):

@@ -1152,6 +1152,66 @@ ORC_EXPORT int orc_rrtstar_dubins_run(const orc_dubins_params_t *p, const double
     return 0;
 }
 
+/* `sum([a, b, c])` of three Python floats as CPython >= 3.12 evaluates it (Neumaier's compensated addition after the first
+ * item, compensation added at the end; bltinmodule.c builtin_sum_impl) -- rrt_03:1470 costs an edge this way. */
+static double py312_sum3(double a, double b, double c) {
+    double f = a, comp = 0.0, t;
+    t = f + b; comp += fabs(f) >= fabs(b) ? (f - t) + b : (b - t) + f; f = t;
+    t = f + c; comp += fabs(f) >= fabs(c) ? (f - t) + c : (c - t) + f; f = t;
+    if (comp != 0.0 && isfinite(comp)) f += comp;
+    return f;
+}
+
+/* RRT-Dubins, rrt_03's `RRT.planning` (:1402-1456): plain RRT whose steer is the whole Dubins course to the sample.
+ * A new node is kept iff its end pose is inside the play area (:1437; play = xmin, xmax, ymin, ymax or NULL) and no course
+ * point is inside a circle; its cost is the parent's plus sum |course lengths| (:1470).  p->expand_dis and
+ * p->connect_circle_dist are unused.  Returns -2 where the reference raises AttributeError (steer returned None while a
+ * play area is set, :1626). */
+ORC_EXPORT int orc_rrt_dubins_run(const orc_dubins_params_t *p, const double *obs3, const double *stream3, const double *play,
+                                  double *x, double *y, double *yaw, double *cost, int32_t *parent, double *edge_from,
+                                  double *edge_to, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index) {
+    const int mode = p->math_mode;
+    int n = 1, it, gi = -1, done = 0, rc = 0;
+    double *buf = (double *)malloc(sizeof(double) * 3 * DUB_MAXPTS);
+    x[0] = p->sx; y[0] = p->sy; yaw[0] = p->syaw; cost[0] = 0.0; parent[0] = -1;
+    for (it = 0; it < p->max_iter; it++) {
+        const double *rnd = stream3 + 3 * it;
+        int ni = 0;
+        double dmin = INFINITY;
+        for (int i = 0; i < n; i++) {
+            double d = sq(mode, x[i] - rnd[0]) + sq(mode, y[i] - rnd[1]);
+            if (d < dmin) { dmin = d; ni = i; }
+        }
+        double from[3] = {x[ni], y[ni], yaw[ni]};
+        int32_t md;
+        double lengths[3];
+        int np = orc_dubins_plan(from[0], from[1], from[2], rnd[0], rnd[1], rnd[2], p->kappa, 0.1, mode, &md, lengths, NULL, 0);
+        const int truthy = np > 1;
+        if (!truthy && play) { rc = -2; it++; break; }
+        if (truthy) {
+            dub_edge_t e = dubins_edge(p, obs3, from, rnd, buf);
+            const int inside = !play || !(e.end[0] < play[0] || e.end[0] > play[1] || e.end[1] < play[2] || e.end[1] > play[3]);
+            if (inside && e.free_) {
+                x[n] = e.end[0]; y[n] = e.end[1]; yaw[n] = e.end[2];
+                cost[n] = cost[ni] + py312_sum3(fabs(lengths[0]), fabs(lengths[1]), fabs(lengths[2]));
+                parent[n] = ni;
+                memcpy(edge_from + 3 * n, from, sizeof from);
+                memcpy(edge_to + 3 * n, rnd, 3 * sizeof(double));
+                n++;
+            }
+        }
+        if (!p->search_until_max_iter && truthy) {
+            gi = dub_best_goal(p, n, x, y, yaw, cost);
+            if (gi > 0) { it++; done = 1; break; }
+        }
+    }
+    if (!done && rc == 0) gi = dub_best_goal(p, n, x, y, yaw, cost);
+    if (gi <= 0) gi = -1; /* `if last_index:` -- index 0 is falsy (rrt_03:1446, :1452) */
+    *n_nodes = n; *iters_done = it; *goal_index = gi;
+    free(buf);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Reeds-Shepp local planner (rs00:73-515 == rrt_06:1021-1437)                             */
 /* ------------------------------------------------------------------------------------ */

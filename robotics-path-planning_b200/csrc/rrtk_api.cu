@@ -50,6 +50,10 @@ int launch_rrtstar_rs(const rrtk_dubins_params &p, const double *start_goal6, co
                       double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,
                       int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                       int32_t *workspace, unsigned int *counter, cudaStream_t s);
+int launch_rrt_dubins(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles, const int32_t *n_obs,
+                      const double *play, const double *stream3, double *xy, double *yaw, double *cost, int32_t *parent,
+                      double *edge_from, double *edge_to, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+                      int32_t *status, unsigned int *counter, cudaStream_t s);
 int launch_dubins_steer(int n_req, double kappa, double step, const double *from3, const double *to3,
                         const int32_t *obs_set, const double *obstacles, int obs_stride, const int32_t *n_obs,
                         int32_t *mode, double *lengths, double *end, int32_t *n_pts, uint8_t *free_flag,
@@ -294,6 +298,22 @@ int rrtk_rrtstar_dubins_run_dev(const rrtk_dubins_params *p, const double *start
     return launch_rrtstar_dubins(*p, start_goal6, obstacles, n_obs, near_r2, stream3, xy, yaw, cost, parent, edge_from,
                                  edge_to, n_nodes, iters_done, goal_index, status, workspace,
                                  ws_tail(workspace, (size_t)p->n_queries * 4 * (size_t)p->node_cap), s);
+}
+
+int rrtk_rrt_dubins_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,
+                            const int32_t *n_obs, const double *play_area, const double *stream3, double *xy, double *yaw,
+                            double *cost, int32_t *parent, double *edge_from, double *edge_to, int32_t *n_nodes,
+                            int32_t *iters_done, int32_t *goal_index, int32_t *status, int32_t *workspace, void *stream) {
+    if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
+    if (p->n_queries < 0 || p->max_iter < 0 || p->node_cap < 1 || p->obs_stride < 0) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (!(p->curvature > 0.0) || !(p->step_size > 0.0)) return set_error(RRTK_ERR_INVALID, "curvature and step_size must be > 0");
+    if (p->n_queries == 0) return RRTK_OK;
+    if (!start_goal6 || !n_obs || !xy || !yaw || !cost || !parent || !edge_from || !edge_to || !n_nodes || !iters_done ||
+        !goal_index || !status || !workspace || (p->max_iter > 0 && !stream3) || (p->obs_stride > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)xy | (uintptr_t)obstacles) & 15) return set_error(RRTK_ERR_INVALID, "xy and obstacles must be 16-byte aligned");
+    return launch_rrt_dubins(*p, start_goal6, obstacles, n_obs, play_area, stream3, xy, yaw, cost, parent, edge_from, edge_to,
+                             n_nodes, iters_done, goal_index, status, ws_tail(workspace, 0), (cudaStream_t)stream);
 }
 
 int rrtk_rrtstar_rs_run_dev(const rrtk_dubins_params *p, const double *start_goal6, const double *obstacles,

@@ -258,9 +258,10 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
 // points of each segment spread over the lanes (each lane reaches its first distance by the reference's repeated
 // `cur += step`), as dubins_steer_kernel does.  Used where the planner has one edge to evaluate (first steer, re-planned
 // rewire edges).
+// lengths_out (optional): the three course lengths plan_dubins_path returns (word lengths / curvature, rrt_05:1095).
 static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, double s_yaw, double g_x, double g_y,
                                                         double g_yaw, double kappa, double step, const double4 *obs,
-                                                        int n_obs, int lane) {
+                                                        int n_obs, int lane, double *lengths_out = nullptr) {
     DubEdge e;
     e.ex = e.ey = e.eyaw = 0.0;
     e.npts = 0;
@@ -286,6 +287,10 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     double len[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, w[k], bi);
+    if (lengths_out) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) lengths_out[k] = len[k] / kappa;
+    }
     double c2, s2;
     rot2d(-s_yaw, &c2, &s2);
     const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);

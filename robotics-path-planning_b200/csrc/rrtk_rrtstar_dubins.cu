@@ -322,6 +322,136 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
     }
 }
 
+// `sum([a, b, c])` of three Python floats as CPython >= 3.12 evaluates it: the first item plainly, the others through
+// Neumaier's compensated addition, the compensation added at the end (bltinmodule.c builtin_sum_impl; rrt_03:1470)
+static __device__ __forceinline__ double py312_sum3(double a, double b, double c) {
+    double f = a, comp = 0.0, t;
+    t = f + b; comp += fabs(f) >= fabs(b) ? (f - t) + b : (b - t) + f; f = t;
+    t = f + c; comp += fabs(f) >= fabs(c) ? (f - t) + c : (c - t) + f; f = t;
+    if (comp != 0.0 && isfinite(comp)) f += comp;
+    return f;
+}
+
+// RRT-Dubins (rrt_03:1402-1456), one warp per query: nearest on xy, ONE Dubins edge per iteration evaluated by the whole
+// warp (words across lanes, course points across lanes), play-area test of the end pose, append.
+__global__ void __launch_bounds__(DUB_WARPS_PER_CTA * 32, 3)
+rrt_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goal6, const double4 *__restrict__ obstacles,
+                  const int32_t *__restrict__ n_obs_arr, const double *__restrict__ play, const double *__restrict__ stream3,
+                  double2 *xy_all, double *yaw_all, double *cost_all, int32_t *parent_all, double *edge_from_all,
+                  double *edge_to_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status_out,
+                  unsigned int *counter) {
+    const int lane = threadIdx.x & 31;
+    const double INF = CUDART_INF;
+    const double kappa = p.curvature, step = p.step_size;
+    double pa[4] = {0.0, 0.0, 0.0, 0.0};
+    if (play) { pa[0] = play[0]; pa[1] = play[1]; pa[2] = play[2]; pa[3] = play[3]; }
+    for (;;) {
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= (unsigned)p.n_queries) break;
+        const double *sg = start_goal6 + 6 * (size_t)q;
+        const double gx = sg[3], gy = sg[4], gyaw = sg[5];
+        const double4 *obs = obstacles + (size_t)q * p.obs_stride;
+        const int n_obs = n_obs_arr[q];
+        double2 *xy = xy_all + (size_t)q * p.node_cap;
+        double *yaw = yaw_all + (size_t)q * p.node_cap;
+        double *cost = cost_all + (size_t)q * p.node_cap;
+        int32_t *parent = parent_all + (size_t)q * p.node_cap;
+        double *efrom = edge_from_all + (size_t)q * p.node_cap * 3;
+        double *eto = edge_to_all + (size_t)q * p.node_cap * 3;
+        const double *stream = stream3 + (size_t)q * p.max_iter * 3;
+        if (lane == 0) {
+            xy[0] = make_double2(sg[0], sg[1]); yaw[0] = sg[2]; cost[0] = 0.0; parent[0] = -1;
+            for (int k = 0; k < 3; k++) { efrom[k] = 0.0; eto[k] = 0.0; }
+        }
+        __syncwarp();
+        int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
+        bool done = false;
+        auto best_goal = [&]() {   // search_best_goal_node (rrt_03:1491-1512): first minimum of the cost, -1 = none
+            double bc = INF;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                const double2 a = xy[i];
+                if (crm_hypot(a.x - gx, a.y - gy) <= p.goal_xy_th && fabs(yaw[i] - gyaw) <= p.goal_yaw_th) {
+                    const double c = cost[i];
+                    if (c < bc) { bc = c; bi = i; }
+                }
+            }
+            warp_argmin(bc, bi);
+            return bi == 0x7fffffff ? -1 : bi;
+        };
+        for (it = 0; it < p.max_iter; it++) {
+            const double rx = stream[3 * it], ry = stream[3 * it + 1], ryaw = stream[3 * it + 2];
+            double bd = INF;
+            int bi = 0x7fffffff;
+#pragma unroll 1
+            for (int i = lane; i < n; i += 32) {   // get_nearest_node_index (rrt_03:1612-1618)
+                const double2 a = xy[i];
+                const double ddx = a.x - rx, ddy = a.y - ry;
+                const double d = ddx * ddx + ddy * ddy;
+                if (d < bd) { bd = d; bi = i; }
+            }
+            warp_argmin(bd, bi);
+            const int ni = bi;
+            const double2 from = xy[ni];
+            const double fyaw = yaw[ni];
+            double len3[3] = {0.0, 0.0, 0.0};
+            const DubEdge e = dubins_edge_warp(from.x, from.y, fyaw, rx, ry, ryaw, kappa, step, obs, n_obs, lane, len3);
+            const bool truthy = e.npts > 1;
+            if (!truthy && play) { status |= RRTK_Q_NONE_STEER; it++; done = true; break; }
+            if (truthy && e.free_ && (!play || !(e.ex < pa[0] || e.ex > pa[1] || e.ey < pa[2] || e.ey > pa[3]))) {
+                if (n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; it++; done = true; break; }
+                if (lane == 0) {
+                    efrom[3 * n] = from.x; efrom[3 * n + 1] = from.y; efrom[3 * n + 2] = fyaw;
+                    eto[3 * n] = rx; eto[3 * n + 1] = ry; eto[3 * n + 2] = ryaw;
+                    xy[n] = make_double2(e.ex, e.ey); yaw[n] = e.eyaw; parent[n] = ni;
+                    cost[n] = cost[ni] + py312_sum3(fabs(len3[0]), fabs(len3[1]), fabs(len3[2]));
+                }
+                n++;
+                __syncwarp();
+            }
+            if (!p.search_until_max_iter && truthy) {
+                gi = best_goal();
+                if (gi > 0) { it++; done = true; break; }
+            }
+        }
+        if (!done) gi = best_goal();
+        if (gi <= 0) gi = -1;   // `if last_index:` -- index 0 is falsy (rrt_03:1446, :1452)
+        if (lane == 0) {
+            n_nodes[q] = n;
+            iters_done[q] = it;
+            goal_index[q] = gi;
+            status_out[q] = status;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_rrt_dubins(const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles, const int32_t *n_obs,
+                      const double *play, const double *stream3, double *xy, double *yaw, double *cost, int32_t *parent,
+                      double *edge_from, double *edge_to, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
+                      int32_t *status, unsigned int *counter, cudaStream_t s) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rrt_dubins_kernel, DUB_WARPS_PER_CTA * 32, 0);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)p.n_queries + DUB_WARPS_PER_CTA - 1) / DUB_WARPS_PER_CTA;
+    long long grid = (long long)sms * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
+    rrt_dubins_kernel<<<(unsigned)grid, DUB_WARPS_PER_CTA * 32, 0, s>>>(
+        p, start_goal6, reinterpret_cast<const double4 *>(obstacles), n_obs, play, stream3, reinterpret_cast<double2 *>(xy), yaw,
+        cost, parent, edge_from, edge_to, n_nodes, iters_done, goal_index, status, counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "rrt_dubins_kernel launch");
+    return RRTK_OK;
+}
+
 int launch_rrtstar_steer(int steer, const rrtk_dubins_params &p, const double *start_goal6, const double *obstacles,
                           const int32_t *n_obs, const double *near_r2, const double *stream3, double *xy,
                           double *yaw, double *cost, int32_t *parent, double *edge_from, double *edge_to,

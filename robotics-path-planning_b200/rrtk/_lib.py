@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("RRTK_LIB", os.path.join(HERE, "librrtk.so"))  # overr
 SAMPLER_STREAM, SAMPLER_SOBOL, SAMPLER_UNIFORM = 0, 1, 2
 EXEC_AUTO, EXEC_WARP, EXEC_CTA = 0, 1, 2   # rrtk_rrtstar_params.exec_mode / rrtk_dubins_params.exec_mode
 WS_TAIL_INTS = 4                           # RRTK_WS_TAIL_INTS: every planner workspace ends with the work-queue counter
-Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW, Q_DIV_ZERO = 0, 1, 2, 4, 8
+Q_OK, Q_NEAR_OVERFLOW, Q_NODE_OVERFLOW, Q_PATH_OVERFLOW, Q_DIV_ZERO, Q_NONE_STEER = 0, 1, 2, 4, 8, 16
 
 
 class RrtkError(RuntimeError):
@@ -99,6 +99,7 @@ _SIGS = {
     "rrtk_tree_exchange_probe_dev": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, C.c_int64, _VP]),
     "rrtk_rrtstar_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_rrtstar_rs_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
+    "rrtk_rrt_dubins_run_dev": (C.c_int, [C.POINTER(DubinsParams)] + [_VP] * 17),
     "rrtk_dubins_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,
                                         _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "rrtk_reeds_shepp_steer_dev": (C.c_int, [C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP, _VP, C.c_int32, _VP,

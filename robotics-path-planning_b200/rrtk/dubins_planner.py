@@ -183,3 +183,139 @@ class RRTStarDubins:
 
     def tree_arrays(self):
         return self._tree
+
+
+def run_rrt_batch(starts, goals, obstacle_lists, max_iter, streams, robot_radius=0.0, curvature=1.0,
+                  goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5, search_until_max_iter=True, play_area=None, device=None,
+                  timing=None):
+    """Q RRT-Dubins queries (rrt_03 semantics, rrtk_rrt_dubins_run_dev) in one launch.  starts / goals [Q, 3]; streams
+    [Q, max_iter, 3]; play_area = None or (xmin, xmax, ymin, ymax) for the whole batch.  Returns a list of dicts like
+    run_batch (status has Q_NONE_STEER where the reference would raise AttributeError)."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
+    goals = np.asarray(goals, dtype=np.float64).reshape(-1, 3)
+    q, cap = starts.shape[0], max_iter + 1
+    rows, counts = engine.pack_obstacles(obstacle_lists, robot_radius)
+    p = _lib.DubinsParams()
+    p.n_queries, p.max_iter, p.node_cap, p.obs_stride, p.near_cap = q, max_iter, cap, rows.shape[1], 32
+    p.search_until_max_iter = int(bool(search_until_max_iter))
+    p.curvature, p.step_size = float(curvature), 0.1
+    p.goal_xy_th, p.goal_yaw_th = float(goal_xy_th), float(goal_yaw_th)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        d_sg, d_obs, d_cnt = t(np.hstack([starts, goals])), t(rows), t(counts)
+        d_st = t(np.asarray(streams, dtype=np.float64).reshape(q, max_iter, 3))
+        d_play = None if play_area is None else t(np.asarray(play_area, dtype=np.float64).reshape(4))
+        f64 = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)    # noqa: E731
+        xy, yaw, cost, parent = f64(q, cap, 2), f64(q, cap), f64(q, cap), i32(q, cap)
+        ef, et = f64(q, cap, 3), f64(q, cap, 3)
+        n_nodes, iters, gi, status, ws = i32(q), i32(q), i32(q), i32(q), i32(_lib.WS_TAIL_INTS)
+        if timing is not None:
+            ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev[0].record()
+        rc = _lib.lib().rrtk_rrt_dubins_run_dev(
+            C.byref(p), d_sg.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), None if d_play is None else d_play.data_ptr(),
+            d_st.data_ptr(), xy.data_ptr(), yaw.data_ptr(), cost.data_ptr(), parent.data_ptr(), ef.data_ptr(), et.data_ptr(),
+            n_nodes.data_ptr(), iters.data_ptr(), gi.data_ptr(), status.data_ptr(), ws.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_rrt_dubins_run_dev")
+        if timing is not None:
+            ev[1].record()
+            ev[1].synchronize()
+            timing["kernel_ms"] = ev[0].elapsed_time(ev[1])
+        h = {k: v.cpu().numpy() for k, v in dict(xy=xy, yaw=yaw, cost=cost, parent=parent, ef=ef, et=et, n=n_nodes,
+                                                 it=iters, gi=gi, st=status).items()}
+    out = []
+    for i in range(q):
+        k = int(h["n"][i])
+        out.append(dict(x=h["xy"][i, :k, 0].copy(), y=h["xy"][i, :k, 1].copy(), yaw=h["yaw"][i, :k].copy(),
+                        cost=h["cost"][i, :k].copy(), parent=h["parent"][i, :k].copy(),
+                        edge_from=h["ef"][i, :k].copy(), edge_to=h["et"][i, :k].copy(), n=k,
+                        iters_done=int(h["it"][i]), goal_index=int(h["gi"][i]), status=int(h["st"][i])))
+    return out
+
+
+class RRTDubins:
+    """rrt_03's `RRT`: plain RRT with Dubins steering, same constructor keywords and defaults (rrt_03:1370-1383).
+    `planning(animation=True, search_until_max_iter=True)` returns the sampled final course (goal -> start) or None.
+    Unlike rrt_05, `sobol_sampler` is honoured (:1430-1433): x, y from points of the 3-D Sobol sequence mapped to
+    rand_area, yaw = -pi + q * pi (:1545-1562); the goal coin and the uniform sampler draw from `random` exactly as the
+    reference does.  The play-area test applies to the new node's end pose (:1437).  No CPU fallback."""
+
+    Node = Node
+
+    def __init__(self, start, goal, obstacle_list, rand_area, goal_sample_rate=10, max_iter=200, play_area=None,
+                 robot_radius=0.0, sobol_sampler=False, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5):
+        self.start = Node(start[0], start[1], start[2])
+        self.end = Node(goal[0], goal[1], goal[2])
+        self.min_rand, self.max_rand = rand_area[0], rand_area[1]
+        self.play_area = play_area
+        self.goal_sample_rate, self.max_iter = goal_sample_rate, max_iter
+        self.obstacle_list = obstacle_list
+        self.node_list = []
+        self.robot_radius = robot_radius
+        self.sobol_inter_, self.sobol_sampler = 0, sobol_sampler
+        self.curvature, self.goal_yaw_th, self.goal_xy_th = curvature, goal_yaw_th, goal_xy_th
+        self._tree = None
+
+    def _draw_stream(self, n):
+        """The samples `get_random_node` / `get_random_node_sobol` return over n iterations (rrt_03:1528-1562), drawing
+        from `random` call for call like the reference; returns (stream [n, 3], is_goal [n])."""
+        from . import sampling
+        goal = (self.end.x, self.end.y, self.end.yaw)
+        stream = np.empty((n, 3), dtype=np.float64)
+        is_goal = np.zeros(n, dtype=bool)
+        if self.sobol_sampler:
+            for i in range(n):
+                is_goal[i] = not (random.randint(0, 100) > self.goal_sample_rate)
+            k = int((~is_goal).sum())
+            pts = sampling.sobol_points(3, self.sobol_inter_, k)
+            xy = self.min_rand + pts[:, 0:2] * (self.max_rand - self.min_rand)
+            stream[~is_goal] = np.column_stack([xy, -pi + pts[:, 2] * pi])
+            stream[is_goal] = goal
+            return stream, is_goal
+        for i in range(n):
+            if random.randint(0, 100) > self.goal_sample_rate:
+                stream[i] = (random.uniform(self.min_rand, self.max_rand), random.uniform(self.min_rand, self.max_rand),
+                             random.uniform(-pi, pi))
+            else:
+                is_goal[i] = True
+                stream[i] = goal
+        return stream, is_goal
+
+    def planning(self, animation=True, search_until_max_iter=True, sample_stream=None):
+        n = int(self.max_iter)
+        rng_state, is_goal = None, None
+        if sample_stream is None:
+            rng_state = random.getstate()
+            sample_stream, is_goal = self._draw_stream(n)
+        stream = np.asarray(sample_stream, dtype=np.float64).reshape(-1, 3)[:n]
+        start = (self.start.x, self.start.y, self.start.yaw)
+        goal = (self.end.x, self.end.y, self.end.yaw)
+        t = run_rrt_batch([start], [goal], [list(self.obstacle_list)], n, stream[None], self.robot_radius, self.curvature,
+                          self.goal_yaw_th, self.goal_xy_th, search_until_max_iter, self.play_area)[0]
+        self._tree = t
+        done = t["iters_done"]
+        if is_goal is not None:
+            # leave `random` and sobol_inter_ where the reference's lazily drawing loop would have left them
+            self.sobol_inter_ += int((~is_goal[:done]).sum()) if self.sobol_sampler else 0
+            if done < n:
+                random.setstate(rng_state)
+                for i in range(done):
+                    if random.randint(0, 100) > self.goal_sample_rate and not self.sobol_sampler:
+                        random.uniform(0, 1), random.uniform(0, 1), random.uniform(0, 1)
+        nodes = [Node(float(x), float(y), float(w)) for x, y, w in zip(t["x"], t["y"], t["yaw"])]
+        for i, nd in enumerate(nodes):
+            nd.cost = float(t["cost"][i])
+            if t["parent"][i] >= 0:
+                nd.parent = nodes[t["parent"][i]]
+                nd._edge = (t["edge_from"][i], t["edge_to"][i], self.curvature)
+        self.node_list = nodes
+        if t["status"] & _lib.Q_NONE_STEER:
+            raise AttributeError("'NoneType' object has no attribute 'x'")       # what rrt_03:1626 raises here
+        return final_course(t, start, goal, self.curvature)
+
+    def tree_arrays(self):
+        return self._tree

@@ -246,3 +246,71 @@ def test_dubins_loop_c_oracle(name, oracle_lib):
     assert c["n"] == r["n"] and np.array_equal(c["parent"], r["parent"]) and c["goal_index"] == r["goal_index"]
     for k in ("x", "y", "yaw", "cost"):
         assert np.allclose(c[k], r[k], rtol=0, atol=1e-12), k
+
+
+# ---- RRT-Dubins loop (rrt_03:1402-1456): plain RRT, Dubins steering, play area, 3-D Sobol sampler ----
+RRT03 = golden_names("rrt03_")
+
+
+def _rrt03_args(m, g):
+    return (m["start"], m["goal"], m["obstacle_list"], m["iters"], m["robot_radius"], m["curvature"], m["goal_yaw_th"],
+            m["goal_xy_th"], m["search_until_max_iter"], g["stream"], m.get("play_area"))
+
+
+@pytest.mark.parametrize("name", RRT03)
+def test_rrt_dubins_python_port_bit_identical_to_reference(name):
+    import pyport
+    g, m = load_golden(name)
+    p = pyport.RRTDubinsPort(m["start"], m["goal"], m["obstacle_list"], m["iters"], m.get("play_area"), m["robot_radius"],
+                             m["curvature"], m["goal_yaw_th"], m["goal_xy_th"], m["search_until_max_iter"])
+    path = p.planning([tuple(r) for r in g["stream"]])
+    for k, v in (("x", p.x), ("y", p.y), ("yaw", p.yaw), ("cost", p.cost), ("parent", p.parent)):
+        assert np.array_equal(np.array(v), g[k]), k
+    assert (path is None and len(g["path"]) == 0) or np.array_equal(np.array(path, float), g["path"])
+
+
+@pytest.mark.parametrize("name", RRT03)
+def test_rrt_dubins_c_oracle(name, oracle_lib):
+    """libm mode: bit-identical to the reference (tree, Dubins-length costs, sampled path).  cr mode: same tree topology,
+    poses and costs within 1e-12."""
+    O = oracle_lib
+    g, m = load_golden(name)
+    r = O.rrt_dubins_run(*_rrt03_args(m, g), math_mode=O.MATH_LIBM)
+    assert r["n"] == len(g["x"]) and r["n"] > 5
+    for k in ("x", "y", "yaw", "cost", "parent"):
+        assert np.array_equal(r[k], g[k]), k
+    assert (r["path"] is None and len(g["path"]) == 0) or np.array_equal(np.array(r["path"], float), g["path"])
+    c = O.rrt_dubins_run(*_rrt03_args(m, g), math_mode=O.MATH_CR)
+    assert c["n"] == r["n"] and np.array_equal(c["parent"], r["parent"]) and c["goal_index"] == r["goal_index"]
+    for k in ("x", "y", "yaw", "cost"):
+        assert np.allclose(c[k], r[k], rtol=0, atol=1e-12), k
+
+
+def test_rrt_dubins_sobol_stream_is_the_3d_sequence(oracle_lib):
+    """The samples rrt_03 drew by itself (get_random_node_sobol :1545-1562): min_rand + q * (max_rand - min_rand) for x, y
+    and -pi + q * pi for yaw, q = point `sobol_inter_` of the 3-D Bratley-Fox sequence, advanced on non-goal coins only."""
+    import math
+    g, m = load_golden("rrt03_builtin_sobol_200")
+    st = g["stream"]
+    goal = np.array(m["goal"], dtype=np.float64)
+    non_goal = ~np.all(st == goal, axis=1)
+    pts = oracle_lib.sobol_fill(3, 0, int(non_goal.sum()))
+    lo, hi = m["rand_area"]
+    want = np.column_stack([lo + pts[:, 0] * (hi - lo), lo + pts[:, 1] * (hi - lo), -math.pi + pts[:, 2] * math.pi])
+    assert np.array_equal(st[non_goal], want)
+    assert m["sobol_inter_"] == int(non_goal.sum())
+
+
+def test_rrt_dubins_none_steer_with_play_area_raises_like_the_reference(oracle_lib):
+    """A second goal sample from a node that already sits on the goal pose makes steer return None; with a play area set
+    rrt_03 then evaluates `node.x` of None (:1626) -> AttributeError.  Port and oracle raise the same."""
+    import pyport
+    start, goal = [0.0, 0.0, 0.0], [4.0, 0.0, 0.0]
+    stream = np.array([goal, goal, [1.0, 1.0, 0.3]])
+    p = pyport.RRTDubinsPort(start, goal, [], 3, [-5.0, 5.0, -5.0, 5.0], 0.0, 1.0, 0.1, 0.5, True)
+    with pytest.raises(AttributeError):
+        p.planning([tuple(r) for r in stream])
+    with pytest.raises(AttributeError):
+        oracle_lib.rrt_dubins_run(start, goal, [], 3, 0.0, 1.0, 0.1, 0.5, True, stream, [-5.0, 5.0, -5.0, 5.0])
+    r = oracle_lib.rrt_dubins_run(start, goal, [], 3, 0.0, 1.0, 0.1, 0.5, True, stream, None)   # no play area: just skipped
+    assert r["n"] == 3 and r["goal_index"] == 1
