@@ -272,8 +272,8 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 if (snap_certain(d0, false, p.expand_dis, q_expand, res, inv_res)) {
                     if (inside_play(p, nx, ny)) {
                         L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
-                        const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
-                                                         lane, 32, ~0ull).v;
+                        const int vl = edge_verdict_fast<false>(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
+                                                                lane, 32, ~0ull).v;
                         const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                         v = blocked ? 0 : (unsure ? -1 : 1);
                         if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
@@ -324,17 +324,13 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                         // ---- choose_parent (rrt_04:1242-1282): one lane per candidate ----
                         double bc = INF, bex = 0.0, bey = 0.0;
                         int bk = 0x7fffffff;
-                        // circles near the segment candidate `lane` - new node (first round), for the reverse edge in rewire
-                        unsigned long long seg_near = ~0ull;
                         for (int k = lane; k < count; k += 32) {
                             int i = near_idx[k];
                             double2 a = xy[i];
                             double ci = cost[i];
                             const double dk = crm_hypot(nx - a.x, ny - a.y);  // what steer's calc_distance_and_angle returns
                             double ex = nx, ey = ny;                          // a snapped edge ends on the new node
-                            const EdgeVerdict ev = edge_verdict_fast(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull);
-                            const int v = ev.v;
-                            if (k < 32) seg_near = v == 1 ? ev.near : ~0ull;
+                            const int v = edge_verdict_fast<false>(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull).v;
                             bool ok = v == 1;                                 // (the new node is inside the play area)
                             if (v < 0) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
@@ -389,18 +385,8 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                     ecost = ccost + dk;
                                     want = TRACE || (snc > ecost);
                                 }
-                                // the reverse edge runs along the segment choose_parent tested (when the new node is the
-                                // sample): only the circles found near it then can matter, usually none
-#ifdef RRTK_V_NOMASK
-                                const unsigned long long only = ~0ull;
-#else
-                                const unsigned long long only = (c_is_new && b0 == 0) ? seg_near : ~0ull;
-#endif
-                                if (want && only == 0ull) {
-                                    st.ex = a.x; st.ey = a.y;
-                                    ok = inside_play(p, a.x, a.y);
-                                } else if (want) {
-                                    const int v = edge_verdict_fast(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, 0, 1, only).v;
+                                if (want) {
+                                    const int v = edge_verdict_fast<false>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull).v;
                                     if (v < 0) {
                                         st = steer(cx, cy, a.x, a.y, INF, res);
                                         ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);

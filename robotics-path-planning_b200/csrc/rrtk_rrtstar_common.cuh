@@ -112,6 +112,9 @@ struct EdgeVerdict {
     int v;
     unsigned long long near;
 };
+// MASK = false: `only` is ignored and `near` is not produced (the warp-per-query kernel: lanes of a warp run the reverse
+// edges in lockstep, so skipping circles in some lanes saves nothing there and the bookkeeping costs 5 % -- measured).
+template <bool MASK>
 static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double fy, double tx, double ty, double d, bool d_exact,
                                                              double extend, double q_ext, double res, double inv_res,
                                                              const ObsList &L, int j0, int jstep, unsigned long long only) {
@@ -142,7 +145,7 @@ static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double f
     const double wx = tx - fx, wy = ty - fy, invl2 = inv_d * inv_d;
     int b = 0;
     for (int j = j0; j < L.m; j += jstep, b++) {
-        if (b < 64 && !((only >> b) & 1ull)) continue;
+        if (MASK && b < 64 && !((only >> b) & 1ull)) continue;
         const double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];
         double dx = ox - fx, dy = oy - fy;             // first point: f itself, exact test
         if (dx * dx + dy * dy <= r2) { r.v = 0; return r; }
@@ -153,7 +156,7 @@ static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double f
         sp = sp < 0.0 ? 0.0 : (sp > 1.0 ? 1.0 : sp);
         const double px = dx - sp * wx, py = dy - sp * wy;
         if (px * px + py * py - r2 > bj + 1e-9 * (1.0 + r2)) continue;
-        near |= b < 64 ? (1ull << b) : 0ull;
+        if (MASK) near |= b < 64 ? (1ull << b) : 0ull;
         dx = ox - tx; dy = oy - ty;                    // last point: t itself (snapped), exact test
         if (dx * dx + dy * dy <= r2) { r.v = 0; return r; }
         double x = fx, y = fy;
@@ -168,7 +171,7 @@ static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double f
         }
     }
     r.v = unsure ? -1 : 1;
-    r.near = b > 64 ? ~0ull : near;
+    r.near = (!MASK || b > 64) ? ~0ull : near;
     return r;
 }
 
@@ -209,7 +212,10 @@ struct SobolState {
 };
 
 // get_random_node / get_random_node_sobol (rrt_04:1132-1153) with a counter-based coin
-static __device__ __forceinline__ Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, int it_key, double gx,
+#ifndef RRTK_DRAW_SAMPLE_INLINE
+#define RRTK_DRAW_SAMPLE_INLINE __forceinline__
+#endif
+static __device__ RRTK_DRAW_SAMPLE_INLINE Sample draw_sample(const rrtk_rrtstar_params &p, int q, int it, int it_key, double gx,
                                               double gy, const double2 *stream, SobolState &sob) {
     Sample s;
     if (p.sampler == RRTK_SAMPLER_STREAM) {

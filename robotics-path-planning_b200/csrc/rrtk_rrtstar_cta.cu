@@ -27,6 +27,7 @@
 #include "crmath.h"
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
+#define RRTK_DRAW_SAMPLE_INLINE __noinline__   // one copy: only the sampling warp runs it
 #include "rrtk_rrtstar_common.cuh"
 
 namespace rrtk {
@@ -58,13 +59,16 @@ struct CtaSmemT {
     double fq_cost[CTA_FQ];
     double red_d[CTA_W], red_ex[CTA_W], red_ey[CTA_W];
     double nx, ny;                   // the new node (warp 0 -> all)
+    double smp[2][2];                // the sample of this iteration [it & 1] and the next (drawn by warp 1)
+    double def_cost;                 // deferred propagate (see the apply loop): root cost
     int near_idx[NC];
     int near_ok[NC];             // unordered indices while the list is built, then the rewire flags
     int red_i[CTA_W];
     int cull_m[2], cull_glob[2];
     int count, cpok, tail;
     int accept, near_valid, t_status;
-    int done, gi, status_or;
+    int done, gi, status_or, ni, leader;
+    int def_root;                    // deferred propagate: root node, -1 = none pending
     unsigned int q;
     unsigned short fq_idx[CTA_FQ];
 };
@@ -186,12 +190,15 @@ static __device__ __noinline__ void cta_rewire_serial(const rrtk_rrtstar_params 
 // near list of the CTA: the unordered hits (S.near_ok = index, S.s_nc = d2) -> S.near_idx / S.nd in ascending index
 // order, every hit replaced by the FIRST hit (lowest index) with the same d2 -- `dist_list.index(i)` of rrt_04:1336-1337.
 // Threads t0, t0 + nt, ... of the caller take the entries.
+// (out of line and not unrolled: the kernel is bound by instruction fetch -- every byte of the per-iteration path counts)
 template <class SM>
-static __device__ __forceinline__ void cta_rank_near(SM &S, int count, int t0, int nt) {
+static __device__ __noinline__ void cta_rank_near(SM &S, int count, int t0, int nt) {
+#pragma unroll 1
     for (int k = t0; k < count; k += nt) {
         const int ik = S.near_ok[k];
         const double dk = S.s_nc[k];
         int rank = 0, first = ik;
+#pragma unroll 1
         for (int j = 0; j < count; j++) {
             const int ij = S.near_ok[j];
             rank += ij < ik ? 1 : 0;
@@ -216,7 +223,18 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
     double2 *s_xy = reinterpret_cast<double2 *>(smem_raw + ((sizeof(CtaSmem) + 15) & ~(size_t)15));
     ushort2 *s_link = reinterpret_cast<ushort2 *>(s_xy + p.node_cap);
     unsigned short *s_par = reinterpret_cast<unsigned short *>(s_link + p.node_cap);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Roles go by VIRTUAL warp number: warp 0 of every CTA lands on the same scheduler (SM sub-partition) of its SM, and
+    // virtual warp 0 carries most of the serial work, so the (up to four) resident CTAs rotate it: CTA slot c of the SM
+    // makes its hardware warp c the leader.  %warpid = the warp's slot in the SM, four consecutive ones per CTA.
+    if (threadIdx.x == 0) {
+        unsigned hw;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
+        S.leader = (int)((hw / CTA_W) % CTA_W);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = ((int)(threadIdx.x >> 5) + CTA_W - S.leader) % CTA_W;
+    const int tid = warp * 32 + lane;
     const int near_cap = p.near_cap;
     const double res = p.path_resolution;
     const double INF = CUDART_INF;
@@ -302,18 +320,24 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         if (tid == 0) { S.count = 0; S.cpok = 0; S.done = 0; S.gi = -1; S.status_or = 0; }
         sobol2(sob.n, sob.q0, sob.q1);
         bool done = false;
+        // costs are read inside an iteration only by choose_parent / rewire (after B2) unless the goal is searched every
+        // iteration: then no propagate may be left pending
+        const bool can_defer = !RRT_ONLY && p.search_until_max_iter != 0;
         const double inv_res = 1.0 / res, q_expand = floor(p.expand_dis / res);   // steer's n_expand at full extension
         // near radius of the current tree size, and (loaded one iteration ahead) of the size after an append
         double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];
         // the sample of iteration 0, and the circles around it
-        Sample smp_next;
-        smp_next.x = smp_next.y = 0.0;
-        if (p.max_iter > 0) smp_next = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sob);
+        if (tid == 0) S.def_root = -1;
         __syncthreads();   // the obstacle cells are built
-        if (warp == 1 && p.max_iter > 0 && inside_play(p, smp_next.x, smp_next.y)) {
-            const ObsList L0 = cull_obstacles_grid(grid, obs, n_obs, smp_next.x, smp_next.y, reach, S.cull[0][0], S.cull[0][1],
-                                                   S.cull[0][2], lane);
-            if (lane == 0) { S.cull_m[0] = L0.m; S.cull_glob[0] = L0.stride == 4 ? 1 : 0; }
+        // warp 1 draws the samples (one iteration ahead) and gathers the circles around them
+        if (warp == 1 && p.max_iter > 0) {
+            const Sample s0 = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sob);
+            if (lane == 0) { S.smp[0][0] = s0.x; S.smp[0][1] = s0.y; }
+            if (inside_play(p, s0.x, s0.y)) {
+                const ObsList L0 = cull_obstacles_grid(grid, obs, n_obs, s0.x, s0.y, reach, S.cull[0][0], S.cull[0][1],
+                                                       S.cull[0][2], lane);
+                if (lane == 0) { S.cull_m[0] = L0.m; S.cull_glob[0] = L0.stride == 4 ? 1 : 0; }
+            }
         }
         __syncthreads();
 
@@ -323,9 +347,12 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             long long clk[10];
 #endif
             CTA_CLK(0);
-            const double rx = smp_next.x, ry = smp_next.y;
-            if (it + 1 < p.max_iter)
-                smp_next = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
+            const double rx = S.smp[cb][0], ry = S.smp[cb][1];
+            // a propagate left over by the previous iteration's rewire runs on warp 3 while the others scan (its costs are
+            // first read after B2)
+            const int def_root = S.def_root;
+            const bool defer = def_root >= 0;
+            const int scan_t = defer ? CTA_T - 32 : CTA_T;
             // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the sample
             // (when the steered node snaps onto the sample -- the common case once the tree is dense -- the near scan
             // would compute exactly these d2 again) ----
@@ -333,30 +360,39 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             int bi = BIG;
             const double r2_grown = RRT_ONLY ? -1.0 : near_r2[n + 2 <= p.node_cap + 1 ? n + 2 : p.node_cap + 1];
             const int n_before = n;
-#pragma unroll 4
-            for (int i = tid; i < n; i += CTA_T) {
-                const double2 a = s_xy[i];
-                const double ddx = a.x - rx, ddy = a.y - ry;
-                const double d = ddx * ddx + ddy * ddy;
-                if (d < bd) { bd = d; bi = i; }
-                if (d <= r2) {
-                    const int slot = atomicAdd(&S.count, 1);
-                    if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
+            if (defer && warp == CTA_W - 1) {
+                cta_propagate(def_root, S.def_cost, false, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
+            } else {
+#pragma unroll 2
+                for (int i = tid; i < n; i += scan_t) {
+                    const double2 a = s_xy[i];
+                    const double ddx = a.x - rx, ddy = a.y - ry;
+                    const double d = ddx * ddx + ddy * ddy;
+                    if (d < bd) { bd = d; bi = i; }
+                    if (d <= r2) {
+                        const int slot = atomicAdd(&S.count, 1);
+                        if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
+                    }
+                }
+                warp_argmin(bd, bi);
+                if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; }
+                CTA_CLK(1);
+                // ---- B1 (the scanning warps only while warp 3 propagates: it joins at B2)
+                if (defer) asm volatile("bar.sync 1, %0;" ::"n"(CTA_T - 32) : "memory");
+            }
+            if (!defer) __syncthreads();   // ---- B1
+            const int scan_w = defer ? CTA_W - 1 : CTA_W;
+            if (!(defer && warp == CTA_W - 1)) {
+                bd = S.red_d[0]; bi = S.red_i[0];
+#pragma unroll 1
+                for (int w = 1; w < scan_w; w++) {
+                    const double dw = S.red_d[w];
+                    const int iw = S.red_i[w];
+                    if (dw < bd || (dw == bd && iw < bi)) { bd = dw; bi = iw; }
                 }
             }
-            warp_argmin(bd, bi);
-            if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; }
-            CTA_CLK(1);
-            __syncthreads();   // ---- B1
-            bd = S.red_d[0]; bi = S.red_i[0];
-#pragma unroll
-            for (int w = 1; w < CTA_W; w++) {
-                const double dw = S.red_d[w];
-                const int iw = S.red_i[w];
-                if (dw < bd || (dw == bd && iw < bi)) { bd = dw; bi = iw; }
-            }
-            const int ni = bi;
-            int count = S.count;
+            int ni = bi;
+            int count = S.count;     // (warp 3 re-reads both after B2 when it skipped the scan)
             int t_near = 0, t_par = -1, t_rwok = 0, t_rwap = 0;
             double2 from = make_double2(0.0, 0.0);
             CTA_CLK(2);
@@ -383,8 +419,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             } else {
                                 L.m = S.cull_m[cb];
                             }
-                            const int vl = edge_verdict_fast(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
-                                                             lane, 32, ~0ull).v;
+                            // (the <true> instantiation: the body the candidate passes run, already in the instruction cache)
+                            const int vl = edge_verdict_fast<true>(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
+                                                                   lane, 32, ~0ull).v;
                             const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                             v = blocked ? 0 : (unsure ? -1 : 1);
                             if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
@@ -406,21 +443,30 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 }
                 if (lane == 0) {
                     S.nx = nx; S.ny = ny; S.accept = accept ? 1 : 0; S.near_valid = near_valid ? 1 : 0; S.t_status = t_status;
+                    S.ni = ni;
                     if (accept && n < p.node_cap) s_link[n] = make_ushort2(NONE16, NONE16);  // children arrive through rewire
                 }
             } else if (warp == 1) {
-                // ---- the circles around the NEXT sample (consumed by iteration it + 1 when its node lands on the sample) ----
-                if (it + 1 < p.max_iter && inside_play(p, smp_next.x, smp_next.y)) {
-                    const ObsList Ln = cull_obstacles_grid(grid, obs, n_obs, smp_next.x, smp_next.y, reach, S.cull[cb ^ 1][0],
-                                                           S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
-                    if (lane == 0) { S.cull_m[cb ^ 1] = Ln.m; S.cull_glob[cb ^ 1] = Ln.stride == 4 ? 1 : 0; }
+                // ---- the NEXT sample and the circles around it (consumed by iteration it + 1 when its node lands on the sample) ----
+                if (it + 1 < p.max_iter) {
+                    const Sample sn = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
+                    if (lane == 0) { S.smp[cb ^ 1][0] = sn.x; S.smp[cb ^ 1][1] = sn.y; }
+                    if (inside_play(p, sn.x, sn.y)) {
+                        const ObsList Ln = cull_obstacles_grid(grid, obs, n_obs, sn.x, sn.y, reach, S.cull[cb ^ 1][0],
+                                                               S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
+                        if (lane == 0) { S.cull_m[cb ^ 1] = Ln.m; S.cull_glob[cb ^ 1] = Ln.stride == 4 ? 1 : 0; }
+                    }
                 }
-            } else if (!RRT_ONLY) {
-                if (count <= near_cap) cta_rank_near(S, count, tid - 64, CTA_T - 64);
+            } else if (!RRT_ONLY && !(defer && warp == CTA_W - 1)) {
+                if (count <= near_cap) cta_rank_near(S, count, tid - 64, defer ? 32 : 64);
             }
             CTA_CLK(3);
             __syncthreads();   // ---- B2
             CTA_CLK(4); CTA_CLK(5); CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
+            if (defer) {
+                ni = S.ni; count = S.count;
+                if (tid == CTA_T - 32) S.def_root = -1;   // (every thread has read it; the apply phase may set the next one)
+            }
             bool accept = S.accept != 0;
             const double nx = S.nx, ny = S.ny;
             int t_status = S.t_status;
@@ -469,6 +515,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     int bk = BIG;
                     // this lane's circles near the segment (its first-round candidate) - (new node), for the reverse edge
                     unsigned long long seg_near = ~0ull;
+#pragma unroll 1
                     for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
                         const int k = k0 + tid / CTA_G;
                         const bool valid = k < count;
@@ -479,7 +526,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             const double2 a = s_xy[i];
                             ci = cost[i];
                             dk = crm_hypot(nx - a.x, ny - a.y);   // what steer's calc_distance_and_angle returns
-                            const EdgeVerdict ev = edge_verdict_fast(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, ~0ull);
+                            const EdgeVerdict ev = edge_verdict_fast<true>(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, ~0ull);
                             const int vv = ev.v;
                             if (k0 == 0) seg_near = vv == 1 ? ev.near : ~0ull;
                             blocked = vv == 0;                    // (the new node is inside the play area)
@@ -521,7 +568,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     __syncthreads();   // ---- B3
                     CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
                     bc = S.red_d[0]; bk = S.red_i[0]; bex = S.red_ex[0]; bey = S.red_ey[0];
-#pragma unroll
+#pragma unroll 1
                     for (int w = 1; w < CTA_W; w++) {
                         const double dw = S.red_d[w];
                         const int kw = S.red_i[w];
@@ -537,6 +584,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         // steer + collision of an entry that fails the test now is dead work.  With a trace every edge is
                         // evaluated (the trace counts collision-free rewire edges).  Flags: 0 = not applicable, 1 = free and
                         // ends on the node, 2 = free but the exact steer stops short of it (the node would MOVE). ----
+#pragma unroll 1
                         for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
                             const int k = k0 + tid / CTA_G;
                             const bool valid = k < count;
@@ -554,7 +602,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                 if (want && only == 0ull) {
                                     blocked = !inside_play(p, a.x, a.y);
                                 } else if (want) {
-                                    const int vv = edge_verdict_fast(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, only).v;
+                                    const int vv = edge_verdict_fast<true>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, only).v;
                                     if (vv < 0) {
                                         Steer st = steer(cx, cy, a.x, a.y, INF, res);
                                         blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
@@ -578,6 +626,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             // ---- rewire, ordered apply (rrt_04:1361-1371) + propagate_cost_to_leaves ----
                             bool dirty = false;      // a propagate ran: node costs must be re-read
                             int fallback_from = -1;  // >= 0: a node moved; redo entries from here serially
+#pragma unroll 1
                             for (int b0 = 0; b0 < count && fallback_from < 0; b0 += 32) {
                                 const int k = b0 + lane;
                                 int i = -1, fl = 0;
@@ -619,7 +668,13 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                         }
                                         __syncwarp();
                                         t_rwap++;
-                                        cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
+                                        if (can_defer && !moved && m == 0 && b0 + 32 >= count) {
+                                            // the last entry that can apply: nothing of this iteration reads a cost any more, so
+                                            // its propagate runs on warp 3 during the next iteration's scan and first edge
+                                            if (lane == 0) { S.def_root = ii; S.def_cost = ec; }
+                                        } else {
+                                            cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
+                                        }
                                         __syncwarp();
                                         dirty = true;
                                         if (moved) {
@@ -702,6 +757,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             if (done) { it++; break; }
         }
         status |= S.status_or;
+        if (S.def_root >= 0) {   // (uniform) the last iteration left a propagate pending
+            if (warp == CTA_W - 1) cta_propagate(S.def_root, S.def_cost, false, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
+            __syncthreads();
+        }
         if (!done && !RRT_ONLY && warp == 0) {
             bool ovf = false;
             ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[0][0], S.cull[0][1], S.cull[0][2], lane);

@@ -133,6 +133,8 @@ def lib():
                             "rrtk has no CPU fallback")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
+            if "RRTK_LIB" in os.environ and not hasattr(handle, name):
+                continue                      # an older tuning build selected through RRTK_LIB (A/B timing only)
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
