@@ -662,8 +662,9 @@ def sharded_curves(torch, dist, rrtk, W, dev, rank, world, iters, n_obs, barrier
                                    st[a:b_], device=dev, timing=tm)
                 kms.append(tm["kernel_ms"])
             kms = sorted(kms[1:])
-            h = np.array([(r["n"] << 40) ^ ((r["goal_index"] + 1) << 20) ^
-                          (int(np.float64(r["cost"][r["goal_index"]]).view(np.int64)) * 1000003 if r["goal_index"] >= 0 else 0)
+            m63 = (1 << 63) - 1       # (Python ints do not wrap: keep the hash inside int64)
+            h = np.array([((r["n"] << 40) ^ ((r["goal_index"] + 1) << 20) ^
+                           (int(np.float64(r["cost"][r["goal_index"]]).view(np.int64)) * 1000003 if r["goal_index"] >= 0 else 0)) & m63
                           for r in res], dtype=np.int64)
             return kms[len(kms) // 2], kms, torch.from_numpy(h).to(dev), int(sum(r["goal_index"] >= 0 for r in res))
         lo, hi = rrtk.shard_range(total, rank, world)

@@ -119,7 +119,8 @@ typedef struct rrtk_rrtstar_params {
     double near_r_max;
     /* how a query is executed (results are bit-identical): RRTK_EXEC_WARP = one warp per query, tree in L2;
      * RRTK_EXEC_CTA = one CTA of 4 warps per query, tree (positions, children lists, parents) in shared memory --
-     * needs node_cap <= 65535 and 22 B / node + the near list in <= 227 KB; RRTK_EXEC_AUTO picks CTA when it fits. */
+     * needs node_cap <= 65535 and 22 B / node + the near list in <= 227 KB; RRTK_EXEC_AUTO picks CTA when it fits
+     * and the whole batch is resident at once (n_queries <= SMs x CTAs per SM: a latency-bound launch), WARP otherwise. */
     int32_t exec_mode;
     /* global index of this launch's query 0: the in-kernel samplers key their counter-based RNG by (seed, query_base + q,
      * iteration), so a shard of a larger batch draws exactly what the unsharded batch draws for the same queries */

@@ -44,7 +44,7 @@ dubins_steer_kernel(int n_req, double kappa, double step, const double *__restri
         double cost = CUDART_INF;
         int bi = 0x7fffffff;
         const DubTrig trig = dubins_trig(alpha, beta);
-        if (lane < 6 && dubins_word(lane, alpha, beta, d, trig, w)) {
+        if (lane < 6 && dubins_word<true>(lane, alpha, beta, d, trig, w)) {
             cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
             bi = lane;
         }

@@ -48,52 +48,81 @@ static __device__ __forceinline__ DubTrig dubins_trig(double alpha, double beta)
     t.cab = crm_cos(alpha - beta);
     return t;
 }
-static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, const DubTrig &t, double *w) {
+// CR = true: the reference's word (correctly rounded atan2 / acos).  CR = false: the same formulas with libdevice's
+// atan2 / acos (<= 2 ulp), used only to rule words out (dubins_best_word); *wrap is set when a mod2pi argument lands
+// within 1e-9 of a multiple of 2 pi, where the approximate value says nothing about the exact one.  Feasibility (p2 < 0,
+// |tmp| > 1) is decided on values both variants compute identically.
+template <bool CR>
+static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, const DubTrig &t, double *w,
+                                                bool *wrap = nullptr) {
     const double sa = t.sa, ca = t.ca, sb = t.sb, cb = t.cb, cab = t.cab;
     const double d2 = d * d;
     double p2, tmp, d1;
+    auto at2 = [](double y, double x) { return CR ? crm_atan2(y, x) : atan2(y, x); };
+    auto m2p = [&](double x) {
+        const double v = mod2pi(x);
+        if (!CR && (v < 1e-9 || v > D_TWO_PI - 1e-9)) *wrap = true;
+        return v;
+    };
     switch (k) {
         case 0:
             p2 = 2 + d2 - (2 * cab) + (2 * d * (sa - sb));
             if (p2 < 0) return false;
-            tmp = crm_atan2((cb - ca), d + sa - sb);
-            w[0] = mod2pi(-alpha + tmp); w[1] = sqrt(p2); w[2] = mod2pi(beta - tmp);
+            tmp = at2((cb - ca), d + sa - sb);
+            w[0] = m2p(-alpha + tmp); w[1] = sqrt(p2); w[2] = m2p(beta - tmp);
             return true;
         case 1:
             p2 = 2 + d2 - (2 * cab) + (2 * d * (sb - sa));
             if (p2 < 0) return false;
-            tmp = crm_atan2((ca - cb), d - sa + sb);
-            w[0] = mod2pi(alpha - tmp); w[1] = sqrt(p2); w[2] = mod2pi(-beta + tmp);
+            tmp = at2((ca - cb), d - sa + sb);
+            w[0] = m2p(alpha - tmp); w[1] = sqrt(p2); w[2] = m2p(-beta + tmp);
             return true;
         case 2:
             p2 = -2 + d2 + (2 * cab) + (2 * d * (sa + sb));
             if (p2 < 0) return false;
             d1 = sqrt(p2);
-            tmp = crm_atan2((-ca - cb), (d + sa + sb)) - crm_atan2(-2.0, d1);
-            w[0] = mod2pi(-alpha + tmp); w[1] = d1; w[2] = mod2pi(-mod2pi(beta) + tmp);
+            tmp = at2((-ca - cb), (d + sa + sb)) - at2(-2.0, d1);
+            w[0] = m2p(-alpha + tmp); w[1] = d1; w[2] = m2p(-mod2pi(beta) + tmp);
             return true;
         case 3:
             p2 = d2 - 2 + (2 * cab) - (2 * d * (sa + sb));
             if (p2 < 0) return false;
             d1 = sqrt(p2);
-            tmp = crm_atan2((ca + cb), (d - sa - sb)) - crm_atan2(2.0, d1);
-            w[0] = mod2pi(alpha - tmp); w[1] = d1; w[2] = mod2pi(beta - tmp);
+            tmp = at2((ca + cb), (d - sa - sb)) - at2(2.0, d1);
+            w[0] = m2p(alpha - tmp); w[1] = d1; w[2] = m2p(beta - tmp);
             return true;
         case 4:
             tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
             if (fabs(tmp) > 1.0) return false;
-            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
-            w[0] = mod2pi(alpha - crm_atan2(ca - cb, d - sa + sb) + w[1] / 2.0);
-            w[2] = mod2pi(alpha - beta - w[0] + w[1]);
+            w[1] = m2p(2 * D_PI - (CR ? crm_acos(tmp) : acos(tmp)));
+            w[0] = m2p(alpha - at2(ca - cb, d - sa + sb) + w[1] / 2.0);
+            w[2] = m2p(alpha - beta - w[0] + w[1]);
             return true;
         default:
             tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (-sa + sb)) / 8.0;
             if (fabs(tmp) > 1.0) return false;
-            w[1] = mod2pi(2 * D_PI - crm_acos(tmp));
-            w[0] = mod2pi(-alpha - crm_atan2(ca - cb, d + sa - sb) + w[1] / 2.0);
-            w[2] = mod2pi(mod2pi(beta) - alpha - w[0] + mod2pi(w[1]));
+            w[1] = m2p(2 * D_PI - (CR ? crm_acos(tmp) : acos(tmp)));
+            w[0] = m2p(-alpha - at2(ca - cb, d + sa - sb) + w[1] / 2.0);
+            w[2] = m2p(mod2pi(beta) - alpha - w[0] + m2p(w[1]));
             return true;
     }
+}
+
+// The reference's choice among the six words (first minimum of the summed lengths in _PATH_TYPE_MAP order, rrt_05:1088-1094)
+// by ONE lane.  (Ruling words out with approximate lengths first -- dubins_word<false> -- was tried: the lanes of a warp
+// then disagree on which words to evaluate exactly and the warp runs all six anyway, plus the approximations: 63 -> 87 ms
+// at config 4.)  Returns the word index or -1, its three lengths in len.
+static __device__ __forceinline__ int dubins_best_word(double alpha, double beta, double d, const DubTrig &trig, double *len) {
+    double best = CUDART_INF;
+    int bi = -1;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        double w[3];
+        if (!dubins_word<true>(k, alpha, beta, d, trig, w)) continue;
+        const double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+        if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
+    }
+    return bi;
 }
 
 // segment type of word `mode` at position k: 0 = L, 1 = S, 2 = R
@@ -156,6 +185,43 @@ static __device__ __forceinline__ bool prefilter_ok(double s_x, double s_y, doub
     return fabs(s_x) < 1e4 && fabs(s_y) < 1e4 && fabs(g_x) < 1e4 && fabs(g_y) < 1e4 && kappa > 1e-3;
 }
 
+// ---- segment-level cull (the planners' edge evaluators only) ----
+// Every sampled point of a course segment lies on the segment's curve: a straight piece from its origin to its end point,
+// or an arc of radius 1 / kappa around c = origin + (-+ sin, +- cos)(origin yaw) / kappa.  A circle (centre o, radius R)
+// whose distance to that CURVE exceeds R + 1e-7 cannot contain any of the points, so the interior points of a segment
+// that no circle comes near are never evaluated (their count is not needed: the planners only ask for the verdict and
+// the end pose, which is always computed exactly).  All in the course's local frame (start pose = origin, yaw 0); the
+// circle centres are brought there with the same rotation the goal is (rounding ~1e-12 for coordinates < 1e4, far
+// inside the 1e-7 margin).  Conservative by construction: any doubt (an angular position within tolerance of the arc's
+// ends) counts as "near".
+//   type 0 = L, 1 = S, 2 = R;  (ox, oy) origin, (so, co) = sin / cos(origin yaw), (ex, ey) the segment's end point,
+//   length = the word length (arc angle in radians for L / R);  (px, py) = the circle centre in the local frame
+static __device__ __forceinline__ bool circle_near_segment(int type, double kappa, double ox, double oy, double so, double co,
+                                                           double ex, double ey, double length, double px, double py,
+                                                           double R) {
+    const double m = R + 1e-7, m2 = m * m;
+    if (type == 1) {
+        const double wx = ex - ox, wy = ey - oy, l2 = wx * wx + wy * wy;
+        const double ax = px - ox, ay = py - oy;
+        double t = l2 > 0.0 ? (ax * wx + ay * wy) / l2 : 0.0;
+        t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+        const double qx = ax - t * wx, qy = ay - t * wy;
+        return qx * qx + qy * qy <= m2;
+    }
+    const double rho = 1.0 / kappa, sgn = type == 0 ? 1.0 : -1.0;
+    const double cx = ox - sgn * rho * so, cy = oy + sgn * rho * co;
+    const double vx = px - cx, vy = py - cy;
+    const double dc = sqrt(vx * vx + vy * vy);
+    if (fabs(dc - rho) > m) return false;                      // clear of the whole circle the arc lies on
+    const double ux = ox - cx, uy = oy - cy, wx = ex - cx, wy = ey - cy;
+    const double c1 = sgn * (ux * vy - uy * vx), c2 = sgn * (vx * wy - vy * wx);   // > 0: o is past the start / before the end
+    const double tol = 1e-9 * (rho * dc + 1.0);
+    const bool in_span = fabs(length) < D_PI ? (c1 >= -tol && c2 >= -tol) : !(c1 < -tol && c2 < -tol);
+    if (in_span) return true;
+    const double ax = px - ox, ay = py - oy, bx = px - ex, by = py - ey;           // nearest arc point = one of its ends
+    return ax * ax + ay * ay <= m2 || bx * bx + by * by <= m2;
+}
+
 struct DubEdge {
     double ex, ey, eyaw;  // last course point (the node pose steer returns, rrt_05:1469-1471); free edges only
     int npts;             // len(px): steer returns None when <= 1 (for a blocked edge only "<= 1 or not" is kept)
@@ -180,18 +246,11 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
     const double theta = mod2pi(crm_atan2(lgy, lgx));
     const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
     const DubTrig trig = dubins_trig(alpha, beta);
-    double len[3] = {0.0, 0.0, 0.0}, best = CUDART_INF;
-    int bi = -1;
-#pragma unroll 1
-    for (int k = 0; k < 6; k++) {
-        double w[3];
-        if (!dubins_word(k, alpha, beta, d, trig, w)) continue;
-        double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
-        if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
-    }
+    double len[3] = {0.0, 0.0, 0.0};
+    const int bi = dubins_best_word(alpha, beta, d, trig, len);
     if (bi < 0) return e;
-    double c2, s2;
-    rot2d(-s_yaw, &c2, &s2);
+    // rot_mat_2d(-s_yaw): the correctly rounded sin / cos are odd / even bit for bit, so c2 = c and s2 = -s exactly
+    const double c2 = c, s2 = -s;
     const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
     bool hit = false;
     double lx = 0.0, ly = 0.0, lyaw = 0.0;
@@ -213,9 +272,19 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
         if (length == 0.0) continue;
         const int type = seg_type(bi, k);
         const double ox = lx, oy = ly, oyaw = lyaw;
-        double so, co, sm, cm;
-        sincos_cr(oyaw, &so, &co);
-        sincos_cr(-oyaw, &sm, &cm);
+        double so = 0.0, co = 1.0;                    // sin / cos(0) of the first segment's origin
+        if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
+        const double sm = -so, cm = co;               // sin / cos(-oyaw), exactly (see c2, s2)
+        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);   // the segment's end point: always exact
+        emit(lx, ly);
+        if (hit) break;
+        bool near = !filt;
+        for (int o = 0; o < n_obs && !near; o++) {
+            const double4 ob = obs[o];
+            const double ux = ob.x - s_x, uy = ob.y - s_y;
+            near = circle_near_segment(type, kappa, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
+        }
+        if (!near) { np++; continue; }          // (np only has to tell "more than one point")
         double cur = step;
 #pragma unroll 1
         while (fabs(cur + step) <= fabs(length)) {
@@ -236,9 +305,6 @@ static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, 
             if (hit) break;
             cur += step;
         }
-        if (hit) break;
-        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
-        emit(lx, ly);
     }
     if (hit) {
         // blocked: the callers only ask whether steer returned a node at all (len(px) > 1, i.e. some segment is non-zero);
@@ -278,7 +344,7 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     double cost = CUDART_INF;
     int bi = 0x7fffffff;
     const DubTrig trig = dubins_trig(alpha, beta);
-    if (lane < 6 && dubins_word(lane, alpha, beta, d, trig, w)) {
+    if (lane < 6 && dubins_word<true>(lane, alpha, beta, d, trig, w)) {
         cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
         bi = lane;
     }
@@ -291,8 +357,7 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
 #pragma unroll
         for (int k = 0; k < 3; k++) lengths_out[k] = len[k] / kappa;
     }
-    double c2, s2;
-    rot2d(-s_yaw, &c2, &s2);
+    const double c2 = c, s2 = -s;   // rot_mat_2d(-s_yaw): sin / cos correctly rounded are odd / even bit for bit
     const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
     bool hit = false;
     auto test = [&](double px, double py) {
@@ -313,37 +378,47 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
         if (length == 0.0) continue;
         const int type = seg_type(bi, k);
         const double ox = lx, oy = ly, oyaw = lyaw;
-        double so, co, sm, cm;
-        sincos_cr(oyaw, &so, &co);
-        sincos_cr(-oyaw, &sm, &cm);
-        int cnt = 0;
-        {
-            double cur = step;
-            while (fabs(cur + step) <= fabs(length)) { cnt++; cur += step; }
-        }
-        double cur = step;
-        for (int t = 0; t < lane; t++) cur += step;
-#pragma unroll 1
-        for (int j = lane; j < cnt; j += 32) {
-            int v = -1;
-            if (filt && type != 1) {
-                double x, y;
-                arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
-                v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
-            }
-            if (v < 0) {
-                double x, y, yaw;
-                interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
-                test(x, y);
-            } else if (v == 1) {
-                hit = true;
-            }
-#pragma unroll 1
-            for (int t = 0; t < 32; t++) cur += step;
-        }
-        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+        double so = 0.0, co = 1.0;                    // sin / cos(0) of the first segment's origin
+        if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
+        const double sm = -so, cm = co;               // sin / cos(-oyaw), exactly (see c2, s2)
+        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);   // the segment's end point: always exact
         if (lane == 0) test(lx, ly);
-        np += cnt + 1;
+        // segment-level cull (circle_near_segment): the lanes split the circles
+        bool near = !filt;
+        for (int o = lane; o < n_obs && !near; o += 32) {
+            const double4 ob = obs[o];
+            const double ux = ob.x - s_x, uy = ob.y - s_y;
+            near = circle_near_segment(type, kappa, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
+        }
+        if (__any_sync(FULL, near)) {
+            int cnt = 0;
+            {
+                double cur = step;
+                while (fabs(cur + step) <= fabs(length)) { cnt++; cur += step; }
+            }
+            double cur = step;
+            for (int t = 0; t < lane; t++) cur += step;
+#pragma unroll 1
+            for (int j = lane; j < cnt; j += 32) {
+                int v = -1;
+                if (filt && type != 1) {
+                    double x, y;
+                    arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
+                    v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
+                }
+                if (v < 0) {
+                    double x, y, yaw;
+                    interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
+                    test(x, y);
+                } else if (v == 1) {
+                    hit = true;
+                }
+#pragma unroll 1
+                for (int t = 0; t < 32; t++) cur += step;
+            }
+            np += cnt;
+        }
+        np += 1;                              // (np only has to tell "more than one point" when a segment was culled)
         if (__any_sync(FULL, hit)) {   // blocked: see dubins_edge_lane
             e.npts = 2;
             return e;

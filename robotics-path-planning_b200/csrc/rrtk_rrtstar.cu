@@ -569,6 +569,7 @@ extern "C" __global__ void crmath_probe_kernel(int kind, int64_t n, const double
 namespace rrtk {
 
 bool rrtstar_cta_fits(const rrtk_rrtstar_params &p);
+int rrtstar_cta_resident(const rrtk_rrtstar_params &p);   // CTAs (= queries) resident on the device at once
 int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
                        const int32_t *n_obs, const double *near_r2, const double *sample_stream,
                        const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
@@ -580,8 +581,11 @@ int launch_rrtstar(const rrtk_rrtstar_params &p, const double *start_goal, const
                    const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
                    int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index, int32_t *status,
                    int32_t *trace, int32_t *workspace, unsigned int *counter, cudaStream_t s) {
-    // one CTA per query with the tree in shared memory (rrtk_rrtstar_cta.cu) whenever it fits; one warp per query otherwise
-    if (p.exec_mode == RRTK_EXEC_CTA || (p.exec_mode == RRTK_EXEC_AUTO && rrtstar_cta_fits(p)))
+    // one CTA per query with the tree in shared memory (rrtk_rrtstar_cta.cu) when it fits AND the batch is small enough for
+    // every query to be resident at once (then the launch time is one query's serial chain, which the CTA shortens);
+    // larger batches are throughput-bound and one warp per query packs the SMs better (measured on B200, config 2:
+    // 128 queries 17.9 vs 24.5 ms, 512 queries 25.0 vs 25.9 ms, 1024 queries 48.2 vs 32.2 ms, 4096 queries 175 vs 85 ms)
+    if (p.exec_mode == RRTK_EXEC_CTA || (p.exec_mode == RRTK_EXEC_AUTO && rrtstar_cta_fits(p) && p.n_queries <= rrtstar_cta_resident(p)))
         return launch_rrtstar_cta(p, start_goal, obstacles, n_obs, near_r2, sample_stream, sobol_offset, xy, cost, parent,
                                   n_nodes, iters_done, goal_index, status, trace, workspace, counter, s);
     const bool fixed_nc = p.near_cap <= 256;

@@ -789,6 +789,42 @@ static int cta_layout(const rrtk_rrtstar_params &p) {
 }
 bool rrtstar_cta_fits(const rrtk_rrtstar_params &p) { return cta_layout(p) != 0; }
 
+typedef void (*cta_kernel_t)(rrtk_rrtstar_params, const double4 *, const double4 *, const int32_t *, const double *,
+                             const double2 *, const int64_t *, double2 *, double *, int32_t *, int32_t *, int32_t *,
+                             int32_t *, int32_t *, int32_t *, int32_t *, unsigned int *);
+
+static cta_kernel_t cta_pick(const rrtk_rrtstar_params &p, int nc, bool trace) {
+    if (p.rrt_only)
+        return p.resume ? rrtstar_cta_kernel<true, false, true, CTA_NC_SMALL>
+                        : (trace ? rrtstar_cta_kernel<true, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<true, false, false, CTA_NC_SMALL>);
+    if (nc == CTA_NC_SMALL)
+        return p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_SMALL>
+                        : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<false, false, false, CTA_NC_SMALL>);
+    return p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_LARGE>
+                    : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_LARGE> : rrtstar_cta_kernel<false, false, false, CTA_NC_LARGE>);
+}
+
+// persistent grid of the launch = CTAs resident on the device at once (a multiple of the SM count); 0 on error
+static int cta_grid(const rrtk_rrtstar_params &p, int nc, cta_kernel_t kern, size_t smem) {
+    (void)nc;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_T, smem) != cudaSuccess) return 0;
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+int rrtstar_cta_resident(const rrtk_rrtstar_params &p) {
+    const int nc = cta_layout(p);
+    if (!nc) return 0;
+    const size_t smem = nc == CTA_NC_SMALL ? cta_smem_bytes<CTA_NC_SMALL>(p.node_cap) : cta_smem_bytes<CTA_NC_LARGE>(p.node_cap);
+    const int g = cta_grid(p, nc, cta_pick(p, nc, false), smem);
+    cudaGetLastError();
+    return g;
+}
+
 int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, const double *obstacles,
                        const int32_t *n_obs, const double *near_r2, const double *sample_stream,
                        const int64_t *sobol_offset, double *xy, double *cost, int32_t *parent,
@@ -799,31 +835,12 @@ int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, c
         return set_error(RRTK_ERR_INVALID, "exec_mode = CTA needs node_cap <= 65535, near_cap <= 1024 and 22 B / node + the near list "
                                            "in 227 KB of shared memory");
     const size_t smem = nc == CTA_NC_SMALL ? cta_smem_bytes<CTA_NC_SMALL>(p.node_cap) : cta_smem_bytes<CTA_NC_LARGE>(p.node_cap);
-    typedef void (*kernel_t)(rrtk_rrtstar_params, const double4 *, const double4 *, const int32_t *, const double *,
-                             const double2 *, const int64_t *, double2 *, double *, int32_t *, int32_t *, int32_t *,
-                             int32_t *, int32_t *, int32_t *, int32_t *, unsigned int *);
-    kernel_t kern;
-    if (p.rrt_only)
-        kern = p.resume ? rrtstar_cta_kernel<true, false, true, CTA_NC_SMALL>
-                        : (trace ? rrtstar_cta_kernel<true, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<true, false, false, CTA_NC_SMALL>);
-    else if (nc == CTA_NC_SMALL)
-        kern = p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_SMALL>
-                        : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_SMALL> : rrtstar_cta_kernel<false, false, false, CTA_NC_SMALL>);
-    else
-        kern = p.resume ? rrtstar_cta_kernel<false, false, true, CTA_NC_LARGE>
-                        : (trace ? rrtstar_cta_kernel<false, true, false, CTA_NC_LARGE> : rrtstar_cta_kernel<false, false, false, CTA_NC_LARGE>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_cta_kernel)");
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_T, smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)sms * per_sm;  // persistent: a multiple of the SM count
+    const cta_kernel_t kern = cta_pick(p, nc, trace != nullptr);
+    long long grid = cta_grid(p, nc, kern, smem);
+    if (grid < 1) return set_cuda_error(cudaGetLastError(), "cudaFuncSetAttribute / occupancy (rrtstar_cta_kernel)");
     if (grid > p.n_queries) grid = p.n_queries;
     if (grid < 1) grid = 1;
-    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
     kern<<<(unsigned)grid, CTA_T, smem, s>>>(
         p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(obstacles),

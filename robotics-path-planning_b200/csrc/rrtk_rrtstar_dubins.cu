@@ -23,8 +23,9 @@ constexpr int DUB_WARPS_PER_CTA = 4;
 
 __host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap) {
     (void)node_cap;
-    // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | frontier length of propagate_lists
-    size_t b = (size_t)near_cap * (4 + 4 + 8 + 24) + 16;
+    // near_idx int | flags int | nd double (d2, then edge cost) | end pose 3 doubles | node cost snapshot double
+    // | frontier length of propagate_lists
+    size_t b = (size_t)near_cap * (4 + 4 + 8 + 24 + 8) + 16;
     b = (b + 15) & ~(size_t)15;
     return b + ((sizeof(RsWarp) + 15) & ~(size_t)15);   // + the 48 candidate words of a warp-cooperative Reeds-Shepp edge
 }
@@ -113,7 +114,8 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
     unsigned char *base = smem_raw + (size_t)(threadIdx.x >> 5) * dub_warp_smem_bytes(near_cap, p.node_cap);
     double *nd = reinterpret_cast<double *>(base);
     double *s_end = nd + near_cap;  // [near_cap][3]
-    int *near_idx = reinterpret_cast<int *>(s_end + 3 * near_cap);
+    double *s_c = s_end + 3 * near_cap;
+    int *near_idx = reinterpret_cast<int *>(s_c + near_cap);
     int *flags = near_idx + near_cap;
     int *qtail = flags + near_cap;
     RsWarp &rsw = *reinterpret_cast<RsWarp *>(base + dub_warp_smem_bytes(near_cap, p.node_cap) - ((sizeof(RsWarp) + 15) & ~(size_t)15));
@@ -245,25 +247,48 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     n++;
                     truthy = true;
                     __syncwarp();
-                    // rewire (rrt_05:1741-1775), phase A: every entry's edge in parallel
+                    // rewire (rrt_05:1741-1775), phase A: the entries' edges in parallel.  With Euclidean costs (STEER 0 / 1) the
+                    // cost an entry would get does not depend on its edge, and planning an edge has no side effect: an entry
+                    // whose node does not cost more than that NOW is not planned (flag 8); phase B looks at it again with the
+                    // node's cost at its turn (a re-parented node moves, so costs can go either way).
 #pragma unroll 1
                     for (int k = lane; k < count; k += 32) {
                         const int i = near_idx[k];
                         const double2 a = xy[i];
-                        const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
-                        flags[k] = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
-                        nd[k] = mc + (STEER == 2 ? e.lsum : crm_hypot(a.x - cx, a.y - cy));
-                        s_end[3 * k] = e.ex; s_end[3 * k + 1] = e.ey; s_end[3 * k + 2] = e.eyaw;
+                        const double ci = cost[i];
+                        double ec = STEER == 2 ? 0.0 : mc + crm_hypot(a.x - cx, a.y - cy);
+                        int fl = 8;
+                        double ex = 0.0, ey = 0.0, eyw = 0.0;
+                        if (STEER == 2 || ci > ec) {
+                            const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
+                            fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
+                            if (STEER == 2) ec = mc + e.lsum;
+                            ex = e.ex; ey = e.ey; eyw = e.eyaw;
+                        }
+                        flags[k] = fl;
+                        nd[k] = ec;
+                        s_c[k] = ci;
+                        s_end[3 * k] = ex; s_end[3 * k + 1] = ey; s_end[3 * k + 2] = eyw;
                     }
                     __syncwarp();
-                    // phase B: apply in list order; costs are re-read (propagation can move them either way)
-                    for (int k = 0; k < count; k++) {
+                    // phase B: apply in list order.  s_c is the current cost of every entry's node (refreshed after each
+                    // re-parenting), so the lanes can find the next entry that can act without walking the list one by one.
+                    for (int k0 = 0; k0 < count;) {
+                        bool need = false;
+                        if (k0 + lane < count) {
+                            const int fl = flags[k0 + lane];
+                            need = (fl & 4) || (((fl & 3) == 3 || (fl & 8)) && s_c[k0 + lane] > nd[k0 + lane]);
+                        }
+                        const unsigned nm = __ballot_sync(FULL, need);
+                        if (!nm) { k0 += 32; continue; }
+                        const int k = k0 + __ffs(nm) - 1;
+                        k0 = k + 1;
                         const int i = near_idx[k];
                         int fl = flags[k];
                         double ecost = nd[k], ex = s_end[3 * k], ey = s_end[3 * k + 1], eyw = s_end[3 * k + 2];
                         const double2 a = xy[i];
                         const double ayaw = yaw[i];
-                        if (fl & 4) {  // node i was re-parented (moved) earlier in this call: redo its edge
+                        if (fl & (4 | 8)) {  // node i was re-parented (moved) earlier in this call, or its edge was not planned yet
                             const PEdge e = plan_edge_warp<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs, lane, rsw);
                             fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
                             ecost = mc + (STEER == 2 ? e.lsum : crm_hypot(a.x - cx, a.y - cy));
@@ -285,6 +310,9 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                             __syncwarp();
                             if (STEER == 2) propagate_lists_rs(i, xy, yaw, cost, links, qtail, lane, kappa, step);
                             else propagate_lists(i, xy, cost, links, qtail, lane);
+                            __syncwarp();
+                            for (int k2 = k + 1 + lane; k2 < count; k2 += 32) s_c[k2] = cost[near_idx[k2]];
+                            __syncwarp();
                         }
                     }
                     if (STEER >= 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
