@@ -1,0 +1,69 @@
+/* crmath_fastcheck.c -- TEST INFRASTRUCTURE.  The first-phase (Ziv) evaluations of crmath.h (-DCRM_FAST, what the GPU
+ * build uses) against the double-double path they stand in for: whenever the fast form accepts, its result must be the
+ * double-double path's, bit for bit.  Prints "<name> n accepted mismatches" per function; exit code 1 on any mismatch.
+ *   gcc -O2 -ffp-contract=off -march=native -DCRM_FAST crmath_fastcheck.c -lm -o _build/crmath_fastcheck && ./crmath_fastcheck [n] */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "../robotics-path-planning_b200/csrc/crmath.h"
+
+static uint64_t st = 0x9E3779B97F4A7C15ull;
+static uint64_t rnd(void) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; }
+static double u01(void) { return (double)(rnd() >> 11) * (1.0 / 9007199254740992.0); }
+static double nudge(double x, int k) { int64_t b; memcpy(&b, &x, 8); b += k; memcpy(&x, &b, 8); return x; }
+
+static long n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at;
+
+static void check_sincos(double x) {
+    double s, c;
+    crm_dd sd, cd;
+    if (!(fabs(x) < 1.6e6)) return;          /* crmath.h's domain: finite, |x| < 2^20 pi/2 */
+    n_sc++;
+    if (!crm_sincos_fast(x, &s, &c)) return;
+    ok_sc++;
+    crm_sincos_dd(x, &sd, &cd);
+    if (s != sd.hi || c != cd.hi) {
+        if (bad_sc < 10) fprintf(stderr, "sincos mismatch x=%a: fast (%a, %a) dd (%a, %a)\n", x, s, c, sd.hi, cd.hi);
+        bad_sc++;
+    }
+}
+static void check_atan2(double y, double x) {
+    double r;
+    if (!(fabs(x) < 1e300 && fabs(y) < 1e300)) return;
+    n_at++;
+    if (y == 0.0 || !crm_atan2_fast(y, x, &r)) return;
+    ok_at++;
+    double d = crm_atan2_dd(y, x).hi;
+    if (r != d) {
+        if (bad_at < 10) fprintf(stderr, "atan2 mismatch y=%a x=%a: fast %a dd %a\n", y, x, r, d);
+        bad_at++;
+    }
+}
+
+int main(int argc, char **argv) {
+    long n = argc > 1 ? atol(argv[1]) : 2000000;
+    for (long i = 0; i < n; i++) {
+        /* angles of the planners (yaws, word lengths, their sums), wide range, tiny values */
+        check_sincos((u01() * 2.0 - 1.0) * 6.5);
+        check_sincos((u01() * 2.0 - 1.0) * 40.0);
+        check_sincos((u01() * 2.0 - 1.0) * 1e5);
+        check_sincos(ldexp(u01() * 2.0 - 1.0, -(int)(rnd() % 60)));
+        /* next to multiples of pi/2 and next to the table points i/128 */
+        double k = (double)((long)(rnd() % 4001) - 2000);
+        check_sincos(nudge(k * 1.5707963267948966, (int)(rnd() % 2001) - 1000));
+        check_sincos(k * 1.5707963267948966 + ldexp(u01() - 0.5, -(int)(rnd() % 50)));
+        check_sincos(nudge((double)(rnd() % 104) * 0.0078125 + 1.5707963267948966 * (double)(rnd() % 8), (int)(rnd() % 65) - 32));
+        check_sincos(nudge((double)(rnd() % 830) * 0.00390625, (int)(rnd() % 65) - 32));
+        /* atan2: planner-sized coordinates, ratios next to table points, extreme ratios, all quadrants */
+        double sx = (rnd() & 1) ? 1.0 : -1.0, sy = (rnd() & 2) ? 1.0 : -1.0;
+        check_atan2(sy * u01() * 30.0, sx * u01() * 30.0);
+        check_atan2(sy * u01(), sx * ldexp(u01(), (int)(rnd() % 80) - 40));
+        double m = 0.5 + u01();
+        check_atan2(sy * nudge(m * (double)(rnd() % 129) * 0.0078125, (int)(rnd() % 65) - 32), sx * m);
+        check_atan2(sy * m, sx * nudge(m * (double)(rnd() % 129) * 0.0078125, (int)(rnd() % 65) - 32));
+        check_atan2(sy * nudge(m, (int)(rnd() % 9) - 4), sx * m);
+        check_atan2(sy * 2.0, sx * u01() * 40.0);
+    }
+    printf("sincos %ld %ld %ld\natan2 %ld %ld %ld\n", n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at);
+    return (bad_sc || bad_at) ? 1 : 0;
+}

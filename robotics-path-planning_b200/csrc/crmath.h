@@ -217,16 +217,101 @@ CRM_NOINLINE void crm_sincos_dd(double x, crm_dd *s_out, crm_dd *c_out) {
     else { *s_out = crm_neg(cr); *c_out = sr; }
 }
 
+#ifdef CRM_FAST
+/* ---- first phase of Ziv's strategy (GPU builds, -DCRM_FAST) ----
+ * The double-double evaluations above cost ~350 dependent FP64 operations; the planners' steering code (Dubins /
+ * Reeds-Shepp words and course points) is bound by exactly that latency.  These first phases compute the same value as
+ * hi + lo with an error bound E (a few 2^-66, derived below) in ~60 operations and return RN(hi + lo) when hi + (lo - E)
+ * and hi + (lo + E) round to the same double -- then that double IS the correctly rounded result, the one the
+ * double-double path returns.  Otherwise (about 1 call in 100 .. 1000) the caller runs the double-double path.  The CPU
+ * oracle is built without CRM_FAST, so every parity test also checks the bounds; tests/test_crmath.py runs both forms
+ * over 10^7 arguments.
+ * sin / cos: r = x - k pi/2 = (rh, rl) (error < 2^-97), |r| = i/128 + h, h = (h, hl), |h| <= 2^-8:
+ *   sin h = h + sl,  sl = h z ps + hl        z = h^2, ps = -1/6 + z/120 - z^2/5040 + z^3/362880   (|sl| < 2^-26 |h|)
+ *   cos h = 1 + cm,  cm = z pc - h hl        pc = -1/2 + z/24 - z^2/720 + z^3/40320                (|cm| < 2^-17)
+ *   sin(i/128 + h) = S + [C h] + (Sl + S cm + C sl + Cl h),  cos(..) = C - [S h] + (Cl + C cm - S sl - Sl h)
+ * with [.] an exact product (two_prod) and (S, Sl), (C, Cl) the table entry.  Rounding errors: every term inside (..) is
+ * below 2^-16 and is formed by <= 3 roundings, their sum by 4 more: < 8 * 2^-69; dropped terms (Sl cm, hl z / 2, ...)
+ * < 2^-69.  E = 2^-65 absolute for i >= 1 (results >= 2^-8.1), 2^-62 relative for i == 0. */
+CRM_FN int crm_sincos_fast(double x, double *s_out, double *c_out) {
+    double kf = rint(x * CRM_2OPI);
+    double rh, rl;
+    if (kf == 0.0) {
+        rh = x; rl = 0.0;
+    } else {
+        double t = x - kf * CRM_PIO2_1;                       /* exact (Sterbenz) */
+        crm_dd r = crm_two_sum(t, -(kf * CRM_PIO2_2));        /* exact product, error-free sum */
+        double l = r.lo - (kf * CRM_PIO2_3H + kf * CRM_PIO2_3L);
+        r = crm_two_sum(r.hi, l);
+        rh = r.hi; rl = r.lo;
+    }
+    int neg = rh < 0.0;
+    if (neg) { rh = -rh; rl = -rl; }
+    /* x within |k| 2^-50 of k pi/2: the reduction above (error ~|k| 2^-121) is no longer good to 2^-64 RELATIVE to r */
+    if (rh < fabs(kf) * 8.8817841970012523e-16) return 0;
+    int ti = (int)rint(rh * 128.0);
+    double xi = (double)ti * 0.0078125;
+    crm_dd hh = crm_fast_two_sum(rh - xi, rl);                /* rh - xi exact (Sterbenz); |rh - xi| >= |rl| or == 0 */
+    double h = hh.hi, hl = hh.lo;
+    double z = h * h;
+    double ps = fma(fma(fma(2.7557319223985893e-06, z, -1.9841269841269841e-04), z, 8.3333333333333332e-03), z, -1.6666666666666666e-01);
+    double pc = fma(fma(fma(2.4801587301587302e-05, z, -1.3888888888888889e-03), z, 4.1666666666666664e-02), z, -0.5);
+    double sl = h * (z * ps) + hl;
+    double cm = z * pc - h * hl;
+    double shi, slo, chi, clo, es, ec;
+    if (ti == 0) {
+        crm_dd a = crm_fast_two_sum(h, sl);
+        shi = a.hi; slo = a.lo; es = fabs(a.hi) * 2.168404344971009e-19;   /* 2^-62 relative */
+        a = crm_fast_two_sum(1.0, cm);
+        chi = a.hi; clo = a.lo; ec = 2.710505431213761e-20;                /* 2^-65 */
+    } else {
+        double S = crm_sincos_tab[ti][0], Sl = crm_sincos_tab[ti][1], C = crm_sincos_tab[ti][2], Cl = crm_sincos_tab[ti][3];
+        crm_dd p = crm_two_prod(C, h);
+        double rest = p.lo + (Sl + (S * cm + (C * sl + Cl * h)));
+        crm_dd a = crm_fast_two_sum(S, p.hi);                 /* S >= 2^-7.1 > |C h| */
+        a = crm_fast_two_sum(a.hi, a.lo + rest);
+        shi = a.hi; slo = a.lo;
+        p = crm_two_prod(-S, h);
+        rest = p.lo + (Cl + (C * cm - (S * sl + Sl * h)));
+        a = crm_fast_two_sum(C, p.hi);
+        a = crm_fast_two_sum(a.hi, a.lo + rest);
+        chi = a.hi; clo = a.lo;
+        es = ec = 2.710505431213761e-20;                      /* 2^-65 */
+    }
+    double s1 = shi + (slo + es), s2 = shi + (slo - es);
+    double c1 = chi + (clo + ec), c2 = chi + (clo - ec);
+    if (s1 != s2 || c1 != c2) return 0;
+    if (neg) s1 = -s1;
+    int q = ((int)kf) & 3;
+    if (q == 0) { *s_out = s1; *c_out = c1; }
+    else if (q == 1) { *s_out = c1; *c_out = -s1; }
+    else if (q == 2) { *s_out = -s1; *c_out = -c1; }
+    else { *s_out = -c1; *c_out = s1; }
+    return 1;
+}
+#endif
+
+/* RN(sin(x)), RN(cos(x)) together.  Out of line on the GPU (one copy per kernel: the planner kernels are bound by
+ * instruction fetch, and this body was being inlined at ~20 call sites of the steering code) */
+CRM_NOINLINE void crm_sincos(double x, double *s, double *c) {
+#ifdef CRM_FAST
+    if (crm_sincos_fast(x, s, c)) return;
+#endif
+    crm_dd sd, cd;
+    crm_sincos_dd(x, &sd, &cd);
+    *s = sd.hi; *c = cd.hi;
+}
+
 CRM_FN double crm_sin(double x) {
     if (x == 0.0) return x;
-    crm_dd s, c;
-    crm_sincos_dd(x, &s, &c);
-    return s.hi;
+    double s, c;
+    crm_sincos(x, &s, &c);
+    return s;
 }
 CRM_FN double crm_cos(double x) {
-    crm_dd s, c;
-    crm_sincos_dd(x, &s, &c);
-    return c.hi;
+    double s, c;
+    crm_sincos(x, &s, &c);
+    return c;
 }
 
 /* RN(tan(x)): the double-double quotient of crm_sincos_dd (relative error ~2^-100 before the final rounding) */
@@ -330,17 +415,73 @@ CRM_NOINLINE double crm_atan2_sincos(double y, double x, double *s, double *c) {
     return y < 0.0 ? -tabs : tabs;
 }
 
-CRM_FN double crm_atan2(double y, double x) {
+#ifdef CRM_FAST
+/* First phase for atan2 (see crm_sincos_fast): t = mn / mx as t0 + tl (quotient + exact-residual correction, relative
+ * error < 2^-104), table entry atan(i/128), u = (t - i/128) / (1 + t i/128) as u0 + ul (relative error < 2^-100),
+ * atan(u) = u0 + al, al = u0 z pa + ul, pa = -1/3 + z/5 - z^2/7 + z^3/9 (|u| <= 2^-8: |al| < 2^-17 |u0|, error < 2^-68 |u0|;
+ * the dropped u^11/11 < 2^-83 |u0|), then the octant reflections with pi/2, pi as (H, L) pairs, each an error-free sum
+ * of the leading parts plus one rounded sum of the tails (< 2^-105).  E = 2^-62 relative to the result. */
+CRM_FN int crm_atan2_fast(double y, double x, double *out) {
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax;
+    double mn = swap ? ax : ay, mx = swap ? ay : ax;
+    if (!(mx < 1e150 && mn > 1e-150)) return 0;               /* residuals would leave the normal range */
+    double t0 = mn / mx;
+    double tl = fma(-t0, mx, mn) / mx;
+    int i = (int)rint(t0 * 128.0);
+    double u0, ul;
+    if (i == 0) {
+        u0 = t0; ul = tl;
+    } else {
+        double ti = (double)i * 0.0078125;
+        crm_dd n = crm_fast_two_sum(t0 - ti, tl);             /* t0 - ti exact (Sterbenz) */
+        crm_dd p = crm_two_prod(t0, ti);
+        crm_dd d = crm_fast_two_sum(1.0, p.hi);
+        double dl = d.lo + (p.lo + tl * ti);
+        u0 = n.hi / d.hi;
+        ul = ((fma(-u0, d.hi, n.hi) + n.lo) - u0 * dl) / d.hi;
+    }
+    double z = u0 * u0;
+    double pa = fma(fma(fma(1.1111111111111110e-01, z, -1.4285714285714285e-01), z, 0.2), z, -3.3333333333333331e-01);
+    double al = u0 * (z * pa) + ul;
+    crm_dd a;
+    if (i == 0) {
+        a = crm_fast_two_sum(u0, al);
+    } else {
+        a = crm_fast_two_sum(crm_atan_tab[i][0], u0);         /* atan(i/128) >= 2^-7.01 > |u0| */
+        a = crm_fast_two_sum(a.hi, a.lo + (crm_atan_tab[i][1] + al));
+    }
+    if (swap) {
+        crm_dd b = crm_two_sum(CRM_PIO2_H, -a.hi);
+        a = crm_fast_two_sum(b.hi, b.lo + (CRM_PIO2_L - a.lo));
+    }
+    if (x < 0.0) {
+        crm_dd b = crm_two_sum(CRM_PI_H, -a.hi);
+        a = crm_fast_two_sum(b.hi, b.lo + (CRM_PI_L - a.lo));
+    }
+    double e = fabs(a.hi) * 2.168404344971009e-19;            /* 2^-62 relative */
+    double r1 = a.hi + (a.lo + e), r2 = a.hi + (a.lo - e);
+    if (r1 != r2) return 0;
+    *out = y < 0.0 ? -r1 : r1;
+    return 1;
+}
+#endif
+
+CRM_NOINLINE double crm_atan2(double y, double x) {
     if (y == 0.0) {
         int neg = (x < 0.0) || (x == 0.0 && signbit(x));
         return neg ? copysign(CRM_PI_H, y) : y;
     }
+#ifdef CRM_FAST
+    double r_;
+    if (crm_atan2_fast(y, x, &r_)) return r_;
+#endif
     return crm_atan2_dd(y, x).hi;
 }
 
 /* RN(acos(x)) for |x| <= 1 (NaN outside): acos(x) = atan2(sqrt((1 - x)(1 + x)), x) with the square root
  * carried in double-double into the same octant core as crm_atan2. */
-CRM_FN double crm_acos(double x) {
+CRM_NOINLINE double crm_acos(double x) {
     if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
     if (x == 1.0) return 0.0;
     if (x == -1.0) return CRM_PI_H;
@@ -358,7 +499,7 @@ CRM_FN double crm_acos(double x) {
 }
 
 /* RN(asin(x)) for |x| <= 1 (NaN outside): asin(x) = atan2(x, sqrt((1 - x)(1 + x))), same double-double core as acos. */
-CRM_FN double crm_asin(double x) {
+CRM_NOINLINE double crm_asin(double x) {
     if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
     if (x == 0.0) return x;
     if (fabs(x) == 1.0) return copysign(CRM_PIO2_H, x);

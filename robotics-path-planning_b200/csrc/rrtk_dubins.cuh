@@ -19,14 +19,26 @@ static __device__ __forceinline__ double py_mod(double a, double b) {
     else r = copysign(0.0, b);
     return r;
 }
-static __device__ __forceinline__ double mod2pi(double t) { return py_mod(t, D_TWO_PI); }
+// t % (2 * math.pi).  Out of line (fmod expands to a long routine and the steering code takes ~25 of these per edge); for
+// |t| < 4 pi -- every call of the planners -- fmod(t, 2 pi) is t or t -+ 2 pi, and that difference is exact (Sterbenz), so
+// the result is the one fmod gives
+static __device__ __noinline__ double mod2pi(double t) {
+    if (t >= 0.0) {
+        if (t < D_TWO_PI) return t + 0.0;                 // fmod = t; a zero result is +0.0 (-0.0 >= 0.0 lands here too)
+        if (t < 2.0 * D_TWO_PI) return t - D_TWO_PI;      // exact
+    } else if (t > -D_TWO_PI) {
+        return t + D_TWO_PI;                              // fmod = t (negative, non-zero): r += b, one rounding
+    } else if (t > -2.0 * D_TWO_PI) {
+        const double r = t + D_TWO_PI;                    // exact
+        return r != 0.0 ? r + D_TWO_PI : 0.0;
+    }
+    return py_mod(t, D_TWO_PI);
+}
 static __device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
 
 static __device__ __forceinline__ void sincos_cr(double x, double *s, double *c) {
-    crm_dd sd, cd;
-    crm_sincos_dd(x, &sd, &cd);
-    *s = x == 0.0 ? x : sd.hi;
-    *c = cd.hi;
+    crm_sincos(x, s, c);                 // (first-phase evaluation + double-double fallback, crmath.h)
+    if (x == 0.0) *s = x;
 }
 
 // rot_mat_2d(angle) = [[c, -s], [s, c]] via SciPy's quaternion: c = w*w - z*z, s = 2*(z*w)

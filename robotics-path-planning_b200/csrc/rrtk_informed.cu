@@ -145,9 +145,9 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 double a = ab.x, b = ab.y;
                 if (b < a) { double t = a; a = b; b = t; }
                 const double ang = 2 * 3.141592653589793 * a / b;  // 2 * math.pi * a / b
-                crm_dd sd, cd;
-                crm_sincos_dd(ang, &sd, &cd);
-                const double bx = b * cd.hi, by = b * (ang == 0.0 ? ang : sd.hi);
+                double sn, cs;
+                crm_sincos(ang, &sn, &cs);
+                const double bx = b * cs, by = b * (ang == 0.0 ? ang : sn);
                 const double m00 = R.x * r0, m01 = R.y * r1, m10 = R.z * r0, m11 = R.w * r1;
                 rx = fma(m00, bx, m01 * by) + xc;  // numpy (3x3)@(3x1) on the reference platform
                 ry = fma(m10, bx, m11 * by) + yc;

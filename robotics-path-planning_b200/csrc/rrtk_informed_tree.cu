@@ -297,9 +297,9 @@ __device__ __noinline__ void draw_sample(const TreeArgs &A, int it, double c_bes
         double a = ab.x, b = ab.y;
         if (b < a) { double t = a; a = b; b = t; }
         const double ang = 2 * 3.141592653589793 * a / b;
-        crm_dd sd, cd;
-        crm_sincos_dd(ang, &sd, &cd);
-        const double bx = b * cd.hi, by = b * (ang == 0.0 ? ang : sd.hi);
+        double sn, cs;
+        crm_sincos(ang, &sn, &cs);
+        const double bx = b * cs, by = b * (ang == 0.0 ? ang : sn);
         const double m00 = A.p.rot[0] * r0, m01 = A.p.rot[1] * r1, m10 = A.p.rot[2] * r0, m11 = A.p.rot[3] * r1;
         rx = fma(m00, bx, m01 * by) + xc;
         ry = fma(m10, bx, m11 * by) + yc;

@@ -10,11 +10,15 @@
 
 namespace rrtk {
 
-// rs00:130-139: C fmod semantics, then wrap into [-pi, pi]
-static __device__ __forceinline__ double rs_mod2pi(double x) {
-    const double m = copysign(2.0 * D_PI, x);
-    double v = fmod(x, m);
-    if (v == 0.0) v = copysign(0.0, m);
+// rs00:130-139: C fmod semantics, then wrap into [-pi, pi].  Out of line, and without the fmod routine for |x| < 4 pi (every
+// call of the planners): there fmod(x, +-2 pi) is x or x -+ 2 pi, an exact difference (Sterbenz).
+static __device__ __noinline__ double rs_mod2pi(double x) {
+    const double ax = fabs(x);
+    double v;
+    if (ax < D_TWO_PI) v = x;
+    else if (ax < 2.0 * D_TWO_PI) v = x - copysign(D_TWO_PI, x);
+    else v = fmod(x, copysign(D_TWO_PI, x));
+    if (v == 0.0) v = copysign(0.0, x);
     if (v < -D_PI) v += 2.0 * D_PI;
     else if (v > D_PI) v -= 2.0 * D_PI;
     return v;

@@ -41,3 +41,22 @@ def test_special_values(oracle_lib):
     assert O.lib().orc_cr_hypot(0.0, 0.0) == 0.0
     assert O.lib().orc_cr_hypot(3.0, 4.0) == 5.0
     assert O.lib().orc_cr_hypot(1e-320, 1e-320) == math.hypot(1e-320, 1e-320)
+
+
+def test_first_phase_evaluations_equal_the_double_double_path(tmp_path):
+    """crmath.h with -DCRM_FAST (what the GPU build compiles): whenever the first-phase sin / cos / atan2 accepts, its
+    result is the double-double path's bit for bit -- 4.8 M sin/cos and 3.6 M atan2 arguments (planner-sized angles, wide
+    ranges, next to multiples of pi/2 and to the table points); almost all calls are accepted."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "crmath_fastcheck")
+    cc = shutil.which("gcc")
+    assert cc, "gcc is part of the image"
+    subprocess.check_call([cc, "-O2", "-ffp-contract=off", "-mfma", "-DCRM_FAST", os.path.join(root, "oracle", "crmath_fastcheck.c"),
+                           "-lm", "-o", exe])
+    out = subprocess.run([exe, "600000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = {ln.split()[0]: [int(v) for v in ln.split()[1:]] for ln in out.stdout.splitlines()}
+    for name, (n, accepted, bad) in rows.items():
+        assert bad == 0 and n > 3_000_000 and accepted > 0.95 * n, (name, n, accepted, bad)
