@@ -186,6 +186,31 @@ RRTK_API int rrtk_steer_collide_dev(int64_t n_req, const double *from_xy, const 
                                     int32_t obs_stride, const int32_t *n_obs, const double *play_area, double *new_xy,
                                     double *dist, int32_t *n_points, uint8_t *free_flag, uint8_t *inside_flag, void *stream);
 
+/* The other per-step methods of the reference's planner classes as stand-alone calls (rrtk.RRT / rrtk.RRTStar route
+ * their `steer`, `check_collision`, `get_nearest_node_index` and `find_near_nodes` methods here; the planning loop
+ * itself is rrtk_rrtstar_run_dev).  FP64, the reference's operation order.
+ *   rrtk_steer_points_dev: the points steer (rrt_04:1086-1115) appends to path_x / path_y for N edges.  extend_length
+ *     [N] per edge, or NULL = extend_all for every edge (+inf = the reference's default); points [N][pt_cap][2],
+ *     n_points [N] = len(path_x) (points beyond pt_cap are not written: size pt_cap >= floor(extend / res) + 2).
+ *   rrtk_points_collide_dev: check_collision (rrt_04:1216-1230) of N point lists (a node's path_x / path_y):
+ *     free_flag [N] = 1 when no point lies within (size + robot_radius) of a circle.  Obstacle rows / sets as in
+ *     rrtk_steer_collide_dev.
+ *   rrtk_nearest_f64_dev: get_nearest_node_index (rrt_04:1196-1202) of B samples [B][2] over n nodes [n][2]:
+ *     idx [B] = dlist.index(min(dlist)) (first minimum), d2 [B] (optional) = that squared distance.
+ *   rrtk_near_f64_dev: find_near_nodes (rrt_04:1314-1338) around (cx, cy) with squared radius r2: out_idx[0 ..
+ *     min(*out_n, cap)) in the reference's order (ascending, each hit replaced by the first node with the same squared
+ *     distance -- `dist_list.index(i)`); *out_n = the number of hits; scratch_d2 [cap] doubles of device memory. */
+RRTK_API int rrtk_steer_points_dev(int64_t n_req, const double *from_xy, const double *to_xy, const double *extend_length,
+                                   double extend_all, double path_resolution, int32_t pt_cap, double *points,
+                                   int32_t *n_points, void *stream);
+RRTK_API int rrtk_points_collide_dev(int32_t n_req, const double *points, const int32_t *n_points, int32_t pt_cap,
+                                     const int32_t *obs_set, const double *obstacles, int32_t obs_stride,
+                                     const int32_t *n_obs, uint8_t *free_flag, void *stream);
+RRTK_API int rrtk_nearest_f64_dev(const double *xy, int64_t n, const double *samples, int32_t n_samples, int32_t *idx,
+                                  double *d2, void *stream);
+RRTK_API int rrtk_near_f64_dev(const double *xy, int32_t n, double cx, double cy, double r2, int32_t *out_idx,
+                               double *scratch_d2, int32_t cap, int32_t *out_n, void *stream);
+
 /* generate_final_course (rrt_04:1117-1125) for every query on the device:
  *   path [Q][path_cap][2] = goal, node(goal_index), ..., root;  path_len [Q] (0 = no path) */
 RRTK_API int rrtk_extract_paths_dev(int32_t n_queries, int32_t node_cap, int32_t path_cap,

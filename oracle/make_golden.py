@@ -68,7 +68,7 @@ def tree_arrays(node_list):
     return x, y, c, np.array(par, dtype=np.int64)
 
 
-def run_rrt04(name, params, sobol_sampler, search_until_max_iter, seed, stream=None):
+def run_rrt04(name, params, sobol_sampler, search_until_max_iter, seed, stream=None, paths=False):
     """Drive rrt_04's RRT (RRT*).  If `stream` is None the reference samples by itself
     (random.seed(seed) + its Sobol code) and the stream it produced is recorded."""
     ns = ref_loader.load("rrt_04")
@@ -117,6 +117,11 @@ def run_rrt04(name, params, sobol_sampler, search_until_max_iter, seed, stream=N
                x=x, y=y, cost=c, parent=par,
                verdicts=np.array(verdicts, dtype=np.uint8),
                path=np.array(path, dtype=np.float64) if path is not None else np.zeros((0, 2)))
+    if paths:   # every node's path_x / path_y (the sampled edge its last steer call made), concatenated
+        lens = [len(n.path_x) for n in rrt.node_list]
+        out["path_off"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out["path_xy"] = np.array([[float(a), float(b)] for n in rrt.node_list for a, b in zip(n.path_x, n.path_y)],
+                                  dtype=np.float64).reshape(-1, 2)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(f"{name}: {len(x)} nodes, {len(recorded)} iterations, path "
           f"{0 if path is None else len(path)} waypoints, {len(verdicts)} verdicts, "
@@ -641,6 +646,10 @@ CASES = {
     "rrt04_c1_uniform_early": lambda: run_rrt04("rrt04_c1_uniform_early", C1, False, False, 2),
     # C2 shape (random circles, no play area, robot_radius 0)
     "rrt04_c2_o64_600": lambda: run_rrt04("rrt04_c2_o64_600", c2_params(1234, 64, 600), True, True, 5),
+    # the same two runs with every node's path_x / path_y kept (rrtk.Node.path_x parity)
+    "paths04_c1_sobol_500": lambda: run_rrt04("paths04_c1_sobol_500", C1, True, True, 0, paths=True),
+    "paths04_c2_o64_600": lambda: run_rrt04("paths04_c2_o64_600", c2_params(1234, 64, 600), True, True, 5, paths=True),
+    "paths04_c1_uniform_early": lambda: run_rrt04("paths04_c1_uniform_early", C1, False, False, 2, paths=True),
     "rrt04_c2_o256_800": lambda: run_rrt04("rrt04_c2_o256_800", c2_params(1235, 256, 800), True, True, 6),
     "rrt04_c2_o256_2000": lambda: run_rrt04("rrt04_c2_o256_2000", c2_params(1236, 256, 2000), True, True, 7),
 }

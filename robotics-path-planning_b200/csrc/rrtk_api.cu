@@ -78,6 +78,14 @@ int launch_bitstar(const rrtk_bitstar_params &p, const double *start_goal, const
 int launch_steer_collide(long long n_req, const double *from_xy, const double *to_xy, double extend, double res,
                          const int32_t *obs_set, const double *obstacles, int obs_stride, const int32_t *n_obs, const double *play,
                          double *new_xy, double *dist, int32_t *n_points, uint8_t *free_flag, uint8_t *inside_flag, cudaStream_t s);
+int launch_steer_points(long long n_req, const double *from_xy, const double *to_xy, const double *extend, double extend_all,
+                        double res, int pt_cap, double *points, int32_t *n_points, cudaStream_t s);
+int launch_points_collide(int n_req, const double *points, const int32_t *n_points, int pt_cap, const int32_t *obs_set,
+                          const double *obstacles, int obs_stride, const int32_t *n_obs, uint8_t *free_flag, cudaStream_t s);
+int launch_nearest_f64(const double *xy, long long n, const double *samples, int n_samples, int32_t *out_idx, double *out_d2,
+                       cudaStream_t s);
+int launch_near_f64(const double *xy, int n, double cx, double cy, double r2, int32_t *out_idx, double *scratch_d2, int cap,
+                    int32_t *out_n, cudaStream_t s);
 int launch_smooth_paths(int n_queries, int path_cap, int max_iter, double *path, int32_t *path_len, const double *draws,
                         const double *obs3, int obs_stride, const int32_t *n_obs, int32_t *status, int32_t *iters_done,
                         cudaStream_t s);
@@ -403,6 +411,49 @@ int rrtk_steer_collide_dev(int64_t n_req, const double *from_xy, const double *t
         return set_error(RRTK_ERR_INVALID, "from_xy / to_xy / new_xy / obstacles must be 16-byte aligned");
     return launch_steer_collide(n_req, from_xy, to_xy, extend_length, path_resolution, obs_set, obstacles, obs_stride, n_obs,
                                 play_area, new_xy, dist, n_points, free_flag, inside_flag, (cudaStream_t)stream);
+}
+
+int rrtk_steer_points_dev(int64_t n_req, const double *from_xy, const double *to_xy, const double *extend_length,
+                          double extend_all, double path_resolution, int32_t pt_cap, double *points, int32_t *n_points,
+                          void *stream) {
+    if (n_req < 0 || pt_cap < 1) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (!(path_resolution > 0.0) || (!extend_length && !(extend_all >= 0.0)))
+        return set_error(RRTK_ERR_INVALID, "path_resolution must be > 0, extend_length >= 0");
+    if (n_req == 0) return RRTK_OK;
+    if (!from_xy || !to_xy || !points || !n_points) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)from_xy | (uintptr_t)to_xy | (uintptr_t)points) & 15)
+        return set_error(RRTK_ERR_INVALID, "from_xy / to_xy / points must be 16-byte aligned");
+    return launch_steer_points(n_req, from_xy, to_xy, extend_length, extend_all, path_resolution, pt_cap, points, n_points,
+                               (cudaStream_t)stream);
+}
+
+int rrtk_points_collide_dev(int32_t n_req, const double *points, const int32_t *n_points, int32_t pt_cap,
+                            const int32_t *obs_set, const double *obstacles, int32_t obs_stride, const int32_t *n_obs,
+                            uint8_t *free_flag, void *stream) {
+    if (n_req < 0 || pt_cap < 1 || obs_stride < 0) return set_error(RRTK_ERR_INVALID, "bad sizes");
+    if (n_req == 0) return RRTK_OK;
+    if (!points || !n_points || !free_flag || (n_obs && obs_stride > 0 && !obstacles))
+        return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)points | (uintptr_t)obstacles) & 15) return set_error(RRTK_ERR_INVALID, "points / obstacles must be 16-byte aligned");
+    return launch_points_collide(n_req, points, n_points, pt_cap, obs_set, obstacles, obs_stride, n_obs, free_flag,
+                                 (cudaStream_t)stream);
+}
+
+int rrtk_nearest_f64_dev(const double *xy, int64_t n, const double *samples, int32_t n_samples, int32_t *idx, double *d2,
+                         void *stream) {
+    if (n < 1 || n > 0x7fffffffll || n_samples < 0) return set_error(RRTK_ERR_INVALID, "need 1 <= n < 2^31 and n_samples >= 0");
+    if (n_samples == 0) return RRTK_OK;
+    if (!xy || !samples || !idx) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if (((uintptr_t)xy | (uintptr_t)samples) & 15) return set_error(RRTK_ERR_INVALID, "xy / samples must be 16-byte aligned");
+    return launch_nearest_f64(xy, n, samples, n_samples, idx, d2, (cudaStream_t)stream);
+}
+
+int rrtk_near_f64_dev(const double *xy, int32_t n, double cx, double cy, double r2, int32_t *out_idx, double *scratch_d2,
+                      int32_t cap, int32_t *out_n, void *stream) {
+    if (n < 1 || cap < 0) return set_error(RRTK_ERR_INVALID, "need n >= 1 and cap >= 0");
+    if (!xy || !out_n || (cap > 0 && (!out_idx || !scratch_d2))) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    if ((uintptr_t)xy & 15) return set_error(RRTK_ERR_INVALID, "xy must be 16-byte aligned");
+    return launch_near_f64(xy, n, cx, cy, r2, out_idx, scratch_d2, cap, out_n, (cudaStream_t)stream);
 }
 
 int rrtk_sample_stream_dev(const rrtk_rrtstar_params *p, const double *start_goal,

@@ -110,6 +110,10 @@ _SIGS = {
     "rrtk_bitstar_run_dev": (C.c_int, [C.POINTER(BitStarParams)] + [_VP] * 12),
     "rrtk_steer_collide_dev": (C.c_int, [C.c_int64, _VP, _VP, C.c_double, C.c_double, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP,
                                          _VP, _VP, _VP]),
+    "rrtk_steer_points_dev": (C.c_int, [C.c_int64, _VP, _VP, _VP, C.c_double, C.c_double, C.c_int32, _VP, _VP, _VP]),
+    "rrtk_points_collide_dev": (C.c_int, [C.c_int32, _VP, _VP, C.c_int32, _VP, _VP, C.c_int32, _VP, _VP, _VP]),
+    "rrtk_nearest_f64_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP]),
+    "rrtk_near_f64_dev": (C.c_int, [_VP, C.c_int32, C.c_double, C.c_double, C.c_double, _VP, _VP, C.c_int32, _VP, _VP]),
     "rrtk_sample_stream_dev": (C.c_int, [C.POINTER(RRTStarParams), _VP, _VP, _VP, _VP]),
     "rrtk_crmath_probe_dev": (C.c_int, [C.c_int, C.c_int64, _VP, _VP, _VP, _VP]),
     "rrtk_nearest_f32_dev": (C.c_int, [_VP, C.c_int64, _VP, C.c_int32, _VP, _VP, _VP, _VP]),

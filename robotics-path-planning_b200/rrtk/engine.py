@@ -215,3 +215,84 @@ def steer_collide(from_xy, to_xy, obstacle_lists, extend_length=float("inf"), pa
         _lib.check(rc, "rrtk_steer_collide_dev")
         return dict(new_xy=new_xy.cpu().numpy(), dist=dist.cpu().numpy(), n_points=npts.cpu().numpy(),
                     free=free.cpu().numpy().astype(bool), inside=inside.cpu().numpy().astype(bool))
+
+
+def steer_points(from_xy, to_xy, extend_length=float("inf"), path_resolution=0.5, device=None):
+    """path_x / path_y of steer (rrt_04:1086-1115) for N edges in one launch (rrtk_steer_points_dev).  from_xy / to_xy
+    [N, 2]; extend_length a scalar or [N].  Returns (points [N, pt_cap, 2] float64, n_points [N]) as numpy arrays; row r
+    holds n_points[r] points."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    f = np.ascontiguousarray(from_xy, dtype=np.float64).reshape(-1, 2)
+    t = np.ascontiguousarray(to_xy, dtype=np.float64).reshape(-1, 2)
+    n = f.shape[0]
+    ext = np.broadcast_to(np.asarray(extend_length, dtype=np.float64), (n,)).copy()
+    reach = np.minimum(ext, np.hypot(t[:, 0] - f[:, 0], t[:, 1] - f[:, 1]) * (1.0 + 1e-12) + 1e-12) if n else ext
+    pt_cap = int(np.floor(reach.max() / path_resolution)) + 4 if n else 1
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        pts = torch.empty((n, pt_cap, 2), dtype=torch.float64, device=dev)
+        npts = torch.empty(n, dtype=torch.int32, device=dev)
+        d_f, d_t, d_e = up(f), up(t), up(ext)
+        rc = _lib.lib().rrtk_steer_points_dev(n, d_f.data_ptr(), d_t.data_ptr(), d_e.data_ptr(), 0.0, float(path_resolution),
+                                              pt_cap, pts.data_ptr(), npts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_steer_points_dev")
+        return pts.cpu().numpy(), npts.cpu().numpy()
+
+
+def points_collide(point_lists, obstacle_list, robot_radius=0.0, device=None):
+    """check_collision (rrt_04:1216-1230) of N point lists (each [[x, y], ...]) against one obstacle list; returns a bool
+    array, True = safe (rrtk_points_collide_dev)."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    n = len(point_lists)
+    pt_cap = max(1, max((len(p) for p in point_lists), default=1))
+    pts = np.zeros((n, pt_cap, 2), dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int32)
+    for r, p in enumerate(point_lists):
+        a = np.asarray(p, dtype=np.float64).reshape(-1, 2)
+        pts[r, :len(a)] = a
+        cnt[r] = len(a)
+    rows, counts = pack_obstacles([list(obstacle_list)], robot_radius)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    with torch.cuda.device(dev):
+        d_p, d_c, d_rows, d_cnt = up(pts), up(cnt), up(rows if rows.size else np.zeros((1, 1, 4))), up(counts)
+        free = torch.empty(n, dtype=torch.uint8, device=dev)
+        rc = _lib.lib().rrtk_points_collide_dev(n, d_p.data_ptr(), d_c.data_ptr(), pt_cap, None, d_rows.data_ptr(), rows.shape[1],
+                                                d_cnt.data_ptr(), free.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_points_collide_dev")
+        return free.cpu().numpy().astype(bool)
+
+
+def nearest_index(xy, samples, device=None):
+    """get_nearest_node_index (rrt_04:1196-1202) of B samples over the nodes xy [n, 2]: first minimum of the squared
+    distance, FP64 (rrtk_nearest_f64_dev).  Returns int32 [B]."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
+    with torch.cuda.device(dev):
+        d_a, d_s = torch.from_numpy(a).to(dev), torch.from_numpy(s).to(dev)
+        idx = torch.empty(len(s), dtype=torch.int32, device=dev)
+        rc = _lib.lib().rrtk_nearest_f64_dev(d_a.data_ptr(), len(a), d_s.data_ptr(), len(s), idx.data_ptr(), None,
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_nearest_f64_dev")
+        return idx.cpu().numpy()
+
+
+def near_indices(xy, cx, cy, r2, device=None):
+    """find_near_nodes (rrt_04:1314-1338) around (cx, cy) with squared radius r2 over the nodes xy [n, 2]: the reference's
+    list, `.index()` mapping included (rrtk_near_f64_dev).  Returns a Python list of ints."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    n = len(a)
+    with torch.cuda.device(dev):
+        d_a = torch.from_numpy(a).to(dev)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        d2 = torch.empty(n, dtype=torch.float64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = _lib.lib().rrtk_near_f64_dev(d_a.data_ptr(), n, float(cx), float(cy), float(r2), out.data_ptr(), d2.data_ptr(), n,
+                                          cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "rrtk_near_f64_dev")
+        return out[:int(cnt.item())].cpu().tolist()
