@@ -12,7 +12,7 @@ static uint64_t rnd(void) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; retur
 static double u01(void) { return (double)(rnd() >> 11) * (1.0 / 9007199254740992.0); }
 static double nudge(double x, int k) { int64_t b; memcpy(&b, &x, 8); b += k; memcpy(&x, &b, 8); return x; }
 
-static long n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at;
+static long n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at, n_as, bad_as;
 
 static void check_sincos(double x) {
     double s, c;
@@ -40,6 +40,21 @@ static void check_atan2(double y, double x) {
     }
 }
 
+/* crm_atan2_sincos as compiled here (first phases + fallback) against its double-double body alone: the three values are
+ * RN(atan2), RN(sin(that)), RN(cos(that)) */
+static void check_atan2_sincos(double y, double x) {
+    if (!(fabs(x) < 1e300 && fabs(y) < 1e300) || y == 0.0) return;
+    double s, c, th = crm_atan2_sincos(y, x, &s, &c);
+    double td = crm_atan2_dd(y, x).hi;
+    crm_dd sd, cd;
+    crm_sincos_dd(td, &sd, &cd);
+    n_as++;
+    if (th != td || s != sd.hi || c != cd.hi) {
+        if (bad_as < 10) fprintf(stderr, "atan2_sincos mismatch y=%a x=%a: (%a %a %a) vs (%a %a %a)\n", y, x, th, s, c, td, sd.hi, cd.hi);
+        bad_as++;
+    }
+}
+
 int main(int argc, char **argv) {
     long n = argc > 1 ? atol(argv[1]) : 2000000;
     for (long i = 0; i < n; i++) {
@@ -63,7 +78,9 @@ int main(int argc, char **argv) {
         check_atan2(sy * m, sx * nudge(m * (double)(rnd() % 129) * 0.0078125, (int)(rnd() % 65) - 32));
         check_atan2(sy * nudge(m, (int)(rnd() % 9) - 4), sx * m);
         check_atan2(sy * 2.0, sx * u01() * 40.0);
+        check_atan2_sincos(sy * u01() * 17.0, sx * u01() * 17.0);
+        check_atan2_sincos(sy * ldexp(u01(), -(int)(rnd() % 40)), sx * u01());
     }
-    printf("sincos %ld %ld %ld\natan2 %ld %ld %ld\n", n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at);
-    return (bad_sc || bad_at) ? 1 : 0;
+    printf("sincos %ld %ld %ld\natan2 %ld %ld %ld\natan2_sincos %ld %ld %ld\n", n_sc, ok_sc, bad_sc, n_at, ok_at, bad_at, n_as, n_as, bad_as);
+    return (bad_sc || bad_at || bad_as) ? 1 : 0;
 }

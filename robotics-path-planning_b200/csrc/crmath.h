@@ -367,54 +367,6 @@ CRM_FN crm_dd crm_atan2_dd(double y, double x) {
     return y < 0.0 ? crm_neg(a) : a;
 }
 
-/* theta = RN(atan2(y, x)); *s = RN(sin(theta)); *c = RN(cos(theta)) -- the three calls of
- * rrt_04:1236 and :1100-1101.  With A the exact angle and e = theta - A (|e| <= ulp(theta) / 2):
- *   cos(theta) = x/d - e * y/d,  sin(theta) = y/d + e * x/d,  d = sqrt(x^2 + y^2)
- * (e^2 < 2^-104 is dropped); x/d and y/d are formed in double-double, no sin/cos series needed.
- * Near the axes cos or sin of theta is itself of the order of e, so e must be known to ~2^-53
- * relative, not absolute: |A| = k pi/2 + sa * a with a = atan(min/max) in [0, pi/4] from the octant core
- * (relative error 2^-100), and e = (|theta| - k PIO2_H) - sa a.hi - k PIO2_L - sa a.lo - k PIO2_LL is
- * summed in double-double (the first difference is exact by Sterbenz). */
-CRM_NOINLINE double crm_atan2_sincos(double y, double x, double *s, double *c) {
-    if (y == 0.0) { /* includes (0, 0): atan2 = +-0 or +-pi */
-        int neg = (x < 0.0) || (x == 0.0 && signbit(x));
-        if (!neg) { *s = y; *c = 1.0; return y; }
-        double th = copysign(CRM_PI_H, y);
-        *s = copysign(CRM_PI_L, y); /* RN(sin(RN(pi))) = RN(pi - RN(pi)) */
-        *c = -1.0;
-        return th;
-    }
-    double ax = fabs(x), ay = fabs(y);
-    int swap = ay > ax, xneg = x < 0.0;
-    crm_dd a = crm_atan_octant_dd(crm_mk(swap ? ax : ay, 0.0), crm_mk(swap ? ay : ax, 0.0));
-    if (swap != xneg) a = crm_neg(a);                 /* sa * a */
-    double ch = swap ? CRM_PIO2_H : CRM_PI_H, cl = swap ? CRM_PIO2_L : CRM_PI_L;
-    double cll = swap ? CRM_PIO2_LL : CRM_PI_LL;
-    double tabs;
-    crm_dd e;
-    if (swap || xneg) {
-        tabs = crm_add(crm_mk(ch, cl), a).hi;
-        e = crm_add(crm_two_sum(tabs - ch, -a.hi), crm_two_sum(-cl, -a.lo));
-        e = crm_add_d(e, -cll);
-    } else {
-        tabs = a.hi;
-        e = crm_mk(-a.lo, 0.0);
-    }
-    if (y < 0.0) e = crm_neg(e);
-    /* d = sqrt(x*x + y*y) and 1/d in double-double */
-    crm_dd d2 = crm_add(crm_two_prod(x, x), crm_two_prod(y, y));
-    double d0 = sqrt(d2.hi);
-    crm_dd r = crm_sub(d2, crm_two_prod(d0, d0));
-    crm_dd d = crm_fast_two_sum(d0, r.hi / (2.0 * d0));
-    double i0 = 1.0 / d.hi;
-    r = crm_sub(crm_mk(1.0, 0.0), crm_mul_d(d, i0));
-    crm_dd inv = crm_fast_two_sum(i0, r.hi * i0);
-    crm_dd cd = crm_mul_d(inv, x), sd = crm_mul_d(inv, y);
-    *c = crm_sub(cd, crm_mul(e, sd)).hi;
-    *s = crm_add(sd, crm_mul(e, cd)).hi;
-    return y < 0.0 ? -tabs : tabs;
-}
-
 #ifdef CRM_FAST
 /* First phase for atan2 (see crm_sincos_fast): t = mn / mx as t0 + tl (quotient + exact-residual correction, relative
  * error < 2^-104), table entry atan(i/128), u = (t - i/128) / (1 + t i/128) as u0 + ul (relative error < 2^-100),
@@ -466,6 +418,61 @@ CRM_FN int crm_atan2_fast(double y, double x, double *out) {
     return 1;
 }
 #endif
+
+/* theta = RN(atan2(y, x)); *s = RN(sin(theta)); *c = RN(cos(theta)) -- the three calls of
+ * rrt_04:1236 and :1100-1101.  With A the exact angle and e = theta - A (|e| <= ulp(theta) / 2):
+ *   cos(theta) = x/d - e * y/d,  sin(theta) = y/d + e * x/d,  d = sqrt(x^2 + y^2)
+ * (e^2 < 2^-104 is dropped); x/d and y/d are formed in double-double, no sin/cos series needed.
+ * Near the axes cos or sin of theta is itself of the order of e, so e must be known to ~2^-53
+ * relative, not absolute: |A| = k pi/2 + sa * a with a = atan(min/max) in [0, pi/4] from the octant core
+ * (relative error 2^-100), and e = (|theta| - k PIO2_H) - sa a.hi - k PIO2_L - sa a.lo - k PIO2_LL is
+ * summed in double-double (the first difference is exact by Sterbenz). */
+CRM_NOINLINE double crm_atan2_sincos(double y, double x, double *s, double *c) {
+    if (y == 0.0) { /* includes (0, 0): atan2 = +-0 or +-pi */
+        int neg = (x < 0.0) || (x == 0.0 && signbit(x));
+        if (!neg) { *s = y; *c = 1.0; return y; }
+        double th = copysign(CRM_PI_H, y);
+        *s = copysign(CRM_PI_L, y); /* RN(sin(RN(pi))) = RN(pi - RN(pi)) */
+        *c = -1.0;
+        return th;
+    }
+#ifdef CRM_FAST
+    {   /* first phases: RN(atan2), then RN(sin), RN(cos) of that double -- the three values by definition */
+        double th;
+        if (crm_atan2_fast(y, x, &th) && crm_sincos_fast(th, s, c)) return th;
+    }
+#endif
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax, xneg = x < 0.0;
+    crm_dd a = crm_atan_octant_dd(crm_mk(swap ? ax : ay, 0.0), crm_mk(swap ? ay : ax, 0.0));
+    if (swap != xneg) a = crm_neg(a);                 /* sa * a */
+    double ch = swap ? CRM_PIO2_H : CRM_PI_H, cl = swap ? CRM_PIO2_L : CRM_PI_L;
+    double cll = swap ? CRM_PIO2_LL : CRM_PI_LL;
+    double tabs;
+    crm_dd e;
+    if (swap || xneg) {
+        tabs = crm_add(crm_mk(ch, cl), a).hi;
+        e = crm_add(crm_two_sum(tabs - ch, -a.hi), crm_two_sum(-cl, -a.lo));
+        e = crm_add_d(e, -cll);
+    } else {
+        tabs = a.hi;
+        e = crm_mk(-a.lo, 0.0);
+    }
+    if (y < 0.0) e = crm_neg(e);
+    /* d = sqrt(x*x + y*y) and 1/d in double-double */
+    crm_dd d2 = crm_add(crm_two_prod(x, x), crm_two_prod(y, y));
+    double d0 = sqrt(d2.hi);
+    crm_dd r = crm_sub(d2, crm_two_prod(d0, d0));
+    crm_dd d = crm_fast_two_sum(d0, r.hi / (2.0 * d0));
+    double i0 = 1.0 / d.hi;
+    r = crm_sub(crm_mk(1.0, 0.0), crm_mul_d(d, i0));
+    crm_dd inv = crm_fast_two_sum(i0, r.hi * i0);
+    crm_dd cd = crm_mul_d(inv, x), sd = crm_mul_d(inv, y);
+    *c = crm_sub(cd, crm_mul(e, sd)).hi;
+    *s = crm_add(sd, crm_mul(e, cd)).hi;
+    return y < 0.0 ? -tabs : tabs;
+}
+
 
 CRM_NOINLINE double crm_atan2(double y, double x) {
     if (y == 0.0) {

@@ -59,4 +59,4 @@ def test_first_phase_evaluations_equal_the_double_double_path(tmp_path):
     assert out.returncode == 0, out.stderr
     rows = {ln.split()[0]: [int(v) for v in ln.split()[1:]] for ln in out.stdout.splitlines()}
     for name, (n, accepted, bad) in rows.items():
-        assert bad == 0 and n > 3_000_000 and accepted > 0.95 * n, (name, n, accepted, bad)
+        assert bad == 0 and n > 1_000_000 and accepted > 0.95 * n, (name, n, accepted, bad)

@@ -12,6 +12,8 @@ checked through size-independent properties of the domain plus an oracle spot ch
     theta_list (arm02:95) of M = 8192 sampled every 8th angle is theta_list of M = 1024 exactly (a power-of-two
     rescale of `2 * i * pi / M`), so grid_8192[:, ::8, ::8] must equal grid_1024 bit for bit; set 0 at M = 512 is
     compared with the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -129,24 +131,33 @@ def test_c2_full_launch_is_deterministic(c2_full):
 
 
 def test_c2_full_spot_queries_equal_the_oracle(c2_full, oracle_lib):
+    """96 of the 4096 queries, spread over every wave of the work queue (plus its ends and the first query of the second
+    wave of resident warps), replayed in the C oracle (one thread each: ctypes releases the GIL) and compared bit for bit."""
     torch, cfg, batch, res, _ = c2_full
+    from concurrent.futures import ThreadPoolExecutor
     from rrtk import workloads as W
     O = oracle_lib
-    picks = [0, 1777, 2368, 4095]       # first, middle, first of the second wave of resident warps, last
-    stream = batch.materialised_stream()
-    for q in picks:
-        s = stream[q].cpu().numpy()
+    picks = sorted(set([0, 1777, 2368, 4095] + list(range(11, cfg["n_queries"], 44))))[:96]
+    assert len(picks) >= 64
+    stream = batch.materialised_stream()[torch.tensor(picks, device=res.xy.device)].cpu().numpy()
+    got = {k: t[torch.tensor(picks, device=t.device)].cpu().numpy() for k, t in
+           dict(n=res.n_nodes, parent=res.parent, xy=res.xy, cost=res.cost, gi=res.goal_index).items()}
+
+    def replay(j):
+        q = picks[j]
         p, obs = O.make_params(cfg["start"], cfg["goal"], W.c2_obstacles(q, cfg["n_obs"]).tolist(), cfg["expand_dis"],
                                cfg["path_resolution"], cfg["max_iter"], None, cfg["robot_radius"],
                                cfg["connect_circle_dist"], True, math_mode=O.MATH_CR)
-        ref = O.rrtstar_run(p, obs, s, want_trace=False)
+        return O.rrtstar_run(p, obs, stream[j], want_trace=False)
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
+        refs = list(ex.map(replay, range(len(picks))))
+    for j, ref in enumerate(refs):
         n = ref["n"]
-        assert int(res.n_nodes[q]) == n
-        assert np.array_equal(res.parent[q, :n].cpu().numpy(), ref["parent"])
-        xy = res.xy[q, :n].cpu().numpy()
-        assert np.array_equal(xy[:, 0], ref["x"]) and np.array_equal(xy[:, 1], ref["y"])
-        assert np.array_equal(res.cost[q, :n].cpu().numpy(), ref["cost"])
-        assert int(res.goal_index[q]) == ref["goal_index"]
+        assert int(got["n"][j]) == n, picks[j]
+        assert np.array_equal(got["parent"][j, :n], ref["parent"]), picks[j]
+        assert np.array_equal(got["xy"][j, :n, 0], ref["x"]) and np.array_equal(got["xy"][j, :n, 1], ref["y"]), picks[j]
+        assert np.array_equal(got["cost"][j, :n], ref["cost"]), picks[j]
+        assert int(got["gi"][j]) == ref["goal_index"], picks[j]
 
 
 def test_c5_full_grid_subsamples_to_the_coarse_grid(oracle_lib):
