@@ -292,14 +292,22 @@ CRM_FN int crm_sincos_fast(double x, double *s_out, double *c_out) {
 #endif
 
 /* RN(sin(x)), RN(cos(x)) together.  Out of line on the GPU (one copy per kernel: the planner kernels are bound by
- * instruction fetch, and this body was being inlined at ~20 call sites of the steering code) */
-CRM_NOINLINE void crm_sincos(double x, double *s, double *c) {
+ * instruction fetch, and this body was being inlined at ~20 call sites of the steering code); the pair comes back BY
+ * VALUE (registers) -- results written through pointers would go through local memory. */
+typedef struct { double s, c; } crm_sc;
+CRM_NOINLINE crm_sc crm_sincos_v(double x) {
+    crm_sc r;
 #ifdef CRM_FAST
-    if (crm_sincos_fast(x, s, c)) return;
+    if (crm_sincos_fast(x, &r.s, &r.c)) return r;
 #endif
     crm_dd sd, cd;
     crm_sincos_dd(x, &sd, &cd);
-    *s = sd.hi; *c = cd.hi;
+    r.s = sd.hi; r.c = cd.hi;
+    return r;
+}
+CRM_FN void crm_sincos(double x, double *s, double *c) {
+    const crm_sc r = crm_sincos_v(x);
+    *s = r.s; *c = r.c;
 }
 
 CRM_FN double crm_sin(double x) {
@@ -427,7 +435,20 @@ CRM_FN int crm_atan2_fast(double y, double x, double *out) {
  * relative, not absolute: |A| = k pi/2 + sa * a with a = atan(min/max) in [0, pi/4] from the octant core
  * (relative error 2^-100), and e = (|theta| - k PIO2_H) - sa a.hi - k PIO2_L - sa a.lo - k PIO2_LL is
  * summed in double-double (the first difference is exact by Sterbenz). */
-CRM_NOINLINE double crm_atan2_sincos(double y, double x, double *s, double *c) {
+typedef struct { double th, s, c; } crm_tsc;
+CRM_FN double crm_atan2_sincos_body(double y, double x, double *s, double *c);
+/* by value (registers) across the call; see crm_sincos_v */
+CRM_NOINLINE crm_tsc crm_atan2_sincos_v(double y, double x) {
+    crm_tsc r;
+    r.th = crm_atan2_sincos_body(y, x, &r.s, &r.c);
+    return r;
+}
+CRM_FN double crm_atan2_sincos(double y, double x, double *s, double *c) {
+    const crm_tsc r = crm_atan2_sincos_v(y, x);
+    *s = r.s; *c = r.c;
+    return r.th;
+}
+CRM_FN double crm_atan2_sincos_body(double y, double x, double *s, double *c) {
     if (y == 0.0) { /* includes (0, 0): atan2 = +-0 or +-pi */
         int neg = (x < 0.0) || (x == 0.0 && signbit(x));
         if (!neg) { *s = y; *c = 1.0; return y; }

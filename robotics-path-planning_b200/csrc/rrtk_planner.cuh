@@ -112,7 +112,7 @@ static __device__ __noinline__ void build_obstacle_grid(const ObsGrid &g, const 
 
 // cull through the grid: exact same keep test as cull_obstacles on the cell's candidates.  Falls back to the full scan
 // when the point is outside the grid or its cell overflowed.
-static __device__ __noinline__ ObsList cull_obstacles_grid(const ObsGrid &g, const double4 *obs, int n_obs, double cx,
+static __device__ __noinline__ ObsList cull_obstacles_grid(const ObsGrid g, const double4 *obs, int n_obs, double cx,
                                                        double cy, double reach, double *sx, double *sy, double *sr2,
                                                        int lane) {
     const double fx = floor((cx - g.x0) * g.inv_cell), fy = floor((cy - g.y0) * g.inv_cell);

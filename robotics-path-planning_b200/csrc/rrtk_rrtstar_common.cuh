@@ -52,8 +52,10 @@ static __device__ __noinline__ Steer steer(double fx, double fy, double tx, doub
 }
 
 // check_collision (rrt_04:1216-1230) of one edge by ONE lane: any path point within any circle.
-static __device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer &st, double tx,
-                                               double ty, const ObsList &L) {
+// (small structs go BY VALUE into out-of-line functions: a reference makes the caller spill the struct to local memory and
+// the callee load it back -- L2 round trips in the CTA-per-query kernel, whose shared-memory carve-out leaves almost no L1)
+static __device__ __noinline__ bool edge_free_lane(double fx, double fy, const Steer st, double tx,
+                                               double ty, const ObsList L) {
     double x = fx, y = fy;
     for (int k = 0;; k++) {
         for (int j = 0; j < L.m; j++) {
@@ -117,7 +119,7 @@ struct EdgeVerdict {
 template <bool MASK>
 static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double fy, double tx, double ty, double d, bool d_exact,
                                                              double extend, double q_ext, double res, double inv_res,
-                                                             const ObsList &L, int j0, int jstep, unsigned long long only) {
+                                                             const ObsList L, int j0, int jstep, unsigned long long only) {
     EdgeVerdict r;
     r.v = -1; r.near = ~0ull;
     if (!(d > 0.0)) return r;
@@ -176,8 +178,8 @@ static __device__ __noinline__ EdgeVerdict edge_verdict_fast(double fx, double f
 }
 
 // the same verdict computed by the whole warp (lanes split the obstacles); uniform result
-static __device__ __noinline__ bool edge_free_warp(double fx, double fy, const Steer &st, double tx,
-                                               double ty, const ObsList &L, int lane) {
+static __device__ __noinline__ bool edge_free_warp(double fx, double fy, const Steer st, double tx,
+                                               double ty, const ObsList L, int lane) {
     bool hit = false;
     for (int j = lane; j < L.m && !hit; j += 32) {
         double ox = L.ox[j * L.stride], oy = L.oy[j * L.stride], r2 = L.r2[j * L.stride];

@@ -11,15 +11,20 @@
 // 22 B / node = 44 KB at config 2's 2001 nodes, four queries per SM.  Global xy / parent are written through (they are
 // the outputs); node costs stay in global memory only: every read of a cost is either issued long before its use
 // (candidates) or replaced by a value carried in shared memory (the propagate frontier carries the parent's cost).
-// The iteration, with the CTA-wide barriers B1..B5:
-//   all warps   nearest (rrt_04:1196-1202) + speculative near set around the SAMPLE, strided over 128 threads; hits are
-//               appended unordered (shared-memory atomic)                                                         B1
-//   warp 0      first edge: steer + play area + collision (edge_verdict_fast / exact steer)           } concurrently
-//   warp 1      obstacle cull around the NEXT iteration's sample (its L2 latency never shows)         }
-//   warps 2-3   near list: rank by index (ascending order) + the `.index()` first-equal-d2 mapping    }          B2
+// An iteration is two stages.  Stage A (nothing in it reads a cost or a parent):
+//   scan        nearest (rrt_04:1196-1202) + speculative near set around the SAMPLE, strided over the scanning threads;
+//               hits are appended unordered (shared-memory atomic)                                                B1
+//   one warp    first edge: steer + play area + collision (edge_verdict_fast / exact steer)           } concurrently
+//   one warp    the NEXT sample and the obstacle cull around it (its L2 latency never shows)          }
+//   the rest    near list: rank by index (ascending order) + the `.index()` first-equal-d2 mapping    }          B2
+// Stage B:
 //   all warps   choose_parent (rrt_04:1242-1282): 4 lanes per candidate split the culled circles                B3
-//   all warps   rewire edges (rrt_04:1340-1373), same split, only entries that pass node.cost > new.cost + d    B4
-//   warp 0      ordered apply + propagate over the shared-memory children lists, append                         B5
+//   all warps   rewire edges (rrt_04:1340-1373), same split, only entries that pass node.cost > new.cost + d;
+//               the few entries that can apply go to a compact list                                               B4
+//   warp 0      ordered apply + propagate over the shared-memory children lists, append
+// SOFTWARE PIPELINE: the apply phase of iteration i (warp 0 alone, ~a quarter of the iteration) and stage A of iteration
+// i + 1 (warps 1-3: the new node's position is known since B3, and stage A reads positions only) run side by side whenever
+// no node can MOVE in that apply phase and the goal is not searched every iteration; one barrier (B2) joins them.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,18 +32,17 @@
 #include "crmath.h"
 #include "rrtk_device.cuh"
 #include "rrtk_planner.cuh"
-#define RRTK_DRAW_SAMPLE_INLINE __noinline__   // one copy: only the sampling warp runs it
+// (draw_sample stays inline: out of line it takes the parameter block and the Sobol state by reference, i.e. through local memory)
 #include "rrtk_rrtstar_common.cuh"
 
 namespace rrtk {
 
 constexpr int CTA_W = 4;              // warps per query
 constexpr int CTA_T = CTA_W * 32;
-constexpr int CTA_G = 4;              // lanes per near candidate
-constexpr int CTA_CPR = CTA_T / CTA_G;  // candidates per round
 constexpr int CTA_NC_SMALL = 256;     // layout capacities of the near list (p.near_cap <= NC): batches / single queries
 constexpr int CTA_NC_LARGE = 1024;
-constexpr int CTA_FQ = 128;           // shared-memory slots of propagate's frontier (more spill to the workspace)
+constexpr int CTA_FQ = 64;            // shared-memory slots of propagate's frontier (more spill to the workspace)
+constexpr int CTA_AL = 32;            // compact apply list (more: the apply phase reads the near-list arrays)
 constexpr unsigned short NONE16 = 0xffffu;
 constexpr int BIG = 0x7fffffff;
 
@@ -59,16 +63,18 @@ struct CtaSmemT {
     double fq_cost[CTA_FQ];
     double red_d[CTA_W], red_ex[CTA_W], red_ey[CTA_W];
     double nx, ny;                   // the new node (warp 0 -> all)
-    double smp[2][2];                // the sample of this iteration [it & 1] and the next (drawn by warp 1)
-    double def_cost;                 // deferred propagate (see the apply loop): root cost
+    double smp[2][2];                // the sample of this iteration [it & 1] and the next (drawn one iteration ahead)
+    double al_ec[CTA_AL], al_c0[CTA_AL], al_dk[CTA_AL];   // compact apply list: new cost, node cost seen, edge length
     int near_idx[NC];
     int near_ok[NC];             // unordered indices while the list is built, then the rewire flags
     int red_i[CTA_W];
     int cull_m[2], cull_glob[2];
-    int count, cpok, tail;
+    int al_w[CTA_AL];                // compact apply list: (flag << 30) | (list position << 16) | node
+    int count2[2];                   // near hits of this iteration's scan [it & 1] (the other one is being reset)
+    int al_n2[2], any_moves2[2];     // compact-list length / "a node would move" of this iteration's stage B [it & 1]
+    int cpok, tail;
     int accept, near_valid, t_status;
     int done, gi, status_or, ni, leader;
-    int def_root;                    // deferred propagate: root node, -1 = none pending
     unsigned int q;
     unsigned short fq_idx[CTA_FQ];
 };
@@ -142,12 +148,12 @@ static __device__ __noinline__ void cta_propagate(int root, double root_cost, bo
     }
 }
 
-// view of every CTA_G-th circle of L starting at `sub` (the share of one lane of a candidate's group)
-static __device__ __forceinline__ ObsList sub_list(const ObsList &L, int sub) {
+// view of every G-th circle of L starting at `sub` (the share of one lane of a candidate's group of G lanes)
+static __device__ __forceinline__ ObsList sub_list(const ObsList &L, int sub, int G) {
     ObsList s;
     s.ox = L.ox + (size_t)sub * L.stride; s.oy = L.oy + (size_t)sub * L.stride; s.r2 = L.r2 + (size_t)sub * L.stride;
-    s.stride = L.stride * CTA_G;
-    s.m = L.m > sub ? (L.m - sub + CTA_G - 1) / CTA_G : 0;
+    s.stride = L.stride * G;
+    s.m = L.m > sub ? (L.m - sub + G - 1) / G : 0;
     return s;
 }
 
@@ -207,6 +213,111 @@ static __device__ __noinline__ void cta_rank_near(SM &S, int count, int t0, int 
         S.near_idx[rank] = first;
         S.nd[rank] = dk;
     }
+}
+
+// State of an iteration whose edges are done (after B4) and whose apply phase is outstanding.
+struct CtaPending {
+    double cx, cy, ccost, new_elen;   // the new node (after choose_parent), its cost, hypot(new - parent) or NaN
+    int n, best, count, al_n, cb;     // its index, its parent, the near-list length, compact-list length, cull buffer of L
+    bool compact, c_is_new;
+};
+
+// rewire, ordered apply (rrt_04:1361-1371) + propagate_cost_to_leaves (:1379-1384) + the append (:1064), by ONE warp.
+// The entries that can apply (flag != 0 and node.cost > new.cost + d when the edges were made) come from the compact list
+// S.al_* (P.compact: <= 32 entries in any order) or from the near-list arrays 32 at a time; they are taken in list order.
+template <bool TRACE, class SM>
+static __device__ __forceinline__ void cta_apply(const rrtk_rrtstar_params &p, const CtaPending &P, SM &S, double2 *s_xy,
+                                              ushort2 *s_link, unsigned short *s_par, double2 *xy, double *cost, int32_t *parent,
+                                              double *elen, const double4 *obs, int n_obs, int *g_idx, double *g_cost, int lane,
+                                              int &t_rwok, int &t_rwap) {
+    const double INF = CUDART_INF, NaN = __longlong_as_double(0x7ff8000000000000ll);
+    const double res = p.path_resolution, cx = P.cx, cy = P.cy, ccost = P.ccost;
+    const int n = P.n;
+    bool dirty = false;      // a propagate ran: node costs must be re-read
+    int fallback_from = -1;  // >= 0: a node moved; redo entries from here serially
+    const int nb = P.compact ? (P.al_n > 0 ? 1 : 0) : P.count;
+#pragma unroll 1
+    for (int b0 = 0; b0 < nb && fallback_from < 0; b0 += 32) {
+        int k = BIG, i = -1, fl = 0;
+        double ecost = 0.0, snc = 0.0, dk = 0.0;
+        if (P.compact) {
+            if (lane < P.al_n) {
+                const int w = S.al_w[lane];
+                i = w & 0xffff; k = (w >> 16) & 0x3fff; fl = (w >> 30) & 3;
+                ecost = S.al_ec[lane]; snc = S.al_c0[lane]; dk = S.al_dk[lane];
+            }
+        } else if (b0 + lane < P.count) {
+            k = b0 + lane;
+            i = S.near_idx[k];
+            fl = S.near_ok[k];
+            snc = S.s_nc[k];
+            dk = S.nd[k];
+            ecost = ccost + dk;
+        }
+        const unsigned okmask = __ballot_sync(FULL, fl != 0);
+        if (TRACE) t_rwok += __popc(okmask);
+        unsigned m = __ballot_sync(FULL, fl != 0 && (snc > ecost));
+        while (m) {  // apply in list order
+            const int kk = (int)__reduce_min_sync(FULL, ((m >> lane) & 1u) ? (unsigned)k : 0xffffffffu);
+            const int b = __ffs(__ballot_sync(FULL, k == kk && ((m >> lane) & 1u))) - 1;
+            m &= ~(1u << b);
+            const int ii = __shfl_sync(FULL, i, b);
+            const double ec = __shfl_sync(FULL, ecost, b);
+            const double c0 = __shfl_sync(FULL, snc, b);
+            const double dkb = __shfl_sync(FULL, dk, b);
+            const int flb = __shfl_sync(FULL, fl, b);
+            const double ci = dirty ? cost[ii] : c0;
+            if (ci > ec) {
+                const double2 a = s_xy[ii];
+                double ex = a.x, ey = a.y;
+                if (flb == 2) {   // the exact edge stops short of the node: it moves there
+                    const Steer st = steer(cx, cy, a.x, a.y, INF, res);
+                    ex = st.ex; ey = st.ey;
+                }
+                const bool moved = (a.x != ex) || (a.y != ey);
+                __syncwarp();
+                if (lane == 0) {
+                    cta_unlink(s_link, (int)s_par[ii], ii);
+                    cta_link(s_link, n, ii);
+                    if (moved) { s_xy[ii] = make_double2(ex, ey); xy[ii] = make_double2(ex, ey); }
+                    cost[ii] = ec;
+                    parent[ii] = n;
+                    s_par[ii] = (unsigned short)n;
+                    elen[ii] = moved ? NaN : dkb;   // hypot(node - new node), what propagate would compute
+                }
+                __syncwarp();
+                if (TRACE) t_rwap++;
+                cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
+                __syncwarp();
+                dirty = true;
+                if (moved) {
+                    // the node no longer sits where the parallel pass saw it, and the costs of its descendants may have
+                    // gone UP: every later entry is re-evaluated from the current tree, one at a time
+                    fallback_from = kk + 1;
+                    if (TRACE) t_rwok -= __popc(okmask >> b >> 1);  // recounted below (TRACE never runs compact)
+                    break;
+                }
+            }
+        }
+    }
+    if (fallback_from >= 0) {
+        ObsList L;
+        if (S.cull_glob[P.cb]) {
+            const double *g = reinterpret_cast<const double *>(obs);
+            L.ox = g; L.oy = g + 1; L.r2 = g + 3; L.stride = 4; L.m = n_obs;
+        } else {
+            L.ox = S.cull[P.cb][0]; L.oy = S.cull[P.cb][1]; L.r2 = S.cull[P.cb][2]; L.stride = 1; L.m = S.cull_m[P.cb];
+        }
+        cta_rewire_serial(p, fallback_from, P.count, S, s_xy, s_link, s_par, xy, cost, parent, elen, n, cx, cy, ccost, L,
+                          g_idx, g_cost, lane, t_rwok, t_rwap);
+    }
+    if (lane == 0) {
+        s_xy[n] = make_double2(cx, cy); s_par[n] = (unsigned short)P.best;
+        xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = P.best;
+        elen[n] = P.new_elen;
+        cta_link(s_link, P.best, n);
+    }
+    __syncwarp();
 }
 
 template <bool RRT_ONLY, bool TRACE, bool RESUME, int NC>
@@ -317,19 +428,19 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         }
         if (skip) continue;   // uniform: every thread read the same outputs
         if (warp == 0 && grid_cells > 0) build_obstacle_grid(grid, obs, n_obs, reach, lane);
-        if (tid == 0) { S.count = 0; S.cpok = 0; S.done = 0; S.gi = -1; S.status_or = 0; }
+        if (tid == 0) {
+            S.count2[0] = 0; S.count2[1] = 0; S.cpok = 0; S.done = 0; S.gi = -1; S.status_or = 0;
+            S.al_n2[0] = S.al_n2[1] = 0; S.any_moves2[0] = S.any_moves2[1] = 0;
+        }
         sobol2(sob.n, sob.q0, sob.q1);
         bool done = false;
-        // costs are read inside an iteration only by choose_parent / rewire (after B2) unless the goal is searched every
-        // iteration: then no propagate may be left pending
-        const bool can_defer = !RRT_ONLY && p.search_until_max_iter != 0;
+        // the apply phase of an iteration may run beside stage A of the next one only when nothing it produces is read before
+        // the next stage B: not with a goal search per iteration, not with a trace (its counters close an iteration)
+        const bool can_overlap = !RRT_ONLY && !TRACE && p.search_until_max_iter != 0;
+        const bool goal_mode = RRT_ONLY || p.search_until_max_iter == 0;   // a goal test closes every iteration
         const double inv_res = 1.0 / res, q_expand = floor(p.expand_dis / res);   // steer's n_expand at full extension
-        // near radius of the current tree size, and (loaded one iteration ahead) of the size after an append
-        double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];
-        // the sample of iteration 0, and the circles around it
-        if (tid == 0) S.def_root = -1;
         __syncthreads();   // the obstacle cells are built
-        // warp 1 draws the samples (one iteration ahead) and gathers the circles around them
+        // the sampling warp draws the samples (one iteration ahead) and gathers the circles around them
         if (warp == 1 && p.max_iter > 0) {
             const Sample s0 = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sob);
             if (lane == 0) { S.smp[0][0] = s0.x; S.smp[0][1] = s0.y; }
@@ -341,66 +452,135 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         }
         __syncthreads();
 
-        for (it = 0; it < p.max_iter; it++) {
+        CtaPending P;                                   // the outstanding apply phase (valid while `pending`)
+        P.cx = P.cy = P.ccost = P.new_elen = 0.0;
+        P.n = P.best = P.count = P.al_n = P.cb = 0;
+        P.compact = P.c_is_new = false;
+        bool pending = false, overlap = false, appended = false;
+#ifdef RRTK_CTA_STATS
+        int st_ov = 0, st_pend = 0, st_big = 0, st_moves = 0;
+        long long st_c[6] = {0, 0, 0, 0, 0, 0};   // [0] role work of this warp in overlapped rounds, [1] its B2 wait, [2] scan, [3] stage B choose, [4] rewire, [5] rounds
+        long long st_t0 = 0, st_t1 = 0, st_r[4] = {0, 0, 0, 0}; int st_rn[4] = {0, 0, 0, 0}, st_cat = -1;   // round time by category
+#endif
+        // trace row of the iteration being closed
+        int t_ni = 0, t_status = 0, t_near = 0, t_par = -1, t_rwok = 0, t_rwap = 0;
+
+        for (it = 0;; it++) {
             const int cb = it & 1;
 #ifdef RRTK_CTA_PROFILE
             long long clk[10];
 #endif
+#ifdef RRTK_CTA_STATS
+            { const long long now = clock64(); if (st_cat >= 0) { st_r[st_cat] += now - st_t0; st_rn[st_cat]++; } st_t0 = now; }
+#endif
             CTA_CLK(0);
+            // ======== close iteration it - 1: its apply phase (warp 0), its trace row, the goal tests ========
+            const bool ov = pending && overlap;           // ... while the other warps already run stage A of iteration it
+            if (it > 0) {
+                if (pending && warp == 0)
+                    cta_apply<TRACE>(p, P, S, s_xy, s_link, s_par, xy, cost, parent, elen, obs, n_obs, g_idx, g_cost, lane, t_rwok, t_rwap);
+                if (TRACE && tid == 0) {
+#ifndef RRTK_CTA_PROFILE
+                    int32_t *tr = trace + (size_t)(it - 1) * 8;
+                    tr[0] = t_ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = S.cpok;
+                    tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
+#endif
+                    S.cpok = 0;
+                }
+                // ---- goal tests, by warp 0 (it wrote the last node itself); scratch = the closed iteration's circle list ----
+                if (goal_mode && warp == 0 && !done) {
+                    __syncwarp();
+                    if (RRT_ONLY) {
+                        // goal test on the last node (rrt_01:90-96)
+                        const double2 last = s_xy[n - 1];
+                        if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
+                            ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb ^ 1][0], S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
+                            Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
+                            if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane) && lane == 0) { S.gi = n - 1; S.done = 1; }
+                        }
+                    } else {
+                        bool ovf = false;
+                        // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
+                        ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb ^ 1][0], S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
+                        const int g = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
+                        if (lane == 0) {
+                            if (ovf) S.status_or |= RRTK_Q_NEAR_OVERFLOW;
+                            if (g >= 0) { S.gi = g; S.done = 1; }
+                        }
+                    }
+                }
+                if (!ov && (pending || appended || goal_mode)) {
+                    __syncthreads();   // ---- BA: stage A below reads what the apply phase / the append wrote
+                    pending = false;
+                }
+                if (goal_mode && S.done) { gi = S.gi; done = true; }
+            }
+            CTA_CLK(9);
+            if (it >= p.max_iter || done) break;
+            appended = false;
+            t_rwok = 0; t_rwap = 0; t_near = 0; t_par = -1;
+
+            // ======== stage A of iteration it ========
+            // roles.  Alone: 128 threads scan, warp 0 takes the first edge, warp 1 the next sample, warps 2-3 rank.  Beside an
+            // apply phase (ov): warp 1 the next sample at once, warps 2-3 scan, then warp 2 the first edge and warp 3 ranks.
+            const bool scanning = !ov || warp >= 2;
+            const int scan_t0 = ov ? tid - 64 : tid, scan_nt = ov ? 64 : CTA_T;
+            const int nslots = ov ? 2 : CTA_W;
+            const bool r_first = ov ? warp == 2 : warp == 0, r_samp = warp == 1;
             const double rx = S.smp[cb][0], ry = S.smp[cb][1];
-            // a propagate left over by the previous iteration's rewire runs on warp 3 while the others scan (its costs are
-            // first read after B2)
-            const int def_root = S.def_root;
-            const bool defer = def_root >= 0;
-            const int scan_t = defer ? CTA_T - 32 : CTA_T;
+            const double r2 = RRT_ONLY ? -1.0 : near_r2[n + 1];   // near radius^2 at the current tree size (rrt_04:1329-1335)
+            const int n_scan = ov ? n - 1 : n;   // (the node of the outstanding apply phase is not in shared memory yet)
             // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the sample
             // (when the steered node snaps onto the sample -- the common case once the tree is dense -- the near scan
             // would compute exactly these d2 again) ----
             double bd = INF;
             int bi = BIG;
-            const double r2_grown = RRT_ONLY ? -1.0 : near_r2[n + 2 <= p.node_cap + 1 ? n + 2 : p.node_cap + 1];
-            const int n_before = n;
-            if (defer && warp == CTA_W - 1) {
-                cta_propagate(def_root, S.def_cost, false, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
-            } else {
+            if (scanning) {
 #pragma unroll 2
-                for (int i = tid; i < n; i += scan_t) {
+                for (int i = scan_t0; i < n_scan; i += scan_nt) {
                     const double2 a = s_xy[i];
                     const double ddx = a.x - rx, ddy = a.y - ry;
                     const double d = ddx * ddx + ddy * ddy;
                     if (d < bd) { bd = d; bi = i; }
                     if (d <= r2) {
-                        const int slot = atomicAdd(&S.count, 1);
+                        const int slot = atomicAdd(&S.count2[cb], 1);
                         if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
                     }
                 }
+                if (ov && scan_t0 == 0) {   // the node the outstanding apply phase appends: index n - 1 at (P.cx, P.cy)
+                    const double ddx = P.cx - rx, ddy = P.cy - ry;
+                    const double d = ddx * ddx + ddy * ddy;
+                    if (d < bd) { bd = d; bi = n - 1; }
+                    if (d <= r2) {
+                        const int slot = atomicAdd(&S.count2[cb], 1);
+                        if (slot < near_cap) { S.near_ok[slot] = n - 1; S.s_nc[slot] = d; }
+                    }
+                }
+#ifdef RRTK_CTA_STATS
+                if (ov) st_c[2] += clock64() - st_t0;
+#endif
                 warp_argmin(bd, bi);
-                if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; }
+                if (lane == 0) { S.red_d[ov ? warp - 2 : warp] = bd; S.red_i[ov ? warp - 2 : warp] = bi; }
                 CTA_CLK(1);
-                // ---- B1 (the scanning warps only while warp 3 propagates: it joins at B2)
-                if (defer) asm volatile("bar.sync 1, %0;" ::"n"(CTA_T - 32) : "memory");
-            }
-            if (!defer) __syncthreads();   // ---- B1
-            const int scan_w = defer ? CTA_W - 1 : CTA_W;
-            if (!(defer && warp == CTA_W - 1)) {
+                // ---- B1: the scanning warps
+                if (ov) asm volatile("bar.sync 1, %0;" ::"n"(64) : "memory");
+                else __syncthreads();
                 bd = S.red_d[0]; bi = S.red_i[0];
 #pragma unroll 1
-                for (int w = 1; w < scan_w; w++) {
+                for (int w = 1; w < nslots; w++) {
                     const double dw = S.red_d[w];
                     const int iw = S.red_i[w];
                     if (dw < bd || (dw == bd && iw < bi)) { bd = dw; bi = iw; }
                 }
             }
             int ni = bi;
-            int count = S.count;     // (warp 3 re-reads both after B2 when it skipped the scan)
-            int t_near = 0, t_par = -1, t_rwok = 0, t_rwap = 0;
-            double2 from = make_double2(0.0, 0.0);
+            int count = 0;
             CTA_CLK(2);
-            if (warp == 0) {
+            if (r_first) {
                 // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the sample the
                 // new node IS the sample and only the collision verdict is needed; otherwise the exact steer runs ----
-                from = s_xy[ni];
-                int t_status = 0;
+                const double2 from = (ov && ni == n - 1) ? make_double2(P.cx, P.cy) : s_xy[ni];
+                int f_status = 0;
                 bool accept = false, near_valid = false;
                 double nx = rx, ny = ry;
                 // (the verdict keeps a 1e-9 margin on every use of the edge length: a plain sqrt is as good as the correctly
@@ -424,7 +604,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                                                    lane, 32, ~0ull).v;
                             const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
                             v = blocked ? 0 : (unsure ? -1 : 1);
-                            if (v >= 0) { t_status = 1; accept = v == 1; near_valid = true; }
+                            if (v >= 0) { f_status = 1; accept = v == 1; near_valid = true; }
                         } else {
                             v = 0;  // outside the play area: rejected before the collision check (rrt_04:1054)
                         }
@@ -434,7 +614,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
                     nx = e0.ex; ny = e0.ey;
                     if (inside_play(p, nx, ny)) {
-                        t_status = 1;
+                        f_status = 1;
                         // (the list prefetched for the sample only holds if the node landed on it)
                         L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
                         if (lane == 0) { S.cull_m[cb] = L.m; S.cull_glob[cb] = L.stride == 4 ? 1 : 0; }
@@ -442,11 +622,15 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     }
                 }
                 if (lane == 0) {
-                    S.nx = nx; S.ny = ny; S.accept = accept ? 1 : 0; S.near_valid = near_valid ? 1 : 0; S.t_status = t_status;
+                    S.nx = nx; S.ny = ny; S.accept = accept ? 1 : 0; S.near_valid = near_valid ? 1 : 0; S.t_status = f_status;
                     S.ni = ni;
                     if (accept && n < p.node_cap) s_link[n] = make_ushort2(NONE16, NONE16);  // children arrive through rewire
+                    // counters of the NEXT scan (last read right after B2 of iteration it - 1, which every thread left before
+                    // this iteration's B1 / the previous B3) and of THIS iteration's stage B (last read after B4 of iteration
+                    // it - 2; B2 of iteration it - 1 lies in between)
+                    S.count2[cb ^ 1] = 0; S.al_n2[cb] = 0; S.any_moves2[cb] = 0;
                 }
-            } else if (warp == 1) {
+            } else if (r_samp) {
                 // ---- the NEXT sample and the circles around it (consumed by iteration it + 1 when its node lands on the sample) ----
                 if (it + 1 < p.max_iter) {
                     const Sample sn = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
@@ -457,19 +641,31 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         if (lane == 0) { S.cull_m[cb ^ 1] = Ln.m; S.cull_glob[cb ^ 1] = Ln.stride == 4 ? 1 : 0; }
                     }
                 }
-            } else if (!RRT_ONLY && !(defer && warp == CTA_W - 1)) {
-                if (count <= near_cap) cta_rank_near(S, count, tid - 64, defer ? 32 : 64);
+            } else if (!RRT_ONLY && scanning) {
+                const int cnt = S.count2[cb];
+                if (cnt <= near_cap) {
+                    if (ov) cta_rank_near(S, cnt, lane, 32);
+                    else cta_rank_near(S, cnt, tid - 64, 64);
+                }
             }
+#ifdef RRTK_CTA_STATS
+            st_t1 = clock64();
+            if (ov) { st_c[0] += st_t1 - st_t0; st_c[5]++; }
+#endif
             CTA_CLK(3);
-            __syncthreads();   // ---- B2
+            __syncthreads();   // ---- B2 (also the end of an apply phase that ran beside this stage A)
+#ifdef RRTK_CTA_STATS
+            if (ov) st_c[1] += clock64() - st_t1;
+            st_t1 = clock64();
+#endif
+            pending = false;
             CTA_CLK(4); CTA_CLK(5); CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
-            if (defer) {
-                ni = S.ni; count = S.count;
-                if (tid == CTA_T - 32) S.def_root = -1;   // (every thread has read it; the apply phase may set the next one)
-            }
+
+            // ======== stage B of iteration it ========
+            ni = S.ni; count = S.count2[cb];
             bool accept = S.accept != 0;
             const double nx = S.nx, ny = S.ny;
-            int t_status = S.t_status;
+            t_status = S.t_status; t_ni = ni;
             if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
             if (accept && RRT_ONLY) {
                 if (tid == 0) {
@@ -478,22 +674,24 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 }
                 t_status = 2; t_par = ni;
                 n++;
+                appended = true;
             } else if (accept) {
                 if (!S.near_valid) {
                     // ---- find_near_nodes (rrt_04:1314-1338) around the new node (it is not the sample) ----
-                    if (tid == 0) S.count = 0;
+                    __syncthreads();   // (every thread has read the speculative count)
+                    if (tid == 0) S.count2[cb] = 0;
                     __syncthreads();
                     for (int i = tid; i < n; i += CTA_T) {
                         const double2 a = s_xy[i];
                         const double ddx = a.x - nx, ddy = a.y - ny;
                         const double d = ddx * ddx + ddy * ddy;
                         if (d <= r2) {
-                            const int slot = atomicAdd(&S.count, 1);
+                            const int slot = atomicAdd(&S.count2[cb], 1);
                             if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
                         }
                     }
                     __syncthreads();
-                    count = S.count;
+                    count = S.count2[cb];
                     if (count <= near_cap) cta_rank_near(S, count, tid, CTA_T);
                     __syncthreads();
                 }
@@ -509,15 +707,20 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     } else {
                         L.ox = S.cull[cb][0]; L.oy = S.cull[cb][1]; L.r2 = S.cull[cb][2]; L.stride = 1; L.m = S.cull_m[cb];
                     }
-                    const int sub = tid & (CTA_G - 1), grp = lane & ~(CTA_G - 1);
-                    // ---- choose_parent (rrt_04:1242-1282): CTA_G lanes per candidate, each tests its share of the circles ----
+                    // lanes per candidate: as many as keep the whole near list in ONE round of the 128 threads (a second round
+                    // costs a warp the fixed part of an edge again -- hypot, the quotient, the error band -- which is more than
+                    // the longer share of the circles; and with 4 lanes each, warp 0 alone took the second round of a list of
+                    // 33 .. 40 entries while the others waited at the barrier)
+                    const int G = count <= CTA_T / 4 ? 4 : (count <= CTA_T / 2 ? 2 : 1), CPR = CTA_T / G;
+                    const int sub = tid & (G - 1), grp = lane & ~(G - 1);
+                    // ---- choose_parent (rrt_04:1242-1282): G lanes per candidate, each tests its share of the circles ----
                     double bc = INF, bex = 0.0, bey = 0.0;
                     int bk = BIG;
                     // this lane's circles near the segment (its first-round candidate) - (new node), for the reverse edge
                     unsigned long long seg_near = ~0ull;
 #pragma unroll 1
-                    for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
-                        const int k = k0 + tid / CTA_G;
+                    for (int k0 = 0; k0 < count; k0 += CPR) {
+                        const int k = k0 + tid / G;
                         const bool valid = k < count;
                         double dk = 0.0, ci = 0.0, ex = nx, ey = ny;
                         bool blocked = false, exact = false;
@@ -526,19 +729,19 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             const double2 a = s_xy[i];
                             ci = cost[i];
                             dk = crm_hypot(nx - a.x, ny - a.y);   // what steer's calc_distance_and_angle returns
-                            const EdgeVerdict ev = edge_verdict_fast<true>(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, ~0ull);
+                            const EdgeVerdict ev = edge_verdict_fast<true>(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, sub, G, ~0ull);
                             const int vv = ev.v;
                             if (k0 == 0) seg_near = vv == 1 ? ev.near : ~0ull;
                             blocked = vv == 0;                    // (the new node is inside the play area)
                             if (vv < 0) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
-                                blocked = !(edge_free_lane(a.x, a.y, st, nx, ny, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
+                                blocked = !(edge_free_lane(a.x, a.y, st, nx, ny, sub_list(L, sub, G)) && inside_play(p, st.ex, st.ey));
                                 ex = st.ex; ey = st.ey;
                                 exact = true;
                             }
                         }
-                        const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << CTA_G) - 1u);
-                        const unsigned em = (__ballot_sync(FULL, exact) >> grp) & ((1u << CTA_G) - 1u);
+                        const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << G) - 1u);
+                        const unsigned em = (__ballot_sync(FULL, exact) >> grp) & ((1u << G) - 1u);
                         const int src = grp + (em ? __ffs(em) - 1 : 0);
                         ex = __shfl_sync(FULL, ex, src);          // an exactly steered edge ends where ITS steer ends
                         ey = __shfl_sync(FULL, ey, src);
@@ -564,6 +767,9 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         }
                         if (lane == 0) { S.red_d[warp] = bc; S.red_i[warp] = bk; S.red_ex[warp] = bex; S.red_ey[warp] = bey; }
                     }
+#ifdef RRTK_CTA_STATS
+                    st_c[3] += clock64() - st_t1; st_t1 = clock64();
+#endif
                     CTA_CLK(5);
                     __syncthreads();   // ---- B3
                     CTA_CLK(6); CTA_CLK(7); CTA_CLK(8);
@@ -579,19 +785,22 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         // the node is re-steered from the winner (rrt_04:1279): same edge as above
                         const double cx = bex, cy = bey, ccost = bc;
                         const bool c_is_new = (cx == nx) && (cy == ny);  // the winner's edge snapped
+                        const double new_elen = c_is_new ? S.nd[bk] : __longlong_as_double(0x7ff8000000000000ll);
                         // ---- rewire (rrt_04:1340-1373), edges.  An entry can only be re-parented if node.cost > new.cost + d
                         // (:1362); costs never increase while the apply loop runs (unless a node MOVES, handled there), so the
                         // steer + collision of an entry that fails the test now is dead work.  With a trace every edge is
                         // evaluated (the trace counts collision-free rewire edges).  Flags: 0 = not applicable, 1 = free and
-                        // ends on the node, 2 = free but the exact steer stops short of it (the node would MOVE). ----
+                        // ends on the node, 2 = free but the exact steer stops short of it (the node would MOVE).  The
+                        // entries with a flag also go to the compact list the apply phase reads. ----
 #pragma unroll 1
-                        for (int k0 = 0; k0 < count; k0 += CTA_CPR) {
-                            const int k = k0 + tid / CTA_G;
+                        for (int k0 = 0; k0 < count; k0 += CPR) {
+                            const int k = k0 + tid / G;
                             const bool valid = k < count;
                             double dk = 0.0;
                             bool want = false, blocked = false, moves = false;
+                            int i = 0;
                             if (valid) {
-                                const int i = S.near_idx[k];
+                                i = S.near_idx[k];
                                 const double2 a = s_xy[i];
                                 // hypot(node - c) == the forward edge's d when c is the sample point itself
                                 dk = c_is_new ? S.nd[k] : crm_hypot(a.x - cx, a.y - cy);
@@ -602,103 +811,50 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                 if (want && only == 0ull) {
                                     blocked = !inside_play(p, a.x, a.y);
                                 } else if (want) {
-                                    const int vv = edge_verdict_fast<true>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, CTA_G, only).v;
+                                    const int vv = edge_verdict_fast<true>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, G, only).v;
                                     if (vv < 0) {
                                         Steer st = steer(cx, cy, a.x, a.y, INF, res);
-                                        blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub)) && inside_play(p, st.ex, st.ey));
+                                        blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub, G)) && inside_play(p, st.ex, st.ey));
                                         moves = (st.ex != a.x) || (st.ey != a.y);
                                     } else {   // snapped: the edge ends on the node itself (it does not move)
                                         blocked = !(vv == 1 && inside_play(p, a.x, a.y));
                                     }
                                 }
                             }
-                            const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << CTA_G) - 1u);
-                            const unsigned mm = (__ballot_sync(FULL, moves) >> grp) & ((1u << CTA_G) - 1u);
+                            const unsigned bm = (__ballot_sync(FULL, blocked) >> grp) & ((1u << G) - 1u);
+                            const unsigned mm = (__ballot_sync(FULL, moves) >> grp) & ((1u << G) - 1u);
                             if (valid && sub == 0) {
                                 if (!c_is_new) S.nd[k] = dk;
-                                S.near_ok[k] = (want && !bm) ? (mm ? 2 : 1) : 0;
+                                const int fl = (want && !bm) ? (mm ? 2 : 1) : 0;
+                                S.near_ok[k] = fl;
+                                if (!TRACE && fl) {
+                                    const int slot = atomicAdd(&S.al_n2[cb], 1);
+                                    if (slot < CTA_AL) {
+                                        S.al_w[slot] = (fl << 30) | (k << 16) | i;
+                                        S.al_ec[slot] = ccost + dk; S.al_c0[slot] = S.s_nc[k]; S.al_dk[slot] = dk;
+                                    }
+                                    if (fl == 2) S.any_moves2[cb] = 1;
+                                }
                             }
                         }
+#ifdef RRTK_CTA_STATS
+                        st_c[4] += clock64() - st_t1;
+#endif
                         CTA_CLK(7);
                         __syncthreads();   // ---- B4
                         CTA_CLK(8);
-                        if (warp == 0) {
-                            // ---- rewire, ordered apply (rrt_04:1361-1371) + propagate_cost_to_leaves ----
-                            bool dirty = false;      // a propagate ran: node costs must be re-read
-                            int fallback_from = -1;  // >= 0: a node moved; redo entries from here serially
-#pragma unroll 1
-                            for (int b0 = 0; b0 < count && fallback_from < 0; b0 += 32) {
-                                const int k = b0 + lane;
-                                int i = -1, fl = 0;
-                                double ecost = 0.0, snc = 0.0;
-                                if (k < count) {
-                                    i = S.near_idx[k];
-                                    fl = S.near_ok[k];
-                                    snc = S.s_nc[k];
-                                    ecost = ccost + S.nd[k];
-                                }
-                                const unsigned okmask = __ballot_sync(FULL, fl != 0);
-                                t_rwok += __popc(okmask);
-                                unsigned m = __ballot_sync(FULL, fl != 0 && (snc > ecost));
-                                while (m) {  // apply in list order
-                                    const int b = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const int ii = __shfl_sync(FULL, i, b);
-                                    const double ec = __shfl_sync(FULL, ecost, b);
-                                    const double c0 = __shfl_sync(FULL, snc, b);
-                                    const int flb = __shfl_sync(FULL, fl, b);
-                                    const double ci = dirty ? cost[ii] : c0;
-                                    if (ci > ec) {
-                                        const double2 a = s_xy[ii];
-                                        double ex = a.x, ey = a.y;
-                                        if (flb == 2) {   // the exact edge stops short of the node: it moves there
-                                            const Steer st = steer(cx, cy, a.x, a.y, INF, res);
-                                            ex = st.ex; ey = st.ey;
-                                        }
-                                        const bool moved = (a.x != ex) || (a.y != ey);
-                                        __syncwarp();
-                                        if (lane == 0) {
-                                            cta_unlink(s_link, (int)s_par[ii], ii);
-                                            cta_link(s_link, n, ii);
-                                            if (moved) { s_xy[ii] = make_double2(ex, ey); xy[ii] = make_double2(ex, ey); }
-                                            cost[ii] = ec;
-                                            parent[ii] = n;
-                                            s_par[ii] = (unsigned short)n;
-                                            elen[ii] = moved ? NaN : S.nd[b0 + b];   // hypot(node - new node), what propagate would compute
-                                        }
-                                        __syncwarp();
-                                        t_rwap++;
-                                        if (can_defer && !moved && m == 0 && b0 + 32 >= count) {
-                                            // the last entry that can apply: nothing of this iteration reads a cost any more, so
-                                            // its propagate runs on warp 3 during the next iteration's scan and first edge
-                                            if (lane == 0) { S.def_root = ii; S.def_cost = ec; }
-                                        } else {
-                                            cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
-                                        }
-                                        __syncwarp();
-                                        dirty = true;
-                                        if (moved) {
-                                            // the node no longer sits where the parallel pass saw it, and the costs of its
-                                            // descendants may have gone UP: every later entry is re-evaluated from the current
-                                            // tree, one at a time
-                                            fallback_from = b0 + b + 1;
-                                            t_rwok -= __popc(okmask >> b >> 1);  // recounted below
-                                            break;
-                                        }
-                                    }
-                                }
-                            }
-                            if (fallback_from >= 0)
-                                cta_rewire_serial(p, fallback_from, count, S, s_xy, s_link, s_par, xy, cost, parent, elen, n, cx, cy, ccost, L,
-                                                  g_idx, g_cost, lane, t_rwok, t_rwap);
-                            if (lane == 0) {
-                                s_xy[n] = make_double2(cx, cy); s_par[n] = (unsigned short)best;
-                                xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best;
-                                elen[n] = c_is_new ? S.nd[bk] : NaN;   // hypot(new node - parent) as long as the node sits on the sample
-                                cta_link(s_link, best, n);
-                            }
-                        }
+                        // the apply phase is now outstanding: warp 0 runs it at the top of the next round -- beside that
+                        // iteration's stage A when no node can move (a moved node changes what the scan reads)
+                        P.cx = cx; P.cy = cy; P.ccost = ccost; P.new_elen = new_elen;
+                        P.n = n; P.best = best; P.count = count; P.cb = cb; P.c_is_new = c_is_new;
+                        P.al_n = TRACE ? 0 : S.al_n2[cb];
+                        P.compact = !TRACE && P.al_n <= CTA_AL;
+                        pending = true;
+                        overlap = can_overlap && P.compact && S.any_moves2[cb] == 0 && it + 1 < p.max_iter;
                         t_status = 3; t_par = best;
+#ifdef RRTK_CTA_STATS
+                        st_pend++; st_ov += overlap ? 1 : 0; st_big += P.compact ? 0 : 1; st_moves += S.any_moves2[cb] ? 1 : 0;
+#endif
                     } else {
                         if (tid == 0) {
                             const double2 f0 = s_xy[ni];
@@ -709,58 +865,33 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             cta_link(s_link, ni, n);
                         }
                         t_status = 2; t_par = ni;
+                        appended = true;
                     }
                     n++;
                 }
             }
-            CTA_CLK(9);
+#ifdef RRTK_CTA_STATS
+            st_cat = (ov ? 0 : 2) + (pending || appended ? 0 : 1);
+#endif
 #ifdef RRTK_CTA_PROFILE
-            if (TRACE && tid == 0) {   // scan | B1 | first edge | B2 | choose_parent | B3 | rewire edges | B4 ; apply + append in [7]
+            if (TRACE && tid == 0) {   // apply of the previous iteration | scan | B1 | first edge | B2 | choose_parent | B3 | rewire edges + B4
                 int32_t *tr = trace + (size_t)it * 8;
-                tr[0] = (int)(clk[1] - clk[0]); tr[1] = (int)(clk[2] - clk[1]); tr[2] = (int)(clk[3] - clk[2]);
-                tr[3] = (int)(clk[4] - clk[3]); tr[4] = (int)(clk[5] - clk[4]); tr[5] = (int)(clk[6] - clk[5]);
-                tr[6] = (int)(clk[8] - clk[6]); tr[7] = (int)(clk[9] - clk[8]);
-            }
-#else
-            if (TRACE && tid == 0) {
-                int32_t *tr = trace + (size_t)it * 8;
-                tr[0] = ni; tr[1] = t_status; tr[2] = t_near; tr[3] = t_par; tr[4] = S.cpok;
-                tr[5] = t_rwok; tr[6] = t_rwap; tr[7] = n;
+                tr[0] = (int)(clk[9] - clk[0]); tr[1] = (int)(clk[1] - clk[9]); tr[2] = (int)(clk[2] - clk[1]);
+                tr[3] = (int)(clk[3] - clk[2]); tr[4] = (int)(clk[4] - clk[3]); tr[5] = (int)(clk[5] - clk[4]);
+                tr[6] = (int)(clk[6] - clk[5]); tr[7] = (int)(clk[8] - clk[6]);
             }
 #endif
-            // ---- goal tests, by warp 0 (it wrote the last node itself) ----
-            if (warp == 0 && !done) {
-                __syncwarp();
-                if (RRT_ONLY) {
-                    // goal test on the last node (rrt_01:90-96)
-                    const double2 last = s_xy[n - 1];
-                    if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
-                        ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
-                        Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
-                        if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane) && lane == 0) { S.gi = n - 1; S.done = 1; }
-                    }
-                } else if (!p.search_until_max_iter) {
-                    bool ovf = false;
-                    // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
-                    ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
-                    const int g = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
-                    if (lane == 0) {
-                        if (ovf) S.status_or |= RRTK_Q_NEAR_OVERFLOW;
-                        if (g >= 0) { S.gi = g; S.done = 1; }
-                    }
-                }
-            }
-            if (tid == 0) { S.count = 0; S.cpok = 0; }
-            if (n != n_before) r2 = r2_grown;
-            __syncthreads();   // ---- B5
-            if (S.done) { gi = S.gi; done = true; }
-            if (done) { it++; break; }
         }
+#ifdef RRTK_CTA_STATS
+        if (lane == 0) {
+            int32_t *o = trace_all + 32 * (size_t)q;
+            if (warp == 0) { o[0] = st_pend; o[1] = st_ov; o[2] = st_big; o[3] = st_moves; }
+            for (int k = 0; k < 6; k++) o[4 + 6 * warp + k] = (int)(st_c[k] >> 4);
+            if (warp == 0) for (int k = 0; k < 4; k++) { o[28 + k] = st_rn[k] ? (int)(st_r[k] / st_rn[k]) : 0; }
+            if (warp == 1) for (int k = 0; k < 4; k++) o[28 + k] += 0;
+        }
+#endif
         status |= S.status_or;
-        if (S.def_root >= 0) {   // (uniform) the last iteration left a propagate pending
-            if (warp == CTA_W - 1) cta_propagate(S.def_root, S.def_cost, false, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
-            __syncthreads();
-        }
         if (!done && !RRT_ONLY && warp == 0) {
             bool ovf = false;
             ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[0][0], S.cull[0][1], S.cull[0][2], lane);
@@ -835,7 +966,11 @@ int launch_rrtstar_cta(const rrtk_rrtstar_params &p, const double *start_goal, c
         return set_error(RRTK_ERR_INVALID, "exec_mode = CTA needs node_cap <= 65535, near_cap <= 1024 and 22 B / node + the near list "
                                            "in 227 KB of shared memory");
     const size_t smem = nc == CTA_NC_SMALL ? cta_smem_bytes<CTA_NC_SMALL>(p.node_cap) : cta_smem_bytes<CTA_NC_LARGE>(p.node_cap);
+#ifdef RRTK_CTA_STATS
+    const cta_kernel_t kern = cta_pick(p, nc, false);   // (the plain kernel writes its pipeline counters into the trace buffer)
+#else
     const cta_kernel_t kern = cta_pick(p, nc, trace != nullptr);
+#endif
     long long grid = cta_grid(p, nc, kern, smem);
     if (grid < 1) return set_cuda_error(cudaGetLastError(), "cudaFuncSetAttribute / occupancy (rrtstar_cta_kernel)");
     if (grid > p.n_queries) grid = p.n_queries;
