@@ -65,6 +65,7 @@ struct CtaSmemT {
     double nx, ny;                   // the new node (warp 0 -> all)
     double smp[2][2];                // the sample of this iteration [it & 1] and the next (drawn one iteration ahead)
     double al_ec[CTA_AL], al_c0[CTA_AL], al_dk[CTA_AL];   // compact apply list: new cost, node cost seen, edge length
+    double p_cx, p_cy, p_ccost, p_elen;   // the outstanding apply phase (CtaPending), kept here rather than in every thread's registers
     int near_idx[NC];
     int near_ok[NC];             // unordered indices while the list is built, then the rewire flags
     int red_i[CTA_W];
@@ -73,6 +74,13 @@ struct CtaSmemT {
     int count2[2];                   // near hits of this iteration's scan [it & 1] (the other one is being reset)
     int al_n2[2], any_moves2[2];     // compact-list length / "a node would move" of this iteration's stage B [it & 1]
     int cpok, tail;
+    int p_n, p_best, p_count, p_cb, p_flags;
+    long long sob_n;                 // Sobol state of the query (only the sampling warp touches it)
+    // per-query pointers / constants used by one role only: read here at the point of use instead of being carried in
+    // every thread's registers for the whole loop (the kernel sits at the 128-register cap; what it spills goes to L2)
+    double2 *q_xy; int32_t *q_parent; double *q_elen; int *q_gidx; double *q_gcost; const double2 *q_stream;
+    int32_t *q_gcnt; uint16_t *q_glists; double q_ginv;
+    unsigned int sob_q0, sob_q1;
     int accept, near_valid, t_status;
     int done, gi, status_or, ni, leader;
     unsigned int q;
@@ -383,6 +391,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         const double NaN = __longlong_as_double(0x7ff8000000000000ll);
         grid.cnt = wsq + 4 * (size_t)p.node_cap + 4 * (size_t)((p.node_cap + 1) / 2);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
+        if (tid == 0) {
+            S.q_xy = xy; S.q_parent = parent; S.q_elen = elen; S.q_gidx = g_idx; S.q_gcost = g_cost; S.q_stream = stream;
+            S.q_gcnt = grid.cnt; S.q_glists = grid.lists; S.q_ginv = grid.inv_cell;
+        }
 
         int n = 1, status = RRTK_Q_OK, gi = -1, it = 0, it_prev = 0;
         SobolState sob;
@@ -433,6 +445,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             S.al_n2[0] = S.al_n2[1] = 0; S.any_moves2[0] = S.any_moves2[1] = 0;
         }
         sobol2(sob.n, sob.q0, sob.q1);
+        if (tid == 0) { S.sob_n = sob.n; S.sob_q0 = sob.q0; S.sob_q1 = sob.q1; }
         bool done = false;
         // the apply phase of an iteration may run beside stage A of the next one only when nothing it produces is read before
         // the next stage B: not with a goal search per iteration, not with a trace (its counters close an iteration)
@@ -442,8 +455,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         __syncthreads();   // the obstacle cells are built
         // the sampling warp draws the samples (one iteration ahead) and gathers the circles around them
         if (warp == 1 && p.max_iter > 0) {
-            const Sample s0 = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sob);
-            if (lane == 0) { S.smp[0][0] = s0.x; S.smp[0][1] = s0.y; }
+            SobolState sb;
+            sb.n = S.sob_n; sb.q0 = S.sob_q0; sb.q1 = S.sob_q1;
+            const Sample s0 = draw_sample(p, (int)q, 0, RESUME ? p.iter_offset : 0, gx, gy, stream, sb);
+            if (lane == 0) { S.smp[0][0] = s0.x; S.smp[0][1] = s0.y; S.sob_n = sb.n; S.sob_q0 = sb.q0; S.sob_q1 = sb.q1; }
             if (inside_play(p, s0.x, s0.y)) {
                 const ObsList L0 = cull_obstacles_grid(grid, obs, n_obs, s0.x, s0.y, reach, S.cull[0][0], S.cull[0][1],
                                                        S.cull[0][2], lane);
@@ -452,10 +467,13 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         }
         __syncthreads();
 
-        CtaPending P;                                   // the outstanding apply phase (valid while `pending`)
-        P.cx = P.cy = P.ccost = P.new_elen = 0.0;
-        P.n = P.best = P.count = P.al_n = P.cb = 0;
-        P.compact = P.c_is_new = false;
+        // the obstacle cell grid, rebuilt from the parameter block + shared memory where it is used
+        auto mk_grid = [&]() {
+            ObsGrid g;
+            g.nx = p.grid_nx; g.ny = p.grid_ny; g.x0 = p.grid_x0; g.y0 = p.grid_y0; g.cell = p.grid_cell;
+            g.inv_cell = S.q_ginv; g.cnt = S.q_gcnt; g.lists = S.q_glists;
+            return g;
+        };
         bool pending = false, overlap = false, appended = false;
 #ifdef RRTK_CTA_STATS
         int st_ov = 0, st_pend = 0, st_big = 0, st_moves = 0;
@@ -477,8 +495,14 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             // ======== close iteration it - 1: its apply phase (warp 0), its trace row, the goal tests ========
             const bool ov = pending && overlap;           // ... while the other warps already run stage A of iteration it
             if (it > 0) {
-                if (pending && warp == 0)
-                    cta_apply<TRACE>(p, P, S, s_xy, s_link, s_par, xy, cost, parent, elen, obs, n_obs, g_idx, g_cost, lane, t_rwok, t_rwap);
+                if (pending && warp == 0) {
+                    CtaPending P;
+                    P.cx = S.p_cx; P.cy = S.p_cy; P.ccost = S.p_ccost; P.new_elen = S.p_elen;
+                    P.n = S.p_n; P.best = S.p_best; P.count = S.p_count; P.cb = S.p_cb;
+                    P.al_n = TRACE ? 0 : S.al_n2[P.cb];
+                    P.compact = !TRACE && P.al_n <= CTA_AL; P.c_is_new = (S.p_flags & 2) != 0;
+                    cta_apply<TRACE>(p, P, S, s_xy, s_link, s_par, S.q_xy, cost, S.q_parent, S.q_elen, obs, n_obs, S.q_gidx, S.q_gcost, lane, t_rwok, t_rwap);
+                }
                 if (TRACE && tid == 0) {
 #ifndef RRTK_CTA_PROFILE
                     int32_t *tr = trace + (size_t)(it - 1) * 8;
@@ -547,8 +571,8 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         if (slot < near_cap) { S.near_ok[slot] = i; S.s_nc[slot] = d; }
                     }
                 }
-                if (ov && scan_t0 == 0) {   // the node the outstanding apply phase appends: index n - 1 at (P.cx, P.cy)
-                    const double ddx = P.cx - rx, ddy = P.cy - ry;
+                if (ov && scan_t0 == 0) {   // the node the outstanding apply phase appends: index n - 1 at (S.p_cx, S.p_cy)
+                    const double ddx = S.p_cx - rx, ddy = S.p_cy - ry;
                     const double d = ddx * ddx + ddy * ddy;
                     if (d < bd) { bd = d; bi = n - 1; }
                     if (d <= r2) {
@@ -579,7 +603,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             if (r_first) {
                 // ---- steer towards the sample (rrt_04:1051-1052).  Fast form: if the edge certainly snaps onto the sample the
                 // new node IS the sample and only the collision verdict is needed; otherwise the exact steer runs ----
-                const double2 from = (ov && ni == n - 1) ? make_double2(P.cx, P.cy) : s_xy[ni];
+                const double2 from = (ov && ni == n - 1) ? make_double2(S.p_cx, S.p_cy) : s_xy[ni];
                 int f_status = 0;
                 bool accept = false, near_valid = false;
                 double nx = rx, ny = ry;
@@ -616,7 +640,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     if (inside_play(p, nx, ny)) {
                         f_status = 1;
                         // (the list prefetched for the sample only holds if the node landed on it)
-                        L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
+                        L = cull_obstacles_grid(mk_grid(), obs, n_obs, nx, ny, reach, S.cull[cb][0], S.cull[cb][1], S.cull[cb][2], lane);
                         if (lane == 0) { S.cull_m[cb] = L.m; S.cull_glob[cb] = L.stride == 4 ? 1 : 0; }
                         accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
                     }
@@ -633,10 +657,12 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             } else if (r_samp) {
                 // ---- the NEXT sample and the circles around it (consumed by iteration it + 1 when its node lands on the sample) ----
                 if (it + 1 < p.max_iter) {
-                    const Sample sn = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, stream, sob);
-                    if (lane == 0) { S.smp[cb ^ 1][0] = sn.x; S.smp[cb ^ 1][1] = sn.y; }
+                    SobolState sb;
+                    sb.n = S.sob_n; sb.q0 = S.sob_q0; sb.q1 = S.sob_q1;
+                    const Sample sn = draw_sample(p, (int)q, it + 1, RESUME ? it + 1 + p.iter_offset : it + 1, gx, gy, S.q_stream, sb);
+                    if (lane == 0) { S.smp[cb ^ 1][0] = sn.x; S.smp[cb ^ 1][1] = sn.y; S.sob_n = sb.n; S.sob_q0 = sb.q0; S.sob_q1 = sb.q1; }
                     if (inside_play(p, sn.x, sn.y)) {
-                        const ObsList Ln = cull_obstacles_grid(grid, obs, n_obs, sn.x, sn.y, reach, S.cull[cb ^ 1][0],
+                        const ObsList Ln = cull_obstacles_grid(mk_grid(), obs, n_obs, sn.x, sn.y, reach, S.cull[cb ^ 1][0],
                                                                S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
                         if (lane == 0) { S.cull_m[cb ^ 1] = Ln.m; S.cull_glob[cb ^ 1] = Ln.stride == 4 ? 1 : 0; }
                     }
@@ -670,7 +696,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
             if (accept && RRT_ONLY) {
                 if (tid == 0) {
                     s_xy[n] = make_double2(nx, ny); s_par[n] = (unsigned short)ni;
-                    xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni;
+                    S.q_xy[n] = make_double2(nx, ny); cost[n] = 0.0; S.q_parent[n] = ni;
                 }
                 t_status = 2; t_par = ni;
                 n++;
@@ -786,6 +812,10 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         const double cx = bex, cy = bey, ccost = bc;
                         const bool c_is_new = (cx == nx) && (cy == ny);  // the winner's edge snapped
                         const double new_elen = c_is_new ? S.nd[bk] : __longlong_as_double(0x7ff8000000000000ll);
+                        if (tid == 0) {   // the outstanding apply phase (read after B4: by warp 0, and by the next stage A for the node)
+                            S.p_cx = cx; S.p_cy = cy; S.p_ccost = ccost; S.p_elen = new_elen;
+                            S.p_n = n; S.p_best = best; S.p_count = count; S.p_cb = cb; S.p_flags = c_is_new ? 2 : 0;
+                        }
                         // ---- rewire (rrt_04:1340-1373), edges.  An entry can only be re-parented if node.cost > new.cost + d
                         // (:1362); costs never increase while the apply loop runs (unless a node MOVES, handled there), so the
                         // steer + collision of an entry that fails the test now is dead work.  With a trace every edge is
@@ -845,15 +875,13 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         CTA_CLK(8);
                         // the apply phase is now outstanding: warp 0 runs it at the top of the next round -- beside that
                         // iteration's stage A when no node can move (a moved node changes what the scan reads)
-                        P.cx = cx; P.cy = cy; P.ccost = ccost; P.new_elen = new_elen;
-                        P.n = n; P.best = best; P.count = count; P.cb = cb; P.c_is_new = c_is_new;
-                        P.al_n = TRACE ? 0 : S.al_n2[cb];
-                        P.compact = !TRACE && P.al_n <= CTA_AL;
+                        const int al_n = TRACE ? 0 : S.al_n2[cb];
+                        const bool compact = !TRACE && al_n <= CTA_AL;
                         pending = true;
-                        overlap = can_overlap && P.compact && S.any_moves2[cb] == 0 && it + 1 < p.max_iter;
+                        overlap = can_overlap && compact && S.any_moves2[cb] == 0 && it + 1 < p.max_iter;
                         t_status = 3; t_par = best;
 #ifdef RRTK_CTA_STATS
-                        st_pend++; st_ov += overlap ? 1 : 0; st_big += P.compact ? 0 : 1; st_moves += S.any_moves2[cb] ? 1 : 0;
+                        st_pend++; st_ov += overlap ? 1 : 0; st_big += compact ? 0 : 1; st_moves += S.any_moves2[cb] ? 1 : 0;
 #endif
                     } else {
                         if (tid == 0) {
@@ -861,7 +889,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             const double nlen = crm_hypot(nx - f0.x, ny - f0.y);
                             const double ncost = cost[ni] + nlen;
                             s_xy[n] = make_double2(nx, ny); s_par[n] = (unsigned short)ni;
-                            xy[n] = make_double2(nx, ny); cost[n] = ncost; parent[n] = ni; elen[n] = nlen;
+                            S.q_xy[n] = make_double2(nx, ny); cost[n] = ncost; S.q_parent[n] = ni; S.q_elen[n] = nlen;
                             cta_link(s_link, ni, n);
                         }
                         t_status = 2; t_par = ni;
