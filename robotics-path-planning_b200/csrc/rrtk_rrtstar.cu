@@ -64,10 +64,10 @@ __device__ __noinline__ int near_scan(const double2 *xy, int n, double cx, doubl
 
 // rewire entries [from, count) one at a time against the current tree (after a re-parented node MOVED, rrt_04:1365-1371:
 // the parallel pass's view of positions and costs is stale).  Out of line: rare.
-__device__ __noinline__ void rewire_serial(const rrtk_rrtstar_params &p, int from, int count, const int *near_idx, double2 *xy,
+__device__ __noinline__ void rewire_serial(const PlanConsts p, int from, int count, const int *near_idx, double2 *xy,
                                           double *cost, int32_t *parent, int4 *links, double *elen, int n, double cx, double cy,
                                           double ccost, const ObsList &L, int *qtail, int lane, int &t_rwok, int &t_rwap) {
-    const double res = p.path_resolution;
+    const double res = p.res;
     for (int k = from; k < count; k++) {
         const int i = near_idx[k];
         const double2 a = xy[i];
@@ -101,7 +101,15 @@ struct WarpSmem {
     // obstacles near the new node of the current iteration (re-used for the goal by best_goal)
     double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];
     int qtail;      // frontier length of propagate_lists
-    int pad_[3];
+    // per-query values used once or twice per iteration: read here at the point of use instead of being carried in registers
+    // through the whole loop (the kernel sits at the 128-register cap and was spilling ~250 B per thread)
+    unsigned int sob_q0, sob_q1;
+    long long sob_n;
+    const double2 *q_stream;
+    int32_t *q_gcnt;
+    uint16_t *q_glists;
+    double q_ginv;
+    double *q_elen;
 };
 
 // layout of the dynamic shared memory of one warp:
@@ -173,6 +181,7 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         grid.cell = p.grid_cell; grid.inv_cell = grid_cells > 0 ? 1.0 / p.grid_cell : 0.0;
         grid.cnt = reinterpret_cast<int32_t *>(links + p.node_cap) + 4 * (size_t)((p.node_cap + 1) / 2);
         grid.lists = reinterpret_cast<uint16_t *>(grid.cnt + grid_cells);
+        if (lane == 0) { ws->q_stream = stream; ws->q_gcnt = grid.cnt; ws->q_glists = grid.lists; ws->q_ginv = grid.inv_cell; ws->q_elen = elen; }
         // every path point of an iteration's edges lies within `reach` of its new node (a snapped first edge starts up to
         // expand_dis + res away; near nodes are within the near radius, <= expand_dis unless near_r_max says otherwise)
         const double reach = (p.near_r_max > p.expand_dis ? p.near_r_max : p.expand_dis) + res;
@@ -214,10 +223,22 @@ rrtstar_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal,
         const double goal_reach = p.expand_dis > res ? p.expand_dis : res;
         const double inv_res = 1.0 / res, q_expand = floor(p.expand_dis / res);   // steer's n_expand at full extension
         sobol2(sob.n, sob.q0, sob.q1);
+        if (lane == 0) { ws->sob_n = sob.n; ws->sob_q0 = sob.q0; ws->sob_q1 = sob.q1; }
+        __syncwarp();
         bool done = false;
+        auto mk_grid = [&]() {   // the obstacle cell grid, rebuilt from the parameter block + the warp's shared memory
+            ObsGrid g;
+            g.nx = p.grid_nx; g.ny = p.grid_ny; g.x0 = p.grid_x0; g.y0 = p.grid_y0; g.cell = p.grid_cell;
+            g.inv_cell = ws->q_ginv; g.cnt = ws->q_gcnt; g.lists = ws->q_glists;
+            return g;
+        };
 
         for (it = 0; it < p.max_iter; it++) {
-            Sample smp = draw_sample(p, (int)q, it, RESUME ? it + p.iter_offset : it, gx, gy, stream, sob);
+            SobolState sb;
+            sb.n = ws->sob_n; sb.q0 = ws->sob_q0; sb.q1 = ws->sob_q1;
+            Sample smp = draw_sample(p, (int)q, it, RESUME ? it + p.iter_offset : it, gx, gy, ws->q_stream, sb);
+            __syncwarp();
+            if (lane == 0) { ws->sob_n = sb.n; ws->sob_q0 = sb.q0; ws->sob_q1 = sb.q1; }
             const double rx = smp.x, ry = smp.y;
             // ---- get_nearest_node_index (rrt_04:1196-1202), merged with a SPECULATIVE find_near_nodes around the
             // sample: when the steered node snaps onto the sample (the common case once the tree is dense) the near
@@ -271,7 +292,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             {
                 if (snap_certain(d0, false, p.expand_dis, q_expand, res, inv_res)) {
                     if (inside_play(p, nx, ny)) {
-                        L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                        L = cull_obstacles_grid(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                         const int vl = edge_verdict_fast<false>(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
                                                                 lane, 32, ~0ull).v;
                         const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
@@ -287,7 +308,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 nx = e0.ex; ny = e0.ey;
                 if (inside_play(p, nx, ny)) {
                     t_status = 1;
-                    L = cull_obstacles_grid(grid, obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                    L = cull_obstacles_grid(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                     accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
                 }
             }
@@ -439,7 +460,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                 }
                             }
                             if (fallback_from >= 0)
-                                rewire_serial(p, fallback_from, count, near_idx, xy, cost, parent, links, elen, n, cx, cy, ccost, L,
+                                rewire_serial(plan_consts(p), fallback_from, count, near_idx, xy, cost, parent, links, elen, n, cx, cy, ccost, L,
                                               &ws->qtail, lane, t_rwok, t_rwap);
                             if (lane == 0) {
                                 xy[n] = make_double2(cx, cy); cost[n] = ccost; parent[n] = best; link_child(links, best, n);
@@ -478,7 +499,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
                 ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
                                            ws->cull_r2, lane);
-                gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
+                gi = best_goal(plan_consts(p), n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
                 if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
                 if (gi >= 0) { it++; done = true; break; }
             }
@@ -486,7 +507,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
         if (!done && !RRT_ONLY) {
             bool ovf = false;
             ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
-            gi = best_goal(p, n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
+            gi = best_goal(plan_consts(p), n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
             if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
         }
         if (lane == 0) {

@@ -199,6 +199,23 @@ static __device__ __noinline__ bool edge_free_warp(double fx, double fy, const S
     return __ballot_sync(FULL, hit) == 0u;
 }
 
+// What the out-of-line helpers need of the parameter block, BY VALUE: taking the address of the kernel parameter `p` (a
+// reference argument of a __noinline__ function) makes the compiler keep a copy of all 168 bytes in local memory and read
+// p.play_area etc. from THERE instead of the constant bank -- in the hot loop.
+struct PlanConsts {
+    double res, expand_dis, play[4];
+    int has_play;
+};
+static __device__ __forceinline__ PlanConsts plan_consts(const rrtk_rrtstar_params &p) {
+    PlanConsts c;
+    c.res = p.path_resolution; c.expand_dis = p.expand_dis; c.has_play = p.has_play_area;
+    c.play[0] = p.play_area[0]; c.play[1] = p.play_area[1]; c.play[2] = p.play_area[2]; c.play[3] = p.play_area[3];
+    return c;
+}
+static __device__ __forceinline__ bool inside_play(const PlanConsts &c, double x, double y) {
+    if (!c.has_play) return true;
+    return !(x < c.play[0] || x > c.play[1] || y < c.play[2] || y > c.play[3]);
+}
 static __device__ __forceinline__ bool inside_play(const rrtk_rrtstar_params &p, double x, double y) {
     if (!p.has_play_area) return true;  // rrt_04:1207-1208
     return !(x < p.play_area[0] || x > p.play_area[1] || y < p.play_area[2] || y > p.play_area[3]);
@@ -247,7 +264,7 @@ static __device__ RRTK_DRAW_SAMPLE_INLINE Sample draw_sample(const rrtk_rrtstar_
 }
 
 // search_best_goal_node (rrt_04:1284-1312).  Returns the goal node index or -1.  Uniform result.
-static __device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n, const double2 *xy,
+static __device__ __noinline__ int best_goal(const PlanConsts p, int n, const double2 *xy,
                                       const double *cost, double gx, double gy, const ObsList &G,
                                       int *near_idx, double *nd, int near_cap, int lane, bool &overflow) {
     // candidates: dist <= expand_dis, each mapped to the first index with the same dist
@@ -277,7 +294,7 @@ static __device__ __noinline__ int best_goal(const rrtk_rrtstar_params &p, int n
             if (nd[j] == dk) { f = j; break; }
         int i = near_idx[f];
         double2 a = xy[i];
-        Steer st = steer(a.x, a.y, gx, gy, CUDART_INF, p.path_resolution);
+        Steer st = steer(a.x, a.y, gx, gy, CUDART_INF, p.res);
         bool ok = edge_free_lane(a.x, a.y, st, gx, gy, G) && inside_play(p, st.ex, st.ey);
         if (ok) {
             double c = cost[i] + crm_hypot(a.x - gx, a.y - gy);

@@ -168,12 +168,12 @@ static __device__ __forceinline__ ObsList sub_list(const ObsList &L, int sub, in
 // rewire entries [from, count) one at a time against the current tree, by warp 0 (a re-parented node MOVED,
 // rrt_04:1365-1371: positions and costs seen by the parallel pass are stale).  Rare.
 template <class SM>
-static __device__ __noinline__ void cta_rewire_serial(const rrtk_rrtstar_params &p, int from, int count, SM &S, double2 *s_xy,
+static __device__ __noinline__ void cta_rewire_serial(const PlanConsts p, int from, int count, SM &S, double2 *s_xy,
                                                       ushort2 *s_link, unsigned short *s_par, double2 *xy, double *cost,
                                                       int32_t *parent, double *elen, int n, double cx, double cy, double ccost,
                                                       const ObsList &L, int *g_idx, double *g_cost, int lane, int &t_rwok,
                                                       int &t_rwap) {
-    const double res = p.path_resolution;
+    const double res = p.res;
     for (int k = from; k < count; k++) {
         const int i = S.near_idx[k];
         const double2 a = s_xy[i];
@@ -316,7 +316,7 @@ static __device__ __forceinline__ void cta_apply(const rrtk_rrtstar_params &p, c
         } else {
             L.ox = S.cull[P.cb][0]; L.oy = S.cull[P.cb][1]; L.r2 = S.cull[P.cb][2]; L.stride = 1; L.m = S.cull_m[P.cb];
         }
-        cta_rewire_serial(p, fallback_from, P.count, S, s_xy, s_link, s_par, xy, cost, parent, elen, n, cx, cy, ccost, L,
+        cta_rewire_serial(plan_consts(p), fallback_from, P.count, S, s_xy, s_link, s_par, xy, cost, parent, elen, n, cx, cy, ccost, L,
                           g_idx, g_cost, lane, t_rwok, t_rwap);
     }
     if (lane == 0) {
@@ -526,7 +526,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                         bool ovf = false;
                         // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
                         ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[cb ^ 1][0], S.cull[cb ^ 1][1], S.cull[cb ^ 1][2], lane);
-                        const int g = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
+                        const int g = best_goal(plan_consts(p), n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
                         if (lane == 0) {
                             if (ovf) S.status_or |= RRTK_Q_NEAR_OVERFLOW;
                             if (g >= 0) { S.gi = g; S.done = 1; }
@@ -923,7 +923,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
         if (!done && !RRT_ONLY && warp == 0) {
             bool ovf = false;
             ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, S.cull[0][0], S.cull[0][1], S.cull[0][2], lane);
-            gi = best_goal(p, n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
+            gi = best_goal(plan_consts(p), n, s_xy, cost, gx, gy, G, S.near_idx, S.nd, near_cap, lane, ovf);
             if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
         }
         if (tid == 0) {
