@@ -292,7 +292,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             {
                 if (snap_certain(d0, false, p.expand_dis, q_expand, res, inv_res)) {
                     if (inside_play(p, nx, ny)) {
-                        L = cull_obstacles_grid(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                        L = cull_obstacles_grid_mem(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                         const int vl = edge_verdict_fast<false>(from.x, from.y, rx, ry, d0, false, p.expand_dis, q_expand, res, inv_res, L,
                                                                 lane, 32, ~0ull).v;
                         const unsigned blocked = __ballot_sync(FULL, vl == 0), unsure = __ballot_sync(FULL, vl < 0);
@@ -308,7 +308,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 nx = e0.ex; ny = e0.ey;
                 if (inside_play(p, nx, ny)) {
                     t_status = 1;
-                    L = cull_obstacles_grid(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+                    L = cull_obstacles_grid_mem(mk_grid(), obs, n_obs, nx, ny, reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                     accept = edge_free_warp(from.x, from.y, e0, rx, ry, L, lane);
                 }
             }
@@ -489,7 +489,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 // goal test on the last node (rrt_01:90-96)
                 double2 last = xy[n - 1];
                 if (crm_hypot(last.x - gx, last.y - gy) <= p.expand_dis) {
-                    ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
+                    ObsList G = cull_obstacles_mem(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
                                                ws->cull_r2, lane);
                     Steer st = steer(last.x, last.y, gx, gy, p.expand_dis, res);
                     if (edge_free_warp(last.x, last.y, st, gx, gy, G, lane)) { gi = n - 1; it++; done = true; break; }
@@ -497,7 +497,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
             } else if (!p.search_until_max_iter) {
                 bool ovf = false;
                 // obstacles that can touch an edge into the goal (search_best_goal_node steers end there)
-                ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
+                ObsList G = cull_obstacles_mem(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y,
                                            ws->cull_r2, lane);
                 gi = best_goal(plan_consts(p), n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
                 if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
@@ -506,7 +506,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
         }
         if (!done && !RRT_ONLY) {
             bool ovf = false;
-            ObsList G = cull_obstacles(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
+            ObsList G = cull_obstacles_mem(obs, n_obs, gx, gy, goal_reach, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
             gi = best_goal(plan_consts(p), n, xy, cost, gx, gy, G, near_idx, nd, near_cap, lane, ovf);
             if (ovf) status |= RRTK_Q_NEAR_OVERFLOW;
         }
