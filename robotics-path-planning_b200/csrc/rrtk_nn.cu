@@ -99,33 +99,48 @@ __global__ void nearest_unpack_kernel(const unsigned long long *best, int B, int
     d2[b] = __uint_as_float((unsigned)(k >> 32));
 }
 
-// near-radius search for ONE centre: out_idx gets every i with d2 <= r2 (unordered), count in *out_n
+// near-radius search for ONE centre: out_idx gets every i with d2 <= r2 (unordered), count in *out_n.
+// Four 16-byte loads in flight per thread like nearest_kernel (one load per round left the scan at ~60 % of the HBM rate);
+// hits are rare for the radii a planner asks for, so a round first votes whether ANY lane has one and only then compacts.
 __global__ void __launch_bounds__(NN_THREADS)
 near_kernel(const float4 *__restrict__ xy2, long long n_pairs, const float2 *__restrict__ tail, long long n,
             float cx, float cy, float r2, int *__restrict__ out_idx, int cap, int *__restrict__ out_n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long rounds = (n_pairs + stride - 1) / stride;
+    const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rounds = (n_pairs + 4 * stride - 1) / (4 * stride);   // the same for every thread: the votes are warp-wide
     for (long long r = 0; r < rounds; r++) {
-        long long i = base + r * stride;
-        bool h0 = false, h1 = false;
-        if (i < n_pairs) {
-            float4 v = __ldcs(&xy2[i]);
-            float dx0 = v.x - cx, dy0 = v.y - cy, dx1 = v.z - cx, dy1 = v.w - cy;
-            h0 = fmaf(dx0, dx0, dy0 * dy0) <= r2;
-            h1 = fmaf(dx1, dx1, dy1 * dy1) <= r2;
+        const long long i0 = base + 4 * r * stride;
+        float4 v[4];
+        unsigned hits = 0u;   // bit 2u / 2u + 1: first / second node of load u
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * stride < n_pairs) v[u] = __ldcs(&xy2[i0 + u * stride]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + u * stride < n_pairs) {
+                const float dx0 = v[u].x - cx, dy0 = v[u].y - cy, dx1 = v[u].z - cx, dy1 = v[u].w - cy;
+                hits |= (fmaf(dx0, dx0, dy0 * dy0) <= r2 ? 1u : 0u) << (2 * u);
+                hits |= (fmaf(dx1, dx1, dy1 * dy1) <= r2 ? 2u : 0u) << (2 * u);
+            }
         }
-        unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-        int tot = __popc(m0) + __popc(m1);
-        if (tot) {
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(out_n, tot);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            unsigned lt = (1u << lane) - 1u;
-            int p0 = slot + __popc(m0 & lt) + __popc(m1 & lt);
-            if (h0) { if (p0 < cap) out_idx[p0] = (int)(2 * i); p0++; }
-            if (h1) { if (p0 < cap) out_idx[p0] = (int)(2 * i + 1); }
+        if (!__any_sync(0xffffffffu, hits != 0u)) continue;
+        const int mine = __popc(hits);
+        int incl = mine;   // inclusive prefix sum of the lanes' hit counts
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(out_n, tot);
+        slot = __shfl_sync(0xffffffffu, slot, 0) + incl - mine;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = i0 + u * stride;
+            if (hits & (1u << (2 * u))) { if (slot < cap) out_idx[slot] = (int)(2 * i); slot++; }
+            if (hits & (2u << (2 * u))) { if (slot < cap) out_idx[slot] = (int)(2 * i + 1); slot++; }
         }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {

@@ -14,6 +14,7 @@ from .smoothing import path_smoothing, get_path_length  # noqa: F401
 from . import closed_loop, bitstar  # noqa: F401
 from .bitstar import BITStar  # noqa: F401
 from .closed_loop import ClosedLoopRRTStar  # noqa: F401
+from .large_tree import LargeTree, RRTLarge  # noqa: F401
 
-__all__ = ["RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "RRTStarDubins", "RRTDubins", "RRTStarReedsShepp", "ClosedLoopRRTStar", "closed_loop", "BITStar", "bitstar", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "astar_torus", "astar_torus_batch", "path_smoothing", "get_path_length", "smoothing", "reeds_shepp", "reeds_shepp_path_planning", "RrtkError",
+__all__ = ["LargeTree", "RRTLarge", "RRT", "RRTStar", "Node", "AreaBounds", "InformedRRTStar", "RRTStarDubins", "RRTDubins", "RRTStarReedsShepp", "ClosedLoopRRTStar", "closed_loop", "BITStar", "bitstar", "plan_dubins_path", "dubins", "RRTStarBatch", "shard_range", "NLinkArm", "get_occupancy_grid", "get_occupancy_grids", "astar_torus", "astar_torus_batch", "path_smoothing", "get_path_length", "smoothing", "reeds_shepp", "reeds_shepp_path_planning", "RrtkError",
            "lib", "LIB_PATH"]
