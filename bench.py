@@ -475,9 +475,11 @@ def main():
         achieved = alg["flop_per_iter"] * Q * iters / (t_dev / args.steps) / 1e12 if alg["flop_per_iter"] else None
         roofline = dict(kernel="rrtstar_kernel", bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
                         frac=achieved / fp64_peak if achieved else None,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the
-                        # committed ncu capture (profiles/r1i_rrtstar_kernel_ncu_summary.txt): 5.76 + 2.40 GB
-                        traffic=8.16e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS build at the default workload
+                        # (ncu --set full, profiles/r2e_rrtstar_kernel_ncu_summary.txt: 8.168 + 2.203 GB; bench.py cannot
+                        # read hardware counters itself -- re-captured whenever the kernel changes)
+                        traffic=10.371e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
+                        traffic_source="profiles/r2e_rrtstar_kernel_ncu_summary.txt",
                         peak_source="FMA-loop probe measured in this run (rrtk_fma_peak_dev); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                         algorithmic_flop_per_iter=alg["flop_per_iter"], algorithmic_note=alg["note"],
@@ -742,6 +744,35 @@ def extras(torch, dev):
     L = _lib.lib()
     s = torch.cuda.current_stream().cuda_stream
     out = {}
+    try:   # large-tree mode (rrtk/large_tree.py): get_nearest_node_index of a 6.7e7-node tree INSIDE the planner loop
+        import rrtk
+        n0, iters = 1 << 26, 40
+        gen = torch.Generator(device=dev).manual_seed(5)
+        seed = torch.rand((n0, 2), dtype=torch.float64, device=dev, generator=gen) * 17.0 - 2.0
+        par = torch.arange(-1, n0 - 1, dtype=torch.int32, device=dev)
+        pl = rrtk.RRTLarge([0.0, 0.0], [60.0, 60.0], [(5, 5, 1), (3, 6, 2), (3, 8, 2), (7, 5, 2), (9, 5, 2)], [-2, 15], 1.0, 0.1, 5, 8,
+                           None, 0.0, capacity=n0 + iters + 1, seed_xy=seed, seed_parent=par, device=dev)
+        del seed, par
+        st = np.random.default_rng(9).uniform(-2, 15, (iters, 2))
+        pl.planning(st[:8])
+        pl.tree.time_scans = True
+        pl.tree.stats.update(scans=0, scan_ms=0.0, candidates=0, nearest_queries=0)
+        pl.max_iter = iters - 8
+        pl.planning(st[8:])
+        ts = pl.tree.stats
+        peaks = measured_peaks()
+        peak = peaks["hbm_gbs"] if peaks else 6650.0
+        gbs = 8.0 * n0 * ts["scans"] / (ts["scan_ms"] / 1e3) / 1e9
+        out["large_tree_rrt"] = dict(nodes=int(pl.tree.n), planner_iterations=iters - 8, scans=ts["scans"],
+                                     us_per_scan=1e3 * ts["scan_ms"] / ts["scans"], scan_gbs=gbs, frac_of_hbm_peak=gbs / peak,
+                                     fp64_rechecks_per_query=ts["candidates"] / max(ts["nearest_queries"], 1),
+                                     note="two streaming passes over the FP32 mirror per get_nearest_node_index (FP32 argmin, then the "
+                                          "candidates inside the rounding band), FP64 re-check; CUDA events around each pass "
+                                          "(memset + scan kernel + unpack) inside RRTLarge.planning")
+        del pl
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["large_tree_rrt"] = dict(error=repr(e))
     try:   # config 5: arm C-space grid, M = 8192, 64 obstacle sets, script arm (arm02:298-304)
         M, S = 8192, 64
         rng = np.random.default_rng(5)
