@@ -381,13 +381,13 @@ CRM_FN crm_dd crm_atan2_dd(double y, double x) {
  * atan(u) = u0 + al, al = u0 z pa + ul, pa = -1/3 + z/5 - z^2/7 + z^3/9 (|u| <= 2^-8: |al| < 2^-17 |u0|, error < 2^-68 |u0|;
  * the dropped u^11/11 < 2^-83 |u0|), then the octant reflections with pi/2, pi as (H, L) pairs, each an error-free sum
  * of the leading parts plus one rounded sum of the tails (< 2^-105).  E = 2^-62 relative to the result. */
-CRM_FN int crm_atan2_fast(double y, double x, double *out) {
-    double ax = fabs(x), ay = fabs(y);
-    int swap = ay > ax;
-    double mn = swap ? ax : ay, mx = swap ? ay : ax;
-    if (!(mx < 1e150 && mn > 1e-150)) return 0;               /* residuals would leave the normal range */
-    double t0 = mn / mx;
-    double tl = fma(-t0, mx, mn) / mx;
+/* atan(mn / mx) for 0 <= mn <= mx given as (hi, lo) pairs, as a normalised (hi, lo) pair.  One reciprocal per quotient:
+ * q0 = n * RN(1 / d) is within 2 ulp of the quotient, the residual fma(-q0, d, n) (rounded: 2^-53 of a 2^-51 term) times the
+ * reciprocal restores it to < 2^-100 relative. */
+CRM_FN crm_dd crm_atan_octant_fast(double mnh, double mnl, double mxh, double mxl, int *idx) {
+    double inv = 1.0 / mxh;
+    double t0 = mnh * inv;
+    double tl = ((fma(-t0, mxh, mnh) + mnl) - t0 * mxl) * inv;
     int i = (int)rint(t0 * 128.0);
     double u0, ul;
     if (i == 0) {
@@ -398,8 +398,9 @@ CRM_FN int crm_atan2_fast(double y, double x, double *out) {
         crm_dd p = crm_two_prod(t0, ti);
         crm_dd d = crm_fast_two_sum(1.0, p.hi);
         double dl = d.lo + (p.lo + tl * ti);
-        u0 = n.hi / d.hi;
-        ul = ((fma(-u0, d.hi, n.hi) + n.lo) - u0 * dl) / d.hi;
+        double invd = 1.0 / d.hi;
+        u0 = n.hi * invd;
+        ul = ((fma(-u0, d.hi, n.hi) + n.lo) - u0 * dl) * invd;
     }
     double z = u0 * u0;
     double pa = fma(fma(fma(1.1111111111111110e-01, z, -1.4285714285714285e-01), z, 0.2), z, -3.3333333333333331e-01);
@@ -411,18 +412,65 @@ CRM_FN int crm_atan2_fast(double y, double x, double *out) {
         a = crm_fast_two_sum(crm_atan_tab[i][0], u0);         /* atan(i/128) >= 2^-7.01 > |u0| */
         a = crm_fast_two_sum(a.hi, a.lo + (crm_atan_tab[i][1] + al));
     }
-    if (swap) {
-        crm_dd b = crm_two_sum(CRM_PIO2_H, -a.hi);
-        a = crm_fast_two_sum(b.hi, b.lo + (CRM_PIO2_L - a.lo));
-    }
-    if (x < 0.0) {
-        crm_dd b = crm_two_sum(CRM_PI_H, -a.hi);
-        a = crm_fast_two_sum(b.hi, b.lo + (CRM_PI_L - a.lo));
-    }
-    double e = fabs(a.hi) * 2.168404344971009e-19;            /* 2^-62 relative */
+    *idx = i;
+    return a;
+}
+/* pi/2 - a, pi - a for a normalised pair a in [0, pi/2] */
+CRM_FN crm_dd crm_reflect_fast(double ch, double cl, crm_dd a) {
+    crm_dd b = crm_two_sum(ch, -a.hi);
+    return crm_fast_two_sum(b.hi, b.lo + (cl - a.lo));
+}
+CRM_FN int crm_round_fast(crm_dd a, double *out) {           /* E = 2^-62 relative */
+    double e = fabs(a.hi) * 2.168404344971009e-19;
     double r1 = a.hi + (a.lo + e), r2 = a.hi + (a.lo - e);
-    if (r1 != r2) return 0;
-    *out = y < 0.0 ? -r1 : r1;
+    *out = r1;
+    return r1 == r2;
+}
+CRM_FN int crm_atan2_fast(double y, double x, double *out) {
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax, i;
+    double mn = swap ? ax : ay, mx = swap ? ay : ax;
+    if (!(mx < 1e150 && mn > 1e-150)) return 0;               /* residuals would leave the normal range */
+    crm_dd a = crm_atan_octant_fast(mn, 0.0, mx, 0.0, &i);
+    if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
+    if (x < 0.0) a = crm_reflect_fast(CRM_PI_H, CRM_PI_L, a);
+    double r;
+    if (!crm_round_fast(a, &r)) return 0;
+    *out = y < 0.0 ? -r : r;
+    return 1;
+}
+/* sqrt((1 - x)(1 + x)) for |x| < 1 as a (hi, lo) pair, relative error < 2^-100: 1 -+ x are exact two-term sums, their
+ * product in double-double, the root corrected once by its exact residual */
+CRM_FN crm_dd crm_sqrt1mx2_fast(double x) {
+    crm_dd a = crm_two_sum(1.0, -x), b = crm_two_sum(1.0, x);
+    crm_dd p = crm_two_prod(a.hi, b.hi);
+    double pl = p.lo + (a.hi * b.lo + a.lo * b.hi);
+    double s0 = sqrt(p.hi);
+    double sl = (fma(-s0, s0, p.hi) + pl) / (2.0 * s0);
+    return crm_fast_two_sum(s0, sl);
+}
+/* first phases of acos / asin for 0 < |x| < 1 (the Dubins RLR / LRL words, every Reeds-Shepp word family with an arc
+ * in the middle): the same octant core on (sqrt(1 - x^2), |x|) */
+CRM_FN int crm_acos_fast(double x, double *out) {
+    crm_dd y = crm_sqrt1mx2_fast(x);
+    double ax = fabs(x);
+    if (!(y.hi > 1e-150 && ax > 1e-150)) return 0;
+    int swap = y.hi > ax, i;
+    crm_dd a = swap ? crm_atan_octant_fast(ax, 0.0, y.hi, y.lo, &i) : crm_atan_octant_fast(y.hi, y.lo, ax, 0.0, &i);
+    if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
+    if (x < 0.0) a = crm_reflect_fast(CRM_PI_H, CRM_PI_L, a);
+    return crm_round_fast(a, out);
+}
+CRM_FN int crm_asin_fast(double x, double *out) {
+    crm_dd c = crm_sqrt1mx2_fast(x);
+    double ax = fabs(x);
+    if (!(c.hi > 1e-150 && ax > 1e-150)) return 0;
+    int swap = ax > c.hi, i;
+    crm_dd a = swap ? crm_atan_octant_fast(c.hi, c.lo, ax, 0.0, &i) : crm_atan_octant_fast(ax, 0.0, c.hi, c.lo, &i);
+    if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
+    double r;
+    if (!crm_round_fast(a, &r)) return 0;
+    *out = x < 0.0 ? -r : r;
     return 1;
 }
 #endif
@@ -513,6 +561,9 @@ CRM_NOINLINE double crm_acos(double x) {
     if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
     if (x == 1.0) return 0.0;
     if (x == -1.0) return CRM_PI_H;
+#ifdef CRM_FAST
+    { double r_; if (crm_acos_fast(x, &r_)) return r_; }
+#endif
     crm_dd a = crm_two_sum(1.0, -x), b = crm_two_sum(1.0, x); /* exact */
     crm_dd p = crm_mul(a, b);
     double s0 = sqrt(p.hi);
@@ -531,6 +582,9 @@ CRM_NOINLINE double crm_asin(double x) {
     if (!(fabs(x) <= 1.0)) return x - x == 0.0 ? (x - x) / (x - x) : x + x; /* NaN */
     if (x == 0.0) return x;
     if (fabs(x) == 1.0) return copysign(CRM_PIO2_H, x);
+#ifdef CRM_FAST
+    { double r_; if (crm_asin_fast(x, &r_)) return r_; }
+#endif
     crm_dd a = crm_two_sum(1.0, -x), b = crm_two_sum(1.0, x); /* exact */
     crm_dd p = crm_mul(a, b);
     double s0 = sqrt(p.hi);

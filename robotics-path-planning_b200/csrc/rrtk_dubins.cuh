@@ -19,10 +19,11 @@ static __device__ __forceinline__ double py_mod(double a, double b) {
     else r = copysign(0.0, b);
     return r;
 }
-// t % (2 * math.pi).  Out of line (fmod expands to a long routine and the steering code takes ~25 of these per edge); for
-// |t| < 4 pi -- every call of the planners -- fmod(t, 2 pi) is t or t -+ 2 pi, and that difference is exact (Sterbenz), so
-// the result is the one fmod gives
-static __device__ __noinline__ double mod2pi(double t) {
+// t % (2 * math.pi).  For |t| < 4 pi -- every call of the planners -- fmod(t, 2 pi) is t or t -+ 2 pi, and that difference
+// is exact (Sterbenz), so the result is the one fmod gives: a few compares inline; the fmod routine (long) stays out of
+// line for anything larger (the steering code takes ~25 of these per edge)
+static __device__ __noinline__ double mod2pi_slow(double t) { return py_mod(t, D_TWO_PI); }
+static __device__ __forceinline__ double mod2pi(double t) {
     if (t >= 0.0) {
         if (t < D_TWO_PI) return t + 0.0;                 // fmod = t; a zero result is +0.0 (-0.0 >= 0.0 lands here too)
         if (t < 2.0 * D_TWO_PI) return t - D_TWO_PI;      // exact
@@ -32,7 +33,7 @@ static __device__ __noinline__ double mod2pi(double t) {
         const double r = t + D_TWO_PI;                    // exact
         return r != 0.0 ? r + D_TWO_PI : 0.0;
     }
-    return py_mod(t, D_TWO_PI);
+    return mod2pi_slow(t);
 }
 static __device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
 
