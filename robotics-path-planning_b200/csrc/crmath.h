@@ -384,7 +384,7 @@ CRM_FN crm_dd crm_atan2_dd(double y, double x) {
 /* atan(mn / mx) for 0 <= mn <= mx given as (hi, lo) pairs, as a normalised (hi, lo) pair.  One reciprocal per quotient:
  * q0 = n * RN(1 / d) is within 2 ulp of the quotient, the residual fma(-q0, d, n) (rounded: 2^-53 of a 2^-51 term) times the
  * reciprocal restores it to < 2^-100 relative. */
-CRM_FN crm_dd crm_atan_octant_fast(double mnh, double mnl, double mxh, double mxl, int *idx) {
+CRM_NOINLINE crm_dd crm_atan_octant_fast(double mnh, double mnl, double mxh, double mxl) {
     double inv = 1.0 / mxh;
     double t0 = mnh * inv;
     double tl = ((fma(-t0, mxh, mnh) + mnl) - t0 * mxl) * inv;
@@ -412,7 +412,6 @@ CRM_FN crm_dd crm_atan_octant_fast(double mnh, double mnl, double mxh, double mx
         a = crm_fast_two_sum(crm_atan_tab[i][0], u0);         /* atan(i/128) >= 2^-7.01 > |u0| */
         a = crm_fast_two_sum(a.hi, a.lo + (crm_atan_tab[i][1] + al));
     }
-    *idx = i;
     return a;
 }
 /* pi/2 - a, pi - a for a normalised pair a in [0, pi/2] */
@@ -428,10 +427,10 @@ CRM_FN int crm_round_fast(crm_dd a, double *out) {           /* E = 2^-62 relati
 }
 CRM_FN int crm_atan2_fast(double y, double x, double *out) {
     double ax = fabs(x), ay = fabs(y);
-    int swap = ay > ax, i;
+    int swap = ay > ax;
     double mn = swap ? ax : ay, mx = swap ? ay : ax;
     if (!(mx < 1e150 && mn > 1e-150)) return 0;               /* residuals would leave the normal range */
-    crm_dd a = crm_atan_octant_fast(mn, 0.0, mx, 0.0, &i);
+    crm_dd a = crm_atan_octant_fast(mn, 0.0, mx, 0.0);
     if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
     if (x < 0.0) a = crm_reflect_fast(CRM_PI_H, CRM_PI_L, a);
     double r;
@@ -455,8 +454,8 @@ CRM_FN int crm_acos_fast(double x, double *out) {
     crm_dd y = crm_sqrt1mx2_fast(x);
     double ax = fabs(x);
     if (!(y.hi > 1e-150 && ax > 1e-150)) return 0;
-    int swap = y.hi > ax, i;
-    crm_dd a = swap ? crm_atan_octant_fast(ax, 0.0, y.hi, y.lo, &i) : crm_atan_octant_fast(y.hi, y.lo, ax, 0.0, &i);
+    int swap = y.hi > ax;
+    crm_dd a = swap ? crm_atan_octant_fast(ax, 0.0, y.hi, y.lo) : crm_atan_octant_fast(y.hi, y.lo, ax, 0.0);
     if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
     if (x < 0.0) a = crm_reflect_fast(CRM_PI_H, CRM_PI_L, a);
     return crm_round_fast(a, out);
@@ -465,8 +464,8 @@ CRM_FN int crm_asin_fast(double x, double *out) {
     crm_dd c = crm_sqrt1mx2_fast(x);
     double ax = fabs(x);
     if (!(c.hi > 1e-150 && ax > 1e-150)) return 0;
-    int swap = ax > c.hi, i;
-    crm_dd a = swap ? crm_atan_octant_fast(c.hi, c.lo, ax, 0.0, &i) : crm_atan_octant_fast(ax, 0.0, c.hi, c.lo, &i);
+    int swap = ax > c.hi;
+    crm_dd a = swap ? crm_atan_octant_fast(c.hi, c.lo, ax, 0.0) : crm_atan_octant_fast(ax, 0.0, c.hi, c.lo);
     if (swap) a = crm_reflect_fast(CRM_PIO2_H, CRM_PIO2_L, a);
     double r;
     if (!crm_round_fast(a, &r)) return 0;

@@ -22,17 +22,18 @@ static __device__ __forceinline__ double py_mod(double a, double b) {
 // t % (2 * math.pi).  For |t| < 4 pi -- every call of the planners -- fmod(t, 2 pi) is t or t -+ 2 pi, and that difference
 // is exact (Sterbenz), so the result is the one fmod gives: a few compares inline; the fmod routine (long) stays out of
 // line for anything larger (the steering code takes ~25 of these per edge)
-static __device__ __noinline__ double mod2pi_slow(double t) { return py_mod(t, D_TWO_PI); }
-static __device__ __forceinline__ double mod2pi(double t) {
+static __device__ __noinline__ double mod2pi_slow(double t) {
     if (t >= 0.0) {
-        if (t < D_TWO_PI) return t + 0.0;                 // fmod = t; a zero result is +0.0 (-0.0 >= 0.0 lands here too)
-        if (t < 2.0 * D_TWO_PI) return t - D_TWO_PI;      // exact
-    } else if (t > -D_TWO_PI) {
-        return t + D_TWO_PI;                              // fmod = t (negative, non-zero): r += b, one rounding
+        if (t < 2.0 * D_TWO_PI) return t - D_TWO_PI;      // [2 pi, 4 pi): exact
     } else if (t > -2.0 * D_TWO_PI) {
-        const double r = t + D_TWO_PI;                    // exact
+        const double r = t + D_TWO_PI;                    // (-4 pi, -2 pi]: exact
         return r != 0.0 ? r + D_TWO_PI : 0.0;
     }
+    return py_mod(t, D_TWO_PI);
+}
+static __device__ __forceinline__ double mod2pi(double t) {
+    if (t >= 0.0 && t < D_TWO_PI) return t + 0.0;         // fmod = t; a zero result is +0.0 (-0.0 >= 0.0 lands here too)
+    if (t < 0.0 && t > -D_TWO_PI) return t + D_TWO_PI;    // fmod = t (negative, non-zero): r += b, one rounding
     return mod2pi_slow(t);
 }
 static __device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
@@ -121,23 +122,8 @@ static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta
     }
 }
 
-// The reference's choice among the six words (first minimum of the summed lengths in _PATH_TYPE_MAP order, rrt_05:1088-1094)
-// by ONE lane.  (Ruling words out with approximate lengths first -- dubins_word<false> -- was tried: the lanes of a warp
-// then disagree on which words to evaluate exactly and the warp runs all six anyway, plus the approximations: 63 -> 87 ms
-// at config 4.)  Returns the word index or -1, its three lengths in len.
-static __device__ __forceinline__ int dubins_best_word(double alpha, double beta, double d, const DubTrig &trig, double *len) {
-    double best = CUDART_INF;
-    int bi = -1;
-#pragma unroll 1
-    for (int k = 0; k < 6; k++) {
-        double w[3];
-        if (!dubins_word<true>(k, alpha, beta, d, trig, w)) continue;
-        const double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
-        if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
-    }
-    return bi;
-}
-
+// (Ruling words out with approximate lengths first -- dubins_word<false> -- was tried: the lanes of a warp then disagree on
+// which words to evaluate exactly and the warp runs all six anyway, plus the approximations: 63 -> 87 ms at config 4.)
 // segment type of word `mode` at position k: 0 = L, 1 = S, 2 = R
 static __device__ __forceinline__ int seg_type(int mode, int k) {
     // LSL RSR LSR RSL RLR LRL
@@ -241,106 +227,19 @@ struct DubEdge {
     bool free_;           // check_collision over the course points (rrt_05:1625-1638)
 };
 
-// One Dubins edge evaluated by ONE lane: plan_dubins_path + sampled collision test.
+// One Dubins edge: plan_dubins_path + sampled collision test.  ONE out-of-line body serves both ways the planners evaluate
+// an edge (the kernels are bound by instruction fetch at 7 warps per SM: two 20 KB copies of this code were half of the hot
+// footprint):
+//   warp = false  the calling lane evaluates the edge alone (choose_parent / rewire: one candidate per lane);
+//   warp = true   the whole warp evaluates ONE edge (uniform arguments, uniform result): the six words on six lanes, the
+//                 circles of the segment cull and the interior points of a segment spread over the lanes (each lane reaches
+//                 its points by the reference's repeated `cur += step`).  Used where the planner has one edge to evaluate
+//                 (first steer, re-planned rewire edges, try_goal_path).
 // obs rows: x, y, size + robot_radius, (size + robot_radius)**2
-static __device__ __noinline__ DubEdge dubins_edge_lane(double s_x, double s_y, double s_yaw, double g_x, double g_y,
-                                                        double g_yaw, double kappa, double step,
-                                                        const double4 *obs, int n_obs) {
-    DubEdge e;
-    e.ex = e.ey = e.eyaw = 0.0;
-    e.npts = 0;
-    e.free_ = false;
-    double c, s;
-    rot2d(s_yaw, &c, &s);
-    const double vx = g_x - s_x, vy = g_y - s_y;
-    const double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s);
-    const double lgyaw = g_yaw - s_yaw;
-    const double d = crm_hypot(lgx, lgy) * kappa;
-    const double theta = mod2pi(crm_atan2(lgy, lgx));
-    const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
-    const DubTrig trig = dubins_trig(alpha, beta);
-    double len[3] = {0.0, 0.0, 0.0};
-    const int bi = dubins_best_word(alpha, beta, d, trig, len);
-    if (bi < 0) return e;
-    // rot_mat_2d(-s_yaw): the correctly rounded sin / cos are odd / even bit for bit, so c2 = c and s2 = -s exactly
-    const double c2 = c, s2 = -s;
-    const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
-    bool hit = false;
-    double lx = 0.0, ly = 0.0, lyaw = 0.0;
-    int np = 0;
-    auto emit = [&](double px, double py) {
-        const double wx = fma(py, s2, px * c2) + s_x;
-        const double wy = fma(py, c2, px * -s2) + s_y;
-        for (int o = 0; o < n_obs && !hit; o++) {
-            const double4 ob = obs[o];
-            const double dx = ob.x - wx, dy = ob.y - wy;
-            if (dx * dx + dy * dy <= ob.w) hit = true;
-        }
-        np++;
-    };
-    emit(lx, ly);
-#pragma unroll 1
-    for (int k = 0; k < 3 && !hit; k++) {
-        const double length = len[k];
-        if (length == 0.0) continue;
-        const int type = seg_type(bi, k);
-        const double ox = lx, oy = ly, oyaw = lyaw;
-        double so = 0.0, co = 1.0;                    // sin / cos(0) of the first segment's origin
-        if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
-        const double sm = -so, cm = co;               // sin / cos(-oyaw), exactly (see c2, s2)
-        interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);   // the segment's end point: always exact
-        emit(lx, ly);
-        if (hit) break;
-        bool near = !filt;
-        for (int o = 0; o < n_obs && !near; o++) {
-            const double4 ob = obs[o];
-            const double ux = ob.x - s_x, uy = ob.y - s_y;
-            near = circle_near_segment(type, kappa, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
-        }
-        if (!near) { np++; continue; }          // (np only has to tell "more than one point")
-        double cur = step;
-#pragma unroll 1
-        while (fabs(cur + step) <= fabs(length)) {
-            int v = -1;
-            if (filt && type != 1) {
-                double x, y;
-                arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
-                v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
-            }
-            if (v < 0) {
-                double x, y, yaw;
-                interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
-                emit(x, y);
-            } else {
-                hit = v == 1;
-                np++;
-            }
-            if (hit) break;
-            cur += step;
-        }
-    }
-    if (hit) {
-        // blocked: the callers only ask whether steer returned a node at all (len(px) > 1, i.e. some segment is non-zero);
-        // the rest of the course, its point count and its end pose are never read for a blocked edge
-        e.npts = (len[0] != 0.0 || len[1] != 0.0 || len[2] != 0.0) ? 2 : 1;
-        return e;
-    }
-    e.npts = np;
-    e.free_ = !hit;
-    e.ex = fma(ly, s2, lx * c2) + s_x;
-    e.ey = fma(ly, c2, lx * -s2) + s_y;
-    e.eyaw = angle_mod_pi(lyaw + s_yaw);
-    return e;
-}
-
-// The same edge evaluated by the WHOLE warp (uniform arguments, uniform result): the six words on six lanes, the interior
-// points of each segment spread over the lanes (each lane reaches its first distance by the reference's repeated
-// `cur += step`), as dubins_steer_kernel does.  Used where the planner has one edge to evaluate (first steer, re-planned
-// rewire edges).
 // lengths_out (optional): the three course lengths plan_dubins_path returns (word lengths / curvature, rrt_05:1095).
-static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, double s_yaw, double g_x, double g_y,
-                                                        double g_yaw, double kappa, double step, const double4 *obs,
-                                                        int n_obs, int lane, double *lengths_out = nullptr) {
+static __device__ __noinline__ DubEdge dubins_edge(double s_x, double s_y, double s_yaw, double g_x, double g_y, double g_yaw,
+                                                   double kappa, double step, const double4 *obs, int n_obs, bool warp, int lane,
+                                                   double *lengths_out) {
     DubEdge e;
     e.ex = e.ey = e.eyaw = 0.0;
     e.npts = 0;
@@ -353,26 +252,38 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     const double d = crm_hypot(lgx, lgy) * kappa;
     const double theta = mod2pi(crm_atan2(lgy, lgx));
     const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
-    double w[3] = {0.0, 0.0, 0.0};
-    double cost = CUDART_INF;
-    int bi = 0x7fffffff;
     const DubTrig trig = dubins_trig(alpha, beta);
-    if (lane < 6 && dubins_word<true>(lane, alpha, beta, d, trig, w)) {
-        cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
-        bi = lane;
+    // first minimum of the summed lengths in _PATH_TYPE_MAP order (`best > cost` over k = 0..5, rrt_05:1088-1094)
+    double len[3] = {0.0, 0.0, 0.0}, best = CUDART_INF;
+    int bi = 0x7fffffff;
+    const int k0 = warp ? lane : 0, k1 = warp ? (lane < 6 ? lane + 1 : lane) : 6;
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
+        double w[3];
+        if (!dubins_word<true>(k, alpha, beta, d, trig, w)) continue;
+        const double cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
+        if (best > cost) { best = cost; bi = k; len[0] = w[0]; len[1] = w[1]; len[2] = w[2]; }
     }
-    warp_argmin(cost, bi);   // first minimum in _PATH_TYPE_MAP order, like `best > cost` over k = 0..5
-    if (bi == 0x7fffffff) return e;
-    double len[3];
+    if (warp) {
+        warp_argmin(best, bi);
+        if (bi != 0x7fffffff) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, w[k], bi);
+            for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, len[k], bi);
+        }
+    }
+    if (bi == 0x7fffffff) return e;
     if (lengths_out) {
 #pragma unroll
         for (int k = 0; k < 3; k++) lengths_out[k] = len[k] / kappa;
     }
-    const double c2 = c, s2 = -s;   // rot_mat_2d(-s_yaw): sin / cos correctly rounded are odd / even bit for bit
+    // rot_mat_2d(-s_yaw): the correctly rounded sin / cos are odd / even bit for bit, so c2 = c and s2 = -s exactly
+    const double c2 = c, s2 = -s;
     const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
+    const bool tester = !warp || lane == 0;          // who tests the segment end points
+    const int jstep = warp ? 32 : 1;
     bool hit = false;
+    double lx = 0.0, ly = 0.0, lyaw = 0.0;
+    int np = 1;
     auto test = [&](double px, double py) {
         const double wx = fma(py, s2, px * c2) + s_x;
         const double wy = fma(py, c2, px * -s2) + s_y;
@@ -382,9 +293,7 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
             if (dx * dx + dy * dy <= ob.w) hit = true;
         }
     };
-    double lx = 0.0, ly = 0.0, lyaw = 0.0;
-    int np = 1;
-    if (lane == 0) test(lx, ly);
+    if (tester) test(lx, ly);
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
         const double length = len[k];
@@ -395,24 +304,20 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
         if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
         const double sm = -so, cm = co;               // sin / cos(-oyaw), exactly (see c2, s2)
         interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);   // the segment's end point: always exact
-        if (lane == 0) test(lx, ly);
-        // segment-level cull (circle_near_segment): the lanes split the circles
+        if (tester) test(lx, ly);
+        // segment-level cull (circle_near_segment); in warp mode the lanes split the circles
         bool near = !filt;
-        for (int o = lane; o < n_obs && !near; o += 32) {
+        for (int o = warp ? lane : 0; o < n_obs && !near; o += jstep) {
             const double4 ob = obs[o];
             const double ux = ob.x - s_x, uy = ob.y - s_y;
             near = circle_near_segment(type, kappa, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
         }
-        if (__any_sync(FULL, near)) {
-            int cnt = 0;
-            {
-                double cur = step;
-                while (fabs(cur + step) <= fabs(length)) { cnt++; cur += step; }
-            }
+        if (warp) near = __any_sync(FULL, near);
+        if (near && !hit) {
             double cur = step;
-            for (int t = 0; t < lane; t++) cur += step;
+            for (int t = 0; t < (warp ? lane : 0); t++) cur += step;
 #pragma unroll 1
-            for (int j = lane; j < cnt; j += 32) {
+            while (fabs(cur + step) <= fabs(length)) {
                 int v = -1;
                 if (filt && type != 1) {
                     double x, y;
@@ -426,18 +331,19 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
                 } else if (v == 1) {
                     hit = true;
                 }
+                if (hit) break;
 #pragma unroll 1
-                for (int t = 0; t < 32; t++) cur += step;
+                for (int t = 0; t < jstep; t++) cur += step;
             }
-            np += cnt;
         }
-        np += 1;                              // (np only has to tell "more than one point" when a segment was culled)
-        if (__any_sync(FULL, hit)) {   // blocked: see dubins_edge_lane
-            e.npts = 2;
-            return e;
-        }
+        np++;                                         // (np only has to tell "more than one point")
+        if (warp) hit = __any_sync(FULL, hit);
+        if (hit) break;
     }
-    if (__any_sync(FULL, hit)) {       // only the origin can have been tested here
+    if (warp) hit = __any_sync(FULL, hit);            // (only the origin can be pending here)
+    if (hit) {
+        // blocked: the callers only ask whether steer returned a node at all (len(px) > 1, i.e. some segment is non-zero);
+        // the rest of the course, its point count and its end pose are never read for a blocked edge
         e.npts = (len[0] != 0.0 || len[1] != 0.0 || len[2] != 0.0) ? 2 : 1;
         return e;
     }
@@ -447,6 +353,15 @@ static __device__ __noinline__ DubEdge dubins_edge_warp(double s_x, double s_y, 
     e.ey = fma(ly, c2, lx * -s2) + s_y;
     e.eyaw = angle_mod_pi(lyaw + s_yaw);
     return e;
+}
+static __device__ __forceinline__ DubEdge dubins_edge_lane(double s_x, double s_y, double s_yaw, double g_x, double g_y, double g_yaw,
+                                                           double kappa, double step, const double4 *obs, int n_obs) {
+    return dubins_edge(s_x, s_y, s_yaw, g_x, g_y, g_yaw, kappa, step, obs, n_obs, false, 0, nullptr);
+}
+static __device__ __forceinline__ DubEdge dubins_edge_warp(double s_x, double s_y, double s_yaw, double g_x, double g_y, double g_yaw,
+                                                           double kappa, double step, const double4 *obs, int n_obs, int lane,
+                                                           double *lengths_out = nullptr) {
+    return dubins_edge(s_x, s_y, s_yaw, g_x, g_y, g_yaw, kappa, step, obs, n_obs, true, lane, lengths_out);
 }
 
 }  // namespace rrtk
