@@ -216,9 +216,10 @@ __device__ __forceinline__ int warp_argmin_lane(double v, int i) {
 // counter; G threads read the records back and reduce.  Measured on B200 (tools/micro/sync_costs.cu): this counter
 // form costs ~2200 cycles at G = 148, an all-to-all poll of self-tagged records ~2000-4900 depending on the piece
 // count, and the latter collapses under the G^2 polling traffic once real work runs beside it.
-__device__ __noinline__ Winner exchange(TreeSmem &S, const TreeWs &ws, unsigned &seq, int G) {
+// (rec / bar / seq by value: a reference to the workspace struct or to the caller's counter is a round trip through local memory)
+__device__ __noinline__ Winner exchange(TreeSmem &S, uint4 *rec, unsigned long long *bar, const unsigned seq, int G) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4 *recs = ws.rec + (size_t)(seq & 1u) * G * TREE_REC_PIECES;
+    uint4 *recs = rec + (size_t)(seq & 1u) * G * TREE_REC_PIECES;
     if (warp == 0) {
         const bool in = lane < TREE_NW;
         const double cc0 = in ? S.w_cc[lane] : CUDART_INF;
@@ -237,11 +238,11 @@ __device__ __noinline__ Winner exchange(TreeSmem &S, const TreeWs &ws, unsigned 
         if (lane == 0) {
             // release: the record and this CTA's tree writes (ordered before by __syncthreads) precede the count
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            atomicAdd(ws.bar + 8, 1ull);
+            atomicAdd(bar + 8, 1ull);
             const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
             unsigned long long v;
-            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
-            (void)ld_acquire(ws.bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
+            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar + 8) : "memory"); } while (v < target);
+            (void)ld_acquire(bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
         }
     }
     __syncthreads();
@@ -283,36 +284,44 @@ __device__ __noinline__ Winner exchange(TreeSmem &S, const TreeWs &ws, unsigned 
         W.flags |= S.q_fl[w];
         W.hits += S.q_hs[w];
     }
-    seq++;
     return W;
 }
 
 // informed_sample (rrt_07:1145-1159) for iteration `it` given c_best
-__device__ __noinline__ void draw_sample(const TreeArgs &A, int it, double c_best, double c_min, double xc, double yc,
-                                            double &rx, double &ry) {
+__device__ __noinline__ double2 draw_sample_v(const double2 *free_s, const double2 *ball, double r00, double r01, double r10,
+                                              double r11, int it, double c_best, double c_min, double xc, double yc) {
+    double rx, ry;
     if (c_best < CUDART_INF) {
         const double r0 = c_best / 2.0;
         const double r1 = sqrt(c_best * c_best - c_min * c_min) / 2.0;
-        const double2 ab = __ldg(A.ball + it);
+        const double2 ab = __ldg(ball + it);
         double a = ab.x, b = ab.y;
         if (b < a) { double t = a; a = b; b = t; }
         const double ang = 2 * 3.141592653589793 * a / b;
         double sn, cs;
         crm_sincos(ang, &sn, &cs);
         const double bx = b * cs, by = b * (ang == 0.0 ? ang : sn);
-        const double m00 = A.p.rot[0] * r0, m01 = A.p.rot[1] * r1, m10 = A.p.rot[2] * r0, m11 = A.p.rot[3] * r1;
+        const double m00 = r00 * r0, m01 = r01 * r1, m10 = r10 * r0, m11 = r11 * r1;
         rx = fma(m00, bx, m01 * by) + xc;
         ry = fma(m10, bx, m11 * by) + yc;
     } else {
-        const double2 f = __ldg(A.free_s + it);
+        const double2 f = __ldg(free_s + it);
         rx = f.x; ry = f.y;
     }
+    return make_double2(rx, ry);
 }
+// (by value across the call; the kernel argument block stays in the constant bank)
+#define draw_sample(A, it, c_best, c_min, xc, yc, rx, ry) do { \
+        const double2 ds_ = draw_sample_v((A).free_s, (A).ball, (A).p.rot[0], (A).p.rot[1], (A).p.rot[2], (A).p.rot[3], (it), (c_best), (c_min), (xc), (yc)); \
+        (rx) = ds_.x; (ry) = ds_.y; } while (0)
 
 // One warp extends `from` towards the sample: get_new_node (rrt_07:1216-1224), line_cost, check_collision(nearest,
 // theta, d) (:1271-1276), is_near_goal (:1226-1230) and the goal segment test (:1096); lanes split the circles.
-__device__ __noinline__ void extend_candidate(const double4 *s_obs, int n_obs, double fx, double fy, double tx, double ty,
-                                              double ed, double gx, double gy, double &nx, double &ny, int &cf) {
+struct ExtResult { double nx, ny; int cf; };
+__device__ __noinline__ ExtResult extend_candidate_v(const double4 *s_obs, int n_obs, double fx, double fy, double tx, double ty,
+                                                    double ed, double gx, double gy) {
+    double nx, ny;
+    int cf;
     const int lane = threadIdx.x & 31;
     double st, ct;
     (void)crm_atan2_sincos(ty - fy, tx - fx, &st, &ct);
@@ -329,7 +338,15 @@ __device__ __noinline__ void extend_candidate(const double4 *s_obs, int n_obs, d
     he = __any_sync(0xffffffffu, he);
     hg = __any_sync(0xffffffffu, hg);
     cf = (he ? CF_BLOCKED : 0) | (near_goal ? CF_NEAR_GOAL : 0) | (hg ? CF_GOAL_BLOCKED : 0);
+    ExtResult r;
+    r.nx = nx; r.ny = ny; r.cf = cf;
+    return r;
 }
+// (result by value across the call: reference outputs would go through local memory)
+#define extend_candidate(obs_, n_, fx_, fy_, tx_, ty_, ed_, gx_, gy_, nx_, ny_, cf_) do { \
+        const ExtResult er_ = extend_candidate_v((obs_), (n_), (fx_), (fy_), (tx_), (ty_), (ed_), (gx_), (gy_)); \
+        (nx_) = er_.nx; (ny_) = er_.ny; (cf_) = er_.cf; } while (0)
+
 
 // Exact `.index()` resolution when two hits at different positions have a bit-equal d^2 (rare): every CTA publishes
 // its hit list, each hit looks for a lower-index hit with the same d^2 (-> shadowed), the best-parent partials are
@@ -378,7 +395,8 @@ __device__ __noinline__ void resolve_equal_d2(TreeSmem &S, const TreeArgs &A, co
             if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = 0; S.w_hs[warp] = 0; }
             if (tid == 0) { S.c_d2 = INF; S.c_idx = NO_IDX; S.c_nx = 0.0; S.c_ny = 0.0; S.c_cf = 0; }
             __syncthreads();
-            const Winner W2 = exchange(S, ws, seq, G);
+            const Winner W2 = exchange(S, ws.rec, ws.bar, seq, G);
+        seq++;
             W.cp_cost = W2.cp_cost; W.cp_idx = W2.cp_idx;
     }
 }
@@ -559,7 +577,8 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_kernel(const TreeArgs
         if (lane == 0) { S.w_cc[warp] = cc; S.w_ci[warp] = ci; S.w_fl[warp] = flags; S.w_hs[warp] = myhits; }
         __syncthreads();
         TREE_TICK(2);
-        const Winner W = exchange(S, ws, seq, G);
+        const Winner W = exchange(S, ws.rec, ws.bar, seq, G);
+        seq++;
         TREE_TICK(3);
         return W;
     };
@@ -773,25 +792,25 @@ struct BatchSmem {
 };
 
 // counter barrier of the batch kernel (records were stored before by this CTA's warps)
-__device__ __forceinline__ void batch_sync(const TreeWs &ws, unsigned &seq, int G) {
+__device__ __forceinline__ void batch_sync(unsigned long long *bar, const unsigned seq, int G) {
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        atomicAdd(ws.bar + 8, 1ull);
+        atomicAdd(bar + 8, 1ull);
         const unsigned long long target = (unsigned long long)(seq + 1u) * (unsigned long long)G;
         unsigned long long v;
-        do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ws.bar + 8) : "memory"); } while (v < target);
-            (void)ld_acquire(ws.bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
+        do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar + 8) : "memory"); } while (v < target);
+            (void)ld_acquire(bar + 8);   // acquire: pairs with the releasing fence + atomicAdd of every CTA, so the record / tree reads below are ordered after them
     }
     __syncthreads();
-    seq++;
 }
 
 // Cross-CTA argmin per sample.  In: S.w_d / w_i [k][warp] per-warp partials of this CTA (and S.w_h hit counts, S.w_m
 // masks when `with_masks`).  Out: S.q_d[k][0], S.q_i[k][0] (+ S.hits[k], S.g_mask), valid for every thread after return.
-__device__ __noinline__ void batch_exchange(BatchSmem &S, const TreeWs &ws, unsigned &seq, int G, int B, bool with_masks) {
+__device__ __noinline__ void batch_exchange(BatchSmem &S, uint4 *rec, unsigned long long *bar, const unsigned seq, int G, int B,
+                                            bool with_masks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4 *recs = ws.rec + (size_t)(seq & 1u) * G * TB_REC;
+    uint4 *recs = rec + (size_t)(seq & 1u) * G * TB_REC;
     if (warp < B) {   // warp k reduces the CTA's partials of sample k and stores its piece
         const bool in = lane < TREE_NW;
         const double v = in ? S.w_d[warp][lane] : CUDART_INF;
@@ -805,7 +824,7 @@ __device__ __noinline__ void batch_exchange(BatchSmem &S, const TreeWs &ws, unsi
         const int m = (int)__reduce_or_sync(0xffffffffu, lane < TREE_NW ? (unsigned)S.w_m[lane] : 0u);
         if (lane == 0) __stcg(recs + (size_t)blockIdx.x * TB_REC + TB_MAX, make_uint4((unsigned)m, 0u, 0u, 0u));
     }
-    batch_sync(ws, seq, G);
+    batch_sync(bar, seq, G);
     double v[TB_MAX];
     int i[TB_MAX], h[TB_MAX], m = 0;
 #pragma unroll
@@ -943,7 +962,8 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
         }
         __syncthreads();
         TB_TICK(1);
-        batch_exchange(S, ws, seq, G, B, false);
+        batch_exchange(S, ws.rec, ws.bar, seq, G, B, false);
+        seq++;
         TB_TICK(2);
         TB_SUB_RESET();
         // ---- warp k extends winner k (get_new_node + check_collision + goal tests, exact leaf math) ----
@@ -1137,7 +1157,8 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
         }
         __syncthreads();
         TB_TICK(3);
-        batch_exchange(S, ws, seq, G, B1, true);
+        batch_exchange(S, ws.rec, ws.bar, seq, G, B1, true);
+        seq++;
         const int gm = S.g_mask;
         if ((gm >> 24) & 1) {   // some CTA's hit list overflowed: nothing was applied yet -- undo the hash inserts and retry smaller
             for (int e = tid; e < H; e += TREE_T) { const int slot = S.hit_slot[e]; if (slot >= 0) tab[slot] = TREE_EMPTY; }
@@ -1193,7 +1214,8 @@ __global__ void __launch_bounds__(TREE_T, 1) informed_tree_batch_kernel(const Tr
                 if (lane == 0) { S.w_d[0][warp] = cc; S.w_i[0][warp] = cc < INF ? ci : NO_IDX; S.w_h[0][warp] = 0; S.w_m[warp] = 0; }
             }
             __syncthreads();
-            batch_exchange(S, ws, seq, G, 1, true);
+            batch_exchange(S, ws.rec, ws.bar, seq, G, 1, true);
+        seq++;
             if (tid == 0) { S.cp_cost[0] = S.q_d[0][0]; S.cp_idx[0] = S.q_i[0][0]; }
             __syncthreads();
         }
@@ -1321,7 +1343,8 @@ __global__ void __launch_bounds__(TREE_T, 1) tree_exchange_probe_kernel(TreeWs w
     double acc = 0.0;
     const long long t0 = clock64();
     for (int k = 0; k < iters; k++) {
-        const Winner W = exchange(S, ws, seq, G);
+        const Winner W = exchange(S, ws.rec, ws.bar, seq, G);
+        seq++;
         acc += W.nn_d2 + W.hits;
         __syncthreads();
     }
