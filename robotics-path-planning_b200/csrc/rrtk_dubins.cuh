@@ -194,7 +194,8 @@ static __device__ __forceinline__ bool prefilter_ok(double s_x, double s_y, doub
 // inside the 1e-7 margin).  Conservative by construction: any doubt (an angular position within tolerance of the arc's
 // ends) counts as "near".
 //   type 0 = L, 1 = S, 2 = R;  (ox, oy) origin, (so, co) = sin / cos(origin yaw), (ex, ey) the segment's end point,
-//   length = the word length (arc angle in radians for L / R);  (px, py) = the circle centre in the local frame
+//   length = the word length (arc angle in radians for L / R; negative = driven backwards, Reeds-Shepp: the same circle
+//   run through the other way);  (px, py) = the circle centre in the local frame
 static __device__ __forceinline__ bool circle_near_segment(int type, double kappa, double ox, double oy, double so, double co,
                                                            double ex, double ey, double length, double px, double py,
                                                            double R) {
@@ -213,7 +214,8 @@ static __device__ __forceinline__ bool circle_near_segment(int type, double kapp
     const double dc = sqrt(vx * vx + vy * vy);
     if (fabs(dc - rho) > m) return false;                      // clear of the whole circle the arc lies on
     const double ux = ox - cx, uy = oy - cy, wx = ex - cx, wy = ey - cy;
-    const double c1 = sgn * (ux * vy - uy * vx), c2 = sgn * (vx * wy - vy * wx);   // > 0: o is past the start / before the end
+    const double dir = length < 0.0 ? -sgn : sgn;
+    const double c1 = dir * (ux * vy - uy * vx), c2 = dir * (vx * wy - vy * wx);   // > 0: o is past the start / before the end
     const double tol = 1e-9 * (rho * dc + 1.0);
     const bool in_span = fabs(length) < D_PI ? (c1 >= -tol && c2 >= -tol) : !(c1 < -tol && c2 < -tol);
     if (in_span) return true;

@@ -239,13 +239,22 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         e.npts = 1;
         return e;
     }
-    double sm0, cm0;
-    sincos_cr(-syaw, &sm0, &cm0);
+    const double sm0 = -s0, cm0 = c0;   // sin / cos(-syaw): the correctly rounded functions are odd / even bit for bit
+    const bool filt = prefilter_ok(sx, sy, gx, gy, maxc);
     bool hit = false;
-    int np = 0;
+    int np = 1;
     double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
+    auto test = [&](double lx, double ly) {
+        const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
+        for (int o = 0; o < n_obs && !hit; o++) {
+            const double4 ob = obs[o];
+            const double ex = ob.x - wx, ey = ob.y - wy;
+            if (ex * ex + ey * ey <= ob.w) hit = true;
+        }
+    };
+    test(0.0, 0.0);                     // the first point of the course (np.arange starts at 0 in every segment)
 #pragma unroll 1
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n && !hit; i++) {
         const double length = best_d[i];
         lsum = lsum + fabs(length / maxc);
         const int t0 = RS_T[f][i];
@@ -253,30 +262,37 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         const double dd = length >= 0.0 ? step : -step;
         long long na = length != 0.0 ? (long long)ceil((length - 0.0) / dd) : 0;
         if (na < 0) na = 0;
-        double so, co, sm, cm;
-        sincos_cr(oyaw, &so, &co);
-        sincos_cr(-oyaw, &sm, &cm);
+        double so = 0.0, co = 1.0;
+        if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
+        const double sm = -so, cm = co;
         double lx = 0.0, ly = 0.0, lyaw = 0.0;
+        rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);   // the segment's last point: always exact
+        test(lx, ly);
+        // segment-level cull (circle_near_segment, rrtk_dubins.cuh): the interior points lie on the arc / straight piece
+        // between the origin and that last point; they are evaluated only when a circle comes near it
+        bool near = !filt;
+        for (int o = 0; o < n_obs && !near && !hit; o++) {
+            const double4 ob = obs[o];
+            const double ux = ob.x - sx, uy = ob.y - sy;
+            near = circle_near_segment(type, maxc, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
+        }
+        if (near && !hit) {
 #pragma unroll 1
-        for (long long j = 0; j <= na; j++) {
-            const double dist = j < na ? 0.0 + (double)j * dd : length;
-            rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
-            const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
-            for (int o = 0; o < n_obs && !hit; o++) {
-                const double4 ob = obs[o];
-                const double ex = ob.x - wx, ey = ob.y - wy;
-                if (ex * ex + ey * ey <= ob.w) hit = true;
-            }
-            if (hit) {   // blocked: the callers read neither the end pose nor the length of a blocked edge, only that a course exists
-                e.npts = 1;
-                return e;
+            for (long long j = 1; j < na && !hit; j++) {
+                double px, py, pyaw;
+                rs_interp(0.0 + (double)j * dd, type, maxc, ox, oy, oyaw, so, co, sm, cm, &px, &py, &pyaw);
+                test(px, py);
             }
         }
         ox = lx; oy = ly; oyaw = lyaw;
-        np += (int)(na + 1);
+        np++;                           // (the callers only ask whether a course exists)
+    }
+    if (hit) {   // blocked: the callers read neither the end pose nor the length of a blocked edge, only that a course exists
+        e.npts = 1;
+        return e;
     }
     e.npts = np;
-    e.free_ = !hit;
+    e.free_ = true;
     e.lsum = lsum;
     e.ex = cm0 * ox + sm0 * oy + sx;
     e.ey = -sm0 * ox + cm0 * oy + sy;
@@ -341,11 +357,20 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
     }
     if (best < 0) return e;
     const int f = best >> 2, k = best & 3, n = RS_N[f];
-    double sm0, cm0;
-    sincos_cr(-syaw, &sm0, &cm0);
+    const double sm0 = -s0, cm0 = c0;   // sin / cos(-syaw), exactly (see rs_edge_lane)
+    const bool filt = prefilter_ok(sx, sy, gx, gy, maxc);
     bool hit = false;
-    int np = 0;
+    int np = 1;
     double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
+    auto test = [&](double lx, double ly) {
+        const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
+        for (int o = 0; o < n_obs && !hit; o++) {
+            const double4 ob = obs[o];
+            const double ex = ob.x - wx, ey = ob.y - wy;
+            if (ex * ex + ey * ey <= ob.w) hit = true;
+        }
+    };
+    if (lane == 0) test(0.0, 0.0);
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
         double length = W.d[best][i];
@@ -356,29 +381,32 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
         const double dd = length >= 0.0 ? step : -step;
         long long na = length != 0.0 ? (long long)ceil((length - 0.0) / dd) : 0;
         if (na < 0) na = 0;
-        double so, co, sm, cm;
-        sincos_cr(oyaw, &so, &co);
-        sincos_cr(-oyaw, &sm, &cm);
+        double so = 0.0, co = 1.0;
+        if (oyaw != 0.0) sincos_cr(oyaw, &so, &co);
+        const double sm = -so, cm = co;
+        double lx, ly, lyaw;   // the segment's last point is the next origin (uniform)
+        rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
+        if (lane == 0) test(lx, ly);
+        bool near = !filt;     // segment-level cull, the lanes split the circles
+        for (int o = lane; o < n_obs && !near; o += 32) {
+            const double4 ob = obs[o];
+            const double ux = ob.x - sx, uy = ob.y - sy;
+            near = circle_near_segment(type, maxc, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
+        }
+        if (__any_sync(FULL, near)) {
 #pragma unroll 1
-        for (long long j = lane; j <= na; j += 32) {
-            const double dist = j < na ? 0.0 + (double)j * dd : length;
-            double lx, ly, lyaw;
-            rs_interp(dist, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
-            const double wx = cm0 * lx + sm0 * ly + sx, wy = -sm0 * lx + cm0 * ly + sy;
-            for (int o = 0; o < n_obs && !hit; o++) {
-                const double4 ob = obs[o];
-                const double ex = ob.x - wx, ey = ob.y - wy;
-                if (ex * ex + ey * ey <= ob.w) hit = true;
+            for (long long j = 1 + lane; j < na; j += 32) {
+                double px, py, pyaw;
+                rs_interp(0.0 + (double)j * dd, type, maxc, ox, oy, oyaw, so, co, sm, cm, &px, &py, &pyaw);
+                test(px, py);
             }
         }
         if (__any_sync(FULL, hit)) {   // blocked: see rs_edge_lane
             e.npts = 1;
             return e;
         }
-        double lx, ly, lyaw;   // the segment's last point is the next origin (uniform)
-        rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
         ox = lx; oy = ly; oyaw = lyaw;
-        np += (int)(na + 1);
+        np++;
     }
     e.npts = np;
     e.free_ = true;
