@@ -12,7 +12,10 @@ from math import pi
 
 import numpy as np
 
+import math
+
 from . import _lib, dubins, engine
+from .planners import RRT as _RRT2D, RRTStar as _RRTStar2D
 
 
 class Node:
@@ -120,7 +123,81 @@ def final_course(tree, start, goal, curvature):
     return path
 
 
-class RRTStarDubins:
+
+class _DubinsSteps:
+    """The reference's per-step methods of the Dubins planners (rrt_05:1458-1479, :1605-1638, :1648-1779; rrt_03 shares the
+    first group), device-backed like rrtk.RRT's: `steer` is one launch of the Dubins steering kernel, the scans and the
+    point-list collision test are the FP64 primitives of include/rrtk.h.  planning() is the fused kernel and refuses to run
+    when one of these is overridden (it would be ignored); an overridden get_random_node is honoured."""
+
+    _FUSED_METHODS = ("steer", "check_collision", "check_if_outside_play_area", "get_nearest_node_index",
+                      "calc_distance_and_angle", "choose_parent", "rewire", "find_near_nodes", "calc_new_cost",
+                      "propagate_cost_to_leaves", "search_best_goal_node")
+
+    check_collision = staticmethod(_RRT2D.check_collision)
+    check_if_outside_play_area = staticmethod(_RRT2D.check_if_outside_play_area)
+    get_nearest_node_index = staticmethod(_RRT2D.get_nearest_node_index)
+    calc_distance_and_angle = staticmethod(_RRT2D.calc_distance_and_angle)
+    _overridden = _RRT2D._overridden
+    find_near_nodes = _RRTStar2D.find_near_nodes
+    calc_new_cost = _RRTStar2D.calc_new_cost
+    propagate_cost_to_leaves = _RRTStar2D.propagate_cost_to_leaves
+
+    def _check_overrides(self, base):
+        bad = self._overridden([m for m in self._FUSED_METHODS if hasattr(base, m)], base)
+        if bad:
+            raise _lib.RrtkError("planning() runs the whole loop as one fused GPU kernel; the overridden method(s) " + ", ".join(bad)
+                                 + " would be ignored.  Call the per-step methods yourself (they are device-backed), or plan "
+                                 "with the stock class.")
+
+    def steer(self, from_node, to_node):
+        """rrt_05:1458-1479: the Dubins course from_node -> to_node as a new node (None when there is no course)."""
+        px, py, pyaw, mode, lengths = dubins.plan_dubins_path(from_node.x, from_node.y, from_node.yaw, to_node.x, to_node.y,
+                                                              to_node.yaw, self.curvature)
+        if len(px) <= 1:
+            return None
+        nd = Node(float(px[-1]), float(py[-1]), float(pyaw[-1]))
+        nd._course = (list(px), list(py), list(pyaw))
+        nd.cost = from_node.cost + sum([abs(c) for c in lengths])
+        nd.parent = from_node
+        return nd
+
+    def choose_parent(self, new_node, near_inds):
+        """rrt_05:1648-1689: the near node with the cheapest (Euclidean, :1777-1779) cost over a collision-free course."""
+        if not near_inds:
+            return None
+        costs = []
+        for i in near_inds:
+            near_node = self.node_list[i]
+            t_node = self.steer(near_node, new_node)
+            if t_node and self.check_collision(t_node, self.obstacle_list, self.robot_radius):
+                costs.append(self.calc_new_cost(near_node, new_node))
+            else:
+                costs.append(float("inf"))
+        min_cost = min(costs)
+        if min_cost == float("inf"):
+            return None
+        new_node = self.steer(self.node_list[near_inds[costs.index(min_cost)]], new_node)
+        new_node.cost = min_cost
+        return new_node
+
+    def rewire(self, new_node, near_inds):
+        """rrt_05:1741-1775."""
+        for i in near_inds:
+            near_node = self.node_list[i]
+            edge_node = self.steer(new_node, near_node)
+            if not edge_node:
+                continue
+            edge_node.cost = self.calc_new_cost(new_node, near_node)
+            if self.check_collision(edge_node, self.obstacle_list, self.robot_radius) and near_node.cost > edge_node.cost:
+                for node in self.node_list:
+                    if node.parent is self.node_list[i]:
+                        node.parent = edge_node
+                self.node_list[i] = edge_node
+                self.propagate_cost_to_leaves(edge_node)
+
+
+class RRTStarDubins(_DubinsSteps):
     """rrt_05's `RRT`: RRT* with Dubins steering, same constructor keywords and defaults (rrt_05:1358-1375)."""
 
     Node = Node
@@ -153,6 +230,7 @@ class RRTStarDubins:
         return (self.end.x, self.end.y, self.end.yaw)
 
     def planning(self, animation=True, search_until_max_iter=True, sample_stream=None):
+        self._check_overrides(RRTStarDubins)
         n = int(self.max_iter)
         rng_state = None
         if sample_stream is None:
@@ -237,7 +315,7 @@ def run_rrt_batch(starts, goals, obstacle_lists, max_iter, streams, robot_radius
     return out
 
 
-class RRTDubins:
+class RRTDubins(_DubinsSteps):
     """rrt_03's `RRT`: plain RRT with Dubins steering, same constructor keywords and defaults (rrt_03:1370-1383).
     `planning(animation=True, search_until_max_iter=True)` returns the sampled final course (goal -> start) or None.
     Unlike rrt_05, `sobol_sampler` is honoured (:1430-1433): x, y from points of the 3-D Sobol sequence mapped to
@@ -286,6 +364,7 @@ class RRTDubins:
         return stream, is_goal
 
     def planning(self, animation=True, search_until_max_iter=True, sample_stream=None):
+        self._check_overrides(RRTDubins)
         n = int(self.max_iter)
         rng_state, is_goal = None, None
         if sample_stream is None:

@@ -145,3 +145,54 @@ def test_nearest_and_near_primitives_follow_the_reference_lists():
     d = [(x - c[0]) ** 2 + (y - c[1]) ** 2 for x, y in xy.tolist()]
     assert engine.nearest_index(xy, [c])[0] == 7
     assert engine.near_indices(xy, c[0], c[1], 4.0) == [d.index(v) for v in d if v <= 4.0]
+
+
+def test_dubins_overridden_method_is_refused():
+    """(no GPU needed) rrt_05 / rrt_03 classes: same rule as rrtk.RRTStar."""
+    import rrtk
+
+    class MySteer(rrtk.RRTStarDubins):
+        def steer(self, from_node, to_node):
+            return None
+
+    class MyCC(rrtk.RRTDubins):
+        @staticmethod
+        def check_collision(node, obstacleList, robot_radius):
+            return True
+    with pytest.raises(rrtk.RrtkError, match="steer"):
+        MySteer([0, 0, 0], [10, 10, 0], [(5, 5, 1)], [-2, 15], max_iter=10).planning(animation=False)
+    with pytest.raises(rrtk.RrtkError, match="check_collision"):
+        MyCC([0, 0, 0], [10, 10, 0], [(5, 5, 1)], [-2, 15], max_iter=10).planning(animation=False)
+
+
+@pytest.mark.gpu
+def test_dubins_loop_built_from_the_per_step_methods_equals_the_fused_kernel():
+    """rrt_05's planning() loop (:1416-1456) written against rrtk.RRTStarDubins' steer / check_collision /
+    get_nearest_node_index / find_near_nodes / choose_parent / rewire gives the tree the kernel gives."""
+    import rrtk
+    g, m = load_golden("rrt05_builtin_500")
+    iters = 120
+    stream = g["stream"][:iters]
+    kw = dict(expand_dis=m["expand_dis"], goal_sample_rate=m["goal_sample_rate"], max_iter=iters, robot_radius=m["robot_radius"],
+              connect_circle_dist=m["connect_circle_dist"], curvature=m["curvature"], goal_yaw_th=m["goal_yaw_th"],
+              goal_xy_th=m["goal_xy_th"])
+    fused = rrtk.RRTStarDubins(m["start"], m["goal"], m["obstacle_list"], m["rand_area"], **kw)
+    fused.planning(animation=False, search_until_max_iter=True, sample_stream=stream)
+    r = rrtk.RRTStarDubins(m["start"], m["goal"], m["obstacle_list"], m["rand_area"], **kw)
+    r.node_list = [r.start]
+    for i in range(iters):
+        rnd = r.Node(*[float(v) for v in stream[i]])
+        ni = r.get_nearest_node_index(r.node_list, rnd)
+        new_node = r.steer(r.node_list[ni], rnd)
+        if r.check_collision(new_node, r.obstacle_list, r.robot_radius):
+            near = r.find_near_nodes(new_node)
+            new_node = r.choose_parent(new_node, near)
+            if new_node:
+                r.node_list.append(new_node)
+                r.rewire(new_node, near)
+    t = fused.tree_arrays()
+    assert len(r.node_list) == len(t["x"])
+    idx = {id(n): i for i, n in enumerate(r.node_list)}
+    assert [(-1 if n.parent is None else idx[id(n.parent)]) for n in r.node_list] == t["parent"].tolist()
+    assert np.array_equal([n.x for n in r.node_list], t["x"]) and np.array_equal([n.yaw for n in r.node_list], t["yaw"])
+    assert np.array_equal([n.cost for n in r.node_list], t["cost"])

@@ -75,6 +75,25 @@ def test_tree_random_scenes_vs_oracle(grid, iters, seed, batch, oracle_lib):
     assert ref["path"] is not None and run.info["goal_events"] > 0 and run.info["resamples"] > 0
 
 
+def test_tree_25000_iterations_vs_oracle(oracle_lib):
+    """The largest tree the C oracle replays in half a minute (O(n) per iteration): 25 000 iterations, ~20 000 nodes, batched
+    kernel on the full grid -- every node, cost, parent and the path, bit for bit."""
+    from rrtk import informed
+    O = oracle_lib
+    rng = np.random.default_rng(4)
+    iters = 25000
+    start, goal = [0.0, 0.0], [10.0, 9.0]
+    obs = [(float(x), float(y), float(r)) for (x, y), r in zip(rng.uniform(1, 12, (40, 2)), rng.uniform(0.2, 0.8, 40))]
+    obs = [o for o in obs if np.hypot(o[0], o[1]) > o[2] + 0.6 and np.hypot(o[0] - 10, o[1] - 9) > o[2] + 0.6]
+    free, ball = _draws(rng, iters, goal)
+    rot = informed.rotation_to_world_frame(start, goal)
+    run = informed.run_tree(start, goal, obs, 0.5, iters, free, ball, grid=0, batch=8)
+    ref = O.informed_run(start, goal, obs, 0.5, iters, rot, free, ball, O.MATH_CR)
+    a = run.arrays()
+    assert a["status"] == 0 and ref["n"] > 15000
+    _same(a, ref)
+
+
 def test_tree_duplicate_positions_and_equal_d2(oracle_lib):
     """Repeated samples create identical nodes (the `.index()` quirk shadows the later twin); a mirrored pair
     gives two DIFFERENT positions at bitwise-equal d^2 from a node on the axis (exact slow path)."""
