@@ -27,6 +27,9 @@
 namespace rrtk {
 
 constexpr int WARPS_PER_CTA = 4;
+// rare branches (exact fall-backs, overflows): told to the compiler so that their code leaves the hot straight-line path
+// (the kernel is bound by instruction fetch; the L1.5 instruction cache holds 32 KB)
+#define RRTK_RARE(c) __builtin_expect(!!(c), 0)
 #define RRTK_PRAGMA(x) _Pragma(#x)
 #define RRTK_UNROLL(n) RRTK_PRAGMA(unroll n)
 #ifndef RRTK_UNROLL_NEAREST
@@ -303,7 +306,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     }
                 }
             }
-            if (v < 0) {
+            if (RRTK_RARE(v < 0)) {
                 Steer e0 = steer(from.x, from.y, rx, ry, p.expand_dis, res);
                 nx = e0.ex; ny = e0.ey;
                 if (inside_play(p, nx, ny)) {
@@ -313,7 +316,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                 }
             }
             {
-                if (accept && n >= p.node_cap) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
+                if (RRTK_RARE(accept && n >= p.node_cap)) { status |= RRTK_Q_NODE_OVERFLOW; accept = false; done = true; }
                 if (accept && RRT_ONLY) {
                     if (lane == 0) { xy[n] = make_double2(nx, ny); cost[n] = 0.0; parent[n] = ni; }
                     t_status = 2; t_par = ni;
@@ -324,9 +327,9 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     const double nlen = crm_hypot(nx - from.x, ny - from.y);
                     const double ncost = cost[ni] + nlen;
                     // ---- find_near_nodes (rrt_04:1314-1338): ballot compaction, ascending index ----
-                    if (!near_valid) count = near_scan(xy, n, nx, ny, r2, near_idx, nd, near_cap, lane);
+                    if (RRTK_RARE(!near_valid)) count = near_scan(xy, n, nx, ny, r2, near_idx, nd, near_cap, lane);
                     __syncwarp();
-                    if (count > near_cap) {
+                    if (RRTK_RARE(count > near_cap)) {
                         status |= RRTK_Q_NEAR_OVERFLOW;
                         done = true;
                     } else {
@@ -353,7 +356,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                             double ex = nx, ey = ny;                          // a snapped edge ends on the new node
                             const int v = edge_verdict_fast<false>(a.x, a.y, nx, ny, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull).v;
                             bool ok = v == 1;                                 // (the new node is inside the play area)
-                            if (v < 0) {
+                            if (RRTK_RARE(v < 0)) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
                                 ok = edge_free_lane(a.x, a.y, st, nx, ny, L) && inside_play(p, st.ex, st.ey);
                                 ex = st.ex; ey = st.ey;
@@ -408,7 +411,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                 }
                                 if (want) {
                                     const int v = edge_verdict_fast<false>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, 0, 1, ~0ull).v;
-                                    if (v < 0) {
+                                    if (RRTK_RARE(v < 0)) {
                                         st = steer(cx, cy, a.x, a.y, INF, res);
                                         ok = edge_free_lane(cx, cy, st, a.x, a.y, L) && inside_play(p, st.ex, st.ey);
                                     } else {   // snapped: the edge ends on the node itself (it does not move)
@@ -448,7 +451,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                         propagate_lists_elen(ii, moved, xy, cost, elen, links, &ws->qtail, lane);
 #endif
                                         dirty = true;
-                                        if (moved) {
+                                        if (RRTK_RARE(moved)) {
                                             // the node no longer sits where the parallel pass saw it, and the
                                             // costs of its descendants may have gone UP: every later entry is
                                             // re-evaluated from the current tree, one at a time
@@ -459,7 +462,7 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                                     }
                                 }
                             }
-                            if (fallback_from >= 0)
+                            if (RRTK_RARE(fallback_from >= 0))
                                 rewire_serial(plan_consts(p), fallback_from, count, near_idx, xy, cost, parent, links, elen, n, cx, cy, ccost, L,
                                               &ws->qtail, lane, t_rwok, t_rwap);
                             if (lane == 0) {
