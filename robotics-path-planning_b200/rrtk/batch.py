@@ -31,6 +31,10 @@ class RRTStarBatch:
         goals = np.asarray(goals, dtype=np.float64).reshape(-1, 2)
         self.n_queries = q = starts.shape[0]
         self.max_iter = int(max_iter)
+        self._ctor = dict(rand_area=rand_area, expand_dis=expand_dis, path_resolution=path_resolution,
+                          goal_sample_rate=goal_sample_rate, play_area=play_area, sampler=sampler,
+                          connect_circle_dist=connect_circle_dist, search_until_max_iter=search_until_max_iter, seed=seed,
+                          near_cap=near_cap)
         self.node_cap = self.max_iter + 1
         if isinstance(obstacle_lists, np.ndarray) and obstacle_lists.ndim == 3 and obstacle_lists.shape[2] == 4:
             rows = np.ascontiguousarray(obstacle_lists, dtype=np.float64)
@@ -141,8 +145,27 @@ class RRTStarBatch:
         self._graph.replay()
 
     def planning(self, animation=False):
-        """Paths for every query: list of `[[x, y], ...]` (goal -> start) or None."""
-        return self.run().paths()
+        """Paths for every query: list of `[[x, y], ...]` (goal -> start) or None.  The reference's near lists have no
+        capacity: a query whose list outgrew `near_cap` (status bit RRTK_Q_NEAR_OVERFLOW, the kernel stops that query) is
+        planned again on its own with near_cap = 1024, same samples; only if that overflows too the call raises."""
+        res = self.run()
+        paths = res.paths()
+        over = (res.status.cpu().numpy() & _lib.Q_NEAR_OVERFLOW) != 0
+        for i in np.flatnonzero(over).tolist():
+            c = self._ctor
+            if c["near_cap"] >= 1024:
+                raise _lib.RrtkError(f"query {i}: near list overflow at near_cap = {c['near_cap']}")
+            sub = RRTStarBatch(self.h_start_goal[i:i + 1, 0:2].numpy(), self.h_start_goal[i:i + 1, 2:4].numpy(),
+                               self.h_obstacles[i:i + 1].numpy(), c["rand_area"], c["expand_dis"], c["path_resolution"],
+                               c["goal_sample_rate"], self.max_iter, c["play_area"], 0.0, c["sampler"], c["connect_circle_dist"],
+                               c["search_until_max_iter"], c["seed"], 1024, self.h_n_obs[i:i + 1].numpy(),
+                               None if self.sample_stream is None else self.sample_stream[i:i + 1].cpu().numpy(),
+                               self.sobol_offset[i:i + 1].cpu().numpy(), self.device, self.params.query_base + i)
+            r1 = sub.run()
+            if int(r1.status[0].item()) & _lib.Q_NEAR_OVERFLOW:
+                raise _lib.RrtkError(f"query {i}: near list overflow at near_cap = 1024")
+            paths[i] = r1.paths()[0]
+        return paths
 
     def materialised_stream(self):
         """The samples the in-kernel sampler produces, [Q, max_iter, 2] (for the CPU oracle)."""

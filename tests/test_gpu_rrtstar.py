@@ -473,3 +473,23 @@ def test_cta_and_warp_executions_agree_on_a_ragged_batch():
         k = a[0][q]
         assert np.array_equal(a[3][q, :k], c[3][q, :k]) and np.array_equal(a[4][q, :k], c[4][q, :k])
         assert np.array_equal(a[5][q, :k], c[5][q, :k])
+
+
+def test_batch_planning_replans_near_list_overflows(torch_cuda):
+    """The reference's near lists have no capacity.  A batch built with a near_cap its queries outgrow still returns the
+    paths of the uncapped run: planning() re-plans the overflowed queries on their own with near_cap = 1024."""
+    import rrtk
+    from rrtk import _lib, workloads as W
+    cfg = W.C2
+    Q, iters, n_obs = 6, 900, 64
+    rows = W.c2_rows(list(range(Q)), n_obs)
+    starts = np.tile(np.array(cfg["start"]), (Q, 1)); goals = np.tile(np.array(cfg["goal"]), (Q, 1))
+    mk = lambda cap: rrtk.RRTStarBatch(starts, goals, rows, cfg["rand_area"], cfg["expand_dis"], cfg["path_resolution"],  # noqa: E731
+                                       cfg["goal_sample_rate"], iters, None, cfg["robot_radius"], "sobol",
+                                       cfg["connect_circle_dist"], True, seed=11, near_cap=cap)
+    small, big = mk(32), mk(256)
+    want = big.planning()
+    assert int((big.result.status != 0).sum()) == 0
+    got = small.planning()
+    assert int(((small.result.status & _lib.Q_NEAR_OVERFLOW) != 0).sum()) > 0, "the scenario should overflow a 32-entry list"
+    assert got == want
