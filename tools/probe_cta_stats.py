@@ -1,3 +1,6 @@
+"""Per-role cycles of the CTA-per-query RRT* kernel's software pipeline (apply phase of iteration i beside stage A of i + 1).
+Needs the statistics build:  make -C robotics-path-planning_b200/csrc stats
+    RRTK_LIB=robotics-path-planning_b200/rrtk/librrtk_stats.so python tools/probe_cta_stats.py"""
 import os, sys
 sys.path.insert(0, "/root/repo/robotics-path-planning_b200")
 os.environ["RRTK_EXEC"] = "cta"
