@@ -37,6 +37,8 @@
 
 namespace rrtk {
 
+#define CTA_RARE(c) __builtin_expect(!!(c), 0)   // rare branches leave the hot straight-line path (the kernel is fetch-bound)
+
 constexpr int CTA_W = 4;              // warps per query
 constexpr int CTA_T = CTA_W * 32;
 constexpr int CTA_NC_SMALL = 256;     // layout capacities of the near list (p.near_cap <= NC): batches / single queries
@@ -278,7 +280,7 @@ static __device__ __forceinline__ void cta_apply(const rrtk_rrtstar_params &p, c
             if (ci > ec) {
                 const double2 a = s_xy[ii];
                 double ex = a.x, ey = a.y;
-                if (flb == 2) {   // the exact edge stops short of the node: it moves there
+                if (CTA_RARE(flb == 2)) {   // the exact edge stops short of the node: it moves there
                     const Steer st = steer(cx, cy, a.x, a.y, INF, res);
                     ex = st.ex; ey = st.ey;
                 }
@@ -298,7 +300,7 @@ static __device__ __forceinline__ void cta_apply(const rrtk_rrtstar_params &p, c
                 cta_propagate(ii, ec, moved, s_xy, s_link, cost, elen, S, g_idx, g_cost, lane);
                 __syncwarp();
                 dirty = true;
-                if (moved) {
+                if (CTA_RARE(moved)) {
                     // the node no longer sits where the parallel pass saw it, and the costs of its descendants may have
                     // gone UP: every later entry is re-evaluated from the current tree, one at a time
                     fallback_from = kk + 1;
@@ -308,7 +310,7 @@ static __device__ __forceinline__ void cta_apply(const rrtk_rrtstar_params &p, c
             }
         }
     }
-    if (fallback_from >= 0) {
+    if (CTA_RARE(fallback_from >= 0)) {
         ObsList L;
         if (S.cull_glob[P.cb]) {
             const double *g = reinterpret_cast<const double *>(obs);
@@ -702,7 +704,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                 n++;
                 appended = true;
             } else if (accept) {
-                if (!S.near_valid) {
+                if (CTA_RARE(!S.near_valid)) {
                     // ---- find_near_nodes (rrt_04:1314-1338) around the new node (it is not the sample) ----
                     __syncthreads();   // (every thread has read the speculative count)
                     if (tid == 0) S.count2[cb] = 0;
@@ -721,7 +723,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                     if (count <= near_cap) cta_rank_near(S, count, tid, CTA_T);
                     __syncthreads();
                 }
-                if (count > near_cap) {
+                if (CTA_RARE(count > near_cap)) {
                     status |= RRTK_Q_NEAR_OVERFLOW;
                     done = true;
                 } else {
@@ -759,7 +761,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                             const int vv = ev.v;
                             if (k0 == 0) seg_near = vv == 1 ? ev.near : ~0ull;
                             blocked = vv == 0;                    // (the new node is inside the play area)
-                            if (vv < 0) {
+                            if (CTA_RARE(vv < 0)) {
                                 Steer st = steer(a.x, a.y, nx, ny, INF, res);
                                 blocked = !(edge_free_lane(a.x, a.y, st, nx, ny, sub_list(L, sub, G)) && inside_play(p, st.ex, st.ey));
                                 ex = st.ex; ey = st.ey;
@@ -842,7 +844,7 @@ rrtstar_cta_kernel(rrtk_rrtstar_params p, const double4 *__restrict__ start_goal
                                     blocked = !inside_play(p, a.x, a.y);
                                 } else if (want) {
                                     const int vv = edge_verdict_fast<true>(cx, cy, a.x, a.y, dk, true, INF, INF, res, inv_res, L, sub, G, only).v;
-                                    if (vv < 0) {
+                                    if (CTA_RARE(vv < 0)) {
                                         Steer st = steer(cx, cy, a.x, a.y, INF, res);
                                         blocked = !(edge_free_lane(cx, cy, st, a.x, a.y, sub_list(L, sub, G)) && inside_play(p, st.ex, st.ey));
                                         moves = (st.ex != a.x) || (st.ey != a.y);
