@@ -28,6 +28,14 @@ static __device__ const int8_t RS_T[12][5] = {{0, 1, 0, -1, -1}, {0, 1, 2, -1, -
                                        {0, 2, 0, 2, -1}, {0, 2, 0, 2, -1},   {0, 2, 1, 0, -1},  {0, 2, 1, 2, -1},  {0, 1, 2, 0, -1},
                                        {0, 1, 0, 2, -1}, {0, 2, 1, 0, 2}};
 static __device__ const int8_t RS_N[12] = {3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5};
+// set_path (rs00:141-160) drops a candidate when an already inserted path of the SAME type string is not longer by more than
+// step_size: `(existing - new) <= step` for ANY of them, i.e. for the SHORTEST of them (the rounded difference is monotone in
+// the existing length).  The 48 candidates (path function f = cand >> 2, symmetry k = cand & 3) have 18 distinct type strings:
+// RS_SLOT[cand] numbers them, so the test is one look-up of the shortest inserted length of that string instead of a scan
+// of everything inserted so far.
+constexpr int RS_SLOTS = 18;
+static __device__ const int8_t RS_SLOT[48] = {0, 0, 5, 5, 1, 1, 4, 4, 2, 2, 3, 3, 2, 2, 3, 3, 2, 2, 3, 3, 8, 8, 13, 13, 8, 8, 13, 13,
+                                              9, 9, 12, 12, 10, 10, 11, 11, 7, 7, 14, 14, 6, 6, 15, 15, 16, 16, 17, 17};
 
 // the path functions of rs00:166-363 in path_functions order; true + travel distances, or false.
 // Every one of them starts from polar(x -/+ sin(phi), y - 1 +/- cos(phi)) (rs00:163-166): (um, thm) is the "minus" pair
@@ -198,8 +206,10 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
     sincos_cr(syaw, &s0, &c0);
     const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;
     // generate_path + set_path in the reference's order; keep the first shortest inserted word
-    double ins_L[48], best_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, best_L = CUDART_INF;
-    int ins_code[48], n_ins = 0, best = -1;
+    double min_L[RS_SLOTS], best_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, best_L = CUDART_INF;
+    int best = -1;
+#pragma unroll
+    for (int j = 0; j < RS_SLOTS; j++) min_L[j] = CUDART_INF;
     double pol[4][4];   // per symmetry: um, thm, up, thp
 #pragma unroll 1
     for (int k = 0; k < 4; k++)
@@ -216,15 +226,10 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
             const double a = fabs(d[i]);
             if (0.1 * tot < a && a < step) return e;   // "Step size too large for Reeds-Shepp paths." -> no path at all
         }
-        int code = n;
-        for (int i = 0; i < n; i++) {
-            const int t0 = RS_T[f][i];
-            code = code * 3 + ((k >= 2 && t0 != 1) ? 2 - t0 : t0);
-        }
-        bool same = false;
-        for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - tot) <= step;
-        if (same || tot <= step) continue;
-        ins_code[n_ins] = code; ins_L[n_ins] = tot; n_ins++;
+        const int slot = RS_SLOT[cand];
+        const double shortest = min_L[slot];
+        if ((shortest - tot) <= step || tot <= step) continue;   // (inf - tot = inf: nothing of this type string inserted yet)
+        if (tot < shortest) min_L[slot] = tot;
         if (fabs(tot / maxc) < best_L) {
             best_L = fabs(tot / maxc); best = cand;
             for (int i = 0; i < 5; i++) best_d[i] = (k == 1 || k == 3) ? -d[i] : d[i];   // timeflip
@@ -332,8 +337,10 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
         W.ok[cand] = ok ? 1 : 0;
     }
     __syncwarp();
-    double ins_L[48], best_L = CUDART_INF;
-    int ins_code[48], n_ins = 0, best = -1;
+    double min_L[RS_SLOTS], best_L = CUDART_INF;
+    int best = -1;
+#pragma unroll
+    for (int j = 0; j < RS_SLOTS; j++) min_L[j] = CUDART_INF;
 #pragma unroll 1
     for (int cand = 0; cand < 48; cand++) {
         if (!W.ok[cand]) continue;
@@ -344,15 +351,10 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
             const double a = fabs(W.d[cand][i]);
             if (0.1 * tot < a && a < step) return e;   // "Step size too large for Reeds-Shepp paths." -> no path at all
         }
-        int code = n;
-        for (int i = 0; i < n; i++) {
-            const int t0 = RS_T[f][i];
-            code = code * 3 + ((k >= 2 && t0 != 1) ? 2 - t0 : t0);
-        }
-        bool same = false;
-        for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - tot) <= step;
-        if (same || tot <= step) continue;
-        ins_code[n_ins] = code; ins_L[n_ins] = tot; n_ins++;
+        const int slot = RS_SLOT[cand];
+        const double shortest = min_L[slot];
+        if ((shortest - tot) <= step || tot <= step) continue;
+        if (tot < shortest) min_L[slot] = tot;
         if (fabs(tot / maxc) < best_L) { best_L = fabs(tot / maxc); best = cand; }
     }
     if (best < 0) return e;
