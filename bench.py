@@ -476,10 +476,10 @@ def main():
         roofline = dict(kernel="rrtstar_kernel", bound="fp64", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
                         frac=achieved / fp64_peak if achieved else None,
                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of THIS build at the default workload
-                        # (ncu --set full, profiles/r2e_rrtstar_kernel_ncu_summary.txt: 8.168 + 2.203 GB; bench.py cannot
+                        # (ncu --set full, profiles/r2k_rrtstar_kernel_ncu_summary.txt: 7.891 + 2.149 GB; bench.py cannot
                         # read hardware counters itself -- re-captured whenever the kernel changes)
-                        traffic=10.371e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
-                        traffic_source="profiles/r2e_rrtstar_kernel_ncu_summary.txt",
+                        traffic=10.040e9 if (Q, iters, n_obs) == (4096, 2000, 256) else None, traffic_unit="bytes/launch",
+                        traffic_source="profiles/r2k_rrtstar_kernel_ncu_summary.txt",
                         peak_source="FMA-loop probe measured in this run (rrtk_fma_peak_dev); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                         algorithmic_flop_per_iter=alg["flop_per_iter"], algorithmic_note=alg["note"],

@@ -162,39 +162,40 @@ class _DubinsSteps:
         nd.parent = from_node
         return nd
 
+    def _course_ok(self, a, b):
+        """steer(a, b) and whether its course is collision free (None / False when there is no course)."""
+        e = self.steer(a, b)
+        return e, bool(e) and self.check_collision(e, self.obstacle_list, self.robot_radius)
+
     def choose_parent(self, new_node, near_inds):
-        """rrt_05:1648-1689: the near node with the cheapest (Euclidean, :1777-1779) cost over a collision-free course."""
+        """rrt_05:1648-1689: the near node with the cheapest (Euclidean, :1777-1779) cost over a collision-free course;
+        first minimum in list order, None when every course is blocked."""
         if not near_inds:
             return None
-        costs = []
-        for i in near_inds:
-            near_node = self.node_list[i]
-            t_node = self.steer(near_node, new_node)
-            if t_node and self.check_collision(t_node, self.obstacle_list, self.robot_radius):
-                costs.append(self.calc_new_cost(near_node, new_node))
-            else:
-                costs.append(float("inf"))
-        min_cost = min(costs)
-        if min_cost == float("inf"):
+        costs = [self.calc_new_cost(self.node_list[i], new_node) if self._course_ok(self.node_list[i], new_node)[1] else math.inf
+                 for i in near_inds]
+        best = min(costs)
+        if best == math.inf:
             return None
-        new_node = self.steer(self.node_list[near_inds[costs.index(min_cost)]], new_node)
-        new_node.cost = min_cost
-        return new_node
+        chosen = self.steer(self.node_list[near_inds[costs.index(best)]], new_node)
+        chosen.cost = best
+        return chosen
 
     def rewire(self, new_node, near_inds):
-        """rrt_05:1741-1775."""
+        """rrt_05:1741-1775: in list order, a near node that new_node reaches cheaper over a collision-free course is replaced
+        by the end of that course (it MOVES there), its children follow and their costs are refreshed."""
         for i in near_inds:
-            near_node = self.node_list[i]
-            edge_node = self.steer(new_node, near_node)
-            if not edge_node:
+            old = self.node_list[i]
+            via, free = self._course_ok(new_node, old)
+            if via is None:
                 continue
-            edge_node.cost = self.calc_new_cost(new_node, near_node)
-            if self.check_collision(edge_node, self.obstacle_list, self.robot_radius) and near_node.cost > edge_node.cost:
-                for node in self.node_list:
-                    if node.parent is self.node_list[i]:
-                        node.parent = edge_node
-                self.node_list[i] = edge_node
-                self.propagate_cost_to_leaves(edge_node)
+            via.cost = self.calc_new_cost(new_node, old)
+            if free and old.cost > via.cost:
+                for child in self.node_list:
+                    if child.parent is old:
+                        child.parent = via
+                self.node_list[i] = via
+                self.propagate_cost_to_leaves(via)
 
 
 class RRTStarDubins(_DubinsSteps):
