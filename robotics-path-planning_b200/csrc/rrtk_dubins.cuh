@@ -69,57 +69,46 @@ static __device__ __forceinline__ DubTrig dubins_trig(double alpha, double beta)
 template <bool CR>
 static __device__ __noinline__ bool dubins_word(int k, double alpha, double beta, double d, const DubTrig &t, double *w,
                                                 bool *wrap = nullptr) {
+    // ONE body for the six word functions (rrt_05:1125-1198): they differ in signs only, so the expensive calls (atan2,
+    // acos, mod2pi) have one call site each instead of 8 / 2 / 16 -- this function was 11 KB of the kernel's 36 KB hot
+    // code, and the kernel is bound by instruction fetch.  Every sub-expression is SELECTED between the forms the reference
+    // writes (never multiplied by +-1: the sign of a zero decides atan2(+-0, x < 0) = +-pi), in the reference's order.
     const double sa = t.sa, ca = t.ca, sb = t.sb, cb = t.cb, cab = t.cab;
     const double d2 = d * d;
-    double p2, tmp, d1;
     auto at2 = [](double y, double x) { return CR ? crm_atan2(y, x) : atan2(y, x); };
     auto m2p = [&](double x) {
         const double v = mod2pi(x);
         if (!CR && (v < 1e-9 || v > D_TWO_PI - 1e-9)) *wrap = true;
         return v;
     };
-    switch (k) {
-        case 0:
-            p2 = 2 + d2 - (2 * cab) + (2 * d * (sa - sb));
-            if (p2 < 0) return false;
-            tmp = at2((cb - ca), d + sa - sb);
-            w[0] = m2p(-alpha + tmp); w[1] = sqrt(p2); w[2] = m2p(beta - tmp);
-            return true;
-        case 1:
-            p2 = 2 + d2 - (2 * cab) + (2 * d * (sb - sa));
-            if (p2 < 0) return false;
-            tmp = at2((ca - cb), d - sa + sb);
-            w[0] = m2p(alpha - tmp); w[1] = sqrt(p2); w[2] = m2p(-beta + tmp);
-            return true;
-        case 2:
-            p2 = -2 + d2 + (2 * cab) + (2 * d * (sa + sb));
-            if (p2 < 0) return false;
-            d1 = sqrt(p2);
-            tmp = at2((-ca - cb), (d + sa + sb)) - at2(-2.0, d1);
-            w[0] = m2p(-alpha + tmp); w[1] = d1; w[2] = m2p(-mod2pi(beta) + tmp);
-            return true;
-        case 3:
-            p2 = d2 - 2 + (2 * cab) - (2 * d * (sa + sb));
-            if (p2 < 0) return false;
-            d1 = sqrt(p2);
-            tmp = at2((ca + cb), (d - sa - sb)) - at2(2.0, d1);
-            w[0] = m2p(alpha - tmp); w[1] = d1; w[2] = m2p(beta - tmp);
-            return true;
-        case 4:
-            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
-            if (fabs(tmp) > 1.0) return false;
-            w[1] = m2p(2 * D_PI - (CR ? crm_acos(tmp) : acos(tmp)));
-            w[0] = m2p(alpha - at2(ca - cb, d - sa + sb) + w[1] / 2.0);
-            w[2] = m2p(alpha - beta - w[0] + w[1]);
-            return true;
-        default:
-            tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (-sa + sb)) / 8.0;
-            if (fabs(tmp) > 1.0) return false;
-            w[1] = m2p(2 * D_PI - (CR ? crm_acos(tmp) : acos(tmp)));
-            w[0] = m2p(-alpha - at2(ca - cb, d + sa - sb) + w[1] / 2.0);
-            w[2] = m2p(mod2pi(beta) - alpha - w[0] + m2p(w[1]));
-            return true;
+    // the atan2 every word takes: y = +-ca +-cb, x = (d +- sa) +- sb
+    //   LSL (cb - ca, d + sa - sb)   RSR (ca - cb, d - sa + sb)   LSR (-ca - cb, d + sa + sb)   RSL (ca + cb, d - sa - sb)
+    //   RLR (ca - cb, d - sa + sb)   LRL (ca - cb, d + sa - sb)
+    const double y = k == 0 ? cb - ca : (k == 2 ? -ca - cb : (k == 3 ? ca + cb : ca - cb));
+    const double x1 = (k == 0 || k == 2 || k == 5) ? d + sa : d - sa;
+    const double x = (k == 0 || k == 3 || k == 5) ? x1 - sb : x1 + sb;
+    if (k < 4) {   // CSC
+        const double s = k < 2 ? (k == 0 ? sa - sb : sb - sa) : sa + sb;
+        const double base = k < 2 ? 2 + d2 - (2 * cab) : d2 - 2 + (2 * cab);     // (-2 + d2 of LSR is the same double)
+        const double p2 = k == 3 ? base - (2 * d * s) : base + (2 * d * s);
+        if (p2 < 0) return false;
+        const double d1 = sqrt(p2);
+        double tmp = at2(y, x);
+        if (k >= 2) tmp = tmp - at2(k == 2 ? -2.0 : 2.0, d1);
+        const bool lfirst = (k & 1) == 0;   // LSL, LSR start with a left turn
+        w[0] = m2p(lfirst ? -alpha + tmp : alpha - tmp);
+        w[1] = d1;
+        w[2] = m2p(k == 0 || k == 3 ? beta - tmp : (k == 1 ? -beta + tmp : -mod2pi(beta) + tmp));
+        return true;
     }
+    // CCC
+    const double tmp = (6.0 - d2 + 2.0 * cab + 2.0 * d * (k == 4 ? sa - sb : -sa + sb)) / 8.0;
+    if (fabs(tmp) > 1.0) return false;
+    w[1] = m2p(2 * D_PI - (CR ? crm_acos(tmp) : acos(tmp)));
+    const double T = at2(y, x);
+    w[0] = m2p((k == 4 ? alpha - T : -alpha - T) + w[1] / 2.0);
+    w[2] = m2p(k == 4 ? alpha - beta - w[0] + w[1] : mod2pi(beta) - alpha - w[0] + mod2pi(w[1]));
+    return true;
 }
 
 // (Ruling words out with approximate lengths first -- dubins_word<false> -- was tried: the lanes of a warp then disagree on
