@@ -36,7 +36,10 @@ static __device__ __forceinline__ double mod2pi(double t) {
     if (t < 0.0 && t > -D_TWO_PI) return t + D_TWO_PI;    // fmod = t (negative, non-zero): r += b, one rounding
     return mod2pi_slow(t);
 }
-static __device__ __forceinline__ double angle_mod_pi(double x) { return py_mod(x + D_PI, D_TWO_PI) - D_PI; }
+static __device__ __forceinline__ double angle_mod_pi(double x) { return mod2pi(x + D_PI) - D_PI; }
+// a / b, correctly rounded as always -- one out-of-line copy of the division sequence (~400 B of SASS per inline site,
+// ~15 sites per edge evaluator) instead of one per use
+static __device__ __noinline__ double div_rn(double a, double b) { return a / b; }
 
 static __device__ __forceinline__ void sincos_cr(double x, double *s, double *c) {
     crm_sincos(x, s, c);                 // (first-phase evaluation + double-double fallback, crmath.h)
@@ -125,14 +128,16 @@ static __device__ __forceinline__ void interp(double length, int type, double ka
                                        double so, double co, double sm, double cm, double *x, double *y,
                                        double *yaw) {
     if (type == 1) {
-        *x = ox + length / kappa * co;
-        *y = oy + length / kappa * so;
+        const double lk = div_rn(length, kappa);
+        *x = ox + lk * co;
+        *y = oy + lk * so;
         *yaw = oyaw;
     } else {
         double sl, cl;
         sincos_cr(length, &sl, &cl);
-        const double ldx = sl / kappa;
-        const double ldy = type == 0 ? (1.0 - cl) / kappa : (1.0 - cl) / -kappa;
+        const double ldx = div_rn(sl, kappa);
+        const double q = div_rn(1.0 - cl, kappa);
+        const double ldy = type == 0 ? q : -q;          // x / -k == -(x / k) exactly
         const double gdx = cm * ldx + sm * ldy;
         const double gdy = -sm * ldx + cm * ldy;
         *x = ox + gdx;
@@ -148,12 +153,13 @@ static __device__ __forceinline__ void interp(double length, int type, double ka
 // correctly rounded one for coordinates below 1e4; the verdict is accepted when every circle is cleared (or one is
 // entered) by more than a band of 1e-9 * (1 + R^2) in squared distance, and the point is re-evaluated with the correctly
 // rounded functions otherwise.  Segment end points (the next origin, the end pose) are always exact.
-static __device__ __forceinline__ void arc_fast(double length, int type, double kappa, double ox, double oy, double sm,
+static __device__ __forceinline__ void arc_fast(double length, int type, double rho, double ox, double oy, double sm,
                                                 double cm, double *x, double *y) {
     double sl, cl;
     sincos(length, &sl, &cl);
-    const double ldx = sl / kappa;
-    const double ldy = type == 0 ? (1.0 - cl) / kappa : (1.0 - cl) / -kappa;
+    const double ldx = sl * rho;                      // rho = 1 / kappa rounded: one more ulp, far inside the band
+    const double q = (1.0 - cl) * rho;
+    const double ldy = type == 0 ? q : -q;
     *x = ox + (cm * ldx + sm * ldy);
     *y = oy + (-sm * ldx + cm * ldy);
 }
@@ -185,19 +191,25 @@ static __device__ __forceinline__ bool prefilter_ok(double s_x, double s_y, doub
 //   type 0 = L, 1 = S, 2 = R;  (ox, oy) origin, (so, co) = sin / cos(origin yaw), (ex, ey) the segment's end point,
 //   length = the word length (arc angle in radians for L / R; negative = driven backwards, Reeds-Shepp: the same circle
 //   run through the other way);  (px, py) = the circle centre in the local frame
-static __device__ __forceinline__ bool circle_near_segment(int type, double kappa, double ox, double oy, double so, double co,
+//   aux = segment_aux(...): 1 / kappa for an arc, 1 / |end - origin|^2 for a straight piece (per segment, not per circle)
+static __device__ __forceinline__ double segment_aux(int type, double rho, double ox, double oy, double ex, double ey) {
+    if (type != 1) return rho;
+    const double wx = ex - ox, wy = ey - oy, l2 = wx * wx + wy * wy;
+    return l2 > 0.0 ? 1.0 / l2 : 0.0;
+}
+static __device__ __forceinline__ bool circle_near_segment(int type, double aux, double ox, double oy, double so, double co,
                                                            double ex, double ey, double length, double px, double py,
                                                            double R) {
     const double m = R + 1e-7, m2 = m * m;
     if (type == 1) {
-        const double wx = ex - ox, wy = ey - oy, l2 = wx * wx + wy * wy;
+        const double wx = ex - ox, wy = ey - oy;
         const double ax = px - ox, ay = py - oy;
-        double t = l2 > 0.0 ? (ax * wx + ay * wy) / l2 : 0.0;
+        double t = (ax * wx + ay * wy) * aux;
         t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
         const double qx = ax - t * wx, qy = ay - t * wy;
         return qx * qx + qy * qy <= m2;
     }
-    const double rho = 1.0 / kappa, sgn = type == 0 ? 1.0 : -1.0;
+    const double rho = aux, sgn = type == 0 ? 1.0 : -1.0;
     const double cx = ox - sgn * rho * so, cy = oy + sgn * rho * co;
     const double vx = px - cx, vy = py - cy;
     const double dc = sqrt(vx * vx + vy * vy);
@@ -265,11 +277,12 @@ static __device__ __noinline__ DubEdge dubins_edge(double s_x, double s_y, doubl
     if (bi == 0x7fffffff) return e;
     if (lengths_out) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) lengths_out[k] = len[k] / kappa;
+        for (int k = 0; k < 3; k++) lengths_out[k] = div_rn(len[k], kappa);
     }
     // rot_mat_2d(-s_yaw): the correctly rounded sin / cos are odd / even bit for bit, so c2 = c and s2 = -s exactly
     const double c2 = c, s2 = -s;
     const bool filt = prefilter_ok(s_x, s_y, g_x, g_y, kappa);
+    const double rho = 1.0 / kappa;                   // the approximate tests' radius (the exact points divide by kappa)
     const bool tester = !warp || lane == 0;          // who tests the segment end points
     const int jstep = warp ? 32 : 1;
     bool hit = false;
@@ -298,10 +311,11 @@ static __device__ __noinline__ DubEdge dubins_edge(double s_x, double s_y, doubl
         if (tester) test(lx, ly);
         // segment-level cull (circle_near_segment); in warp mode the lanes split the circles
         bool near = !filt;
+        const double aux = segment_aux(type, rho, ox, oy, lx, ly);
         for (int o = warp ? lane : 0; o < n_obs && !near; o += jstep) {
             const double4 ob = obs[o];
             const double ux = ob.x - s_x, uy = ob.y - s_y;
-            near = circle_near_segment(type, kappa, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
+            near = circle_near_segment(type, aux, ox, oy, so, co, lx, ly, length, fma(uy, s, ux * c), fma(uy, c, ux * -s), ob.z);
         }
         if (warp) near = __any_sync(FULL, near);
         if (near && !hit) {
@@ -312,7 +326,7 @@ static __device__ __noinline__ DubEdge dubins_edge(double s_x, double s_y, doubl
                 int v = -1;
                 if (filt && type != 1) {
                     double x, y;
-                    arc_fast(cur, type, kappa, ox, oy, sm, cm, &x, &y);
+                    arc_fast(cur, type, rho, ox, oy, sm, cm, &x, &y);
                     v = circle_verdict(fma(y, s2, x * c2) + s_x, fma(y, c2, x * -s2) + s_y, obs, n_obs);
                 }
                 if (v < 0) {

@@ -166,14 +166,16 @@ static __device__ __noinline__ bool rs_word(int f, double x, double y, double ph
 static __device__ __forceinline__ void rs_interp(double dist, int type, double maxc, double ox, double oy, double oyaw,
                                                  double so, double co, double sm, double cm, double *x, double *y, double *yaw) {
     if (type == 1) {
-        *x = ox + dist / maxc * co;
-        *y = oy + dist / maxc * so;
+        const double lk = div_rn(dist, maxc);
+        *x = ox + lk * co;
+        *y = oy + lk * so;
         *yaw = oyaw;
     } else {
         double sl, cl;
         sincos_cr(dist, &sl, &cl);
-        const double ldx = sl / maxc;
-        const double ldy = type == 0 ? (1.0 - cl) / maxc : (1.0 - cl) / -maxc;
+        const double ldx = div_rn(sl, maxc);
+        const double q = div_rn(1.0 - cl, maxc);
+        const double ldy = type == 0 ? q : -q;          // x / -k == -(x / k) exactly
         *yaw = type == 0 ? oyaw + dist : oyaw - dist;
         const double gdx = cm * ldx + sm * ldy;
         const double gdy = -sm * ldx + cm * ldy;
@@ -230,8 +232,9 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         const double shortest = min_L[slot];
         if ((shortest - tot) <= step || tot <= step) continue;   // (inf - tot = inf: nothing of this type string inserted yet)
         if (tot < shortest) min_L[slot] = tot;
-        if (fabs(tot / maxc) < best_L) {
-            best_L = fabs(tot / maxc); best = cand;
+        const double tl = fabs(div_rn(tot, maxc));
+        if (tl < best_L) {
+            best_L = tl; best = cand;
             for (int i = 0; i < 5; i++) best_d[i] = (k == 1 || k == 3) ? -d[i] : d[i];   // timeflip
         }
     }
@@ -239,13 +242,14 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
     const int f = best >> 2, k = best & 3, n = RS_N[f];
     if (lengths_only) {
         double ls = 0.0;
-        for (int i = 0; i < n; i++) ls = ls + fabs(best_d[i] / maxc);
+        for (int i = 0; i < n; i++) ls = ls + fabs(div_rn(best_d[i], maxc));
         e.lsum = ls;
         e.npts = 1;
         return e;
     }
     const double sm0 = -s0, cm0 = c0;   // sin / cos(-syaw): the correctly rounded functions are odd / even bit for bit
     const bool filt = prefilter_ok(sx, sy, gx, gy, maxc);
+    const double rho = 1.0 / maxc;                    // the segment cull's radius (approximate test)
     bool hit = false;
     int np = 1;
     double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
@@ -261,7 +265,7 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
 #pragma unroll 1
     for (int i = 0; i < n && !hit; i++) {
         const double length = best_d[i];
-        lsum = lsum + fabs(length / maxc);
+        lsum = lsum + fabs(div_rn(length, maxc));
         const int t0 = RS_T[f][i];
         const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;
         const double dd = length >= 0.0 ? step : -step;
@@ -276,10 +280,11 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         // segment-level cull (circle_near_segment, rrtk_dubins.cuh): the interior points lie on the arc / straight piece
         // between the origin and that last point; they are evaluated only when a circle comes near it
         bool near = !filt;
+        const double aux = segment_aux(type, rho, ox, oy, lx, ly);
         for (int o = 0; o < n_obs && !near && !hit; o++) {
             const double4 ob = obs[o];
             const double ux = ob.x - sx, uy = ob.y - sy;
-            near = circle_near_segment(type, maxc, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
+            near = circle_near_segment(type, aux, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
         }
         if (near && !hit) {
 #pragma unroll 1
@@ -344,7 +349,7 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
 #pragma unroll 1
     for (int cand = 0; cand < 48; cand++) {
         if (!W.ok[cand]) continue;
-        const int f = cand >> 2, k = cand & 3, n = RS_N[f];
+        const int f = cand >> 2, n = RS_N[f];
         double tot = 0.0;
         for (int i = 0; i < n; i++) tot += fabs(W.d[cand][i]);
         for (int i = 0; i < n; i++) {
@@ -355,12 +360,14 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
         const double shortest = min_L[slot];
         if ((shortest - tot) <= step || tot <= step) continue;
         if (tot < shortest) min_L[slot] = tot;
-        if (fabs(tot / maxc) < best_L) { best_L = fabs(tot / maxc); best = cand; }
+        const double tl = fabs(div_rn(tot, maxc));
+        if (tl < best_L) { best_L = tl; best = cand; }
     }
     if (best < 0) return e;
     const int f = best >> 2, k = best & 3, n = RS_N[f];
     const double sm0 = -s0, cm0 = c0;   // sin / cos(-syaw), exactly (see rs_edge_lane)
     const bool filt = prefilter_ok(sx, sy, gx, gy, maxc);
+    const double rho = 1.0 / maxc;                    // the segment cull's radius (approximate test)
     bool hit = false;
     int np = 1;
     double ox = 0.0, oy = 0.0, oyaw = 0.0, lsum = 0.0;
@@ -377,7 +384,7 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
     for (int i = 0; i < n; i++) {
         double length = W.d[best][i];
         if (k == 1 || k == 3) length = -length;   // timeflip
-        lsum = lsum + fabs(length / maxc);
+        lsum = lsum + fabs(div_rn(length, maxc));
         const int t0 = RS_T[f][i];
         const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;
         const double dd = length >= 0.0 ? step : -step;
@@ -390,10 +397,11 @@ static __device__ __noinline__ RsEdge rs_edge_warp(double sx, double sy, double 
         rs_interp(length, type, maxc, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);
         if (lane == 0) test(lx, ly);
         bool near = !filt;     // segment-level cull, the lanes split the circles
+        const double aux = segment_aux(type, rho, ox, oy, lx, ly);
         for (int o = lane; o < n_obs && !near; o += 32) {
             const double4 ob = obs[o];
             const double ux = ob.x - sx, uy = ob.y - sy;
-            near = circle_near_segment(type, maxc, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
+            near = circle_near_segment(type, aux, ox, oy, so, co, lx, ly, length, c0 * ux + s0 * uy, -s0 * ux + c0 * uy, ob.z);
         }
         if (__any_sync(FULL, near)) {
 #pragma unroll 1
