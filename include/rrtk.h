@@ -382,7 +382,10 @@ typedef struct rrtk_dubins_params {
     int32_t rs_cost;                /* rrtk_rrtstar_rs_run_dev only.  0: rrt_06 (Euclidean costs, the later calc_new_cost wins);
                                      * 1: rrt_10:1005-1207 -- choose_parent / rewire / propagate_cost_to_leaves cost an edge by
                                      * its Reeds-Shepp length (calc_new_cost :1153-1161) */
-    int32_t pad_;
+    int32_t exec_mode;              /* the RRT* planners (rrtk_rrtstar_dubins_run_dev, rrtk_rrtstar_rs_run_dev): RRTK_EXEC_WARP =
+                                     * one warp per query, RRTK_EXEC_CTA = one CTA of 4 warps per query (the candidates of
+                                     * choose_parent / rewire spread over 128 threads), RRTK_EXEC_AUTO (0) = CTA while the batch
+                                     * is at most one wave of CTAs.  Results are bit-identical. */
 } rrtk_dubins_params;
 
 /*   start_goal6 [Q][6] = sx, sy, syaw, gx, gy, gyaw;  obstacles [Q][obs_stride][4] = x, y, size + rr, (size + rr)**2;

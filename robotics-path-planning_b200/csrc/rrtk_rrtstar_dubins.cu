@@ -7,6 +7,11 @@
 //   * goal test by xy and yaw thresholds, minimum cost, index 0 counts as "not found" (:1445, :1691-1712).
 // Each edge (6 words + sampled course + collision) is evaluated by one lane (rrtk_dubins.cuh); the first steer
 // of an iteration is uniform, choose_parent and rewire run one lane per near candidate.
+// TW = 1: one warp per query (the batch fills the GPU).  TW = 4: one CTA per query, for batches of at most one wave of
+// CTAs -- the near lists here hold most of the tree (the radius is ~10 in a 17 x 17 area), so an iteration is
+// ceil(count / 32) rounds of edge evaluations per warp, and four warps cut that chain.  Every warp of the team runs the
+// same control flow on the same data (nearest, the first edge, the near list: recomputed per warp, no exchange); the
+// candidates of choose_parent and of rewire's edge phase are split over the 128 threads; warp 0 alone appends and applies.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -100,7 +105,7 @@ static __device__ __noinline__ void propagate_lists_rs(int root, const double2 *
 // choose_parent / rewire / propagate (the host passes an unclipped near radius table, rrt_10:521-523).
 // STEER = 1 also runs rrt_06's try_goal_path after every append (:1572-1582): the new node is steered to the goal and
 // that node is appended too when its course is free, costing the Reeds-Shepp length (:1601).
-template <int STEER>
+template <int STEER, int TW>
 __global__ void __launch_bounds__(DUB_WARPS_PER_CTA * 32, 3)
 rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goal6,
                       const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
@@ -108,24 +113,42 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                       double *yaw_all, double *cost_all, int32_t *parent_all, double *edge_from_all,
                       double *edge_to_all, int32_t *n_nodes, int32_t *iters_done, int32_t *goal_index,
                       int32_t *status_out, int32_t *workspace, unsigned int *counter) {
+    static_assert(TW == 1 || TW == DUB_WARPS_PER_CTA, "a team is one warp or the whole CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
+    __shared__ double t_red[DUB_WARPS_PER_CTA][4];   // team reduction of choose_parent: cost, end pose of each warp's best
+    __shared__ int t_bk[DUB_WARPS_PER_CTA];
+    __shared__ unsigned int t_q;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool lead = TW == 1 || warp == 0;           // the warp that writes the tree
+    const int kfirst = TW == 1 ? lane : (int)threadIdx.x, kstride = 32 * TW;   // candidate split
     const int near_cap = p.near_cap;
-    unsigned char *base = smem_raw + (size_t)(threadIdx.x >> 5) * dub_warp_smem_bytes(near_cap, p.node_cap);
+    unsigned char *base = smem_raw + (size_t)warp * dub_warp_smem_bytes(near_cap, p.node_cap);
     double *nd = reinterpret_cast<double *>(base);
     double *s_end = nd + near_cap;  // [near_cap][3]
     double *s_c = s_end + 3 * near_cap;
     int *near_idx = reinterpret_cast<int *>(s_c + near_cap);
     int *flags = near_idx + near_cap;
     int *qtail = flags + near_cap;
+    // rewire's edge phase writes warp 0's arrays (the warp that applies); every warp keeps its own copy of the near list
+    double *nd0 = TW == 1 ? nd : reinterpret_cast<double *>(smem_raw);
+    double *s_end0 = nd0 + near_cap, *s_c0 = s_end0 + 3 * near_cap;
+    int *flags0 = reinterpret_cast<int *>(s_c0 + near_cap) + near_cap;
+    auto team_sync = [&]() { if (TW > 1) __syncthreads(); else __syncwarp(); };
     RsWarp &rsw = *reinterpret_cast<RsWarp *>(base + dub_warp_smem_bytes(near_cap, p.node_cap) - ((sizeof(RsWarp) + 15) & ~(size_t)15));
     const double INF = CUDART_INF;
     const double kappa = p.curvature, step = p.step_size;
 
     for (;;) {
         unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(counter, 1u);
-        q = __shfl_sync(FULL, q, 0);
+        if (TW > 1) {
+            __syncthreads();   // (the previous query's t_q has been read)
+            if (threadIdx.x == 0) t_q = atomicAdd(counter, 1u);
+            __syncthreads();
+            q = t_q;
+        } else {
+            if (lane == 0) q = atomicAdd(counter, 1u);
+            q = __shfl_sync(FULL, q, 0);
+        }
         if (q >= (unsigned)p.n_queries) break;
         const double *sg = start_goal6 + 6 * (size_t)q;
         const double sx = sg[0], sy = sg[1], syaw = sg[2], gx = sg[3], gy = sg[4], gyaw = sg[5];
@@ -139,11 +162,10 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
         double *eto = edge_to_all + (size_t)q * p.node_cap * 3;
         int4 *links = reinterpret_cast<int4 *>(workspace + (size_t)q * 4 * p.node_cap);   // children lists (rrtk_planner.cuh)
         const double *stream = stream3 + (size_t)q * p.max_iter * 3;
-        if (lane == 0) {
+        if (lead && lane == 0) {
             xy[0] = make_double2(sx, sy); yaw[0] = syaw; cost[0] = 0.0; parent[0] = -1; links[0] = make_int4(-1, -1, -1, 0);
             for (int k = 0; k < 3; k++) { efrom[k] = 0.0; eto[k] = 0.0; }
         }
-        __syncwarp();
         int n = 1, status = RRTK_Q_OK, gi = -1, it = 0;
         bool done = false;
 
@@ -163,6 +185,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
         };
 
         for (it = 0; it < p.max_iter; it++) {
+            team_sync();   // what the lead warp wrote in the previous iteration is visible; t_red may be reused
             const double rx = stream[3 * it], ry = stream[3 * it + 1], ryaw = stream[3 * it + 2];
             // nearest on xy (rrt_05:1605-1610)
             double bd = INF;
@@ -219,7 +242,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                 double mc = INF, bex = 0.0, bey = 0.0, beyaw = 0.0;
                 int bk = 0x7fffffff;
 #pragma unroll 1
-                for (int k = lane; k < count; k += 32) {
+                for (int k = kfirst; k < count; k += kstride) {
                     const int i = near_idx[k];
                     const double2 a = xy[i];
                     const PEdge e = plan_edge<STEER>(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
@@ -229,14 +252,28 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     }
                 }
                 warp_argmin(mc, bk);
-                if (bk != 0x7fffffff) {
+                double cx = 0.0, cy = 0.0, cyaw = 0.0;
+                if (bk != 0x7fffffff) {   // (candidate k sits on lane k & 31 of its warp)
                     const int src = bk & 31;
-                    const double cx = __shfl_sync(FULL, bex, src), cy = __shfl_sync(FULL, bey, src);
-                    const double cyaw = __shfl_sync(FULL, beyaw, src);
+                    cx = __shfl_sync(FULL, bex, src); cy = __shfl_sync(FULL, bey, src); cyaw = __shfl_sync(FULL, beyaw, src);
+                }
+                if (TW > 1) {   // the first minimum over the team's warps
+                    if (lane == 0) { t_red[warp][0] = mc; t_red[warp][1] = cx; t_red[warp][2] = cy; t_red[warp][3] = cyaw; t_bk[warp] = bk; }
+                    __syncthreads();
+                    mc = t_red[0][0]; bk = t_bk[0];
+                    int bw = 0;
+                    for (int w = 1; w < TW; w++) {
+                        const double cw = t_red[w][0];
+                        const int kw = t_bk[w];
+                        if (cw < mc || (cw == mc && kw < bk)) { mc = cw; bk = kw; bw = w; }
+                    }
+                    cx = t_red[bw][1]; cy = t_red[bw][2]; cyaw = t_red[bw][3];
+                }
+                if (bk != 0x7fffffff) {
                     const int best = near_idx[bk];
                     const int newi = n;
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lead && lane == 0) {
                         const double2 b = xy[best];
                         efrom[3 * newi] = b.x; efrom[3 * newi + 1] = b.y; efrom[3 * newi + 2] = yaw[best];
                         eto[3 * newi] = nx; eto[3 * newi + 1] = ny; eto[3 * newi + 2] = nyaw;
@@ -252,7 +289,7 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     // whose node does not cost more than that NOW is not planned (flag 8); phase B looks at it again with the
                     // node's cost at its turn (a re-parented node moves, so costs can go either way).
 #pragma unroll 1
-                    for (int k = lane; k < count; k += 32) {
+                    for (int k = kfirst; k < count; k += kstride) {
                         const int i = near_idx[k];
                         const double2 a = xy[i];
                         const double ci = cost[i];
@@ -265,15 +302,15 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                             if (STEER == 2) ec = mc + e.lsum;
                             ex = e.ex; ey = e.ey; eyw = e.eyaw;
                         }
-                        flags[k] = fl;
-                        nd[k] = ec;
-                        s_c[k] = ci;
-                        s_end[3 * k] = ex; s_end[3 * k + 1] = ey; s_end[3 * k + 2] = eyw;
+                        flags0[k] = fl;
+                        nd0[k] = ec;
+                        s_c0[k] = ci;
+                        s_end0[3 * k] = ex; s_end0[3 * k + 1] = ey; s_end0[3 * k + 2] = eyw;
                     }
-                    __syncwarp();
+                    team_sync();
                     // phase B: apply in list order.  s_c is the current cost of every entry's node (refreshed after each
                     // re-parenting), so the lanes can find the next entry that can act without walking the list one by one.
-                    for (int k0 = 0; k0 < count;) {
+                    for (int k0 = 0; lead && k0 < count;) {
                         bool need = false;
                         if (k0 + lane < count) {
                             const int fl = flags[k0 + lane];
@@ -316,11 +353,12 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                         }
                     }
                     if (STEER >= 1) {   // try_goal_path (rrt_06:1572-1582), from the new node as it is now
+                        team_sync();
                         const double2 a = xy[newi];
                         const double ayaw = yaw[newi];
                         const PEdge eg = plan_edge_warp<STEER>(a.x, a.y, ayaw, gx, gy, gyaw, kappa, step, obs, n_obs, lane, rsw);
                         if (eg.valid && eg.free_) {
-                            if (lane == 0) {
+                            if (lead && lane == 0) {
                                 efrom[3 * n] = a.x; efrom[3 * n + 1] = a.y; efrom[3 * n + 2] = ayaw;
                                 eto[3 * n] = gx; eto[3 * n + 1] = gy; eto[3 * n + 2] = gyaw;
                                 xy[n] = make_double2(eg.ex, eg.ey); yaw[n] = eg.eyaw; cost[n] = cost[newi] + eg.lsum; parent[n] = newi;
@@ -334,13 +372,15 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                 }
             }
             if (!p.search_until_max_iter && truthy) {
+                team_sync();
                 gi = best_goal();
                 if (gi > 0) { it++; done = true; break; }
             }
         }
+        team_sync();
         if (!done) gi = best_goal();
         if (gi <= 0) gi = -1;  // `if last_index:` -- index 0 is falsy (rrt_05:1445, :1451)
-        if (lane == 0) {
+        if (lead && lane == 0) {
             n_nodes[q] = n;
             iters_done[q] = it;
             goal_index[q] = gi;
@@ -490,16 +530,31 @@ int launch_rrtstar_steer(int steer, const rrtk_dubins_params &p, const double *s
     typedef void (*kernel_t)(rrtk_dubins_params, const double *, const double4 *, const int32_t *, const double *, const double *,
                              double2 *, double *, double *, int32_t *, double *, double *, int32_t *, int32_t *, int32_t *,
                              int32_t *, int32_t *, unsigned int *);
-    const kernel_t kern = steer == 2 ? rrtstar_dubins_kernel<2> : steer == 1 ? rrtstar_dubins_kernel<1> : rrtstar_dubins_kernel<0>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
+    const kernel_t kern_w = steer == 2 ? rrtstar_dubins_kernel<2, 1> : steer == 1 ? rrtstar_dubins_kernel<1, 1> : rrtstar_dubins_kernel<0, 1>;
+    const kernel_t kern_c = steer == 2 ? rrtstar_dubins_kernel<2, DUB_WARPS_PER_CTA>
+                          : steer == 1 ? rrtstar_dubins_kernel<1, DUB_WARPS_PER_CTA> : rrtstar_dubins_kernel<0, DUB_WARPS_PER_CTA>;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // execution: a CTA per query while the batch is at most two CTAs per SM (the chain of a query is what a launch of
+    // that size takes), a warp per query beyond
+    bool cta = p.exec_mode == RRTK_EXEC_CTA;
+    if (p.exec_mode != RRTK_EXEC_CTA && p.exec_mode != RRTK_EXEC_WARP) {
+        cudaError_t e0 = cudaFuncSetAttribute(kern_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e0 != cudaSuccess) return set_cuda_error(e0, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
+        int per_c = 0;
+        e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_c, kern_c, DUB_WARPS_PER_CTA * 32, smem);
+        if (e0 != cudaSuccess) return set_cuda_error(e0, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (per_c > 2) per_c = 2;   // (measured: at three CTAs per SM the teams contend and a warp per query is faster)
+        cta = (long long)p.n_queries <= (long long)sms * (per_c < 1 ? 1 : per_c);
+    }
+    const kernel_t kern = cta ? kern_c : kern_w;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(rrtstar_dubins_kernel)");
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DUB_WARPS_PER_CTA * 32, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (per_sm < 1) per_sm = 1;
-    long long want = ((long long)p.n_queries + DUB_WARPS_PER_CTA - 1) / DUB_WARPS_PER_CTA;
+    long long want = cta ? (long long)p.n_queries : ((long long)p.n_queries + DUB_WARPS_PER_CTA - 1) / DUB_WARPS_PER_CTA;
     long long grid = (long long)sms * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;

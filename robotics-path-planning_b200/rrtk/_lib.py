@@ -60,7 +60,7 @@ class DubinsParams(C.Structure):
     _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
                 ("obs_stride", C.c_int32), ("near_cap", C.c_int32), ("search_until_max_iter", C.c_int32),
                 ("curvature", C.c_double), ("step_size", C.c_double), ("goal_xy_th", C.c_double),
-                ("goal_yaw_th", C.c_double), ("rs_cost", C.c_int32), ("pad_", C.c_int32)]
+                ("goal_yaw_th", C.c_double), ("rs_cost", C.c_int32), ("exec_mode", C.c_int32)]
 
 
 class ClosedLoopParams(C.Structure):

@@ -47,10 +47,11 @@ class Node:
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0,
               connect_circle_dist=50.0, curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5,
               search_until_max_iter=True, near_cap=256, device=None, steer="dubins", step_size=0.1, timing=None,
-              rs_cost=False):
+              rs_cost=False, exec_mode="auto"):
     """Q RRT*-Dubins (steer="dubins") or RRT*-Reeds-Shepp (steer="rs", rrt_06) queries in one launch.
     starts/goals [Q, 3]; streams [Q, max_iter, 3].  Returns a list of dicts (numpy arrays trimmed to n_nodes).
-    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch)."""
+    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch).
+    `exec_mode`: "warp" (a warp per query), "cta" (a CTA per query: small batches), "auto"; same results."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     starts = np.asarray(starts, dtype=np.float64).reshape(-1, 3)
@@ -64,6 +65,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robo
     p.curvature, p.step_size = float(curvature), 0.1 if steer == "dubins" else float(step_size)
     p.goal_xy_th, p.goal_yaw_th = float(goal_xy_th), float(goal_yaw_th)
     p.rs_cost = int(bool(rs_cost))          # rrt_10's RRTStarReedsShepp: Reeds-Shepp-length costs (steer="rs" only)
+    p.exec_mode = {"auto": 0, "warp": 1, "cta": 2}[exec_mode]
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     with torch.cuda.device(dev):
         d_sg, d_obs, d_cnt = t(np.hstack([starts, goals])), t(rows), t(counts)

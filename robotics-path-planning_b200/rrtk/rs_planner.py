@@ -43,12 +43,12 @@ class Node:
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius=0.0, connect_circle_dist=50.0,
               curvature=1.0, goal_yaw_th=np.deg2rad(1.0), goal_xy_th=0.5, search_until_max_iter=True, step_size=0.2,
-              near_cap=256, device=None, timing=None, rs_cost=False):
+              near_cap=256, device=None, timing=None, rs_cost=False, exec_mode="auto"):
     """Q RRT*-Reeds-Shepp queries in one launch (rrtk_rrtstar_rs_run_dev).  starts / goals [Q, 3]; streams [Q, max_iter, 3].
     rs_cost=True: rrt_10's variant (Reeds-Shepp-length costs; pass expand_dis=inf for its unclipped near radius)."""
     return _run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, streams, robot_radius, connect_circle_dist,
                       curvature, goal_yaw_th, goal_xy_th, search_until_max_iter, near_cap, device, steer="rs",
-                      step_size=step_size, timing=timing, rs_cost=rs_cost)
+                      step_size=step_size, timing=timing, rs_cost=rs_cost, exec_mode=exec_mode)
 
 
 def final_course(tree, start, goal, curvature, step_size):

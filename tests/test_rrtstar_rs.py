@@ -123,3 +123,41 @@ def test_gpu_batch_of_queries_matches_oracle(oracle_lib):
         t = out[q]
         assert t["n"] == ref["n"] and np.array_equal(t["parent"], ref["parent"]) and t["goal_index"] == ref["goal_index"]
         assert np.array_equal(t["x"], ref["x"]) and np.array_equal(t["cost"], ref["cost"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["dubins", "rs", "rs_cost"])
+def test_gpu_warp_and_cta_execution_agree_with_the_oracle(kind, oracle_lib):
+    """exec_mode: a warp per query and a CTA per query give the same trees bit for bit (and the oracle's), also when the
+    near lists span several rounds of the team (rs_cost: unclipped near radius) and when goals are reached early."""
+    from rrtk import dubins_planner as DP
+    O = oracle_lib
+    Q, iters = 10, 120
+    rng = np.random.default_rng(5)
+    obs = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (7, 5, 2), (9, 5, 2)]
+    streams = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-np.pi, np.pi, (Q, iters, 1))], axis=2)
+    starts = [[0.0, 0.0, 0.0]] * Q
+    goals = [[10.0, 10.0, 0.0]] * (Q // 2) + [[6.0, 10.0, 1.0]] * (Q - Q // 2)
+    streams[rng.integers(0, 101, (Q, iters)) <= 10] = (10.0, 10.0, 0.0)
+    expand = float("inf") if kind == "rs_cost" else 3.0
+    kw = dict(steer="dubins") if kind == "dubins" else dict(steer="rs", step_size=0.2, rs_cost=(kind == "rs_cost"))
+    outs = {}
+    for until in (True, False):
+        for mode in ("warp", "cta"):
+            outs[mode] = DP.run_batch(starts, goals, [obs] * Q, expand, iters, streams, robot_radius=0.3, near_cap=256,
+                                      search_until_max_iter=until, exec_mode=mode, **kw)
+        for q in range(Q):
+            a, b = outs["warp"][q], outs["cta"][q]
+            assert a["n"] == b["n"] and a["goal_index"] == b["goal_index"] and a["iters_done"] == b["iters_done"]
+            for k in ("parent", "x", "y", "yaw", "cost", "edge_from", "edge_to"):
+                assert np.array_equal(a[k], b[k], equal_nan=True), (kind, q, k)
+        for q in (0, Q - 1):
+            if kind == "dubins":
+                ref = O.rrtstar_dubins_run(starts[q], goals[q], obs, expand, iters, 0.3, 50.0, 1.0, np.deg2rad(1.0), 0.5, until,
+                                           streams[q], O.MATH_CR)
+            else:
+                ref = O.rrtstar_rs_run(starts[q], goals[q], obs, expand, iters, 0.3, 50.0, 1.0, np.deg2rad(1.0), 0.5, until,
+                                       streams[q], step_size=0.2, math_mode=O.MATH_CR, rs_cost=(kind == "rs_cost"))
+            t = outs["cta"][q]
+            assert t["n"] == ref["n"] and np.array_equal(t["parent"], ref["parent"]) and t["goal_index"] == ref["goal_index"]
+            assert np.array_equal(t["x"], ref["x"]) and np.array_equal(t["cost"], ref["cost"], equal_nan=True)
