@@ -523,6 +523,12 @@ RRTK_API int rrtk_fma_peak_dev(int fp64, int32_t iters, int32_t blocks, void *ou
 RRTK_API int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
                                const double *link_lengths, const double *obstacles, int32_t n_sets,
                                int32_t n_obs, uint8_t *grid, void *stream);
+/* The same grid, every cell evaluated on its own in the reference's order (one thread per cell; rrtk_arm_grid_dev
+ * rasterises whole rows and evaluates only the cells it cannot decide).  Same arguments, same result; kept as the
+ * cross-check of the rasteriser (tests) -- about 20x slower at M = 8192. */
+RRTK_API int rrtk_arm_grid_cells_dev(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
+                                     const double *link_lengths, const double *obstacles, int32_t n_sets,
+                                     int32_t n_obs, uint8_t *grid, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * astar_torus (arm02:113-184, with calc_heuristic_map :221-233 and find_neighbors :187-209) for Q queries at once:

@@ -96,7 +96,7 @@ int launch_rs_steer(int n_req, double maxc, double step_size, const double *from
                     const double *obstacles, int obs_stride, const int32_t *n_obs, int32_t *types, double *lengths, double *L,
                     int32_t *n_paths, double *end, int32_t *n_pts, uint8_t *free_flag, double *pts, int max_pts, cudaStream_t s);
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
-                    const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s);
+                    const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s, int cells_only);
 
 static int check_params(const rrtk_rrtstar_params *p) {
     if (!p) return set_error(RRTK_ERR_INVALID, "params is NULL");
@@ -498,7 +498,19 @@ int rrtk_arm_grid_dev(int32_t M, const double *theta, int32_t row0, int32_t n_ro
     if (n_rows == 0 || n_sets == 0) return RRTK_OK;
     if (!theta || !link_lengths || !grid || (n_obs > 0 && !obstacles)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
     return launch_arm_grid(M, theta, row0, n_rows, n_links, link_lengths, obstacles, n_sets, n_obs, grid,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, 0);
+}
+
+int rrtk_arm_grid_cells_dev(int32_t M, const double *theta, int32_t row0, int32_t n_rows, int32_t n_links,
+                            const double *link_lengths, const double *obstacles, int32_t n_sets, int32_t n_obs,
+                            uint8_t *grid, void *stream) {
+    if (M < 1 || row0 < 0 || n_rows < 0 || row0 + n_rows > M) return set_error(RRTK_ERR_INVALID, "bad M / row range");
+    if (n_links < 1 || n_links > 16) return set_error(RRTK_ERR_INVALID, "1 <= n_links <= 16");
+    if (n_sets < 0 || n_obs < 0) return set_error(RRTK_ERR_INVALID, "negative set / obstacle count");
+    if (n_rows == 0 || n_sets == 0) return RRTK_OK;
+    if (!theta || !link_lengths || !grid || (n_obs > 0 && !obstacles)) return set_error(RRTK_ERR_INVALID, "NULL pointer argument");
+    return launch_arm_grid(M, theta, row0, n_rows, n_links, link_lengths, obstacles, n_sets, n_obs, grid,
+                           (cudaStream_t)stream, 1);
 }
 
 int rrtk_astar_torus_dev(int32_t M, int32_t n_queries, const int32_t *start_goal, uint8_t *grids, int32_t *routes,

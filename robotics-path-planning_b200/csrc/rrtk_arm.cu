@@ -146,8 +146,178 @@ arm_grid_kernel(ArmParams p, const double *__restrict__ theta, const double *__r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row rasteriser.  With joint 1 fixed (one row of the grid) links 2..n are one stretch of length Ls = sum(link[1:]) that
+// turns about joint 1 with the column angle, and a circle (centre at distance d > r from joint 1, direction psi) is
+// touched exactly for the column angles within +-alpha of psi:
+//     alpha = asin(r / d)                                  if Ls reaches the tangent point (Ls >= sqrt(d^2 - r^2)),
+//     alpha = acos((d^2 + Ls^2 - r^2) / (2 d Ls))          if only the far end reaches in (d - r < Ls < that), none otherwise.
+// The columns are theta_list[j] = 2 (j - M // 2) pi / M, so each circle is a run of columns (mod M).  Per (row, set,
+// circle) the thread of that set computes the run twice: the CERTAIN one (alpha shrunk by 1e-7 rad and the ratios by 1e-9,
+// orders of magnitude above every rounding involved) and the POSSIBLE one (alpha grown by the same); the grid row of a set
+// is then written 32 cells at a time as the OR of the certain runs, and the few cells that are possible but not certain
+// (at most a couple per circle and row) are evaluated like the reference does -- arm_cell_hit: the joints by the
+// reference's running sums, per link the filter / exact sequence above.  The kernel writes M^2 S bytes and is bound by
+// that store stream instead of the FP64 pipe.
+// A theta array that is not the reference's list (checked on the device), or links that the stretch argument does not
+// cover, make every cell "possible": the result is still the reference's, cell by cell.
+constexpr int ARM_RASTER_THREADS = 256;
+
+// cell (joint 1 at p1, column angle a2) against the O circles of one set, links 2..n only -- the reference's sequence
+__device__ __noinline__ bool arm_cell_hit(const double *link, int n_links, int stretch, double p1x, double p1y, double a2,
+                                          const double *ob, int O) {
+    const double c2 = crm_cos(a2), s2 = crm_sin(a2);
+    double px[ARM_MAX_LINKS + 1], py[ARM_MAX_LINKS + 1];
+    px[1] = p1x; py[1] = p1y;
+    for (int k = 2; k <= n_links; k++) {
+        px[k] = px[k - 1] + link[k - 1] * c2;
+        py[k] = py[k - 1] + link[k - 1] * s2;
+    }
+    const double ex = px[n_links], ey = py[n_links];
+    const double u0 = ex - p1x, u1 = ey - p1y, U2 = fma(u1, u1, u0 * u0);
+    for (int o = 0; o < O; o++) {
+        const double cx = ob[4 * o], cy = ob[4 * o + 1], r2 = ob[4 * o + 3];
+        const int v = stretch ? link_circle_filter(p1x, p1y, ex, ey, U2, cx, cy, r2) : -1;
+        if (v > 0) return true;
+        if (v == 0) continue;
+        for (int k = 1; k < n_links; k++)
+            if (link_circle_hit(px[k], py[k], px[k + 1], py[k + 1], cx, cy, ob[4 * o + 2], r2)) return true;
+    }
+    return false;
+}
+
+// the cells k of [j0, j0 + 32) with ((j0 + k - lo) mod M) <= w, as a bit mask (w < 0: none)
+__device__ __forceinline__ unsigned span_bits(int lo, int w, int j0, int M) {
+    if (w < 0) return 0u;
+    if (w >= M - 1) return ~0u;
+    int d0 = j0 - lo;
+    if (d0 < 0) d0 += M;
+    unsigned m = 0u;
+    if (d0 <= w) { const int n = w - d0 + 1; m = n >= 32 ? ~0u : (1u << n) - 1u; }      // the run continues into the chunk
+    const int kb = M - d0;                                                                 // the run starts at cell kb
+    if (kb < 32) { const int n = w + 1; m |= (n >= 32 ? ~0u : (1u << n) - 1u) << kb; }
+    return m;
+}
+
+__global__ void __launch_bounds__(ARM_RASTER_THREADS)
+arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double *__restrict__ obstacles,
+                     uint8_t *__restrict__ grid, int vec_ok) {
+    extern __shared__ double s_obs[];  // [S * O][4]: x, y, r, r * r; then the runs [S * O] int4; then S row flags
+    const int n_circ = p.S * p.O;
+    int4 *s_run = reinterpret_cast<int4 *>(s_obs + 4 * (size_t)n_circ);   // certain (lo, w), possible (lo, w)
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_run + n_circ);
+    __shared__ double s_link[ARM_MAX_LINKS];
+    for (int t = threadIdx.x; t < n_circ; t += blockDim.x) {
+        double x = obstacles[3 * t], y = obstacles[3 * t + 1], r = obstacles[3 * t + 2];
+        s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r * r;
+    }
+    if (threadIdx.x < ARM_MAX_LINKS) s_link[threadIdx.x] = p.link[threadIdx.x];
+    const int M = p.M, off = -((M + 1) / 2);            // Python's -M // 2
+    // is theta the reference's list?  (2 * i * pi / M, i = j - M // 2 ...: the host evaluates it in Python floats)
+    bool bad = false;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const double want = 2.0 * (double)(j + off) * 3.141592653589793 / (double)M;
+        if (!(fabs(theta[j] - want) <= 1e-12)) bad = true;
+    }
+    const bool raster = !__syncthreads_or(bad) && p.stretch && p.n_links >= 2;
+    double Ls = 0.0;
+    for (int k = 1; k < p.n_links; k++) Ls += p.link[k];
+    const double m_per_rad = (double)M / 6.283185307179586;
+    const int nchunk = (M + 31) >> 5;
+    for (int ir = blockIdx.x; ir < p.n_rows; ir += gridDim.x) {
+        const int i = p.row0 + ir;
+        const double a1 = theta[i];
+        const double c1 = crm_cos(a1), s1 = crm_sin(a1);
+        const double p1x = 0.0 + p.link[0] * c1, p1y = 0.0 + p.link[0] * s1;   // points[1] (arm02:259-260)
+        __syncthreads();   // the previous row's runs and flags have been read
+        for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
+            const double *ob = s_obs + (size_t)s * p.O * 4;
+            bool hit = false;
+            for (int o = 0; o < p.O && !hit; o++)   // link 1: the same for the whole row
+                hit = link_circle_hit(0.0, 0.0, p1x, p1y, ob[4 * o], ob[4 * o + 1], ob[4 * o + 2], ob[4 * o + 3]);
+            s_row[s] = hit ? 1 : 0;
+            if (hit || p.n_links < 2) continue;
+            for (int o = 0; o < p.O; o++) {
+                int4 run = make_int4(0, -1, 0, M);   // certain: none, possible: every column
+                const double vx = ob[4 * o] - p1x, vy = ob[4 * o + 1] - p1y, r = ob[4 * o + 2];
+                const double d2 = vx * vx + vy * vy, d = sqrt(d2);
+                if (raster && d > r * (1.0 + 1e-9) + 1e-12 && d < 1e4 && Ls > 1e-6 && Ls < 1e4 && r >= 0.0) {
+                    const double em = 1e-9, ea = 1e-7;
+                    const double q = r / d, Lt = sqrt(d2 - r * r);
+                    const double at_out = asin(fmin(1.0, q + em)) + ea, at_in = q - em > 0.0 ? asin(q - em) - ea : -1.0;
+                    double a_out, a_in;
+                    if (Ls >= Lt * (1.0 + 1e-9)) { a_out = at_out; a_in = at_in; }
+                    else if (Ls <= (d - r) * (1.0 - 1e-9) - 1e-12) { a_out = -1.0; a_in = -1.0; }   // out of reach
+                    else {
+                        const double x = (d2 + Ls * Ls - r * r) / (2.0 * d * Ls);
+                        const double ae_out = x - em > 1.0 ? -1.0 : acos(fmax(-1.0, x - em)) + ea;
+                        const double ae_in = x + em >= 1.0 ? -1.0 : acos(fmax(-1.0, x + em)) - ea;
+                        a_out = Ls < Lt * (1.0 - 1e-9) ? ae_out : fmax(at_out, ae_out);
+                        a_in = fmin(at_in, ae_in);
+                    }
+                    const double psi = atan2(vy, vx);
+                    auto cells = [&](double a, int &lo, int &w) {   // columns j with |a1 + theta[j] - psi| <= a (mod 2 pi)
+                        if (a < 0.0) { lo = 0; w = -1; return; }
+                        if (a >= 3.14159) { lo = 0; w = M; return; }
+                        const double tl = (psi - a - a1) * m_per_rad - (double)off, th = (psi + a - a1) * m_per_rad - (double)off;
+                        const double fl = ceil(tl), fh = floor(th);
+                        if (fh < fl) { lo = 0; w = -1; return; }
+                        w = (int)(fh - fl);
+                        double lm = fmod(fl, (double)M);
+                        if (lm < 0.0) lm += (double)M;
+                        lo = (int)lm;
+                        if (lo >= M) lo -= M;
+                    };
+                    cells(a_in, run.x, run.y);
+                    cells(a_out, run.z, run.w);
+                }
+                s_run[s * p.O + o] = run;
+            }
+        }
+        __syncthreads();
+        uint8_t *row_out = grid + (size_t)ir * M;
+        const size_t set_stride = (size_t)p.n_rows * M;
+        for (int u = threadIdx.x; u < p.S * nchunk; u += blockDim.x) {
+            const int s = u / nchunk, j0 = (u - s * nchunk) << 5;
+            const int ncell = M - j0 < 32 ? M - j0 : 32;
+            unsigned bits = 0u;
+            if (s_row[s]) bits = ~0u;
+            else if (p.n_links >= 2) {
+                unsigned maybe = 0u;
+                for (int o = 0; o < p.O; o++) {
+                    const int4 run = s_run[s * p.O + o];
+                    bits |= span_bits(run.x, run.y, j0, M);
+                    if (run.z != run.x || run.w != run.y) maybe |= span_bits(run.z, run.w, j0, M);
+                }
+                maybe &= ~bits;
+                if (ncell < 32) maybe &= (1u << ncell) - 1u;
+                while (maybe) {   // possible but not certain: the reference's evaluation of the cell
+                    const int k = __ffs(maybe) - 1;
+                    maybe &= maybe - 1u;
+                    if (arm_cell_hit(s_link, p.n_links, p.stretch, p1x, p1y, a1 + theta[j0 + k], s_obs + (size_t)s * p.O * 4, p.O))
+                        bits |= 1u << k;
+                }
+            }
+            uint8_t *out = row_out + (size_t)s * set_stride + j0;
+            if (vec_ok && ncell == 32) {
+                uint4 v[2];
+                unsigned *w = reinterpret_cast<unsigned *>(v);
+#pragma unroll
+                for (int b = 0; b < 8; b++) {   // 4 cells per word: bit -> byte
+                    const unsigned n = (bits >> (4 * b)) & 15u;
+                    w[b] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+                }
+                reinterpret_cast<uint4 *>(out)[0] = v[0];
+                reinterpret_cast<uint4 *>(out)[1] = v[1];
+            } else {
+                for (int k = 0; k < ncell; k++) out[k] = (bits >> k) & 1u;
+            }
+        }
+    }
+}
+
 int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_links, const double *link_host,
-                    const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s) {
+                    const double *obstacles, int S, int O, uint8_t *grid, cudaStream_t s, int cells_only) {
     ArmParams p;
     p.M = M; p.row0 = row0; p.n_rows = n_rows; p.n_links = n_links; p.S = S; p.O = O;
     for (int k = 0; k < ARM_MAX_LINKS; k++) p.link[k] = k < n_links ? link_host[k] : 0.0;
@@ -156,6 +326,25 @@ int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_link
         if (!(link_host[k] > 0.0)) p.stretch = 0;
     size_t smem = (size_t)S * O * 4 * sizeof(double) + (((size_t)S + 15) & ~(size_t)15);
     if (smem > 200 * 1024) return set_error(RRTK_ERR_INVALID, "S * O circles do not fit in shared memory (max 6400)");
+    if (!cells_only) {   // the row rasteriser (every input: what it cannot rasterise it evaluates cell by cell)
+        const size_t smem_r = (size_t)S * O * (4 * sizeof(double) + sizeof(int4)) + (((size_t)S + 15) & ~(size_t)15);
+        if (smem_r <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(arm_grid_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(arm_grid_rows_kernel)");
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arm_grid_rows_kernel, ARM_RASTER_THREADS, smem_r);
+            if (per_sm < 1) per_sm = 1;
+            long long grid_dim = (long long)sms * per_sm;
+            if (grid_dim > n_rows) grid_dim = n_rows;
+            const int vec_ok = (M % 32 == 0) && (((uintptr_t)grid) % 16 == 0);
+            arm_grid_rows_kernel<<<(unsigned)grid_dim, ARM_RASTER_THREADS, smem_r, s>>>(p, theta, obstacles, grid, vec_ok);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return set_cuda_error(e, "arm_grid_rows_kernel launch");
+            return RRTK_OK;
+        }
+    }
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -122,6 +122,8 @@ _SIGS = {
     "rrtk_fma_peak_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _VP, _VP]),
     "rrtk_arm_grid_dev": (C.c_int, [C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.c_int32,
                                     C.c_int32, _VP, _VP]),
+    "rrtk_arm_grid_cells_dev": (C.c_int, [C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.c_int32,
+                                    C.c_int32, _VP, _VP]),
 }
 
 EXPORTED = tuple(_SIGS)
