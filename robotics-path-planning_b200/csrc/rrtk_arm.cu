@@ -201,18 +201,24 @@ __device__ __forceinline__ unsigned span_bits(int lo, int w, int j0, int M) {
 
 __global__ void __launch_bounds__(ARM_RASTER_THREADS)
 arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double *__restrict__ obstacles,
-                     uint8_t *__restrict__ grid, int vec_ok) {
-    extern __shared__ double s_obs[];  // [S * O][4]: x, y, r, r * r; then the runs [S * O] int4; then S row flags
-    const int n_circ = p.S * p.O;
-    int4 *s_run = reinterpret_cast<int4 *>(s_obs + 4 * (size_t)n_circ);   // certain (lo, w), possible (lo, w)
-    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_run + n_circ);
+                     uint8_t *__restrict__ grid, int vec_ok, int G) {
+    // [S * O][4] doubles: x, y, r, r * r | [S * O] int4 runs: certain (lo, w), possible (lo, w) | [G][W] row bitmaps of a
+    // group of G sets | S row flags | S "evaluate every cell" flags
+    extern __shared__ double s_obs[];
+    const int n_circ = p.S * p.O, M = p.M, W = (M + 31) >> 5;
+    int4 *s_run = reinterpret_cast<int4 *>(s_obs + 4 * (size_t)n_circ);
+    unsigned *s_bm = reinterpret_cast<unsigned *>(s_run + n_circ);
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_bm + (size_t)G * W);
+    uint8_t *s_all = s_row + p.S;
     __shared__ double s_link[ARM_MAX_LINKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int t = threadIdx.x; t < n_circ; t += blockDim.x) {
         double x = obstacles[3 * t], y = obstacles[3 * t + 1], r = obstacles[3 * t + 2];
         s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r * r;
     }
+    for (int t = threadIdx.x; t < G * W; t += blockDim.x) s_bm[t] = 0u;
     if (threadIdx.x < ARM_MAX_LINKS) s_link[threadIdx.x] = p.link[threadIdx.x];
-    const int M = p.M, off = -((M + 1) / 2);            // Python's -M // 2
+    const int off = -((M + 1) / 2);                     // Python's -M // 2
     // is theta the reference's list?  (2 * i * pi / M, i = j - M // 2 ...: the host evaluates it in Python floats)
     bool bad = false;
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
@@ -223,95 +229,123 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
     double Ls = 0.0;
     for (int k = 1; k < p.n_links; k++) Ls += p.link[k];
     const double m_per_rad = (double)M / 6.283185307179586;
-    const int nchunk = (M + 31) >> 5;
     for (int ir = blockIdx.x; ir < p.n_rows; ir += gridDim.x) {
         const int i = p.row0 + ir;
         const double a1 = theta[i];
         const double c1 = crm_cos(a1), s1 = crm_sin(a1);
         const double p1x = 0.0 + p.link[0] * c1, p1y = 0.0 + p.link[0] * s1;   // points[1] (arm02:259-260)
-        __syncthreads();   // the previous row's runs and flags have been read
-        for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
-            const double *ob = s_obs + (size_t)s * p.O * 4;
-            bool hit = false;
-            for (int o = 0; o < p.O && !hit; o++)   // link 1: the same for the whole row
-                hit = link_circle_hit(0.0, 0.0, p1x, p1y, ob[4 * o], ob[4 * o + 1], ob[4 * o + 2], ob[4 * o + 3]);
-            s_row[s] = hit ? 1 : 0;
-            if (hit || p.n_links < 2) continue;
-            for (int o = 0; o < p.O; o++) {
-                int4 run = make_int4(0, -1, 0, M);   // certain: none, possible: every column
-                const double vx = ob[4 * o] - p1x, vy = ob[4 * o + 1] - p1y, r = ob[4 * o + 2];
-                const double d2 = vx * vx + vy * vy, d = sqrt(d2);
-                if (raster && d > r * (1.0 + 1e-9) + 1e-12 && d < 1e4 && Ls > 1e-6 && Ls < 1e4 && r >= 0.0) {
-                    const double em = 1e-9, ea = 1e-7;
-                    const double q = r / d, Lt = sqrt(d2 - r * r);
-                    const double at_out = asin(fmin(1.0, q + em)) + ea, at_in = q - em > 0.0 ? asin(q - em) - ea : -1.0;
-                    double a_out, a_in;
-                    if (Ls >= Lt * (1.0 + 1e-9)) { a_out = at_out; a_in = at_in; }
-                    else if (Ls <= (d - r) * (1.0 - 1e-9) - 1e-12) { a_out = -1.0; a_in = -1.0; }   // out of reach
-                    else {
-                        const double x = (d2 + Ls * Ls - r * r) / (2.0 * d * Ls);
-                        const double ae_out = x - em > 1.0 ? -1.0 : acos(fmax(-1.0, x - em)) + ea;
-                        const double ae_in = x + em >= 1.0 ? -1.0 : acos(fmax(-1.0, x + em)) - ea;
-                        a_out = Ls < Lt * (1.0 - 1e-9) ? ae_out : fmax(at_out, ae_out);
-                        a_in = fmin(at_in, ae_in);
-                    }
-                    const double psi = atan2(vy, vx);
-                    auto cells = [&](double a, int &lo, int &w) {   // columns j with |a1 + theta[j] - psi| <= a (mod 2 pi)
-                        if (a < 0.0) { lo = 0; w = -1; return; }
-                        if (a >= 3.14159) { lo = 0; w = M; return; }
-                        const double tl = (psi - a - a1) * m_per_rad - (double)off, th = (psi + a - a1) * m_per_rad - (double)off;
-                        const double fl = ceil(tl), fh = floor(th);
-                        if (fh < fl) { lo = 0; w = -1; return; }
-                        w = (int)(fh - fl);
-                        double lm = fmod(fl, (double)M);
-                        if (lm < 0.0) lm += (double)M;
-                        lo = (int)lm;
-                        if (lo >= M) lo -= M;
-                    };
-                    cells(a_in, run.x, run.y);
-                    cells(a_out, run.z, run.w);
+        // ---- per (set, circle): link 1 (the same for the whole row), then the circle's runs ----
+        for (int t = threadIdx.x; t < p.S; t += blockDim.x) { s_row[t] = 0; s_all[t] = 0; }
+        __syncthreads();
+        for (int u = threadIdx.x; u < n_circ; u += blockDim.x) {
+            const int s = u / p.O;
+            const double *ob = s_obs + (size_t)u * 4;
+            if (link_circle_hit(0.0, 0.0, p1x, p1y, ob[0], ob[1], ob[2], ob[3])) s_row[s] = 1;   // (every writer writes 1)
+            if (p.n_links < 2) continue;
+            int4 run = make_int4(0, -1, 0, M);   // certain: none, possible: every column
+            const double vx = ob[0] - p1x, vy = ob[1] - p1y, r = ob[2];
+            const double d2 = vx * vx + vy * vy, d = sqrt(d2);
+            if (raster && d > r * (1.0 + 1e-9) + 1e-12 && d < 1e4 && Ls > 1e-6 && Ls < 1e4 && r >= 0.0) {
+                const double em = 1e-9, ea = 1e-7;
+                const double q = r / d, Lt = sqrt(d2 - r * r);
+                const double at_out = asin(fmin(1.0, q + em)) + ea, at_in = q - em > 0.0 ? asin(q - em) - ea : -1.0;
+                double a_out, a_in;
+                if (Ls >= Lt * (1.0 + 1e-9)) { a_out = at_out; a_in = at_in; }
+                else if (Ls <= (d - r) * (1.0 - 1e-9) - 1e-12) { a_out = -1.0; a_in = -1.0; }   // out of reach
+                else {
+                    const double x = (d2 + Ls * Ls - r * r) / (2.0 * d * Ls);
+                    const double ae_out = x - em > 1.0 ? -1.0 : acos(fmax(-1.0, x - em)) + ea;
+                    const double ae_in = x + em >= 1.0 ? -1.0 : acos(fmax(-1.0, x + em)) - ea;
+                    a_out = Ls < Lt * (1.0 - 1e-9) ? ae_out : fmax(at_out, ae_out);
+                    a_in = fmin(at_in, ae_in);
                 }
-                s_run[s * p.O + o] = run;
+                const double psi = atan2(vy, vx);
+                auto cells = [&](double a, int &lo, int &w) {   // columns j with |a1 + theta[j] - psi| <= a (mod 2 pi)
+                    if (a < 0.0) { lo = 0; w = -1; return; }
+                    if (a >= 3.14159) { lo = 0; w = M; return; }
+                    const double tl = (psi - a - a1) * m_per_rad - (double)off, th = (psi + a - a1) * m_per_rad - (double)off;
+                    const double fl = ceil(tl), fh = floor(th);
+                    if (fh < fl) { lo = 0; w = -1; return; }
+                    w = (int)(fh - fl);
+                    double lm = fl - floor(fl / (double)M) * (double)M;   // fl mod M (|fl| < 2^31: exact)
+                    if (lm < 0.0) lm += (double)M;
+                    lo = (int)lm;
+                    if (lo >= M) lo -= M;
+                };
+                cells(a_in, run.x, run.y);
+                cells(a_out, run.z, run.w);
             }
+            if (run.w >= M - 1 && run.y < M - 1) s_all[s] = 1;   // undecided everywhere: the set's row cell by cell
+            s_run[u] = run;
         }
         __syncthreads();
         uint8_t *row_out = grid + (size_t)ir * M;
         const size_t set_stride = (size_t)p.n_rows * M;
-        for (int u = threadIdx.x; u < p.S * nchunk; u += blockDim.x) {
-            const int s = u / nchunk, j0 = (u - s * nchunk) << 5;
-            const int ncell = M - j0 < 32 ? M - j0 : 32;
-            unsigned bits = 0u;
-            if (s_row[s]) bits = ~0u;
-            else if (p.n_links >= 2) {
-                unsigned maybe = 0u;
-                for (int o = 0; o < p.O; o++) {
-                    const int4 run = s_run[s * p.O + o];
-                    bits |= span_bits(run.x, run.y, j0, M);
-                    if (run.z != run.x || run.w != run.y) maybe |= span_bits(run.z, run.w, j0, M);
+        for (int g0 = 0; g0 < p.S; g0 += G) {
+            const int gn = p.S - g0 < G ? p.S - g0 : G;
+            // ---- paint: one warp per (set, circle); the certain run word by word, the few undecided cells one by one ----
+            if (p.n_links >= 2) {
+                for (int u = warp; u < gn * p.O; u += n_warps) {
+                    const int sl = u / p.O, s = g0 + sl;
+                    if (s_row[s] || s_all[s]) continue;
+                    const int4 run = s_run[s * p.O + (u - sl * p.O)];
+                    unsigned *bm = s_bm + (size_t)sl * W;
+                    if (run.y >= 0) {
+                        // words the run can reach into, from the one holding lo (one more when the last word of the row is
+                        // partial: fewer cells there before the run wraps to column 0)
+                        const int nw = ((run.y + 32) >> 5) + 2;
+                        for (int t = lane; t < nw && t < W; t += 32) {
+                            int wi = (run.x >> 5) + t;
+                            if (wi >= W) wi -= W;
+                            const unsigned m = span_bits(run.x, run.y, wi << 5, M);
+                            if (m) atomicOr(&bm[wi], m);
+                        }
+                    }
+                    if (run.z != run.x || run.w != run.y) {
+                        // possible but not certain: gl cells before the certain run, the rest after it (all of the possible
+                        // run when nothing is certain)
+                        int gl = run.w + 1, skip = 0;
+                        if (run.y >= 0) { gl = run.x - run.z; if (gl < 0) gl += M; skip = run.y + 1; }
+                        const int n_und = run.w + 1 - skip;
+                        for (int t = lane; t < n_und; t += 32) {
+                            int j = run.z + (t < gl ? t : t + skip);
+                            if (j >= M) j -= M;
+                            if (j >= M) j -= M;
+                            if (arm_cell_hit(s_link, p.n_links, p.stretch, p1x, p1y, a1 + theta[j], s_obs + (size_t)s * p.O * 4, p.O))
+                                atomicOr(&bm[j >> 5], 1u << (j & 31));
+                        }
+                    }
                 }
-                maybe &= ~bits;
-                if (ncell < 32) maybe &= (1u << ncell) - 1u;
-                while (maybe) {   // possible but not certain: the reference's evaluation of the cell
-                    const int k = __ffs(maybe) - 1;
-                    maybe &= maybe - 1u;
-                    if (arm_cell_hit(s_link, p.n_links, p.stretch, p1x, p1y, a1 + theta[j0 + k], s_obs + (size_t)s * p.O * 4, p.O))
-                        bits |= 1u << k;
+                for (int sl = 0; sl < gn; sl++) {   // sets to evaluate cell by cell (inputs the runs do not cover)
+                    const int s = g0 + sl;
+                    if (s_row[s] || !s_all[s]) continue;
+                    for (int j = threadIdx.x; j < M; j += blockDim.x)
+                        if (arm_cell_hit(s_link, p.n_links, p.stretch, p1x, p1y, a1 + theta[j], s_obs + (size_t)s * p.O * 4, p.O))
+                            atomicOr(&s_bm[(size_t)sl * W + (j >> 5)], 1u << (j & 31));
                 }
             }
-            uint8_t *out = row_out + (size_t)s * set_stride + j0;
-            if (vec_ok && ncell == 32) {
-                uint4 v[2];
-                unsigned *w = reinterpret_cast<unsigned *>(v);
+            __syncthreads();
+            // ---- emit: 32 cells per thread and step, bit -> byte; the bitmap is left cleared for the next group / row ----
+            for (int u = threadIdx.x; u < gn * W; u += blockDim.x) {
+                const int sl = u / W, wi = u - sl * W, s = g0 + sl, j0 = wi << 5;
+                const int ncell = M - j0 < 32 ? M - j0 : 32;
+                unsigned bits = s_bm[u];
+                s_bm[u] = 0u;
+                if (s_row[s]) bits = ~0u;
+                uint8_t *out = row_out + (size_t)s * set_stride + j0;
+                if (vec_ok && ncell == 32) {
+                    uint4 v[2];
+                    unsigned *w = reinterpret_cast<unsigned *>(v);
 #pragma unroll
-                for (int b = 0; b < 8; b++) {   // 4 cells per word: bit -> byte
-                    const unsigned n = (bits >> (4 * b)) & 15u;
-                    w[b] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
+                    for (int b = 0; b < 8; b++)   // 4 cells per word: bit k -> byte k (the shifted copies do not overlap)
+                        w[b] = (((bits >> (4 * b)) & 15u) * 0x00204081u) & 0x01010101u;
+                    reinterpret_cast<uint4 *>(out)[0] = v[0];
+                    reinterpret_cast<uint4 *>(out)[1] = v[1];
+                } else {
+                    for (int k = 0; k < ncell; k++) out[k] = (bits >> k) & 1u;
                 }
-                reinterpret_cast<uint4 *>(out)[0] = v[0];
-                reinterpret_cast<uint4 *>(out)[1] = v[1];
-            } else {
-                for (int k = 0; k < ncell; k++) out[k] = (bits >> k) & 1u;
             }
+            __syncthreads();
         }
     }
 }
@@ -327,8 +361,15 @@ int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_link
     size_t smem = (size_t)S * O * 4 * sizeof(double) + (((size_t)S + 15) & ~(size_t)15);
     if (smem > 200 * 1024) return set_error(RRTK_ERR_INVALID, "S * O circles do not fit in shared memory (max 6400)");
     if (!cells_only) {   // the row rasteriser (every input: what it cannot rasterise it evaluates cell by cell)
-        const size_t smem_r = (size_t)S * O * (4 * sizeof(double) + sizeof(int4)) + (((size_t)S + 15) & ~(size_t)15);
-        if (smem_r <= 200 * 1024) {
+        const size_t base_r = (size_t)S * O * (4 * sizeof(double) + sizeof(int4)) + (((size_t)2 * S + 15) & ~(size_t)15);
+        const size_t W = ((size_t)M + 31) / 32;
+        // row bitmaps of as many sets at a time as fit beside the circles (64 KB keeps three CTAs on an SM)
+        size_t budget = 64 * 1024;
+        if (base_r + W * 4 > budget) budget = 200 * 1024;
+        long long G = base_r + W * 4 <= budget ? (long long)((budget - base_r) / (W * 4)) : 0;
+        if (G > S) G = S;
+        if (G >= 1) {
+            const size_t smem_r = base_r + (size_t)G * W * 4;
             cudaError_t e = cudaFuncSetAttribute(arm_grid_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
             if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(arm_grid_rows_kernel)");
             int dev = 0, sms = 0, per_sm = 0;
@@ -339,7 +380,7 @@ int launch_arm_grid(int M, const double *theta, int row0, int n_rows, int n_link
             long long grid_dim = (long long)sms * per_sm;
             if (grid_dim > n_rows) grid_dim = n_rows;
             const int vec_ok = (M % 32 == 0) && (((uintptr_t)grid) % 16 == 0);
-            arm_grid_rows_kernel<<<(unsigned)grid_dim, ARM_RASTER_THREADS, smem_r, s>>>(p, theta, obstacles, grid, vec_ok);
+            arm_grid_rows_kernel<<<(unsigned)grid_dim, ARM_RASTER_THREADS, smem_r, s>>>(p, theta, obstacles, grid, vec_ok, (int)G);
             e = cudaGetLastError();
             if (e != cudaSuccess) return set_cuda_error(e, "arm_grid_rows_kernel launch");
             return RRTK_OK;

@@ -84,3 +84,8 @@ for fn, name in ((L.rrtk_arm_grid_dev, "rows"), (L.rrtk_arm_grid_cells_dev, "cel
         print("%s M=%d S=%d  %.2f ms  %.0f Gcell/s  %.0f GB/s written" % (name, M, S, ms, M * M * S / ms / 1e6, M * M * S / ms / 1e6), flush=True)
     grids.append(grid)
 print("config 5 identical:", torch.equal(grids[0], grids[1]), "occupied", int(grids[0].sum(dtype=torch.int64).item()))
+# the store stream's ceiling on this box: a plain fill of the same 4.3 GB
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); grids[1].fill_(1); e1.record(); e1.synchronize()
+    print("torch fill_ of the same tensor: %.2f ms  %.0f GB/s" % (e0.elapsed_time(e1), M * M * S / e0.elapsed_time(e1) / 1e6), flush=True)
