@@ -699,9 +699,18 @@ def sharded_curves(torch, dist, rrtk, W, dev, rank, world, iters, n_obs, barrier
         link = [0.5, 0.5, 0.3, 0.5, 0.1]
         lo, hi = rrtk.shard_range(M, rank, world)
         keep = {}
+        # inputs staged once (the launch is ~1 ms: per-call uploads and a 4 GB allocation would be what is timed)
+        L5, link5 = rrtk._lib.lib(), np.ascontiguousarray(link, dtype=np.float64)
+        d_theta, d_sets = torch.from_numpy(A.theta_list(M)).to(dev), torch.from_numpy(np.ascontiguousarray(sets)).to(dev)
+        bufs = {}
 
         def run5(a, b_):
-            keep["g"] = A.occupancy_grids_device(link, sets, M, a, b_ - a, device=dev)
+            g = bufs.get(b_ - a)
+            if g is None:
+                g = bufs[b_ - a] = torch.empty((S, b_ - a, M), dtype=torch.uint8, device=dev)
+            rrtk._lib.check(L5.rrtk_arm_grid_dev(M, d_theta.data_ptr(), a, b_ - a, 5, link5.ctypes.data, d_sets.data_ptr(), S, 5,
+                                                 g.data_ptr(), torch.cuda.current_stream().cuda_stream), "rrtk_arm_grid_dev")
+            keep["g"] = g
         barrier()
         med, ms = _median_ms(torch, lambda: run5(lo, hi), 1, 3)
         barrier()
@@ -716,10 +725,12 @@ def sharded_curves(torch, dist, rrtk, W, dev, rank, world, iters, n_obs, barrier
             else:
                 t_1, ok, occ1 = t_n, True, occ
             out["c5_arm_grid"] = dict(M=M, sets=S, rows_per_gpu=hi - lo, ms=t_n, ms_rank0=ms, cells_per_s=M * M * S / (t_n / 1e3),
+                                      written_gbs=M * M * S / (t_n / 1e3) / 1e9,
                                       ms_one_gpu=t_1, speedup_vs_one_gpu=t_1 / t_n, shard_invariant=ok, gather_bytes=8 * S * world,
                                       occupied_total=int(occ1.sum().item()), occupied_set0=int(occ1[0].item()),
                                       sharding="grid rows (each rank: M / N rows x all 64 sets)")
         keep.clear()
+        bufs.clear()
     except Exception as e:  # noqa: BLE001
         out["c5_arm_grid"] = dict(error=repr(e))
     barrier()
@@ -788,7 +799,13 @@ def extras(torch, dev):
         t = _timed(torch, lambda: L.rrtk_arm_grid_dev(M, theta.data_ptr(), 0, M, 5, link.ctypes.data, d_obs.data_ptr(),
                                                       S, 5, grid.data_ptr(), s), reps=2)
         out["c5_arm_grid"] = dict(cells_per_s=M * M * S / t, ms=t * 1e3, M=M, sets=S, out_gb=M * M * S / 1e9,
-                                  occupied_set0=int(grid[0].sum().item()))
+                                  written_gbs=M * M * S / t / 1e9, occupied_set0=int(grid[0].sum().item()),
+                                  kernel="arm_grid_rows_kernel (row rasteriser; bound: the M^2 S byte store stream)")
+        t0 = _timed(torch, lambda: grid.fill_(1), reps=3)
+        out["c5_arm_grid"]["plain_fill_gbs"] = M * M * S / t0 / 1e9       # the same bytes by torch's fill_: the store ceiling here
+        tc = _timed(torch, lambda: L.rrtk_arm_grid_cells_dev(M, theta.data_ptr(), 0, M, 5, link.ctypes.data, d_obs.data_ptr(),
+                                                             S, 5, grid.data_ptr(), s), reps=1)
+        out["c5_arm_grid"]["cell_by_cell_ms"] = tc * 1e3                    # every cell in the reference's order (cross-check kernel)
         del grid
     except Exception as e:  # noqa: BLE001
         out["c5_arm_grid"] = dict(error=repr(e))

@@ -199,7 +199,10 @@ __device__ __forceinline__ unsigned span_bits(int lo, int w, int j0, int M) {
     return m;
 }
 
-__global__ void __launch_bounds__(ARM_RASTER_THREADS)
+#ifndef ARM_RASTER_MINB
+#define ARM_RASTER_MINB 3
+#endif
+__global__ void __launch_bounds__(ARM_RASTER_THREADS, ARM_RASTER_MINB)
 arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double *__restrict__ obstacles,
                      uint8_t *__restrict__ grid, int vec_ok, int G) {
     // [S * O][4] doubles: x, y, r, r * r | [S * O] int4 runs: certain (lo, w), possible (lo, w) | [G][W] row bitmaps of a

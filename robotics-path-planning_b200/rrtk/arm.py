@@ -56,9 +56,11 @@ def theta_list(M: int) -> np.ndarray:
     return np.array([2 * i * pi / M for i in range(-M // 2, M // 2 + 1)][:M], dtype=np.float64)
 
 
-def occupancy_grids_device(link_lengths, obstacle_sets, M, row0=0, n_rows=None, device=None):
+def occupancy_grids_device(link_lengths, obstacle_sets, M, row0=0, n_rows=None, device=None, cell_by_cell=False, theta=None):
     """uint8 tensor [S, n_rows, M] on the GPU: cell (i, j) of set s is 1 iff the arm at joint angles
-    (theta_list[row0 + i], theta_list[j]) touches a circle of `obstacle_sets[s]` ([S, O, 3])."""
+    (theta_list[row0 + i], theta_list[j]) touches a circle of `obstacle_sets[s]` ([S, O, 3]).
+    cell_by_cell=True runs rrtk_arm_grid_cells_dev (every cell on its own, the cross-check of the row rasteriser);
+    `theta` replaces the reference's theta_list (tests: any other list makes the rasteriser evaluate cell by cell)."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     n_rows = M - row0 if n_rows is None else n_rows
@@ -68,12 +70,12 @@ def occupancy_grids_device(link_lengths, obstacle_sets, M, row0=0, n_rows=None, 
     S, O = obs.shape[0], obs.shape[1]
     link = np.ascontiguousarray(link_lengths, dtype=np.float64)
     with torch.cuda.device(dev):
-        theta = torch.from_numpy(theta_list(M)).to(dev)
+        theta = torch.from_numpy(theta_list(M) if theta is None else np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
         d_obs = torch.from_numpy(obs).to(dev)
         grid = torch.empty((S, n_rows, M), dtype=torch.uint8, device=dev)
-        _lib.check(_lib.lib().rrtk_arm_grid_dev(M, theta.data_ptr(), row0, n_rows, len(link), link.ctypes.data,
-                                                d_obs.data_ptr(), S, O, grid.data_ptr(),
-                                                torch.cuda.current_stream().cuda_stream), "rrtk_arm_grid_dev")
+        fn = _lib.lib().rrtk_arm_grid_cells_dev if cell_by_cell else _lib.lib().rrtk_arm_grid_dev
+        _lib.check(fn(M, theta.data_ptr(), row0, n_rows, len(link), link.ctypes.data, d_obs.data_ptr(), S, O, grid.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream), "rrtk_arm_grid_dev")
     return grid
 
 

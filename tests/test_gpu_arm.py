@@ -69,3 +69,69 @@ def test_degenerate_zero_length_link(oracle_lib):
     got = A.occupancy_grids_device(links, sets, 40).cpu().numpy()[0]
     assert np.array_equal(got, Or.arm_grid(40, links, sets[0], Or.MATH_CR))
     assert got.all()
+
+
+def _adversarial_sets(rng, link, S=12, O=5):
+    """Random circles plus the cases the row rasteriser has to get right: circles tangent to the reach of links 2..n from
+    some joint-1 position, joint 1 / the base exactly on a circle, radius 0, far away, everything inside, the far end of
+    the arm reaching exactly the tangent point."""
+    sets = np.concatenate([rng.uniform(-2.5, 2.5, (S, O, 2)), rng.uniform(0.05, 0.9, (S, O, 1))], axis=2)
+    Ls, l0 = float(np.sum(link[1:])), link[0]
+    ang = rng.uniform(-np.pi, np.pi)
+    p1 = np.array([l0 * np.cos(ang), l0 * np.sin(ang)])
+    u = rng.normal(size=2)
+    u /= np.linalg.norm(u)
+    sets[1, 0] = [*(p1 + u * (Ls + 0.4)), 0.4]
+    sets[2, 0] = [*(p1 + u * (Ls + 0.4)), 0.4 * (1 + 1e-12)]
+    sets[3, 0] = [*(p1 + u * 0.3), 0.3]
+    sets[4, 0] = [0.4, 0.0, 0.4]
+    sets[5, :, 2] = 0.0
+    sets[6, :, :2] += 50.0
+    sets[7, 0] = [0.0, 0.0, 10.0]
+    sets[8, 0] = [*(p1 + u * np.sqrt(Ls * Ls + 0.25)), 0.5]
+    return sets
+
+
+@pytest.mark.parametrize("M", [64, 100, 101, 257, 1000, 2048])
+@pytest.mark.parametrize("link", [[0.5, 0.5, 0.3, 0.5, 0.1], [1.0, 1.0], [0.7], [0.3, 1.2, 0.2]])
+def test_row_rasteriser_equals_cell_by_cell(M, link):
+    """rrtk_arm_grid_dev (runs of columns per circle, undecided cells evaluated exactly) against rrtk_arm_grid_cells_dev
+    (every cell in the reference's order), bit for bit, on adversarial circles; odd M and M not a multiple of 32 take the
+    unaligned store path and the partial last bitmap word."""
+    from rrtk import arm as A
+    rng = np.random.default_rng(M + len(link))
+    sets = _adversarial_sets(rng, link)
+    a = A.occupancy_grids_device(link, sets, M)
+    b = A.occupancy_grids_device(link, sets, M, cell_by_cell=True)
+    assert bool((a == b).all()), int((a != b).sum().item())
+
+
+def test_row_rasteriser_fallbacks_and_shards():
+    """A theta list that is not the reference's, a zero-length link, a row shard: still equal to the cell-by-cell grid."""
+    from rrtk import arm as A
+    rng = np.random.default_rng(9)
+    link, M = [0.5, 0.5, 0.3, 0.5, 0.1], 500
+    sets = _adversarial_sets(rng, link)
+    th = A.theta_list(M).copy()
+    th[250] += 1e-3
+    for kw in (dict(theta=th), dict(row0=123, n_rows=200)):
+        a = A.occupancy_grids_device(link, sets, M, **kw)
+        b = A.occupancy_grids_device(link, sets, M, cell_by_cell=True, **kw)
+        assert bool((a == b).all()), kw.keys()
+    a = A.occupancy_grids_device([0.5, 0.0, 0.3], sets, M)
+    b = A.occupancy_grids_device([0.5, 0.0, 0.3], sets, M, cell_by_cell=True)
+    assert bool((a == b).all())
+
+
+def test_row_rasteriser_full_size_rows_equal_cell_by_cell():
+    """Config 5's size (M = 8192, the script's arm, 64 obstacle sets): 512 rows of it, both ways."""
+    from rrtk import arm as A
+    rng = np.random.default_rng(5)
+    S, M = 64, 8192
+    sets = np.concatenate([rng.uniform(-2, 2, (S, 5, 2)), rng.uniform(0.2, 0.7, (S, 5, 1))], axis=2)
+    sets[0] = [[1.75, 0.75, 0.6], [0.55, 1.5, 0.5], [0, -1, 0.7], [0, -0.6, 0.4], [-1, 1., 0.3]]
+    link = [0.5, 0.5, 0.3, 0.5, 0.1]
+    for row0 in (0, 3840, 7680):
+        a = A.occupancy_grids_device(link, sets, M, row0, 512)
+        b = A.occupancy_grids_device(link, sets, M, row0, 512, cell_by_cell=True)
+        assert bool((a == b).all()), row0
