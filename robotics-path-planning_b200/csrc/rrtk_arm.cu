@@ -214,6 +214,7 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
     uint8_t *s_row = reinterpret_cast<uint8_t *>(s_bm + (size_t)G * W);
     uint8_t *s_all = s_row + p.S;
     __shared__ double s_link[ARM_MAX_LINKS];
+    __shared__ int s_any_all;   // some set of this row is evaluated cell by cell
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int t = threadIdx.x; t < n_circ; t += blockDim.x) {
         double x = obstacles[3 * t], y = obstacles[3 * t + 1], r = obstacles[3 * t + 2];
@@ -239,6 +240,7 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
         const double p1x = 0.0 + p.link[0] * c1, p1y = 0.0 + p.link[0] * s1;   // points[1] (arm02:259-260)
         // ---- per (set, circle): link 1 (the same for the whole row), then the circle's runs ----
         for (int t = threadIdx.x; t < p.S; t += blockDim.x) { s_row[t] = 0; s_all[t] = 0; }
+        if (threadIdx.x == 0) s_any_all = 0;
         __syncthreads();
         for (int u = threadIdx.x; u < n_circ; u += blockDim.x) {
             const int s = u / p.O;
@@ -278,7 +280,7 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
                 cells(a_in, run.x, run.y);
                 cells(a_out, run.z, run.w);
             }
-            if (run.w >= M - 1 && run.y < M - 1) s_all[s] = 1;   // undecided everywhere: the set's row cell by cell
+            if (run.w >= M - 1 && run.y < M - 1) { s_all[s] = 1; s_any_all = 1; }   // undecided everywhere: the set's row cell by cell
             s_run[u] = run;
         }
         __syncthreads();
@@ -287,12 +289,18 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
         for (int g0 = 0; g0 < p.S; g0 += G) {
             const int gn = p.S - g0 < G ? p.S - g0 : G;
             // ---- paint: one warp per (set, circle); the certain run word by word, the few undecided cells one by one ----
-            if (p.n_links >= 2) {
-                for (int u = warp; u < gn * p.O; u += n_warps) {
-                    const int sl = u / p.O, s = g0 + sl;
-                    if (s_row[s] || s_all[s]) continue;
-                    const int4 run = s_run[s * p.O + (u - sl * p.O)];
-                    unsigned *bm = s_bm + (size_t)sl * W;
+            if (p.n_links >= 2 && p.O > 0) {
+                // (set, circle) pairs warp, warp + n_warps, ...: the pair index is split without a division
+                const int dsl_p = n_warps / p.O, do_p = n_warps - dsl_p * p.O;
+                for (int sl = warp / p.O, o = warp - (warp / p.O) * p.O; sl < gn;) {
+                    const int s = g0 + sl, o_cur = o;
+                    const bool skip_pair = s_row[s] || s_all[s];
+                    const int4 run = s_run[s * p.O + o_cur];
+                    sl += dsl_p; o += do_p;
+                    if (o >= p.O) { o -= p.O; sl++; }
+                    if (skip_pair) continue;
+                    const int sl_cur = s - g0;
+                    unsigned *bm = s_bm + (size_t)sl_cur * W;
                     if (run.y >= 0) {
                         // words the run can reach into, from the one holding lo (one more when the last word of the row is
                         // partial: fewer cells there before the run wraps to column 0)
@@ -319,7 +327,7 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
                         }
                     }
                 }
-                for (int sl = 0; sl < gn; sl++) {   // sets to evaluate cell by cell (inputs the runs do not cover)
+                for (int sl = 0; s_any_all && sl < gn; sl++) {   // sets to evaluate cell by cell (inputs the runs do not cover)
                     const int s = g0 + sl;
                     if (s_row[s] || !s_all[s]) continue;
                     for (int j = threadIdx.x; j < M; j += blockDim.x)
@@ -329,8 +337,11 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
             }
             __syncthreads();
             // ---- emit: 32 cells per thread and step, bit -> byte; the bitmap is left cleared for the next group / row ----
-            for (int u = threadIdx.x; u < gn * W; u += blockDim.x) {
-                const int sl = u / W, wi = u - sl * W, s = g0 + sl, j0 = wi << 5;
+            const int dsl_e = blockDim.x / W, dwi_e = blockDim.x - dsl_e * W;
+            for (int sl = threadIdx.x / W, wi = threadIdx.x - (threadIdx.x / W) * W; sl < gn;) {
+                const int s = g0 + sl, j0 = wi << 5, u = sl * W + wi;
+                sl += dsl_e; wi += dwi_e;
+                if (wi >= W) { wi -= W; sl++; }
                 const int ncell = M - j0 < 32 ? M - j0 : 32;
                 unsigned bits = s_bm[u];
                 s_bm[u] = 0u;
