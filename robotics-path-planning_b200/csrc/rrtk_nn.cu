@@ -189,7 +189,7 @@ int launch_nearest(const float *xy, long long n, const float *samples, int B, un
         int b = B - done;
         const float *sp = samples + 2 * done;
         unsigned long long *bp = scratch + done;
-        if (b >= 8) { rc = launch_nearest_b<8>(xy, n, sp, bp, s); done += 8; }
+        if (b >= NN_MAX_B) { rc = launch_nearest_b<NN_MAX_B>(xy, n, sp, bp, s); done += NN_MAX_B; }
         else if (b >= 4) { rc = launch_nearest_b<4>(xy, n, sp, bp, s); done += 4; }
         else if (b >= 2) { rc = launch_nearest_b<2>(xy, n, sp, bp, s); done += 2; }
         else { rc = launch_nearest_b<1>(xy, n, sp, bp, s); done += 1; }
