@@ -894,6 +894,40 @@ def extras(torch, dev):
                                         solved=int(sum(r["goal_index"] >= 0 for r in res)))
     except Exception as e:  # noqa: BLE001
         out["c4_rrtstar_dubins"] = dict(error=repr(e))
+    try:   # rrt_03: RRT-Dubins (plain RRT, one whole-warp Dubins edge per iteration), the config-4 scenario and streams
+        Q, iters = 1024, 500
+        rng = np.random.default_rng(7)
+        st = np.concatenate([rng.uniform(-2, 15, (Q, iters, 2)), rng.uniform(-math.pi, math.pi, (Q, iters, 1))], axis=2)
+        st[rng.integers(0, 101, (Q, iters)) <= 10] = (10.0, 10.0, 0.0)
+        obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2)]] * Q
+        tm, kms = {}, []
+        for rep in range(4):
+            res = DP.run_rrt_batch([[0.0, 0.0, 0.0]] * Q, [[10.0, 10.0, 0.0]] * Q, obs, iters, st, timing=tm)
+            kms.append(tm["kernel_ms"])
+        kms = sorted(kms[1:])
+        out["rrt_dubins"] = dict(tree_iters_per_s=Q * iters / (kms[1] / 1e3), kernel_ms=kms[1], kernel_ms_runs=kms, queries=Q,
+                                 iters=iters, mean_nodes=float(np.mean([r["n"] for r in res])),
+                                 solved=int(sum(r["goal_index"] >= 0 for r in res)))
+    except Exception as e:  # noqa: BLE001
+        out["rrt_dubins"] = dict(error=repr(e))
+    try:   # rrt_01: basic RRT (no near / choose_parent / rewire), 4096 queries x 2000 iterations of the config-2 scenes
+        import rrtk
+        from rrtk import workloads as W2
+        cfg, Q, iters = W2.C2, 4096, 2000
+        rows = W2.c2_rows(list(range(Q)), 256)
+        b = rrtk.RRTStarBatch(np.tile(np.array(cfg["start"]), (Q, 1)), np.tile(np.array(cfg["goal"]), (Q, 1)), rows, cfg["rand_area"],
+                              cfg["expand_dis"], cfg["path_resolution"], cfg["goal_sample_rate"], iters, None, cfg["robot_radius"],
+                              "sobol", cfg["connect_circle_dist"], True, seed=0xC2, sobol_offset=np.arange(Q, dtype=np.int64) * iters)
+        b.params.rrt_only = 1
+        t = _timed(torch, lambda: b.run(), reps=3)
+        r = b.run()
+        out["rrt_basic"] = dict(tree_iters_per_s=float(r.iters_done.sum().item()) / t, kernel_ms=t * 1e3, queries=Q, max_iter=iters,
+                                mean_iters=float(r.iters_done.double().mean().item()),
+                                mean_nodes=float(r.n_nodes.double().mean().item()),
+                                note="rrt_01 stops at the first goal connection: iterations actually run are counted")
+        del b, r
+    except Exception as e:  # noqa: BLE001
+        out["rrt_basic"] = dict(error=repr(e))
     try:   # config 3: ONE Informed RRT* tree grown to 10^6 nodes (rrt_07 semantics, built-in scenario), whole GPU on it
         cap, iters = 1_000_001, 1_700_000
         rng = np.random.default_rng(9)
