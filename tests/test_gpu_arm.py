@@ -135,3 +135,36 @@ def test_row_rasteriser_full_size_rows_equal_cell_by_cell():
         a = A.occupancy_grids_device(link, sets, M, row0, 512)
         b = A.occupancy_grids_device(link, sets, M, row0, 512, cell_by_cell=True)
         assert bool((a == b).all()), row0
+
+
+def test_arm_grid_argument_checks_and_empty_inputs():
+    """Both entry points: bad row ranges / link counts / NULL pointers are RRTK_ERR_INVALID with a message; zero rows or
+    zero sets is a no-op; zero circles per set gives an all-free grid; M = 1 works."""
+    import torch
+    from rrtk import _lib, arm as A
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    M = 48
+    theta = torch.from_numpy(A.theta_list(M)).to(dev)
+    link = np.array([0.6, 0.5], dtype=np.float64)
+    obs = torch.from_numpy(np.array([[[1.0, 0.2, 0.3]]], dtype=np.float64)).to(dev)
+    grid = torch.full((1, M, M), 9, dtype=torch.uint8, device=dev)
+    for fn in (L.rrtk_arm_grid_dev, L.rrtk_arm_grid_cells_dev):
+        call = lambda M_=M, th=theta.data_ptr(), r0=0, nr=M, nl=2, lk=link.ctypes.data, ob=obs.data_ptr(), S=1, O=1, g=grid.data_ptr(): \
+            fn(M_, th, r0, nr, nl, lk, ob, S, O, g, s)  # noqa: E731
+        assert call() == 0
+        assert call(M_=0) < 0 and b"M" in L.rrtk_last_error()
+        assert call(r0=40, nr=20) < 0                      # rows past the grid
+        assert call(nl=0) < 0 and call(nl=17) < 0          # 1 <= n_links <= 16
+        assert call(th=None) < 0 and call(g=None) < 0 and call(ob=None) < 0 and call(lk=None) < 0
+        assert call(S=-1) < 0 and call(O=-1) < 0
+        grid.fill_(9)
+        assert call(nr=0) == 0 and call(S=0) == 0          # nothing to do, nothing written
+        torch.cuda.synchronize()
+        assert bool((grid == 9).all())
+        assert call(O=0, ob=None) == 0                     # no circles: every cell free
+        torch.cuda.synchronize()
+        assert bool((grid == 0).all())
+    one = A.occupancy_grids_device([0.5, 0.5], np.array([[[0.0, 0.0, 0.1]]]), 1)
+    assert one.shape == (1, 1, 1) and int(one.item()) == 1  # the base sits inside the circle
