@@ -25,6 +25,9 @@
 namespace rrtk {
 
 constexpr int DUB_WARPS_PER_CTA = 4;
+// Reeds-Shepp candidate rounds of at most this many edges share their 48 words out over the warp (rs_pick_coop: 12 word
+// evaluations per group of eight edges); fuller rounds keep one lane per edge
+constexpr int RS_COOP_MAX = 16;
 
 __host__ __device__ inline size_t dub_warp_smem_bytes(int near_cap, int node_cap) {
     (void)node_cap;
@@ -261,11 +264,21 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                 double mc = INF, bex = 0.0, bey = 0.0, beyaw = 0.0;
                 int bk = 0x7fffffff;
 #pragma unroll 1
-                for (int k = kfirst; k < count; k += kstride) {
-                    const int i = near_idx[k];
+                for (int k0 = kfirst - lane; k0 < count; k0 += kstride) {   // (uniform trip count: see RS_COOP_MAX)
+                    const int k = k0 + lane;
+                    const bool in = k < count;
+                    const int i = in ? near_idx[k] : 0;
                     const double2 a = xy[i];
-                    const PEdge e = plan_edge<STEER>(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
-                    if (e.valid && e.free_) {
+                    const int nact = count - k0 < 32 ? count - k0 : 32;
+                    PEdge e;
+                    e.valid = false; e.free_ = false; e.ex = e.ey = e.eyaw = e.lsum = 0.0;
+                    if (STEER >= 1 && nact <= RS_COOP_MAX) {   // few candidates: their words shared out over the warp
+                        const RsEdge re = rs_edges_coop(nact, lane, a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
+                        e.ex = re.ex; e.ey = re.ey; e.eyaw = re.eyaw; e.lsum = re.lsum; e.valid = re.npts > 0; e.free_ = re.free_;
+                    } else if (in) {
+                        e = plan_edge<STEER>(a.x, a.y, yaw[i], nx, ny, nyaw, kappa, step, obs, n_obs);
+                    }
+                    if (in && e.valid && e.free_) {
                         const double c = cost[i] + (STEER == 2 ? e.lsum : crm_hypot(nx - a.x, ny - a.y));
                         if (c < mc) { mc = c; bk = k; bex = e.ex; bey = e.ey; beyaw = e.eyaw; }
                     }
@@ -308,23 +321,47 @@ rrtstar_dubins_kernel(rrtk_dubins_params p, const double *__restrict__ start_goa
                     // whose node does not cost more than that NOW is not planned (flag 8); phase B looks at it again with the
                     // node's cost at its turn (a re-parented node moves, so costs can go either way).
 #pragma unroll 1
-                    for (int k = kfirst; k < count; k += kstride) {
-                        const int i = near_idx[k];
+                    for (int k0 = kfirst - lane; k0 < count; k0 += kstride) {
+                        const int k = k0 + lane;
+                        const bool in = k < count;
+                        const int i = in ? near_idx[k] : 0;
                         const double2 a = xy[i];
+                        const double ayaw = yaw[i];
                         const double ci = cost[i];
                         double ec = STEER == 2 ? 0.0 : mc + crm_hypot(a.x - cx, a.y - cy);
                         int fl = 8;
                         double ex = 0.0, ey = 0.0, eyw = 0.0;
-                        if (STEER == 2 || ci > ec) {
-                            const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, yaw[i], kappa, step, obs, n_obs);
+                        const bool need = in && (STEER == 2 || ci > ec);
+                        const unsigned nm = __ballot_sync(FULL, need);
+                        const int nact = __popc(nm);
+                        if (STEER >= 1 && nact > 0 && nact <= RS_COOP_MAX) {
+                            // the entries to plan move to lanes 0..nact-1 (rs_edges_coop shares their words out)
+                            const int srcl = lane < nact ? (int)__fns(nm, 0, lane + 1) : 0;
+                            const double tx = __shfl_sync(FULL, a.x, srcl), ty = __shfl_sync(FULL, a.y, srcl);
+                            const double tyaw = __shfl_sync(FULL, ayaw, srcl);
+                            const RsEdge re = rs_edges_coop(nact, lane, cx, cy, cyaw, tx, ty, tyaw, kappa, step, obs, n_obs);
+                            // ... and their results go back to the lanes that hold the entries
+                            const int rank = __popc(nm & ((1u << lane) - 1u));
+                            const int rfl = (re.npts > 0 ? 1 : 0) | (re.free_ ? 2 : 0);
+                            const int bfl = __shfl_sync(FULL, rfl, rank);
+                            const double bex_ = __shfl_sync(FULL, re.ex, rank), bey_ = __shfl_sync(FULL, re.ey, rank);
+                            const double beyw_ = __shfl_sync(FULL, re.eyaw, rank), bls_ = __shfl_sync(FULL, re.lsum, rank);
+                            if (need) {
+                                fl = bfl; ex = bex_; ey = bey_; eyw = beyw_;
+                                if (STEER == 2) ec = mc + bls_;
+                            }
+                        } else if (need) {
+                            const PEdge e = plan_edge<STEER>(cx, cy, cyaw, a.x, a.y, ayaw, kappa, step, obs, n_obs);
                             fl = (e.valid ? 1 : 0) | (e.free_ ? 2 : 0);
                             if (STEER == 2) ec = mc + e.lsum;
                             ex = e.ex; ey = e.ey; eyw = e.eyaw;
                         }
-                        flags0[k] = fl;
-                        nd0[k] = ec;
-                        s_c0[k] = ci;
-                        s_end0[3 * k] = ex; s_end0[3 * k + 1] = ey; s_end0[3 * k + 2] = eyw;
+                        if (in) {
+                            flags0[k] = fl;
+                            nd0[k] = ec;
+                            s_c0[k] = ci;
+                            s_end0[3 * k] = ex; s_end0[3 * k + 1] = ey; s_end0[3 * k + 2] = eyw;
+                        }
                     }
                     team_sync();
                     // phase B: apply in list order.  s_c is the current cost of every entry's node (refreshed after each

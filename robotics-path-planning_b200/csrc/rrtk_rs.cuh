@@ -193,22 +193,20 @@ struct RsEdge {
     bool free_;
 };
 
-// lengths_only: stop after the word selection (npts = 1 marks "a course exists", lsum = its length) -- what
-// rrt_10's calc_new_cost (:1153-1161) needs from reeds_shepp_path_planning.
-static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
-                                                   double maxc, double step_size, const double4 *obs, int n_obs,
-                                                   bool lengths_only = false) {
-    RsEdge e;
-    e.ex = e.ey = e.eyaw = e.lsum = 0.0;
-    e.npts = 0;
-    e.free_ = false;
-    const double step = step_size * maxc;
+// The word of an edge: generate_path + set_path in the reference's order, the first shortest inserted word.
+//   best = candidate index (family * 4 + symmetry), -1: no course at all; d = its signed lengths (time flip applied)
+struct RsPick { double d[5]; int best; };
+static __device__ __noinline__ RsPick rs_pick_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                   double maxc, double step) {
+    RsPick P;
+    P.best = -1;
+#pragma unroll
+    for (int i = 0; i < 5; i++) P.d[i] = 0.0;
     const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
     double s0, c0;
     sincos_cr(syaw, &s0, &c0);
     const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;
-    // generate_path + set_path in the reference's order; keep the first shortest inserted word
-    double min_L[RS_SLOTS], best_d[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, best_L = CUDART_INF;
+    double min_L[RS_SLOTS], best_L = CUDART_INF;
     int best = -1;
 #pragma unroll
     for (int j = 0; j < RS_SLOTS; j++) min_L[j] = CUDART_INF;
@@ -226,7 +224,7 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         for (int i = 0; i < n; i++) tot += fabs(d[i]);
         for (int i = 0; i < n; i++) {
             const double a = fabs(d[i]);
-            if (0.1 * tot < a && a < step) return e;   // "Step size too large for Reeds-Shepp paths." -> no path at all
+            if (0.1 * tot < a && a < step) return P;   // "Step size too large for Reeds-Shepp paths." -> no path at all
         }
         const int slot = RS_SLOT[cand];
         const double shortest = min_L[slot];
@@ -235,10 +233,118 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
         const double tl = fabs(div_rn(tot, maxc));
         if (tl < best_L) {
             best_L = tl; best = cand;
-            for (int i = 0; i < 5; i++) best_d[i] = (k == 1 || k == 3) ? -d[i] : d[i];   // timeflip
+            for (int i = 0; i < 5; i++) P.d[i] = (k == 1 || k == 3) ? -d[i] : d[i];   // timeflip
         }
     }
+    P.best = best;
+    return P;
+}
+
+// The same for up to 32 edges at once -- warp-collective, lanes 0..nact-1 hold one edge each.  A lane that evaluates its
+// 48 candidate words one after the other spends ~90 % of an edge there while (choose_parent / rewire hold ~10 candidates)
+// two thirds of the warp idle.  Here lane L works on edge L / 4 of a group of eight and symmetry L % 4 (its polar
+// coordinates stay in its registers), the twelve word families run one after the other for the whole warp (uniform code),
+// and set_path's bookkeeping runs replicated in the four lanes of an edge, fed by shuffles in candidate order:
+// 12 word evaluations per group of eight edges instead of 48 per edge.
+static __device__ __noinline__ RsPick rs_pick_coop(int nact, int lane, double sx, double sy, double syaw, double gx, double gy,
+                                                   double gyaw, double maxc, double step) {
+    RsPick R;
+    R.best = -1;
+#pragma unroll
+    for (int i = 0; i < 5; i++) R.d[i] = 0.0;
+#pragma unroll 1
+    for (int g0 = 0; g0 < nact; g0 += 8) {
+        const int e = g0 + (lane >> 2), k = lane & 3, base = lane & ~3;
+        const bool valid = e < nact;
+        const int src = valid ? e : 0;
+        const double esx = __shfl_sync(FULL, sx, src), esy = __shfl_sync(FULL, sy, src), esyaw = __shfl_sync(FULL, syaw, src);
+        const double egx = __shfl_sync(FULL, gx, src), egy = __shfl_sync(FULL, gy, src), egyaw = __shfl_sync(FULL, gyaw, src);
+        const double dx = egx - esx, dy = egy - esy, dth = egyaw - esyaw;
+        double s0, c0;
+        sincos_cr(esyaw, &s0, &c0);
+        const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;
+        const double dthk = (k == 1 || k == 2) ? -dth : dth;
+        double um, thm, up, thp;
+        rs_polars((k & 1) ? -x : x, (k & 2) ? -y : y, dthk, true, true, &um, &thm, &up, &thp);
+        double min_L[RS_SLOTS], best_L = CUDART_INF, bd[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        int best = -1;
+        bool dead = false;   // "Step size too large": no path at all
+#pragma unroll
+        for (int j = 0; j < RS_SLOTS; j++) min_L[j] = CUDART_INF;
+#pragma unroll 1
+        for (int f = 0; f < 12; f++) {
+            const int n = RS_N[f];
+            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const bool ok = valid && rs_word_core(f, dthk, um, thm, up, thp, d);
+            double tot = 0.0;
+            for (int i = 0; i < n; i++) tot += fabs(d[i]);
+            bool bad = false;
+            for (int i = 0; i < n; i++) {
+                const double a = fabs(d[i]);
+                if (0.1 * tot < a && a < step) bad = true;
+            }
+#pragma unroll 1
+            for (int kk = 0; kk < 4; kk++) {   // the four symmetries of this family in candidate order
+                const int sl = base + kk;
+                const bool okk = __shfl_sync(FULL, (int)ok, sl) != 0, badk = __shfl_sync(FULL, (int)bad, sl) != 0;
+                const double totk = __shfl_sync(FULL, tot, sl);
+                bool newbest = false;
+                if (!dead && okk) {
+                    if (badk) dead = true;
+                    else {
+                        const int cand = 4 * f + kk, slot = RS_SLOT[cand];
+                        const double shortest = min_L[slot];
+                        if (!((shortest - totk) <= step || totk <= step)) {
+                            if (totk < shortest) min_L[slot] = totk;
+                            const double tl = fabs(div_rn(totk, maxc));
+                            if (tl < best_L) { best_L = tl; best = cand; newbest = true; }
+                        }
+                    }
+                }
+                if (__any_sync(FULL, newbest)) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        const double di = __shfl_sync(FULL, d[i], sl);
+                        if (newbest) bd[i] = (kk == 1 || kk == 3) ? -di : di;   // timeflip
+                    }
+                }
+            }
+        }
+        if (dead) best = -1;
+        // the edge's own lane takes its group's result
+        const int j = lane - g0;
+        const bool mine = j >= 0 && j < 8 && lane < nact;
+        const int from = mine ? 4 * j : 0;
+        const int b = __shfl_sync(FULL, best, from);
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const double di = __shfl_sync(FULL, bd[i], from);
+            if (mine) R.d[i] = di;
+        }
+        if (mine) R.best = b;
+    }
+    return R;
+}
+
+// The course of the picked word: sampled collision test, end pose, length (steer rrt_06:1584-1604, check_collision
+// :1749-1762).  npts = len(px) (0: steer returns None), lsum = sum(|lengths|).
+// lengths_only: stop after the lengths (npts = 1 marks "a course exists", lsum = its length) -- what rrt_10's
+// calc_new_cost (:1153-1161) needs from reeds_shepp_path_planning.
+static __device__ __noinline__ RsEdge rs_course_lane(double sx, double sy, double syaw, double gx, double gy, double maxc,
+                                                     double step_size, const double4 *obs, int n_obs, RsPick pick,
+                                                     bool lengths_only) {
+    RsEdge e;
+    e.ex = e.ey = e.eyaw = e.lsum = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    const int best = pick.best;
     if (best < 0) return e;
+    const double step = step_size * maxc;
+    double s0, c0;
+    sincos_cr(syaw, &s0, &c0);
+    double best_d[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) best_d[i] = pick.d[i];
     const int f = best >> 2, k = best & 3, n = RS_N[f];
     if (lengths_only) {
         double ls = 0.0;
@@ -307,6 +413,24 @@ static __device__ __noinline__ RsEdge rs_edge_lane(double sx, double sy, double 
     e.ex = cm0 * ox + sm0 * oy + sx;
     e.ey = -sm0 * ox + cm0 * oy + sy;
     e.eyaw = angle_mod_pi(oyaw + syaw);
+    return e;
+}
+// One Reeds-Shepp edge evaluated by ONE lane: reeds_shepp_path_planning + the sampled collision test
+static __device__ __forceinline__ RsEdge rs_edge_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                      double maxc, double step_size, const double4 *obs, int n_obs,
+                                                      bool lengths_only = false) {
+    const RsPick pick = rs_pick_lane(sx, sy, syaw, gx, gy, gyaw, maxc, step_size * maxc);
+    return rs_course_lane(sx, sy, syaw, gx, gy, maxc, step_size, obs, n_obs, pick, lengths_only);
+}
+// Warp-collective: lanes 0..nact-1 evaluate one edge each, the candidate words shared out (rs_pick_coop)
+static __device__ __forceinline__ RsEdge rs_edges_coop(int nact, int lane, double sx, double sy, double syaw, double gx, double gy,
+                                                       double gyaw, double maxc, double step_size, const double4 *obs, int n_obs) {
+    const RsPick pick = rs_pick_coop(nact, lane, sx, sy, syaw, gx, gy, gyaw, maxc, step_size * maxc);
+    RsEdge e;
+    e.ex = e.ey = e.eyaw = e.lsum = 0.0;
+    e.npts = 0;
+    e.free_ = false;
+    if (lane < nact) e = rs_course_lane(sx, sy, syaw, gx, gy, maxc, step_size, obs, n_obs, pick, false);
     return e;
 }
 
