@@ -4,10 +4,10 @@
 // (generate_local_course / interpolate :431-470 with np.arange's  start + i * step  distances) rotated to the world
 // frame (calc_paths :473-493), and the sampled collision test of RRT*-Reeds-Shepp's check_collision over the course.
 //
-// One warp per request.  The 48 words are solved one per lane (two rounds): their atan2 / acos / asin / sin / cos are
-// the correctly rounded crmath.h functions, so the lengths -- and with them every `>= 0`, `<= step_size` and
-// minimum decision -- are platform independent.  The insertion logic then runs in the reference's order (uniformly,
-// 48 cheap steps over shared memory) and the course points of each segment are spread over the lanes.
+// Eight requests per warp and round.  Their 48 words each are shared out over the lanes (rs_pick_coop, rrtk_rs.cuh): the
+// atan2 / acos / asin / sin / cos are the correctly rounded crmath.h functions, so the lengths -- and with them every
+// `>= 0`, `<= step_size` and minimum decision -- are platform independent; the insertion logic runs in the reference's
+// order per request.  The warp then takes the courses one after the other, the points of a segment spread over the lanes.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,57 +27,27 @@ rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restri
                 const int32_t *__restrict__ obs_set, const double4 *__restrict__ obstacles, int obs_stride,
                 const int32_t *__restrict__ n_obs_arr, int32_t *types_out, double *lengths_out, double *L_out,
                 int32_t *n_paths_out, double *end_out, int32_t *n_pts_out, uint8_t *free_out, double *pts_out, int max_pts) {
-    __shared__ RsWarp smem[RS_WARPS];
     const int lane = threadIdx.x & 31;
-    RsWarp &W = smem[threadIdx.x >> 5];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const double step = step_size * maxc;
-    for (int r = warp; r < n_req; r += n_warps) {
-        const double sx = from3[3 * r], sy = from3[3 * r + 1], syaw = from3[3 * r + 2];
-        const double gx = to3[3 * r], gy = to3[3 * r + 1], gyaw = to3[3 * r + 2];
-        const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
-        double s0, c0;
-        sincos_cr(syaw, &s0, &c0);
-        const double x = (c0 * dx + s0 * dy) * maxc, y = (-s0 * dx + c0 * dy) * maxc;   // rs00:369-374
-        __syncwarp();
-        for (int cand = lane; cand < 48; cand += 32) {
-            const int f = cand >> 2, k = cand & 3;
-            double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            const bool ok = rs_word(f, (k & 1) ? -x : x, (k & 2) ? -y : y, (k == 1 || k == 2) ? -dth : dth, d);
+    // eight requests per warp and round: their 48 words each are shared out over the lanes (rs_pick_coop: twelve uniform
+    // family passes for the eight of them instead of twelve four-lane passes per request); then the warp takes the eight
+    // courses one after the other, the points of a segment spread over the lanes
+    for (int r0 = 8 * warp; r0 < n_req; r0 += 8 * n_warps) {
+        const int nact = n_req - r0 < 8 ? n_req - r0 : 8;
+        const int rl = r0 + (lane < nact ? lane : 0);
+        const double l_sx = from3[3 * rl], l_sy = from3[3 * rl + 1], l_syaw = from3[3 * rl + 2];
+        const double l_gx = to3[3 * rl], l_gy = to3[3 * rl + 1], l_gyaw = to3[3 * rl + 2];
+        const RsPick pick = rs_pick_coop(nact, lane, l_sx, l_sy, l_syaw, l_gx, l_gy, l_gyaw, maxc, step);
+#pragma unroll 1
+      for (int e8 = 0; e8 < nact; e8++) {
+        const int r = r0 + e8;
+        const double sx = __shfl_sync(FULL, l_sx, e8), sy = __shfl_sync(FULL, l_sy, e8), syaw = __shfl_sync(FULL, l_syaw, e8);
+        const int best = __shfl_sync(FULL, pick.best, e8), n_ins = __shfl_sync(FULL, pick.n_ins, e8);
+        double bd[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) W.d[cand][i] = d[i];
-            W.ok[cand] = ok ? 1 : 0;
-        }
-        __syncwarp();
-        // generate_path's loop + set_path, in the reference's order (uniform across the warp)
-        int n_ins = 0, best = -1, too_large = 0;
-        double ins_L[48], best_L = CUDART_INF;
-        int ins_code[48];
-        // (local arrays: 48 entries each; indexed uniformly)
-        for (int cand = 0; cand < 48; cand++) {
-            if (!W.ok[cand]) continue;
-            const int f = cand >> 2, k = cand & 3, n = RS_N[f];
-            double tot = 0.0;
-            for (int i = 0; i < n; i++) tot += fabs(W.d[cand][i]);
-            for (int i = 0; i < n; i++) {
-                const double a = fabs(W.d[cand][i]);
-                if (0.1 * tot < a && a < step) too_large = 1;   // "Step size too large for Reeds-Shepp paths." -> []
-            }
-            int code = n;
-            for (int i = 0; i < n; i++) {
-                const int t0 = RS_T[f][i];
-                const int ty = (k >= 2 && t0 != 1) ? 2 - t0 : t0;   // reflect
-                code = code * 3 + ty;
-            }
-            const double L = tot;   // timeflip only negates: sum(np.abs(lengths)) is the same left-to-right sum
-            bool same = false;
-            for (int j = 0; j < n_ins && !same; j++) same = ins_code[j] == code && (ins_L[j] - L) <= step;
-            if (same || L <= step) continue;
-            ins_code[n_ins] = code; ins_L[n_ins] = L; n_ins++;
-            if (fabs(L / maxc) < best_L) { best_L = fabs(L / maxc); best = cand; }   // first minimum of abs(p.L)
-        }
-        if (too_large) { n_ins = 0; best = -1; }
+        for (int i = 0; i < 5; i++) bd[i] = __shfl_sync(FULL, pick.d[i], e8);   // (time flip applied)
         if (best < 0) {
             if (lane == 0) {
                 n_paths_out[r] = 0; n_pts_out[r] = 0; free_out[r] = 0; L_out[r] = 0.0;
@@ -86,6 +56,9 @@ rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restri
             continue;
         }
         const int f = best >> 2, k = best & 3, n = RS_N[f];
+        double tot = 0.0;
+        for (int i = 0; i < n; i++) tot += fabs(bd[i]);
+        const double best_L = fabs(tot / maxc);   // abs(p.L): the time flip only negates
         const int set = obs_set ? obs_set[r] : 0;
         const double4 *obs = obstacles + (size_t)set * obs_stride;
         const int n_obs = n_obs_arr ? n_obs_arr[set] : 0;
@@ -96,8 +69,7 @@ rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restri
         int np = 0;
         double ox = 0.0, oy = 0.0, oyaw = 0.0, lastx = sx, lasty = sy, lastyaw = syaw;
         for (int i = 0; i < n; i++) {
-            double length = W.d[best][i];
-            if (k == 1 || k == 3) length = -length;              // timeflip
+            const double length = bd[i];
             const int t0 = RS_T[f][i];
             const int type = (k >= 2 && t0 != 1) ? 2 - t0 : t0;  // reflect
             const double dd = length >= 0.0 ? step : -step;
@@ -132,14 +104,14 @@ rs_steer_kernel(int n_req, double maxc, double step_size, const double *__restri
         if (lane == 0) {
             n_paths_out[r] = n_ins; n_pts_out[r] = np; free_out[r] = any_hit ? 0 : 1; L_out[r] = best_L;
             for (int i = 0; i < 5; i++) {
-                double length = i < n ? W.d[best][i] : 0.0;
-                if (k == 1 || k == 3) length = -length;
+                const double length = i < n ? bd[i] : 0.0;
                 const int t0 = i < n ? RS_T[f][i] : -1;
                 types_out[5 * r + i] = i < n ? ((k >= 2 && t0 != 1) ? 2 - t0 : t0) : -1;
                 lengths_out[5 * r + i] = i < n ? length / maxc : 0.0;
             }
             end_out[3 * r] = lastx; end_out[3 * r + 1] = lasty; end_out[3 * r + 2] = lastyaw;
         }
+      }
     }
 }
 
@@ -149,7 +121,7 @@ int launch_rs_steer(int n_req, double maxc, double step_size, const double *from
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long want = ((long long)n_req + RS_WARPS - 1) / RS_WARPS;
+    long long want = ((long long)n_req + 8 * RS_WARPS - 1) / (8 * RS_WARPS);
     long long grid = (long long)sms * 8;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;

@@ -194,12 +194,15 @@ struct RsEdge {
 };
 
 // The word of an edge: generate_path + set_path in the reference's order, the first shortest inserted word.
-//   best = candidate index (family * 4 + symmetry), -1: no course at all; d = its signed lengths (time flip applied)
-struct RsPick { double d[5]; int best; };
+//   best = candidate index (family * 4 + symmetry), -1: no course at all; d = its signed lengths (time flip applied);
+//   n_ins = len(paths): the words set_path inserted (0 with best = -1)
+struct RsPick { double d[5]; int best, n_ins; };
 static __device__ __noinline__ RsPick rs_pick_lane(double sx, double sy, double syaw, double gx, double gy, double gyaw,
                                                    double maxc, double step) {
     RsPick P;
     P.best = -1;
+    P.n_ins = 0;
+    int n_ins = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) P.d[i] = 0.0;
     const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
@@ -230,6 +233,7 @@ static __device__ __noinline__ RsPick rs_pick_lane(double sx, double sy, double 
         const double shortest = min_L[slot];
         if ((shortest - tot) <= step || tot <= step) continue;   // (inf - tot = inf: nothing of this type string inserted yet)
         if (tot < shortest) min_L[slot] = tot;
+        n_ins++;
         const double tl = fabs(div_rn(tot, maxc));
         if (tl < best_L) {
             best_L = tl; best = cand;
@@ -237,6 +241,7 @@ static __device__ __noinline__ RsPick rs_pick_lane(double sx, double sy, double 
         }
     }
     P.best = best;
+    P.n_ins = n_ins;
     return P;
 }
 
@@ -250,6 +255,7 @@ static __device__ __noinline__ RsPick rs_pick_coop(int nact, int lane, double sx
                                                    double gyaw, double maxc, double step) {
     RsPick R;
     R.best = -1;
+    R.n_ins = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) R.d[i] = 0.0;
 #pragma unroll 1
@@ -267,7 +273,7 @@ static __device__ __noinline__ RsPick rs_pick_coop(int nact, int lane, double sx
         double um, thm, up, thp;
         rs_polars((k & 1) ? -x : x, (k & 2) ? -y : y, dthk, true, true, &um, &thm, &up, &thp);
         double min_L[RS_SLOTS], best_L = CUDART_INF, bd[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        int best = -1;
+        int best = -1, n_ins = 0;
         bool dead = false;   // "Step size too large": no path at all
 #pragma unroll
         for (int j = 0; j < RS_SLOTS; j++) min_L[j] = CUDART_INF;
@@ -296,6 +302,7 @@ static __device__ __noinline__ RsPick rs_pick_coop(int nact, int lane, double sx
                         const double shortest = min_L[slot];
                         if (!((shortest - totk) <= step || totk <= step)) {
                             if (totk < shortest) min_L[slot] = totk;
+                            n_ins++;
                             const double tl = fabs(div_rn(totk, maxc));
                             if (tl < best_L) { best_L = tl; best = cand; newbest = true; }
                         }
@@ -310,18 +317,18 @@ static __device__ __noinline__ RsPick rs_pick_coop(int nact, int lane, double sx
                 }
             }
         }
-        if (dead) best = -1;
+        if (dead) { best = -1; n_ins = 0; }
         // the edge's own lane takes its group's result
         const int j = lane - g0;
         const bool mine = j >= 0 && j < 8 && lane < nact;
         const int from = mine ? 4 * j : 0;
-        const int b = __shfl_sync(FULL, best, from);
+        const int b = __shfl_sync(FULL, best, from), ni = __shfl_sync(FULL, n_ins, from);
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             const double di = __shfl_sync(FULL, bd[i], from);
             if (mine) R.d[i] = di;
         }
-        if (mine) R.best = b;
+        if (mine) { R.best = b; R.n_ins = ni; }
     }
     return R;
 }
