@@ -19,6 +19,8 @@
 
 namespace rrtk {
 
+constexpr int DUB_CUR_TAB = 1024;   // running sums of `step` kept per CTA (8 KB): courses up to 1024 points per segment
+
 extern "C" __global__ void __launch_bounds__(128)
 dubins_steer_kernel(int n_req, double kappa, double step, const double *__restrict__ from3,
                     const double *__restrict__ to3, const int32_t *__restrict__ obs_set,
@@ -28,36 +30,42 @@ dubins_steer_kernel(int n_req, double kappa, double step, const double *__restri
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < n_req; r += n_warps) {
-        const double s_x = from3[3 * r], s_y = from3[3 * r + 1], s_yaw = from3[3 * r + 2];
-        const double g_x = to3[3 * r], g_y = to3[3 * r + 1], g_yaw = to3[3 * r + 2];
-        double c, s;
-        rot2d(s_yaw, &c, &s);
-        const double vx = g_x - s_x, vy = g_y - s_y;
-        const double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s);  // numpy (2,)@(2,2), reference platform
-        const double lgyaw = g_yaw - s_yaw;
-        const double d = crm_hypot(lgx, lgy) * kappa;
-        const double theta = mod2pi(crm_atan2(lgy, lgx));
-        const double alpha = mod2pi(-theta), beta = mod2pi(lgyaw - theta);
-        // six words, one per lane; first minimum of |d1|+|d2|+|d3| in _PATH_TYPE_MAP order (:1214-1221)
-        double w[3] = {0.0, 0.0, 0.0};
-        double cost = CUDART_INF;
-        int bi = 0x7fffffff;
-        const DubTrig trig = dubins_trig(alpha, beta);
-        if (lane < 6 && dubins_word<true>(lane, alpha, beta, d, trig, w)) {
-            cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]);
-            bi = lane;
-        }
-        warp_argmin(cost, bi);
+    // the interior points of a segment sit at cur = step, step + step, ... (rrt_05:1107-1123: a running sum, not j * step):
+    // the sums are the same for every edge of the launch, so they are formed once per CTA -- s_cur[j] = cur after j
+    // additions -- instead of being counted through (~260 additions per edge) and walked up to (32 per lane and round)
+    __shared__ double s_cur[DUB_CUR_TAB];
+    if (threadIdx.x == 0) {
+        double cur = step;
+        for (int j = 0; j < DUB_CUR_TAB; j++) { s_cur[j] = cur; cur += step; }
+    }
+    __syncthreads();
+    // eight edges per warp and round: lanes 0..7 take one edge's frame, angles and sines / cosines each, the 6 words of the
+    // eight are shared out over the lanes (dubins_words_coop), then the warp emits the eight courses one after the other
+    for (int r0 = 8 * warp; r0 < n_req; r0 += 8 * n_warps) {
+        const int nact = n_req - r0 < 8 ? n_req - r0 : 8;
+        const int rl = r0 + (lane < nact ? lane : 0);
+        const double l_sx = from3[3 * rl], l_sy = from3[3 * rl + 1], l_syaw = from3[3 * rl + 2];
+        double l_c = 1.0, l_s = 0.0, l_alpha = 0.0, l_beta = 0.0, l_d = 0.0;
+        DubTrig l_trig;
+        l_trig.sa = l_trig.ca = l_trig.sb = l_trig.cb = l_trig.cab = 0.0;
+        if (lane < nact)
+            dubins_front(l_sx, l_sy, l_syaw, to3[3 * rl], to3[3 * rl + 1], to3[3 * rl + 2], kappa, l_c, l_s, l_alpha, l_beta, l_d, l_trig);
+        // first minimum of |d1|+|d2|+|d3| in _PATH_TYPE_MAP order (:1214-1221)
+        const DubWord l_w = dubins_words_coop(nact, lane, l_alpha, l_beta, l_d, l_trig);
+#pragma unroll 1
+      for (int e8 = 0; e8 < nact; e8++) {
+        const int r = r0 + e8;
+        const int bi = __shfl_sync(FULL, l_w.bi, e8);
         if (bi == 0x7fffffff) {  // no word is feasible
             if (lane == 0) { mode_out[r] = -1; n_pts_out[r] = 0; free_out[r] = 0; }
             continue;
         }
+        const double s_x = __shfl_sync(FULL, l_sx, e8), s_y = __shfl_sync(FULL, l_sy, e8), s_yaw = __shfl_sync(FULL, l_syaw, e8);
+        const double c = __shfl_sync(FULL, l_c, e8), s = __shfl_sync(FULL, l_s, e8);
         double len[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) len[k] = __shfl_sync(FULL, w[k], bi);
-        double c2, s2;
-        rot2d(-s_yaw, &c2, &s2);
+        len[0] = __shfl_sync(FULL, l_w.l0, e8); len[1] = __shfl_sync(FULL, l_w.l1, e8); len[2] = __shfl_sync(FULL, l_w.l2, e8);
+        // rot_mat_2d(-s_yaw): the correctly rounded sin / cos are odd / even bit for bit, so c2 = c and s2 = -s exactly
+        const double c2 = c, s2 = -s;
         const int set = obs_set ? obs_set[r] : 0;
         const double4 *obs = obstacles + (size_t)set * obs_stride;
         const int n_obs = n_obs_arr ? n_obs_arr[set] : 0;
@@ -85,23 +93,32 @@ dubins_steer_kernel(int n_req, double kappa, double step, const double *__restri
             if (length == 0.0) continue;
             const int type = seg_type(bi, k);
             const double ox = lx, oy = ly, oyaw = lyaw;
-            double so, co, sm, cm;
+            double so, co;
             sincos_cr(oyaw, &so, &co);
-            sincos_cr(-oyaw, &sm, &cm);
-            // interior points: cur = step, step + step, ... while |cur + step| <= |length|
-            int cnt = 0;
-            {
-                double cur = step;
-                while (fabs(cur + step) <= fabs(length)) { cnt++; cur += step; }
+            const double sm = -so, cm = co;               // sin / cos(-oyaw), exactly
+            // interior points: cur = step, step + step, ... while |cur + step| <= |length|, i.e. as many as there are sums
+            // s_cur[1..] not above |length| (the sums grow): a binary search; past the table the reference's walk
+            const double alen = fabs(length);
+            int cnt;
+            if (s_cur[DUB_CUR_TAB - 1] <= alen) {
+                cnt = DUB_CUR_TAB - 1;
+                double cur = s_cur[DUB_CUR_TAB - 1];
+                while (fabs(cur + step) <= alen) { cnt++; cur += step; }
+            } else {
+                int lo = 0, hi = DUB_CUR_TAB - 1;         // s_cur[hi] > alen; the answer is the last j >= 0 with s_cur[j] <= alen, or 0
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_cur[mid] <= alen) lo = mid; else hi = mid;
+                }
+                cnt = lo;                                  // (s_cur[0] = step itself does not count: cnt = #{j >= 1: s_cur[j] <= alen})
             }
-            double cur = step;
-            for (int t = 0; t < lane; t++) cur += step;  // lane's first point: `lane` sequential additions
             for (int j = lane; j < cnt; j += 32) {
+                double cur;
+                if (j < DUB_CUR_TAB) cur = s_cur[j];
+                else { cur = s_cur[DUB_CUR_TAB - 1]; for (int t = DUB_CUR_TAB - 1; t < j; t++) cur += step; }
                 double x, y, yaw;
                 interp(cur, type, kappa, ox, oy, oyaw, so, co, sm, cm, &x, &y, &yaw);
                 emit(x, y, yaw, np + j);
-#pragma unroll 1
-                for (int t = 0; t < 32; t++) cur += step;
             }
             interp(length, type, kappa, ox, oy, oyaw, so, co, sm, cm, &lx, &ly, &lyaw);  // segment end (uniform)
             if (lane == 0) emit(lx, ly, lyaw, np + cnt);
@@ -117,6 +134,7 @@ dubins_steer_kernel(int n_req, double kappa, double step, const double *__restri
             end_out[3 * r + 1] = fma(ly, c2, lx * -s2) + s_y;
             end_out[3 * r + 2] = angle_mod_pi(lyaw + s_yaw);
         }
+      }
     }
 }
 
@@ -127,7 +145,7 @@ int launch_dubins_steer(int n_req, double kappa, double step, const double *from
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long want = ((long long)n_req + 3) / 4;
+    long long want = ((long long)n_req + 31) / 32;   // 4 warps x 8 edges per CTA and round
     long long grid = (long long)sms * 8;  // persistent-style, a multiple of the SM count
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;

@@ -230,6 +230,71 @@ struct DubEdge {
     bool free_;           // check_collision over the course points (rrt_05:1625-1638)
 };
 
+// ---- pieces of plan_dubins_path for kernels that hold SEVERAL edges per warp (the batched steering kernel) ----
+// dubins_front: the goal in the start pose's frame, alpha / beta / d and their sines and cosines (one lane per edge);
+// dubins_words_coop: the six words of up to 32 edges shared out over the warp.  (The planners' candidate rounds evaluate
+// their words per lane: there the words are a fifth of an edge and the extra code cost more than it saved)
+static __device__ __forceinline__ void dubins_front(double s_x, double s_y, double s_yaw, double g_x, double g_y, double g_yaw,
+                                                    double kappa, double &c, double &s, double &alpha, double &beta, double &d,
+                                                    DubTrig &trig) {
+    rot2d(s_yaw, &c, &s);
+    const double vx = g_x - s_x, vy = g_y - s_y;
+    const double lgx = fma(vy, s, vx * c), lgy = fma(vy, c, vx * -s);
+    const double lgyaw = g_yaw - s_yaw;
+    d = crm_hypot(lgx, lgy) * kappa;
+    const double theta = mod2pi(crm_atan2(lgy, lgx));
+    alpha = mod2pi(-theta);
+    beta = mod2pi(lgyaw - theta);
+    trig = dubins_trig(alpha, beta);
+}
+
+// the winning word of an edge: index in _PATH_TYPE_MAP order (0x7fffffff = no word) and its three lengths
+struct DubWord { double l0, l1, l2; int bi; };
+
+// Warp-collective: lanes 0..nact-1 hold one edge each (its alpha, beta, d, trig); every such lane gets its edge's first
+// minimum of the summed lengths in _PATH_TYPE_MAP order (`best > cost` over k = 0..5, rrt_05:1088-1094).  Two passes so
+// that a round runs one kind of word: the four CSC words of 8 edges per round, then the two CCC words of 16 edges per
+// round; the first minimum inside an edge's lane group by shuffles, then the edge's own lane takes it.
+static __device__ __noinline__ DubWord dubins_words_coop(int nact, int lane, double alpha, double beta, double d, DubTrig trig) {
+    DubWord r;
+    r.l0 = r.l1 = r.l2 = 0.0;
+    r.bi = 0x7fffffff;
+    double best = CUDART_INF;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int gl = pass == 0 ? 4 : 2, per = 32 / gl;   // lanes per edge, edges per round
+#pragma unroll 1
+        for (int c0 = 0; c0 < nact; c0 += per) {
+            const int sub = lane & (gl - 1);
+            const int cnd = c0 + (pass == 0 ? lane >> 2 : lane >> 1);   // the edge this lane evaluates a word of
+            const int k = pass == 0 ? sub : 4 + sub;
+            const int src = cnd < 32 ? cnd : 31;
+            const double a_ = __shfl_sync(FULL, alpha, src), b_ = __shfl_sync(FULL, beta, src), d_ = __shfl_sync(FULL, d, src);
+            DubTrig t_;
+            t_.sa = __shfl_sync(FULL, trig.sa, src); t_.ca = __shfl_sync(FULL, trig.ca, src);
+            t_.sb = __shfl_sync(FULL, trig.sb, src); t_.cb = __shfl_sync(FULL, trig.cb, src);
+            t_.cab = __shfl_sync(FULL, trig.cab, src);
+            double w[3] = {0.0, 0.0, 0.0}, cost = CUDART_INF;
+            int kk = 0x7fffffff;
+            if (cnd < nact && dubins_word<true>(k, a_, b_, d_, t_, w)) { cost = fabs(w[0]) + fabs(w[1]) + fabs(w[2]); kk = k; }
+            for (int off = 1; off < gl; off <<= 1) {   // first minimum inside the group
+                const double oc = __shfl_xor_sync(FULL, cost, off);
+                const int ok = __shfl_xor_sync(FULL, kk, off);
+                if (oc < cost || (oc == cost && ok < kk)) { cost = oc; kk = ok; }
+            }
+            const int g = lane - c0;                   // this lane's own edge is group g of this round when 0 <= g < per
+            const bool mine = g >= 0 && g < per && lane < nact;
+            const int gsrc = mine ? g * gl : 0;
+            const double gc = __shfl_sync(FULL, cost, gsrc);
+            const int gk = __shfl_sync(FULL, kk, gsrc);
+            const int wsrc = gsrc + (gk != 0x7fffffff ? (pass == 0 ? gk : gk - 4) : 0);
+            const double w0 = __shfl_sync(FULL, w[0], wsrc), w1 = __shfl_sync(FULL, w[1], wsrc), w2 = __shfl_sync(FULL, w[2], wsrc);
+            if (mine && best > gc) { best = gc; r.bi = gk; r.l0 = w0; r.l1 = w1; r.l2 = w2; }
+        }
+    }
+    return r;
+}
+
 // One Dubins edge: plan_dubins_path + sampled collision test.  ONE out-of-line body serves both ways the planners evaluate
 // an edge (the kernels are bound by instruction fetch at 7 warps per SM: two 20 KB copies of this code were half of the hot
 // footprint):
