@@ -4,10 +4,12 @@
 // the world frame, and the reference's sampled collision test (check_collision rrt_05:1625-1638) over the
 // course points -- what RRT*-Dubins' `steer` + `check_collision` do for one edge (rrt_05:1458-1479).
 //
-// One warp per steering request.  Lanes 0..5 solve one word each (the expensive atan2/acos run in parallel),
-// a shuffle first-min picks the word in the reference's order; the course points of each segment are spread
-// over the 32 lanes (one correctly rounded sin/cos pair per curve point), transformed and tested against the
-// request's obstacle set.  FP64, reference operation order, crmath.h leaf functions, numpy's fma matmul.
+// Eight steering requests per warp and round.  Lanes 0..7 take one request's frame, angles and sines / cosines each,
+// the six words of the eight are shared out over the lanes (four CSC words x 8 requests = one pass, two CCC words x 8 =
+// another; a shuffle first-min picks the word in the reference's order), then the warp emits the eight courses one
+// after the other: the points of each segment spread over the 32 lanes (one correctly rounded sin/cos pair per curve
+// point, the running sums that place them looked up in a per-CTA table), transformed and tested against the request's
+// obstacle set.  FP64, reference operation order, crmath.h leaf functions, numpy's fma matmul.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
