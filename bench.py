@@ -1042,12 +1042,14 @@ def extras(torch, dev):
         free[coin] = (6.0, 10.0)
         ball = rng.random((Q, iters, 2))
         obs = [[(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]] * Q
+        tm = {}
         for rep in range(2):
             t0 = time.perf_counter()
-            res = INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, obs, 0.5, iters, free, ball)
+            res = INF.run_batch([[0.0, 0.0]] * Q, [[6.0, 10.0]] * Q, obs, 0.5, iters, free, ball, timing=tm)
             torch.cuda.synchronize()
             t = time.perf_counter() - t0
-        out["informed_rrtstar"] = dict(tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
+        out["informed_rrtstar"] = dict(tree_iters_per_s=Q * iters / (tm["kernel_ms"] / 1e3), kernel_ms=tm["kernel_ms"],
+                                       tree_iters_per_s_e2e=Q * iters / t, s=t, queries=Q, iters=iters,
                                        mean_nodes=float(np.mean([r["n"] for r in res])),
                                        solved=int(sum(r["path"] is not None for r in res)))
     except Exception as e:  # noqa: BLE001

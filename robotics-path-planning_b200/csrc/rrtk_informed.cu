@@ -92,8 +92,11 @@ __device__ __forceinline__ bool near_edge_free(double ax, double ay, double nx, 
     return !hit;
 }
 
+// slots of the per-warp duplicate detector (a power of two; lists longer than 3/4 of it take the exact mapping)
+constexpr int INF_HASH = 1024;
 struct InfWarpSmem {
     double cull_x[CULL_CAP], cull_y[CULL_CAP], cull_r2[CULL_CAP];
+    unsigned long long dup[INF_HASH];
 };
 
 extern "C" __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32, 4)
@@ -201,16 +204,44 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 count += __popc(mask);
             }
             __syncwarp();
-            // ---- choose_parent (:1110-1135): lane per candidate, `.index()` mapping first ----
+            // ---- the `.index()` mapping of find_near_nodes (:1140-1143): every hit stands for the FIRST hit with the same
+            // d2.  The near lists of rrt_07 hold a quarter of the tree (the radius is not clipped), and looking for an equal
+            // d2 among the earlier hits is quadratic: ~175 dependent loads per candidate, twice per iteration, were 40 % of an
+            // iteration.  Equal d2 of different nodes are rare, so a shared-memory hash set of the d2 bit patterns first says
+            // whether ANY two hits are equal; only then does the exact mapping run (once, in place: an entry that changes is
+            // not a first occurrence, and only first occurrences are read) ----
+            {
+                bool dup = count > INF_HASH * 3 / 4;
+                if (!dup && count > 1) {
+                    for (int t = lane; t < INF_HASH; t += 32) ws->dup[t] = ~0ull;
+                    __syncwarp();
+                    for (int k = lane; k < count && !dup; k += 32) {
+                        const unsigned long long key = (unsigned long long)__double_as_longlong(near_d[k]);
+                        unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 54) & (INF_HASH - 1);
+                        for (;;) {
+                            const unsigned long long old = atomicCAS(&ws->dup[slot], ~0ull, key);
+                            if (old == ~0ull) break;
+                            if (old == key) { dup = true; break; }
+                            slot = (slot + 1) & (INF_HASH - 1);
+                        }
+                    }
+                    dup = __any_sync(FULL, dup);
+                }
+                if (dup) {
+                    for (int k = lane; k < count; k += 32) {
+                        const double dk = near_d[k];
+                        for (int j = 0; j < k; j++)
+                            if (near_d[j] == dk) { near_idx[k] = near_idx[j]; break; }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- choose_parent (:1110-1135): lane per candidate ----
             double mc = INF;
             int bk = 0x7fffffff, bnode = -1;
 #pragma unroll 1
             for (int k = lane; k < count; k += 32) {
-                double dk = near_d[k];
-                int f = k;
-                for (int j = 0; j < k; j++)
-                    if (near_d[j] == dk) { f = j; break; }
-                const int i = near_idx[f];
+                const int i = near_idx[k];
                 const double2 a = xy[i];
                 const double dx = nx - a.x, dy = ny - a.y;
                 const double dd = crm_hypot(dx, dy);
@@ -234,11 +265,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
             for (int b0 = 0; b0 < count; b0 += 32) {
                 const int k = b0 + lane;
                 if (k < count) {
-                    double dk = near_d[k];
-                    int f = k;
-                    for (int j = 0; j < k; j++)
-                        if (near_d[j] == dk) { f = j; break; }
-                    const int i = near_idx[f];
+                    const int i = near_idx[k];
                     const double2 a = xy[i];
                     const double dd = crm_hypot(a.x - nx, a.y - ny);
                     const double sc = ncost + dd;

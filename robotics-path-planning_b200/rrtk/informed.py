@@ -56,9 +56,10 @@ def near_table(node_cap: int) -> np.ndarray:
 
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples, ball_draws, path_cap=1024,
-              device=None):
+              device=None, timing=None):
     """Q informed searches in one launch.  free_samples / ball_draws: [Q, max_iter, 2].
-    Returns dict of numpy arrays / lists (trees trimmed to n_nodes)."""
+    Returns dict of numpy arrays / lists (trees trimmed to n_nodes).
+    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch)."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     starts = np.asarray(starts, dtype=np.float64).reshape(-1, 2)
@@ -96,12 +97,19 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples,
         status = torch.empty((q,), dtype=torch.int32, device=dev)
         ws_idx = torch.empty((q * cap + _lib.WS_TAIL_INTS,), dtype=torch.int32, device=dev)
         ws_d = torch.empty((q, cap), dtype=torch.float64, device=dev)
+        if timing is not None:
+            ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev[0].record()
         rc = _lib.lib().rrtk_informed_run_dev(
             C.byref(p), d_sg.data_ptr(), d_rot.data_ptr(), d_obs.data_ptr(), d_cnt.data_ptr(), d_near.data_ptr(),
             d_free.data_ptr(), d_ball.data_ptr(), xy.data_ptr(), cost.data_ptr(), parent.data_ptr(),
             n_nodes.data_ptr(), path.data_ptr(), plen.data_ptr(), c_best.data_ptr(), status.data_ptr(),
             ws_idx.data_ptr(), ws_d.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "rrtk_informed_run_dev")
+        if timing is not None:
+            ev[1].record()
+            ev[1].synchronize()
+            timing["kernel_ms"] = ev[0].elapsed_time(ev[1])
         n = n_nodes.cpu().numpy()
         pl = plen.cpu().numpy()
         h_xy, h_cost, h_par, h_path = xy.cpu().numpy(), cost.cpu().numpy(), parent.cpu().numpy(), path.cpu().numpy()

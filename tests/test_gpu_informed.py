@@ -77,3 +77,37 @@ def test_informed_batch_random(oracle_lib):
         assert a["c_best"] == ref["c_best"] and a["path"] == ref["path"]
         solved += a["path"] is not None
     assert solved >= 1
+
+
+def test_informed_batch_equal_d2_and_long_near_lists(oracle_lib):
+    """The `.index()` mapping of find_near_nodes in the batched kernel: the hash set that detects equal d2 among the hits
+    must send the iteration to the exact mapping.  Repeated samples create coincident nodes (equal d2 at every later
+    iteration that has both in its near list), a mirrored pair gives two DIFFERENT positions at bitwise-equal d2 from nodes
+    on the axis; 1500 iterations push the near lists past 3/4 of the detector's 1024 slots (always-exact path)."""
+    from rrtk import informed
+    O = oracle_lib
+    start, goal = [0.0, 0.0], [6.0, 0.25]
+    obs = [(3.0, 2.5, 1.0), (3.0, -2.5, 1.0)]
+    iters = 1500
+    rng = np.random.default_rng(11)
+    free = rng.uniform(-3.0, 8.0, (iters, 2))
+    free[rng.integers(0, 101, iters) <= 10] = goal
+    ball = rng.random((iters, 2))
+    free[0] = (-1.0, 5.0); free[1] = (-1.0, -5.0)   # mirrored pair about the x axis, both grown from the root
+    free[2:6] = (0.1, 0.0)                          # nearest stays the root: (0.5, 0) four times, on the axis
+    free[200:260:2] = (0.1, 0.0)
+    rot = informed.rotation_to_world_frame(start, goal)
+    ref = O.informed_run(start, goal, obs, 0.5, iters, rot, free, ball, O.MATH_CR)
+    xy = np.column_stack([ref["x"], ref["y"]])
+    assert len(np.unique(xy, axis=0)) < len(xy), "scenario should contain coincident nodes"
+    # the same query three times in one launch (several warps, one of them beside a plain random query)
+    free2 = rng.uniform(-3.0, 8.0, (iters, 2))
+    out = informed.run_batch([start] * 4, [goal] * 4, [obs] * 4, 0.5, iters, np.array([free, free, free2, free]),
+                             np.array([ball] * 4))
+    for q in (0, 1, 3):
+        a = out[q]
+        assert a["n"] == ref["n"] and np.array_equal(a["parent"], ref["parent"])
+        assert np.array_equal(a["x"], ref["x"]) and np.array_equal(a["y"], ref["y"]) and np.array_equal(a["cost"], ref["cost"])
+        assert a["c_best"] == ref["c_best"] and a["path"] == ref["path"]
+    ref2 = O.informed_run(start, goal, obs, 0.5, iters, rot, free2, ball, O.MATH_CR)
+    assert out[2]["n"] == ref2["n"] and np.array_equal(out[2]["parent"], ref2["parent"]) and np.array_equal(out[2]["cost"], ref2["cost"])
