@@ -248,7 +248,8 @@ typedef struct rrtk_informed_params {
     int32_t node_cap;    /* >= max_iter + 1 */
     int32_t obs_stride;
     int32_t path_cap;    /* capacity of each best-path snapshot */
-    int32_t pad_;
+    int32_t exec_mode;   /* RRTK_EXEC_AUTO (0) / _WARP / _CTA: a warp or a CTA of 4 warps per query (same trees); AUTO takes
+                            the CTA while the whole batch is resident at once */
     double expand_dis;
     double coord_bound;  /* upper bound on |coordinate| of anything in the scenes (samples, nodes, circles): sets the
                             tolerance band inside which a near edge falls back to the reference's exact end-point

@@ -99,23 +99,43 @@ struct InfWarpSmem {
     unsigned long long dup[INF_HASH];
 };
 
-extern "C" __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32, 4)
+// TW = 1: one warp per query.  TW = 4: one CTA per query, for batches that are resident all at once (a launch of up to a
+// few hundred queries lasts as long as ONE query's chain, and rrt_07's near lists -- a quarter of the tree -- are several
+// rounds of 32 candidates): every warp runs the same control flow on the same data (sample, nearest, steer, cull, first
+// segment: recomputed per warp), warp 0 writes the near list and the tree, the candidates of choose_parent and rewire
+// are split over the 128 threads.  Same trees bit for bit.
+template <int TW>
+__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32, 4)
 informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, const double4 *__restrict__ rot,
                 const double4 *__restrict__ obstacles, const int32_t *__restrict__ n_obs_arr,
                 const double2 *__restrict__ near_rr2, const double2 *__restrict__ free_samples,
                 const double2 *__restrict__ ball_draws, double2 *xy_all, double *cost_all, int32_t *parent_all,
                 int32_t *n_nodes, double2 *path_all, int32_t *path_len, double *c_best_out, int32_t *status_out,
                 int32_t *ws_idx_all, double *ws_d_all, unsigned int *counter) {
+    static_assert(TW == 1 || TW == INF_WARPS_PER_CTA, "a team is one warp or the whole CTA");
     __shared__ InfWarpSmem smem[INF_WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31;
-    InfWarpSmem *ws = &smem[threadIdx.x >> 5];
+    __shared__ double t_mc[INF_WARPS_PER_CTA];    // team reduction of choose_parent
+    __shared__ int t_bk[INF_WARPS_PER_CTA], t_bnode[INF_WARPS_PER_CTA];
+    __shared__ unsigned int t_q;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool lead = TW == 1 || warp == 0;       // the warp that writes the near list and the tree
+    const int kfirst = TW == 1 ? lane : (int)threadIdx.x, kstride = 32 * TW;
+    InfWarpSmem *ws = &smem[warp];
     const double INF = CUDART_INF;
     const double ed = p.expand_dis;
+    auto team_sync = [&]() { if (TW > 1) __syncthreads(); else __syncwarp(); };
 
     for (;;) {
         unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(counter, 1u);
-        q = __shfl_sync(FULL, q, 0);
+        if (TW > 1) {
+            __syncthreads();   // (the previous query's t_q has been read)
+            if (threadIdx.x == 0) t_q = atomicAdd(counter, 1u);
+            __syncthreads();
+            q = t_q;
+        } else {
+            if (lane == 0) q = atomicAdd(counter, 1u);
+            q = __shfl_sync(FULL, q, 0);
+        }
         if (q >= (unsigned)p.n_queries) break;
         const double4 sg = start_goal[q];
         const double4 R = rot[q];  // c00, c01, c10, c11
@@ -130,8 +150,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
         double2 *path = path_all + (size_t)q * p.path_cap;
         const double2 *fs = free_samples + (size_t)q * p.max_iter;
         const double2 *bd = ball_draws + (size_t)q * p.max_iter;
-        if (lane == 0) { xy[0] = make_double2(sx, sy); cost[0] = 0.0; parent[0] = -1; }
-        __syncwarp();
+        if (lead && lane == 0) { xy[0] = make_double2(sx, sy); cost[0] = 0.0; parent[0] = -1; }
         int n = 1, status = RRTK_Q_OK, plen_best = 0;
         double c_best = INF;
         const double band_k = 1e-12 * p.coord_bound * p.coord_bound;
@@ -139,6 +158,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
         const double xc = (sx + gx) / 2.0, yc = (sy + gy) / 2.0;
 
         for (int it = 0; it < p.max_iter; it++) {
+            team_sync();   // the tree as the previous iteration left it (append, rewire) is visible to every warp
             // ---- informed_sample (rrt_07:1145-1159) ----
             double rx, ry;
             if (c_best < INF) {
@@ -200,10 +220,10 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 }
                 unsigned mask = __ballot_sync(FULL, hit);
                 int pos = count + __popc(mask & ((1u << lane) - 1u));
-                if (hit) { near_idx[pos] = i; near_d[pos] = d; }
+                if (hit && lead) { near_idx[pos] = i; near_d[pos] = d; }
                 count += __popc(mask);
             }
-            __syncwarp();
+            team_sync();
             // ---- the `.index()` mapping of find_near_nodes (:1140-1143): every hit stands for the FIRST hit with the same
             // d2.  The near lists of rrt_07 hold a quarter of the tree (the radius is not clipped), and looking for an equal
             // d2 among the earlier hits is quadratic: ~175 dependent loads per candidate, twice per iteration, were 40 % of an
@@ -227,12 +247,13 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                     }
                     dup = __any_sync(FULL, dup);
                 }
-                if (dup) {
-                    for (int k = lane; k < count; k += 32) {
+                if (dup) {   // (uniform over the team: every warp looked at the same list)
+                    for (int k = kfirst; k < count; k += kstride) {
                         const double dk = near_d[k];
                         for (int j = 0; j < k; j++)
                             if (near_d[j] == dk) { near_idx[k] = near_idx[j]; break; }
                     }
+                    team_sync();
                 }
                 __syncwarp();
             }
@@ -240,7 +261,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
             double mc = INF;
             int bk = 0x7fffffff, bnode = -1;
 #pragma unroll 1
-            for (int k = lane; k < count; k += 32) {
+            for (int k = kfirst; k < count; k += kstride) {
                 const int i = near_idx[k];
                 const double2 a = xy[i];
                 const double dx = nx - a.x, dy = ny - a.y;
@@ -251,19 +272,27 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 }
             }
             warp_argmin(mc, bk);
+            if (bk != 0x7fffffff) bnode = __shfl_sync(FULL, bnode, bk & 31);   // (candidate k sits on lane k & 31 of its warp)
+            if (TW > 1) {   // the first minimum over the team's warps
+                if (lane == 0) { t_mc[warp] = mc; t_bk[warp] = bk; t_bnode[warp] = bnode; }
+                __syncthreads();
+                mc = t_mc[0]; bk = t_bk[0]; bnode = t_bnode[0];
+                for (int w = 1; w < TW; w++)
+                    if (t_mc[w] < mc || (t_mc[w] == mc && t_bk[w] < bk)) { mc = t_mc[w]; bk = t_bk[w]; bnode = t_bnode[w]; }
+            }
             if (bk != 0x7fffffff) {
                 ncost = mc;
-                npar = __shfl_sync(FULL, bnode, bk & 31);
+                npar = bnode;
             }
             const int newi = n;
             __syncwarp();
-            if (lane == 0) { xy[newi] = make_double2(nx, ny); cost[newi] = ncost; parent[newi] = npar; }
+            if (lead && lane == 0) { xy[newi] = make_double2(nx, ny); cost[newi] = ncost; parent[newi] = npar; }
             n++;
             __syncwarp();
             // ---- rewire (:1232-1246): entries are independent (no propagation); repeats are idempotent ----
 #pragma unroll 1
-            for (int b0 = 0; b0 < count; b0 += 32) {
-                const int k = b0 + lane;
+            for (int b0 = 0; b0 < count; b0 += kstride) {
+                const int k = b0 + kfirst;
                 if (k < count) {
                     const int i = near_idx[k];
                     const double2 a = xy[i];
@@ -280,6 +309,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
             }
             // ---- goal bookkeeping (:1094-1103) ----
             if (crm_hypot(nx - gx, ny - gy) < ed) {
+                team_sync();   // the walk below reads parents the other warps may just have rewired
                 ObsList G = cull_obstacles(obs, n_obs, nx, ny, ed, ws->cull_x, ws->cull_y, ws->cull_r2, lane);
                 if (seg_free_warp(nx, ny, gx, gy, G, lane)) {
                     // get_final_course + get_path_len: goal, new node, ..., root, start; serial walk (lane 0)
@@ -305,7 +335,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                         c_best = plen;
                         plen_best = len;
                         if (len > p.path_cap) status |= RRTK_Q_PATH_OVERFLOW;
-                        if (lane == 0) {
+                        if (lead && lane == 0) {
                             int w = 0;
                             if (w < p.path_cap) path[w] = make_double2(gx, gy);
                             w++;
@@ -318,7 +348,7 @@ informed_kernel(rrtk_informed_params p, const double4 *__restrict__ start_goal, 
                 }
             }
         }
-        if (lane == 0) {
+        if (lead && lane == 0) {
             n_nodes[q] = n;
             path_len[q] = plen_best;
             c_best_out[q] = c_best;
@@ -336,16 +366,19 @@ int launch_informed(const rrtk_informed_params &p, const double *start_goal, con
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, informed_kernel, INF_WARPS_PER_CTA * 32, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, informed_kernel<INF_WARPS_PER_CTA>, INF_WARPS_PER_CTA * 32, 0);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (per_sm < 1) per_sm = 1;
-    long long want = ((long long)p.n_queries + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
+    // a CTA per query while every query of the batch is resident at once (p.exec_mode: RRTK_EXEC_WARP / _CTA force one)
+    const bool cta = p.exec_mode == RRTK_EXEC_CTA || (p.exec_mode != RRTK_EXEC_WARP && (long long)p.n_queries <= (long long)sms * per_sm);
+    const auto kern = cta ? informed_kernel<INF_WARPS_PER_CTA> : informed_kernel<1>;
+    long long want = cta ? (long long)p.n_queries : ((long long)p.n_queries + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA;
     long long grid = (long long)sms * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counter)");
-    informed_kernel<<<(unsigned)grid, INF_WARPS_PER_CTA * 32, 0, s>>>(
+    kern<<<(unsigned)grid, INF_WARPS_PER_CTA * 32, 0, s>>>(
         p, reinterpret_cast<const double4 *>(start_goal), reinterpret_cast<const double4 *>(rot),
         reinterpret_cast<const double4 *>(obstacles), n_obs, reinterpret_cast<const double2 *>(near_rr2),
         reinterpret_cast<const double2 *>(free_s), reinterpret_cast<const double2 *>(ball),

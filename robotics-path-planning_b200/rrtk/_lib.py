@@ -35,7 +35,7 @@ class RRTStarParams(C.Structure):
 class InformedParams(C.Structure):
     """struct rrtk_informed_params (include/rrtk.h)."""
     _fields_ = [("n_queries", C.c_int32), ("max_iter", C.c_int32), ("node_cap", C.c_int32),
-                ("obs_stride", C.c_int32), ("path_cap", C.c_int32), ("pad_", C.c_int32),
+                ("obs_stride", C.c_int32), ("path_cap", C.c_int32), ("exec_mode", C.c_int32),
                 ("expand_dis", C.c_double), ("coord_bound", C.c_double)]
 
 

@@ -56,10 +56,11 @@ def near_table(node_cap: int) -> np.ndarray:
 
 
 def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples, ball_draws, path_cap=1024,
-              device=None, timing=None):
+              device=None, timing=None, exec_mode="auto"):
     """Q informed searches in one launch.  free_samples / ball_draws: [Q, max_iter, 2].
     Returns dict of numpy arrays / lists (trees trimmed to n_nodes).
-    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch)."""
+    `timing`: optional dict that receives `kernel_ms` (CUDA events around the launch).
+    `exec_mode`: "warp" (a warp per query), "cta" (a CTA per query: batches resident all at once), "auto"; same trees."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda" if device is None else device)
     starts = np.asarray(starts, dtype=np.float64).reshape(-1, 2)
@@ -77,6 +78,7 @@ def run_batch(starts, goals, obstacle_lists, expand_dis, max_iter, free_samples,
     p = _lib.InformedParams()
     p.n_queries, p.max_iter, p.node_cap, p.obs_stride, p.path_cap = q, max_iter, cap, stride, path_cap
     p.expand_dis = float(expand_dis)
+    p.exec_mode = {"auto": 0, "warp": 1, "cta": 2}[exec_mode]
     fs = np.asarray(free_samples, dtype=np.float64)
     bound = max(float(np.abs(starts).max()), float(np.abs(goals).max()), float(np.abs(fs).max()) if fs.size else 0.0,
                 float(np.abs(rows[:, :, :3]).max()) if rows.size else 0.0, 1.0)
