@@ -111,3 +111,31 @@ def test_informed_batch_equal_d2_and_long_near_lists(oracle_lib):
         assert a["c_best"] == ref["c_best"] and a["path"] == ref["path"]
     ref2 = O.informed_run(start, goal, obs, 0.5, iters, rot, free2, ball, O.MATH_CR)
     assert out[2]["n"] == ref2["n"] and np.array_equal(out[2]["parent"], ref2["parent"]) and np.array_equal(out[2]["cost"], ref2["cost"])
+
+
+def test_informed_warp_and_cta_execution_agree(oracle_lib):
+    """exec_mode: a warp per query and a CTA per query build the same trees (and the oracle's), with near lists of several
+    rounds per warp and best-path updates along the way."""
+    from rrtk import informed
+    O = oracle_lib
+    Q, iters = 6, 700
+    rng = np.random.default_rng(23)
+    obs = [(5, 5, 1), (3, 6, 2), (3, 8, 2), (3, 10, 2), (7, 5, 2), (9, 5, 2), (8, 10, 1)]
+    starts, goals = [[0.0, 0.0]] * Q, [[6.0, 10.0]] * (Q - 1) + [[12.0, 3.0]]
+    free = rng.uniform(-2, 15, (Q, iters, 2))
+    coin = rng.integers(0, 101, (Q, iters)) <= 10
+    for q in range(Q):
+        free[q][coin[q]] = goals[q]
+    ball = rng.random((Q, iters, 2))
+    out = {m: informed.run_batch(starts, goals, [obs] * Q, 0.5, iters, free, ball, exec_mode=m) for m in ("warp", "cta")}
+    for q in range(Q):
+        a, b = out["warp"][q], out["cta"][q]
+        assert a["n"] == b["n"] and a["c_best"] == b["c_best"] and a["path"] == b["path"] and a["status"] == b["status"]
+        for k in ("x", "y", "cost", "parent"):
+            assert np.array_equal(a[k], b[k]), (q, k)
+    for q in (0, Q - 1):
+        rot = informed.rotation_to_world_frame(starts[q], goals[q])
+        ref = O.informed_run(starts[q], goals[q], obs, 0.5, iters, rot, free[q], ball[q], O.MATH_CR)
+        b = out["cta"][q]
+        assert b["n"] == ref["n"] and np.array_equal(b["parent"], ref["parent"]) and np.array_equal(b["cost"], ref["cost"])
+        assert b["c_best"] == ref["c_best"] and b["path"] == ref["path"]
