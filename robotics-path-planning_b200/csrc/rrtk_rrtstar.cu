@@ -335,12 +335,21 @@ RRTK_UNROLL(RRTK_UNROLL_NEAREST)
                     } else {
                         t_near = count;
                         // `.index()` quirk: every hit is replaced by the first hit with the same d2
-                        for (int k = lane; k < count; k += 32) {
+                        // (the first 32 hits -- usually all of them -- by one warp MATCH on the d2 bit patterns: d2 is a finite
+                        // non-negative double, so equal values are equal bits; idle lanes offer distinct NaN patterns)
+                        {
+                            const double d0k = lane < count ? nd[lane] : 0.0;
+                            const unsigned long long key = lane < count ? (unsigned long long)__double_as_longlong(d0k)
+                                                                        : (0xfff8000000000000ull | (unsigned)lane);
+                            const unsigned same = __match_any_sync(FULL, key);
+                            if (lane < count) near_ok[lane] = near_idx[__ffs(same) - 1];  // staged: resolved node index
+                        }
+                        for (int k = 32 + lane; k < count; k += 32) {
                             double dk = nd[k];
                             int f = k;
                             for (int j = 0; j < k; j++)
                                 if (nd[j] == dk) { f = j; break; }
-                            near_ok[k] = near_idx[f];  // staged: resolved node index
+                            near_ok[k] = near_idx[f];
                         }
                         __syncwarp();
                         for (int k = lane; k < count; k += 32) near_idx[k] = near_ok[k];
