@@ -89,7 +89,7 @@ arm_grid_kernel(ArmParams p, const double *__restrict__ theta, const double *__r
     uint8_t *s_row = reinterpret_cast<uint8_t *>(s_obs + 4 * (size_t)n_circ);
     for (int t = threadIdx.x; t < n_circ; t += blockDim.x) {
         double x = obstacles[3 * t], y = obstacles[3 * t + 1], r = obstacles[3 * t + 2];
-        s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r * r;
+        s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r < 0.0 ? -1.0 : r * r;   // (a negative radius touches nothing: dist > r always, arm02:72)
     }
     const int tiles_per_row = (p.M + ARM_THREADS - 1) / ARM_THREADS;
     const long long tiles = (long long)p.n_rows * tiles_per_row;
@@ -218,7 +218,7 @@ arm_grid_rows_kernel(ArmParams p, const double *__restrict__ theta, const double
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int t = threadIdx.x; t < n_circ; t += blockDim.x) {
         double x = obstacles[3 * t], y = obstacles[3 * t + 1], r = obstacles[3 * t + 2];
-        s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r * r;
+        s_obs[4 * t] = x; s_obs[4 * t + 1] = y; s_obs[4 * t + 2] = r; s_obs[4 * t + 3] = r < 0.0 ? -1.0 : r * r;   // (a negative radius touches nothing: dist > r always, arm02:72)
     }
     for (int t = threadIdx.x; t < G * W; t += blockDim.x) s_bm[t] = 0u;
     if (threadIdx.x < ARM_MAX_LINKS) s_link[threadIdx.x] = p.link[threadIdx.x];

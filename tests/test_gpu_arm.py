@@ -168,3 +168,17 @@ def test_arm_grid_argument_checks_and_empty_inputs():
         assert bool((grid == 0).all())
     one = A.occupancy_grids_device([0.5, 0.5], np.array([[[0.0, 0.0, 0.1]]]), 1)
     assert one.shape == (1, 1, 1) and int(one.item()) == 1  # the base sits inside the circle
+
+
+def test_negative_radius_touches_nothing(oracle_lib):
+    """detect_collision returns False whenever dist > radius (arm02:72): a circle of negative radius never collides, in
+    either kernel (the squared-radius filter must not see it as |r|)."""
+    from rrtk import arm as A
+    Or = oracle_lib
+    links = [0.5, 0.5, 0.3]
+    sets = np.array([[[0.3, 0.2, -0.5], [1.0, 0.4, 0.3]], [[0.1, 0.1, -0.2], [0.0, 0.0, -1.0]]])
+    for cbc in (False, True):
+        got = A.occupancy_grids_device(links, sets, 40, cell_by_cell=cbc).cpu().numpy()
+        for s in range(2):
+            assert np.array_equal(got[s], Or.arm_grid(40, links, sets[s], Or.MATH_CR)), (cbc, s)
+        assert int(got[1].sum()) == 0
